@@ -1,0 +1,75 @@
+"""TEST INFRASTRUCTURE -- the seeded input cases shared by oracle/gen_golden.py (which runs the live reference on them) and the
+tests (which run the oracle and the CUDA path on them).  No reference imports here: this module also runs on the GPU box."""
+import numpy as np
+
+from . import synth
+
+SAMPLES = 96
+
+
+def sample_positions(numel, k=SAMPLES, seed=7):
+    """deterministic positions of the sub-sampled activations kept in the fixtures"""
+    rs = np.random.RandomState(seed + numel % 9973)
+    return np.sort(rs.randint(0, numel, k))
+
+
+NMS_CASES = {
+    # name: (make_predictions kwargs, nms kwargs)
+    "predict": (dict(batch=4, n_anchors=8400, seed=10), dict(conf_thres=0.25, iou_thres=0.7, max_det=300)),
+    "predict_iou45": (dict(batch=2, n_anchors=8400, seed=11), dict(conf_thres=0.25, iou_thres=0.45, max_det=300)),
+    "agnostic": (dict(batch=2, n_anchors=8400, seed=12), dict(conf_thres=0.25, iou_thres=0.6, agnostic=True, max_det=300)),
+    "classes": (dict(batch=2, n_anchors=8400, seed=13), dict(conf_thres=0.25, iou_thres=0.7, classes=[0, 3, 17, 79], max_det=300)),
+    "maxdet": (dict(batch=2, n_anchors=8400, seed=14, p_hot=0.5, cluster=False), dict(conf_thres=0.25, iou_thres=0.7, max_det=50)),
+    "val_multilabel": (dict(batch=2, n_anchors=2100, seed=15, p_hot=0.2), dict(conf_thres=0.001, iou_thres=0.7, multi_label=True, max_det=300)),
+    "val_truncate": (dict(batch=1, n_anchors=2100, seed=16, p_hot=0.2),
+                     dict(conf_thres=0.001, iou_thres=0.7, multi_label=True, max_det=300, max_nms=30000)),
+    "none_pass": (dict(batch=2, n_anchors=525, seed=17, p_hot=0.0), dict(conf_thres=0.25, iou_thres=0.7, max_det=300)),
+    "odd_sizes": (dict(batch=3, n_anchors=1333, seed=18, p_hot=0.3, nc=5), dict(conf_thres=0.3, iou_thres=0.5, max_det=300)),
+}
+
+
+def train_inputs(batch, seed, hw=(20, 10, 5), empty_images=(0,), no_targets=False):
+    """Raw train-mode head outputs (3 levels) + targets, from seeds. Logits are shaped so that predicted boxes are a few cells wide."""
+    rs = np.random.RandomState(seed)
+    feats = []
+    for s in hw:
+        f = rs.standard_normal((batch, 144, s, s)).astype(np.float32)
+        f[:, :64] *= np.float32(1.5)
+        f[:, 64:] = np.float32(-3.0) + np.float32(1.5) * f[:, 64:]
+        feats.append(f)
+    bi, cl, bb = synth.make_targets(batch, seed=seed + 1, max_per_img=12, empty_images=empty_images)
+    if no_targets:
+        bi, cl, bb = bi[:0], cl[:0], bb[:0]
+    return feats, bi, cl, bb
+
+
+TRAIN_CASES = {
+    "small": dict(batch=4, seed=30, hw=(20, 10, 5)),
+    "b2_640": dict(batch=2, seed=31, hw=(80, 40, 20), empty_images=()),
+    "no_targets": dict(batch=2, seed=32, hw=(20, 10, 5), no_targets=True),
+}
+
+
+
+def tal_inputs():
+    """Stand-alone TaskAlignedAssigner call with padded gts (tal.py:38-88): B=3 images with 9, 4 and 0 valid gts."""
+    import torch  # noqa: F401
+    from .model import make_anchors as mk
+    rs = np.random.RandomState(40)
+    B, N, nc, M = 3, 2100, 80, 9
+    from oracle.model import make_anchors as mk
+    anc, st = mk([(40, 40), (20, 20), (10, 10)], (8, 16, 32))
+    anc_px = (anc * st).numpy()
+    pd_scores = rs.uniform(0, 1, (B, N, nc)).astype(np.float32) ** 4
+    ctr = anc_px[None] + rs.standard_normal((B, N, 2)).astype(np.float32) * 4
+    wh = rs.uniform(10, 120, (B, N, 2)).astype(np.float32)
+    pd_bboxes = np.concatenate([ctr - wh / 2, ctr + wh / 2], -1).astype(np.float32)
+    gt_bboxes = np.zeros((B, M, 4), np.float32)
+    gt_labels = np.zeros((B, M, 1), np.float32)
+    mask_gt = np.zeros((B, M, 1), np.float32)
+    for b, n in enumerate((9, 4, 0)):
+        c = rs.uniform(60, 260, (n, 2)); s = rs.uniform(20, 150, (n, 2))
+        gt_bboxes[b, :n] = np.concatenate([c - s / 2, c + s / 2], -1)
+        gt_labels[b, :n, 0] = rs.randint(0, nc, n)
+        mask_gt[b, :n] = 1
+    return pd_scores, pd_bboxes, anc_px, gt_labels, gt_bboxes, mask_gt

@@ -1,0 +1,198 @@
+"""TEST INFRASTRUCTURE -- generates the committed golden fixtures in tests/golden/ by running the LIVE reference
+(/root/reference, imported read-only through oracle/ref_shims.py) on deterministic synthetic weights and inputs
+(oracle/synth.py).  Run in the build container only:   python -m oracle.gen_golden
+
+The reference's own tests hold no golden vectors for this path, so these fixtures -- outputs of the
+reference's own PyTorch code -- are what pins the oracle restatement (tests/test_oracle_*.py) and, through it, the CUDA
+kernels.  Fixtures are kept small (sub-sampled activations, index outputs as int32) so that they can be committed.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shims, synth  # noqa: E402
+
+ref_shims.install()
+import torch  # noqa: E402
+
+torch.set_num_threads(os.cpu_count() or 1)
+from ultralytics.nn.tasks import DetectionModel  # noqa: E402
+from ultralytics.utils import ops as ref_ops  # noqa: E402
+from ultralytics.utils.loss import v8DetectionLoss  # noqa: E402
+from ultralytics.utils.tal import TaskAlignedAssigner  # noqa: E402
+
+YAML = os.path.join(ref_shims.REFERENCE_ROOT, "z-yaml", "yolo11-701-YOLO-AD-Refine.yaml")
+from oracle.cases import NMS_CASES, TRAIN_CASES, sample_positions, tal_inputs, train_inputs  # noqa: E402
+
+
+def build_reference_model(fuse=True):
+    m = DetectionModel(YAML, ch=3, nc=80, verbose=False)
+    spec = [(k, list(v.shape), str(v.dtype)) for k, v in m.state_dict().items()]
+    os.makedirs(GOLD, exist_ok=True)
+    with open(synth.SPEC_PATH, "w") as f:
+        json.dump(spec, f)
+    sd = synth.make_state_dict(seed=1, spec=spec)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    if fuse:
+        m.fuse(verbose=False)
+    return m, spec
+
+
+def run_model(m, img):
+    outs = {}
+    hooks = []
+    for i, layer in enumerate(m.model):
+        hooks.append(layer.register_forward_hook(lambda mod, inp, out, i=i: outs.__setitem__(i, out)))
+    m.model[-1].shape = None  # anchors are cached by shape (head.py:1184)
+    with torch.inference_mode():
+        y, feats = m(torch.from_numpy(img))
+    for h in hooks:
+        h.remove()
+    return y, feats, outs
+
+
+def layer_fixture(outs):
+    d = {}
+    for i in range(33):
+        o = outs[i].detach().float().numpy().reshape(-1)
+        pos = sample_positions(o.size)
+        d[f"L{i}_shape"] = np.asarray(outs[i].shape, np.int32)
+        d[f"L{i}_samples"] = o[pos]
+        d[f"L{i}_absmean"] = np.float64(np.abs(o).mean())
+        d[f"L{i}_mean"] = np.float64(o.astype(np.float64).mean())
+    return d
+
+
+def gen_model(m):
+    # --- 160x160, batch 2: everything kept
+    img = synth.make_images(2, 160, 160, seed=2)
+    y, feats, outs = run_model(m, img)
+    d = layer_fixture(outs)
+    d["y"] = y.numpy()
+    for i, f in enumerate(feats):
+        d[f"feat{i}"] = f.numpy()
+    np.savez_compressed(os.path.join(GOLD, "model_160.npz"), **d)
+    print("model_160: y", tuple(y.shape), "max cls", float(y[:, 4:].max()))
+
+    # --- 640x640, batch 1: sub-sampled y + NMS outputs (BASELINE.json configs[0])
+    img = synth.make_images(1, 640, 640, seed=2)
+    y, feats, outs = run_model(m, img)
+    d = layer_fixture(outs)
+    d["y_sub"] = y.numpy()[:, :, ::7]
+    d["y_absmean"] = np.float64(y.abs().mean())
+    for name, kw in (("predict", dict(conf_thres=0.25, iou_thres=0.7, max_det=300)),
+                     ("val", dict(conf_thres=0.001, iou_thres=0.7, max_det=300, multi_label=True))):
+        out = ref_ops.non_max_suppression(y.clone(), max_time_img=1e9, **kw)
+        d[f"nms_{name}"] = out[0].numpy()
+        print("model_640 nms", name, tuple(out[0].shape))
+    np.savez_compressed(os.path.join(GOLD, "model_640.npz"), **d)
+
+
+def gen_nms():
+    d = {}
+    for name, (pk, nk) in NMS_CASES.items():
+        pred = synth.make_predictions(**pk)
+        out = ref_ops.non_max_suppression(torch.from_numpy(pred.copy()), max_time_img=1e9, **nk)
+        d[f"{name}_count"] = np.asarray([o.shape[0] for o in out], np.int32)
+        d[f"{name}_rows"] = np.concatenate([o.numpy() for o in out], 0) if out else np.zeros((0, 6), np.float32)
+        print("nms", name, d[f"{name}_count"])
+    # decode + NMS on raw head logits (reduced batch)
+    raw = synth.make_head_logits(4, 8400, seed=0)
+    from ultralytics.nn.modules.block import DFL
+    from ultralytics.utils.tal import dist2bbox, make_anchors
+    x = torch.from_numpy(raw)
+    feats = [torch.zeros(1, 1, 80, 80), torch.zeros(1, 1, 40, 40), torch.zeros(1, 1, 20, 20)]
+    anchors, strides = (t.transpose(0, 1) for t in make_anchors(feats, torch.tensor([8.0, 16.0, 32.0]), 0.5))
+    dfl = DFL(16)
+    box, cls = x.split((64, 80), 1)
+    dbox = dist2bbox(dfl(box), anchors.unsqueeze(0), xywh=True, dim=1) * strides
+    y = torch.cat((dbox, cls.sigmoid()), 1)
+    d["decode_y_sub"] = y.numpy()[:, :, ::11]
+    out = ref_ops.non_max_suppression(y.clone(), conf_thres=0.25, iou_thres=0.7, max_det=300, max_time_img=1e9)
+    d["decode_count"] = np.asarray([o.shape[0] for o in out], np.int32)
+    d["decode_rows"] = np.concatenate([o.numpy() for o in out], 0)
+    print("decode+nms", d["decode_count"])
+    np.savez_compressed(os.path.join(GOLD, "nms_cases.npz"), **d)
+
+
+class _Args:
+    box, cls, dfl = 7.5, 0.5, 1.5
+
+
+def gen_train(m):
+    m.args = _Args()
+    crit = v8DetectionLoss(m)
+    d = {}
+    for name, kw in TRAIN_CASES.items():
+        feats_np, bi, cl, bb = train_inputs(**kw)
+        feats = [torch.from_numpy(f).requires_grad_(True) for f in feats_np]
+        batch = dict(batch_idx=torch.from_numpy(bi), cls=torch.from_numpy(cl), bboxes=torch.from_numpy(bb))
+        captured = {}
+        orig = crit.assigner.forward
+
+        def spy(*a, **k):
+            out = orig(*a, **k)
+            captured["in"] = [t.detach().clone() for t in a]
+            captured["out"] = [t.detach().clone() for t in out]
+            return out
+
+        crit.assigner.forward = spy
+        loss, items = crit(feats, batch)
+        crit.assigner.forward = orig
+        loss.backward()
+        tl, tb, ts, fg, tgi = captured["out"]
+        d[f"{name}_loss"] = np.float64(loss.item())
+        d[f"{name}_items"] = items.numpy().astype(np.float64)
+        d[f"{name}_target_labels"] = tl.numpy().astype(np.int32)
+        d[f"{name}_fg_mask"] = fg.numpy().astype(np.uint8)
+        d[f"{name}_target_gt_idx"] = tgi.numpy().astype(np.int32)
+        fgm = fg.numpy().astype(bool)
+        d[f"{name}_target_bboxes_fg"] = tb.numpy()[fgm]
+        d[f"{name}_target_scores_fgmax"] = ts.numpy().max(-1)[fgm]
+        d[f"{name}_target_scores_sum"] = np.float64(ts.sum().item())
+        for i, f in enumerate(feats):
+            g = f.grad.numpy().reshape(-1)
+            pos = sample_positions(g.size, 256)
+            d[f"{name}_grad{i}_samples"] = g[pos]
+            d[f"{name}_grad{i}_abssum"] = np.float64(np.abs(g).sum())
+        print("train", name, "loss", loss.item(), items.numpy(), "fg", int(fgm.sum()))
+    np.savez_compressed(os.path.join(GOLD, "train_cases.npz"), **d)
+
+    # stand-alone TaskAlignedAssigner call with padded gts (tal.py:38-88)
+    pd_scores, pd_bboxes, anc_px, gt_labels, gt_bboxes, mask_gt = tal_inputs()
+    nc = pd_scores.shape[-1]
+    tal = TaskAlignedAssigner(topk=10, num_classes=nc, alpha=0.5, beta=6.0)
+    out = tal(torch.from_numpy(pd_scores), torch.from_numpy(pd_bboxes), torch.from_numpy(anc_px), torch.from_numpy(gt_labels),
+              torch.from_numpy(gt_bboxes), torch.from_numpy(mask_gt))
+    tl, tb, ts, fg, tgi = out
+    fgm = fg.numpy().astype(bool)
+    np.savez_compressed(os.path.join(GOLD, "tal_case.npz"), target_labels=tl.numpy().astype(np.int32), fg_mask=fg.numpy().astype(np.uint8),
+                        target_gt_idx=tgi.numpy().astype(np.int32), target_bboxes_fg=tb.numpy()[fgm],
+                        target_scores_fgmax=ts.numpy().max(-1)[fgm], target_scores_sum=np.float64(ts.sum().item()))
+    print("tal fg", int(fgm.sum()))
+
+
+def main():
+    m, spec = build_reference_model()
+    sd = synth.make_state_dict_np(seed=1, spec=spec)
+    with open(os.path.join(GOLD, "state_checksum.json"), "w") as f:
+        json.dump({"seed": 1, "checksum": synth.state_checksum(sd), "n_keys": len(spec)}, f)
+    which = sys.argv[1:] or ["model", "nms", "train"]
+    if "model" in which:
+        gen_model(m)
+    if "nms" in which:
+        gen_nms()
+    if "train" in which:
+        gen_train(m)
+
+
+if __name__ == "__main__":
+    main()

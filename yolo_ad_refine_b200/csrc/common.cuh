@@ -1,0 +1,168 @@
+// Shared device helpers for libyad.so (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/yad.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ---- host side error plumbing -------------------------------------------------------------------
+void yad_set_error(const char* fmt, ...);
+#define YAD_CHECK(cond, ...)          \
+  do {                                \
+    if (!(cond)) {                    \
+      yad_set_error(__VA_ARGS__);     \
+      return 1;                       \
+    }                                 \
+  } while (0)
+#define YAD_LAUNCH_CHECK(name)                                              \
+  do {                                                                      \
+    cudaError_t _e = cudaGetLastError();                                    \
+    if (_e != cudaSuccess) {                                                \
+      yad_set_error("%s: launch failed: %s", name, cudaGetErrorString(_e)); \
+      return 2;                                                             \
+    }                                                                       \
+  } while (0)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- vector access: 8 consecutive channels ------------------------------------------------------
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float (&v)[4]) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
+  uint2 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+  h[0] = __floats2bfloat162_rn(v[0], v[1]);
+  h[1] = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ float ld1(const float* p) { return *p; }
+__device__ __forceinline__ float ld1(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// ---- activations (match torch fp32 semantics) ----------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case YAD_ACT_SILU: return x * sigmoidf_(x);
+    case YAD_ACT_RELU: return fmaxf(x, 0.0f);
+    case YAD_ACT_SIGMOID: return sigmoidf_(x);
+    case YAD_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    case YAD_ACT_HARDSWISH: return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f);
+    default: return x;
+  }
+}
+
+// ---- reductions ------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; `red` is >= 32 floats of shared memory; result broadcast to all threads
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : 0.0f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}
+
+// ---- fused conv epilogue on 4 consecutive output channels ------------------------------------------
+template <typename T>
+__device__ __forceinline__ void epilogue4(float (&acc)[4], const yad_epilogue& e, int img, int64_t pix, int co) {
+  float s = 1.0f;
+  if (e.img_scale) s = e.img_scale[img];
+  if (e.pix_scale) s *= ld1(reinterpret_cast<const T*>(e.pix_scale) + pix * e.pix_scale_ld);
+  float b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (e.bias) {
+    float4 bb = *reinterpret_cast<const float4*>(e.bias + co);
+    b[0] = bb.x; b[1] = bb.y; b[2] = bb.z; b[3] = bb.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) acc[i] = apply_act(acc[i] * s + b[i], e.act) * e.alpha;
+  if (e.mul) {
+    float m[4];
+    load4(reinterpret_cast<const T*>(e.mul) + pix * e.mul_ld + co, m);
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc[i] *= m[i];
+  }
+  if (e.add) {
+    float a[4];
+    load4(reinterpret_cast<const T*>(e.add) + pix * e.add_ld + co, a);
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc[i] += a[i];
+  }
+}
+
+#define YAD_DISPATCH_DTYPE(dtype, ...)                    \
+  if ((dtype) == YAD_F32) {                               \
+    typedef float T;                                      \
+    __VA_ARGS__                                           \
+  } else if ((dtype) == YAD_BF16) {                       \
+    typedef bf16 T;                                       \
+    __VA_ARGS__                                           \
+  } else {                                                \
+    yad_set_error("unsupported dtype %d", (int)(dtype));  \
+    return 1;                                             \
+  }
