@@ -49,9 +49,9 @@ typedef struct {
 
 typedef struct {
   int32_t mode;        /* YAD_CONV_* */
-  int32_t k;           /* 1 or 3 (square) */
-  int32_t stride;      /* 1 or 2.  TRANSPOSED: k=3, stride=2, pad=1, output_padding=1 */
-  int32_t pad;
+  int32_t kh, kw;      /* kernel size: 1x1, 3x3, or 7x1 (ELA_HSFPN's Conv1d over a (n, L, 1, c) view) */
+  int32_t stride;      /* 1 or 2.  TRANSPOSED: 3x3, stride=2, pad=1, output_padding=1 */
+  int32_t pad_h, pad_w;
   const void* offmask; /* DEFORM: NHWC view (activation dtype) with >= 27 channels: 18 offsets (dy,dx per tap) + 9 mask logits */
   int32_t offmask_ld;
   int32_t impl;        /* 0 = auto, 1 = SIMT fp32-accumulate kernel, 2 = tcgen05/TMEM kernel (bf16 only) */
@@ -65,7 +65,7 @@ int yad_device_is_sm100(void);
 /* -- a1/a7/a8: dense convolution as implicit GEMM, fused epilogue.  Replaces Conv.forward_fuse (nn/modules/conv.py:52-54),
  *    nn.Conv2d / nn.ConvTranspose2d of the neck (z-yaml L12,13,15,20,22), Linear layers of layer 10, the per-image dynamic 1x1
  *    of TaskDecomposition (nn/modules/head.py:651-669) and mmcv ModulatedDeformConv2d (head.py:772-779).
- *    w: [cout][k*k][cin] in the activation dtype (taps row-major), cin = x->c, cout = y->c. */
+ *    w: [cout][kh*kw][cin] in the activation dtype (taps row-major), cin = x->c, cout = y->c. */
 int yad_conv2d(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y,
                int dtype, void* stream);
 
@@ -87,29 +87,22 @@ int yad_gn_apply(const yad_tensor* x, const double* stats, int groups, const flo
 int yad_sppf_pool(const yad_tensor* x, const yad_tensor* y1, const yad_tensor* y2, const yad_tensor* y3, int dtype, void* stream);
 /* global average pool -> out fp32 [n][c] */
 int yad_gap(const yad_tensor* x, float* out, int dtype, void* stream);
-/* row / column means -> rowmean fp32 [n][h][c], colmean fp32 [n][w][c]  (ELA_HSFPN block.py:1421-1422, CoordAtt head.py:691-692) */
-int yad_rowcol_mean(const yad_tensor* x, float* rowmean, float* colmean, int dtype, void* stream);
-/* out = x * gh[n][y][ch] * gw[n][x][ch] (x may be NULL: pure outer product, ELA flag=False) */
-int yad_rowcol_gate(const yad_tensor* x, const float* gh, const float* gw, const yad_tensor* y, int dtype, void* stream);
+/* row / column means -> views rowmean (n, h, 1, c), colmean (n, w, 1, c) in the activation dtype
+ * (ELA_HSFPN block.py:1421-1422, CoordAtt head.py:691-692).  The 1-D conv / GroupNorm / 1x1 convs that follow in the reference run
+ * through yad_conv2d (kh=7,kw=1 or 1x1) + yad_gn_* on these (n, L, 1, c) views. */
+int yad_rowcol_mean(const yad_tensor* x, const yad_tensor* rowmean, const yad_tensor* colmean, int dtype, void* stream);
+/* y = x * gh[n][y][ch] * gw[n][x][ch]  (x may be NULL: pure outer product, ELA flag=False); gh (n,h,1,c), gw (n,w,1,c) views */
+int yad_rowcol_gate(const yad_tensor* x, const yad_tensor* gh, const yad_tensor* gw, const yad_tensor* y, int dtype, void* stream);
 /* adaptive_avg_pool to (h/s, w/s) followed by bilinear upsample back, align_corners=False (block.py:2451-2457) */
 int yad_pool_upsample(const yad_tensor* x, int s, const yad_tensor* y, int dtype, void* stream);
 
-/* -- MLCA (block.py:1540-1584). local: fp32 [n][25][c] workspace, att: fp32 [n][25][c].
- *    yad_mlca_apply: y = x*att_unpooled (+ add) */
-int yad_mlca_pool(const yad_tensor* x, float* local, int dtype, void* stream);
+/* -- MLCA (block.py:1540-1584). local: fp32 [n][ls*ls][c] workspace, att: fp32 [n][ls*ls][c] (ls = local_size = 5).
+ *    yad_mlca_apply: y = x * adaptive_avg_pool(att -> (h,w)) (+ add) */
+int yad_mlca_pool(const yad_tensor* x, float* local, int local_size, int dtype, void* stream);
 int yad_mlca_att(const float* local, const float* w_global, const float* w_local, int ksize, float local_weight, int n, int c,
-                 float* att, void* stream);
-int yad_mlca_apply(const yad_tensor* x, const float* att, const void* add, int add_ld, const yad_tensor* y, int dtype, void* stream);
-
-/* -- ELA_HSFPN gate (block.py:1411-1423): v fp32 [n][L][c] (row or column means) -> sigmoid(GN16(conv1d_k7(v)+b)) fp32 [n][L][c].
- *    w: fp32 [cout][7][cin]. */
-int yad_ela_gate(const float* v, const float* w, const float* bias, const float* gamma, const float* beta, int n, int L, int c,
-                 int groups, float eps, float* out, void* stream);
-
-/* -- CoordAtt gates (head.py:687-705): pooled fp32 [n][L][c] -> sigmoid(conv_x(hardswish(bn(conv1(pooled))))) fp32 [n][L][c]
- *    w1 [mip][c], b1/bn_scale/bn_shift [mip], w2 [c][mip], b2 [c]. */
-int yad_coordatt_gate(const float* pooled, const float* w1, const float* b1, const float* bn_scale, const float* bn_shift,
-                      const float* w2, const float* b2, int n, int L, int c, int mip, float* out, void* stream);
+                 int local_size, float* att, void* stream);
+int yad_mlca_apply(const yad_tensor* x, const float* att, int local_size, const void* add, int add_ld, const yad_tensor* y, int dtype,
+                   void* stream);
 
 /* -- tiny per-image MLPs on a GAP vector g fp32 [n][c]:
  *    kind 0: sigmoid(w2 . relu(w1 g + b1) + b2)        -> out [n]      (TaskDecomposition la_conv1/2, head.py:655-656)
@@ -125,9 +118,10 @@ int yad_adt_apply(const yad_tensor* x, const float* imp, const float* alphas, co
 int yad_eltwise(int op, const yad_tensor* a, const void* b, int b_ld, const void* c3, int c3_ld, const void* d4, int d4_ld,
                 float alpha, float beta, float gamma, const yad_tensor* y, int dtype, void* stream);
 
-/* -- CrossScaleAttentionTSSA token statistics (block.py:2459-2474) for one scale: qkv view (n, 1, T, 3c) -> out view (n,1,T,c)
+/* -- CrossScaleAttentionTSSA token statistics (block.py:2459-2474) for one scale: qkv view (n, h, w, 3c) with T = h*w tokens ->
+ *    tokens [out_token_offset, out_token_offset + T) of the out view (n, T_out, 1, c)  (torch.stack over scales, block.py:2476-2477).
  *    temps: fp32 [heads]. */
-int yad_tssa(const yad_tensor* qkv, const float* temps, int heads, const yad_tensor* out, int dtype, void* stream);
+int yad_tssa(const yad_tensor* qkv, const float* temps, int heads, const yad_tensor* out, int out_token_offset, int dtype, void* stream);
 /* -- multi-head self attention core (nn.MultiheadAttention, block.py:2432-2434,2479-2486): qkv view (n,1,T,3c) -> out (n,1,T,c) */
 int yad_mha(const yad_tensor* qkv, int heads, const yad_tensor* out, int dtype, void* stream);
 /* -- mean over `s` token groups: x (n,1,s*T,c) -> y (n,1,T,c) */
@@ -150,38 +144,43 @@ int yad_decode(const void* const* lvl_ptr_host, const int64_t* lvl_sb_host, cons
                int reg_max, const float* proj, float* y, int dtype, void* stream);
 
 /* -- a10: batched NMS, replaces utils/ops.py:163-312 non_max_suppression (+ torchvision.ops.nms at :292).
- *    pred: fp32 (B, 4+nc, N) xywh + scores (NOT modified).  classes_mask: uint8[nc] or NULL.
- *    Outputs: out fp32 [B][max_det][6] (x1,y1,x2,y2,conf,cls), out_idx int32 [B][max_det][2] (anchor, class), out_count int32 [B].
- *    workspace: yad_nms_workspace_bytes(B, N, nc) bytes.  status int32[B]: 0 ok, 1 = candidate capacity exceeded. */
-int64_t yad_nms_workspace_bytes(int batch, int n_anchors, int nc);
+ *    pred: fp32 (B, 4+nc, N) xywh + scores (NOT modified).  classes_mask: uint8[nc] (1 = keep class) or NULL.
+ *    Outputs: out fp32 [B][max_det][6] (x1,y1,x2,y2,conf,cls), out_idx int32 [B][max_det][2] (anchor, class), out_count int32 [B];
+ *    rows >= out_count[b] are not written.  workspace: yad_nms_workspace_bytes(...) bytes.  The wall-clock early exit of the
+ *    reference (ops.py:234,308-310) is not reproduced. */
+int64_t yad_nms_workspace_bytes(int batch, int n_anchors, int nc, int multi_label, int max_nms);
 int yad_nms(const float* pred, int batch, int nc, int n_anchors, float conf_thres, float iou_thres, const uint8_t* classes_mask,
             int agnostic, int multi_label, int max_det, int max_nms, float max_wh, float* out, int32_t* out_idx, int32_t* out_count,
-            int32_t* status, void* workspace, void* stream);
+            void* workspace, void* stream);
 
-/* -- a12: TaskAlignedAssigner.forward (utils/tal.py:38-88), one CTA per image.
+/* -- a12: TaskAlignedAssigner.forward (utils/tal.py:38-88): one CTA per (image, gt) for the top-k, one CTA per image for the rest.
  *    pd_scores fp32 (B,N,nc) sigmoid scores, pd_bboxes fp32 (B,N,4) xyxy px, anc fp32 (N,2) px, gt_labels fp32 (B,M), gt_bboxes
  *    fp32 (B,M,4), mask_gt fp32 (B,M).  Outputs: target_labels int64 (B,N), target_bboxes fp32 (B,N,4), target_scores fp32 (B,N,nc),
- *    fg_mask uint8 (B,N), target_gt_idx int64 (B,N).  workspace: yad_tal_workspace_bytes(B,N,M). */
+ *    fg_mask uint8 (B,N), target_gt_idx int64 (B,N).  sums: double[8] (may be NULL), [4] += n_fg, [5] += sum(target_scores);
+ *    the caller zeroes it.  Top-k ties (equal align metric, in practice only metric 0) go to the lower anchor index; torch.topk
+ *    leaves them unspecified.  workspace: yad_tal_workspace_bytes(B,N,M). */
 int64_t yad_tal_workspace_bytes(int batch, int n_anchors, int n_max_boxes);
 int yad_tal_assign(const float* pd_scores, const float* pd_bboxes, const float* anc, const float* gt_labels, const float* gt_bboxes,
                    const float* mask_gt, int batch, int n_anchors, int nc, int n_max_boxes, int topk, float alpha, float beta, float eps,
                    int64_t* target_labels, float* target_bboxes, float* target_scores, uint8_t* fg_mask, int64_t* target_gt_idx,
-                   void* workspace, void* stream);
+                   double* sums, void* workspace, void* stream);
 
-/* -- a11/a13/a14: v8DetectionLoss pieces (utils/loss.py:410-417, 264-311, 18-42, 426-520).
- *    yad_loss_decode: pred_distri fp32 (B,N,4*reg_max) -> pred_bboxes (B,N,4) xyxy grid units and *stride (px) copies;
- *                     pred_scores logits (B,N,nc) -> sigmoid.
- *    yad_loss_bbox : over foreground anchors: CIoU + NWD + DFL terms, accumulates sums[0..3] = {sum (1-ciou) w, sum (1-nwd) w,
- *                     sum dfl w, sum ciou, n_fg} (double[5]) and writes d(loss)/d(pred_distri) into grad_distri given the final
- *                     scale factors (two-phase: call with grad_distri=NULL first to get sums; then with scales).
- *    yad_loss_cls  : SlideLoss-BCE sum over (B,N,nc) -> sums_cls double[1]; grad_scores optional. */
+/* -- a11/a13/a14: v8DetectionLoss pieces (utils/loss.py:410-417, 264-311, 18-42, 426-520).  All scalars stay on the device in
+ *    sums double[8]: [0] sum (1-CIoU) w, [1] sum (1-NWD) w, [2] sum DFL w, [3] sum CIoU, [4] n_fg, [5] sum target_scores, [6] sum
+ *    SlideLoss-BCE.  Call order: zero sums -> yad_loss_decode -> yad_tal_assign -> yad_loss_bbox -> yad_loss_cls -> yad_loss_finalize.
+ *    yad_loss_decode: pred_distri fp32 (B,N,4*reg_max) -> pred_bboxes (B,N,4) xyxy in grid units and a *stride (px) copy;
+ *                     pred_logits (B,N,nc) -> sigmoid (pred_scores_sig may be NULL).
+ *    yad_loss_bbox : over foreground anchors; grad_distri (may be NULL) receives d(loss.sum()*B)/d(pred_distri).
+ *    yad_loss_cls  : SlideLoss-BCE with auto_iou = sums[3]/sums[4]; grad_logits (may be NULL) receives d(loss.sum()*B)/d(pred_logits).
+ *    yad_loss_finalize: out4 = {box*gain, cls*gain, dfl*gain, (sum of the three) * B}. */
 int yad_loss_decode(const float* pred_distri, const float* pred_logits, const float* anc, const float* stride_t, int batch,
                     int n_anchors, int nc, int reg_max, float* pred_bboxes, float* pred_bboxes_px, float* pred_scores_sig, void* stream);
 int yad_loss_bbox(const float* pred_distri, const float* pred_bboxes, const float* anc, const float* stride_t,
                   const float* target_bboxes_px, const float* target_scores, const uint8_t* fg_mask, int batch, int n_anchors, int nc,
-                  int reg_max, double* sums, float box_scale, float dfl_scale, float* grad_distri, void* stream);
-int yad_loss_cls(const float* pred_logits, const float* target_scores, int64_t count, float auto_iou, double* sum_out,
-                 float grad_scale, float* grad_logits, void* stream);
+                  int reg_max, double* sums, float box_gain, float dfl_gain, float* grad_distri, void* stream);
+int yad_loss_cls(const float* pred_logits, const float* target_scores, int batch, int n_anchors, int nc, double* sums, float cls_gain,
+                 float* grad_logits, void* stream);
+int yad_loss_finalize(const double* sums, float box_gain, float cls_gain, float dfl_gain, int batch, float* out4, void* stream);
 
 /* -- tcgen05 self-test: C[M][N] (fp32) = A[M][K] (bf16, row-major) x B[N][K]^T (bf16) through the UMMA/TMEM path.  Used by the GPU
  *    tests to validate descriptor encodings independently of the convolution loader. */

@@ -1,0 +1,45 @@
+// libyad.so: error plumbing, version / device queries and the conv dispatcher.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void yad_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int yad_conv2d_simt(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, int dtype,
+                    void* stream);
+int yad_conv2d_tc(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream);
+int yad_conv2d_tc_supported(const yad_tensor* x, const yad_conv_desc* d, const yad_tensor* y);
+
+extern "C" {
+
+const char* yad_last_error(void) { return g_err; }
+int yad_version(void) { return 100; }
+
+int yad_device_is_sm100(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+int yad_conv2d(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, int dtype,
+               void* stream) {
+  YAD_CHECK(x && w && d && e && y && x->ptr && y->ptr, "conv2d: null argument");
+  int impl = d->impl;
+  if (impl == 0) impl = (dtype == YAD_BF16 && yad_conv2d_tc_supported(x, d, y)) ? 2 : 1;
+  if (impl == 2) {
+    YAD_CHECK(dtype == YAD_BF16, "conv2d: the tcgen05 path is bf16 only");
+    YAD_CHECK(yad_conv2d_tc_supported(x, d, y), "conv2d: shape not supported by the tcgen05 path");
+    return yad_conv2d_tc(x, w, d, e, y, stream);
+  }
+  return yad_conv2d_simt(x, w, d, e, y, dtype, stream);
+}
+
+}  // extern "C"

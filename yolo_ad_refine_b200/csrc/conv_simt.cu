@@ -9,7 +9,7 @@ constexpr int BM = 64, BN = 64, BK = 32, NTHREADS = 256;
 
 struct ConvGeom {
   int n, hi, wi, cin, ho, wo, cout;
-  int k, stride, pad, mode;
+  int kh, kw, stride, pad_h, pad_w, mode;
   int x_ld, y_ld, om_ld;
 };
 
@@ -17,15 +17,15 @@ struct ConvGeom {
 template <typename T>
 __device__ __forceinline__ void gather8(const T* __restrict__ x, const T* __restrict__ om, const ConvGeom& g, int img, int oy, int ox,
                                         int tap, int ci, float (&v)[8]) {
-  const int ky = tap / g.k, kx = tap - ky * g.k;
+  const int ky = tap / g.kw, kx = tap - ky * g.kw;
 #pragma unroll
   for (int i = 0; i < 8; i++) v[i] = 0.f;
   if (g.mode == YAD_CONV_NORMAL) {
-    int iy = oy * g.stride - g.pad + ky, ix = ox * g.stride - g.pad + kx;
+    int iy = oy * g.stride - g.pad_h + ky, ix = ox * g.stride - g.pad_w + kx;
     if (iy >= 0 && iy < g.hi && ix >= 0 && ix < g.wi) load8(x + ((int64_t)(img * g.hi + iy) * g.wi + ix) * g.x_ld + ci, v);
   } else if (g.mode == YAD_CONV_TRANSPOSED) {
     // y[oy] += x[iy] * w[ky] with oy = iy*stride - pad + ky
-    int ty = oy + g.pad - ky, tx = ox + g.pad - kx;
+    int ty = oy + g.pad_h - ky, tx = ox + g.pad_w - kx;
     if (ty >= 0 && tx >= 0 && (ty % g.stride) == 0 && (tx % g.stride) == 0) {
       int iy = ty / g.stride, ix = tx / g.stride;
       if (iy < g.hi && ix < g.wi) load8(x + ((int64_t)(img * g.hi + iy) * g.wi + ix) * g.x_ld + ci, v);
@@ -34,7 +34,7 @@ __device__ __forceinline__ void gather8(const T* __restrict__ x, const T* __rest
     const T* o = om + ((int64_t)(img * g.ho + oy) * g.wo + ox) * g.om_ld;
     float dy = ld1(o + 2 * tap), dx = ld1(o + 2 * tap + 1);
     float mk = sigmoidf_(ld1(o + 18 + tap));
-    float py = (float)(oy - g.pad + ky) + dy, px = (float)(ox - g.pad + kx) + dx;
+    float py = (float)(oy - g.pad_h + ky) + dy, px = (float)(ox - g.pad_w + kx) + dx;
     if (py > -1.f && px > -1.f && py < (float)g.hi && px < (float)g.wi) {
       float fy = floorf(py), fx = floorf(px);
       int y0 = (int)fy, x0 = (int)fx;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_simt_kernel(const T* __restrict
   __shared__ float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
   const int64_t M = (int64_t)g.n * g.ho * g.wo;
-  const int K = g.k * g.k * g.cin;
+  const int K = g.kh * g.kw * g.cin;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
 
@@ -138,18 +138,20 @@ int yad_conv2d_simt(const yad_tensor* x, const void* w, const yad_conv_desc* d, 
   ConvGeom g;
   g.n = x->n; g.hi = x->h; g.wi = x->w; g.cin = x->c;
   g.ho = y->h; g.wo = y->w; g.cout = y->c;
-  g.k = d->k; g.stride = d->stride; g.pad = d->pad; g.mode = d->mode;
+  g.kh = d->kh; g.kw = d->kw; g.stride = d->stride; g.pad_h = d->pad_h; g.pad_w = d->pad_w; g.mode = d->mode;
   g.x_ld = x->ld; g.y_ld = y->ld; g.om_ld = d->offmask_ld;
   YAD_CHECK(x->n == y->n, "conv2d: batch mismatch %d vs %d", x->n, y->n);
   YAD_CHECK(g.cin % 8 == 0 && g.cout % 4 == 0, "conv2d: cin (%d) must be a multiple of 8 and cout (%d) of 4", g.cin, g.cout);
   YAD_CHECK(g.x_ld % 8 == 0 && g.y_ld % 4 == 0, "conv2d: ld must be aligned (x %d, y %d)", g.x_ld, g.y_ld);
   if (d->mode == YAD_CONV_NORMAL) {
-    YAD_CHECK(g.ho == (g.hi + 2 * g.pad - g.k) / g.stride + 1 && g.wo == (g.wi + 2 * g.pad - g.k) / g.stride + 1,
-              "conv2d: output shape %dx%d does not match input %dx%d k%d s%d p%d", g.ho, g.wo, g.hi, g.wi, g.k, g.stride, g.pad);
+    YAD_CHECK(g.ho == (g.hi + 2 * g.pad_h - g.kh) / g.stride + 1 && g.wo == (g.wi + 2 * g.pad_w - g.kw) / g.stride + 1,
+              "conv2d: output shape %dx%d does not match input %dx%d k%dx%d s%d p%d,%d", g.ho, g.wo, g.hi, g.wi, g.kh, g.kw, g.stride, g.pad_h,
+              g.pad_w);
   } else if (d->mode == YAD_CONV_TRANSPOSED) {
-    YAD_CHECK(g.k == 3 && g.stride == 2 && g.pad == 1 && g.ho == 2 * g.hi && g.wo == 2 * g.wi, "conv2d: transposed mode is k3 s2 p1 op1 only");
+    YAD_CHECK(g.kh == 3 && g.kw == 3 && g.stride == 2 && g.pad_h == 1 && g.pad_w == 1 && g.ho == 2 * g.hi && g.wo == 2 * g.wi,
+              "conv2d: transposed mode is k3 s2 p1 op1 only");
   } else if (d->mode == YAD_CONV_DEFORM) {
-    YAD_CHECK(g.k == 3 && g.stride == 1 && g.pad == 1 && g.ho == g.hi && g.wo == g.wi && d->offmask != nullptr,
+    YAD_CHECK(g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad_h == 1 && g.pad_w == 1 && g.ho == g.hi && g.wo == g.wi && d->offmask != nullptr,
               "conv2d: deformable mode is 3x3 s1 p1 with an offset/mask view");
   } else {
     YAD_CHECK(false, "conv2d: bad mode %d", d->mode);

@@ -1,0 +1,837 @@
+// Memory-bound refinement-block kernels (NHWC, 128-bit vector access on 8 consecutive channels, smem staging and
+// warp-shuffle reductions where a reduction is involved).  Each entry point cites the reference operator it replaces.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ int64_t pix_off(const yad_tensor& t, int n, int y, int x) { return ((int64_t)(n * t.h + y) * t.w + x) * t.ld; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// NCHW fp32 image -> NHWC (zero-filled tail channels)
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int c_src, yad_tensor y) {
+  int64_t hw = (int64_t)y.h * y.w, total = (int64_t)y.n * hw;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = p / hw, r = p - n * hw;
+    T* o = reinterpret_cast<T*>(y.ptr) + p * y.ld;
+    for (int c0 = 0; c0 < y.c; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = (c0 + i < c_src) ? src[(n * c_src + c0 + i) * hw + r] : 0.f;
+      store8(o + c0, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// GroupNorm statistics + apply
+// ------------------------------------------------------------------------------------------------------------------
+// grid (chunks, n).  stats[n][g][2] += (sum, sumsq) in double.
+template <typename T>
+__global__ void gn_stats_kernel(yad_tensor x, int groups, double* __restrict__ stats) {
+  extern __shared__ float sm[];  // [2][c]
+  const int c = x.c, n = blockIdx.y, oct = c >> 3;
+  float* ssum = sm;
+  float* ssq = sm + c;
+  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int64_t hw = (int64_t)x.h * x.w;
+  const int64_t per = (hw + gridDim.x - 1) / gridDim.x;
+  const int64_t p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
+  const T* base = reinterpret_cast<const T*>(x.ptr) + (int64_t)n * hw * x.ld;
+  // thread -> fixed octet, strided pixels (blockDim is a multiple of oct when oct | blockDim; otherwise generic loop)
+  const int64_t items = (p1 - p0) * oct;
+  if (blockDim.x % oct == 0) {
+    const int o = threadIdx.x % oct, lane = threadIdx.x / oct, step = blockDim.x / oct;
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { s[i] = 0.f; q[i] = 0.f; }
+    for (int64_t p = p0 + lane; p < p1; p += step) {
+      float v[8];
+      load8(base + p * x.ld + o * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; i++) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) { atomicAdd(&ssum[o * 8 + i], s[i]); atomicAdd(&ssq[o * 8 + i], q[i]); }
+  } else {
+    for (int64_t it = threadIdx.x; it < items; it += blockDim.x) {
+      int64_t p = p0 + it / oct;
+      int o = (int)(it % oct);
+      float v[8];
+      load8(base + p * x.ld + o * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; i++) { atomicAdd(&ssum[o * 8 + i], v[i]); atomicAdd(&ssq[o * 8 + i], v[i] * v[i]); }
+    }
+  }
+  __syncthreads();
+  const int cpg = c / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < cpg; i++) { a += (double)ssum[g * cpg + i]; b += (double)ssq[g * cpg + i]; }
+    atomicAdd(&stats[((int64_t)n * groups + g) * 2 + 0], a);
+    atomicAdd(&stats[((int64_t)n * groups + g) * 2 + 1], b);
+  }
+}
+
+template <typename T>
+__global__ void gn_apply_kernel(yad_tensor x, const double* __restrict__ stats, int groups, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, int act, const T* __restrict__ add, int add_ld, yad_tensor y) {
+  extern __shared__ float sm[];  // scale[c], shift[c]
+  const int c = x.c, n = blockIdx.y, oct = c >> 3, cpg = c / groups;
+  const int64_t hw = (int64_t)x.h * x.w;
+  const double cnt = (double)hw * cpg;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    int g = ch / cpg;
+    double mean = stats[((int64_t)n * groups + g) * 2] / cnt;
+    double var = stats[((int64_t)n * groups + g) * 2 + 1] / cnt - mean * mean;
+    float rstd = (float)(1.0 / sqrt(fmax(var, 0.0) + (double)eps));
+    float sc = rstd * gamma[ch];
+    sm[ch] = sc;
+    sm[c + ch] = beta[ch] - (float)mean * sc;
+  }
+  __syncthreads();
+  const int64_t items = hw * oct;
+  const T* xb = reinterpret_cast<const T*>(x.ptr) + (int64_t)n * hw * x.ld;
+  T* yb = reinterpret_cast<T*>(y.ptr) + (int64_t)n * hw * y.ld;
+  const T* ab = add ? add + (int64_t)n * hw * add_ld : nullptr;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = it / oct;
+    int o = (int)(it - p * oct) * 8;
+    float v[8];
+    load8(xb + p * x.ld + o, v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = apply_act(fmaf(v[i], sm[o + i], sm[c + o + i]), act);
+    if (ab) {
+      float a[8];
+      load8(ab + p * add_ld + o, a);
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] += a[i];
+    }
+    store8(yb + p * y.ld + o, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// depthwise k x k, stride 1, pad k/2 (+bias, per-channel affine, activation, GELU gate, residual)
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void dwconv_kernel(yad_tensor x, const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ scale,
+                              const float* __restrict__ shift, int k, int act, int gate_split, const T* __restrict__ add, int add_ld,
+                              yad_tensor y) {
+  const int cw = x.c;                              // weight channel count
+  const int cout = gate_split > 0 ? gate_split : x.c;
+  const int oct = cout >> 3, r = k >> 1;
+  const int64_t total = (int64_t)x.n * x.h * x.w * oct;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+    int o = (int)(it % oct) * 8;
+    int64_t p = it / oct;
+    int px = (int)(p % x.w);
+    int py = (int)((p / x.w) % x.h);
+    int n = (int)(p / ((int64_t)x.w * x.h));
+    float acc[8], acc2[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { acc[i] = bias ? bias[o + i] : 0.f; acc2[i] = (bias && gate_split > 0) ? bias[o + gate_split + i] : 0.f; }
+    for (int ky = 0; ky < k; ky++) {
+      int iy = py + ky - r;
+      if (iy < 0 || iy >= x.h) continue;
+      for (int kx = 0; kx < k; kx++) {
+        int ix = px + kx - r;
+        if (ix < 0 || ix >= x.w) continue;
+        const T* src = reinterpret_cast<const T*>(x.ptr) + pix_off(x, n, iy, ix);
+        const float* wt = w + (int64_t)(ky * k + kx) * cw;
+        float v[8], wv[8];
+        load8(src + o, v);
+        load8(wt + o, wv);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = fmaf(v[i], wv[i], acc[i]);
+        if (gate_split > 0) {
+          load8(src + o + gate_split, v);
+          load8(wt + o + gate_split, wv);
+#pragma unroll
+          for (int i = 0; i < 8; i++) acc2[i] = fmaf(v[i], wv[i], acc2[i]);
+        }
+      }
+    }
+    if (gate_split > 0) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[i] = apply_act(acc[i], YAD_ACT_GELU) * acc2[i];
+    } else {
+      if (scale) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = fmaf(acc[i], scale[o + i], shift[o + i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[i] = apply_act(acc[i], act);
+    }
+    if (add) {
+      float a[8];
+      load8(add + p * add_ld + o, a);
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[i] += a[i];
+    }
+    store8(reinterpret_cast<T*>(y.ptr) + p * y.ld + o, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// SPPF: 5x5 / 9x9 / 13x13 max windows (= three chained 5x5 s1 p2 max-pools with -inf padding)
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void sppf_pool_kernel(yad_tensor x, yad_tensor y1, yad_tensor y2, yad_tensor y3) {
+  const int oct = x.c >> 3;
+  const int64_t total = (int64_t)x.n * x.h * x.w * oct;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+    int o = (int)(it % oct) * 8;
+    int64_t p = it / oct;
+    int px = (int)(p % x.w);
+    int py = (int)((p / x.w) % x.h);
+    int n = (int)(p / ((int64_t)x.w * x.h));
+    float m1[8], m2[8], m3[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) m1[i] = m2[i] = m3[i] = -INFINITY;
+    for (int dy = -6; dy <= 6; dy++) {
+      int iy = py + dy;
+      if (iy < 0 || iy >= x.h) continue;
+      for (int dx = -6; dx <= 6; dx++) {
+        int ix = px + dx;
+        if (ix < 0 || ix >= x.w) continue;
+        float v[8];
+        load8(reinterpret_cast<const T*>(x.ptr) + pix_off(x, n, iy, ix) + o, v);
+        int rad = max(abs(dy), abs(dx));
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          m3[i] = fmaxf(m3[i], v[i]);
+          if (rad <= 4) m2[i] = fmaxf(m2[i], v[i]);
+          if (rad <= 2) m1[i] = fmaxf(m1[i], v[i]);
+        }
+      }
+    }
+    store8(reinterpret_cast<T*>(y1.ptr) + p * y1.ld + o, m1);
+    store8(reinterpret_cast<T*>(y2.ptr) + p * y2.ld + o, m2);
+    store8(reinterpret_cast<T*>(y3.ptr) + p * y3.ld + o, m3);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// reductions over pixels: global average pool, row / column means, MLCA 5x5 adaptive pool
+// ------------------------------------------------------------------------------------------------------------------
+// Sum of 8-channel vectors over a pixel range; block = (oct lanes) x (pixel lanes).  Result for octet o, channel i lands in
+// smem acc[o*8+i] (caller zeroes it).
+template <typename T, typename F>
+__device__ __forceinline__ void block_pixel_sum(const yad_tensor& x, int64_t count, F pixel_offset, float* acc) {
+  const int oct = x.c >> 3;
+  const int64_t items = count * oct;
+  for (int64_t it = threadIdx.x; it < items; it += blockDim.x) {
+    int64_t j = it / oct;
+    int o = (int)(it - j * oct) * 8;
+    float v[8];
+    load8(reinterpret_cast<const T*>(x.ptr) + pixel_offset(j) + o, v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) atomicAdd(&acc[o + i], v[i]);
+  }
+}
+
+// grid (splits, n): out[n][c] += partial mean (out zeroed by the launcher)
+template <typename T>
+__global__ void gap_kernel(yad_tensor x, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.y, c = x.c, oct = c >> 3;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int64_t hw = (int64_t)x.h * x.w;
+  const int64_t per = (hw + gridDim.x - 1) / gridDim.x, p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
+  const T* base = reinterpret_cast<const T*>(x.ptr) + (int64_t)n * hw * x.ld;
+  if (blockDim.x % oct == 0) {
+    const int o = (threadIdx.x % oct) * 8, lane = threadIdx.x / oct, step = blockDim.x / oct;
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = 0.f;
+    for (int64_t p = p0 + lane; p < p1; p += step) {
+      float v[8];
+      load8(base + p * x.ld + o, v);
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) atomicAdd(&sm[o + i], s[i]);
+  } else if (p1 > p0) {
+    block_pixel_sum<T>(x, p1 - p0, [&](int64_t j) { return ((int64_t)n * hw + p0 + j) * x.ld; }, sm);
+  }
+  __syncthreads();
+  const float inv = 1.0f / (float)hw;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&out[(int64_t)n * c + i], sm[i] * inv);
+}
+
+// grid (L, n, 2): z=0 -> row y=blockIdx.x: mean over x ; z=1 -> column x=blockIdx.x: mean over y
+template <typename T>
+__global__ void rowcol_mean_kernel(yad_tensor x, yad_tensor rowmean, yad_tensor colmean) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.y, c = x.c;
+  const bool is_col = blockIdx.z == 1;
+  const int L = is_col ? x.w : x.h;
+  if ((int)blockIdx.x >= L) return;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int idx = blockIdx.x;
+  const int count = is_col ? x.h : x.w;
+  block_pixel_sum<T>(x, count, [&](int64_t j) { return is_col ? pix_off(x, n, (int)j, idx) : pix_off(x, n, idx, (int)j); }, sm);
+  __syncthreads();
+  const yad_tensor& o = is_col ? colmean : rowmean;  // views (n, L, 1, c)
+  T* dst = reinterpret_cast<T*>(o.ptr) + ((int64_t)n * L + idx) * o.ld;
+  const float inv = 1.0f / (float)count;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) st1(dst + i, sm[i] * inv);
+}
+
+template <typename T>
+__global__ void rowcol_gate_kernel(yad_tensor x, bool has_x, yad_tensor gh, yad_tensor gw, yad_tensor y) {
+  const int oct = y.c >> 3;
+  const int64_t total = (int64_t)y.n * y.h * y.w * oct;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+    int o = (int)(it % oct) * 8;
+    int64_t p = it / oct;
+    int px = (int)(p % y.w);
+    int py = (int)((p / y.w) % y.h);
+    int n = (int)(p / ((int64_t)y.w * y.h));
+    float a[8], b[8];
+    load8(reinterpret_cast<const T*>(gh.ptr) + ((int64_t)n * y.h + py) * gh.ld + o, a);
+    load8(reinterpret_cast<const T*>(gw.ptr) + ((int64_t)n * y.w + px) * gw.ld + o, b);
+    if (has_x) {
+      float v[8];
+      load8(reinterpret_cast<const T*>(x.ptr) + p * x.ld + o, v);
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = v[i] * a[i] * b[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = a[i] * b[i];
+    }
+    store8(reinterpret_cast<T*>(y.ptr) + p * y.ld + o, a);
+  }
+}
+
+__device__ __forceinline__ int bin_start(int i, int in, int out) { return (int)(((int64_t)i * in) / out); }
+__device__ __forceinline__ int bin_end(int i, int in, int out) { return (int)((((int64_t)(i + 1)) * in + out - 1) / out); }
+
+// grid (25, n): local[n][bin][c] = adaptive average of bin (block.py:1559 local_arv_pool)
+template <typename T>
+__global__ void mlca_pool_kernel(yad_tensor x, float* __restrict__ local, int ls) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.y, c = x.c, bin = blockIdx.x, by = bin / ls, bx = bin % ls;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int y0 = bin_start(by, x.h, ls), y1 = bin_end(by, x.h, ls), x0 = bin_start(bx, x.w, ls), x1 = bin_end(bx, x.w, ls);
+  const int bw = x1 - x0, cnt = (y1 - y0) * bw;
+  block_pixel_sum<T>(x, cnt, [&](int64_t j) { return pix_off(x, n, y0 + (int)(j / bw), x0 + (int)(j % bw)); }, sm);
+  __syncthreads();
+  const float inv = 1.0f / (float)cnt;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) local[((int64_t)n * ls * ls + bin) * c + i] = sm[i] * inv;
+}
+
+// one block per image: att[n][bin][c] = (1-lw)*sigmoid(conv1d_k(global)) + lw*sigmoid(conv1d_k(local sequence))  (block.py:1565-1581)
+__global__ void mlca_att_kernel(const float* __restrict__ local, const float* __restrict__ wg, const float* __restrict__ wl, int k, float lw,
+                                int c, int nb, float* __restrict__ att) {
+  extern __shared__ float sm[];  // seq[nb*c], glob[c], yg[c]
+  float* seq = sm;
+  float* glob = sm + nb * c;
+  float* yg = glob + c;
+  const int n = blockIdx.x, len = nb * c, r = (k - 1) / 2;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) seq[i] = local[(int64_t)n * len + i];
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < nb; b++) s += seq[b * c + ch];
+    glob[ch] = s / (float)nb;
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < k; j++) {
+      int q = ch + j - r;
+      if (q >= 0 && q < c) s = fmaf(wg[j], glob[q], s);
+    }
+    yg[ch] = sigmoidf_(s);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < k; j++) {
+      int q = i + j - r;
+      if (q >= 0 && q < len) s = fmaf(wl[j], seq[q], s);
+    }
+    att[(int64_t)n * len + i] = yg[i % c] * (1.0f - lw) + sigmoidf_(s) * lw;
+  }
+}
+
+// y = x * adaptive_avg_pool2d(att (ls x ls) -> (h, w)) (+ add)   (block.py:1581-1583)
+template <typename T>
+__global__ void mlca_apply_kernel(yad_tensor x, const float* __restrict__ att, int ls, const T* __restrict__ add, int add_ld, yad_tensor y) {
+  const int oct = x.c >> 3, c = x.c;
+  const int64_t total = (int64_t)x.n * x.h * x.w * oct;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+    int o = (int)(it % oct) * 8;
+    int64_t p = it / oct;
+    int px = (int)(p % x.w);
+    int py = (int)((p / x.w) % x.h);
+    int n = (int)(p / ((int64_t)x.w * x.h));
+    const int y0 = bin_start(py, ls, x.h), y1 = bin_end(py, ls, x.h), x0 = bin_start(px, ls, x.w), x1 = bin_end(px, ls, x.w);
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = 0.f;
+    for (int by = y0; by < y1; by++)
+      for (int bx = x0; bx < x1; bx++) {
+        float t[8];
+        load8(att + ((int64_t)n * ls * ls + by * ls + bx) * c + o, t);
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] += t[i];
+      }
+    const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
+    float v[8];
+    load8(reinterpret_cast<const T*>(x.ptr) + p * x.ld + o, v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] *= a[i] * inv;
+    if (add) {
+      float r[8];
+      load8(add + p * add_ld + o, r);
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] += r[i];
+    }
+    store8(reinterpret_cast<T*>(y.ptr) + p * y.ld + o, v);
+  }
+}
+
+// adaptive_avg_pool2d(x, (h/s, w/s)) -> bilinear upsample to (h, w), align_corners=False (block.py:2451-2457)
+template <typename T>
+__global__ void pool_upsample_kernel(yad_tensor x, int s, yad_tensor y) {
+  const int oct = x.c >> 3;
+  const int hp = x.h / s, wp = x.w / s;
+  const float sy = (float)hp / (float)x.h, sx = (float)wp / (float)x.w;
+  const int64_t total = (int64_t)x.n * x.h * x.w * oct;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+    int o = (int)(it % oct) * 8;
+    int64_t p = it / oct;
+    int px = (int)(p % x.w);
+    int py = (int)((p / x.w) % x.h);
+    int n = (int)(p / ((int64_t)x.w * x.h));
+    float fy = fmaxf(sy * ((float)py + 0.5f) - 0.5f, 0.f), fx = fmaxf(sx * ((float)px + 0.5f) - 0.5f, 0.f);
+    int iy0 = (int)fy, ix0 = (int)fx;
+    int iy1 = min(iy0 + 1, hp - 1), ix1 = min(ix0 + 1, wp - 1);
+    float ly = fy - (float)iy0, lx = fx - (float)ix0;
+    float out[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = 0.f;
+    for (int q = 0; q < 4; q++) {
+      int by = (q >> 1) ? iy1 : iy0, bx = (q & 1) ? ix1 : ix0;
+      float wgt = ((q >> 1) ? ly : 1.f - ly) * ((q & 1) ? lx : 1.f - lx);
+      if (wgt == 0.f) continue;
+      const int y0 = bin_start(by, x.h, hp), y1 = bin_end(by, x.h, hp), x0 = bin_start(bx, x.w, wp), x1 = bin_end(bx, x.w, wp);
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[i] = 0.f;
+      for (int yy = y0; yy < y1; yy++)
+        for (int xx = x0; xx < x1; xx++) {
+          float v[8];
+          load8(reinterpret_cast<const T*>(x.ptr) + pix_off(x, n, yy, xx) + o, v);
+#pragma unroll
+          for (int i = 0; i < 8; i++) acc[i] += v[i];
+        }
+      const float sc = wgt / (float)((y1 - y0) * (x1 - x0));
+#pragma unroll
+      for (int i = 0; i < 8; i++) out[i] = fmaf(acc[i], sc, out[i]);
+    }
+    store8(reinterpret_cast<T*>(y.ptr) + p * y.ld + o, out);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// tiny per-image MLPs and AdaptiveDynamicTanh
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void gate_mlp_kernel(const float* __restrict__ g, const float* __restrict__ w1, const float* __restrict__ b1,
+                                const float* __restrict__ w2, const float* __restrict__ b2, int c, int hidden, int nout, int kind,
+                                float* __restrict__ out) {
+  extern __shared__ float sm[];  // hid[hidden], o[nout]
+  float* hid = sm;
+  float* o = sm + hidden;
+  const int n = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int h = wid; h < hidden; h += nw) {
+    float s = 0.f;
+    for (int i = lane; i < c; i += 32) s = fmaf(w1[h * c + i], g[(int64_t)n * c + i], s);
+    s = warp_sum(s);
+    if (lane == 0) hid[h] = fmaxf(s + b1[h], 0.f);
+  }
+  __syncthreads();
+  for (int j = wid; j < nout; j += nw) {
+    float s = 0.f;
+    for (int i = lane; i < hidden; i += 32) s = fmaf(w2[j * hidden + i], hid[i], s);
+    s = warp_sum(s);
+    if (lane == 0) o[j] = s + b2[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (kind == 0) {
+      for (int j = 0; j < nout; j++) out[(int64_t)n * nout + j] = sigmoidf_(o[j]);
+    } else {
+      float m = -INFINITY, sum = 0.f;
+      for (int j = 0; j < nout; j++) m = fmaxf(m, o[j]);
+      for (int j = 0; j < nout; j++) sum += expf(o[j] - m);
+      for (int j = 0; j < nout; j++) out[(int64_t)n * nout + j] = expf(o[j] - m) / sum;
+    }
+  }
+}
+
+template <typename T>
+__global__ void adt_apply_kernel(yad_tensor x, const float* __restrict__ imp, const float* __restrict__ alphas, const float* __restrict__ weight,
+                                 const float* __restrict__ bias, yad_tensor y) {
+  const int oct = x.c >> 3;
+  const int64_t hw = (int64_t)x.h * x.w, total = (int64_t)x.n * hw * oct;
+  const float a0 = alphas[0], a1 = alphas[1], a2 = alphas[2];
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+    int o = (int)(it % oct) * 8;
+    int64_t p = it / oct;
+    int n = (int)(p / hw);
+    const float i0 = imp[n * 3], i1 = imp[n * 3 + 1], i2 = imp[n * 3 + 2];
+    float v[8], wv[8], bv[8];
+    load8(reinterpret_cast<const T*>(x.ptr) + p * x.ld + o, v);
+    load8(weight + o, wv);
+    load8(bias + o, bv);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      float t = tanhf(a0 * v[i]) * i0 + tanhf(a1 * v[i]) * i1 + tanhf(a2 * v[i]) * i2;
+      v[i] = fmaf(t, wv[i], bv[i]);
+    }
+    store8(reinterpret_cast<T*>(y.ptr) + p * y.ld + o, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// generic elementwise combine
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void eltwise_kernel(int op, yad_tensor a, const T* __restrict__ b, int b_ld, const T* __restrict__ c3, int c3_ld,
+                               const T* __restrict__ d4, int d4_ld, float alpha, float beta, float gamma, yad_tensor y) {
+  const int oct = a.c >> 3;
+  const int64_t total = (int64_t)a.n * a.h * a.w * oct;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+    int o = (int)(it % oct) * 8;
+    int64_t p = it / oct;
+    float va[8], vb[8];
+    load8(reinterpret_cast<const T*>(a.ptr) + p * a.ld + o, va);
+    if (op == 2) {
+      float s = ld1(b + p * b_ld);
+#pragma unroll
+      for (int i = 0; i < 8; i++) va[i] *= s;
+    } else {
+      load8(b + p * b_ld + o, vb);
+      if (op == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) va[i] *= vb[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) va[i] = alpha * va[i] + beta * vb[i];
+        if (op == 3) {
+          float vc[8], vd[8];
+          load8(c3 + p * c3_ld + o, vc);
+          load8(d4 + p * d4_ld + o, vd);
+#pragma unroll
+          for (int i = 0; i < 8; i++) va[i] += gamma * vc[i] + vd[i];
+        }
+      }
+    }
+    store8(reinterpret_cast<T*>(y.ptr) + p * y.ld + o, va);
+  }
+}
+
+// mean over s token groups: x (n,1,s*T,c) -> y (n,1,T,c)
+template <typename T>
+__global__ void group_mean_kernel(yad_tensor x, int s, yad_tensor y) {
+  const int oct = y.c >> 3, Tn = y.w * y.h;
+  const int64_t total = (int64_t)y.n * Tn * oct;
+  const float inv = 1.0f / (float)s;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+    int o = (int)(it % oct) * 8;
+    int64_t p = it / oct;
+    int64_t n = p / Tn, t = p - n * Tn;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+    for (int g = 0; g < s; g++) {
+      float v[8];
+      load8(reinterpret_cast<const T*>(x.ptr) + ((n * s + g) * Tn + t) * x.ld + o, v);
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] *= inv;
+    store8(reinterpret_cast<T*>(y.ptr) + p * y.ld + o, acc);
+  }
+}
+
+// EDFFN 8x8 patch spectral filter as a per-channel 64x64 matrix (block.py:2398-2413); grid (patches, n), block = c threads
+template <typename T>
+__global__ void patch_filter_kernel(yad_tensor x, const float* __restrict__ m, float alpha, const T* __restrict__ add, int add_ld, yad_tensor y) {
+  const int c = x.c, n = blockIdx.y;
+  const int wp = (x.w + 7) / 8;
+  const int pr = blockIdx.x / wp, pc = blockIdx.x % wp;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float in[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+      int yy = pr * 8 + (i >> 3), xx = pc * 8 + (i & 7);
+      if (yy >= x.h) yy = 2 * x.h - 2 - yy;  // F.pad(..., mode='reflect') on the bottom / right edge
+      if (xx >= x.w) xx = 2 * x.w - 2 - xx;
+      in[i] = ld1(reinterpret_cast<const T*>(x.ptr) + pix_off(x, n, yy, xx) + ch);
+    }
+    for (int o = 0; o < 64; o++) {
+      int yy = pr * 8 + (o >> 3), xx = pc * 8 + (o & 7);
+      if (yy >= x.h || xx >= x.w) continue;
+      const float* mo = m + (int64_t)o * 64 * c + ch;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; i++) s = fmaf(mo[(int64_t)i * c], in[i], s);
+      int64_t p = ((int64_t)n * x.h + yy) * x.w + xx;
+      float r = alpha * s;
+      if (add) r += ld1(add + p * add_ld + ch);
+      st1(reinterpret_cast<T*>(y.ptr) + p * y.ld + ch, r);
+    }
+  }
+}
+
+int grid_for(int64_t items, int tpb = TPB) {
+  int64_t g = (items + tpb - 1) / tpb;
+  const int64_t cap = 148 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int check_view(const yad_tensor* t, const char* what) {
+  YAD_CHECK(t && t->ptr, "%s: null tensor", what);
+  YAD_CHECK(t->c % 8 == 0 && t->ld % 8 == 0 && t->ld >= t->c, "%s: channels (%d) and ld (%d) must be multiples of 8, ld >= c", what, t->c, t->ld);
+  YAD_CHECK(((uintptr_t)t->ptr & 15) == 0, "%s: pointer must be 16-byte aligned", what);
+  return 0;
+}
+#define CHECK_VIEW(t, what) \
+  do {                      \
+    if (check_view(t, what)) return 1; \
+  } while (0)
+#define SAME_SHAPE(a, b, what) YAD_CHECK((a)->n == (b)->n && (a)->h == (b)->h && (a)->w == (b)->w, "%s: shape mismatch", what)
+
+}  // namespace
+
+extern "C" {
+
+int yad_nchw_to_nhwc(const float* src, int c_src, const yad_tensor* y, int dtype, void* stream) {
+  CHECK_VIEW(y, "nchw_to_nhwc");
+  YAD_CHECK(c_src <= y->c, "nchw_to_nhwc: c_src %d > c %d", c_src, y->c);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = (int64_t)y->n * y->h * y->w;
+  YAD_DISPATCH_DTYPE(dtype, nchw_to_nhwc_kernel<T><<<grid_for(total), TPB, 0, st>>>(src, c_src, *y);)
+  YAD_LAUNCH_CHECK("nchw_to_nhwc");
+  return 0;
+}
+
+int yad_gn_stats(const yad_tensor* x, int groups, double* stats, int dtype, void* stream) {
+  CHECK_VIEW(x, "gn_stats");
+  YAD_CHECK(groups > 0 && x->c % groups == 0, "gn_stats: %d channels not divisible into %d groups", x->c, groups);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * x->n, st);
+  int64_t hw = (int64_t)x->h * x->w;
+  int chunks = (int)((hw * (x->c / 8) + TPB * 8 - 1) / (TPB * 8));
+  chunks = chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks);
+  dim3 grid(chunks, x->n);
+  YAD_DISPATCH_DTYPE(dtype, gn_stats_kernel<T><<<grid, TPB, 2 * x->c * sizeof(float), st>>>(*x, groups, stats);)
+  YAD_LAUNCH_CHECK("gn_stats");
+  return 0;
+}
+
+int yad_gn_apply(const yad_tensor* x, const double* stats, int groups, const float* gamma, const float* beta, float eps, int act,
+                 const void* add, int add_ld, const yad_tensor* y, int dtype, void* stream) {
+  CHECK_VIEW(x, "gn_apply x");
+  CHECK_VIEW(y, "gn_apply y");
+  SAME_SHAPE(x, y, "gn_apply");
+  YAD_CHECK(x->c == y->c && x->c % groups == 0, "gn_apply: channel mismatch");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t items = (int64_t)x->h * x->w * (x->c / 8);
+  int gx = (int)((items + TPB * 4 - 1) / (TPB * 4));
+  gx = gx < 1 ? 1 : (gx > 256 ? 256 : gx);
+  dim3 grid(gx, x->n);
+  YAD_DISPATCH_DTYPE(dtype, gn_apply_kernel<T><<<grid, TPB, 2 * x->c * sizeof(float), st>>>(*x, stats, groups, gamma, beta, eps, act,
+                                                                                               (const T*)add, add_ld, *y);)
+  YAD_LAUNCH_CHECK("gn_apply");
+  return 0;
+}
+
+int yad_dwconv(const yad_tensor* x, const float* w, const float* bias, const float* scale, const float* shift, int k, int act,
+               int gate_split, const void* add, int add_ld, const yad_tensor* y, int dtype, void* stream) {
+  CHECK_VIEW(x, "dwconv x");
+  CHECK_VIEW(y, "dwconv y");
+  SAME_SHAPE(x, y, "dwconv");
+  YAD_CHECK(k == 3 || k == 5 || k == 7, "dwconv: k=%d unsupported", k);
+  YAD_CHECK(gate_split > 0 ? (x->c == 2 * gate_split && y->c == gate_split) : (x->c == y->c), "dwconv: channel mismatch");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = (int64_t)y->n * y->h * y->w * (y->c / 8);
+  YAD_DISPATCH_DTYPE(dtype, dwconv_kernel<T><<<grid_for(total, 128), 128, 0, st>>>(*x, w, bias, scale, shift, k, act, gate_split,
+                                                                                    (const T*)add, add_ld, *y);)
+  YAD_LAUNCH_CHECK("dwconv");
+  return 0;
+}
+
+int yad_sppf_pool(const yad_tensor* x, const yad_tensor* y1, const yad_tensor* y2, const yad_tensor* y3, int dtype, void* stream) {
+  CHECK_VIEW(x, "sppf x");
+  CHECK_VIEW(y1, "sppf y1");
+  CHECK_VIEW(y2, "sppf y2");
+  CHECK_VIEW(y3, "sppf y3");
+  SAME_SHAPE(x, y1, "sppf");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = (int64_t)x->n * x->h * x->w * (x->c / 8);
+  YAD_DISPATCH_DTYPE(dtype, sppf_pool_kernel<T><<<grid_for(total, 128), 128, 0, st>>>(*x, *y1, *y2, *y3);)
+  YAD_LAUNCH_CHECK("sppf_pool");
+  return 0;
+}
+
+int yad_gap(const yad_tensor* x, float* out, int dtype, void* stream) {
+  CHECK_VIEW(x, "gap");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(out, 0, sizeof(float) * x->n * x->c, st);
+  int64_t hw = (int64_t)x->h * x->w;
+  int splits = (int)((hw * (x->c / 8) + TPB * 8 - 1) / (TPB * 8));
+  splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
+  dim3 grid(splits, x->n);
+  YAD_DISPATCH_DTYPE(dtype, gap_kernel<T><<<grid, TPB, x->c * sizeof(float), st>>>(*x, out);)
+  YAD_LAUNCH_CHECK("gap");
+  return 0;
+}
+
+int yad_rowcol_mean(const yad_tensor* x, const yad_tensor* rowmean, const yad_tensor* colmean, int dtype, void* stream) {
+  CHECK_VIEW(x, "rowcol_mean x");
+  CHECK_VIEW(rowmean, "rowcol_mean rows");
+  CHECK_VIEW(colmean, "rowcol_mean cols");
+  YAD_CHECK(rowmean->c == x->c && colmean->c == x->c, "rowcol_mean: channel mismatch");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(x->h > x->w ? x->h : x->w, x->n, 2);
+  int tpb = (x->c / 8) * 8;  // 8 pixel lanes per octet
+  tpb = tpb < 64 ? 64 : (tpb > 256 ? 256 : tpb);
+  YAD_DISPATCH_DTYPE(dtype, rowcol_mean_kernel<T><<<grid, tpb, x->c * sizeof(float), st>>>(*x, *rowmean, *colmean);)
+  YAD_LAUNCH_CHECK("rowcol_mean");
+  return 0;
+}
+
+int yad_rowcol_gate(const yad_tensor* x, const yad_tensor* gh, const yad_tensor* gw, const yad_tensor* y, int dtype, void* stream) {
+  CHECK_VIEW(y, "rowcol_gate y");
+  CHECK_VIEW(gh, "rowcol_gate gh");
+  CHECK_VIEW(gw, "rowcol_gate gw");
+  if (x) { CHECK_VIEW(x, "rowcol_gate x"); SAME_SHAPE(x, y, "rowcol_gate"); }
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = (int64_t)y->n * y->h * y->w * (y->c / 8);
+  yad_tensor xx = x ? *x : *y;
+  YAD_DISPATCH_DTYPE(dtype, rowcol_gate_kernel<T><<<grid_for(total), TPB, 0, st>>>(xx, x != nullptr, *gh, *gw, *y);)
+  YAD_LAUNCH_CHECK("rowcol_gate");
+  return 0;
+}
+
+int yad_pool_upsample(const yad_tensor* x, int s, const yad_tensor* y, int dtype, void* stream) {
+  CHECK_VIEW(x, "pool_upsample x");
+  CHECK_VIEW(y, "pool_upsample y");
+  SAME_SHAPE(x, y, "pool_upsample");
+  YAD_CHECK(s >= 1 && x->h / s >= 1 && x->w / s >= 1, "pool_upsample: scale %d too large for %dx%d", s, x->h, x->w);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = (int64_t)x->n * x->h * x->w * (x->c / 8);
+  YAD_DISPATCH_DTYPE(dtype, pool_upsample_kernel<T><<<grid_for(total, 128), 128, 0, st>>>(*x, s, *y);)
+  YAD_LAUNCH_CHECK("pool_upsample");
+  return 0;
+}
+
+int yad_mlca_pool(const yad_tensor* x, float* local, int local_size, int dtype, void* stream) {
+  CHECK_VIEW(x, "mlca_pool");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(local_size * local_size, x->n);
+  YAD_DISPATCH_DTYPE(dtype, mlca_pool_kernel<T><<<grid, 128, x->c * sizeof(float), st>>>(*x, local, local_size);)
+  YAD_LAUNCH_CHECK("mlca_pool");
+  return 0;
+}
+
+int yad_mlca_att(const float* local, const float* w_global, const float* w_local, int ksize, float local_weight, int n, int c,
+                 int local_size, float* att, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int nb = local_size * local_size;
+  size_t smem = (size_t)(nb * c + 2 * c) * sizeof(float);
+  YAD_CHECK(smem <= 48 * 1024, "mlca_att: %d channels need %zu B of shared memory", c, smem);
+  mlca_att_kernel<<<n, 256, smem, st>>>(local, w_global, w_local, ksize, local_weight, c, nb, att);
+  YAD_LAUNCH_CHECK("mlca_att");
+  return 0;
+}
+
+int yad_mlca_apply(const yad_tensor* x, const float* att, int local_size, const void* add, int add_ld, const yad_tensor* y, int dtype,
+                   void* stream) {
+  CHECK_VIEW(x, "mlca_apply x");
+  CHECK_VIEW(y, "mlca_apply y");
+  SAME_SHAPE(x, y, "mlca_apply");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = (int64_t)x->n * x->h * x->w * (x->c / 8);
+  YAD_DISPATCH_DTYPE(dtype, mlca_apply_kernel<T><<<grid_for(total), TPB, 0, st>>>(*x, att, local_size, (const T*)add, add_ld, *y);)
+  YAD_LAUNCH_CHECK("mlca_apply");
+  return 0;
+}
+
+int yad_gate_mlp(const float* g, const float* w1, const float* b1, const float* w2, const float* b2, int n, int c, int hidden,
+                 int nout, int kind, float* out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  gate_mlp_kernel<<<n, 128, (hidden + nout) * sizeof(float), st>>>(g, w1, b1, w2, b2, c, hidden, nout, kind, out);
+  YAD_LAUNCH_CHECK("gate_mlp");
+  return 0;
+}
+
+int yad_adt_apply(const yad_tensor* x, const float* imp, const float* alphas, const float* weight, const float* bias,
+                  const yad_tensor* y, int dtype, void* stream) {
+  CHECK_VIEW(x, "adt x");
+  CHECK_VIEW(y, "adt y");
+  SAME_SHAPE(x, y, "adt_apply");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = (int64_t)x->n * x->h * x->w * (x->c / 8);
+  YAD_DISPATCH_DTYPE(dtype, adt_apply_kernel<T><<<grid_for(total), TPB, 0, st>>>(*x, imp, alphas, weight, bias, *y);)
+  YAD_LAUNCH_CHECK("adt_apply");
+  return 0;
+}
+
+int yad_eltwise(int op, const yad_tensor* a, const void* b, int b_ld, const void* c3, int c3_ld, const void* d4, int d4_ld,
+                float alpha, float beta, float gamma, const yad_tensor* y, int dtype, void* stream) {
+  CHECK_VIEW(a, "eltwise a");
+  CHECK_VIEW(y, "eltwise y");
+  SAME_SHAPE(a, y, "eltwise");
+  YAD_CHECK(op >= 0 && op <= 3 && b != nullptr, "eltwise: bad op %d or null operand", op);
+  YAD_CHECK(op != 3 || (c3 && d4), "eltwise: op 3 needs four operands");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = (int64_t)a->n * a->h * a->w * (a->c / 8);
+  YAD_DISPATCH_DTYPE(dtype, eltwise_kernel<T><<<grid_for(total), TPB, 0, st>>>(op, *a, (const T*)b, b_ld, (const T*)c3, c3_ld,
+                                                                                (const T*)d4, d4_ld, alpha, beta, gamma, *y);)
+  YAD_LAUNCH_CHECK("eltwise");
+  return 0;
+}
+
+int yad_group_mean(const yad_tensor* x, int s, const yad_tensor* y, int dtype, void* stream) {
+  CHECK_VIEW(x, "group_mean x");
+  CHECK_VIEW(y, "group_mean y");
+  YAD_CHECK(x->n == y->n && x->c == y->c && (int64_t)x->h * x->w == (int64_t)s * y->h * y->w, "group_mean: shape mismatch");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = (int64_t)y->n * y->h * y->w * (y->c / 8);
+  YAD_DISPATCH_DTYPE(dtype, group_mean_kernel<T><<<grid_for(total), TPB, 0, st>>>(*x, s, *y);)
+  YAD_LAUNCH_CHECK("group_mean");
+  return 0;
+}
+
+int yad_patch_filter(const yad_tensor* x, const float* m, float alpha, const void* add, int add_ld, const yad_tensor* y, int dtype,
+                     void* stream) {
+  CHECK_VIEW(x, "patch_filter x");
+  CHECK_VIEW(y, "patch_filter y");
+  SAME_SHAPE(x, y, "patch_filter");
+  YAD_CHECK(x->h >= 2 && x->w >= 2, "patch_filter: reflect padding needs h, w >= 2");
+  YAD_CHECK(((8 - x->h % 8) % 8) < x->h && ((8 - x->w % 8) % 8) < x->w, "patch_filter: reflect pad wider than the map (%dx%d)", x->h, x->w);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(((x->h + 7) / 8) * ((x->w + 7) / 8), x->n);
+  int tpb = x->c < 128 ? ((x->c + 31) / 32) * 32 : 128;
+  YAD_DISPATCH_DTYPE(dtype, patch_filter_kernel<T><<<grid, tpb, 0, st>>>(*x, m, alpha, (const T*)add, add_ld, *y);)
+  YAD_LAUNCH_CHECK("patch_filter");
+  return 0;
+}
+
+}  // extern "C"

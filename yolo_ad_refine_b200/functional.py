@@ -1,0 +1,366 @@
+"""The YOLO-AD-Refine forward pass expressed as calls into libyad.so (via ops.py), block by block.
+
+Every function names the reference module whose `forward` it replaces (paths relative to /root/reference/ultralytics).  Activations
+are NHWC `Act` views; concatenations are eliminated by writing producers into channel windows of one buffer.  This file contains no
+arithmetic of its own: all math happens in the CUDA kernels (weights are prepared once in weights.py).
+"""
+import torch
+
+from . import ops
+from .ops import ACT_HARDSWISH, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, Act
+from .weights import GN_EPS, ConvW, edffn_spectral_matrix, fold_bn, gn_groups
+
+
+class Ctx:
+    """Execution context: prepared weights + allocation helpers (torch caching allocator = plumbing)."""
+
+    def __init__(self, P, conv_impl=0):
+        self.P, self.dtype, self.device, self.conv_impl = P, P.dtype, P.device, conv_impl
+
+    def act(self, n, h, w, c, ld=None):
+        return Act.empty(n, h, w, c, self.dtype, self.device, ld)
+
+    def f32(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    def f64(self, *shape):
+        return torch.empty(shape, dtype=torch.float64, device=self.device)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# generic pieces
+# --------------------------------------------------------------------------------------------------------------------
+def conv(ctx, x, cw: ConvW, out=None, act=ACT_NONE, mode=ops.CONV_NORMAL, **epi):
+    assert x.c == cw.cin, f"conv: input has {x.c} channels, weight expects {cw.cin}"
+    if mode == ops.CONV_TRANSPOSED:
+        ho, wo = 2 * x.h, 2 * x.w
+    elif mode == ops.CONV_DEFORM:
+        ho, wo = x.h, x.w
+    else:
+        ho = (x.h + 2 * cw.pad_h - cw.kh) // cw.stride + 1
+        wo = (x.w + 2 * cw.pad_w - cw.kw) // cw.stride + 1
+    if out is None:
+        out = ctx.act(x.n, ho, wo, cw.cout)
+    assert (out.n, out.h, out.w, out.c) == (x.n, ho, wo, cw.cout), ((out.n, out.h, out.w, out.c), (x.n, ho, wo, cw.cout))
+    return ops.conv2d(x, cw.w, out, bias=cw.b, kh=cw.kh, kw=cw.kw, stride=cw.stride, pad_h=cw.pad_h, pad_w=cw.pad_w, act=act, mode=mode,
+                      impl=ctx.conv_impl, **epi)
+
+
+def conv_bn_act(ctx, p, x, stride=1, out=None, add=None):
+    """nn/modules/conv.py:36-54 Conv.forward_fuse: conv (BN folded) + SiLU"""
+    return conv(ctx, x, ctx.P.conv_bn(p, stride), out=out, act=ACT_SILU, add=add)
+
+
+def conv_gn_act(ctx, p, x, out=None, add=None, act=ACT_SILU, img_scale=None):
+    """nn/modules/head.py:1265-1279 Conv_GN: conv(bias=False) -> GroupNorm -> SiLU"""
+    cw = ctx.P.conv(p + ".conv.weight")
+    t = conv(ctx, x, cw, img_scale=img_scale)
+    g = gn_groups(ctx.P.sd[p + ".conv.weight"].shape[0])
+    if out is None:
+        out = ctx.act(t.n, t.h, t.w, t.c)
+    return ops.group_norm(t, out, ctx.f64(t.n, g, 2), g, ctx.P.f32(p + ".gn.weight"), ctx.P.f32(p + ".gn.bias"), GN_EPS, act, add)
+
+
+def mlca(ctx, p, x, out, add=None):
+    """nn/modules/block.py:1540-1584 MLCA (+ the residual add of Bottleneck_MLCA)"""
+    P = ctx.P
+    wg, wl = P.f32(p + ".conv.weight"), P.f32(p + ".conv_local.weight")
+    k = wg.numel()
+    return ops.mlca(x, out, wg, wl, k, ctx.f32(x.n, 25, x.c), ctx.f32(x.n, 25, x.c), 5, 0.5, add)
+
+
+def bottleneck(ctx, p, x, out=None, attention=False):
+    """nn/modules/block.py:341-354 Bottleneck / :1586-1594 Bottleneck_MLCA (shortcut=True, c1 == c2)"""
+    t = conv_bn_act(ctx, p + ".cv1", x)
+    if out is None:
+        out = ctx.act(x.n, x.h, x.w, x.c)
+    if attention:
+        t2 = conv_bn_act(ctx, p + ".cv2", t)
+        return mlca(ctx, p + ".attention", t2, out, add=x)
+    return conv_bn_act(ctx, p + ".cv2", t, out=out, add=x)
+
+
+def c3k(ctx, p, x, out, attention=False):
+    """nn/modules/block.py:256-270 C3.forward / :742-750 C3k / :1596-1600 C3k_MLCA (n = 2 bottlenecks)"""
+    c_ = ctx.P.conv_bn(p + ".cv1").cout
+    cat = ctx.act(x.n, x.h, x.w, 2 * c_)
+    a = conv_bn_act(ctx, p + ".cv1", x)
+    a = bottleneck(ctx, p + ".m.0", a, attention=attention)
+    bottleneck(ctx, p + ".m.1", a, out=cat.slice(0, c_), attention=attention)
+    conv_bn_act(ctx, p + ".cv2", x, out=cat.slice(c_, c_))
+    return conv_bn_act(ctx, p + ".cv3", cat, out=out)
+
+
+def c3k2(ctx, p, x, use_c3k=False, attention=False):
+    """nn/modules/block.py:232-247 C2f.forward / :731-739 C3k2 / :1602-1605 C3k2_MLCA (n = 1)"""
+    c = ctx.P.conv_bn(p + ".cv1").cout // 2
+    cat = ctx.act(x.n, x.h, x.w, 3 * c)
+    conv_bn_act(ctx, p + ".cv1", x, out=cat.slice(0, 2 * c))
+    y1 = cat.slice(c, c)
+    if use_c3k:
+        c3k(ctx, p + ".m.0", y1, cat.slice(2 * c, c), attention)
+    else:
+        bottleneck(ctx, p + ".m.0", y1, out=cat.slice(2 * c, c), attention=attention)
+    return conv_bn_act(ctx, p + ".cv2", cat)
+
+
+def sppf(ctx, p, x):
+    """nn/modules/block.py:177-196 SPPF"""
+    c = ctx.P.conv_bn(p + ".cv1").cout
+    cat = ctx.act(x.n, x.h, x.w, 4 * c)
+    y0 = conv_bn_act(ctx, p + ".cv1", x, out=cat.slice(0, c))
+    ops.sppf_pool(y0, cat.slice(c, c), cat.slice(2 * c, c), cat.slice(3 * c, c))
+    return conv_bn_act(ctx, p + ".cv2", cat)
+
+
+def ela_hsfpn(ctx, p, x, flag=True, out=None):
+    """nn/modules/block.py:1408-1424 ELA_HSFPN: both 1-D branches share Conv1d(k7) + GroupNorm(16) + sigmoid"""
+    P = ctx.P
+    n, h, w, c = x.n, x.h, x.w, x.c
+    cw = P.conv(p + ".conv1x1.0.weight", p + ".conv1x1.0.bias")
+    gamma, beta = P.f32(p + ".conv1x1.1.weight"), P.f32(p + ".conv1x1.1.bias")
+    if out is None:
+        out = ctx.act(n, h, w, c)
+
+    def branch(means):
+        t = conv(ctx, means, cw)
+        g = ctx.act(t.n, t.h, t.w, t.c)
+        return ops.group_norm(t, g, ctx.f64(t.n, 16, 2), 16, gamma, beta, GN_EPS, ACT_SIGMOID)
+
+    if h == w:  # one batched pass over (2n, L, 1, c)
+        means = ctx.act(2 * n, h, 1, c)
+        ops.rowcol_mean(x, means.images(0, n), means.images(n, n))
+        g = branch(means)
+        gh, gw = g.images(0, n), g.images(n, n)
+    else:
+        rows, cols = ctx.act(n, h, 1, c), ctx.act(n, w, 1, c)
+        ops.rowcol_mean(x, rows, cols)
+        gh, gw = branch(rows), branch(cols)
+    return ops.rowcol_gate(x if flag else None, gh, gw, out)
+
+
+def fusion_bifpn(ctx, p, xs):
+    """nn/modules/block.py:1532-1535 Fusion('bifpn') for two inputs"""
+    w = torch.relu(ctx.P.sd[p + ".fusion_weight"].float())
+    w = (w / (w.sum() + 1e-4)).tolist()
+    assert len(xs) == 2
+    return ops.eltwise(0, xs[0], xs[1], ctx.act(xs[0].n, xs[0].h, xs[0].w, xs[0].c), alpha=w[0], beta=w[1])
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# layer 10: C2ProgressiveTSSA_Fusion
+# --------------------------------------------------------------------------------------------------------------------
+def progressive_feature_fusion(ctx, p, x):
+    """nn/modules/block.py:2579-2630 ProgressiveFeatureFusion"""
+    P = ctx.P
+    n, h, w, c = x.n, x.h, x.w, x.c
+    outs, cur = [], x
+    for i in range(3):
+        q = f"{p}.stages.{i}"
+        dw3, b3, _ = P.dw(q + ".conv.weight", q + ".conv.bias")
+        sc, sh = P.bn_affine(q + ".norm")
+        t = ops.dwconv(cur, dw3, ctx.act(n, h, w, c), bias=b3, scale=sc, shift=sh, k=3, act=ops.ACT_GELU)
+        dw7, b7, _ = P.dw(q + ".spatial_mix.weight", q + ".spatial_mix.bias")
+        sm = ops.dwconv(t, dw7, ctx.act(n, h, w, c), bias=b7, k=7, add=cur)  # spatial_mix(t) + cur
+        o = conv(ctx, t, P.conv(q + ".channel_mix.weight", q + ".channel_mix.bias"), add=sm)  # + channel_mix(t)
+        outs.append(o)
+        if i < 2:  # stage_fusion over cat([cur, o]) as two accumulating 1x1 convs (no concat buffer)
+            wk, bk = f"{p}.stage_fusion.{i}.weight", f"{p}.stage_fusion.{i}.bias"
+            wfull = P.sd[wk].float()
+            c1 = P.conv_raw(wk + "#a", wfull[:, :c], P.sd[bk].float())
+            c2 = P.conv_raw(wk + "#b", wfull[:, c:], None)
+            tmp = conv(ctx, cur, c1)
+            cur = conv(ctx, o, c2, add=tmp)
+    sa = P.vec(p + ".stage_attention")
+    return ops.eltwise(3, outs[0], outs[1], ctx.act(n, h, w, c), c3=outs[2], d4=x, alpha=sa[0], beta=sa[1], gamma=sa[2])
+
+
+def adaptive_dynamic_tanh(ctx, p, x):
+    """nn/modules/block.py:2493-2577 AdaptiveDynamicTanh"""
+    P = ctx.P
+    g = ops.gap(x, ctx.f32(x.n, x.c))
+    w1 = P.misc(p + ".ig1", lambda: P.f32(p + ".importance_gate.1.weight").reshape(-1, x.c).contiguous())
+    w2 = P.misc(p + ".ig3", lambda: P.f32(p + ".importance_gate.3.weight").reshape(3, -1).contiguous())
+    imp = ops.gate_mlp(g, w1, P.f32(p + ".importance_gate.1.bias"), w2, P.f32(p + ".importance_gate.3.bias"), ctx.f32(x.n, 3), kind=1)
+    alphas = P.misc(p + ".al", lambda: P.f32(p + ".alphas").reshape(-1).contiguous())
+    return ops.adt_apply(x, imp, alphas, P.f32(p + ".weight"), P.f32(p + ".bias"), ctx.act(x.n, x.h, x.w, x.c))
+
+
+def cross_scale_attention_tssa(ctx, p, x, identity, rw, heads=2, scales=(1, 2, 4)):
+    """nn/modules/block.py:2417-2491 CrossScaleAttentionTSSA, fused with `identity + attn * residual_weight1` (block.py:2680-2683).
+    out_proj (of nn.MultiheadAttention), the mean over scales and to_out are all linear, so they run as ONE 1x1 conv after the mean."""
+    P = ctx.P
+    n, h, w, c = x.n, x.h, x.w, x.c
+    T = h * w
+    st = ctx.act(n, len(scales) * T, 1, c)
+    temps = P.misc(p + ".temps", lambda: P.f32(p + ".temps").reshape(len(scales), heads).contiguous())
+    for i, s in enumerate(scales):
+        xs = x if s == 1 else ops.pool_upsample(x, s, ctx.act(n, h, w, c))
+        qkv = conv(ctx, xs, P.conv(f"{p}.qkv_projections.{i}.weight"))
+        ops.tssa(qkv, temps[i], heads, st, i * T)
+    q = p + ".cross_scale_fusion"
+    qkv2 = conv(ctx, st, P.conv(q + ".in_proj_weight", q + ".in_proj_bias"))
+    ao = ops.mha(qkv2, heads, ctx.act(n, len(scales) * T, 1, c))
+    am = ops.group_mean(ao, len(scales), ctx.act(n, h, w, c))
+
+    def fold():
+        wo, bo = P.sd[q + ".out_proj.weight"].double(), P.sd[q + ".out_proj.bias"].double()
+        wt, bt = P.sd[p + ".to_out.0.weight"].double(), P.sd[p + ".to_out.0.bias"].double()
+        return (wt @ wo).float()[:, :, None, None], (wt @ bo + bt).float()
+
+    wf, bf = P.misc(p + ".fold", fold)
+    return conv(ctx, am, P.conv_raw(p + ".out_fold", wf, bf), alpha=rw, add=identity)
+
+
+def edffn(ctx, p, x, residual, rw):
+    """nn/modules/block.py:2376-2415 EDFFN, fused with `x + ffn * residual_weight2` (block.py:2694-2697); writes into `residual`'s shape"""
+    P = ctx.P
+    n, h, w = x.n, x.h, x.w
+    t = conv(ctx, x, P.conv(p + ".project_in.weight"))
+    dw, _, _ = P.dw(p + ".dwconv.weight")
+    g = ops.dwconv(t, dw, ctx.act(n, h, w, t.c // 2), k=3, gate_split=t.c // 2)
+    o = conv(ctx, g, P.conv(p + ".project_out.weight"))
+    m = P.misc(p + ".spectral", lambda: edffn_spectral_matrix(P.sd[p + ".fft"]).to(ctx.device))
+    return o, m
+
+
+def progressive_tssa_fusion(ctx, p, x, out):
+    """nn/modules/block.py:2632-2698 ProgressiveTSSA_Fusion.forward (shortcut=True); result written into `out`"""
+    P = ctx.P
+    t = progressive_feature_fusion(ctx, p + ".progressive_fusion1", x)
+    t = adaptive_dynamic_tanh(ctx, p + ".dyt1", t)
+    t = cross_scale_attention_tssa(ctx, p + ".attn", t, identity=x, rw=P.scalar(p + ".residual_weight1"))
+    t = progressive_feature_fusion(ctx, p + ".progressive_fusion2", t)
+    f = adaptive_dynamic_tanh(ctx, p + ".dyt2", t)
+    o, m = edffn(ctx, p + ".ffn", f, t, None)
+    return ops.patch_filter(o, m, out, alpha=P.scalar(p + ".residual_weight2"), add=t)
+
+
+def c2ptssa(ctx, p, x):
+    """nn/modules/block.py:2700-2710 C2ProgressiveTSSA_Fusion + C2PSA.forward :1045-1049"""
+    c = ctx.P.conv_bn(p + ".cv1").cout // 2
+    ab = conv_bn_act(ctx, p + ".cv1", x)
+    b = ab.slice(c, c)
+    progressive_tssa_fusion(ctx, p + ".m.0", b, out=b)  # b is dead once the attention residual has consumed it
+    return conv_bn_act(ctx, p + ".cv2", ab)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# AYHead1
+# --------------------------------------------------------------------------------------------------------------------
+def task_decomposition(ctx, p, feat, avg, out):
+    """nn/modules/head.py:626-669 TaskDecomposition (stacked_convs = 1): per-image scalar gate on a 1x1 conv, then GN + SiLU"""
+    P = ctx.P
+    w1 = P.misc(p + ".la1", lambda: P.f32(p + ".la_conv1.weight").reshape(-1, feat.c).contiguous())
+    w2 = P.misc(p + ".la2", lambda: P.f32(p + ".la_conv2.weight").reshape(1, -1).contiguous())
+    gate = ops.gate_mlp(avg, w1, P.f32(p + ".la_conv1.bias"), w2, P.f32(p + ".la_conv2.bias"), ctx.f32(feat.n, 1), kind=0)
+    return conv_gn_act(ctx, p + ".reduction_conv", feat, out=out, img_scale=gate)
+
+
+def coord_att(ctx, p, x, out=None):
+    """nn/modules/head.py:671-707 CoordAtt (conv1 + bn1 folded, h-swish, per-axis 1x1 + sigmoid gates)"""
+    P = ctx.P
+    n, h, w, c = x.n, x.h, x.w, x.c
+
+    def fold():
+        return fold_bn(P.sd[p + ".conv1.weight"].float(), P.sd[p + ".bn1.weight"].float(), P.sd[p + ".bn1.bias"].float(),
+                       P.sd[p + ".bn1.running_mean"].float(), P.sd[p + ".bn1.running_var"].float(), P.sd[p + ".conv1.bias"].float())
+
+    wf, bf = P.misc(p + ".fold", fold)
+    c1 = P.conv_raw(p + ".conv1f", wf, bf)
+    rows, cols = ctx.act(n, h, 1, c), ctx.act(n, w, 1, c)
+    ops.rowcol_mean(x, rows, cols)
+    gh = conv(ctx, conv(ctx, rows, c1, act=ACT_HARDSWISH), P.conv(p + ".conv_h.weight", p + ".conv_h.bias"), act=ACT_SIGMOID)
+    gw = conv(ctx, conv(ctx, cols, c1, act=ACT_HARDSWISH), P.conv(p + ".conv_w.weight", p + ".conv_w.bias"), act=ACT_SIGMOID)
+    return ops.rowcol_gate(x, gh, gw, out if out is not None else ctx.act(n, h, w, c))
+
+
+def ayhead_level(ctx, p, x, i):
+    """nn/modules/head.py:1131-1175: one pyramid level of AYHead1.forward -> raw (n, h, w, 4*reg_max + nc)"""
+    P = ctx.P
+    n, h, w = x.n, x.h, x.w
+    ad = conv_gn_act(ctx, f"{p}.stems.{i}", x)
+    feat = conv_gn_act(ctx, p + ".share_conv.1", conv_gn_act(ctx, p + ".share_conv.0", ad))
+    fc = feat.c
+    avg = ops.gap(feat, ctx.f32(n, fc))
+    crc, crr = ctx.act(n, h, w, 2 * fc), ctx.act(n, h, w, 2 * fc)  # [cls | reg_to_cls(reg)] and [reg | cls_to_reg(cls)]
+    cls = task_decomposition(ctx, p + ".cls_decomp", feat, avg, crc.slice(0, fc))
+    reg = task_decomposition(ctx, p + ".reg_decomp", feat, avg, crr.slice(0, fc))
+    # CrossTaskInteraction head.py:1319-1333
+    q = p + ".cross_task"
+    conv(ctx, cls, P.conv(q + ".cls_to_reg.weight", q + ".cls_to_reg.bias"), out=crr.slice(fc, fc))
+    conv(ctx, reg, P.conv(q + ".reg_to_cls.weight", q + ".reg_to_cls.bias"), out=crc.slice(fc, fc))
+    cls2 = conv(ctx, crc, P.conv(q + ".cls_gate.0.weight", q + ".cls_gate.0.bias"), act=ACT_SIGMOID, mul=crc.slice(fc, fc), add=cls)
+    reg2 = conv(ctx, crr, P.conv(q + ".reg_gate.0.weight", q + ".reg_gate.0.bias"), act=ACT_SIGMOID, mul=crr.slice(fc, fc), add=reg)
+    # ResidualBlockGN head.py:1031-1047
+    cls_e = conv_gn_act(ctx, p + ".rep_block_cls.conv2", conv_gn_act(ctx, p + ".rep_block_cls.conv1", cls2), add=cls2)
+    # DyDCNv2 head.py:751-782 (offsets / mask from `feat`, head.py:1155-1159) + GroupNorm(16) + CoordAtt
+    om = conv(ctx, feat, P.conv(p + ".spatial_conv_offset.weight", p + ".spatial_conv_offset.bias"))
+    ra = conv(ctx, reg2, P.conv(p + ".DyDCNV2.conv.weight"), mode=ops.CONV_DEFORM, offmask=om)
+    ra = ops.group_norm(ra, ctx.act(n, h, w, fc), ctx.f64(n, 16, 2), 16, P.f32(p + ".DyDCNV2.norm.weight"), P.f32(p + ".DyDCNV2.norm.bias"),
+                        GN_EPS, ACT_NONE)
+    reg_e = coord_att(ctx, p + ".coord_attention_reg", ra)
+    # cls_prob head.py:1168-1169
+    cp = conv(ctx, feat, P.conv(p + ".cls_prob_conv.0.weight", p + ".cls_prob_conv.0.bias"), act=ACT_RELU)
+    cp = conv(ctx, cp, P.conv(p + ".cls_prob_conv.2.weight", p + ".cls_prob_conv.2.bias"), act=ACT_SIGMOID)  # channel 0 of 8
+    cv2, cv3 = P.conv(p + ".cv2.weight", p + ".cv2.bias"), P.conv(p + ".cv3.weight", p + ".cv3.bias")
+    out = ctx.act(n, h, w, cv2.cout + cv3.cout)
+    conv(ctx, reg_e, cv2, out=out.slice(0, cv2.cout), alpha=P.scalar(f"{p}.scale.{i}.scale"))
+    conv(ctx, cls_e, cv3, out=out.slice(cv2.cout, cv3.cout), pix_scale=cp)  # cv3(cls * cls_prob): the 1x1 conv commutes with a per-pixel scalar
+    return out
+
+
+def ayhead(ctx, p, xs, strides=(8, 16, 32), nc=80, reg_max=16, decode=True):
+    """nn/modules/head.py:1127-1204 AYHead1.forward -> (y (B, 4+nc, N) fp32, [raw level outputs])"""
+    outs = [ayhead_level(ctx, p, x, i) for i, x in enumerate(xs)]
+    if not decode:
+        return None, outs
+    n_anchors = sum(o.h * o.w for o in outs)
+    y = ctx.f32(outs[0].n, 4 + nc, n_anchors)
+    proj = ctx.P.misc(p + ".proj", lambda: ctx.P.f32(p + ".dfl.conv.weight").reshape(-1).contiguous())
+    ops.decode(outs, strides, nc, reg_max, proj, y)
+    return y, outs
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# whole model (z-yaml/yolo11-701-YOLO-AD-Refine.yaml at scale n; nn/tasks.py:141-168 _predict_once)
+# --------------------------------------------------------------------------------------------------------------------
+def forward_model(ctx, img, decode=True, keep_layers=False):
+    """img: fp32 (n, 3, H, W) in [0, 1] on the device.  Returns (y, raw_levels[, layer outputs])."""
+    n, _, H, W = img.shape
+    assert H % 32 == 0 and W % 32 == 0, "image size must be a multiple of the maximum stride 32"
+    L = {}
+    x = ops.nchw_to_nhwc(img, ctx.act(n, H, W, 8))
+    L[0] = conv_bn_act(ctx, "model.0", x, 2)
+    L[1] = conv_bn_act(ctx, "model.1", L[0], 2)
+    L[2] = c3k2(ctx, "model.2", L[1])
+    L[3] = conv_bn_act(ctx, "model.3", L[2], 2)
+    L[4] = c3k2(ctx, "model.4", L[3])
+    L[5] = conv_bn_act(ctx, "model.5", L[4], 2)
+    L[6] = c3k2(ctx, "model.6", L[5], True, True)
+    L[7] = conv_bn_act(ctx, "model.7", L[6], 2)
+    L[8] = c3k2(ctx, "model.8", L[7], True, True)
+    L[9] = sppf(ctx, "model.9", L[8])
+    L[10] = c2ptssa(ctx, "model.10", L[9])
+    P = ctx.P
+    # neck (HS-FPN): lateral 1x1 * gate + upsampled, fused into the 1x1 conv epilogue (yaml layers 15-18 and 22-25)
+    L[11] = ela_hsfpn(ctx, "model.11", L[10], True)
+    L[12] = conv(ctx, L[11], P.conv("model.12.weight", "model.12.bias"))
+    L[13] = conv(ctx, L[12], P.conv("model.13.weight", "model.13.bias", transposed=True), mode=ops.CONV_TRANSPOSED)
+    L[14] = ela_hsfpn(ctx, "model.14", L[6], True)
+    L[16] = ela_hsfpn(ctx, "model.16", L[13], False)
+    L[18] = conv(ctx, L[14], P.conv("model.15.weight", "model.15.bias"), mul=L[16], add=L[13])  # Multiply (17) + Add (18)
+    L[19] = c3k2(ctx, "model.19", L[18], False, True)
+    L[20] = conv(ctx, L[19], P.conv("model.20.weight", "model.20.bias", transposed=True), mode=ops.CONV_TRANSPOSED)
+    L[21] = ela_hsfpn(ctx, "model.21", L[4], True)
+    L[23] = ela_hsfpn(ctx, "model.23", L[20], False)
+    L[25] = conv(ctx, L[21], P.conv("model.22.weight", "model.22.bias"), mul=L[23], add=L[20])  # Multiply (24) + Add (25)
+    L[26] = c3k2(ctx, "model.26", L[25], False, True)
+    L[27] = conv_bn_act(ctx, "model.27", L[26], 2)
+    L[28] = fusion_bifpn(ctx, "model.28", [L[27], L[19]])
+    L[29] = c3k2(ctx, "model.29", L[28])
+    L[30] = conv_bn_act(ctx, "model.30", L[29], 2)
+    L[31] = fusion_bifpn(ctx, "model.31", [L[30], L[12]])
+    L[32] = c3k2(ctx, "model.32", L[31])
+    y, outs = ayhead(ctx, "model.33", [L[26], L[29], L[32]], decode=decode)
+    return (y, outs, L) if keep_layers else (y, outs)

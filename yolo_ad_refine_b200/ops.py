@@ -1,0 +1,269 @@
+"""Thin Python wrappers over the C ABI (include/yad.h).  PyTorch is only plumbing here: it owns device memory and streams.
+
+`Act` is an NHWC activation view: a torch buffer of shape (n, h, w, ld) plus a channel window [c0, c0+c) -- the `yad_tensor` of the
+C side.  A channel window of a wider buffer is how concatenations are eliminated (C2f / C3 / SPPF concat, cross-task concat).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_HARDSWISH, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, BF16, CONV_DEFORM, CONV_NORMAL,  # noqa: F401
+                   CONV_TRANSPOSED, F32, YadConvDesc, YadEpilogue, YadTensor, check)
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+# number of libyad kernel launches issued through this module (bench.py reports it as gpu_launches)
+LAUNCHES = 0
+# per-launch multiplicity of the multi-kernel entry points
+_MULTI = {"yad_nms": 6, "yad_tal_assign": 2, "yad_gn_stats": 1}
+
+
+def _count(name):
+    global LAUNCHES
+    LAUNCHES += _MULTI.get(name, 1)
+
+
+def lib():
+    return _lib.load()
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dt(t):
+    return _DT[t.dtype if isinstance(t, torch.Tensor) else t]
+
+
+class Act:
+    """NHWC activation view (n, h, w, c) with pixel stride ld inside `buf` (n, h, w, ld)."""
+    __slots__ = ("buf", "c0", "c", "_yt")
+
+    def __init__(self, buf, c0=0, c=None):
+        assert buf.dim() == 4 and buf.is_contiguous(), "Act buffers are contiguous (n, h, w, ld)"
+        self.buf, self.c0 = buf, c0
+        self.c = buf.shape[3] - c0 if c is None else c
+        assert self.c0 % 8 == 0 and self.c % 8 == 0 and buf.shape[3] % 8 == 0, (self.c0, self.c, buf.shape)
+        self._yt = None
+
+    n = property(lambda s: s.buf.shape[0])
+    h = property(lambda s: s.buf.shape[1])
+    w = property(lambda s: s.buf.shape[2])
+    ld = property(lambda s: s.buf.shape[3])
+    dtype = property(lambda s: s.buf.dtype)
+    device = property(lambda s: s.buf.device)
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr() + self.c0 * self.buf.element_size()
+
+    def yt(self):
+        if self._yt is None:
+            self._yt = YadTensor(self.ptr, self.n, self.h, self.w, self.c, self.ld)
+        return C.byref(self._yt)
+
+    def slice(self, c0, c):
+        assert 0 <= c0 and c0 + c <= self.c
+        return Act(self.buf, self.c0 + c0, c)
+
+    def images(self, i0, cnt):
+        """sub-batch view (images are contiguous)"""
+        return Act(self.buf[i0:i0 + cnt], self.c0, self.c)
+
+    def reshape(self, n, h, w):
+        """same memory, different (n, h, w) factorisation of the pixel axis (only for full-width views)"""
+        assert n * h * w == self.n * self.h * self.w
+        return Act(self.buf.view(n, h, w, self.ld), self.c0, self.c)
+
+    def torch(self):
+        """(n, h, w, c) torch view"""
+        return self.buf[..., self.c0:self.c0 + self.c]
+
+    def nchw(self):
+        """(n, c, h, w) torch view with channels-last strides (no copy)"""
+        return self.torch().permute(0, 3, 1, 2)
+
+    @staticmethod
+    def empty(n, h, w, c, dtype, device, ld=None):
+        return Act(torch.empty((n, h, w, ld or c), dtype=dtype, device=device), 0, c)
+
+    @staticmethod
+    def from_nchw(x, dtype=None):
+        """copy an (n, c, h, w) torch tensor into a fresh NHWC buffer (channels padded to a multiple of 8 with zeros)"""
+        n, c, h, w = x.shape
+        cp = (c + 7) // 8 * 8
+        buf = torch.zeros((n, h, w, cp), dtype=dtype or x.dtype, device=x.device)
+        buf[..., :c] = x.permute(0, 2, 3, 1)
+        return Act(buf, 0, cp)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _ap(a):
+    return (None, 0) if a is None else (C.c_void_p(a.ptr), a.ld)
+
+
+def conv2d(x, w, y, bias=None, kh=1, kw=1, stride=1, pad_h=0, pad_w=0, act=ACT_NONE, alpha=1.0, img_scale=None, pix_scale=None,
+           mul=None, add=None, mode=CONV_NORMAL, offmask=None, impl=0):
+    """y = epilogue(conv(x, w)); w packed [cout][kh*kw][cin] in the activation dtype."""
+    d = YadConvDesc(mode, kh, kw, stride, pad_h, pad_w, None if offmask is None else offmask.ptr, 0 if offmask is None else offmask.ld, impl)
+    mp, mld = _ap(mul)
+    adp, ald = _ap(add)
+    psp, psld = _ap(pix_scale)
+    e = YadEpilogue(None if bias is None else bias.data_ptr(), None if img_scale is None else img_scale.data_ptr(),
+                    psp, psld, act, alpha, mp, mld, adp, ald)
+    _count("yad_conv2d")
+    check(lib().yad_conv2d(x.yt(), _p(w), C.byref(d), C.byref(e), y.yt(), dt(x.dtype), stream_ptr()), "yad_conv2d")
+    return y
+
+
+def dwconv(x, w, y, bias=None, scale=None, shift=None, k=3, act=ACT_NONE, gate_split=0, add=None):
+    adp, ald = _ap(add)
+    _count("yad_dwconv")
+    check(lib().yad_dwconv(x.yt(), _p(w), _p(bias), _p(scale), _p(shift), k, act, gate_split, adp, ald, y.yt(), dt(x.dtype), stream_ptr()),
+          "yad_dwconv")
+    return y
+
+
+def group_norm(x, y, stats, groups, gamma, beta, eps=1e-5, act=ACT_NONE, add=None):
+    """stats: double (n, groups, 2) scratch"""
+    L = lib()
+    _count("yad_gn_stats")
+    check(L.yad_gn_stats(x.yt(), groups, _p(stats), dt(x.dtype), stream_ptr()), "yad_gn_stats")
+    adp, ald = _ap(add)
+    _count("yad_gn_apply")
+    check(L.yad_gn_apply(x.yt(), _p(stats), groups, _p(gamma), _p(beta), eps, act, adp, ald, y.yt(), dt(x.dtype), stream_ptr()), "yad_gn_apply")
+    return y
+
+
+def sppf_pool(x, y1, y2, y3):
+    _count("yad_sppf_pool")
+    check(lib().yad_sppf_pool(x.yt(), y1.yt(), y2.yt(), y3.yt(), dt(x.dtype), stream_ptr()), "yad_sppf_pool")
+
+
+def gap(x, out):
+    _count("yad_gap")
+    check(lib().yad_gap(x.yt(), _p(out), dt(x.dtype), stream_ptr()), "yad_gap")
+    return out
+
+
+def rowcol_mean(x, rows, cols):
+    _count("yad_rowcol_mean")
+    check(lib().yad_rowcol_mean(x.yt(), rows.yt(), cols.yt(), dt(x.dtype), stream_ptr()), "yad_rowcol_mean")
+
+
+def rowcol_gate(x, gh, gw, y):
+    _count("yad_rowcol_gate")
+    check(lib().yad_rowcol_gate(None if x is None else x.yt(), gh.yt(), gw.yt(), y.yt(), dt(y.dtype), stream_ptr()), "yad_rowcol_gate")
+    return y
+
+
+def pool_upsample(x, s, y):
+    _count("yad_pool_upsample")
+    check(lib().yad_pool_upsample(x.yt(), s, y.yt(), dt(x.dtype), stream_ptr()), "yad_pool_upsample")
+    return y
+
+
+def mlca(x, y, w_global, w_local, ksize, local, att, local_size=5, local_weight=0.5, add=None):
+    """y = x * MLCA_attention(x) (+ add); local/att: fp32 (n, ls*ls, c) scratch"""
+    L = lib()
+    _count("yad_mlca_pool")
+    check(L.yad_mlca_pool(x.yt(), _p(local), local_size, dt(x.dtype), stream_ptr()), "yad_mlca_pool")
+    _count("yad_mlca_att")
+    check(L.yad_mlca_att(_p(local), _p(w_global), _p(w_local), ksize, local_weight, x.n, x.c, local_size, _p(att), stream_ptr()), "yad_mlca_att")
+    adp, ald = _ap(add)
+    _count("yad_mlca_apply")
+    check(L.yad_mlca_apply(x.yt(), _p(att), local_size, adp, ald, y.yt(), dt(x.dtype), stream_ptr()), "yad_mlca_apply")
+    return y
+
+
+def gate_mlp(g, w1, b1, w2, b2, out, kind):
+    n, c = g.shape
+    hidden, nout = w1.shape[0], w2.shape[0]
+    _count("yad_gate_mlp")
+    check(lib().yad_gate_mlp(_p(g), _p(w1), _p(b1), _p(w2), _p(b2), n, c, hidden, nout, kind, _p(out), stream_ptr()), "yad_gate_mlp")
+    return out
+
+
+def adt_apply(x, imp, alphas, weight, bias, y):
+    _count("yad_adt_apply")
+    check(lib().yad_adt_apply(x.yt(), _p(imp), _p(alphas), _p(weight), _p(bias), y.yt(), dt(x.dtype), stream_ptr()), "yad_adt_apply")
+    return y
+
+
+def eltwise(op, a, b, y, c3=None, d4=None, alpha=1.0, beta=1.0, gamma=1.0):
+    bp, bld = _ap(b)
+    cp, cld = _ap(c3)
+    dp, dld = _ap(d4)
+    _count("yad_eltwise")
+    check(lib().yad_eltwise(op, a.yt(), bp, bld, cp, cld, dp, dld, alpha, beta, gamma, y.yt(), dt(a.dtype), stream_ptr()), "yad_eltwise")
+    return y
+
+
+def tssa(qkv, temps, heads, out, tok_offset):
+    _count("yad_tssa")
+    check(lib().yad_tssa(qkv.yt(), _p(temps), heads, out.yt(), tok_offset, dt(qkv.dtype), stream_ptr()), "yad_tssa")
+
+
+def mha(qkv, heads, out):
+    _count("yad_mha")
+    check(lib().yad_mha(qkv.yt(), heads, out.yt(), dt(qkv.dtype), stream_ptr()), "yad_mha")
+    return out
+
+
+def group_mean(x, s, y):
+    _count("yad_group_mean")
+    check(lib().yad_group_mean(x.yt(), s, y.yt(), dt(x.dtype), stream_ptr()), "yad_group_mean")
+    return y
+
+
+def patch_filter(x, m, y, alpha=1.0, add=None):
+    adp, ald = _ap(add)
+    _count("yad_patch_filter")
+    check(lib().yad_patch_filter(x.yt(), _p(m), alpha, adp, ald, y.yt(), dt(x.dtype), stream_ptr()), "yad_patch_filter")
+    return y
+
+
+def nchw_to_nhwc(img, y):
+    """img: fp32 (n, c, h, w) contiguous"""
+    assert img.dtype == torch.float32 and img.is_contiguous()
+    _count("yad_nchw_to_nhwc")
+    check(lib().yad_nchw_to_nhwc(_p(img), img.shape[1], y.yt(), dt(y.dtype), stream_ptr()), "yad_nchw_to_nhwc")
+    return y
+
+
+def decode(levels, strides, nc, reg_max, proj, y):
+    """levels: list of Act (n, h, w, 4*reg_max+nc) raw head outputs, or list of (B, no, H, W) torch tensors.  y: fp32 (B, 4+nc, N)."""
+    nl = len(levels)
+    ptrs, sb, sc, sa, hs, ws = (C.c_void_p * nl)(), (C.c_int64 * nl)(), (C.c_int64 * nl)(), (C.c_int64 * nl)(), (C.c_int32 * nl)(), (C.c_int32 * nl)()
+    st = (C.c_float * nl)(*[float(s) for s in strides])
+    dtype = None
+    for i, lv in enumerate(levels):
+        if isinstance(lv, Act):
+            ptrs[i], sb[i], sc[i], sa[i], hs[i], ws[i] = lv.ptr, lv.h * lv.w * lv.ld, 1, lv.ld, lv.h, lv.w
+            batch, d = lv.n, lv.dtype
+        else:  # (B, no, H, W) tensor with arbitrary strides, as long as (H, W) flatten to one anchor stride
+            b_, no_, h_, w_ = lv.shape
+            assert lv.stride(2) == w_ * lv.stride(3), "decode: level must have a uniform anchor stride"
+            ptrs[i], sb[i], sc[i], sa[i], hs[i], ws[i] = lv.data_ptr(), lv.stride(0), lv.stride(1), lv.stride(3), h_, w_
+            batch, d = b_, lv.dtype
+        assert dtype in (None, d)
+        dtype = d
+    _count("yad_decode")
+    check(lib().yad_decode(ptrs, sb, sc, sa, hs, ws, st, nl, batch, nc, reg_max, _p(proj), _p(y), dt(dtype), stream_ptr()), "yad_decode")
+    return y
+
+
+def nms_workspace_bytes(batch, n_anchors, nc, multi_label, max_nms):
+    return int(lib().yad_nms_workspace_bytes(batch, n_anchors, nc, int(multi_label), max_nms))
+
+
+def nms(pred, conf_thres, iou_thres, classes_mask, agnostic, multi_label, max_det, max_nms, max_wh, out, out_idx, out_count, workspace):
+    b, ch, n = pred.shape
+    assert pred.dtype == torch.float32 and pred.is_contiguous()
+    _count("yad_nms")
+    check(lib().yad_nms(_p(pred), b, ch - 4, n, conf_thres, iou_thres, _p(classes_mask), int(agnostic), int(multi_label), max_det, max_nms,
+                        max_wh, _p(out), _p(out_idx), _p(out_count), _p(workspace), stream_ptr()), "yad_nms")
