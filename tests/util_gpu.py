@@ -19,14 +19,14 @@ def from_act(a, c=None):
 
 
 def rel_err(got, ref):
-    """max abs error relative to the mean magnitude of the reference"""
+    """max over elements of |got - ref| / (|ref| + mean|ref|): element-wise relative error with the mean magnitude as the floor"""
     got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
-    return float(np.abs(got - ref).max() / (np.abs(ref).mean() + 1e-12))
+    return float((np.abs(got - ref) / (np.abs(ref) + np.abs(ref).mean() + 1e-12)).max())
 
 
 def tol(dtype):
-    # fp32 kernels: 1e-3 relative (north_star); bf16 storage: 8 mantissa bits -> 2^-8 per rounding, a few roundings per op
-    return 1e-3 if dtype == torch.float32 else 4e-2
+    # fp32 kernels: 1e-3 relative (north_star); bf16 storage: 8 mantissa bits -> 2^-9 relative per rounding, a few roundings per op
+    return 1e-3 if dtype == torch.float32 else 2e-2
 
 
 DTYPES = [torch.float32, torch.bfloat16]

@@ -346,12 +346,12 @@ def forward_model(ctx, img, decode=True, keep_layers=False):
     # neck (HS-FPN): lateral 1x1 * gate + upsampled, fused into the 1x1 conv epilogue (yaml layers 15-18 and 22-25)
     L[11] = ela_hsfpn(ctx, "model.11", L[10], True)
     L[12] = conv(ctx, L[11], P.conv("model.12.weight", "model.12.bias"))
-    L[13] = conv(ctx, L[12], P.conv("model.13.weight", "model.13.bias", transposed=True), mode=ops.CONV_TRANSPOSED)
+    L[13] = conv(ctx, L[12], P.conv("model.13.weight", "model.13.bias", stride=2, transposed=True), mode=ops.CONV_TRANSPOSED)
     L[14] = ela_hsfpn(ctx, "model.14", L[6], True)
     L[16] = ela_hsfpn(ctx, "model.16", L[13], False)
     L[18] = conv(ctx, L[14], P.conv("model.15.weight", "model.15.bias"), mul=L[16], add=L[13])  # Multiply (17) + Add (18)
     L[19] = c3k2(ctx, "model.19", L[18], False, True)
-    L[20] = conv(ctx, L[19], P.conv("model.20.weight", "model.20.bias", transposed=True), mode=ops.CONV_TRANSPOSED)
+    L[20] = conv(ctx, L[19], P.conv("model.20.weight", "model.20.bias", stride=2, transposed=True), mode=ops.CONV_TRANSPOSED)
     L[21] = ela_hsfpn(ctx, "model.21", L[4], True)
     L[23] = ela_hsfpn(ctx, "model.23", L[20], False)
     L[25] = conv(ctx, L[21], P.conv("model.22.weight", "model.22.bias"), mul=L[23], add=L[20])  # Multiply (24) + Add (25)

@@ -79,7 +79,9 @@ class _DetLossFn(torch.autograd.Function):
                                                gt_labels, gt_bboxes, mask_gt, gains, topk, reg_max, True)
         ctx.save_for_backward(gd, gs)
         ctx.aux = aux
-        return out4[3], out4[:3].detach()
+        items = out4[:3].clone()
+        ctx.mark_non_differentiable(items)
+        return out4[3].clone(), items
 
     @staticmethod
     def backward(ctx, g_total, _g_items):
