@@ -1,0 +1,244 @@
+#!/usr/bin/env python
+"""bench.py -- YOLO-AD-Refine inference hot path (forward + fused DFL decode + batched NMS) at 640x640, batch 64 per GPU, bf16.
+
+Contract (see DESIGN.md "Measurement"):  python bench.py --gpus N --steps K --warmup W [--impl reference]
+  value        img/s, whole job, inputs already resident in HBM (CUDA-graph replay of the full hot path), device-timed with CUDA events,
+               max over ranks.
+  e2e          same metric through the public API with HOST buffers: pinned uint8 image batch -> H2D -> hot path -> D2H of the detections,
+               every step inside the timed region.
+  roofline     for the dominant kernel (the implicit-GEMM convolution entry point yad_conv2d): algorithmic FLOPs / CUDA-event time of its
+               launches, measured live in one instrumented eager step, against the measured bf16 peak in MEASURED_PEAKS.json.
+  cpu_baseline the oracle port of the reference's PyTorch path, fp32, all host threads, on a bounded sample (rank 0, N=1 only).
+--impl reference times that same CPU path as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))  # set explicitly, before torch is imported
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "img/s @640^2 b64 fwd+decode+NMS"
+NMS_ARGS = dict(conf_thres=0.25, iou_thres=0.7, max_det=300)
+FLOPS_PER_IMG_640 = 12.44e9  # SURVEY.md section 8d (conv + linear + bmm + DCN + MHA, 2*MAC)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.samples, self._stop, self._t = gpu, [], threading.Event(), None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples if len(s) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (test infrastructure, used here only as the reported baseline / reference arm)
+# ---------------------------------------------------------------------------------------------------------------------------
+def cpu_path_img_per_s(batch, imgsz, reps):
+    from oracle import model as om
+    from oracle import postprocess as op
+    from yolo_ad_refine_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.make_state_dict(seed=1)
+    img = torch.from_numpy(synth.make_images(batch, imgsz, imgsz, seed=2))
+    with torch.inference_mode():
+        best = float("inf")
+        for r in range(reps + 1):  # first pass = warm-up
+            t0 = time.perf_counter()
+            y, _ = om.forward(sd, img)
+            op.non_max_suppression(y.numpy(), **NMS_ARGS)
+            dt = time.perf_counter() - t0
+            if r > 0:
+                best = min(best, dt)
+    return batch / best, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b = 4
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        v, cores = cpu_path_img_per_s(b, args.imgsz, reps=1)
+        vals.append(v)
+    v = float(np.median(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * args.batch / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"YOLO-AD-Refine inference batch {args.batch} at {args.imgsz}x{args.imgsz}, fwd+decode+NMS",
+                                            "sample_batch": b},
+            "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
+                             "sample": f"oracle port (fp32 torch-CPU restatement of the reference path), batch {b} at {args.imgsz}^2, median of {len(vals)}"},
+            "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU")
+    ap.add_argument("--imgsz", type=int, default=640)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-json", default=None, help="write the per-entry-point CUDA-event profile of one eager step here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (impl ours) needs a GPU: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from yolo_ad_refine_b200 import ops, synth
+    from yolo_ad_refine_b200.engine import RefineEngine
+
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    W = max(args.warmup, 3)
+    sd = synth.make_state_dict(seed=1)
+    eng = RefineEngine(sd, batch=args.batch, imgsz=args.imgsz, dtype=dtype, nms_args=NMS_ARGS, input_u8=True)
+    rs = np.random.RandomState(100 + rank)
+    host_u8 = torch.from_numpy(rs.randint(0, 256, (args.batch, 3, args.imgsz, args.imgsz), dtype=np.uint8)).pin_memory()
+    eng.img.copy_(host_u8)
+    eng.step()  # builds weights, warms the allocator, captures the graph
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        for _ in range(W):
+            fn()
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(k):
+            fn()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident throughput (graph replay of forward + decode + NMS)
+    with ClockSampler(local) as clk:
+        ms = timed(eng.step, args.steps)
+    ms_per_step = ms / args.steps
+    value = world * args.batch / (ms_per_step / 1000.0)
+
+    # ---- end to end through the public API: pinned host uint8 -> H2D -> hot path -> D2H of detections and counts
+    det_host = torch.empty((args.batch, NMS_ARGS["max_det"], 6), dtype=torch.float32).pin_memory()
+    cnt_host = torch.empty((args.batch,), dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        eng.img.copy_(host_u8, non_blocking=True)
+        _, _, det, _, count = eng.step()
+        det_host.copy_(det, non_blocking=True)
+        cnt_host.copy_(count, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the detections on the host every step
+
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e = {"value": world * args.batch / (e2e_ms / 1000.0), "unit": "img/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": host_u8.numel(), "d2h_bytes_per_step": det_host.numel() * 4 + cnt_host.numel() * 4}
+
+    # ---- roofline of the dominant kernel: one instrumented eager step, CUDA events around every libyad entry point
+    ops.PROFILE = {}
+    eng._run()
+    torch.cuda.synchronize()
+    prof = {}
+    for name, evs in ops.PROFILE.items():
+        t = sum(s.elapsed_time(e) for s, e, _ in evs)
+        fl = sum(m for _, _, m in evs if m)
+        prof[name] = {"calls": len(evs), "ms": t, "flops": fl}
+    ops.PROFILE = None
+    eager_ms = sum(p["ms"] for p in prof.values())
+    conv = prof["yad_conv2d"]
+    pk = peaks()
+    ach = conv["flops"] / (conv["ms"] / 1000.0) / 1e12
+    roofline = {"kernel": "yad_conv2d (implicit-GEMM convolution, all launches of one step)", "bound": "tensor", "achieved": ach,
+                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None,
+                "peak_source": f"bf16_tflops_sustained of MEASURED_PEAKS.json ({pk['src']})", "launches": conv["calls"],
+                "avg_launch_us": 1000.0 * conv["ms"] / conv["calls"], "share_of_step": conv["ms"] / eager_ms,
+                "whole_step_frac_of_roofline": (args.batch * FLOPS_PER_IMG_640 * (args.imgsz / 640.0) ** 2 / (ms_per_step / 1000.0) / 1e12) / pk["tf_sustained"]}
+    if args.profile_json and rank == 0:
+        json.dump({"eager_ms": eager_ms, "graph_ms_per_step": ms_per_step, "entries": prof}, open(args.profile_json, "w"), indent=1)
+
+    line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"YOLO-AD-Refine (yolo11-701 yaml, scale n) inference batch {args.batch}/GPU at {args.imgsz}x{args.imgsz}, "
+                                   "forward + DFL decode + NMS(conf .25, iou .7, max_det 300), random-init synthetic weights",
+                       "global_batch": world * args.batch, "parallelism": f"batch-sharded replicas x{world}, no collective",
+                       "l2": "inputs + activations of one step (>1 GB) exceed the 126 MB L2; no explicit flush"},
+            "e2e": e2e, "gpu_launches": eng.launches_per_step * args.steps, "launches_per_step": eng.launches_per_step,
+            "clocks": clk.summary(), "roofline": roofline}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores = cpu_path_img_per_s(2, args.imgsz, reps=2)
+            line["cpu_baseline"] = {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
+                                    "sample": f"oracle port (fp32 torch-CPU restatement of the reference path), batch 2 at {args.imgsz}^2, best of 2"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -133,6 +133,9 @@ int yad_patch_filter(const yad_tensor* x, const float* m, float alpha, const voi
 
 /* -- layout conversion: NCHW fp32 image (n,c,h,w) -> NHWC view (channels >= c zero-filled) */
 int yad_nchw_to_nhwc(const float* src, int c_src, const yad_tensor* y, int dtype, void* stream);
+/* uint8 NCHW image batch -> NHWC view, multiplied by `scale` (1/255): the device half of BasePredictor.preprocess
+ * (engine/predictor.py:129-133: H2D of the uint8 batch, .float(), /= 255) */
+int yad_u8_to_nhwc(const uint8_t* src, int c_src, const yad_tensor* y, float scale, int dtype, void* stream);
 
 /* -- a9: fused DFL softmax-expectation + make_anchors + dist2bbox(xywh) + x stride + class sigmoid
  *    (head.py:1181-1204,1236-1252; block.py:78-81; utils/tal.py:303-327).

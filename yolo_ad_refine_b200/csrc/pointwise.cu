@@ -26,6 +26,22 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int c_src, ya
   }
 }
 
+// uint8 NCHW image -> NHWC * scale (the reference does H2D of the uint8 batch and then /255 on the device, engine/predictor.py:129-133)
+template <typename T>
+__global__ void u8_to_nhwc_kernel(const uint8_t* __restrict__ src, int c_src, float scale, yad_tensor y) {
+  int64_t hw = (int64_t)y.h * y.w, total = (int64_t)y.n * hw;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = p / hw, r = p - n * hw;
+    T* o = reinterpret_cast<T*>(y.ptr) + p * y.ld;
+    for (int c0 = 0; c0 < y.c; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = (c0 + i < c_src) ? (float)src[(n * c_src + c0 + i) * hw + r] * scale : 0.f;
+      store8(o + c0, v);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // GroupNorm statistics + apply
 // ------------------------------------------------------------------------------------------------------------------
@@ -627,6 +643,16 @@ int yad_nchw_to_nhwc(const float* src, int c_src, const yad_tensor* y, int dtype
   int64_t total = (int64_t)y->n * y->h * y->w;
   YAD_DISPATCH_DTYPE(dtype, nchw_to_nhwc_kernel<T><<<grid_for(total), TPB, 0, st>>>(src, c_src, *y);)
   YAD_LAUNCH_CHECK("nchw_to_nhwc");
+  return 0;
+}
+
+int yad_u8_to_nhwc(const uint8_t* src, int c_src, const yad_tensor* y, float scale, int dtype, void* stream) {
+  CHECK_VIEW(y, "u8_to_nhwc");
+  YAD_CHECK(c_src <= y->c, "u8_to_nhwc: c_src %d > c %d", c_src, y->c);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = (int64_t)y->n * y->h * y->w;
+  YAD_DISPATCH_DTYPE(dtype, u8_to_nhwc_kernel<T><<<grid_for(total), TPB, 0, st>>>(src, c_src, scale, *y);)
+  YAD_LAUNCH_CHECK("u8_to_nhwc");
   return 0;
 }
 

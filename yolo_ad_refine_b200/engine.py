@@ -12,7 +12,7 @@ from .weights import prepare
 
 class RefineEngine:
     def __init__(self, state_dict, batch, imgsz=640, dtype=torch.bfloat16, device="cuda", nc=80, reg_max=16, strides=(8, 16, 32),
-                 use_graph=True, conv_impl=0, nms_args=None):
+                 use_graph=True, conv_impl=0, nms_args=None, input_u8=False):
         if not torch.cuda.is_available():
             raise RuntimeError("RefineEngine needs a CUDA device: the YOLO-AD-Refine hot path has no CPU fallback")
         ops.lib()  # fail loudly now if libyad.so is missing
@@ -22,7 +22,7 @@ class RefineEngine:
         self.ctx = Fn.Ctx(prepare(state_dict, dtype, self.device), conv_impl)
         self.nms_args = dict(conf_thres=0.25, iou_thres=0.7, max_det=300)
         self.nms_args.update(nms_args or {})
-        self.img = torch.zeros((batch, 3, self.h, self.w), dtype=torch.float32, device=self.device)
+        self.img = torch.zeros((batch, 3, self.h, self.w), dtype=torch.uint8 if input_u8 else torch.float32, device=self.device)
         self.graph = None
         self.launches_per_step = None
         self._out = None

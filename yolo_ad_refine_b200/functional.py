@@ -326,11 +326,14 @@ def ayhead(ctx, p, xs, strides=(8, 16, 32), nc=80, reg_max=16, decode=True):
 # whole model (z-yaml/yolo11-701-YOLO-AD-Refine.yaml at scale n; nn/tasks.py:141-168 _predict_once)
 # --------------------------------------------------------------------------------------------------------------------
 def forward_model(ctx, img, decode=True, keep_layers=False):
-    """img: fp32 (n, 3, H, W) in [0, 1] on the device.  Returns (y, raw_levels[, layer outputs])."""
+    """img: fp32 (n, 3, H, W) in [0, 1], or uint8 (n, 3, H, W) in [0, 255], on the device.  Returns (y, raw_levels[, layer outputs])."""
     n, _, H, W = img.shape
     assert H % 32 == 0 and W % 32 == 0, "image size must be a multiple of the maximum stride 32"
     L = {}
-    x = ops.nchw_to_nhwc(img, ctx.act(n, H, W, 8))
+    if img.dtype == torch.uint8:  # the reference's predictor ships uint8 and divides by 255 on the device (engine/predictor.py:129-133)
+        x = ops.u8_to_nhwc(img, ctx.act(n, H, W, 8))
+    else:
+        x = ops.nchw_to_nhwc(img, ctx.act(n, H, W, 8))
     L[0] = conv_bn_act(ctx, "model.0", x, 2)
     L[1] = conv_bn_act(ctx, "model.1", L[0], 2)
     L[2] = c3k2(ctx, "model.2", L[1])

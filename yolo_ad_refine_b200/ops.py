@@ -19,9 +19,27 @@ LAUNCHES = 0
 _MULTI = {"yad_nms": 6, "yad_tal_assign": 2, "yad_gn_stats": 1}
 
 
+# when set to a dict, every entry point is bracketed by CUDA events on the launching stream: name -> [(start, end, meta), ...]
+PROFILE = None
+
+
 def _count(name):
     global LAUNCHES
     LAUNCHES += _MULTI.get(name, 1)
+
+
+def _call(name, *args, meta=None):
+    """count, optionally time with CUDA events on the current stream, call the C entry point and raise on a non-zero status"""
+    _count(name)
+    fn = getattr(lib(), name)
+    if PROFILE is None:
+        check(fn(*args), name)
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    check(fn(*args), name)
+    e.record()
+    PROFILE.setdefault(name, []).append((s, e, meta))
 
 
 def lib():
@@ -115,82 +133,68 @@ def conv2d(x, w, y, bias=None, kh=1, kw=1, stride=1, pad_h=0, pad_w=0, act=ACT_N
     psp, psld = _ap(pix_scale)
     e = YadEpilogue(None if bias is None else bias.data_ptr(), None if img_scale is None else img_scale.data_ptr(),
                     psp, psld, act, alpha, mp, mld, adp, ald)
-    _count("yad_conv2d")
-    check(lib().yad_conv2d(x.yt(), _p(w), C.byref(d), C.byref(e), y.yt(), dt(x.dtype), stream_ptr()), "yad_conv2d")
+    flops = 2.0 * y.n * y.h * y.w * y.c * kh * kw * x.c if mode != CONV_TRANSPOSED else 2.0 * x.n * x.h * x.w * y.c * kh * kw * x.c
+    _call("yad_conv2d", x.yt(), _p(w), C.byref(d), C.byref(e), y.yt(), dt(x.dtype), stream_ptr(), meta=flops)
     return y
 
 
 def dwconv(x, w, y, bias=None, scale=None, shift=None, k=3, act=ACT_NONE, gate_split=0, add=None):
     adp, ald = _ap(add)
-    _count("yad_dwconv")
-    check(lib().yad_dwconv(x.yt(), _p(w), _p(bias), _p(scale), _p(shift), k, act, gate_split, adp, ald, y.yt(), dt(x.dtype), stream_ptr()),
-          "yad_dwconv")
+    _call("yad_dwconv", x.yt(), _p(w), _p(bias), _p(scale), _p(shift), k, act, gate_split, adp, ald, y.yt(), dt(x.dtype), stream_ptr())
     return y
 
 
 def group_norm(x, y, stats, groups, gamma, beta, eps=1e-5, act=ACT_NONE, add=None):
     """stats: double (n, groups, 2) scratch"""
     L = lib()
-    _count("yad_gn_stats")
-    check(L.yad_gn_stats(x.yt(), groups, _p(stats), dt(x.dtype), stream_ptr()), "yad_gn_stats")
+    _call("yad_gn_stats", x.yt(), groups, _p(stats), dt(x.dtype), stream_ptr())
     adp, ald = _ap(add)
-    _count("yad_gn_apply")
-    check(L.yad_gn_apply(x.yt(), _p(stats), groups, _p(gamma), _p(beta), eps, act, adp, ald, y.yt(), dt(x.dtype), stream_ptr()), "yad_gn_apply")
+    _call("yad_gn_apply", x.yt(), _p(stats), groups, _p(gamma), _p(beta), eps, act, adp, ald, y.yt(), dt(x.dtype), stream_ptr())
     return y
 
 
 def sppf_pool(x, y1, y2, y3):
-    _count("yad_sppf_pool")
-    check(lib().yad_sppf_pool(x.yt(), y1.yt(), y2.yt(), y3.yt(), dt(x.dtype), stream_ptr()), "yad_sppf_pool")
+    _call("yad_sppf_pool", x.yt(), y1.yt(), y2.yt(), y3.yt(), dt(x.dtype), stream_ptr())
 
 
 def gap(x, out):
-    _count("yad_gap")
-    check(lib().yad_gap(x.yt(), _p(out), dt(x.dtype), stream_ptr()), "yad_gap")
+    _call("yad_gap", x.yt(), _p(out), dt(x.dtype), stream_ptr())
     return out
 
 
 def rowcol_mean(x, rows, cols):
-    _count("yad_rowcol_mean")
-    check(lib().yad_rowcol_mean(x.yt(), rows.yt(), cols.yt(), dt(x.dtype), stream_ptr()), "yad_rowcol_mean")
+    _call("yad_rowcol_mean", x.yt(), rows.yt(), cols.yt(), dt(x.dtype), stream_ptr())
 
 
 def rowcol_gate(x, gh, gw, y):
-    _count("yad_rowcol_gate")
-    check(lib().yad_rowcol_gate(None if x is None else x.yt(), gh.yt(), gw.yt(), y.yt(), dt(y.dtype), stream_ptr()), "yad_rowcol_gate")
+    _call("yad_rowcol_gate", None if x is None else x.yt(), gh.yt(), gw.yt(), y.yt(), dt(y.dtype), stream_ptr())
     return y
 
 
 def pool_upsample(x, s, y):
-    _count("yad_pool_upsample")
-    check(lib().yad_pool_upsample(x.yt(), s, y.yt(), dt(x.dtype), stream_ptr()), "yad_pool_upsample")
+    _call("yad_pool_upsample", x.yt(), s, y.yt(), dt(x.dtype), stream_ptr())
     return y
 
 
 def mlca(x, y, w_global, w_local, ksize, local, att, local_size=5, local_weight=0.5, add=None):
     """y = x * MLCA_attention(x) (+ add); local/att: fp32 (n, ls*ls, c) scratch"""
     L = lib()
-    _count("yad_mlca_pool")
-    check(L.yad_mlca_pool(x.yt(), _p(local), local_size, dt(x.dtype), stream_ptr()), "yad_mlca_pool")
-    _count("yad_mlca_att")
-    check(L.yad_mlca_att(_p(local), _p(w_global), _p(w_local), ksize, local_weight, x.n, x.c, local_size, _p(att), stream_ptr()), "yad_mlca_att")
+    _call("yad_mlca_pool", x.yt(), _p(local), local_size, dt(x.dtype), stream_ptr())
+    _call("yad_mlca_att", _p(local), _p(w_global), _p(w_local), ksize, local_weight, x.n, x.c, local_size, _p(att), stream_ptr())
     adp, ald = _ap(add)
-    _count("yad_mlca_apply")
-    check(L.yad_mlca_apply(x.yt(), _p(att), local_size, adp, ald, y.yt(), dt(x.dtype), stream_ptr()), "yad_mlca_apply")
+    _call("yad_mlca_apply", x.yt(), _p(att), local_size, adp, ald, y.yt(), dt(x.dtype), stream_ptr())
     return y
 
 
 def gate_mlp(g, w1, b1, w2, b2, out, kind):
     n, c = g.shape
     hidden, nout = w1.shape[0], w2.shape[0]
-    _count("yad_gate_mlp")
-    check(lib().yad_gate_mlp(_p(g), _p(w1), _p(b1), _p(w2), _p(b2), n, c, hidden, nout, kind, _p(out), stream_ptr()), "yad_gate_mlp")
+    _call("yad_gate_mlp", _p(g), _p(w1), _p(b1), _p(w2), _p(b2), n, c, hidden, nout, kind, _p(out), stream_ptr())
     return out
 
 
 def adt_apply(x, imp, alphas, weight, bias, y):
-    _count("yad_adt_apply")
-    check(lib().yad_adt_apply(x.yt(), _p(imp), _p(alphas), _p(weight), _p(bias), y.yt(), dt(x.dtype), stream_ptr()), "yad_adt_apply")
+    _call("yad_adt_apply", x.yt(), _p(imp), _p(alphas), _p(weight), _p(bias), y.yt(), dt(x.dtype), stream_ptr())
     return y
 
 
@@ -198,40 +202,41 @@ def eltwise(op, a, b, y, c3=None, d4=None, alpha=1.0, beta=1.0, gamma=1.0):
     bp, bld = _ap(b)
     cp, cld = _ap(c3)
     dp, dld = _ap(d4)
-    _count("yad_eltwise")
-    check(lib().yad_eltwise(op, a.yt(), bp, bld, cp, cld, dp, dld, alpha, beta, gamma, y.yt(), dt(a.dtype), stream_ptr()), "yad_eltwise")
+    _call("yad_eltwise", op, a.yt(), bp, bld, cp, cld, dp, dld, alpha, beta, gamma, y.yt(), dt(a.dtype), stream_ptr())
     return y
 
 
 def tssa(qkv, temps, heads, out, tok_offset):
-    _count("yad_tssa")
-    check(lib().yad_tssa(qkv.yt(), _p(temps), heads, out.yt(), tok_offset, dt(qkv.dtype), stream_ptr()), "yad_tssa")
+    _call("yad_tssa", qkv.yt(), _p(temps), heads, out.yt(), tok_offset, dt(qkv.dtype), stream_ptr())
 
 
 def mha(qkv, heads, out):
-    _count("yad_mha")
-    check(lib().yad_mha(qkv.yt(), heads, out.yt(), dt(qkv.dtype), stream_ptr()), "yad_mha")
+    _call("yad_mha", qkv.yt(), heads, out.yt(), dt(qkv.dtype), stream_ptr())
     return out
 
 
 def group_mean(x, s, y):
-    _count("yad_group_mean")
-    check(lib().yad_group_mean(x.yt(), s, y.yt(), dt(x.dtype), stream_ptr()), "yad_group_mean")
+    _call("yad_group_mean", x.yt(), s, y.yt(), dt(x.dtype), stream_ptr())
     return y
 
 
 def patch_filter(x, m, y, alpha=1.0, add=None):
     adp, ald = _ap(add)
-    _count("yad_patch_filter")
-    check(lib().yad_patch_filter(x.yt(), _p(m), alpha, adp, ald, y.yt(), dt(x.dtype), stream_ptr()), "yad_patch_filter")
+    _call("yad_patch_filter", x.yt(), _p(m), alpha, adp, ald, y.yt(), dt(x.dtype), stream_ptr())
+    return y
+
+
+def u8_to_nhwc(img_u8, y, scale=1.0 / 255.0):
+    """img_u8: uint8 (n, c, h, w) contiguous on the device -> y = img * scale, NHWC (engine/predictor.py:129-133: H2D of uint8, then /255)"""
+    assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous()
+    _call("yad_u8_to_nhwc", _p(img_u8), img_u8.shape[1], y.yt(), scale, dt(y.dtype), stream_ptr())
     return y
 
 
 def nchw_to_nhwc(img, y):
     """img: fp32 (n, c, h, w) contiguous"""
     assert img.dtype == torch.float32 and img.is_contiguous()
-    _count("yad_nchw_to_nhwc")
-    check(lib().yad_nchw_to_nhwc(_p(img), img.shape[1], y.yt(), dt(y.dtype), stream_ptr()), "yad_nchw_to_nhwc")
+    _call("yad_nchw_to_nhwc", _p(img), img.shape[1], y.yt(), dt(y.dtype), stream_ptr())
     return y
 
 
@@ -252,8 +257,7 @@ def decode(levels, strides, nc, reg_max, proj, y):
             batch, d = b_, lv.dtype
         assert dtype in (None, d)
         dtype = d
-    _count("yad_decode")
-    check(lib().yad_decode(ptrs, sb, sc, sa, hs, ws, st, nl, batch, nc, reg_max, _p(proj), _p(y), dt(dtype), stream_ptr()), "yad_decode")
+    _call("yad_decode", ptrs, sb, sc, sa, hs, ws, st, nl, batch, nc, reg_max, _p(proj), _p(y), dt(dtype), stream_ptr())
     return y
 
 
@@ -264,6 +268,5 @@ def nms_workspace_bytes(batch, n_anchors, nc, multi_label, max_nms):
 def nms(pred, conf_thres, iou_thres, classes_mask, agnostic, multi_label, max_det, max_nms, max_wh, out, out_idx, out_count, workspace):
     b, ch, n = pred.shape
     assert pred.dtype == torch.float32 and pred.is_contiguous()
-    _count("yad_nms")
-    check(lib().yad_nms(_p(pred), b, ch - 4, n, conf_thres, iou_thres, _p(classes_mask), int(agnostic), int(multi_label), max_det, max_nms,
-                        max_wh, _p(out), _p(out_idx), _p(out_count), _p(workspace), stream_ptr()), "yad_nms")
+    _call("yad_nms", _p(pred), b, ch - 4, n, conf_thres, iou_thres, _p(classes_mask), int(agnostic), int(multi_label), max_det, max_nms,
+                        max_wh, _p(out), _p(out_idx), _p(out_count), _p(workspace), stream_ptr())
