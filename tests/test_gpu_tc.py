@@ -1,0 +1,108 @@
+"""GPU parity for the tcgen05 / TMEM implicit-GEMM convolution (impl=2): first the bare UMMA GEMM self-test (descriptor encodings, swizzled
+staging, TMEM read-back), then every convolution mode against torch fp32 on bf16-rounded inputs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import model as om
+from util_gpu import DEV, from_act, rel_err, to_act
+from yolo_ad_refine_b200 import ops
+from yolo_ad_refine_b200._lib import check
+from yolo_ad_refine_b200.ops import Act
+from yolo_ad_refine_b200.weights import pack_conv
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+TOL = 2e-2
+
+
+def q(x):
+    return x.to(BF).float()
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 16, 64), (128, 64, 64), (256, 128, 128), (300, 80, 72), (1000, 256, 576), (128, 32, 16), (77, 8, 8)])
+def test_umma_gemm_selftest(m, n, k):
+    g = torch.Generator().manual_seed(m + n + k)
+    a, b = q(torch.randn(m, k, generator=g)), q(torch.randn(n, k, generator=g))
+    c = torch.full((m, n), float("nan"), device=DEV)
+    ad, bd = a.to(DEV).to(BF).contiguous(), b.to(DEV).to(BF).contiguous()
+    check(ops.lib().yad_tc_gemm_selftest(C.c_void_p(ad.data_ptr()), C.c_void_p(bd.data_ptr()), C.c_void_p(c.data_ptr()), m, n, k, ops.stream_ptr()),
+          "selftest")
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double().t()
+    err = float((c.cpu().double() - ref).abs().max() / ref.abs().mean())
+    assert err < 1e-4, err  # exact products, fp32 accumulation
+
+
+@pytest.mark.parametrize("cin,cout,k,s,hw", [(8, 16, 3, 2, 32), (16, 8, 3, 1, 20), (48, 64, 1, 1, 20), (128, 64, 3, 1, 10), (64, 32, 3, 2, 40),
+                                             (192, 128, 1, 1, 7), (64, 27, 3, 1, 12), (32, 1, 3, 1, 9), (256, 256, 1, 1, 5), (128, 384, 1, 1, 20),
+                                             (128, 512, 1, 1, 10), (64, 64, 3, 1, 80)])
+def test_conv_tc_bias_silu_add(cin, cout, k, s, hw):
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    x = q(torch.randn(2, cin, hw, hw, generator=g))
+    w = q(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    ho = (hw + 2 * (k // 2) - k) // s + 1
+    add = q(torch.randn(2, cout, ho, ho, generator=g))
+    ref = F.silu(F.conv2d(x, w, b, s, k // 2)) + add
+    cw = pack_conv(w, b, BF, DEV, s)
+    out = Act.empty(2, ho, ho, cw.cout, BF, DEV)
+    ops.conv2d(to_act(x, BF), cw.w, out, bias=cw.b, kh=k, kw=k, stride=s, pad_h=k // 2, pad_w=k // 2, act=ops.ACT_SILU, add=to_act(add, BF), impl=2)
+    assert rel_err(from_act(out, cout), ref) < TOL
+
+
+def test_conv_tc_epilogue_scales_and_concat_slice():
+    g = torch.Generator().manual_seed(5)
+    x = q(torch.randn(3, 64, 12, 9, generator=g))
+    w = q(torch.randn(80, 64, 1, 1, generator=g) / 8)
+    b = torch.randn(80, generator=g) * 0.1
+    img_scale = torch.rand(3, generator=g) + 0.5
+    pix = q(torch.rand(3, 8, 12, 9, generator=g))
+    mul = q(torch.randn(3, 80, 12, 9, generator=g))
+    ref = torch.sigmoid(F.conv2d(x, w) * img_scale.view(3, 1, 1, 1) * pix[:, :1] + b.view(1, -1, 1, 1)) * 0.7 * mul
+    cw = pack_conv(w, b, BF, DEV)
+    wide = Act.empty(3, 12, 9, 144, BF, DEV)
+    wide.buf.zero_()
+    ops.conv2d(to_act(x, BF), cw.w, wide.slice(64, 80), bias=cw.b, act=ops.ACT_SIGMOID, alpha=0.7, img_scale=img_scale.to(DEV),
+               pix_scale=to_act(pix, BF), mul=to_act(mul, BF), impl=2)
+    assert rel_err(from_act(wide)[:, 64:144], ref) < TOL
+    assert float(from_act(wide)[:, :64].abs().max()) == 0.0
+
+
+def test_conv_tc_transposed():
+    g = torch.Generator().manual_seed(6)
+    x = q(torch.randn(2, 32, 7, 9, generator=g))
+    w = q(torch.randn(32, 24, 3, 3, generator=g) / 17)
+    b = torch.randn(24, generator=g) * 0.1
+    ref = F.conv_transpose2d(x, w, b, stride=2, padding=1, output_padding=1)
+    cw = pack_conv(w, b, BF, DEV, transposed=True)
+    out = Act.empty(2, 14, 18, 24, BF, DEV)
+    ops.conv2d(to_act(x, BF), cw.w, out, bias=cw.b, kh=3, kw=3, stride=2, pad_h=1, pad_w=1, mode=ops.CONV_TRANSPOSED, impl=2)
+    assert rel_err(from_act(out), ref) < TOL
+
+
+def test_conv_tc_deformable():
+    g = torch.Generator().manual_seed(7)
+    x = q(torch.randn(2, 64, 10, 12, generator=g))
+    w = q(torch.randn(64, 64, 3, 3, generator=g) / 24)
+    om_ = q(torch.randn(2, 27, 10, 12, generator=g) * 1.5)
+    ref = om.deform_conv3x3(x, om_[:, :18], om_[:, 18:].sigmoid(), w)
+    cw = pack_conv(w, None, BF, DEV)
+    out = Act.empty(2, 10, 12, 64, BF, DEV)
+    ops.conv2d(to_act(x, BF), cw.w, out, kh=3, kw=3, pad_h=1, pad_w=1, mode=ops.CONV_DEFORM, offmask=to_act(om_, BF), impl=2)
+    assert rel_err(from_act(out), ref) < 3e-2  # the bilinear blend is rounded to bf16 before the MMA
+
+
+def test_conv_tc_7x1():
+    g = torch.Generator().manual_seed(8)
+    v = q(torch.randn(4, 128, 20, generator=g))
+    w = q(torch.randn(128, 128, 7, generator=g) / 30)
+    b = torch.randn(128, generator=g) * 0.1
+    ref = F.conv1d(v, w, b, padding=3)
+    cw = pack_conv(w[:, :, :, None], b, BF, DEV)
+    out = Act.empty(4, 20, 1, 128, BF, DEV)
+    ops.conv2d(to_act(v[:, :, :, None], BF), cw.w, out, bias=cw.b, kh=7, kw=1, pad_h=3, pad_w=0, impl=2)
+    assert rel_err(from_act(out)[:, :, :, 0], ref) < TOL

@@ -1,13 +1,458 @@
-// tcgen05 / TMEM implicit-GEMM convolution (placeholder until the UMMA path lands: reports "unsupported" so that the dispatcher
-// keeps every shape on the SIMT kernel).
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
+//
+// GEMM view per launch:  D[128 pixels][N_TILE couts] += A[128][64] * B[N_TILE][64]^T  per 64-wide K chunk, K = taps * cin.
+//   * A (im2col rows) and B (weights) are staged in shared memory in the canonical K-major SWIZZLE_128B layout (row = 128 B, 16-byte
+//     chunk c of row r stored at chunk position c ^ (r & 7); tile base 1024-byte aligned) -- the layout a SWIZZLE_128B TMA box would
+//     produce -- by 128 producer threads (one output pixel each, 128-bit loads, zero-fill for padding / ragged edges / K tail),
+//     made visible to the tensor core with fence.proxy.async, and handed over through a ring of mbarriers.
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x N_TILE x 16) and commits to the "slot empty" /
+//     "accumulator full" mbarriers (tcgen05.commit).
+//   * the 128 producer threads then become the epilogue: tcgen05.ld (32 lanes x 32 bit x 16 columns per warp), fused
+//     bias / per-image / per-pixel scale / activation / alpha / mul / add, 128-bit bf16 stores into the (possibly channel-sliced) output.
+// Modes: normal (1x1, 3x3, 7x1; stride 1 or 2), transposed 3x3 s2 (4 sub-pixel phases, each a dense GEMM over the input grid), and
+// modulated deformable 3x3 (bilinear gather in the producer).
+#include <cuda.h>
+
 #include "common.cuh"
 
-int yad_conv2d_tc_supported(const yad_tensor*, const yad_conv_desc*, const yad_tensor*) { return 0; }
-int yad_conv2d_tc(const yad_tensor*, const void*, const yad_conv_desc*, const yad_epilogue*, const yad_tensor*, void*) {
-  yad_set_error("conv2d: tcgen05 path not built");
+namespace {
+
+constexpr int BM = 128;  // UMMA M (pixels per CTA)
+constexpr int BK = 64;   // K elements per stage (= 128 bytes of bf16 = one swizzle row)
+constexpr int MAX_TAPS = 9;
+constexpr int NPROD = 128;         // producer / epilogue threads (warps 0-3)
+constexpr int NTHREADS = NPROD + 32;  // + the MMA warp
+
+struct TcParams {
+  const bf16* x;
+  const bf16* w;
+  const bf16* om;
+  void* y;
+  int n, hi, wi, cin, x_ld;
+  int hm, wm;  // logical pixel grid per image that the M index enumerates
+  int ho, wo, cout, y_ld;
+  int stride;      // source pixel = stride * m + dy[tap]
+  int os, py, px;  // destination pixel = os * m + py
+  int ntaps;
+  int dy[MAX_TAPS], dx[MAX_TAPS], wtap[MAX_TAPS];
+  int w_row;  // elements per weight row (all taps * cin)
+  int deform, om_ld;
+  int n_tile, stages, tmem_cols;
+  int out_f32;
+  yad_epilogue e;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; spin++) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();  // a protocol bug must fault, never hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO(16 B) << 16 | SBO(1024 B) << 32 |
+// version 1 << 46 | layout SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b_format BF16 (1) @7/@10, K-major A and B, N >> 3 @17, M >> 4 @24
+__device__ __forceinline__ uint32_t make_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
+
+__device__ __forceinline__ uint4 ldg16(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void sts16(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void bf8_to_f(const uint4& u, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ uint4 f_to_bf8(const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  return u;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool DEFORM>
+__global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // carve: [1024-aligned] stages x (A 16 KB + B n_tile*128 B), then barriers
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t a_bytes = BM * 128, b_bytes = (uint32_t)p.n_tile * 128;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t bars = base + p.stages * stage_bytes;  // full[stages], empty[stages], tmem_full, tmem_ptr
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (p.stages + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * p.stages);
+  const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int K = p.ntaps * p.cin;
+  const int nk = (K + BK - 1) / BK;
+  const int n0 = blockIdx.y * p.n_tile;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), NPROD); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp < 4) {
+    // ================= producer: this thread owns A row `tid` and B rows tid, tid + 128 =================
+    const int64_t M = (int64_t)p.n * p.hm * p.wm;
+    const int64_t m = (int64_t)blockIdx.x * BM + tid;
+    const bool mvalid = m < M;
+    int img = 0, my = 0, mx = 0;
+    if (mvalid) {
+      img = (int)(m / ((int64_t)p.hm * p.wm));
+      int r = (int)(m - (int64_t)img * p.hm * p.wm);
+      my = r / p.wm;
+      mx = r - my * p.wm;
+    }
+    const int swz = tid & 7;
+    const bool fast = (p.cin % BK) == 0;  // every 64-wide K chunk lies inside one tap
+    for (int kc = 0; kc < nk; kc++) {
+      const int s = kc % p.stages;
+      const uint32_t ph = (uint32_t)(kc / p.stages) & 1u;
+      const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
+      const int k0 = kc * BK;
+      // ---- A: gather into registers first (global latency overlaps the wait for the slot)
+      uint4 av[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) av[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (mvalid) {
+        if (!DEFORM) {
+          if (fast) {
+            const int t = k0 / p.cin, ci = k0 - t * p.cin;
+            const int sy = p.stride * my + p.dy[t], sx = p.stride * mx + p.dx[t];
+            if (sy >= 0 && sy < p.hi && sx >= 0 && sx < p.wi) {
+              const bf16* src = p.x + ((int64_t)(img * p.hi + sy) * p.wi + sx) * p.x_ld + ci;
+#pragma unroll
+              for (int j = 0; j < 8; j++) av[j] = ldg16(src + j * 8);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const int kk = k0 + j * 8;
+              if (kk < K) {
+                const int t = kk / p.cin, ci = kk - t * p.cin;
+                const int sy = p.stride * my + p.dy[t], sx = p.stride * mx + p.dx[t];
+                if (sy >= 0 && sy < p.hi && sx >= 0 && sx < p.wi) av[j] = ldg16(p.x + ((int64_t)(img * p.hi + sy) * p.wi + sx) * p.x_ld + ci);
+              }
+            }
+          }
+        } else {
+          // modulated deformable 3x3 (stride 1, pad 1): bilinear sample, zero outside (-1, H) x (-1, W); cin % 64 == 0 here
+          const int t = k0 / p.cin, ci = k0 - t * p.cin;
+          const bf16* o = p.om + ((int64_t)(img * p.ho + my) * p.wo + mx) * p.om_ld;
+          const float ody = __bfloat162float(o[2 * t]), odx = __bfloat162float(o[2 * t + 1]);
+          const float mk = sigmoidf_(__bfloat162float(o[18 + t]));
+          const float fy_ = (float)(my + p.dy[t]) + ody, fx_ = (float)(mx + p.dx[t]) + odx;
+          if (fy_ > -1.f && fx_ > -1.f && fy_ < (float)p.hi && fx_ < (float)p.wi) {
+            const float fy = floorf(fy_), fx = floorf(fx_);
+            const int y0 = (int)fy, x0 = (int)fx;
+            const float ly = fy_ - fy, lx = fx_ - fx;
+            const float wgt[4] = {(1.f - ly) * (1.f - lx) * mk, (1.f - ly) * lx * mk, ly * (1.f - lx) * mk, ly * lx * mk};
+            float acc[8][8];
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+#pragma unroll
+              for (int i = 0; i < 8; i++) acc[j][i] = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; c4++) {
+              const int yy = y0 + (c4 >> 1), xx = x0 + (c4 & 1);
+              if (yy >= 0 && yy < p.hi && xx >= 0 && xx < p.wi) {
+                const bf16* src = p.x + ((int64_t)(img * p.hi + yy) * p.wi + xx) * p.x_ld + ci;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                  float v[8];
+                  bf8_to_f(ldg16(src + j * 8), v);
+#pragma unroll
+                  for (int i = 0; i < 8; i++) acc[j][i] = fmaf(wgt[c4], v[i], acc[j][i]);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) av[j] = f_to_bf8(acc[j]);
+          }
+        }
+      }
+      mbar_wait(empty_bar(s), ph ^ 1u);
+#pragma unroll
+      for (int j = 0; j < 8; j++) sts16(a_s + tid * 128 + ((j ^ swz) << 4), av[j]);
+      // ---- B: weight rows (L2 resident)
+      for (int row = tid; row < p.n_tile; row += NPROD) {
+        const int co = n0 + row;
+        uint4 bv[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) bv[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (co < p.cout) {
+          const bf16* wr = p.w + (int64_t)co * p.w_row;
+          if (fast) {
+            const int t = k0 / p.cin, ci = k0 - t * p.cin;
+            const bf16* src = wr + p.wtap[t] * p.cin + ci;
+#pragma unroll
+            for (int j = 0; j < 8; j++) bv[j] = ldg16(src + j * 8);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const int kk = k0 + j * 8;
+              if (kk < K) {
+                const int t = kk / p.cin, ci = kk - t * p.cin;
+                bv[j] = ldg16(wr + p.wtap[t] * p.cin + ci);
+              }
+            }
+          }
+        }
+        const int sw = row & 7;
+#pragma unroll
+        for (int j = 0; j < 8; j++) sts16(b_s + row * 128 + ((j ^ sw) << 4), bv[j]);
+      }
+      fence_proxy_async();
+      mbar_arrive(full_bar(s));
+    }
+
+    // ================= epilogue: TMEM lane = row; this warp reads lanes [32 * warp, 32 * warp + 32) =================
+    mbar_wait(tmem_full_bar, 0u);
+    tc_fence_after();
+    int64_t dpix = 0;
+    if (mvalid) dpix = ((int64_t)(img * p.ho + p.os * my + p.py)) * p.wo + (p.os * mx + p.px);
+    const yad_epilogue& e = p.e;
+    float sc = 1.0f;
+    if (mvalid) {
+      if (e.img_scale) sc = e.img_scale[img];
+      if (e.pix_scale) sc *= __bfloat162float(reinterpret_cast<const bf16*>(e.pix_scale)[dpix * e.pix_scale_ld]);
+    }
+    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + lane_base + (uint32_t)c0, r);  // warp-collective: executed by all lanes, valid row or not
+      const int co = n0 + c0;
+      if (!mvalid || co >= p.cout) continue;
+      if (p.out_f32) {
+        float* dst = reinterpret_cast<float*>(p.y) + dpix * p.y_ld + co;
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+          if (co + i < p.cout) dst[i] = __uint_as_float(r[i]);
+        continue;
+      }
+#pragma unroll
+      for (int hlf = 0; hlf < 2; hlf++) {
+        const int c = co + hlf * 8;
+        if (c >= p.cout) break;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[hlf * 8 + i]) * sc;
+        if (e.bias) {
+          const float4 b0 = *reinterpret_cast<const float4*>(e.bias + c), b1 = *reinterpret_cast<const float4*>(e.bias + c + 4);
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = apply_act(v[i], e.act) * e.alpha;
+        if (e.mul) {
+          float mv[8];
+          bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.mul) + dpix * e.mul_ld + c), mv);
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] *= mv[i];
+        }
+        if (e.add) {
+          float adv[8];
+          bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.add) + dpix * e.add_ld + c), adv);
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] += adv[i];
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.y) + dpix * p.y_ld + c) = f_to_bf8(v);
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ================= MMA issuer: one elected thread =================
+    if ((tid & 31) == 0) {
+      const uint32_t idesc = make_idesc(p.n_tile);
+      for (int kc = 0; kc < nk; kc++) {
+        const int s = kc % p.stages;
+        const uint32_t ph = (uint32_t)(kc / p.stages) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
+        const uint64_t ad = make_sdesc(a_s), bd = make_sdesc(b_s);
+#pragma unroll
+        for (int k = 0; k < BK / 16; k++)  // advance 32 bytes (>> 4 = 2) along K inside the 128-byte swizzle row
+          umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+        umma_commit(empty_bar(s));  // implies tcgen05.fence::before_thread_sync
+      }
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+int pick_n_tile(int cout) {
+  int c16 = (cout + 15) / 16 * 16;
+  if (c16 <= 256) return c16;
+  // split evenly into tiles of at most 256 channels (multiples of 16)
+  int tiles = (c16 + 255) / 256;
+  int nt = ((c16 + tiles - 1) / tiles + 15) / 16 * 16;
+  return nt;
+}
+
+int launch(TcParams& p, int64_t M, cudaStream_t st) {
+  p.n_tile = pick_n_tile(p.cout);
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.n_tile) p.tmem_cols <<= 1;
+  const int stage_bytes = BM * 128 + p.n_tile * 128;
+  const int K = p.ntaps * p.cin, nk = (K + BK - 1) / BK;
+  int stages = (96 * 1024) / stage_bytes;
+  stages = stages > 4 ? 4 : (stages < 2 ? 2 : stages);
+  if (stages > nk) stages = nk < 1 ? 1 : nk;
+  p.stages = stages;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + 8 * (2 * stages + 1) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+      yad_set_error("conv2d_tc: cannot raise the dynamic shared memory limit");
+      return 2;
+    }
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((p.cout + p.n_tile - 1) / p.n_tile));
+  if (p.deform)
+    conv_tc_kernel<true><<<grid, NTHREADS, smem, st>>>(p);
+  else
+    conv_tc_kernel<false><<<grid, NTHREADS, smem, st>>>(p);
+  YAD_LAUNCH_CHECK("conv2d_tc");
+  return 0;
+}
+
+}  // namespace
+
+int yad_conv2d_tc_supported(const yad_tensor* x, const yad_conv_desc* d, const yad_tensor* y) {
+  if (x->c % 8 || x->ld % 8 || y->c % 8 || y->ld % 8) return 0;
+  if (((uintptr_t)x->ptr & 15) || ((uintptr_t)y->ptr & 15)) return 0;
+  if (d->kh * d->kw > MAX_TAPS) return 0;
+  if (d->mode == YAD_CONV_DEFORM && (x->c % BK) != 0) return 0;
   return 1;
 }
-extern "C" int yad_tc_gemm_selftest(const void*, const void*, float*, int, int, int, void*) {
-  yad_set_error("tc_gemm_selftest: tcgen05 path not built");
-  return 1;
+
+int yad_conv2d_tc(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream) {
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = (const bf16*)x->ptr; p.w = (const bf16*)w; p.om = (const bf16*)d->offmask; p.y = y->ptr;
+  p.n = x->n; p.hi = x->h; p.wi = x->w; p.cin = x->c; p.x_ld = x->ld;
+  p.ho = y->h; p.wo = y->w; p.cout = y->c; p.y_ld = y->ld;
+  p.w_row = d->kh * d->kw * x->c;
+  p.om_ld = d->offmask_ld;
+  p.e = *e;
+  YAD_CHECK(x->n == y->n, "conv2d: batch mismatch %d vs %d", x->n, y->n);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->mode == YAD_CONV_NORMAL || d->mode == YAD_CONV_DEFORM) {
+    if (d->mode == YAD_CONV_NORMAL) {
+      YAD_CHECK(y->h == (x->h + 2 * d->pad_h - d->kh) / d->stride + 1 && y->w == (x->w + 2 * d->pad_w - d->kw) / d->stride + 1,
+                "conv2d: output shape %dx%d does not match input %dx%d k%dx%d s%d p%d,%d", y->h, y->w, x->h, x->w, d->kh, d->kw, d->stride,
+                d->pad_h, d->pad_w);
+    } else {
+      YAD_CHECK(d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad_h == 1 && d->pad_w == 1 && y->h == x->h && y->w == x->w && d->offmask,
+                "conv2d: deformable mode is 3x3 s1 p1 with an offset/mask view");
+      p.deform = 1;
+    }
+    p.hm = y->h; p.wm = y->w; p.stride = d->stride; p.os = 1; p.py = 0; p.px = 0;
+    p.ntaps = d->kh * d->kw;
+    for (int t = 0; t < p.ntaps; t++) { p.dy[t] = t / d->kw - d->pad_h; p.dx[t] = t % d->kw - d->pad_w; p.wtap[t] = t; }
+    return launch(p, (int64_t)x->n * p.hm * p.wm, st);
+  }
+  if (d->mode == YAD_CONV_TRANSPOSED) {
+    YAD_CHECK(d->kh == 3 && d->kw == 3 && d->stride == 2 && d->pad_h == 1 && d->pad_w == 1 && y->h == 2 * x->h && y->w == 2 * x->w,
+              "conv2d: transposed mode is k3 s2 p1 op1 only");
+    // oy = 2*iy - 1 + ky: even rows take ky = 1 (iy = m); odd rows take ky = 0 (iy = m + 1) and ky = 2 (iy = m)
+    p.hm = x->h; p.wm = x->w; p.stride = 1; p.os = 2;
+    for (int py = 0; py < 2; py++)
+      for (int px = 0; px < 2; px++) {
+        p.py = py; p.px = px; p.ntaps = 0;
+        for (int ky = 0; ky < 3; ky++) {
+          if (((py + 1 - ky) & 1) != 0) continue;
+          for (int kx = 0; kx < 3; kx++) {
+            if (((px + 1 - kx) & 1) != 0) continue;
+            p.dy[p.ntaps] = (py + 1 - ky) / 2; p.dx[p.ntaps] = (px + 1 - kx) / 2; p.wtap[p.ntaps] = ky * 3 + kx;
+            p.ntaps++;
+          }
+        }
+        int r = launch(p, (int64_t)x->n * p.hm * p.wm, st);
+        if (r) return r;
+      }
+    return 0;
+  }
+  YAD_CHECK(false, "conv2d: bad mode %d", d->mode);
+}
+
+// C[M][N] (fp32) = A[M][K] (bf16 row-major) x B[N][K]^T (bf16) through the UMMA/TMEM path: validates the descriptor encodings, the
+// swizzled staging and the TMEM read-back independently of the convolution address logic.
+extern "C" int yad_tc_gemm_selftest(const void* a, const void* b, float* c, int m, int n, int k, void* stream) {
+  YAD_CHECK(k % 8 == 0 && n % 8 == 0, "tc_gemm_selftest: k and n must be multiples of 8");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = (const bf16*)a; p.w = (const bf16*)b; p.y = c;
+  p.n = 1; p.hi = m; p.wi = 1; p.cin = k; p.x_ld = k;
+  p.hm = m; p.wm = 1; p.ho = m; p.wo = 1; p.cout = n; p.y_ld = n;
+  p.stride = 1; p.os = 1; p.ntaps = 1; p.w_row = k; p.out_f32 = 1;
+  p.e.alpha = 1.0f;
+  return launch(p, m, (cudaStream_t)stream);
 }
