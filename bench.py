@@ -207,8 +207,10 @@ def main():
     prof = {}
     for name, evs in ops.PROFILE.items():
         t = sum(s.elapsed_time(e) for s, e, _ in evs)
-        fl = sum(m for _, _, m in evs if m)
+        fl = sum(m["flops"] for _, _, m in evs if m)
         prof[name] = {"calls": len(evs), "ms": t, "flops": fl}
+        if name == "yad_conv2d":
+            prof[name]["per_call"] = [dict(m, ms=s.elapsed_time(e)) for s, e, m in evs]
     ops.PROFILE = None
     eager_ms = sum(p["ms"] for p in prof.values())
     conv = prof["yad_conv2d"]

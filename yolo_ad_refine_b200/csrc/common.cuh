@@ -95,6 +95,37 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
+// fast variants for the fused epilogues (ex2.approx / rcp.approx: ~2 ulp, far below bf16 and the 1e-3 fp32 bound) with the activation
+// switch hoisted out of the element loop: one warp-uniform branch per N values instead of one per value
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+template <int N>
+__device__ __forceinline__ void apply_act_n(float (&v)[N], int act) {
+  switch (act) {
+    case YAD_ACT_SILU:
+#pragma unroll
+      for (int i = 0; i < N; i++) v[i] = v[i] * sigmoid_fast(v[i]);
+      break;
+    case YAD_ACT_RELU:
+#pragma unroll
+      for (int i = 0; i < N; i++) v[i] = fmaxf(v[i], 0.0f);
+      break;
+    case YAD_ACT_SIGMOID:
+#pragma unroll
+      for (int i = 0; i < N; i++) v[i] = sigmoid_fast(v[i]);
+      break;
+    case YAD_ACT_GELU:
+#pragma unroll
+      for (int i = 0; i < N; i++) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752440f));
+      break;
+    case YAD_ACT_HARDSWISH:
+#pragma unroll
+      for (int i = 0; i < N; i++) v[i] = v[i] * fminf(fmaxf(v[i] + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f);
+      break;
+    default:
+      break;
+  }
+}
+
 // ---- reductions ------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -140,7 +171,10 @@ __device__ __forceinline__ void epilogue4(float (&acc)[4], const yad_epilogue& e
     b[0] = bb.x; b[1] = bb.y; b[2] = bb.z; b[3] = bb.w;
   }
 #pragma unroll
-  for (int i = 0; i < 4; i++) acc[i] = apply_act(acc[i] * s + b[i], e.act) * e.alpha;
+  for (int i = 0; i < 4; i++) acc[i] = acc[i] * s + b[i];
+  apply_act_n<4>(acc, e.act);
+#pragma unroll
+  for (int i = 0; i < 4; i++) acc[i] *= e.alpha;
   if (e.mul) {
     float m[4];
     load4(reinterpret_cast<const T*>(e.mul) + pix * e.mul_ld + co, m);

@@ -3,7 +3,7 @@
 // GEMM view per launch:  D[128 pixels][N_TILE couts] += A[128][64] * B[N_TILE][64]^T  per 64-wide K chunk, K = taps * cin.
 //   * A (im2col rows) and B (weights) are staged in shared memory in the canonical K-major SWIZZLE_128B layout (row = 128 B, 16-byte
 //     chunk c of row r stored at chunk position c ^ (r & 7); tile base 1024-byte aligned) -- the layout a SWIZZLE_128B TMA box would
-//     produce -- by 128 producer threads (one output pixel each, 128-bit loads, zero-fill for padding / ragged edges / K tail),
+//     produce -- by 128 producer threads (8 lanes sweep one 128-byte row: coalesced 128-bit loads, zero-fill for padding / ragged edges / K tail),
 //     made visible to the tensor core with fence.proxy.async, and handed over through a ring of mbarriers.
 //   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x N_TILE x 16) and commits to the "slot empty" /
 //     "accumulator full" mbarriers (tcgen05.commit).
@@ -37,7 +37,7 @@ struct TcParams {
   int dy[MAX_TAPS], dx[MAX_TAPS], wtap[MAX_TAPS];
   int w_row;  // elements per weight row (all taps * cin)
   int deform, om_ld;
-  int n_tile, stages, tmem_cols;
+  int n_tile, stages, tmem_cols, pipe_bytes;
   int out_f32;
   yad_epilogue e;
 };
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t a_bytes = BM * 128, b_bytes = (uint32_t)p.n_tile * 128;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  const uint32_t bars = base + p.stages * stage_bytes;  // full[stages], empty[stages], tmem_full, tmem_ptr
+  const uint32_t bars = base + (uint32_t)p.pipe_bytes;  // full[stages], empty[stages], tmem_full, tmem_ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (p.stages + s); };
   const uint32_t tmem_full_bar = bars + 8u * (2 * p.stages);
@@ -150,53 +150,49 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   if (warp < 4) {
-    // ================= producer: this thread owns A row `tid` and B rows tid, tid + 128 =================
+    // ================= producer =================
+    // Coalesced gather: lane l of warp w handles the 16-byte chunk c = l & 7 of rows 32w + 4i + (l >> 3), i = 0..7, so one warp
+    // instruction reads 4 rows x 128 contiguous bytes (4 L1 wavefronts instead of 32) and writes 4 conflict-free swizzled smem rows.
     const int64_t M = (int64_t)p.n * p.hm * p.wm;
-    const int64_t m = (int64_t)blockIdx.x * BM + tid;
-    const bool mvalid = m < M;
-    int img = 0, my = 0, mx = 0;
-    if (mvalid) {
-      img = (int)(m / ((int64_t)p.hm * p.wm));
-      int r = (int)(m - (int64_t)img * p.hm * p.wm);
-      my = r / p.wm;
-      mx = r - my * p.wm;
+    const int lane = tid & 31, sr = lane >> 3, c = lane & 7;
+    int rimg[8], ryx[8];  // per owned row: image index (-1 = beyond M) and (my << 16 | mx)
+    {
+      // decode the first owned row with 32-bit divisions, then step by 4 pixels with carries (M < 2^31 is checked by the launcher)
+      const uint32_t m0 = (uint32_t)blockIdx.x * BM + warp * 32 + sr, hw = (uint32_t)(p.hm * p.wm);
+      int img = (int)(m0 / hw);
+      const uint32_t r = m0 - (uint32_t)img * hw;
+      int my = (int)(r / (uint32_t)p.wm), mx = (int)(r - (uint32_t)my * (uint32_t)p.wm);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const bool ok = (int64_t)m0 + 4 * i < M;
+        rimg[i] = ok ? img : -1;
+        ryx[i] = (my << 16) | mx;
+        mx += 4;
+        while (mx >= p.wm) { mx -= p.wm; my++; }
+        while (my >= p.hm) { my -= p.hm; img++; }
+      }
     }
-    const int swz = tid & 7;
-    const bool fast = (p.cin % BK) == 0;  // every 64-wide K chunk lies inside one tap
     for (int kc = 0; kc < nk; kc++) {
       const int s = kc % p.stages;
       const uint32_t ph = (uint32_t)(kc / p.stages) & 1u;
       const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
-      const int k0 = kc * BK;
+      const int kk = kc * BK + c * 8;  // this thread's K offset inside the chunk: fixed tap / channel for all its rows
+      const bool kvalid = kk < K;
+      const int t = kvalid ? kk / p.cin : 0;
+      const int ci = kk - t * p.cin;
       // ---- A: gather into registers first (global latency overlaps the wait for the slot)
       uint4 av[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) av[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (mvalid) {
+      for (int i = 0; i < 8; i++) {
+        av[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (!kvalid || rimg[i] < 0) continue;
+        const int my = ryx[i] >> 16, mx = ryx[i] & 0xFFFF;
         if (!DEFORM) {
-          if (fast) {
-            const int t = k0 / p.cin, ci = k0 - t * p.cin;
-            const int sy = p.stride * my + p.dy[t], sx = p.stride * mx + p.dx[t];
-            if (sy >= 0 && sy < p.hi && sx >= 0 && sx < p.wi) {
-              const bf16* src = p.x + ((int64_t)(img * p.hi + sy) * p.wi + sx) * p.x_ld + ci;
-#pragma unroll
-              for (int j = 0; j < 8; j++) av[j] = ldg16(src + j * 8);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const int kk = k0 + j * 8;
-              if (kk < K) {
-                const int t = kk / p.cin, ci = kk - t * p.cin;
-                const int sy = p.stride * my + p.dy[t], sx = p.stride * mx + p.dx[t];
-                if (sy >= 0 && sy < p.hi && sx >= 0 && sx < p.wi) av[j] = ldg16(p.x + ((int64_t)(img * p.hi + sy) * p.wi + sx) * p.x_ld + ci);
-              }
-            }
-          }
+          const int sy = p.stride * my + p.dy[t], sx = p.stride * mx + p.dx[t];
+          if (sy >= 0 && sy < p.hi && sx >= 0 && sx < p.wi) av[i] = ldg16(p.x + ((int64_t)(rimg[i] * p.hi + sy) * p.wi + sx) * p.x_ld + ci);
         } else {
-          // modulated deformable 3x3 (stride 1, pad 1): bilinear sample, zero outside (-1, H) x (-1, W); cin % 64 == 0 here
-          const int t = k0 / p.cin, ci = k0 - t * p.cin;
-          const bf16* o = p.om + ((int64_t)(img * p.ho + my) * p.wo + mx) * p.om_ld;
+          // modulated deformable 3x3 (stride 1, pad 1): bilinear sample, zero outside (-1, H) x (-1, W)
+          const bf16* o = p.om + ((int64_t)(rimg[i] * p.ho + my) * p.wo + mx) * p.om_ld;
           const float ody = __bfloat162float(o[2 * t]), odx = __bfloat162float(o[2 * t + 1]);
           const float mk = sigmoidf_(__bfloat162float(o[18 + t]));
           const float fy_ = (float)(my + p.dy[t]) + ody, fx_ = (float)(mx + p.dx[t]) + odx;
@@ -205,115 +201,132 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
             const int y0 = (int)fy, x0 = (int)fx;
             const float ly = fy_ - fy, lx = fx_ - fx;
             const float wgt[4] = {(1.f - ly) * (1.f - lx) * mk, (1.f - ly) * lx * mk, ly * (1.f - lx) * mk, ly * lx * mk};
-            float acc[8][8];
+            float acc[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-#pragma unroll
-              for (int i = 0; i < 8; i++) acc[j][i] = 0.f;
+            for (int q = 0; q < 8; q++) acc[q] = 0.f;
 #pragma unroll
             for (int c4 = 0; c4 < 4; c4++) {
               const int yy = y0 + (c4 >> 1), xx = x0 + (c4 & 1);
               if (yy >= 0 && yy < p.hi && xx >= 0 && xx < p.wi) {
-                const bf16* src = p.x + ((int64_t)(img * p.hi + yy) * p.wi + xx) * p.x_ld + ci;
+                float v[8];
+                bf8_to_f(ldg16(p.x + ((int64_t)(rimg[i] * p.hi + yy) * p.wi + xx) * p.x_ld + ci), v);
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                  float v[8];
-                  bf8_to_f(ldg16(src + j * 8), v);
-#pragma unroll
-                  for (int i = 0; i < 8; i++) acc[j][i] = fmaf(wgt[c4], v[i], acc[j][i]);
-                }
+                for (int q = 0; q < 8; q++) acc[q] = fmaf(wgt[c4], v[q], acc[q]);
               }
             }
-#pragma unroll
-            for (int j = 0; j < 8; j++) av[j] = f_to_bf8(acc[j]);
+            av[i] = f_to_bf8(acc);
           }
         }
       }
       mbar_wait(empty_bar(s), ph ^ 1u);
 #pragma unroll
-      for (int j = 0; j < 8; j++) sts16(a_s + tid * 128 + ((j ^ swz) << 4), av[j]);
-      // ---- B: weight rows (L2 resident)
-      for (int row = tid; row < p.n_tile; row += NPROD) {
-        const int co = n0 + row;
-        uint4 bv[8];
+      for (int i = 0; i < 8; i++) {
+        const int r = warp * 32 + 4 * i + sr;
+        sts16(a_s + r * 128 + ((c ^ (r & 7)) << 4), av[i]);
+      }
+      // ---- B: weight rows (L2 resident), 16 rows per pass over the 4 warps
+      const int64_t woff = (int64_t)p.wtap[t] * p.cin + ci;
+      for (int r0 = 0; r0 < p.n_tile; r0 += 64) {
+        uint4 bv[4];
 #pragma unroll
-        for (int j = 0; j < 8; j++) bv[j] = make_uint4(0u, 0u, 0u, 0u);
-        if (co < p.cout) {
-          const bf16* wr = p.w + (int64_t)co * p.w_row;
-          if (fast) {
-            const int t = k0 / p.cin, ci = k0 - t * p.cin;
-            const bf16* src = wr + p.wtap[t] * p.cin + ci;
-#pragma unroll
-            for (int j = 0; j < 8; j++) bv[j] = ldg16(src + j * 8);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const int kk = k0 + j * 8;
-              if (kk < K) {
-                const int t = kk / p.cin, ci = kk - t * p.cin;
-                bv[j] = ldg16(wr + p.wtap[t] * p.cin + ci);
-              }
-            }
-          }
+        for (int j = 0; j < 4; j++) {
+          const int row = r0 + 16 * j + 4 * warp + sr, co = n0 + row;
+          bv[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (kvalid && row < p.n_tile && co < p.cout) bv[j] = ldg16(p.w + (int64_t)co * p.w_row + woff);
         }
-        const int sw = row & 7;
 #pragma unroll
-        for (int j = 0; j < 8; j++) sts16(b_s + row * 128 + ((j ^ sw) << 4), bv[j]);
+        for (int j = 0; j < 4; j++) {
+          const int row = r0 + 16 * j + 4 * warp + sr;
+          if (row < p.n_tile) sts16(b_s + row * 128 + ((c ^ (row & 7)) << 4), bv[j]);
+        }
       }
       fence_proxy_async();
       mbar_arrive(full_bar(s));
     }
 
-    // ================= epilogue: TMEM lane = row; this warp reads lanes [32 * warp, 32 * warp + 32) =================
+    // ================= epilogue =================
+    // phase 1 (thread = TMEM lane = tile row): tcgen05.ld 16 columns at a time, scale / bias / activation / alpha, park fp32 in a per-warp
+    // smem staging tile; phase 2 (lanes sweep each row contiguously): mul / add / convert, 128-bit coalesced stores.
     mbar_wait(tmem_full_bar, 0u);
     tc_fence_after();
-    int64_t dpix = 0;
-    if (mvalid) dpix = ((int64_t)(img * p.ho + p.os * my + p.py)) * p.wo + (p.os * mx + p.px);
+    // the pipeline buffers are dead now (every MMA that read them has completed): alias the staging tile onto them
+    constexpr int STG_LD = 68;  // floats per staged row (64 + 4: 16-byte aligned rows, conflict-free 128-bit writes)
+    float* stg = reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * (32 * STG_LD);
+    int* drow = reinterpret_cast<int*>(smem_raw + (base - raw) + 4 * 32 * STG_LD * 4) + warp * 32;
     const yad_epilogue& e = p.e;
     float sc = 1.0f;
-    if (mvalid) {
-      if (e.img_scale) sc = e.img_scale[img];
-      if (e.pix_scale) sc *= __bfloat162float(reinterpret_cast<const bf16*>(e.pix_scale)[dpix * e.pix_scale_ld]);
+    {
+      const uint32_t m = (uint32_t)blockIdx.x * BM + tid, hw = (uint32_t)(p.hm * p.wm);
+      int dp = -1;
+      if ((int64_t)m < M) {
+        const int img = (int)(m / hw);
+        const int r = (int)(m - (uint32_t)img * hw);
+        const int my = r / p.wm, mx = r - my * p.wm;
+        dp = (img * p.ho + p.os * my + p.py) * p.wo + (p.os * mx + p.px);
+        if (e.img_scale) sc = e.img_scale[img];
+        if (e.pix_scale) sc *= __bfloat162float(reinterpret_cast<const bf16*>(e.pix_scale)[(int64_t)dp * e.pix_scale_ld]);
+      }
+      drow[lane] = dp;
     }
     const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
-    for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + lane_base + (uint32_t)c0, r);  // warp-collective: executed by all lanes, valid row or not
-      const int co = n0 + c0;
-      if (!mvalid || co >= p.cout) continue;
-      if (p.out_f32) {
-        float* dst = reinterpret_cast<float*>(p.y) + dpix * p.y_ld + co;
+    for (int c0 = 0; c0 < p.n_tile; c0 += 64) {
+      const int cw = min(64, p.n_tile - c0);
+      __syncwarp();
+      for (int q0 = 0; q0 < cw; q0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + lane_base + (uint32_t)(c0 + q0), r);
+        const int co = n0 + c0 + q0;
+        float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++)
-          if (co + i < p.cout) dst[i] = __uint_as_float(r[i]);
-        continue;
-      }
+        for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+        if (!p.out_f32) {
 #pragma unroll
-      for (int hlf = 0; hlf < 2; hlf++) {
-        const int c = co + hlf * 8;
-        if (c >= p.cout) break;
-        float v[8];
+          for (int i = 0; i < 16; i++) v[i] *= sc;
+          if (e.bias) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[hlf * 8 + i]) * sc;
-        if (e.bias) {
-          const float4 b0 = *reinterpret_cast<const float4*>(e.bias + c), b1 = *reinterpret_cast<const float4*>(e.bias + c + 4);
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            for (int i4 = 0; i4 < 4; i4++) {
+              if (co + 4 * i4 < p.cout) {
+                const float4 b4 = *reinterpret_cast<const float4*>(e.bias + co + 4 * i4);
+                v[4 * i4] += b4.x; v[4 * i4 + 1] += b4.y; v[4 * i4 + 2] += b4.z; v[4 * i4 + 3] += b4.w;
+              }
+            }
+          }
+          apply_act_n<16>(v, e.act);
+#pragma unroll
+          for (int i = 0; i < 16; i++) v[i] *= e.alpha;
         }
+        float4* dst = reinterpret_cast<float4*>(stg + lane * STG_LD + q0);
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = apply_act(v[i], e.act) * e.alpha;
+        for (int i4 = 0; i4 < 4; i4++) dst[i4] = make_float4(v[4 * i4], v[4 * i4 + 1], v[4 * i4 + 2], v[4 * i4 + 3]);
+      }
+      __syncwarp();
+      const int cpr = cw >> 3;  // 8-column chunks per row
+      for (int q = lane; q < 32 * cpr; q += 32) {
+        const int row = q / cpr, ch = (q - row * cpr) * 8;
+        const int dp = drow[row];
+        const int co = n0 + c0 + ch;
+        if (dp < 0 || co >= p.cout) continue;
+        const float4 f0 = *reinterpret_cast<const float4*>(stg + row * STG_LD + ch), f1 = *reinterpret_cast<const float4*>(stg + row * STG_LD + ch + 4);
+        float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.y) + (int64_t)dp * p.y_ld + co;
+          *reinterpret_cast<float4*>(o) = f0;
+          *reinterpret_cast<float4*>(o + 4) = f1;
+          continue;
+        }
         if (e.mul) {
           float mv[8];
-          bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.mul) + dpix * e.mul_ld + c), mv);
+          bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.mul) + (int64_t)dp * e.mul_ld + co), mv);
 #pragma unroll
           for (int i = 0; i < 8; i++) v[i] *= mv[i];
         }
         if (e.add) {
           float adv[8];
-          bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.add) + dpix * e.add_ld + c), adv);
+          bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.add) + (int64_t)dp * e.add_ld + co), adv);
 #pragma unroll
           for (int i = 0; i < 8; i++) v[i] += adv[i];
         }
-        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.y) + dpix * p.y_ld + c) = f_to_bf8(v);
+        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.y) + (int64_t)dp * p.y_ld + co) = f_to_bf8(v);
       }
     }
     tc_fence_before();
@@ -355,6 +368,10 @@ int pick_n_tile(int cout) {
 }
 
 int launch(TcParams& p, int64_t M, cudaStream_t st) {
+  if (M + BM >= (int64_t)1 << 31 || (int64_t)p.n * p.ho * p.wo >= (int64_t)1 << 31) {
+    yad_set_error("conv2d_tc: more than 2^31 pixels");
+    return 1;
+  }
   p.n_tile = pick_n_tile(p.cout);
   p.tmem_cols = 32;
   while (p.tmem_cols < p.n_tile) p.tmem_cols <<= 1;
@@ -364,7 +381,11 @@ int launch(TcParams& p, int64_t M, cudaStream_t st) {
   stages = stages > 4 ? 4 : (stages < 2 ? 2 : stages);
   if (stages > nk) stages = nk < 1 ? 1 : nk;
   p.stages = stages;
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + 8 * (2 * stages + 1) + 16;
+  size_t pipe = (size_t)stages * stage_bytes;
+  const size_t stg = 4 * 32 * 68 * 4 + 4 * 32 * 4;  // epilogue staging (aliased onto the pipeline buffers) + row table
+  if (pipe < stg) pipe = (stg + 127) / 128 * 128;
+  p.pipe_bytes = (int)pipe;
+  const size_t smem = 1024 + pipe + 8 * (2 * stages + 1) + 16;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||

@@ -120,7 +120,8 @@ __global__ void gn_apply_kernel(yad_tensor x, const double* __restrict__ stats, 
     float v[8];
     load8(xb + p * x.ld + o, v);
 #pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = apply_act(fmaf(v[i], sm[o + i], sm[c + o + i]), act);
+    for (int i = 0; i < 8; i++) v[i] = fmaf(v[i], sm[o + i], sm[c + o + i]);
+    apply_act_n<8>(v, act);
     if (ab) {
       float a[8];
       load8(ab + p * add_ld + o, a);
@@ -180,8 +181,7 @@ __global__ void dwconv_kernel(yad_tensor x, const float* __restrict__ w, const f
 #pragma unroll
         for (int i = 0; i < 8; i++) acc[i] = fmaf(acc[i], scale[o + i], shift[o + i]);
       }
-#pragma unroll
-      for (int i = 0; i < 8; i++) acc[i] = apply_act(acc[i], act);
+      apply_act_n<8>(acc, act);
     }
     if (add) {
       float a[8];

@@ -134,7 +134,12 @@ def conv2d(x, w, y, bias=None, kh=1, kw=1, stride=1, pad_h=0, pad_w=0, act=ACT_N
     e = YadEpilogue(None if bias is None else bias.data_ptr(), None if img_scale is None else img_scale.data_ptr(),
                     psp, psld, act, alpha, mp, mld, adp, ald)
     flops = 2.0 * y.n * y.h * y.w * y.c * kh * kw * x.c if mode != CONV_TRANSPOSED else 2.0 * x.n * x.h * x.w * y.c * kh * kw * x.c
-    _call("yad_conv2d", x.yt(), _p(w), C.byref(d), C.byref(e), y.yt(), dt(x.dtype), stream_ptr(), meta=flops)
+    meta = None
+    if PROFILE is not None:
+        esz = x.buf.element_size()
+        byts = esz * (x.n * x.h * x.w * x.c + y.n * y.h * y.w * y.c * (1 + (mul is not None) + (add is not None)) + w.numel())
+        meta = dict(flops=flops, bytes=byts, shape=f"{x.c}->{y.c} k{kh}x{kw} s{stride} m{mode} in{x.h}x{x.w} out{y.h}x{y.w} n{x.n}")
+    _call("yad_conv2d", x.yt(), _p(w), C.byref(d), C.byref(e), y.yt(), dt(x.dtype), stream_ptr(), meta=meta)
     return y
 
 
