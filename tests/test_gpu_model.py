@@ -95,3 +95,23 @@ def test_engine_graph_replay_matches_eager_and_detects(gold, state_dict):
     assert (det[:k, 5] == ref[:k, 5]).mean() > 0.9
     np.testing.assert_allclose(np.sort(det[:k, 4])[::-1], np.sort(ref[:k, 4])[::-1], atol=2e-3)
     assert eng.launches_per_step and eng.launches_per_step > 100
+
+
+def test_module_mirrors_forward_matches_reference_golden(gold, state_dict):
+    """the drop-in nn.Module path (one libyad-backed module per yaml layer, routed like _predict_once) reproduces the reference output"""
+    from yolo_ad_refine_b200 import modules as M
+    g = gold("model_160.npz")
+    model = M.YoloADRefine(nc=80)
+    model.load_state_dict(state_dict, strict=True)
+    model = model.eval().to(DEV)
+    img = torch.from_numpy(synth.make_images(2, 160, 160, seed=2)).to(DEV)
+    with torch.inference_mode():
+        y, raw = model(img)
+    yy = y.cpu().numpy()
+    np.testing.assert_allclose(yy[:, 4:], g["y"][:, 4:], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(yy[:, :4], g["y"][:, :4], rtol=1e-3, atol=1e-2)
+    for i, f in enumerate(raw):
+        assert tuple(f.shape) == tuple(g[f"feat{i}"].shape)
+        assert rel_err(f.float().cpu().numpy(), g[f"feat{i}"]) < 1e-3
+    with pytest.raises(NotImplementedError):
+        model.train()(img)

@@ -1,0 +1,72 @@
+"""Drop-in installation into an Ultralytics tree (the reference fork): rebinds the names that `parse_model`, the predictor / validator and the
+trainer look up at call time (SURVEY.md section 8b "How to bind"), so that `YOLO(yaml).predict/val` run the YOLO-AD-Refine hot path
+through libyad.so without touching the reference's source.
+
+    import yolo_ad_refine_b200.plugin as yad
+    yad.install()                       # before building the model
+    model = YOLO("z-yaml/yolo11-701-YOLO-AD-Refine.yaml", task="detect")
+    yad.convert_model(model.model)      # swaps the yaml's plain nn.Conv2d / nn.ConvTranspose2d layers for libyad-backed twins
+"""
+import importlib
+
+import torch.nn as nn
+
+from . import loss as yloss
+from . import modules as M
+from . import postprocess as ypost
+from . import tal as ytal
+
+BLOCKS = ["Conv", "C3k2", "C3k2_MLCA", "SPPF", "C2PTSSA", "C2ProgressiveTSSA_Fusion", "ELA_HSFPN", "Multiply", "Add", "Fusion"]
+HEADS = ["AYHead", "AYHead1"]
+
+
+def install(ultralytics_pkg="ultralytics"):
+    """Rebind the reference's names to the libyad-backed implementations.  Returns the list of rebound qualified names."""
+    done = []
+
+    def bind(modname, attr, obj):
+        try:
+            mod = importlib.import_module(f"{ultralytics_pkg}.{modname}")
+        except Exception:
+            return
+        if hasattr(mod, attr):
+            setattr(mod, attr, obj)
+            done.append(f"{modname}.{attr}")
+
+    for name in BLOCKS:
+        obj = getattr(M, name)
+        bind("nn.tasks", name, obj)          # parse_model resolves classes through globals() (nn/tasks.py:969)
+        bind("nn.modules", name, obj)
+        bind("nn.modules.block", name, obj)  # unpickling of checkpoints
+    bind("nn.modules.conv", "Conv", M.Conv)
+    for name in HEADS:
+        bind("nn.tasks", name, M.AYHead)
+        bind("nn.modules", name, M.AYHead)
+        bind("nn.modules.head", name, M.AYHead)
+    bind("utils.ops", "non_max_suppression", ypost.non_max_suppression)  # looked up at call time (detect/predict.py:25, detect/val.py:93)
+    bind("nn.tasks", "v8DetectionLoss", yloss.v8DetectionLoss)           # nn/tasks.py:396-398
+    bind("utils.loss", "v8DetectionLoss", yloss.v8DetectionLoss)
+    bind("utils.loss", "TaskAlignedAssigner", ytal.TaskAlignedAssigner)   # utils/loss.py:379
+    bind("utils.tal", "TaskAlignedAssigner", ytal.TaskAlignedAssigner)
+    return done
+
+
+def convert_model(model):
+    """Replace the plain torch layers the yaml names (`nn.Conv2d` laterals, `nn.ConvTranspose2d` upsamplers) in a parsed model by their
+    libyad-backed twins, keeping parameters (same state-dict keys) and the routing attributes parse_model attached (i, f, type, np)."""
+    seq = model.model if hasattr(model, "model") else model
+    for idx, m in enumerate(seq):
+        new = None
+        if type(m) is nn.Conv2d and m.groups == 1:
+            new = M.YadConv2d(m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0], m.padding[0], m.bias is not None)
+        elif type(m) is nn.ConvTranspose2d:
+            new = M.YadConvTranspose2d(m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0], m.padding[0], m.output_padding[0])
+        if new is None:
+            continue
+        new.weight, new.bias = m.weight, m.bias
+        for attr in ("i", "f", "type", "np"):
+            if hasattr(m, attr):
+                setattr(new, attr, getattr(m, attr))
+        new.train(m.training)
+        seq[idx] = new
+    return model
