@@ -136,14 +136,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from yolo_ad_refine_b200 import parallel
+    world, rank, local = parallel.env_world()
     assert torch.cuda.is_available(), "bench.py (impl ours) needs a GPU: there is no CPU fallback"
     torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    parallel.init("nccl")
     from yolo_ad_refine_b200 import ops, synth
     from yolo_ad_refine_b200.engine import RefineEngine
 
@@ -158,8 +155,7 @@ def main():
     torch.cuda.synchronize()
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        parallel.barrier()
         torch.cuda.synchronize()
 
     def timed(fn, k):
@@ -172,12 +168,7 @@ def main():
             fn()
         e.record()
         barrier()
-        ms = s.elapsed_time(e)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return parallel.max_over_ranks(s.elapsed_time(e), device="cuda")
 
     # ---- device-resident throughput (graph replay of forward + decode + NMS)
     with ClockSampler(local) as clk:
@@ -239,7 +230,7 @@ def main():
                                     "sample": f"oracle port (fp32 torch-CPU restatement of the reference path), batch 2 at {args.imgsz}^2, best of 2"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
