@@ -117,6 +117,108 @@ __device__ __forceinline__ uint4 f_to_bf8(const float (&v)[8]) {
   return u;
 }
 
+// bf16-grade activations for the tensor-core epilogue: one MUFU.TANH per value (sigmoid(x) = 0.5 + 0.5 tanh(x / 2))
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int N>
+__device__ __forceinline__ void apply_act_bf16_n(float (&v)[N], int act) {
+  if (act == YAD_ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < N; i++) { const float h = 0.5f * v[i]; v[i] = fmaf(h, tanh_approx(h), h); }
+  } else if (act == YAD_ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = fmaf(0.5f, tanh_approx(0.5f * v[i]), 0.5f);
+  } else if (act != YAD_ACT_NONE) {
+    apply_act_n<N>(v, act);
+  }
+}
+
+constexpr int STG_LD = 68;  // floats per staged row (64 + 4: 16-byte aligned rows, conflict-free 128-bit writes)
+
+// Epilogue of one warp = one 32-lane quarter of the accumulator tile.
+//   phase 1 (thread = TMEM lane = tile row): tcgen05.ld 16 columns at a time, scale / bias / activation / alpha, park fp32 in a per-warp
+//   smem staging tile; phase 2 (lanes sweep each row contiguously): mul / add / convert, 128-bit coalesced stores.
+// dp = destination pixel index of this thread's row (or -1), img = its image (for img_scale).
+__device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_base, int quarter, int lane, float* stg, int* drow, int dp, int img,
+                                              int n0) {
+  const yad_epilogue& e = p.e;
+  float sc = 1.0f;
+  if (dp >= 0) {
+    if (e.img_scale) sc = e.img_scale[img];
+    if (e.pix_scale) sc *= __bfloat162float(reinterpret_cast<const bf16*>(e.pix_scale)[(int64_t)dp * e.pix_scale_ld]);
+  }
+  drow[lane] = dp;
+  const uint32_t lane_base = ((uint32_t)(quarter * 32)) << 16;
+  for (int c0 = 0; c0 < p.n_tile; c0 += 64) {
+    const int cw = min(64, p.n_tile - c0);
+    __syncwarp();
+    for (int q0 = 0; q0 < cw; q0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + lane_base + (uint32_t)(c0 + q0), r);
+      const int co = n0 + c0 + q0;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+      if (!p.out_f32) {
+        if (e.bias && co + 16 <= p.cout) {
+#pragma unroll
+          for (int i4 = 0; i4 < 4; i4++) {
+            const float4 b4 = *reinterpret_cast<const float4*>(e.bias + co + 4 * i4);
+            v[4 * i4] = fmaf(v[4 * i4], sc, b4.x); v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], sc, b4.y);
+            v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], sc, b4.z); v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], sc, b4.w);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i++) v[i] = fmaf(v[i], sc, (e.bias && co + i < p.cout) ? e.bias[co + i] : 0.f);
+        }
+        apply_act_bf16_n<16>(v, e.act);
+        if (e.alpha != 1.0f) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) v[i] *= e.alpha;
+        }
+      }
+      float4* dst = reinterpret_cast<float4*>(stg + lane * STG_LD + q0);
+#pragma unroll
+      for (int i4 = 0; i4 < 4; i4++) dst[i4] = make_float4(v[4 * i4], v[4 * i4 + 1], v[4 * i4 + 2], v[4 * i4 + 3]);
+    }
+    __syncwarp();
+    // phase 2: cpr lanes per row, rpp rows per pass (cw in {16, 32, 48, 64} -> cpr in {2, 4, 6, 8})
+    const int cpr = cw >> 3, rpp = 32 / cpr;
+    const int rr = lane / cpr, ch = (lane - rr * cpr) * 8;
+    const int co = n0 + c0 + ch;
+    if (rr < rpp && co < p.cout) {
+      for (int row = rr; row < 32; row += rpp) {
+        const int d = drow[row];
+        if (d < 0) continue;
+        const float4 f0 = *reinterpret_cast<const float4*>(stg + row * STG_LD + ch), f1 = *reinterpret_cast<const float4*>(stg + row * STG_LD + ch + 4);
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.y) + (int64_t)d * p.y_ld + co;
+          *reinterpret_cast<float4*>(o) = f0;
+          *reinterpret_cast<float4*>(o + 4) = f1;
+          continue;
+        }
+        float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+        if (e.mul) {
+          float mv[8];
+          bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.mul) + (int64_t)d * e.mul_ld + co), mv);
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] *= mv[i];
+        }
+        if (e.add) {
+          float adv[8];
+          bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.add) + (int64_t)d * e.add_ld + co), adv);
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] += adv[i];
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.y) + (int64_t)d * p.y_ld + co) = f_to_bf8(v);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool DEFORM>
 __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
@@ -155,7 +257,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
     // instruction reads 4 rows x 128 contiguous bytes (4 L1 wavefronts instead of 32) and writes 4 conflict-free swizzled smem rows.
     const int64_t M = (int64_t)p.n * p.hm * p.wm;
     const int lane = tid & 31, sr = lane >> 3, c = lane & 7;
-    int rimg[8], ryx[8];  // per owned row: image index (-1 = beyond M) and (my << 16 | mx)
+    int rimg[8], ryx[8];  // per owned row: image index (-1 = beyond M) and (stride*my << 16 | stride*mx) (DEFORM: stride = 1)
     {
       // decode the first owned row with 32-bit divisions, then step by 4 pixels with carries (M < 2^31 is checked by the launcher)
       const uint32_t m0 = (uint32_t)blockIdx.x * BM + warp * 32 + sr, hw = (uint32_t)(p.hm * p.wm);
@@ -165,8 +267,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         const bool ok = (int64_t)m0 + 4 * i < M;
-        rimg[i] = ok ? img : -1;
-        ryx[i] = (my << 16) | mx;
+        rimg[i] = ok ? img * p.hi : -1;  // pre-multiplied row base of the image
+        ryx[i] = ((p.stride * my) << 16) | (p.stride * mx);
         mx += 4;
         while (mx >= p.wm) { mx -= p.wm; my++; }
         while (my >= p.hm) { my -= p.hm; img++; }
@@ -180,6 +282,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
       const bool kvalid = kk < K;
       const int t = kvalid ? kk / p.cin : 0;
       const int ci = kk - t * p.cin;
+      const int tdy = p.dy[t], tdx = p.dx[t];
+      const bf16* xk = p.x + ci;
       // ---- A: gather into registers first (global latency overlaps the wait for the slot)
       uint4 av[8];
 #pragma unroll
@@ -188,11 +292,12 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
         if (!kvalid || rimg[i] < 0) continue;
         const int my = ryx[i] >> 16, mx = ryx[i] & 0xFFFF;
         if (!DEFORM) {
-          const int sy = p.stride * my + p.dy[t], sx = p.stride * mx + p.dx[t];
-          if (sy >= 0 && sy < p.hi && sx >= 0 && sx < p.wi) av[i] = ldg16(p.x + ((int64_t)(rimg[i] * p.hi + sy) * p.wi + sx) * p.x_ld + ci);
+          const int sy = my + tdy, sx = mx + tdx;
+          if ((unsigned)sy < (unsigned)p.hi && (unsigned)sx < (unsigned)p.wi)
+            av[i] = ldg16(xk + (int64_t)((rimg[i] + sy) * p.wi + sx) * p.x_ld);
         } else {
           // modulated deformable 3x3 (stride 1, pad 1): bilinear sample, zero outside (-1, H) x (-1, W)
-          const bf16* o = p.om + ((int64_t)(rimg[i] * p.ho + my) * p.wo + mx) * p.om_ld;
+          const bf16* o = p.om + ((int64_t)(rimg[i] + my) * p.wo + mx) * p.om_ld;  // deformable: ho == hi
           const float ody = __bfloat162float(o[2 * t]), odx = __bfloat162float(o[2 * t + 1]);
           const float mk = sigmoidf_(__bfloat162float(o[18 + t]));
           const float fy_ = (float)(my + p.dy[t]) + ody, fx_ = (float)(mx + p.dx[t]) + odx;
@@ -209,7 +314,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
               const int yy = y0 + (c4 >> 1), xx = x0 + (c4 & 1);
               if (yy >= 0 && yy < p.hi && xx >= 0 && xx < p.wi) {
                 float v[8];
-                bf8_to_f(ldg16(p.x + ((int64_t)(rimg[i] * p.hi + yy) * p.wi + xx) * p.x_ld + ci), v);
+                bf8_to_f(ldg16(xk + (int64_t)((rimg[i] + yy) * p.wi + xx) * p.x_ld), v);
 #pragma unroll
                 for (int q = 0; q < 8; q++) acc[q] = fmaf(wgt[c4], v[q], acc[q]);
               }
@@ -245,89 +350,21 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
     }
 
     // ================= epilogue =================
-    // phase 1 (thread = TMEM lane = tile row): tcgen05.ld 16 columns at a time, scale / bias / activation / alpha, park fp32 in a per-warp
-    // smem staging tile; phase 2 (lanes sweep each row contiguously): mul / add / convert, 128-bit coalesced stores.
     mbar_wait(tmem_full_bar, 0u);
     tc_fence_after();
     // the pipeline buffers are dead now (every MMA that read them has completed): alias the staging tile onto them
-    constexpr int STG_LD = 68;  // floats per staged row (64 + 4: 16-byte aligned rows, conflict-free 128-bit writes)
     float* stg = reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * (32 * STG_LD);
     int* drow = reinterpret_cast<int*>(smem_raw + (base - raw) + 4 * 32 * STG_LD * 4) + warp * 32;
-    const yad_epilogue& e = p.e;
-    float sc = 1.0f;
     {
       const uint32_t m = (uint32_t)blockIdx.x * BM + tid, hw = (uint32_t)(p.hm * p.wm);
-      int dp = -1;
+      int dp = -1, img = 0;
       if ((int64_t)m < M) {
-        const int img = (int)(m / hw);
+        img = (int)(m / hw);
         const int r = (int)(m - (uint32_t)img * hw);
         const int my = r / p.wm, mx = r - my * p.wm;
         dp = (img * p.ho + p.os * my + p.py) * p.wo + (p.os * mx + p.px);
-        if (e.img_scale) sc = e.img_scale[img];
-        if (e.pix_scale) sc *= __bfloat162float(reinterpret_cast<const bf16*>(e.pix_scale)[(int64_t)dp * e.pix_scale_ld]);
       }
-      drow[lane] = dp;
-    }
-    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
-    for (int c0 = 0; c0 < p.n_tile; c0 += 64) {
-      const int cw = min(64, p.n_tile - c0);
-      __syncwarp();
-      for (int q0 = 0; q0 < cw; q0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + lane_base + (uint32_t)(c0 + q0), r);
-        const int co = n0 + c0 + q0;
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
-        if (!p.out_f32) {
-#pragma unroll
-          for (int i = 0; i < 16; i++) v[i] *= sc;
-          if (e.bias) {
-#pragma unroll
-            for (int i4 = 0; i4 < 4; i4++) {
-              if (co + 4 * i4 < p.cout) {
-                const float4 b4 = *reinterpret_cast<const float4*>(e.bias + co + 4 * i4);
-                v[4 * i4] += b4.x; v[4 * i4 + 1] += b4.y; v[4 * i4 + 2] += b4.z; v[4 * i4 + 3] += b4.w;
-              }
-            }
-          }
-          apply_act_n<16>(v, e.act);
-#pragma unroll
-          for (int i = 0; i < 16; i++) v[i] *= e.alpha;
-        }
-        float4* dst = reinterpret_cast<float4*>(stg + lane * STG_LD + q0);
-#pragma unroll
-        for (int i4 = 0; i4 < 4; i4++) dst[i4] = make_float4(v[4 * i4], v[4 * i4 + 1], v[4 * i4 + 2], v[4 * i4 + 3]);
-      }
-      __syncwarp();
-      const int cpr = cw >> 3;  // 8-column chunks per row
-      for (int q = lane; q < 32 * cpr; q += 32) {
-        const int row = q / cpr, ch = (q - row * cpr) * 8;
-        const int dp = drow[row];
-        const int co = n0 + c0 + ch;
-        if (dp < 0 || co >= p.cout) continue;
-        const float4 f0 = *reinterpret_cast<const float4*>(stg + row * STG_LD + ch), f1 = *reinterpret_cast<const float4*>(stg + row * STG_LD + ch + 4);
-        float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-        if (p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.y) + (int64_t)dp * p.y_ld + co;
-          *reinterpret_cast<float4*>(o) = f0;
-          *reinterpret_cast<float4*>(o + 4) = f1;
-          continue;
-        }
-        if (e.mul) {
-          float mv[8];
-          bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.mul) + (int64_t)dp * e.mul_ld + co), mv);
-#pragma unroll
-          for (int i = 0; i < 8; i++) v[i] *= mv[i];
-        }
-        if (e.add) {
-          float adv[8];
-          bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.add) + (int64_t)dp * e.add_ld + co), adv);
-#pragma unroll
-          for (int i = 0; i < 8; i++) v[i] += adv[i];
-        }
-        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.y) + (int64_t)dp * p.y_ld + co) = f_to_bf8(v);
-      }
+      epilogue_warp(p, tmem_base, warp, lane, stg, drow, dp, img, n0);
     }
     tc_fence_before();
   } else {
