@@ -54,7 +54,8 @@ typedef struct {
   int32_t pad_h, pad_w;
   const void* offmask; /* DEFORM: NHWC view (activation dtype) with >= 27 channels: 18 offsets (dy,dx per tap) + 9 mask logits */
   int32_t offmask_ld;
-  int32_t impl;        /* 0 = auto, 1 = SIMT fp32-accumulate kernel, 2 = tcgen05/TMEM kernel (bf16 only) */
+  int32_t impl;        /* 0 = auto, 1 = SIMT fp32-accumulate kernel, 2 = tcgen05/TMEM kernel (bf16 only; TMA-fed where eligible),
+                          3 = tcgen05/TMEM kernel with thread-gathered operands only */
 } yad_conv_desc;
 
 const char* yad_last_error(void);

@@ -39,8 +39,10 @@ def test_umma_gemm_selftest(m, n, k):
 
 @pytest.mark.parametrize("cin,cout,k,s,hw", [(8, 16, 3, 2, 32), (16, 8, 3, 1, 20), (48, 64, 1, 1, 20), (128, 64, 3, 1, 10), (64, 32, 3, 2, 40),
                                              (192, 128, 1, 1, 7), (64, 27, 3, 1, 12), (32, 1, 3, 1, 9), (256, 256, 1, 1, 5), (128, 384, 1, 1, 20),
-                                             (128, 512, 1, 1, 10), (64, 64, 3, 1, 80)])
-def test_conv_tc_bias_silu_add(cin, cout, k, s, hw):
+                                             (128, 512, 1, 1, 10), (64, 64, 3, 1, 80), (128, 128, 3, 1, 40), (64, 64, 3, 1, 13),
+                                             (96, 128, 1, 1, 21), (128, 64, 3, 1, 20)])
+@pytest.mark.parametrize("impl", [2, 3])  # 2 = TMA-fed where eligible, 3 = thread-gathered operands
+def test_conv_tc_bias_silu_add(cin, cout, k, s, hw, impl):
     g = torch.Generator().manual_seed(cin * 1000 + cout)
     x = q(torch.randn(2, cin, hw, hw, generator=g))
     w = q(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5)
@@ -50,7 +52,7 @@ def test_conv_tc_bias_silu_add(cin, cout, k, s, hw):
     ref = F.silu(F.conv2d(x, w, b, s, k // 2)) + add
     cw = pack_conv(w, b, BF, DEV, s)
     out = Act.empty(2, ho, ho, cw.cout, BF, DEV)
-    ops.conv2d(to_act(x, BF), cw.w, out, bias=cw.b, kh=k, kw=k, stride=s, pad_h=k // 2, pad_w=k // 2, act=ops.ACT_SILU, add=to_act(add, BF), impl=2)
+    ops.conv2d(to_act(x, BF), cw.w, out, bias=cw.b, kh=k, kw=k, stride=s, pad_h=k // 2, pad_w=k // 2, act=ops.ACT_SILU, add=to_act(add, BF), impl=impl)
     assert rel_err(from_act(out, cout), ref) < TOL
 
 

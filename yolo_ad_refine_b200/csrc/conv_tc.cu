@@ -395,6 +395,260 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
   }
 }
 
+
+// =====================================================================================================================
+// TMA-fed variant: stride-1 convolutions whose 64-wide K chunks lie inside one tap (1x1 with any cin; kxk with cin % 64 == 0).
+//   warp 0 / lane 0 : producer -- per K chunk one cp.async.bulk.tensor load of the A box (64 channels x BW x BH pixels of one image, or
+//                     64 channels x 128 consecutive pixels for 1x1) and one of the B box (64 K x N_TILE couts), SWIZZLE_128B, arriving on
+//                     the stage's mbarrier with complete_tx; out-of-bounds coordinates (conv padding, ragged tiles, K tail) are zero-filled
+//                     by the TMA unit, so there is no address arithmetic in the kernel at all.
+//   warp 1 / lane 0 : tcgen05.mma issuer (same as above); warp 1 also owns the TMEM allocation.
+//   warps 2-5       : epilogue (TMEM lane quarter = warp % 4).
+// =====================================================================================================================
+constexpr int TMA_THREADS = 192;
+
+struct TmaParams {
+  TcParams p;
+  int patch;            // 0: rows = 128 consecutive pixels (1x1, 2-D map); 1: rows = BH x BW patch of one image (4-D map)
+  int bw, bh, tiles_x, tiles_y;
+  int a_bytes;          // bytes TMA writes per A box
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(tm),
+               "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+               "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_constant__ TmaParams tp, const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB) {
+  extern __shared__ uint8_t smem_raw[];
+  const TcParams& p = tp.p;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t a_bytes = BM * 128, b_bytes = (uint32_t)p.n_tile * 128;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t bars = base + (uint32_t)p.pipe_bytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (p.stages + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * p.stages);
+  const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = p.ntaps * p.cin;  // cin rounded up to 64 per tap by the host when ntaps > 1 is not needed: cin % 64 == 0 there
+  const int kpt = (p.cin + BK - 1) / BK;      // K chunks per tap
+  const int nk = p.ntaps * kpt;
+  const int n0 = blockIdx.y * p.n_tile;
+  (void)K;
+
+  // tile origin
+  int img = 0, ty0 = 0, tx0 = 0;
+  if (tp.patch) {
+    const int per_img = tp.tiles_x * tp.tiles_y;
+    img = blockIdx.x / per_img;
+    const int r = blockIdx.x - img * per_img;
+    ty0 = (r / tp.tiles_x) * tp.bh;
+    tx0 = (r % tp.tiles_x) * tp.bw;
+  }
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)tp.a_bytes + b_bytes;
+      for (int kc = 0; kc < nk; kc++) {
+        const int s = kc % p.stages;
+        const uint32_t ph = (uint32_t)(kc / p.stages) & 1u;
+        const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
+        const int t = kc / kpt, ci = (kc - t * kpt) * BK;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), tx_bytes);
+        if (tp.patch)
+          tma_load_4d(a_s, &tmA, full_bar(s), ci, tx0 + p.dx[t], ty0 + p.dy[t], img);
+        else
+          tma_load_2d(a_s, &tmA, full_bar(s), ci, (int)blockIdx.x * BM);
+        tma_load_2d(b_s, &tmB, full_bar(s), p.wtap[t] * p.cin + ci, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.n_tile);
+      for (int kc = 0; kc < nk; kc++) {
+        const int s = kc % p.stages;
+        const uint32_t ph = (uint32_t)(kc / p.stages) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
+        const uint64_t ad = make_sdesc(a_s), bd = make_sdesc(b_s);
+#pragma unroll
+        for (int k = 0; k < BK / 16; k++) umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+    tc_fence_before();
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int dp = -1;
+    if (tp.patch) {
+      const int ry = row / tp.bw, rx = row - ry * tp.bw;
+      const int oy = ty0 + ry, ox = tx0 + rx;
+      if (ry < tp.bh && oy < p.ho && ox < p.wo) dp = (img * p.ho + oy) * p.wo + ox;
+    } else {
+      const int64_t m = (int64_t)blockIdx.x * BM + row;
+      if (m < (int64_t)p.n * p.ho * p.wo) { dp = (int)m; img = (int)(m / ((int64_t)p.ho * p.wo)); }
+    }
+    mbar_wait(tmem_full_bar, 0u);
+    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem_raw + (base - raw)) + quarter * (32 * STG_LD);
+    int* drow = reinterpret_cast<int*>(smem_raw + (base - raw) + 4 * 32 * STG_LD * 4) + quarter * 32;
+    epilogue_warp(p, tmem_base, quarter, lane, stg, drow, dp, img, n0);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// bf16 tensor map, SWIZZLE_128B, zero OOB fill.  dims / strides innermost first; strides[i] (bytes) for dims 1..rank-1.
+int make_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { yad_set_error("conv2d_tma: cuTensorMapEncodeTiled is unavailable"); return 1; }
+  cuuint64_t d[5], st[5];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; i++) st[i] = strides_bytes[i];
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { yad_set_error("conv2d_tma: cuTensorMapEncodeTiled failed with %d", (int)r); return 1; }
+  return 0;
+}
+
+int pick_n_tile(int cout);
+
+// best (bw, bh) with bw * bh <= 128 for an (h, w) map: maximise useful pixels per 128-row MMA tile
+void pick_patch(int h, int w, int* bw_out, int* bh_out) {
+  double best = -1;
+  for (int bw = 1; bw <= (w < 128 ? w : 128); bw++) {
+    int bh = 128 / bw;
+    if (bh > h) bh = h;
+    if (bh < 1 || bh > 256) continue;
+    int tx = (w + bw - 1) / bw, ty = (h + bh - 1) / bh;
+    double eff = (double)h * w / ((double)tx * ty * 128.0);
+    if (eff > best + 1e-9) { best = eff; *bw_out = bw; *bh_out = bh; }
+  }
+}
+
+int tma_supported(const yad_tensor* x, const yad_conv_desc* d, const yad_tensor* y) {
+  if (d->mode != YAD_CONV_NORMAL || d->stride != 1) return 0;
+  if (d->kh * d->kw > 1 && (x->c % BK) != 0) return 0;
+  if (d->kh * d->kw > MAX_TAPS) return 0;
+  if (((uintptr_t)x->ptr & 15) || (x->ld % 8) || (y->ld % 8)) return 0;
+  if (d->kh * d->kw > 1 && (y->h != x->h || y->w != x->w)) return 0;
+  return get_encode() != nullptr;
+}
+
+int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
+  TmaParams tp;
+  memset(&tp, 0, sizeof(tp));
+  p.n_tile = pick_n_tile(p.cout);
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.n_tile) p.tmem_cols <<= 1;
+  const int stage_bytes = BM * 128 + p.n_tile * 128;
+  const int kpt = (p.cin + BK - 1) / BK, nk = p.ntaps * kpt;
+  int stages = (96 * 1024) / stage_bytes;
+  stages = stages > 4 ? 4 : (stages < 2 ? 2 : stages);
+  if (stages > nk) stages = nk;
+  p.stages = stages;
+  size_t pipe = (size_t)stages * stage_bytes;
+  const size_t stg = 4 * 32 * 68 * 4 + 4 * 32 * 4;
+  if (pipe < stg) pipe = (stg + 127) / 128 * 128;
+  p.pipe_bytes = (int)pipe;
+  const size_t smem = 1024 + pipe + 8 * (2 * stages + 1) + 16;
+
+  CUtensorMap tmA, tmB;
+  unsigned grid_x;
+  if (p.ntaps == 1) {  // 1x1: rows are consecutive pixels
+    tp.patch = 0;
+    const int64_t M = (int64_t)p.n * p.hi * p.wi;
+    uint64_t dims[2] = {(uint64_t)p.cin, (uint64_t)M}, strides[1] = {(uint64_t)p.x_ld * 2};
+    uint32_t box[2] = {BK, BM};
+    if (make_map(&tmA, p.x, 2, dims, strides, box)) return 1;
+    tp.a_bytes = BM * 128;
+    grid_x = (unsigned)((M + BM - 1) / BM);
+  } else {
+    tp.patch = 1;
+    pick_patch(p.hi, p.wi, &tp.bw, &tp.bh);
+    tp.tiles_x = (p.wi + tp.bw - 1) / tp.bw;
+    tp.tiles_y = (p.hi + tp.bh - 1) / tp.bh;
+    uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)p.wi, (uint64_t)p.hi, (uint64_t)p.n};
+    uint64_t strides[3] = {(uint64_t)p.x_ld * 2, (uint64_t)p.wi * p.x_ld * 2, (uint64_t)p.hi * p.wi * p.x_ld * 2};
+    uint32_t box[4] = {BK, (uint32_t)tp.bw, (uint32_t)tp.bh, 1};
+    if (make_map(&tmA, p.x, 4, dims, strides, box)) return 1;
+    tp.a_bytes = tp.bw * tp.bh * 128;
+    grid_x = (unsigned)(p.n * tp.tiles_x * tp.tiles_y);
+  }
+  {
+    const int cout_rows = (p.cout + 7) / 8 * 8;
+    uint64_t dims[2] = {(uint64_t)p.w_row, (uint64_t)cout_rows}, strides[1] = {(uint64_t)p.w_row * 2};
+    uint32_t box[2] = {BK, (uint32_t)p.n_tile};
+    if (make_map(&tmB, p.w, 2, dims, strides, box)) return 1;
+  }
+  tp.p = p;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+      yad_set_error("conv2d_tma: cannot raise the dynamic shared memory limit");
+      return 2;
+    }
+    attr_set = true;
+  }
+  dim3 grid(grid_x, (unsigned)((p.cout + p.n_tile - 1) / p.n_tile));
+  conv_tma_kernel<<<grid, TMA_THREADS, smem, st>>>(tp, tmA, tmB);
+  YAD_LAUNCH_CHECK("conv2d_tma");
+  (void)d;
+  return 0;
+}
+
 int pick_n_tile(int cout) {
   int c16 = (cout + 15) / 16 * 16;
   if (c16 <= 256) return c16;
@@ -475,6 +729,7 @@ int yad_conv2d_tc(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
     p.hm = y->h; p.wm = y->w; p.stride = d->stride; p.os = 1; p.py = 0; p.px = 0;
     p.ntaps = d->kh * d->kw;
     for (int t = 0; t < p.ntaps; t++) { p.dy[t] = t / d->kw - d->pad_h; p.dx[t] = t % d->kw - d->pad_w; p.wtap[t] = t; }
+    if (d->impl != 3 && tma_supported(x, d, y)) return launch_tma(p, d, st);
     return launch(p, (int64_t)x->n * p.hm * p.wm, st);
   }
   if (d->mode == YAD_CONV_TRANSPOSED) {
