@@ -136,14 +136,16 @@ __device__ __forceinline__ void apply_act_bf16_n(float (&v)[N], int act) {
   }
 }
 
-constexpr int STG_LD = 68;  // floats per staged row (64 + 4: 16-byte aligned rows, conflict-free 128-bit writes)
+constexpr int STG_ROW = 144;            // bytes per staged row: 64 bf16 + 16 (16-byte aligned rows, conflict-free 128-bit accesses)
+constexpr int STG_WARP = 32 * STG_ROW;  // staging bytes per epilogue warp
 
-// Epilogue of one warp = one 32-lane quarter of the accumulator tile.
-//   phase 1 (thread = TMEM lane = tile row): tcgen05.ld 16 columns at a time, scale / bias / activation / alpha, park fp32 in a per-warp
-//   smem staging tile; phase 2 (lanes sweep each row contiguously): mul / add / convert, 128-bit coalesced stores.
+// Epilogue of one warp over the 32 accumulator rows of its TMEM lane quarter and the column range [col_begin, col_end) of the tile.
+//   phase 1 (thread = TMEM lane = tile row): tcgen05.ld 16 columns at a time, scale / bias / activation / alpha, round to bf16 and park
+//   in a per-warp smem staging tile; phase 2 (lanes sweep each row contiguously): optional mul / add, 128-bit coalesced stores.
+//   (The conv output is rounded to bf16 before mul / add -- exactly what the unfused bf16 reference path materialises.)
 // dp = destination pixel index of this thread's row (or -1), img = its image (for img_scale).
-__device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_base, int quarter, int lane, float* stg, int* drow, int dp, int img,
-                                              int n0) {
+__device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_acc, int quarter, int lane, uint8_t* stg, int* drow, int dp, int img,
+                                              int n0, int col_begin, int col_end) {
   const yad_epilogue& e = p.e;
   float sc = 1.0f;
   if (dp >= 0) {
@@ -152,38 +154,49 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_b
   }
   drow[lane] = dp;
   const uint32_t lane_base = ((uint32_t)(quarter * 32)) << 16;
-  for (int c0 = 0; c0 < p.n_tile; c0 += 64) {
-    const int cw = min(64, p.n_tile - c0);
+  for (int c0 = col_begin; c0 < col_end; c0 += 64) {
+    const int cw = min(64, col_end - c0);
     __syncwarp();
     for (int q0 = 0; q0 < cw; q0 += 16) {
       uint32_t r[16];
-      tmem_ld16(tmem_base + lane_base + (uint32_t)(c0 + q0), r);
+      tmem_ld16(tmem_acc + lane_base + (uint32_t)(c0 + q0), r);
       const int co = n0 + c0 + q0;
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
-      if (!p.out_f32) {
-        if (e.bias && co + 16 <= p.cout) {
+      if (p.out_f32) {  // self-test path: raw accumulators straight to global
+        if (dp >= 0) {
+          float* o = reinterpret_cast<float*>(p.y) + (int64_t)dp * p.y_ld + co;
 #pragma unroll
-          for (int i4 = 0; i4 < 4; i4++) {
-            const float4 b4 = *reinterpret_cast<const float4*>(e.bias + co + 4 * i4);
-            v[4 * i4] = fmaf(v[4 * i4], sc, b4.x); v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], sc, b4.y);
-            v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], sc, b4.z); v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], sc, b4.w);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; i++) v[i] = fmaf(v[i], sc, (e.bias && co + i < p.cout) ? e.bias[co + i] : 0.f);
+          for (int i = 0; i < 16; i++)
+            if (co + i < p.cout) o[i] = v[i];
         }
-        apply_act_bf16_n<16>(v, e.act);
-        if (e.alpha != 1.0f) {
-#pragma unroll
-          for (int i = 0; i < 16; i++) v[i] *= e.alpha;
-        }
+        continue;
       }
-      float4* dst = reinterpret_cast<float4*>(stg + lane * STG_LD + q0);
+      if (e.bias && co + 16 <= p.cout) {
 #pragma unroll
-      for (int i4 = 0; i4 < 4; i4++) dst[i4] = make_float4(v[4 * i4], v[4 * i4 + 1], v[4 * i4 + 2], v[4 * i4 + 3]);
+        for (int i4 = 0; i4 < 4; i4++) {
+          const float4 b4 = *reinterpret_cast<const float4*>(e.bias + co + 4 * i4);
+          v[4 * i4] = fmaf(v[4 * i4], sc, b4.x); v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], sc, b4.y);
+          v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], sc, b4.z); v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], sc, b4.w);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = fmaf(v[i], sc, (e.bias && co + i < p.cout) ? e.bias[co + i] : 0.f);
+      }
+      apply_act_bf16_n<16>(v, e.act);
+      if (e.alpha != 1.0f) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] *= e.alpha;
+      }
+      float lo[8], hi[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) { lo[i] = v[i]; hi[i] = v[8 + i]; }
+      uint4* dst = reinterpret_cast<uint4*>(stg + lane * STG_ROW + q0 * 2);
+      dst[0] = f_to_bf8(lo);
+      dst[1] = f_to_bf8(hi);
     }
+    if (p.out_f32) continue;
     __syncwarp();
     // phase 2: cpr lanes per row, rpp rows per pass (cw in {16, 32, 48, 64} -> cpr in {2, 4, 6, 8})
     const int cpr = cw >> 3, rpp = 32 / cpr;
@@ -193,27 +206,25 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_b
       for (int row = rr; row < 32; row += rpp) {
         const int d = drow[row];
         if (d < 0) continue;
-        const float4 f0 = *reinterpret_cast<const float4*>(stg + row * STG_LD + ch), f1 = *reinterpret_cast<const float4*>(stg + row * STG_LD + ch + 4);
-        if (p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.y) + (int64_t)d * p.y_ld + co;
-          *reinterpret_cast<float4*>(o) = f0;
-          *reinterpret_cast<float4*>(o + 4) = f1;
-          continue;
-        }
-        float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-        if (e.mul) {
-          float mv[8];
-          bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.mul) + (int64_t)d * e.mul_ld + co), mv);
+        uint4 u = *reinterpret_cast<const uint4*>(stg + row * STG_ROW + ch * 2);
+        if (e.mul || e.add) {
+          float v[8];
+          bf8_to_f(u, v);
+          if (e.mul) {
+            float mv[8];
+            bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.mul) + (int64_t)d * e.mul_ld + co), mv);
 #pragma unroll
-          for (int i = 0; i < 8; i++) v[i] *= mv[i];
-        }
-        if (e.add) {
-          float adv[8];
-          bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.add) + (int64_t)d * e.add_ld + co), adv);
+            for (int i = 0; i < 8; i++) v[i] *= mv[i];
+          }
+          if (e.add) {
+            float adv[8];
+            bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.add) + (int64_t)d * e.add_ld + co), adv);
 #pragma unroll
-          for (int i = 0; i < 8; i++) v[i] += adv[i];
+            for (int i = 0; i < 8; i++) v[i] += adv[i];
+          }
+          u = f_to_bf8(v);
         }
-        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.y) + (int64_t)d * p.y_ld + co) = f_to_bf8(v);
+        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.y) + (int64_t)d * p.y_ld + co) = u;
       }
     }
   }
@@ -353,8 +364,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
     mbar_wait(tmem_full_bar, 0u);
     tc_fence_after();
     // the pipeline buffers are dead now (every MMA that read them has completed): alias the staging tile onto them
-    float* stg = reinterpret_cast<float*>(smem_raw + (base - raw)) + warp * (32 * STG_LD);
-    int* drow = reinterpret_cast<int*>(smem_raw + (base - raw) + 4 * 32 * STG_LD * 4) + warp * 32;
+    uint8_t* stg = smem_raw + (base - raw) + warp * STG_WARP;
+    int* drow = reinterpret_cast<int*>(smem_raw + (base - raw) + 4 * STG_WARP) + warp * 32;
     {
       const uint32_t m = (uint32_t)blockIdx.x * BM + tid, hw = (uint32_t)(p.hm * p.wm);
       int dp = -1, img = 0;
@@ -364,7 +375,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
         const int my = r / p.wm, mx = r - my * p.wm;
         dp = (img * p.ho + p.os * my + p.py) * p.wo + (p.os * mx + p.px);
       }
-      epilogue_warp(p, tmem_base, warp, lane, stg, drow, dp, img, n0);
+      epilogue_warp(p, tmem_base, warp, lane, stg, drow, dp, img, n0, 0, p.n_tile);
     }
     tc_fence_before();
   } else {
@@ -403,15 +414,17 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
 //                     the stage's mbarrier with complete_tx; out-of-bounds coordinates (conv padding, ragged tiles, K tail) are zero-filled
 //                     by the TMA unit, so there is no address arithmetic in the kernel at all.
 //   warp 1 / lane 0 : tcgen05.mma issuer (same as above); warp 1 also owns the TMEM allocation.
-//   warps 2-5       : epilogue (TMEM lane quarter = warp % 4).
+//   warps 2-9       : epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter split the tile's columns).
 // =====================================================================================================================
-constexpr int TMA_THREADS = 192;
+constexpr int TMA_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int TMA_THREADS = 64 + 32 * TMA_EPI_WARPS;
 
 struct TmaParams {
   TcParams p;
   int patch;            // 0: rows = 128 consecutive pixels (1x1, 2-D map); 1: rows = BH x BW patch of one image (4-D map)
   int bw, bh, tiles_x, tiles_y;
   int a_bytes;          // bytes TMA writes per A box
+  int tiles_n, total_tiles, acc_stages;
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -430,39 +443,32 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
 
 __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_constant__ TmaParams tp, const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB) {
+  // Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA producer runs ahead across tile boundaries and the
+  // accumulator is double-buffered in TMEM (when 2 * N_TILE <= 512 columns), so loads, MMAs and the epilogue of consecutive tiles overlap.
   extern __shared__ uint8_t smem_raw[];
   const TcParams& p = tp.p;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t a_bytes = BM * 128, b_bytes = (uint32_t)p.n_tile * 128;
   const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t stg_off = (uint32_t)p.stages * stage_bytes;             // dedicated epilogue staging (not aliased: the pipeline stays busy)
   const uint32_t bars = base + (uint32_t)p.pipe_bytes;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (p.stages + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (2 * p.stages);
-  const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * p.stages + 2 + a); };
+  const uint32_t tmem_ptr_addr = bars + 8u * (2 * p.stages + 4);
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int K = p.ntaps * p.cin;  // cin rounded up to 64 per tap by the host when ntaps > 1 is not needed: cin % 64 == 0 there
-  const int kpt = (p.cin + BK - 1) / BK;      // K chunks per tap
+  const int kpt = (p.cin + BK - 1) / BK;  // K chunks per tap
   const int nk = p.ntaps * kpt;
-  const int n0 = blockIdx.y * p.n_tile;
-  (void)K;
-
-  // tile origin
-  int img = 0, ty0 = 0, tx0 = 0;
-  if (tp.patch) {
-    const int per_img = tp.tiles_x * tp.tiles_y;
-    img = blockIdx.x / per_img;
-    const int r = blockIdx.x - img * per_img;
-    ty0 = (r / tp.tiles_x) * tp.bh;
-    tx0 = (r % tp.tiles_x) * tp.bw;
-  }
+  const int acc_stages = tp.acc_stages;
+  const int per_img = tp.tiles_x * tp.tiles_y;
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TMA_EPI_WARPS); }
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -476,56 +482,87 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)tp.a_bytes + b_bytes;
-      for (int kc = 0; kc < nk; kc++) {
-        const int s = kc % p.stages;
-        const uint32_t ph = (uint32_t)(kc / p.stages) & 1u;
-        const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
-        const int t = kc / kpt, ci = (kc - t * kpt) * BK;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), tx_bytes);
-        if (tp.patch)
-          tma_load_4d(a_s, &tmA, full_bar(s), ci, tx0 + p.dx[t], ty0 + p.dy[t], img);
-        else
-          tma_load_2d(a_s, &tmA, full_bar(s), ci, (int)blockIdx.x * BM);
-        tma_load_2d(b_s, &tmB, full_bar(s), p.wtap[t] * p.cin + ci, n0);
+      uint32_t it = 0;  // running K-chunk counter across tiles
+      for (int tile = blockIdx.x; tile < tp.total_tiles; tile += gridDim.x) {
+        const int mt = tile / tp.tiles_n, n0 = (tile - mt * tp.tiles_n) * p.n_tile;
+        int img = 0, ty0 = 0, tx0 = 0;
+        if (tp.patch) {
+          img = mt / per_img;
+          const int r = mt - img * per_img;
+          ty0 = (r / tp.tiles_x) * tp.bh;
+          tx0 = (r % tp.tiles_x) * tp.bw;
+        }
+        for (int kc = 0; kc < nk; kc++, it++) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1u;
+          const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
+          const int t = kc / kpt, ci = (kc - t * kpt) * BK;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), tx_bytes);
+          if (tp.patch)
+            tma_load_4d(a_s, &tmA, full_bar(s), ci, tx0 + p.dx[t], ty0 + p.dy[t], img);
+          else
+            tma_load_2d(a_s, &tmA, full_bar(s), ci, mt * BM);
+          tma_load_2d(b_s, &tmB, full_bar(s), p.wtap[t] * p.cin + ci, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.n_tile);
-      for (int kc = 0; kc < nk; kc++) {
-        const int s = kc % p.stages;
-        const uint32_t ph = (uint32_t)(kc / p.stages) & 1u;
-        mbar_wait(full_bar(s), ph);
+      uint32_t it = 0;
+      int i = 0;
+      for (int tile = blockIdx.x; tile < tp.total_tiles; tile += gridDim.x, i++) {
+        const int acc = i % acc_stages;
+        mbar_wait(tempty_bar(acc), (((uint32_t)(i / acc_stages)) & 1u) ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
-        const uint64_t ad = make_sdesc(a_s), bd = make_sdesc(b_s);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
+        for (int kc = 0; kc < nk; kc++, it++) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
+          const uint64_t ad = make_sdesc(a_s), bd = make_sdesc(b_s);
 #pragma unroll
-        for (int k = 0; k < BK / 16; k++) umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
-        umma_commit(empty_bar(s));
+          for (int k = 0; k < BK / 16; k++) umma_f16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(acc));
       }
-      umma_commit(tmem_full_bar);
     }
     __syncwarp();
     tc_fence_before();
   } else {
-    const int quarter = warp & 3;
+    const int quarter = warp & 3, ew = warp - 2, half = ew >> 2;  // warps 2..9 -> quarters 2,3,0,1,2,3,0,1; half 0 / 1
     const int row = quarter * 32 + lane;
-    int dp = -1;
-    if (tp.patch) {
-      const int ry = row / tp.bw, rx = row - ry * tp.bw;
-      const int oy = ty0 + ry, ox = tx0 + rx;
-      if (ry < tp.bh && oy < p.ho && ox < p.wo) dp = (img * p.ho + oy) * p.wo + ox;
-    } else {
-      const int64_t m = (int64_t)blockIdx.x * BM + row;
-      if (m < (int64_t)p.n * p.ho * p.wo) { dp = (int)m; img = (int)(m / ((int64_t)p.ho * p.wo)); }
+    uint8_t* stg = smem_raw + (base - raw) + stg_off + ew * STG_WARP;
+    int* drow = reinterpret_cast<int*>(smem_raw + (base - raw) + stg_off + TMA_EPI_WARPS * STG_WARP) + ew * 32;
+    // column split between the two warps of a quarter: multiples of 16, first half rounded up
+    const int csplit = ((p.n_tile / 16 + 1) / 2) * 16;
+    const int col_begin = half ? csplit : 0, col_end = half ? p.n_tile : csplit;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < tp.total_tiles; tile += gridDim.x, i++) {
+      const int mt = tile / tp.tiles_n, n0 = (tile - mt * tp.tiles_n) * p.n_tile;
+      int dp = -1, img = 0;
+      if (tp.patch) {
+        img = mt / per_img;
+        const int r = mt - img * per_img;
+        const int ry = row / tp.bw, rx = row - ry * tp.bw;
+        const int oy = (r / tp.tiles_x) * tp.bh + ry, ox = (r % tp.tiles_x) * tp.bw + rx;
+        if (ry < tp.bh && oy < p.ho && ox < p.wo) dp = (img * p.ho + oy) * p.wo + ox;
+      } else {
+        const uint32_t m = (uint32_t)mt * BM + row;
+        if (m < (uint32_t)(p.n * p.ho * p.wo)) { dp = (int)m; img = (int)(m / (uint32_t)(p.ho * p.wo)); }
+      }
+      const int acc = i % acc_stages;
+      mbar_wait(tfull_bar(acc), ((uint32_t)(i / acc_stages)) & 1u);
+      tc_fence_after();
+      epilogue_warp(p, tmem_base + (uint32_t)(acc * p.n_tile), quarter, lane, stg, drow, dp, img, n0, col_begin, col_end);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));  // all epilogue warps -> accumulator free
     }
-    mbar_wait(tmem_full_bar, 0u);
-    tc_fence_after();
-    float* stg = reinterpret_cast<float*>(smem_raw + (base - raw)) + quarter * (32 * STG_LD);
-    int* drow = reinterpret_cast<int*>(smem_raw + (base - raw) + 4 * 32 * STG_LD * 4) + quarter * 32;
-    epilogue_warp(p, tmem_base, quarter, lane, stg, drow, dp, img, n0);
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
@@ -591,22 +628,20 @@ int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
   TmaParams tp;
   memset(&tp, 0, sizeof(tp));
   p.n_tile = pick_n_tile(p.cout);
+  tp.acc_stages = (2 * p.n_tile <= 512) ? 2 : 1;
   p.tmem_cols = 32;
-  while (p.tmem_cols < p.n_tile) p.tmem_cols <<= 1;
+  while (p.tmem_cols < tp.acc_stages * p.n_tile) p.tmem_cols <<= 1;
   const int stage_bytes = BM * 128 + p.n_tile * 128;
-  const int kpt = (p.cin + BK - 1) / BK, nk = p.ntaps * kpt;
-  int stages = (96 * 1024) / stage_bytes;
+  const size_t stg = TMA_EPI_WARPS * STG_WARP + TMA_EPI_WARPS * 32 * 4;  // dedicated epilogue staging + row tables
+  int stages = (int)((110 * 1024 - stg) / stage_bytes);  // aim at two resident CTAs per SM
   stages = stages > 4 ? 4 : (stages < 2 ? 2 : stages);
-  if (stages > nk) stages = nk;
   p.stages = stages;
-  size_t pipe = (size_t)stages * stage_bytes;
-  const size_t stg = 4 * 32 * 68 * 4 + 4 * 32 * 4;
-  if (pipe < stg) pipe = (stg + 127) / 128 * 128;
+  const size_t pipe = ((size_t)stages * stage_bytes + stg + 127) / 128 * 128;
   p.pipe_bytes = (int)pipe;
-  const size_t smem = 1024 + pipe + 8 * (2 * stages + 1) + 16;
+  const size_t smem = 1024 + pipe + 8 * (2 * stages + 4) + 16;
 
   CUtensorMap tmA, tmB;
-  unsigned grid_x;
+  int tiles_m;
   if (p.ntaps == 1) {  // 1x1: rows are consecutive pixels
     tp.patch = 0;
     const int64_t M = (int64_t)p.n * p.hi * p.wi;
@@ -614,7 +649,8 @@ int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
     uint32_t box[2] = {BK, BM};
     if (make_map(&tmA, p.x, 2, dims, strides, box)) return 1;
     tp.a_bytes = BM * 128;
-    grid_x = (unsigned)((M + BM - 1) / BM);
+    tp.tiles_x = tp.tiles_y = 1;
+    tiles_m = (int)((M + BM - 1) / BM);
   } else {
     tp.patch = 1;
     pick_patch(p.hi, p.wi, &tp.bw, &tp.bh);
@@ -625,7 +661,7 @@ int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
     uint32_t box[4] = {BK, (uint32_t)tp.bw, (uint32_t)tp.bh, 1};
     if (make_map(&tmA, p.x, 4, dims, strides, box)) return 1;
     tp.a_bytes = tp.bw * tp.bh * 128;
-    grid_x = (unsigned)(p.n * tp.tiles_x * tp.tiles_y);
+    tiles_m = p.n * tp.tiles_x * tp.tiles_y;
   }
   {
     const int cout_rows = (p.cout + 7) / 8 * 8;
@@ -633,16 +669,28 @@ int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
     uint32_t box[2] = {BK, (uint32_t)p.n_tile};
     if (make_map(&tmB, p.w, 2, dims, strides, box)) return 1;
   }
+  tp.tiles_n = (p.cout + p.n_tile - 1) / p.n_tile;
+  tp.total_tiles = tiles_m * tp.tiles_n;
   tp.p = p;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
       yad_set_error("conv2d_tma: cannot raise the dynamic shared memory limit");
+      num_sms = 0;
       return 2;
     }
-    attr_set = true;
   }
-  dim3 grid(grid_x, (unsigned)((p.cout + p.n_tile - 1) / p.n_tile));
+  // resident CTAs per SM: shared memory and TMEM columns (512 per SM)
+  int per_sm = (int)((227 * 1024) / smem);
+  const int by_tmem = 512 / p.tmem_cols;
+  if (per_sm > by_tmem) per_sm = by_tmem;
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  int grid = num_sms * per_sm;
+  if (grid > tp.total_tiles) grid = tp.total_tiles;
   conv_tma_kernel<<<grid, TMA_THREADS, smem, st>>>(tp, tmA, tmB);
   YAD_LAUNCH_CHECK("conv2d_tma");
   (void)d;
@@ -673,7 +721,7 @@ int launch(TcParams& p, int64_t M, cudaStream_t st) {
   if (stages > nk) stages = nk < 1 ? 1 : nk;
   p.stages = stages;
   size_t pipe = (size_t)stages * stage_bytes;
-  const size_t stg = 4 * 32 * 68 * 4 + 4 * 32 * 4;  // epilogue staging (aliased onto the pipeline buffers) + row table
+  const size_t stg = 4 * STG_WARP + 4 * 32 * 4;  // epilogue staging (aliased onto the pipeline buffers) + row table
   if (pipe < stg) pipe = (stg + 127) / 128 * 128;
   p.pipe_bytes = (int)pipe;
   const size_t smem = 1024 + pipe + 8 * (2 * stages + 1) + 16;

@@ -240,6 +240,23 @@ __global__ void sppf_pool_kernel(yad_tensor x, yad_tensor y1, yad_tensor y2, yad
 template <typename T, typename F>
 __device__ __forceinline__ void block_pixel_sum(const yad_tensor& x, int64_t count, F pixel_offset, float* acc) {
   const int oct = x.c >> 3;
+  if (blockDim.x % oct == 0) {  // thread -> fixed octet, strided pixels: register accumulation, 8 smem atomics per thread in total
+    const int o = (threadIdx.x % oct) * 8, lane = threadIdx.x / oct, step = blockDim.x / oct;
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = 0.f;
+    for (int64_t j = lane; j < count; j += step) {
+      float v[8];
+      load8(reinterpret_cast<const T*>(x.ptr) + pixel_offset(j) + o, v);
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] += v[i];
+    }
+    if (lane < count) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) atomicAdd(&acc[o + i], s[i]);
+    }
+    return;
+  }
   const int64_t items = count * oct;
   for (int64_t it = threadIdx.x; it < items; it += blockDim.x) {
     int64_t j = it / oct;
