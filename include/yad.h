@@ -138,6 +138,12 @@ int yad_nchw_to_nhwc(const float* src, int c_src, const yad_tensor* y, int dtype
  * (engine/predictor.py:129-133: H2D of the uint8 batch, .float(), /= 255) */
 int yad_u8_to_nhwc(const uint8_t* src, int c_src, const yad_tensor* y, float scale, int dtype, void* stream);
 
+/* -- stem: layer 0 (Conv 3->16 k3 s2 p1, BN folded, activation) computed straight from the NCHW image (uint8 when img_is_u8, else fp32)
+ *    into an NHWC view: fuses BasePredictor.preprocess' device half (engine/predictor.py:129-133; fold 1/255 into wgt), the layout change
+ *    and Conv.forward_fuse (nn/modules/conv.py:52-54).  wgt: fp32 [16][9*cin] with K index = tap*cin + ci; bias fp32[16] or NULL. */
+int yad_stem_conv(const void* img, int img_is_u8, int n, int h, int w, int cin, const float* wgt, const float* bias, int act,
+                  const yad_tensor* y, int dtype, void* stream);
+
 /* -- a9: fused DFL softmax-expectation + make_anchors + dist2bbox(xywh) + x stride + class sigmoid
  *    (head.py:1181-1204,1236-1252; block.py:78-81; utils/tal.py:303-327).
  *    levels: nl raw head outputs; element (b, ch, anchor a of level l) at lvl_ptr[l][b*lvl_sb[l] + ch*lvl_sc[l] + a*lvl_sa[l]]

@@ -262,3 +262,17 @@ def test_nchw_to_nhwc():
     got = from_act(y)
     np.testing.assert_array_equal(got[:, :3].numpy(), img.numpy())
     assert float(got[:, 3:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("u8", [False, True])
+def test_stem_conv(dtype, u8):
+    g = torch.Generator().manual_seed(11)
+    img = torch.randint(0, 256, (2, 3, 64, 96), generator=g, dtype=torch.uint8) if u8 else torch.rand(2, 3, 64, 96, generator=g)
+    w = torch.randn(16, 3, 3, 3, generator=g) / 5
+    b = torch.randn(16, generator=g) * 0.1
+    x = img.float() / 255.0 if u8 else img
+    ref = F.silu(F.conv2d(x, w, b, 2, 1))
+    wq = (w / 255.0 if u8 else w).permute(0, 2, 3, 1).reshape(16, -1).contiguous()
+    y = ops.stem_conv(img.to(DEV), wq.to(DEV), b.to(DEV), Act.empty(2, 32, 48, 16, dtype, DEV))
+    assert rel_err(from_act(y), ref) < tol(dtype)

@@ -285,6 +285,39 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
         while (my >= p.hm) { my -= p.hm; img++; }
       }
     }
+    // DEFORM: sampling parameters of (row, tap) are computed once per CTA by the row's own thread (offsets, sigmoid(mask), bilinear
+    // weights with invalid corners zeroed, clamped corner position) and parked in smem; the gather below only does 4 loads + 32 FMAs.
+    float4* dpar_w = reinterpret_cast<float4*>(smem_raw + (((tmem_ptr_addr + 16u + 15u) & ~15u) - raw));
+    int* dpar_pos = reinterpret_cast<int*>(dpar_w + BM * MAX_TAPS);
+    if (DEFORM) {
+      const uint32_t m = (uint32_t)blockIdx.x * BM + tid, hw = (uint32_t)(p.hm * p.wm);
+      if ((int64_t)m < M) {
+        const int img = (int)(m / hw);
+        const int r = (int)(m - (uint32_t)img * hw);
+        const int my = r / p.wm, mx = r - my * p.wm;
+        const bf16* o = p.om + ((int64_t)(img * p.ho + my) * p.wo + mx) * p.om_ld;
+        for (int t = 0; t < p.ntaps; t++) {
+          const float ody = __bfloat162float(o[2 * t]), odx = __bfloat162float(o[2 * t + 1]);
+          const float mk = sigmoidf_(__bfloat162float(o[18 + t]));
+          const float fy_ = (float)(my + p.dy[t]) + ody, fx_ = (float)(mx + p.dx[t]) + odx;
+          float4 wq = make_float4(0.f, 0.f, 0.f, 0.f);
+          int y0 = 0, x0 = 0;
+          if (fy_ > -1.f && fx_ > -1.f && fy_ < (float)p.hi && fx_ < (float)p.wi) {
+            const float fy = floorf(fy_), fx = floorf(fx_);
+            y0 = (int)fy; x0 = (int)fx;
+            const float ly = fy_ - fy, lx = fx_ - fx;
+            const bool vy0 = y0 >= 0, vy1 = y0 + 1 < p.hi, vx0 = x0 >= 0, vx1 = x0 + 1 < p.wi;
+            wq.x = (vy0 && vx0) ? (1.f - ly) * (1.f - lx) * mk : 0.f;
+            wq.y = (vy0 && vx1) ? (1.f - ly) * lx * mk : 0.f;
+            wq.z = (vy1 && vx0) ? ly * (1.f - lx) * mk : 0.f;
+            wq.w = (vy1 && vx1) ? ly * lx * mk : 0.f;
+          }
+          dpar_w[tid * MAX_TAPS + t] = wq;
+          dpar_pos[tid * MAX_TAPS + t] = (y0 << 16) | (x0 & 0xFFFF);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // producer warps only
+    }
     for (int kc = 0; kc < nk; kc++) {
       const int s = kc % p.stages;
       const uint32_t ph = (uint32_t)(kc / p.stages) & 1u;
@@ -307,31 +340,29 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
           if ((unsigned)sy < (unsigned)p.hi && (unsigned)sx < (unsigned)p.wi)
             av[i] = ldg16(xk + (int64_t)((rimg[i] + sy) * p.wi + sx) * p.x_ld);
         } else {
-          // modulated deformable 3x3 (stride 1, pad 1): bilinear sample, zero outside (-1, H) x (-1, W)
-          const bf16* o = p.om + ((int64_t)(rimg[i] + my) * p.wo + mx) * p.om_ld;  // deformable: ho == hi
-          const float ody = __bfloat162float(o[2 * t]), odx = __bfloat162float(o[2 * t + 1]);
-          const float mk = sigmoidf_(__bfloat162float(o[18 + t]));
-          const float fy_ = (float)(my + p.dy[t]) + ody, fx_ = (float)(mx + p.dx[t]) + odx;
-          if (fy_ > -1.f && fx_ > -1.f && fy_ < (float)p.hi && fx_ < (float)p.wi) {
-            const float fy = floorf(fy_), fx = floorf(fx_);
-            const int y0 = (int)fy, x0 = (int)fx;
-            const float ly = fy_ - fy, lx = fx_ - fx;
-            const float wgt[4] = {(1.f - ly) * (1.f - lx) * mk, (1.f - ly) * lx * mk, ly * (1.f - lx) * mk, ly * lx * mk};
-            float acc[8];
+          // modulated deformable 3x3: parameters from smem, corners clamped into the map (their weights are already zero when invalid)
+          const int rrow = warp * 32 + 4 * i + sr;
+          const float4 wq = dpar_w[rrow * MAX_TAPS + t];
+          const int pos = dpar_pos[rrow * MAX_TAPS + t];
+          const int y0 = pos >> 16, x0 = (int)(short)(pos & 0xFFFF);
+          const int ya = max(y0, 0), yb = min(y0 + 1, p.hi - 1), xa = max(x0, 0), xb = min(x0 + 1, p.wi - 1);
+          const int ib = rimg[i];
+          const uint4 u00 = ldg16(xk + (int64_t)((ib + ya) * p.wi + xa) * p.x_ld), u01 = ldg16(xk + (int64_t)((ib + ya) * p.wi + xb) * p.x_ld);
+          const uint4 u10 = ldg16(xk + (int64_t)((ib + yb) * p.wi + xa) * p.x_ld), u11 = ldg16(xk + (int64_t)((ib + yb) * p.wi + xb) * p.x_ld);
+          float acc[8], v[8];
+          bf8_to_f(u00, v);
 #pragma unroll
-            for (int q = 0; q < 8; q++) acc[q] = 0.f;
+          for (int q = 0; q < 8; q++) acc[q] = wq.x * v[q];
+          bf8_to_f(u01, v);
 #pragma unroll
-            for (int c4 = 0; c4 < 4; c4++) {
-              const int yy = y0 + (c4 >> 1), xx = x0 + (c4 & 1);
-              if (yy >= 0 && yy < p.hi && xx >= 0 && xx < p.wi) {
-                float v[8];
-                bf8_to_f(ldg16(xk + (int64_t)((rimg[i] + yy) * p.wi + xx) * p.x_ld), v);
+          for (int q = 0; q < 8; q++) acc[q] = fmaf(wq.y, v[q], acc[q]);
+          bf8_to_f(u10, v);
 #pragma unroll
-                for (int q = 0; q < 8; q++) acc[q] = fmaf(wgt[c4], v[q], acc[q]);
-              }
-            }
-            av[i] = f_to_bf8(acc);
-          }
+          for (int q = 0; q < 8; q++) acc[q] = fmaf(wq.z, v[q], acc[q]);
+          bf8_to_f(u11, v);
+#pragma unroll
+          for (int q = 0; q < 8; q++) acc[q] = fmaf(wq.w, v[q], acc[q]);
+          av[i] = f_to_bf8(acc);
         }
       }
       mbar_wait(empty_bar(s), ph ^ 1u);
@@ -724,7 +755,7 @@ int launch(TcParams& p, int64_t M, cudaStream_t st) {
   const size_t stg = 4 * STG_WARP + 4 * 32 * 4;  // epilogue staging (aliased onto the pipeline buffers) + row table
   if (pipe < stg) pipe = (stg + 127) / 128 * 128;
   p.pipe_bytes = (int)pipe;
-  const size_t smem = 1024 + pipe + 8 * (2 * stages + 1) + 16;
+  const size_t smem = 1024 + pipe + 8 * (2 * stages + 1) + 16 + (p.deform ? 32 + BM * MAX_TAPS * 20 : 0);
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||

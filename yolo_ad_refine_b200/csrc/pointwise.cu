@@ -43,6 +43,56 @@ __global__ void u8_to_nhwc_kernel(const uint8_t* __restrict__ src, int c_src, fl
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Stem: layer 0 of the model (Conv 3->16, k3 s2 p1, BN folded, SiLU) straight from the NCHW image (uint8 or fp32) to NHWC.
+// Fuses the predictor's uint8 -> float / 255 (engine/predictor.py:129-133, the scale is folded into the weights), the NCHW -> NHWC
+// change and nn/modules/conv.py:52-54 into one pass: reads 3 bytes per input pixel instead of a padded 8-channel bf16 copy.
+// One thread per output pixel, COUT accumulators in registers, weights in shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T, typename IN, int COUT>
+__global__ void __launch_bounds__(128) stem_conv_kernel(const IN* __restrict__ img, int n, int h, int w, int cin, const float* __restrict__ wgt,
+                                                        const float* __restrict__ bias, int act, yad_tensor y) {
+  extern __shared__ float sw[];  // [27 or 9*cin][COUT] then bias[COUT]
+  const int K = 9 * cin;
+  for (int i = threadIdx.x; i < K * COUT; i += blockDim.x) {
+    int co = i % COUT, k = i / COUT;
+    sw[i] = wgt[co * K + k];
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sw[K * COUT + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int ho = y.h, wo = y.w;
+  const int64_t total = (int64_t)n * ho * wo;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(p % wo), oy = (int)((p / wo) % ho), b = (int)(p / ((int64_t)wo * ho));
+    float acc[COUT];
+#pragma unroll
+    for (int i = 0; i < COUT; i++) acc[i] = sw[K * COUT + i];
+    for (int ky = 0; ky < 3; ky++) {
+      const int iy = 2 * oy - 1 + ky;
+      if (iy < 0 || iy >= h) continue;
+      for (int kx = 0; kx < 3; kx++) {
+        const int ix = 2 * ox - 1 + kx;
+        if (ix < 0 || ix >= w) continue;
+        for (int ci = 0; ci < cin; ci++) {
+          const float v = (float)img[((int64_t)(b * cin + ci) * h + iy) * w + ix];
+          const float* wr = sw + ((ky * 3 + kx) * cin + ci) * COUT;  // K index = tap * cin + ci, as in the packed conv weights
+#pragma unroll
+          for (int i = 0; i < COUT; i++) acc[i] = fmaf(v, wr[i], acc[i]);
+        }
+      }
+    }
+    T* o = reinterpret_cast<T*>(y.ptr) + p * y.ld;
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = acc[c0 + i];
+      apply_act_n<8>(v, act);
+      store8(o + c0, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // GroupNorm statistics + apply
 // ------------------------------------------------------------------------------------------------------------------
 // grid (chunks, n).  stats[n][g][2] += (sum, sumsq) in double.
@@ -670,6 +720,26 @@ int yad_u8_to_nhwc(const uint8_t* src, int c_src, const yad_tensor* y, float sca
   int64_t total = (int64_t)y->n * y->h * y->w;
   YAD_DISPATCH_DTYPE(dtype, u8_to_nhwc_kernel<T><<<grid_for(total), TPB, 0, st>>>(src, c_src, scale, *y);)
   YAD_LAUNCH_CHECK("u8_to_nhwc");
+  return 0;
+}
+
+int yad_stem_conv(const void* img, int img_is_u8, int n, int h, int w, int cin, const float* wgt, const float* bias, int act,
+                  const yad_tensor* y, int dtype, void* stream) {
+  CHECK_VIEW(y, "stem_conv");
+  YAD_CHECK(y->c == 16, "stem_conv: built for 16 output channels (layer 0 of the yaml at scale n), got %d", y->c);
+  YAD_CHECK(y->n == n && y->h == (h + 2 - 3) / 2 + 1 && y->w == (w + 2 - 3) / 2 + 1, "stem_conv: output shape does not match a k3 s2 p1 convolution");
+  YAD_CHECK(cin >= 1 && cin <= 4, "stem_conv: cin %d unsupported", cin);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = (int64_t)n * y->h * y->w;
+  const size_t smem = (size_t)(9 * cin * 16 + 16) * sizeof(float);
+  const int grid = grid_for(total, 128);
+  YAD_DISPATCH_DTYPE(dtype, {
+    if (img_is_u8)
+      stem_conv_kernel<T, uint8_t, 16><<<grid, 128, smem, st>>>((const uint8_t*)img, n, h, w, cin, wgt, bias, act, *y);
+    else
+      stem_conv_kernel<T, float, 16><<<grid, 128, smem, st>>>((const float*)img, n, h, w, cin, wgt, bias, act, *y);
+  })
+  YAD_LAUNCH_CHECK("stem_conv");
   return 0;
 }
 

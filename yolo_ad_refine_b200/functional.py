@@ -325,16 +325,38 @@ def ayhead(ctx, p, xs, strides=(8, 16, 32), nc=80, reg_max=16, decode=True):
 # --------------------------------------------------------------------------------------------------------------------
 # whole model (z-yaml/yolo11-701-YOLO-AD-Refine.yaml at scale n; nn/tasks.py:141-168 _predict_once)
 # --------------------------------------------------------------------------------------------------------------------
+def stem(ctx, p, img):
+    """Layer 0: Conv(3 -> 16, k3, s2) + BN + SiLU straight from the NCHW image.  uint8 images carry the predictor's /255 (engine/predictor.py:129-133)
+    folded into the weights.  Falls back to layout conversion + the generic conv for any other first layer."""
+    P = ctx.P
+    n, cin, H, W = img.shape
+    w0 = P.sd[p + ".conv.weight"]
+    if tuple(w0.shape[1:]) == (cin, 3, 3) and w0.shape[0] == 16 and cin <= 4:
+        u8 = img.dtype == torch.uint8
+
+        def fold():
+            wf, bf = w0.float(), None
+            if p + ".bn.weight" in P.sd:
+                wf, bf = fold_bn(wf, P.sd[p + ".bn.weight"].float(), P.sd[p + ".bn.bias"].float(), P.sd[p + ".bn.running_mean"].float(),
+                                 P.sd[p + ".bn.running_var"].float(), P.sd.get(p + ".conv.bias"))
+            else:
+                bf = P.sd[p + ".conv.bias"].float()
+            if u8:
+                wf = wf / 255.0
+            return (wf.permute(0, 2, 3, 1).reshape(16, -1).contiguous().to(ctx.device), bf.contiguous().to(ctx.device))
+
+        wq, bq = P.misc(p + (".stem_u8" if u8 else ".stem_f32"), fold)
+        return ops.stem_conv(img, wq, bq, ctx.act(n, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 16))
+    x = ops.u8_to_nhwc(img, ctx.act(n, H, W, 8)) if img.dtype == torch.uint8 else ops.nchw_to_nhwc(img, ctx.act(n, H, W, 8))
+    return conv_bn_act(ctx, p, x, 2)
+
+
 def forward_model(ctx, img, decode=True, keep_layers=False):
     """img: fp32 (n, 3, H, W) in [0, 1], or uint8 (n, 3, H, W) in [0, 255], on the device.  Returns (y, raw_levels[, layer outputs])."""
     n, _, H, W = img.shape
     assert H % 32 == 0 and W % 32 == 0, "image size must be a multiple of the maximum stride 32"
     L = {}
-    if img.dtype == torch.uint8:  # the reference's predictor ships uint8 and divides by 255 on the device (engine/predictor.py:129-133)
-        x = ops.u8_to_nhwc(img, ctx.act(n, H, W, 8))
-    else:
-        x = ops.nchw_to_nhwc(img, ctx.act(n, H, W, 8))
-    L[0] = conv_bn_act(ctx, "model.0", x, 2)
+    L[0] = stem(ctx, "model.0", img)
     L[1] = conv_bn_act(ctx, "model.1", L[0], 2)
     L[2] = c3k2(ctx, "model.2", L[1])
     L[3] = conv_bn_act(ctx, "model.3", L[2], 2)

@@ -238,6 +238,14 @@ def u8_to_nhwc(img_u8, y, scale=1.0 / 255.0):
     return y
 
 
+def stem_conv(img, wgt, bias, y, act=ACT_SILU):
+    """img: (n, cin, h, w) contiguous uint8 or fp32 on the device; wgt fp32 (16, 9*cin); y: NHWC (n, h/2, w/2, 16)"""
+    assert img.is_contiguous() and img.dtype in (torch.uint8, torch.float32)
+    n, cin, h, w = img.shape
+    _call("yad_stem_conv", _p(img), int(img.dtype == torch.uint8), n, h, w, cin, _p(wgt), _p(bias), act, y.yt(), dt(y.dtype), stream_ptr())
+    return y
+
+
 def nchw_to_nhwc(img, y):
     """img: fp32 (n, c, h, w) contiguous"""
     assert img.dtype == torch.float32 and img.is_contiguous()
