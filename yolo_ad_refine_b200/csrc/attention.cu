@@ -167,6 +167,131 @@ __global__ void __launch_bounds__(QB) mha_kernel(const T* __restrict__ qkv, int6
   }
 }
 
+// ---- multi-head self-attention core on tensor cores (bf16 storage): flash-style streaming softmax ---------------------------------
+// One CTA = 64 queries of one (image, head): 4 warps x 16 query rows.  S = Q K^T and O += P V run on mma.sync.m16n8k16 (bf16 -> fp32);
+// K / V tiles of 64 keys are staged in shared memory with a 144-byte row pitch (conflict-free ldmatrix), P never leaves registers
+// (the S accumulator layout is re-used as the A fragment of the second GEMM).  [tcgen05 / TMEM version: next round.]
+constexpr int FA_Q = 64, FA_K = 64, FA_PITCH = 72;  // pitch in bf16 elements
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(128) mha_mma_kernel(const bf16* __restrict__ qkv, int64_t ld, int Tn, int c, int heads, bf16* __restrict__ out,
+                                                      int64_t out_ld, float scale_log2e) {
+  __shared__ __align__(16) bf16 Ks[FA_K * FA_PITCH];
+  __shared__ __align__(16) bf16 Vs[FA_K * FA_PITCH];
+  const int n = blockIdx.y / heads, h = blockIdx.y % heads;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
+  const bf16* base = qkv + (int64_t)n * Tn * ld + h * HD;
+  const int q0 = blockIdx.x * FA_Q + warp * 16;  // this warp's first query row
+  // Q fragments (A operand, 16 x 64): rows g and g + 8, k = kt * 16 + 2 * q4 (+8)
+  uint32_t qa[4][4];
+#pragma unroll
+  for (int kt = 0; kt < 4; kt++) {
+    const int r0 = q0 + g, r1 = q0 + g + 8, col = kt * 16 + 2 * q4;
+    qa[kt][0] = r0 < Tn ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r0 * ld + col) : 0u;
+    qa[kt][1] = r1 < Tn ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r1 * ld + col) : 0u;
+    qa[kt][2] = r0 < Tn ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r0 * ld + col + 8) : 0u;
+    qa[kt][3] = r1 < Tn ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r1 * ld + col + 8) : 0u;
+  }
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) o[j][i] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const uint32_t ks_addr = (uint32_t)__cvta_generic_to_shared(Ks), vs_addr = (uint32_t)__cvta_generic_to_shared(Vs);
+
+  for (int k0 = 0; k0 < Tn; k0 += FA_K) {
+    __syncthreads();
+    for (int ch = tid; ch < FA_K * 8; ch += 128) {  // 64 rows x 8 chunks of 16 bytes, 8 lanes per row
+      const int row = ch >> 3, cc = (ch & 7) * 8;
+      uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
+      if (k0 + row < Tn) {
+        kv = *reinterpret_cast<const uint4*>(base + (int64_t)(k0 + row) * ld + c + cc);
+        vv = *reinterpret_cast<const uint4*>(base + (int64_t)(k0 + row) * ld + 2 * c + cc);
+      }
+      *reinterpret_cast<uint4*>(Ks + row * FA_PITCH + cc) = kv;
+      *reinterpret_cast<uint4*>(Vs + row * FA_PITCH + cc) = vv;
+    }
+    __syncthreads();
+    // S = Q K^T : 8 key tiles of 8
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) s[j][i] = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < 4; kt++) {
+        uint32_t b0, b1;  // B fragment: rows = keys j*8 + (lane & 7), two 8x8 matrices along d
+        ldsm_x2(b0, b1, ks_addr + (uint32_t)(((j * 8 + (lane & 7)) * FA_PITCH + kt * 16 + ((lane >> 3) & 1) * 8) * 2));
+        mma_bf16_16816(s[j], qa[kt], b0, b1);
+      }
+    }
+    // mask the key tail, running max / sum (rows g and g + 8 of this warp)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int key = k0 + j * 8 + 2 * q4;
+      if (key >= Tn) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+      if (key + 1 >= Tn) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float c0 = exp2f((m0 - mn0) * scale_log2e), c1 = exp2f((m1 - mn1) * scale_log2e);  // m = -inf on the first tile -> 0
+    l0 *= c0; l1 *= c1;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
+    const float mb0 = mn0 * scale_log2e, mb1 = mn1 * scale_log2e;
+    uint32_t pa[4][4];  // P as A fragments: key tile pairs (2kt, 2kt+1)
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float p0 = exp2f(fmaf(s[j][0], scale_log2e, -mb0)), p1 = exp2f(fmaf(s[j][1], scale_log2e, -mb0));
+      const float p2 = exp2f(fmaf(s[j][2], scale_log2e, -mb1)), p3 = exp2f(fmaf(s[j][3], scale_log2e, -mb1));
+      l0 += p0 + p1; l1 += p2 + p3;
+      pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
+      pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+    }
+    // O += P V : k = keys (4 tiles of 16), n = d (8 tiles of 8); V fragments via transposed ldmatrix
+#pragma unroll
+    for (int kt = 0; kt < 4; kt++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, vs_addr + (uint32_t)(((kt * 16 + (lane & 15)) * FA_PITCH + j * 8) * 2));
+        mma_bf16_16816(o[j], pa[kt], b0, b1);
+      }
+    }
+    m0 = mn0; m1 = mn1;
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int r0 = q0 + g, r1 = q0 + g + 8;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int col = h * HD + j * 8 + 2 * q4;
+    if (r0 < Tn) *reinterpret_cast<uint32_t*>(out + ((int64_t)n * Tn + r0) * out_ld + col) = pack_bf16(o[j][0] * i0, o[j][1] * i0);
+    if (r1 < Tn) *reinterpret_cast<uint32_t*>(out + ((int64_t)n * Tn + r1) * out_ld + col) = pack_bf16(o[j][2] * i1, o[j][3] * i1);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -194,8 +319,14 @@ int yad_mha(const yad_tensor* qkv, int heads, const yad_tensor* out, int dtype, 
   YAD_CHECK(qkv->c == 3 * c && c == heads * HD, "mha: only head_dim 64 is built (c=%d, heads=%d)", c, heads);
   YAD_CHECK(out->n == qkv->n && out->h * out->w == Tn, "mha: token count mismatch");
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((Tn + QB - 1) / QB, qkv->n * heads);
   const float scale = 1.0f / sqrtf((float)HD);
+  if (dtype == YAD_BF16) {  // tensor-core path
+    dim3 g2((Tn + FA_Q - 1) / FA_Q, qkv->n * heads);
+    mha_mma_kernel<<<g2, 128, 0, st>>>((const bf16*)qkv->ptr, qkv->ld, Tn, c, heads, (bf16*)out->ptr, out->ld, scale * 1.44269504088896340736f);
+    YAD_LAUNCH_CHECK("mha");
+    return 0;
+  }
+  dim3 grid((Tn + QB - 1) / QB, qkv->n * heads);
   YAD_DISPATCH_DTYPE(dtype, mha_kernel<T><<<grid, QB, 0, st>>>((const T*)qkv->ptr, qkv->ld, Tn, c, heads, (T*)out->ptr, out->ld, scale);)
   YAD_LAUNCH_CHECK("mha");
   return 0;
