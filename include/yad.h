@@ -45,6 +45,10 @@ typedef struct {
   int32_t mul_ld;
   const void* add;
   int32_t add_ld;
+  /* optional fused GroupNorm statistics of the conv output (after scale / bias / act / alpha, before mul / add): stats double
+   * [n][gn_groups][2] += (sum, sum of squares); yad_conv2d zeroes the buffer itself.  Used by Conv_GN (nn/modules/head.py:1265-1279). */
+  double* gn_stats;
+  int32_t gn_groups;
 } yad_epilogue;
 
 typedef struct {

@@ -18,7 +18,7 @@ class YadTensor(C.Structure):
 class YadEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("img_scale", C.c_void_p), ("pix_scale", C.c_void_p), ("pix_scale_ld", C.c_int32),
                 ("act", C.c_int32), ("alpha", C.c_float), ("mul", C.c_void_p), ("mul_ld", C.c_int32), ("add", C.c_void_p),
-                ("add_ld", C.c_int32)]
+                ("add_ld", C.c_int32), ("gn_stats", C.c_void_p), ("gn_groups", C.c_int32)]
 
 
 class YadConvDesc(C.Structure):

@@ -39,6 +39,14 @@ int yad_conv2d(const yad_tensor* x, const void* w, const yad_conv_desc* d, const
     YAD_CHECK(yad_conv2d_tc_supported(x, d, y), "conv2d: shape not supported by the tcgen05 path");
     return yad_conv2d_tc(x, w, d, e, y, stream);
   }
+  if (e->gn_stats) {  // the SIMT kernel has no fused statistics: run it, then the stand-alone statistics kernel on its output
+    yad_epilogue e2 = *e;
+    e2.gn_stats = nullptr;
+    YAD_CHECK(e->mul == nullptr && e->add == nullptr, "conv2d: fused GroupNorm statistics cannot be combined with mul / add");
+    int r = yad_conv2d_simt(x, w, d, &e2, y, dtype, stream);
+    if (r) return r;
+    return yad_gn_stats(y, e->gn_groups, e->gn_stats, dtype, stream);
+  }
   return yad_conv2d_simt(x, w, d, e, y, dtype, stream);
 }
 

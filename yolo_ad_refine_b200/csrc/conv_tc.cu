@@ -39,6 +39,7 @@ struct TcParams {
   int deform, om_ld;
   int n_tile, stages, tmem_cols, pipe_bytes;
   int out_f32;
+  int cout_real;  // channel count GroupNorm statistics are defined over (= cout of the view)
   yad_epilogue e;
 };
 
@@ -136,6 +137,56 @@ __device__ __forceinline__ void apply_act_bf16_n(float (&v)[N], int act) {
   }
 }
 
+// Fused GroupNorm statistics: the 16 freshly computed output channels [co, co + 16) of this thread's row are folded into per-(image, group)
+// sums.  cpg = channels per group in {4, 8, 16} (host-checked).  Rows of a warp normally belong to one image: warp-shuffle reduction and
+// one double atomicAdd pair per group; a warp that straddles two images falls back to per-thread atomics.
+template <int CPG>
+__device__ __forceinline__ void gn_accumulate_t(const TcParams& p, const float (&v)[16], int co, int dp, int img) {
+  constexpr int NG = 16 / CPG;
+  const int groups = p.e.gn_groups;
+  const bool valid = dp >= 0;
+  const int img0 = __shfl_sync(0xffffffffu, valid ? img : -1, 0);
+  const bool uniform = __all_sync(0xffffffffu, !valid || img == img0) && img0 >= 0;
+  float s[NG], q[NG];
+#pragma unroll
+  for (int g = 0; g < NG; g++) {
+    s[g] = 0.f; q[g] = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPG; i++) { const float x = valid ? v[g * CPG + i] : 0.f; s[g] += x; q[g] = fmaf(x, x, q[g]); }
+  }
+  const int g0 = co / CPG;
+  if (uniform) {
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { s[g] += __shfl_xor_sync(0xffffffffu, s[g], o); q[g] += __shfl_xor_sync(0xffffffffu, q[g], o); }
+    }
+    // lanes 0 .. 2*NG-1 each issue one atomic
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+      if (g0 + g < groups) {
+        if (lane == 2 * g) atomicAdd(&p.e.gn_stats[((int64_t)img0 * groups + g0 + g) * 2], (double)s[g]);
+        if (lane == 2 * g + 1) atomicAdd(&p.e.gn_stats[((int64_t)img0 * groups + g0 + g) * 2 + 1], (double)q[g]);
+      }
+    }
+  } else if (valid) {
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+      if (g0 + g < groups) {
+        atomicAdd(&p.e.gn_stats[((int64_t)img * groups + g0 + g) * 2], (double)s[g]);
+        atomicAdd(&p.e.gn_stats[((int64_t)img * groups + g0 + g) * 2 + 1], (double)q[g]);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void gn_accumulate(const TcParams& p, const float (&v)[16], int co, int dp, int img) {
+  const int cpg = p.cout_real / p.e.gn_groups;
+  if (cpg == 4) gn_accumulate_t<4>(p, v, co, dp, img);
+  else if (cpg == 8) gn_accumulate_t<8>(p, v, co, dp, img);
+  else gn_accumulate_t<16>(p, v, co, dp, img);
+}
+
 constexpr int STG_ROW = 144;            // bytes per staged row: 64 bf16 + 16 (16-byte aligned rows, conflict-free 128-bit accesses)
 constexpr int STG_WARP = 32 * STG_ROW;  // staging bytes per epilogue warp
 
@@ -189,6 +240,7 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_a
 #pragma unroll
         for (int i = 0; i < 16; i++) v[i] *= e.alpha;
       }
+      if (e.gn_stats) gn_accumulate(p, v, co, dp, img);
       float lo[8], hi[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) { lo[i] = v[i]; hi[i] = v[8 + i]; }
@@ -580,8 +632,8 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
         img = mt / per_img;
         const int r = mt - img * per_img;
         const int ry = row / tp.bw, rx = row - ry * tp.bw;
-        const int oy = (r / tp.tiles_x) * tp.bh + ry, ox = (r % tp.tiles_x) * tp.bw + rx;
-        if (ry < tp.bh && oy < p.ho && ox < p.wo) dp = (img * p.ho + oy) * p.wo + ox;
+        const int oy = (r / tp.tiles_x) * tp.bh + ry, ox = (r % tp.tiles_x) * tp.bw + rx;  // position in the logical (hm x wm) grid
+        if (ry < tp.bh && oy < p.hm && ox < p.wm) dp = (img * p.ho + p.os * oy + p.py) * p.wo + (p.os * ox + p.px);
       } else {
         const uint32_t m = (uint32_t)mt * BM + row;
         if (m < (uint32_t)(p.n * p.ho * p.wo)) { dp = (int)m; img = (int)(m / (uint32_t)(p.ho * p.wo)); }
@@ -673,7 +725,7 @@ int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
 
   CUtensorMap tmA, tmB;
   int tiles_m;
-  if (p.ntaps == 1) {  // 1x1: rows are consecutive pixels
+  if (p.ntaps == 1 && p.os == 1 && p.dy[0] == 0 && p.dx[0] == 0) {  // 1x1: rows are consecutive pixels
     tp.patch = 0;
     const int64_t M = (int64_t)p.n * p.hi * p.wi;
     uint64_t dims[2] = {(uint64_t)p.cin, (uint64_t)M}, strides[1] = {(uint64_t)p.x_ld * 2};
@@ -684,9 +736,9 @@ int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
     tiles_m = (int)((M + BM - 1) / BM);
   } else {
     tp.patch = 1;
-    pick_patch(p.hi, p.wi, &tp.bw, &tp.bh);
-    tp.tiles_x = (p.wi + tp.bw - 1) / tp.bw;
-    tp.tiles_y = (p.hi + tp.bh - 1) / tp.bh;
+    pick_patch(p.hm, p.wm, &tp.bw, &tp.bh);
+    tp.tiles_x = (p.wm + tp.bw - 1) / tp.bw;
+    tp.tiles_y = (p.hm + tp.bh - 1) / tp.bh;
     uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)p.wi, (uint64_t)p.hi, (uint64_t)p.n};
     uint64_t strides[3] = {(uint64_t)p.x_ld * 2, (uint64_t)p.wi * p.x_ld * 2, (uint64_t)p.hi * p.wi * p.x_ld * 2};
     uint32_t box[4] = {BK, (uint32_t)tp.bw, (uint32_t)tp.bh, 1};
@@ -793,8 +845,16 @@ int yad_conv2d_tc(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
   p.w_row = d->kh * d->kw * x->c;
   p.om_ld = d->offmask_ld;
   p.e = *e;
+  p.cout_real = y->c;
   YAD_CHECK(x->n == y->n, "conv2d: batch mismatch %d vs %d", x->n, y->n);
   cudaStream_t st = (cudaStream_t)stream;
+  if (e->gn_stats) {
+    const int cpg = e->gn_groups > 0 ? y->c / e->gn_groups : 0;
+    YAD_CHECK(e->gn_groups > 0 && y->c % e->gn_groups == 0 && (cpg == 4 || cpg == 8 || cpg == 16),
+              "conv2d: fused GroupNorm statistics need 4, 8 or 16 channels per group (got %d channels / %d groups)", y->c, e->gn_groups);
+    YAD_CHECK(d->mode != YAD_CONV_TRANSPOSED, "conv2d: fused GroupNorm statistics are not built for the transposed mode");
+    cudaMemsetAsync(e->gn_stats, 0, sizeof(double) * 2 * e->gn_groups * y->n, st);
+  }
   if (d->mode == YAD_CONV_NORMAL || d->mode == YAD_CONV_DEFORM) {
     if (d->mode == YAD_CONV_NORMAL) {
       YAD_CHECK(y->h == (x->h + 2 * d->pad_h - d->kh) / d->stride + 1 && y->w == (x->w + 2 * d->pad_w - d->kw) / d->stride + 1,
@@ -827,7 +887,9 @@ int yad_conv2d_tc(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
             p.ntaps++;
           }
         }
-        int r = launch(p, (int64_t)x->n * p.hm * p.wm, st);
+        // each phase is a stride-1 convolution over the input grid with 1, 2 or 4 taps: TMA-eligible when cin % 64 == 0
+        const bool tma_ok = d->impl != 3 && (x->c % BK) == 0 && !((uintptr_t)x->ptr & 15) && get_encode() != nullptr;
+        int r = tma_ok ? launch_tma(p, d, st) : launch(p, (int64_t)x->n * p.hm * p.wm, st);
         if (r) return r;
       }
     return 0;

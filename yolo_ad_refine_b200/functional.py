@@ -54,11 +54,12 @@ def conv_bn_act(ctx, p, x, stride=1, out=None, add=None):
 def conv_gn_act(ctx, p, x, out=None, add=None, act=ACT_SILU, img_scale=None):
     """nn/modules/head.py:1265-1279 Conv_GN: conv(bias=False) -> GroupNorm -> SiLU"""
     cw = ctx.P.conv(p + ".conv.weight")
-    t = conv(ctx, x, cw, img_scale=img_scale)
     g = gn_groups(ctx.P.sd[p + ".conv.weight"].shape[0])
+    stats = ctx.f64(x.n, g, 2)
+    t = conv(ctx, x, cw, img_scale=img_scale, gn_stats=stats, gn_groups=g)  # statistics accumulated in the conv epilogue
     if out is None:
         out = ctx.act(t.n, t.h, t.w, t.c)
-    return ops.group_norm(t, out, ctx.f64(t.n, g, 2), g, ctx.P.f32(p + ".gn.weight"), ctx.P.f32(p + ".gn.bias"), GN_EPS, act, add)
+    return ops.group_norm(t, out, stats, g, ctx.P.f32(p + ".gn.weight"), ctx.P.f32(p + ".gn.bias"), GN_EPS, act, add, stats_ready=True)
 
 
 def mlca(ctx, p, x, out, add=None):
@@ -123,9 +124,10 @@ def ela_hsfpn(ctx, p, x, flag=True, out=None):
         out = ctx.act(n, h, w, c)
 
     def branch(means):
-        t = conv(ctx, means, cw)
+        stats = ctx.f64(means.n, 16, 2)
+        t = conv(ctx, means, cw, gn_stats=stats, gn_groups=16)
         g = ctx.act(t.n, t.h, t.w, t.c)
-        return ops.group_norm(t, g, ctx.f64(t.n, 16, 2), 16, gamma, beta, GN_EPS, ACT_SIGMOID)
+        return ops.group_norm(t, g, stats, 16, gamma, beta, GN_EPS, ACT_SIGMOID, stats_ready=True)
 
     if h == w:  # one batched pass over (2n, L, 1, c)
         means = ctx.act(2 * n, h, 1, c)
@@ -296,9 +298,10 @@ def ayhead_level(ctx, p, x, i):
     cls_e = conv_gn_act(ctx, p + ".rep_block_cls.conv2", conv_gn_act(ctx, p + ".rep_block_cls.conv1", cls2), add=cls2)
     # DyDCNv2 head.py:751-782 (offsets / mask from `feat`, head.py:1155-1159) + GroupNorm(16) + CoordAtt
     om = conv(ctx, feat, P.conv(p + ".spatial_conv_offset.weight", p + ".spatial_conv_offset.bias"))
-    ra = conv(ctx, reg2, P.conv(p + ".DyDCNV2.conv.weight"), mode=ops.CONV_DEFORM, offmask=om)
-    ra = ops.group_norm(ra, ctx.act(n, h, w, fc), ctx.f64(n, 16, 2), 16, P.f32(p + ".DyDCNV2.norm.weight"), P.f32(p + ".DyDCNV2.norm.bias"),
-                        GN_EPS, ACT_NONE)
+    dstats = ctx.f64(n, 16, 2)
+    ra = conv(ctx, reg2, P.conv(p + ".DyDCNV2.conv.weight"), mode=ops.CONV_DEFORM, offmask=om, gn_stats=dstats, gn_groups=16)
+    ra = ops.group_norm(ra, ctx.act(n, h, w, fc), dstats, 16, P.f32(p + ".DyDCNV2.norm.weight"), P.f32(p + ".DyDCNV2.norm.bias"),
+                        GN_EPS, ACT_NONE, stats_ready=True)
     reg_e = coord_att(ctx, p + ".coord_attention_reg", ra)
     # cls_prob head.py:1168-1169
     cp = conv(ctx, feat, P.conv(p + ".cls_prob_conv.0.weight", p + ".cls_prob_conv.0.bias"), act=ACT_RELU)

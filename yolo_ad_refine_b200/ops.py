@@ -125,14 +125,14 @@ def _ap(a):
 
 
 def conv2d(x, w, y, bias=None, kh=1, kw=1, stride=1, pad_h=0, pad_w=0, act=ACT_NONE, alpha=1.0, img_scale=None, pix_scale=None,
-           mul=None, add=None, mode=CONV_NORMAL, offmask=None, impl=0):
+           mul=None, add=None, mode=CONV_NORMAL, offmask=None, impl=0, gn_stats=None, gn_groups=0):
     """y = epilogue(conv(x, w)); w packed [cout][kh*kw][cin] in the activation dtype."""
     d = YadConvDesc(mode, kh, kw, stride, pad_h, pad_w, None if offmask is None else offmask.ptr, 0 if offmask is None else offmask.ld, impl)
     mp, mld = _ap(mul)
     adp, ald = _ap(add)
     psp, psld = _ap(pix_scale)
     e = YadEpilogue(None if bias is None else bias.data_ptr(), None if img_scale is None else img_scale.data_ptr(),
-                    psp, psld, act, alpha, mp, mld, adp, ald)
+                    psp, psld, act, alpha, mp, mld, adp, ald, None if gn_stats is None else gn_stats.data_ptr(), gn_groups)
     flops = 2.0 * y.n * y.h * y.w * y.c * kh * kw * x.c if mode != CONV_TRANSPOSED else 2.0 * x.n * x.h * x.w * y.c * kh * kw * x.c
     meta = None
     if PROFILE is not None:
@@ -149,10 +149,10 @@ def dwconv(x, w, y, bias=None, scale=None, shift=None, k=3, act=ACT_NONE, gate_s
     return y
 
 
-def group_norm(x, y, stats, groups, gamma, beta, eps=1e-5, act=ACT_NONE, add=None):
-    """stats: double (n, groups, 2) scratch"""
-    L = lib()
-    _call("yad_gn_stats", x.yt(), groups, _p(stats), dt(x.dtype), stream_ptr())
+def group_norm(x, y, stats, groups, gamma, beta, eps=1e-5, act=ACT_NONE, add=None, stats_ready=False):
+    """stats: double (n, groups, 2) scratch; stats_ready: already filled by the producing conv's fused epilogue"""
+    if not stats_ready:
+        _call("yad_gn_stats", x.yt(), groups, _p(stats), dt(x.dtype), stream_ptr())
     adp, ald = _ap(add)
     _call("yad_gn_apply", x.yt(), _p(stats), groups, _p(gamma), _p(beta), eps, act, adp, ald, y.yt(), dt(x.dtype), stream_ptr())
     return y
