@@ -115,3 +115,15 @@ def test_module_mirrors_forward_matches_reference_golden(gold, state_dict):
         assert rel_err(f.float().cpu().numpy(), g[f"feat{i}"]) < 1e-3
     with pytest.raises(NotImplementedError):
         model.train()(img)
+
+
+def test_engine_streaming_detect_many_matches_detect(state_dict):
+    eng = RefineEngine(state_dict, batch=2, imgsz=160, dtype=torch.float32, conv_impl=1, input_u8=True)
+    rs = np.random.RandomState(0)
+    batches = [torch.from_numpy(rs.randint(0, 256, (2, 3, 160, 160), dtype=np.uint8)).pin_memory() for _ in range(3)]
+    ref = [[d.cpu().numpy() for d in eng.detect(b)] for b in batches]
+    for (dh, ch), r in zip(eng.detect_many(batches), ref):
+        for i in range(2):
+            k = int(ch[i])
+            assert k == r[i].shape[0]
+            np.testing.assert_allclose(dh[i, :k].numpy(), r[i], rtol=1e-4, atol=1e-3)

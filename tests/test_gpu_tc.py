@@ -40,7 +40,9 @@ def test_umma_gemm_selftest(m, n, k):
 @pytest.mark.parametrize("cin,cout,k,s,hw", [(8, 16, 3, 2, 32), (16, 8, 3, 1, 20), (48, 64, 1, 1, 20), (128, 64, 3, 1, 10), (64, 32, 3, 2, 40),
                                              (192, 128, 1, 1, 7), (64, 27, 3, 1, 12), (32, 1, 3, 1, 9), (256, 256, 1, 1, 5), (128, 384, 1, 1, 20),
                                              (128, 512, 1, 1, 10), (64, 64, 3, 1, 80), (128, 128, 3, 1, 40), (64, 64, 3, 1, 13),
-                                             (96, 128, 1, 1, 21), (128, 64, 3, 1, 20)])
+                                             (96, 128, 1, 1, 21), (128, 64, 3, 1, 20), (16, 32, 3, 2, 64), (64, 64, 3, 2, 32), (128, 256, 3, 2, 20),
+                                             (32, 32, 3, 1, 40), (16, 8, 3, 1, 32), (8, 16, 3, 1, 32), (32, 64, 1, 1, 16), (16, 16, 1, 1, 24),
+                                             (128, 128, 3, 2, 18)])
 @pytest.mark.parametrize("impl", [2, 3])  # 2 = TMA-fed where eligible, 3 = thread-gathered operands
 def test_conv_tc_bias_silu_add(cin, cout, k, s, hw, impl):
     g = torch.Generator().manual_seed(cin * 1000 + cout)

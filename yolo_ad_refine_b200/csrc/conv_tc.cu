@@ -98,6 +98,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// generic K-major descriptor: row_bytes in {32, 64, 128} <-> SWIZZLE_32B (6) / SWIZZLE_64B (4) / SWIZZLE_128B (2); SBO = 8 rows
+__device__ __forceinline__ uint64_t make_sdesc_rb(uint32_t saddr, uint32_t row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)((8u * row_bytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
 // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b_format BF16 (1) @7/@10, K-major A and B, N >> 3 @17, M >> 4 @24
 __device__ __forceinline__ uint32_t make_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
 
@@ -508,6 +513,9 @@ struct TmaParams {
   int bw, bh, tiles_x, tiles_y;
   int a_bytes;          // bytes TMA writes per A box
   int tiles_n, total_tiles, acc_stages;
+  int bk;               // K elements per chunk: 16 / 32 / 64 (smem row = 2*bk bytes, SWIZZLE_32B / 64B / 128B)
+  int s2;               // stride-2 mode: 5-D parity-split map, coordinates (cpx[t] + ci, tx0 + dx[t], tpy[t], ty0 + dy[t], img)
+  int cpx[MAX_TAPS], tpy[MAX_TAPS];
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -516,6 +524,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(tm),
                "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+               "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -532,8 +545,9 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
   const TcParams& p = tp.p;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t a_bytes = BM * 128, b_bytes = (uint32_t)p.n_tile * 128;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t row_bytes = 2u * (uint32_t)tp.bk;
+  const uint32_t a_bytes = BM * row_bytes, b_bytes = (uint32_t)p.n_tile * row_bytes;
+  const uint32_t stage_bytes = (a_bytes + b_bytes + 1023u) & ~1023u;
   const uint32_t stg_off = (uint32_t)p.stages * stage_bytes;             // dedicated epilogue staging (not aliased: the pipeline stays busy)
   const uint32_t bars = base + (uint32_t)p.pipe_bytes;
   auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -544,7 +558,7 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kpt = (p.cin + BK - 1) / BK;  // K chunks per tap
+  const int kpt = (p.cin + tp.bk - 1) / tp.bk;  // K chunks per tap
   const int nk = p.ntaps * kpt;
   const int acc_stages = tp.acc_stages;
   const int per_img = tp.tiles_x * tp.tiles_y;
@@ -579,10 +593,12 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1u;
           const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
-          const int t = kc / kpt, ci = (kc - t * kpt) * BK;
+          const int t = kc / kpt, ci = (kc - t * kpt) * tp.bk;
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_expect_tx(full_bar(s), tx_bytes);
-          if (tp.patch)
+          if (tp.s2)
+            tma_load_5d(a_s, &tmA, full_bar(s), tp.cpx[t] + ci, tx0 + p.dx[t], tp.tpy[t], ty0 + p.dy[t], img);
+          else if (tp.patch)
             tma_load_4d(a_s, &tmA, full_bar(s), ci, tx0 + p.dx[t], ty0 + p.dy[t], img);
           else
             tma_load_2d(a_s, &tmA, full_bar(s), ci, mt * BM);
@@ -606,9 +622,8 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
-          const uint64_t ad = make_sdesc(a_s), bd = make_sdesc(b_s);
-#pragma unroll
-          for (int k = 0; k < BK / 16; k++) umma_f16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
+          const uint64_t ad = make_sdesc_rb(a_s, row_bytes), bd = make_sdesc_rb(b_s, row_bytes);
+          for (int k = 0; k < tp.bk / 16; k++) umma_f16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
           umma_commit(empty_bar(s));
         }
         umma_commit(tfull_bar(acc));
@@ -670,7 +685,7 @@ EncodeTiledFn get_encode() {
 }
 
 // bf16 tensor map, SWIZZLE_128B, zero OOB fill.  dims / strides innermost first; strides[i] (bytes) for dims 1..rank-1.
-int make_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+int make_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int bk = BK) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { yad_set_error("conv2d_tma: cuTensorMapEncodeTiled is unavailable"); return 1; }
   cuuint64_t d[5], st[5];
@@ -678,7 +693,8 @@ int make_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, 
   for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; i++) st[i] = strides_bytes[i];
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { yad_set_error("conv2d_tma: cuTensorMapEncodeTiled failed with %d", (int)r); return 1; }
   return 0;
 }
@@ -698,12 +714,24 @@ void pick_patch(int h, int w, int* bw_out, int* bh_out) {
   }
 }
 
+int pick_bk(int cin) { return cin <= 16 ? 16 : (cin <= 32 ? 32 : 64); }
+
 int tma_supported(const yad_tensor* x, const yad_conv_desc* d, const yad_tensor* y) {
-  if (d->mode != YAD_CONV_NORMAL || d->stride != 1) return 0;
-  if (d->kh * d->kw > 1 && (x->c % BK) != 0) return 0;
-  if (d->kh * d->kw > MAX_TAPS) return 0;
+  if (d->mode != YAD_CONV_NORMAL) return 0;
+  const int taps = d->kh * d->kw;
+  if (taps > MAX_TAPS) return 0;
   if (((uintptr_t)x->ptr & 15) || (x->ld % 8) || (y->ld % 8)) return 0;
-  if (d->kh * d->kw > 1 && (y->h != x->h || y->w != x->w)) return 0;
+  // kxk: every K chunk must lie inside one tap: cin is a multiple of the chunk, or a single (zero-filled) chunk covers it
+  if (taps > 1 && (x->c % pick_bk(x->c)) != 0 && x->c > pick_bk(x->c)) return 0;
+  if (d->stride == 1) {
+    if (taps > 1 && (y->h != x->h || y->w != x->w)) return 0;
+  } else if (d->stride == 2) {  // 3x3 s2 p1 on even maps stored without channel slicing: parity-split 5-D map
+    if (!(d->kh == 3 && d->kw == 3 && d->pad_h == 1 && d->pad_w == 1)) return 0;
+    if ((x->h & 1) || (x->w & 1) || x->ld != x->c) return 0;
+    if (x->c % pick_bk(x->c)) return 0;  // the zero-filled K tail needs dim 0 == cin, which the parity-split view does not have
+  } else {
+    return 0;
+  }
   return get_encode() != nullptr;
 }
 
@@ -714,7 +742,10 @@ int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
   tp.acc_stages = (2 * p.n_tile <= 512) ? 2 : 1;
   p.tmem_cols = 32;
   while (p.tmem_cols < tp.acc_stages * p.n_tile) p.tmem_cols <<= 1;
-  const int stage_bytes = BM * 128 + p.n_tile * 128;
+  tp.bk = pick_bk(p.cin);
+  tp.s2 = p.stride == 2;
+  const int row_bytes = 2 * tp.bk;
+  const int stage_bytes = ((BM + p.n_tile) * row_bytes + 1023) / 1024 * 1024;  // stages stay 1024-byte aligned for every swizzle mode
   const size_t stg = TMA_EPI_WARPS * STG_WARP + TMA_EPI_WARPS * 32 * 4;  // dedicated epilogue staging + row tables
   int stages = (int)((110 * 1024 - stg) / stage_bytes);  // aim at two resident CTAs per SM
   stages = stages > 4 ? 4 : (stages < 2 ? 2 : stages);
@@ -725,13 +756,30 @@ int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
 
   CUtensorMap tmA, tmB;
   int tiles_m;
-  if (p.ntaps == 1 && p.os == 1 && p.dy[0] == 0 && p.dx[0] == 0) {  // 1x1: rows are consecutive pixels
+  if (tp.s2) {
+    // input pixel (2*oy + ky - 1, 2*ox + kx - 1) = parity (py, px) of half-resolution cell (oy + ay, ox + ax)
+    tp.patch = 1;
+    pick_patch(p.hm, p.wm, &tp.bw, &tp.bh);
+    tp.tiles_x = (p.wm + tp.bw - 1) / tp.bw;
+    tp.tiles_y = (p.hm + tp.bh - 1) / tp.bh;
+    for (int t = 0; t < p.ntaps; t++) {
+      const int qy = t / 3 - 1, qx = t % 3 - 1;
+      tp.tpy[t] = qy & 1; tp.cpx[t] = (qx & 1) * p.cin;
+      p.dy[t] = qy < 0 ? -1 : 0; p.dx[t] = qx < 0 ? -1 : 0;
+    }
+    uint64_t dims[5] = {(uint64_t)2 * p.cin, (uint64_t)p.wi / 2, 2, (uint64_t)p.hi / 2, (uint64_t)p.n};
+    uint64_t strides[4] = {(uint64_t)2 * p.x_ld * 2, (uint64_t)p.wi * p.x_ld * 2, (uint64_t)2 * p.wi * p.x_ld * 2, (uint64_t)p.hi * p.wi * p.x_ld * 2};
+    uint32_t box[5] = {(uint32_t)tp.bk, (uint32_t)tp.bw, 1, (uint32_t)tp.bh, 1};
+    if (make_map(&tmA, p.x, 5, dims, strides, box, tp.bk)) return 1;
+    tp.a_bytes = tp.bw * tp.bh * row_bytes;
+    tiles_m = p.n * tp.tiles_x * tp.tiles_y;
+  } else if (p.ntaps == 1 && p.os == 1 && p.dy[0] == 0 && p.dx[0] == 0) {  // 1x1: rows are consecutive pixels
     tp.patch = 0;
     const int64_t M = (int64_t)p.n * p.hi * p.wi;
     uint64_t dims[2] = {(uint64_t)p.cin, (uint64_t)M}, strides[1] = {(uint64_t)p.x_ld * 2};
-    uint32_t box[2] = {BK, BM};
-    if (make_map(&tmA, p.x, 2, dims, strides, box)) return 1;
-    tp.a_bytes = BM * 128;
+    uint32_t box[2] = {(uint32_t)tp.bk, BM};
+    if (make_map(&tmA, p.x, 2, dims, strides, box, tp.bk)) return 1;
+    tp.a_bytes = BM * row_bytes;
     tp.tiles_x = tp.tiles_y = 1;
     tiles_m = (int)((M + BM - 1) / BM);
   } else {
@@ -741,16 +789,16 @@ int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
     tp.tiles_y = (p.hm + tp.bh - 1) / tp.bh;
     uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)p.wi, (uint64_t)p.hi, (uint64_t)p.n};
     uint64_t strides[3] = {(uint64_t)p.x_ld * 2, (uint64_t)p.wi * p.x_ld * 2, (uint64_t)p.hi * p.wi * p.x_ld * 2};
-    uint32_t box[4] = {BK, (uint32_t)tp.bw, (uint32_t)tp.bh, 1};
-    if (make_map(&tmA, p.x, 4, dims, strides, box)) return 1;
-    tp.a_bytes = tp.bw * tp.bh * 128;
+    uint32_t box[4] = {(uint32_t)tp.bk, (uint32_t)tp.bw, (uint32_t)tp.bh, 1};
+    if (make_map(&tmA, p.x, 4, dims, strides, box, tp.bk)) return 1;
+    tp.a_bytes = tp.bw * tp.bh * row_bytes;
     tiles_m = p.n * tp.tiles_x * tp.tiles_y;
   }
   {
     const int cout_rows = (p.cout + 7) / 8 * 8;
     uint64_t dims[2] = {(uint64_t)p.w_row, (uint64_t)cout_rows}, strides[1] = {(uint64_t)p.w_row * 2};
-    uint32_t box[2] = {BK, (uint32_t)p.n_tile};
-    if (make_map(&tmB, p.w, 2, dims, strides, box)) return 1;
+    uint32_t box[2] = {(uint32_t)tp.bk, (uint32_t)p.n_tile};
+    if (make_map(&tmB, p.w, 2, dims, strides, box, tp.bk)) return 1;
   }
   tp.tiles_n = (p.cout + p.n_tile - 1) / p.n_tile;
   tp.total_tiles = tiles_m * tp.tiles_n;

@@ -72,3 +72,46 @@ class RefineEngine:
         _, _, det, _, count = self.step()
         counts = count.tolist()
         return [det[i, :k] for i, k in enumerate(counts)]
+
+    def detect_many(self, host_batches, det_host=None, cnt_host=None):
+        """Streaming end-to-end path: yields, per host batch (pinned (B,3,H,W) uint8 or float tensor matching the engine input), the pinned host
+        tensors (detections (B, max_det, 6), counts (B,)).  The host->device copy of batch i+1 runs on a copy stream while batch i computes
+        (double-buffered staging), so the steady-state step time is max(copy, compute) instead of their sum."""
+        if self._out is None:
+            self._capture()
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._staging = [torch.empty_like(self.img) for _ in range(2)]
+            self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._free = [torch.cuda.Event(), torch.cuda.Event()]
+            for e in self._free:
+                e.record(main)
+        max_det = self.nms_args["max_det"]
+        det_host = det_host if det_host is not None else torch.empty((self.batch, max_det, 6), dtype=torch.float32).pin_memory()
+        cnt_host = cnt_host if cnt_host is not None else torch.empty((self.batch,), dtype=torch.int32).pin_memory()
+
+        def enqueue(i, hb):
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._free[i % 2])
+                self._staging[i % 2].copy_(hb, non_blocking=True)
+                self._ready[i % 2].record(self._copy_stream)
+
+        it = iter(host_batches)
+        nxt = next(it, None)
+        i = 0
+        if nxt is not None:
+            enqueue(0, nxt)
+        while nxt is not None:
+            nxt = next(it, None)
+            if nxt is not None:
+                enqueue(i + 1, nxt)
+            main.wait_event(self._ready[i % 2])
+            self.img.copy_(self._staging[i % 2], non_blocking=True)  # device-to-device into the graph's static input
+            self._free[i % 2].record(main)
+            _, _, det, _, count = self.step()
+            det_host.copy_(det, non_blocking=True)
+            cnt_host.copy_(count, non_blocking=True)
+            main.synchronize()  # the caller reads this batch's detections on the host
+            yield det_host, cnt_host
+            i += 1
