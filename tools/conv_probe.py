@@ -21,14 +21,17 @@ ho = (hw + 2 * (k // 2) - k) // s + 1
 y = Act.empty(n, ho, ho, cw.cout, dt, dev)
 flops = 2.0 * n * ho * ho * cw.cout * k * k * cin
 byts = 2.0 * (x.buf.numel() + y.buf.numel() + cw.w.numel())
+deform = os.environ.get("DEFORM") == "1"
+om = Act(torch.randn(n, hw, hw, 32, device=dev).to(dt)) if deform else None
+mode = ops.CONV_DEFORM if deform else ops.CONV_NORMAL
 for impl in impls:
     for _ in range(3):
-        ops.conv2d(x, cw.w, y, bias=cw.b, kh=k, kw=k, stride=s, pad_h=k // 2, pad_w=k // 2, act=ops.ACT_SILU, impl=impl)
+        ops.conv2d(x, cw.w, y, bias=cw.b, kh=k, kw=k, stride=s, pad_h=k // 2, pad_w=k // 2, act=ops.ACT_SILU, impl=impl, mode=mode, offmask=om)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(reps):
-        ops.conv2d(x, cw.w, y, bias=cw.b, kh=k, kw=k, stride=s, pad_h=k // 2, pad_w=k // 2, act=ops.ACT_SILU, impl=impl)
+        ops.conv2d(x, cw.w, y, bias=cw.b, kh=k, kw=k, stride=s, pad_h=k // 2, pad_w=k // 2, act=ops.ACT_SILU, impl=impl, mode=mode, offmask=om)
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
