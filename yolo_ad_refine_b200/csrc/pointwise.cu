@@ -51,44 +51,58 @@ __global__ void u8_to_nhwc_kernel(const uint8_t* __restrict__ src, int c_src, fl
 template <typename T, typename IN, int COUT>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const IN* __restrict__ img, int n, int h, int w, int cin, const float* __restrict__ wgt,
                                                         const float* __restrict__ bias, int act, yad_tensor y) {
-  extern __shared__ float sw[];  // [27 or 9*cin][COUT] then bias[COUT]
+  // grid (ceil(wo / 128), ho, n): one CTA = 128 consecutive output pixels of one output row.  The 3 input rows x (2*128 + 1) columns x cin
+  // it needs are staged in shared memory with coalesced loads (zero-filled outside the image); weights are broadcast reads.
+  extern __shared__ float sw[];  // weights [9*cin][COUT], bias [COUT], input tile [cin][3][257]
   const int K = 9 * cin;
+  float* sb = sw + K * COUT;
+  float* tile = sb + COUT;
+  constexpr int TW = 2 * 128 + 1;
   for (int i = threadIdx.x; i < K * COUT; i += blockDim.x) {
     int co = i % COUT, k = i / COUT;
     sw[i] = wgt[co * K + k];
   }
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sw[K * COUT + i] = bias ? bias[i] : 0.f;
-  __syncthreads();
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
   const int ho = y.h, wo = y.w;
-  const int64_t total = (int64_t)n * ho * wo;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-    const int ox = (int)(p % wo), oy = (int)((p / wo) % ho), b = (int)(p / ((int64_t)wo * ho));
-    float acc[COUT];
+  const int b = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * 128;
+  const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy - 1;
+  for (int i = threadIdx.x; i < cin * 3 * TW; i += blockDim.x) {
+    const int col = i % TW, r = (i / TW) % 3, ci = i / (3 * TW);
+    const int iy = iy0 + r, ix = ix0 + col;
+    float v = 0.f;
+    if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = (float)img[((int64_t)(b * cin + ci) * h + iy) * w + ix];
+    tile[i] = v;
+  }
+  __syncthreads();
+  const int ox = ox0 + threadIdx.x;
+  if (ox >= wo) return;
+  float acc[COUT];
 #pragma unroll
-    for (int i = 0; i < COUT; i++) acc[i] = sw[K * COUT + i];
+  for (int i = 0; i < COUT; i++) acc[i] = sb[i];
+  for (int ci = 0; ci < cin; ci++) {
+#pragma unroll
     for (int ky = 0; ky < 3; ky++) {
-      const int iy = 2 * oy - 1 + ky;
-      if (iy < 0 || iy >= h) continue;
-      for (int kx = 0; kx < 3; kx++) {
-        const int ix = 2 * ox - 1 + kx;
-        if (ix < 0 || ix >= w) continue;
-        for (int ci = 0; ci < cin; ci++) {
-          const float v = (float)img[((int64_t)(b * cin + ci) * h + iy) * w + ix];
-          const float* wr = sw + ((ky * 3 + kx) * cin + ci) * COUT;  // K index = tap * cin + ci, as in the packed conv weights
 #pragma unroll
-          for (int i = 0; i < COUT; i++) acc[i] = fmaf(v, wr[i], acc[i]);
+      for (int kx = 0; kx < 3; kx++) {
+        const float v = tile[(ci * 3 + ky) * TW + 2 * threadIdx.x + kx];
+        const float4* wr = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * cin + ci) * COUT);  // K index = tap * cin + ci
+#pragma unroll
+        for (int i4 = 0; i4 < COUT / 4; i4++) {
+          const float4 w4 = wr[i4];
+          acc[4 * i4] = fmaf(v, w4.x, acc[4 * i4]); acc[4 * i4 + 1] = fmaf(v, w4.y, acc[4 * i4 + 1]);
+          acc[4 * i4 + 2] = fmaf(v, w4.z, acc[4 * i4 + 2]); acc[4 * i4 + 3] = fmaf(v, w4.w, acc[4 * i4 + 3]);
         }
       }
     }
-    T* o = reinterpret_cast<T*>(y.ptr) + p * y.ld;
+  }
+  T* o = reinterpret_cast<T*>(y.ptr) + (((int64_t)b * ho + oy) * wo + ox) * y.ld;
 #pragma unroll
-    for (int c0 = 0; c0 < COUT; c0 += 8) {
-      float v[8];
+  for (int c0 = 0; c0 < COUT; c0 += 8) {
+    float v[8];
 #pragma unroll
-      for (int i = 0; i < 8; i++) v[i] = acc[c0 + i];
-      apply_act_n<8>(v, act);
-      store8(o + c0, v);
-    }
+    for (int i = 0; i < 8; i++) v[i] = acc[c0 + i];
+    apply_act_n<8>(v, act);
+    store8(o + c0, v);
   }
 }
 
@@ -730,9 +744,9 @@ int yad_stem_conv(const void* img, int img_is_u8, int n, int h, int w, int cin, 
   YAD_CHECK(y->n == n && y->h == (h + 2 - 3) / 2 + 1 && y->w == (w + 2 - 3) / 2 + 1, "stem_conv: output shape does not match a k3 s2 p1 convolution");
   YAD_CHECK(cin >= 1 && cin <= 4, "stem_conv: cin %d unsupported", cin);
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t total = (int64_t)n * y->h * y->w;
-  const size_t smem = (size_t)(9 * cin * 16 + 16) * sizeof(float);
-  const int grid = grid_for(total, 128);
+  const size_t smem = (size_t)(9 * cin * 16 + 16 + cin * 3 * 257) * sizeof(float);
+  const dim3 grid((y->w + 127) / 128, y->h, n);
+  YAD_CHECK(y->h <= 65535 && n <= 65535, "stem_conv: grid too large");
   YAD_DISPATCH_DTYPE(dtype, {
     if (img_is_u8)
       stem_conv_kernel<T, uint8_t, 16><<<grid, 128, smem, st>>>((const uint8_t*)img, n, h, w, cin, wgt, bias, act, *y);

@@ -24,26 +24,35 @@ constexpr int DA = 32;  // anchors per block
 template <typename T>
 __global__ void __launch_bounds__(128) decode_kernel(DecodeLevels L, int nc, int reg_max, const float* __restrict__ proj, float* __restrict__ y,
                                                      int N) {
-  extern __shared__ float tile[];  // [no][DA+1] then dist[4][DA]
-  const int no = 4 * reg_max + nc;
-  float* dist = tile + no * (DA + 1);
+  extern __shared__ float tile[];  // [DA anchors][no + 1] (odd pitch: conflict-free column reads), then dist[4][DA]
+  const int no = 4 * reg_max + nc, pitch = no + 1;
+  float* dist = tile + DA * pitch;
   const int b = blockIdx.y, a0 = blockIdx.x * DA;
   const int na = min(DA, N - a0);
-  // which levels does this block touch
-  for (int l = 0; l < L.nl; l++) {
+  for (int l = 0; l < L.nl; l++) {  // levels this block touches
     const int lo = max(a0, L.start[l]), hi = min(a0 + na, L.start[l + 1]);
     if (lo >= hi) continue;
     const T* src = reinterpret_cast<const T*>(L.ptr[l]) + (int64_t)b * L.sb[l];
     const int cnt = hi - lo;
-    if (L.sc[l] == 1) {  // channel-contiguous (NHWC): consecutive threads -> consecutive channels
+    if (L.sc[l] == 1 && (no & 7) == 0 && (L.sa[l] & 7) == 0) {  // channel-contiguous (NHWC): 128-bit loads, consecutive lanes -> consecutive channels
+      const int vpr = no >> 3;
+      for (int idx = threadIdx.x; idx < cnt * vpr; idx += blockDim.x) {
+        const int al = idx / vpr, v8 = (idx - al * vpr) * 8;
+        float v[8];
+        load8(src + (int64_t)(lo - L.start[l] + al) * L.sa[l] + v8, v);
+        float* dst = tile + ((lo - a0) + al) * pitch + v8;
+#pragma unroll
+        for (int i = 0; i < 8; i++) dst[i] = v[i];
+      }
+    } else if (L.sc[l] == 1) {
       for (int idx = threadIdx.x; idx < cnt * no; idx += blockDim.x) {
         int al = idx / no, ch = idx - al * no;
-        tile[ch * (DA + 1) + (lo - a0) + al] = ld1(src + (int64_t)(lo - L.start[l] + al) * L.sa[l] + ch);
+        tile[((lo - a0) + al) * pitch + ch] = ld1(src + (int64_t)(lo - L.start[l] + al) * L.sa[l] + ch);
       }
-    } else {  // anchor-contiguous ((B,no,N) layout)
+    } else {  // anchor-contiguous ((B, no, N) layout)
       for (int idx = threadIdx.x; idx < cnt * no; idx += blockDim.x) {
         int ch = idx / cnt, al = idx - ch * cnt;
-        tile[ch * (DA + 1) + (lo - a0) + al] = ld1(src + (int64_t)(lo - L.start[l] + al) * L.sa[l] + (int64_t)ch * L.sc[l]);
+        tile[((lo - a0) + al) * pitch + ch] = ld1(src + (int64_t)(lo - L.start[l] + al) * L.sa[l] + (int64_t)ch * L.sc[l]);
       }
     }
   }
@@ -52,12 +61,12 @@ __global__ void __launch_bounds__(128) decode_kernel(DecodeLevels L, int nc, int
   for (int idx = threadIdx.x; idx < 4 * DA; idx += blockDim.x) {
     int side = idx / DA, al = idx % DA;
     if (al < na) {
-      const float* col = tile + (side * reg_max) * (DA + 1) + al;
+      const float* row = tile + al * pitch + side * reg_max;
       float m = -INFINITY;
-      for (int k = 0; k < reg_max; k++) m = fmaxf(m, col[k * (DA + 1)]);
+      for (int k = 0; k < reg_max; k++) m = fmaxf(m, row[k]);
       float s = 0.f, e = 0.f;
       for (int k = 0; k < reg_max; k++) {
-        float p = expf(col[k * (DA + 1)] - m);
+        float p = expf(row[k] - m);
         s += p;
         e = fmaf(p, proj[k], e);
       }
@@ -80,7 +89,7 @@ __global__ void __launch_bounds__(128) decode_kernel(DecodeLevels L, int nc, int
   }
   for (int idx = threadIdx.x; idx < nc * DA; idx += blockDim.x) {
     int c = idx / DA, al = idx % DA;
-    if (al < na) yb[(int64_t)(4 + c) * N + a0 + al] = sigmoidf_(tile[(4 * reg_max + c) * (DA + 1) + al]);
+    if (al < na) yb[(int64_t)(4 + c) * N + a0 + al] = sigmoidf_(tile[al * pitch + 4 * reg_max + c]);
   }
 }
 
@@ -514,7 +523,7 @@ int yad_decode(const void* const* lvl_ptr_host, const int64_t* lvl_sb_host, cons
   const int N = L.start[nl];
   if (N == 0 || batch == 0) return 0;
   const int no = 4 * reg_max + nc;
-  size_t smem = (size_t)(no * (DA + 1) + 4 * DA) * sizeof(float);
+  size_t smem = (size_t)(DA * (no + 1) + 4 * DA) * sizeof(float);
   YAD_CHECK(smem <= 48 * 1024, "decode: %d channels per anchor need %zu B of shared memory", no, smem);
   dim3 grid((N + DA - 1) / DA, batch);
   cudaStream_t st = (cudaStream_t)stream;
