@@ -210,13 +210,20 @@ def main():
         prof[name] = {"calls": len(evs), "ms": t, "flops": fl}
         if name == "yad_conv2d":
             prof[name]["per_call"] = [dict(m, ms=s.elapsed_time(e)) for s, e, m in evs]
+    conv_evs = ops.PROFILE.get("yad_conv2d", [])
     ops.PROFILE = None
     eager_ms = sum(p["ms"] for p in prof.values())
     conv = prof["yad_conv2d"]
     pk = peaks()
     ach = conv["flops"] / (conv["ms"] / 1000.0) / 1e12
-    roofline = {"kernel": "yad_conv2d (implicit-GEMM convolution, all launches of one step)", "bound": "tensor", "achieved": ach,
-                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None,
+    traffic = None  # DRAM bytes per launch of the same kernels from the committed ncu capture (profiles/r1_conv_traffic.json)
+    tpath = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
+    if os.path.exists(tpath) and args.batch == 64 and args.imgsz == 640:
+        traffic = json.load(open(tpath))["dram_bytes_per_launch"]
+    roofline = {"kernel": "yad_conv2d = conv_tma_kernel / conv_tc_kernel (tcgen05 implicit-GEMM convolution, all launches of one step)",
+                "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                "traffic": traffic, "algorithmic_bytes_per_launch": sum(m["bytes"] for _, _, m in conv_evs) / max(1, len(conv_evs)),
+                "achieved_GBps_algorithmic": sum(m["bytes"] for _, _, m in conv_evs) / (conv["ms"] / 1000.0) / 1e9, "hbm_peak_GBps": pk["hbm"],
                 "peak_source": f"bf16_tflops_sustained of MEASURED_PEAKS.json ({pk['src']})", "launches": conv["calls"],
                 "avg_launch_us": 1000.0 * conv["ms"] / conv["calls"], "share_of_step": conv["ms"] / eager_ms,
                 "whole_step_frac_of_roofline": (args.batch * FLOPS_PER_IMG_640 * (args.imgsz / 640.0) ** 2 / (ms_per_step / 1000.0) / 1e12) / pk["tf_sustained"]}

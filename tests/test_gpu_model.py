@@ -130,3 +130,15 @@ def test_engine_streaming_detect_many_matches_detect(state_dict):
             assert abs(k - r[i].shape[0]) <= 2
             m = min(k, r[i].shape[0], 10)
             np.testing.assert_allclose(dh[i, :m, 4].numpy(), r[i][:m, 4], rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("size,batch", [(320, 3), (1280, 1), (160, 1)])
+def test_bf16_engine_other_sizes_track_fp32(state_dict, size, batch):
+    """BASELINE configs[4] (1280^2) and odd batch sizes: the bf16 tcgen05/TMA path tracks the fp32 SIMT path of the same library"""
+    img = synth.make_images(batch, size, size, seed=9)
+    y32, _, _ = _run(state_dict, img, torch.float32)
+    y16, _, _ = _run(state_dict, img, torch.bfloat16)
+    a, b = y32.cpu(), y16.cpu()
+    assert a.shape == b.shape == (batch, 84, (size // 8) ** 2 + (size // 16) ** 2 + (size // 32) ** 2)
+    assert float((a[:, 4:] - b[:, 4:]).abs().mean()) < 0.01
+    assert float((a[:, :4] - b[:, :4]).abs().mean() / a[:, :4].abs().mean()) < 0.03
