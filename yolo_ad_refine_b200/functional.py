@@ -14,8 +14,15 @@ from .weights import GN_EPS, ConvW, edffn_spectral_matrix, fold_bn, gn_groups
 class Ctx:
     """Execution context: prepared weights + allocation helpers (torch caching allocator = plumbing)."""
 
-    def __init__(self, P, conv_impl=0):
+    def __init__(self, P, conv_impl=0, parallel_levels=True):
         self.P, self.dtype, self.device, self.conv_impl = P, P.dtype, P.device, conv_impl
+        self.parallel_levels = parallel_levels
+        self._side = []
+
+    def side_streams(self, n):
+        while len(self._side) < n:
+            self._side.append(torch.cuda.Stream(device=self.device))
+        return self._side[:n]
 
     def act(self, n, h, w, c, ld=None):
         return Act.empty(n, h, w, c, self.dtype, self.device, ld)
@@ -315,7 +322,26 @@ def ayhead_level(ctx, p, x, i):
 
 def ayhead(ctx, p, xs, strides=(8, 16, 32), nc=80, reg_max=16, decode=True):
     """nn/modules/head.py:1127-1204 AYHead1.forward -> (y (B, 4+nc, N) fp32, [raw level outputs])"""
-    outs = [ayhead_level(ctx, p, x, i) for i, x in enumerate(xs)]
+    # the pyramid levels are independent until decode: run P4 / P5 (small grids) on side streams next to P3 -- fork / join with events,
+    # which a CUDA-graph capture records as parallel branches
+    if ctx.parallel_levels and len(xs) > 1:
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        side = ctx.side_streams(len(xs) - 1)
+        outs, joins = [None] * len(xs), []
+        for i in range(1, len(xs)):
+            side[i - 1].wait_event(fork)
+            with torch.cuda.stream(side[i - 1]):
+                outs[i] = ayhead_level(ctx, p, xs[i], i)
+                ev = torch.cuda.Event()
+                ev.record(side[i - 1])
+                joins.append(ev)
+        outs[0] = ayhead_level(ctx, p, xs[0], 0)
+        for ev in joins:
+            cur.wait_event(ev)
+    else:
+        outs = [ayhead_level(ctx, p, x, i) for i, x in enumerate(xs)]
     if not decode:
         return None, outs
     n_anchors = sum(o.h * o.w for o in outs)
