@@ -196,6 +196,124 @@ int yad_loss_cls(const float* pred_logits, const float* target_scores, int batch
                  float* grad_logits, void* stream);
 int yad_loss_finalize(const double* sums, float box_gain, float cls_gain, float dfl_gain, int batch, float* out4, void* stream);
 
+/* =====================================================================================================================
+ * Training path: backward kernels of every operator above + optimizer.  The reference's
+ * backward is PyTorch autograd over the same modules (engine/trainer.py:389-401 loss.backward(); optimizer_step :580-588).
+ * Conventions: activation gradients are written (acc = 0) or accumulated (acc = 1: dx += ...) in the activation dtype;
+ * parameter gradients are ACCUMULATED into fp32 buffers that the caller zeroes once per step.
+ * dgrad of a convolution is yad_conv2d itself on the gradient with permuted weights (stride 1: flipped taps; stride 2:
+ * the TRANSPOSED mode; ConvTranspose2d: a stride-2 NORMAL conv) -- see yad_permute_pack.
+ * ===================================================================================================================== */
+
+/* y = f(a, b, c3, d4) with coefficients that may live on the device (model parameters): *_dev non-NULL overrides the host value.
+ * ops 0-3 as yad_eltwise; 4: a*b (+ c3); 5: alpha*a (+ c3); 6: alpha*a*b (+ c3); 7: gelu(a)*b (EDFFN gate, block.py:2396);
+ * 8: a * s[pixel] + c3 (s = b, per-pixel scalar view).  y may alias c3 (in-place accumulation). */
+int yad_eltwise_dev(int op, const yad_tensor* a, const void* b, int b_ld, const void* c3, int c3_ld, const void* d4, int d4_ld, float alpha,
+                    float beta, float gamma, const float* alpha_dev, const float* beta_dev, const float* gamma_dev, const yad_tensor* y, int dtype,
+                    void* stream);
+
+/* conv weight gradient (autograd of F.conv2d w.r.t. weight): dw fp32 [cout][kh*kw][cin] += sum_m dy[m][co] * x[pix(m,tap)][ci].
+ * NORMAL mode geometry only (kh, kw, stride, pad of `d`; d->impl 1 = SIMT twin); ConvTranspose2d / deformable weights go through it with
+ * swapped operands / the column tensor.  bf16: mma.sync tensor cores; split-K with fp32 atomics. */
+int yad_conv_wgrad(const yad_tensor* x, const yad_tensor* dy, const yad_conv_desc* d, float* dw, int dtype, void* stream);
+/* depthwise weight gradient: dw fp32 [k*k][c] += sum_p dy[p][c] * x[p + tap][c] */
+int yad_dwconv_wgrad(const yad_tensor* x, const yad_tensor* dy, int k, float* dw, int dtype, void* stream);
+/* out[c] += sum over pixels of a[p][c] (* b[p][c] when b != NULL): bias and per-channel parameter gradients */
+int yad_colsum(const yad_tensor* a, const void* b, int b_ld, float* out, int dtype, void* stream);
+/* out[0] += scale * sum(a*b)  (per_image = 0)   or   out[n] += scale * sum over image n of a*b / img_div[n]  (per_image = 1; img_div may be NULL) */
+int yad_dot(const yad_tensor* a, const void* b, int b_ld, int per_image, float scale, const float* img_div, float* out, int dtype, void* stream);
+/* y[p][0] = sum_c a[p][c]*b[p][c], y[p][1..7] = 0 (y: 8-channel view): gradient of the per-pixel cls_prob gate (head.py:1168-1175) */
+int yad_dot_pixel(const yad_tensor* a, const void* b, int b_ld, const yad_tensor* y, int dtype, void* stream);
+
+/* GroupNorm / batch-statistics BatchNorm backward (autograd of F.group_norm / F.batch_norm(training=True) fused with the activation that
+ * follows): x = the normalised op's INPUT, stats = (sum, sumsq) as produced by yad_gn_stats, y = act(xhat*gamma+beta).  BatchNorm: pass the
+ * batch as ONE image (n=1, h=N*H) with groups = c.  sums: double [n][groups][2] scratch.  dgamma/dbeta fp32 [c] accumulated (may be NULL). */
+int yad_norm_bwd(const yad_tensor* x, const yad_tensor* dy, const double* stats, int groups, const float* gamma, const float* beta, float eps,
+                 int act, double* sums, float* dgamma, float* dbeta, const yad_tensor* dx, int acc, int dtype, void* stream);
+/* nn.BatchNorm2d running statistics in train(): r = (1-m) r + m * batch stat (unbiased variance); stats double [c][2], count = N*H*W */
+int yad_bn_running_update(const double* stats, int c, double count, float momentum, float* running_mean, float* running_var, void* stream);
+/* dx (+)= dy * f'(y) for activations that are functions of their output (sigmoid, relu) */
+int yad_act_bwd(const yad_tensor* y, const yad_tensor* dy, int act, const yad_tensor* dx, int acc, int dtype, void* stream);
+
+/* dx[n,y,x,:] (+)= img[n][:] * s_img + row[n,y,:] * s_row + col[n,x,:] * s_col: backward of yad_gap / yad_rowcol_mean (NULL = absent) */
+int yad_bcast_add(const yad_tensor* dx, const float* img, float s_img, const yad_tensor* row, float s_row, const yad_tensor* col, float s_col,
+                  int acc, int dtype, void* stream);
+/* backward of yad_rowcol_gate: dgh (n,h,1,c) / dgw (n,w,1,c) overwritten; dx (+)= dy*gh*gw when x != NULL */
+int yad_rowcol_gate_bwd(const yad_tensor* x, const yad_tensor* gh, const yad_tensor* gw, const yad_tensor* dy, const yad_tensor* dx, int acc,
+                        const yad_tensor* dgh, const yad_tensor* dgw, int dtype, void* stream);
+/* backward of yad_mlca_pool/att/apply (block.py:1540-1584, incl. the batch-axis pooling of the global branch).  local / att: the forward's
+ * fp32 [n][ls*ls][c] buffers; datt, dlocal: fp32 scratch of the same size; dG: fp32 [ls][c] scratch; dw_*: fp32 [ksize] accumulated */
+int yad_mlca_bwd(const yad_tensor* x, const yad_tensor* dy, const float* local, const float* att, const float* w_global, const float* w_local,
+                 int ksize, float local_weight, int local_size, float* datt, float* dlocal, float* dG, float* dw_global, float* dw_local,
+                 const yad_tensor* dx, int acc, int dtype, void* stream);
+/* 5x5/s1/p2 max-pool backward (SPPF, block.py:190-196): output gradient = dy_t (view, may be NULL) + dy_f (fp32 dense, may be NULL);
+ * dx_f fp32 dense (n,h,w,c) += ... (first maximum in row-major order, torch's index rule) */
+int yad_maxpool5_bwd(const yad_tensor* x, const void* dy_t, int dy_ld, const float* dy_f, float* dx_f, int dtype, void* stream);
+/* y (+)= scale * src (fp32 dense NHWC with y->c channels) */
+int yad_cast_acc(const float* src, float scale, const yad_tensor* y, int acc, int dtype, void* stream);
+/* backward of yad_pool_upsample; dpool: fp32 [n][h/s][w/s][c] scratch */
+int yad_pool_upsample_bwd(const yad_tensor* dy, int s, float* dpool, const yad_tensor* dx, int acc, int dtype, void* stream);
+/* backward of yad_gate_mlp: dout [n][nout] -> dg [n][c] overwritten; dw1, db1, dw2, db2 accumulated */
+int yad_gate_mlp_bwd(const float* g, const float* w1, const float* b1, const float* w2, const float* b2, int n, int c, int hidden, int nout,
+                     int kind, const float* dout, float* dg, float* dw1, float* db1, float* dw2, float* db2, void* stream);
+/* backward of yad_adt_apply: dimp fp32 [n][3] (zeroed here); dalpha[3], dweight[c], dbias[c] accumulated */
+int yad_adt_bwd(const yad_tensor* x, const yad_tensor* dy, const float* imp, const float* alphas, const float* weight, const yad_tensor* dx, int acc,
+                float* dimp, float* dalpha, float* dweight, float* dbias, int dtype, void* stream);
+/* backward of y = gelu(a) * b */
+int yad_gelu_gate_bwd(const yad_tensor* a, const void* b, int b_ld, const yad_tensor* dy, const yad_tensor* da, void* db, int db_ld, int acc,
+                      int dtype, void* stream);
+/* y (+)= a * s[n] (fp32 per-image scale): TaskDecomposition's per-image dynamic weight (head.py:651-669) */
+int yad_scale_img(const yad_tensor* a, const float* s, const yad_tensor* y, int acc, int dtype, void* stream);
+int yad_group_mean_bwd(const yad_tensor* dy, int s, const yad_tensor* dx, int acc, int dtype, void* stream);
+/* backward of yad_patch_filter: dx_f fp32 dense (n,h,w,c) (zeroed here); dm fp32 [64][64][c] accumulated (may be NULL) */
+int yad_patch_filter_bwd(const yad_tensor* x, const yad_tensor* dy, const float* m, float alpha, float* dx_f, float* dm, int dtype, void* stream);
+/* backward of yad_tssa for one scale; dqkv overwritten (dq = 0: the statistic sum_j normalize(q)_j^2 is identically 1); dtemps accumulated */
+int yad_tssa_bwd(const yad_tensor* qkv, const float* temps, int heads, const yad_tensor* dout, int out_token_offset, const yad_tensor* dqkv,
+                 float* dtemps, int dtype, void* stream);
+/* backward of yad_mha; lse_d: fp32 [n*heads][T][2] scratch */
+int yad_mha_bwd(const yad_tensor* qkv, int heads, const yad_tensor* out, const yad_tensor* dout, const yad_tensor* dqkv, float* lse_d, int dtype,
+                void* stream);
+
+/* DCNv2 as column tensor (training path): col (n,h,w,9c) = mask * bilinear sample, tap-major; the convolution itself, its dgrad and wgrad
+ * are then 1x1 yad_conv2d / yad_conv_wgrad calls on col.  yad_deform_col_bwd: dx_f fp32 dense (n,h,w,c) (zeroed here), doffmask view
+ * (>= 27 channels) overwritten with d(offsets), d(mask logits) */
+int yad_deform_col(const yad_tensor* x, const yad_tensor* offmask, const yad_tensor* col, int dtype, void* stream);
+int yad_deform_col_bwd(const yad_tensor* x, const yad_tensor* offmask, const yad_tensor* dcol, float* dx_f, const yad_tensor* doffmask, int dtype,
+                       void* stream);
+
+/* raw head outputs (n,h,w,4*reg_max+nc) of one level <-> the loss layout: distri fp32 (B,N,4*reg_max), logits fp32 (B,N,nc)
+ * (utils/loss.py:430-436 cat / permute), and the scatter of the loss gradients back (x scale) */
+int yad_head_pack(const yad_tensor* level, int anchor0, int n_anchors, int reg_ch, int nc, float* distri, float* logits, int dtype, void* stream);
+int yad_head_unpack(const float* grad_distri, const float* grad_logits, float scale, int anchor0, int n_anchors, int reg_ch, int nc,
+                    const yad_tensor* level, int dtype, void* stream);
+
+/* Fusion('bifpn') weights (block.py:1532-1534): w = relu(p)/(sum relu(p) + 1e-4) (w may be NULL); dp += J^T dw when dp != NULL */
+int yad_fusion_weights(const float* p, int k, float* w, const float* dw, float* dp, void* stream);
+/* tiny parameter-sized matrices: C[m][n] (+)= sum_k A[m][k] B[n][k] (trans_a = 0) or sum_k A[k][m] B[k][n] (trans_a = 1) */
+int yad_small_gemm(const float* a, const float* b, float* c, int m, int n, int k, int trans_a, int acc, void* stream);
+
+/* Layout table entry: dst[(i*n1 + t')*p2 + j] = src[src_off + i*s0 + t*s1 + j*s2] for i < n0, j < n2 (zero padding up to p0, p2),
+ * t' = flip ? n1-1-t : t.  Covers conv weights (OIHW -> [cout][tap][cin]), their dgrad twins, ConvTranspose2d, depthwise, padded biases. */
+typedef struct {
+  int64_t src_off, dst_off;
+  int64_t n0, n1, n2, p0, p2;
+  int64_t s0, s1, s2;
+  int32_t flip, dst_f32;
+} yad_permute_entry;
+/* master fp32 parameters (torch layout) -> kernel layouts; entries with dst_f32 go to dst_f32, the others to dst_t (activation dtype) */
+int yad_permute_pack(const yad_permute_entry* table_dev, int n_entries, int64_t max_elems, const float* src, void* dst_t, float* dst_f32, int dtype,
+                     void* stream);
+/* packed fp32 gradients -> += torch-layout gradient arena */
+int yad_permute_unpack(const yad_permute_entry* table_dev, int n_entries, int64_t max_elems, const float* packed, float* grads, void* stream);
+
+/* optimizer (engine/trainer.py:580-588, 784-808): *out += sum x^2;  clip_grad_norm_(max_norm) + SGD(nesterov) with three parameter groups
+ * (group[i] in {0: decay, 1: norm weight, 2: bias, 255: frozen}); ModelEMA (utils/torch_utils.py:530-541) */
+int yad_sqnorm(const float* x, int64_t n, double* out, void* stream);
+int yad_sgd_step(float* params, const float* grads, float* momentum_buf, const uint8_t* group, int64_t n, const float* lr3_host,
+                 const float* wd3_host, float momentum, float max_norm, const double* norm_sq, int first_step, void* stream);
+int yad_ema_update(float* ema, const float* params, int64_t n, float decay, void* stream);
+
+
 /* -- tcgen05 self-test: C[M][N] (fp32) = A[M][K] (bf16, row-major) x B[N][K]^T (bf16) through the UMMA/TMEM path.  Used by the GPU
  *    tests to validate descriptor encodings independently of the convolution loader. */
 int yad_tc_gemm_selftest(const void* a, const void* b, float* c, int m, int n, int k, void* stream);

@@ -51,6 +51,20 @@ TRAIN_CASES = {
 
 
 
+TRAIN_STEP_CASES = {
+    "b2_160": dict(batch=2, size=160, seed=50),
+    "b3_192x256": dict(batch=3, size=(192, 256), seed=52, empty_images=(1,)),
+}
+
+
+def train_step_inputs(batch, size, seed, empty_images=()):
+    """images (B,3,H,W) in [0,1] + targets for one full training step (forward + loss + backward)"""
+    h, w = (size, size) if isinstance(size, int) else size
+    img = synth.make_images(batch, h, w, seed=seed)
+    bi, cl, bb = synth.make_targets(batch, seed=seed + 1, max_per_img=6, empty_images=empty_images)
+    return img, bi, cl, bb
+
+
 def tal_inputs():
     """Stand-alone TaskAlignedAssigner call with padded gts (tal.py:38-88): B=3 images with 9, 4 and 0 valid gts."""
     import torch  # noqa: F401

@@ -180,7 +180,54 @@ def gen_train(m):
     print("tal fg", int(fgm.sum()))
 
 
+def gen_train_step():
+    """One full training forward + backward of the UNFUSED reference model in train() mode (batch-statistics BatchNorm) through
+    BaseModel.loss (nn/tasks.py:270-297): pins oracle.model.train_step_grads and, through it, the CUDA backward path."""
+    from oracle.cases import TRAIN_STEP_CASES, train_step_inputs
+    m, _ = build_reference_model(fuse=False)
+    m.args = _Args()
+    m.train()
+    d = {}
+    for name, kw in TRAIN_STEP_CASES.items():
+        img, bi, cl, bb = train_step_inputs(**kw)
+        sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        m.zero_grad()
+        m.criterion = None
+        m.model[-1].shape = None
+        batch = dict(img=torch.from_numpy(img), batch_idx=torch.from_numpy(bi), cls=torch.from_numpy(cl), bboxes=torch.from_numpy(bb))
+        loss, items = m.loss(batch)
+        loss.backward()
+        d[f"{name}_loss"] = np.float64(loss.item())
+        d[f"{name}_items"] = items.detach().numpy().astype(np.float64)
+        for k, p in m.named_parameters():
+            if p.grad is None:
+                d[f"{name}|{k}|none"] = np.int32(1)
+                continue
+            g = p.grad.detach().numpy().reshape(-1)
+            d[f"{name}|{k}|norm"] = np.float64(np.sqrt((g.astype(np.float64) ** 2).sum()))
+            d[f"{name}|{k}|samples"] = g[sample_positions(g.size, 16)]
+        sd1 = m.state_dict()
+        for k in sd1:
+            if k.endswith(("running_mean", "running_var")):
+                d[f"{name}|{k}|buf"] = sd1[k].numpy().reshape(-1)[:8].copy()
+        m.load_state_dict(sd0)  # restore the BatchNorm buffers for the next case
+        print("train_step", name, "loss", loss.item(), items.detach().numpy())
+    # optimizer parameter groups (engine/trainer.py:784-808): 0 = weight with decay, 1 = norm weight (no decay), 2 = bias (no decay)
+    from torch import nn
+    bn = tuple(v for k, v in nn.__dict__.items() if "Norm" in k)
+    groups = {}
+    for module_name, module in m.named_modules():
+        for param_name, param in module.named_parameters(recurse=False):
+            fullname = f"{module_name}.{param_name}" if module_name else param_name
+            groups[fullname] = 2 if "bias" in fullname else (1 if isinstance(module, bn) else 0)
+    with open(os.path.join(GOLD, "optimizer_groups.json"), "w") as f:
+        json.dump(groups, f)
+    np.savez_compressed(os.path.join(GOLD, "train_step.npz"), **d)
+
+
 def main():
+    if sys.argv[1:] == ["train_step"]:
+        return gen_train_step()
     m, spec = build_reference_model()
     sd = synth.make_state_dict_np(seed=1, spec=spec)
     with open(os.path.join(GOLD, "state_checksum.json"), "w") as f:

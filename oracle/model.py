@@ -37,9 +37,30 @@ def conv_bn_act(sd, p, x, act=True):
     w = sd[p + ".conv.weight"]
     k = w.shape[-1]
     s = sd.get(p + ".__stride__", 1)
+    if sd.get("__bn_train__"):  # nn.Module.train(): batch statistics (Conv.forward, conv.py:50)
+        y = batch_norm(sd, p + ".bn", F.conv2d(x, w, None, stride=s, padding=k // 2))
+        return F.silu(y) if act else y
     wf, bf = fold_bn(w, sd[p + ".bn.weight"], sd[p + ".bn.bias"], sd[p + ".bn.running_mean"], sd[p + ".bn.running_var"])
     y = F.conv2d(x, wf, bf, stride=s, padding=k // 2)
     return F.silu(y) if act else y
+
+
+BN_MOMENTUM = 0.03  # utils/torch_utils.py:426-436
+
+
+def batch_norm(sd, p, x):
+    """nn.BatchNorm2d (eps 1e-3, momentum 0.03): running statistics in eval, batch statistics when sd['__bn_train__'] is set; the updated
+    running statistics are recorded in sd['__bn_updates__'] (a dict) when present."""
+    if not sd.get("__bn_train__"):
+        return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"], False, 0.0, BN_EPS)
+    upd = sd.get("__bn_updates__") if isinstance(sd.get("__bn_updates__"), dict) else {}
+    # a module applied several times per step (the head's shared CoordAtt.bn1, once per pyramid level) updates its buffers each time
+    rm = upd.get(p + ".running_mean", sd[p + ".running_mean"]).detach().clone()
+    rv = upd.get(p + ".running_var", sd[p + ".running_var"]).detach().clone()
+    y = F.batch_norm(x, rm, rv, sd[p + ".weight"], sd[p + ".bias"], True, BN_MOMENTUM, BN_EPS)
+    if isinstance(sd.get("__bn_updates__"), dict):
+        sd["__bn_updates__"][p + ".running_mean"], sd["__bn_updates__"][p + ".running_var"] = rm, rv
+    return y
 
 
 def group_norm(x, w, b, groups, eps=GN_EPS):
@@ -74,9 +95,13 @@ def mlca(sd, p, x, local_size=5, local_weight=0.5):
     seq_l = local.reshape(b, c, -1).transpose(1, 2).reshape(b, 1, -1)
     y_l = F.conv1d(seq_l, w_l, padding=(k - 1) // 2)
     y_l = y_l.reshape(b, local_size * local_size, c).transpose(1, 2).reshape(b, c, local_size, local_size)
-    y_g = F.conv1d(glob.reshape(b, 1, c), w_g, padding=(k - 1) // 2).reshape(b, c, 1, 1)
+    y_g = F.conv1d(glob.reshape(b, 1, c), w_g, padding=(k - 1) // 2).reshape(b, c)
     att_l = y_l.sigmoid()
-    att_g = y_g.sigmoid().expand(b, c, local_size, local_size)  # adaptive_avg_pool2d of a 1x1 map = broadcast
+    # block.py:1575-1579: `y_global.view(b, -1).transpose(-1, -2).unsqueeze(-1)` is a 3-D (c, b, 1) tensor, so the adaptive pool that
+    # follows treats the BATCH axis as the height: row i of the 5x5 grid = mean of sigmoid(y_g[b0:b1]) over the images
+    # b0 = floor(i*b/5) .. b1 = ceil((i+1)*b/5), and the resulting (c, 5, 5) map is broadcast to every image.  For b == 1 this is the
+    # plain per-image broadcast; for b > 1 the global branch mixes images -- reference behaviour, reproduced here.
+    att_g = F.adaptive_avg_pool2d(y_g.t().unsqueeze(-1).sigmoid(), [local_size, local_size]).unsqueeze(0)  # (1,c,5,5)
     att = F.adaptive_avg_pool2d(att_g * (1 - local_weight) + att_l * local_weight, [m, n])
     return x * att
 
@@ -146,8 +171,7 @@ def progressive_feature_fusion(sd, p, x):
     for i in range(3):
         q = f"{p}.stages.{i}"
         t = F.conv2d(cur, sd[q + ".conv.weight"], sd[q + ".conv.bias"], 1, 1, groups=c)
-        t = F.batch_norm(t, sd[q + ".norm.running_mean"], sd[q + ".norm.running_var"], sd[q + ".norm.weight"],
-                         sd[q + ".norm.bias"], False, 0.0, BN_EPS)
+        t = batch_norm(sd, q + ".norm", t)
         t = F.gelu(t)
         cm = F.conv2d(t, sd[q + ".channel_mix.weight"], sd[q + ".channel_mix.bias"])
         sm = F.conv2d(t, sd[q + ".spatial_mix.weight"], sd[q + ".spatial_mix.bias"], 1, 3, groups=c)
@@ -312,8 +336,7 @@ def coord_att(sd, p, x):
     x_w = x.mean(2, keepdim=True).permute(0, 1, 3, 2)  # (n,c,w,1)
     y = torch.cat([x_h, x_w], 2)
     y = F.conv2d(y, sd[p + ".conv1.weight"], sd[p + ".conv1.bias"])
-    y = F.batch_norm(y, sd[p + ".bn1.running_mean"], sd[p + ".bn1.running_var"], sd[p + ".bn1.weight"], sd[p + ".bn1.bias"],
-                     False, 0.0, BN_EPS)
+    y = batch_norm(sd, p + ".bn1", y)
     y = F.hardswish(y)
     y_h, y_w = torch.split(y, [h, w], 2)
     a_h = torch.sigmoid(F.conv2d(y_h, sd[p + ".conv_h.weight"], sd[p + ".conv_h.bias"]))
@@ -432,15 +455,35 @@ def run_layer(sd, i, kind, args, x, training=False):
     raise ValueError(kind)
 
 
-def forward(sd, img, training=False, return_layers=False):
-    """nn/tasks.py:141-168 BaseModel._predict_once over LAYERS. sd: fp32 CPU state dict; img: (B,3,H,W) 0-1."""
+def forward(sd, img, training=False, return_layers=False, grad=False):
+    """nn/tasks.py:141-168 BaseModel._predict_once over LAYERS. sd: fp32 CPU state dict; img: (B,3,H,W) 0-1.
+    training: the head returns the raw level outputs (head.py:1178-1179); batch-statistics BatchNorm additionally needs
+    sd['__bn_train__'] = True.  grad: run with autograd enabled (train_step_grads)."""
     sd = dict(sd)
     ys = []
     x = img
-    with torch.no_grad():
+    with torch.set_grad_enabled(grad):
         for i, (f, kind, args) in enumerate(LAYERS):
             if f != -1:
                 x = ys[f] if isinstance(f, int) else [x if j == -1 else ys[j] for j in f]
             x = run_layer(sd, i, kind, args, x, training)
             ys.append(x)
     return (x, ys) if return_layers else x
+
+
+def train_step_grads(sd, img, batch_idx, cls, bboxes, gains=(7.5, 0.5, 1.5)):
+    """One training forward + backward (nn/tasks.py:270-297 BaseModel.loss -> utils/loss.py:419-520; model.train(), so BatchNorm uses
+    batch statistics).  Returns (loss*B, loss_items, {key: grad}, {bn buffer key: updated running stat}, raw head outputs)."""
+    from .tal_loss import detection_loss
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()
+              if isinstance(v, torch.Tensor) and v.dtype.is_floating_point and not k.endswith(("running_mean", "running_var"))
+              and not k.endswith("dfl.conv.weight")}
+    work = dict(sd)
+    work.update(params)
+    work["__bn_train__"] = True
+    work["__bn_updates__"] = {}
+    feats = forward(work, img, training=True, grad=True)
+    loss, items, aux = detection_loss(feats, batch_idx, cls, bboxes, gains=gains)
+    loss.backward()
+    grads = {k: (p.grad if p.grad is not None else None) for k, p in params.items()}
+    return loss.detach(), items, grads, work["__bn_updates__"], [f.detach() for f in feats]

@@ -26,6 +26,11 @@ class YadConvDesc(C.Structure):
                 ("pad_w", C.c_int32), ("offmask", C.c_void_p), ("offmask_ld", C.c_int32), ("impl", C.c_int32)]
 
 
+class YadPermuteEntry(C.Structure):
+    _fields_ = [("src_off", C.c_int64), ("dst_off", C.c_int64), ("n0", C.c_int64), ("n1", C.c_int64), ("n2", C.c_int64), ("p0", C.c_int64),
+                ("p2", C.c_int64), ("s0", C.c_int64), ("s1", C.c_int64), ("s2", C.c_int64), ("flip", C.c_int32), ("dst_f32", C.c_int32)]
+
+
 TP = C.POINTER(YadTensor)
 vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -67,6 +72,41 @@ SIGNATURES = {
     "yad_loss_cls": (i32, [vp, vp, i32, i32, i32, vp, f32, vp, vp]),
     "yad_loss_finalize": (i32, [vp, f32, f32, f32, i32, vp, vp]),
     "yad_tc_gemm_selftest": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    # ---- training path
+    "yad_eltwise_dev": (i32, [i32, TP, vp, i32, vp, i32, vp, i32, f32, f32, f32, vp, vp, vp, TP, i32, vp]),
+    "yad_conv_wgrad": (i32, [TP, TP, C.POINTER(YadConvDesc), vp, i32, vp]),
+    "yad_dwconv_wgrad": (i32, [TP, TP, i32, vp, i32, vp]),
+    "yad_colsum": (i32, [TP, vp, i32, vp, i32, vp]),
+    "yad_dot": (i32, [TP, vp, i32, i32, f32, vp, vp, i32, vp]),
+    "yad_dot_pixel": (i32, [TP, vp, i32, TP, i32, vp]),
+    "yad_norm_bwd": (i32, [TP, TP, vp, i32, vp, vp, f32, i32, vp, vp, vp, TP, i32, i32, vp]),
+    "yad_bn_running_update": (i32, [vp, i32, C.c_double, f32, vp, vp, vp]),
+    "yad_act_bwd": (i32, [TP, TP, i32, TP, i32, i32, vp]),
+    "yad_bcast_add": (i32, [TP, vp, f32, TP, f32, TP, f32, i32, i32, vp]),
+    "yad_rowcol_gate_bwd": (i32, [TP, TP, TP, TP, TP, i32, TP, TP, i32, vp]),
+    "yad_mlca_bwd": (i32, [TP, TP, vp, vp, vp, vp, i32, f32, i32, vp, vp, vp, vp, vp, TP, i32, i32, vp]),
+    "yad_maxpool5_bwd": (i32, [TP, vp, i32, vp, vp, i32, vp]),
+    "yad_cast_acc": (i32, [vp, f32, TP, i32, i32, vp]),
+    "yad_pool_upsample_bwd": (i32, [TP, i32, vp, TP, i32, i32, vp]),
+    "yad_gate_mlp_bwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "yad_adt_bwd": (i32, [TP, TP, vp, vp, vp, TP, i32, vp, vp, vp, vp, i32, vp]),
+    "yad_gelu_gate_bwd": (i32, [TP, vp, i32, TP, TP, vp, i32, i32, i32, vp]),
+    "yad_scale_img": (i32, [TP, vp, TP, i32, i32, vp]),
+    "yad_group_mean_bwd": (i32, [TP, i32, TP, i32, i32, vp]),
+    "yad_patch_filter_bwd": (i32, [TP, TP, vp, f32, vp, vp, i32, vp]),
+    "yad_tssa_bwd": (i32, [TP, vp, i32, TP, i32, TP, vp, i32, vp]),
+    "yad_mha_bwd": (i32, [TP, i32, TP, TP, TP, vp, i32, vp]),
+    "yad_deform_col": (i32, [TP, TP, TP, i32, vp]),
+    "yad_deform_col_bwd": (i32, [TP, TP, TP, vp, TP, i32, vp]),
+    "yad_head_pack": (i32, [TP, i32, i32, i32, i32, vp, vp, i32, vp]),
+    "yad_head_unpack": (i32, [vp, vp, f32, i32, i32, i32, i32, TP, i32, vp]),
+    "yad_fusion_weights": (i32, [vp, i32, vp, vp, vp, vp]),
+    "yad_small_gemm": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "yad_permute_pack": (i32, [vp, i32, i64, vp, vp, vp, i32, vp]),
+    "yad_permute_unpack": (i32, [vp, i32, i64, vp, vp, vp]),
+    "yad_sqnorm": (i32, [vp, i64, vp, vp]),
+    "yad_sgd_step": (i32, [vp, vp, vp, vp, i64, C.POINTER(f32), C.POINTER(f32), f32, f32, vp, i32, vp]),
+    "yad_ema_update": (i32, [vp, vp, i64, f32, vp]),
 }
 
 _lib = None

@@ -427,29 +427,40 @@ __global__ void mlca_pool_kernel(yad_tensor x, float* __restrict__ local, int ls
   for (int i = threadIdx.x; i < c; i += blockDim.x) local[((int64_t)n * ls * ls + bin) * c + i] = sm[i] * inv;
 }
 
-// one block per image: att[n][bin][c] = (1-lw)*sigmoid(conv1d_k(global)) + lw*sigmoid(conv1d_k(local sequence))  (block.py:1565-1581)
+// one block per image: att[n][bin][c] = (1-lw)*G[row(bin)][c] + lw*sigmoid(conv1d_k(local sequence))  (block.py:1565-1581).
+// G: the reference reshapes the global branch to a 3-D (c, b, 1) tensor before `adaptive_avg_pool2d(.., [ls, ls])` (block.py:1575-1579),
+// so the pool runs over the BATCH axis: G[i][c] = mean over images b in [floor(i*B/ls), ceil((i+1)*B/ls)) of sigmoid(conv1d_k(glob_b))[c],
+// shared by every image (for B == 1 this is the plain per-image broadcast).  Reproduced as is.
 __global__ void mlca_att_kernel(const float* __restrict__ local, const float* __restrict__ wg, const float* __restrict__ wl, int k, float lw,
-                                int c, int nb, float* __restrict__ att) {
-  extern __shared__ float sm[];  // seq[nb*c], glob[c], yg[c]
+                                int c, int ls, int batch, float* __restrict__ att) {
+  extern __shared__ float sm[];  // seq[nb*c], glob[c], G[ls*c]
+  const int nb = ls * ls;
   float* seq = sm;
   float* glob = sm + nb * c;
-  float* yg = glob + c;
+  float* G = glob + c;
   const int n = blockIdx.x, len = nb * c, r = (k - 1) / 2;
   for (int i = threadIdx.x; i < len; i += blockDim.x) seq[i] = local[(int64_t)n * len + i];
-  __syncthreads();
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < nb; b++) s += seq[b * c + ch];
-    glob[ch] = s / (float)nb;
-  }
-  __syncthreads();
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    float s = 0.f;
-    for (int j = 0; j < k; j++) {
-      int q = ch + j - r;
-      if (q >= 0 && q < c) s = fmaf(wg[j], glob[q], s);
+  for (int i = threadIdx.x; i < ls * c; i += blockDim.x) G[i] = 0.f;
+  for (int b = 0; b < batch; b++) {
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      float s = 0.f;
+      for (int q = 0; q < nb; q++) s += local[(int64_t)b * len + q * c + ch];
+      glob[ch] = s / (float)nb;
     }
-    yg[ch] = sigmoidf_(s);
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      float s = 0.f;
+      for (int j = 0; j < k; j++) {
+        int q = ch + j - r;
+        if (q >= 0 && q < c) s = fmaf(wg[j], glob[q], s);
+      }
+      const float sg = sigmoidf_(s);
+      for (int i = 0; i < ls; i++) {
+        const int b0 = bin_start(i, batch, ls), b1 = bin_end(i, batch, ls);
+        if (b >= b0 && b < b1) G[i * c + ch] += sg / (float)(b1 - b0);
+      }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < len; i += blockDim.x) {
@@ -458,7 +469,7 @@ __global__ void mlca_att_kernel(const float* __restrict__ local, const float* __
       int q = i + j - r;
       if (q >= 0 && q < len) s = fmaf(wl[j], seq[q], s);
     }
-    att[(int64_t)n * len + i] = yg[i % c] * (1.0f - lw) + sigmoidf_(s) * lw;
+    att[(int64_t)n * len + i] = G[((i / c) / ls) * c + i % c] * (1.0f - lw) + sigmoidf_(s) * lw;
   }
 }
 
@@ -607,28 +618,57 @@ __global__ void adt_apply_kernel(yad_tensor x, const float* __restrict__ imp, co
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void eltwise_kernel(int op, yad_tensor a, const T* __restrict__ b, int b_ld, const T* __restrict__ c3, int c3_ld,
-                               const T* __restrict__ d4, int d4_ld, float alpha, float beta, float gamma, yad_tensor y) {
+                               const T* __restrict__ d4, int d4_ld, float alpha, float beta, float gamma, const float* __restrict__ pa,
+                               const float* __restrict__ pb, const float* __restrict__ pg, yad_tensor y) {
+  if (pa) alpha = *pa;  // coefficients that are model parameters stay on the device (training path)
+  if (pb) beta = *pb;
+  if (pg) gamma = *pg;
   const int oct = a.c >> 3;
   const int64_t total = (int64_t)a.n * a.h * a.w * oct;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
     int o = (int)(it % oct) * 8;
     int64_t p = it / oct;
-    float va[8], vb[8];
+    float va[8], vb[8], vc[8];
     load8(reinterpret_cast<const T*>(a.ptr) + p * a.ld + o, va);
-    if (op == 2) {
+    if (op == 2 || op == 8) {
       float s = ld1(b + p * b_ld);
 #pragma unroll
       for (int i = 0; i < 8; i++) va[i] *= s;
+      if (op == 8) {
+        load8(c3 + p * c3_ld + o, vc);
+#pragma unroll
+        for (int i = 0; i < 8; i++) va[i] += vc[i];
+      }
+    } else if (op == 5) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) va[i] *= alpha;
+      if (c3) {
+        load8(c3 + p * c3_ld + o, vc);
+#pragma unroll
+        for (int i = 0; i < 8; i++) va[i] += vc[i];
+      }
     } else {
       load8(b + p * b_ld + o, vb);
       if (op == 1) {
 #pragma unroll
         for (int i = 0; i < 8; i++) va[i] *= vb[i];
+      } else if (op == 4 || op == 6) {
+        const float sc = op == 6 ? alpha : 1.0f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) va[i] *= vb[i] * sc;
+        if (c3) {
+          load8(c3 + p * c3_ld + o, vc);
+#pragma unroll
+          for (int i = 0; i < 8; i++) va[i] += vc[i];
+        }
+      } else if (op == 7) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) va[i] = apply_act(va[i], YAD_ACT_GELU) * vb[i];
       } else {
 #pragma unroll
         for (int i = 0; i < 8; i++) va[i] = alpha * va[i] + beta * vb[i];
         if (op == 3) {
-          float vc[8], vd[8];
+          float vd[8];
           load8(c3 + p * c3_ld + o, vc);
           load8(d4 + p * d4_ld + o, vd);
 #pragma unroll
@@ -881,9 +921,9 @@ int yad_mlca_att(const float* local, const float* w_global, const float* w_local
                  int local_size, float* att, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int nb = local_size * local_size;
-  size_t smem = (size_t)(nb * c + 2 * c) * sizeof(float);
+  size_t smem = (size_t)(nb * c + c + local_size * c) * sizeof(float);
   YAD_CHECK(smem <= 48 * 1024, "mlca_att: %d channels need %zu B of shared memory", c, smem);
-  mlca_att_kernel<<<n, 256, smem, st>>>(local, w_global, w_local, ksize, local_weight, c, nb, att);
+  mlca_att_kernel<<<n, 256, smem, st>>>(local, w_global, w_local, ksize, local_weight, c, local_size, n, att);
   YAD_LAUNCH_CHECK("mlca_att");
   return 0;
 }
@@ -920,19 +960,26 @@ int yad_adt_apply(const yad_tensor* x, const float* imp, const float* alphas, co
   return 0;
 }
 
-int yad_eltwise(int op, const yad_tensor* a, const void* b, int b_ld, const void* c3, int c3_ld, const void* d4, int d4_ld,
-                float alpha, float beta, float gamma, const yad_tensor* y, int dtype, void* stream) {
+int yad_eltwise_dev(int op, const yad_tensor* a, const void* b, int b_ld, const void* c3, int c3_ld, const void* d4, int d4_ld, float alpha,
+                    float beta, float gamma, const float* alpha_dev, const float* beta_dev, const float* gamma_dev, const yad_tensor* y, int dtype,
+                    void* stream) {
   CHECK_VIEW(a, "eltwise a");
   CHECK_VIEW(y, "eltwise y");
   SAME_SHAPE(a, y, "eltwise");
-  YAD_CHECK(op >= 0 && op <= 3 && b != nullptr, "eltwise: bad op %d or null operand", op);
+  YAD_CHECK(op >= 0 && op <= 8 && (b != nullptr || op == 5), "eltwise: bad op %d or null operand", op);
   YAD_CHECK(op != 3 || (c3 && d4), "eltwise: op 3 needs four operands");
+  YAD_CHECK(op != 8 || c3, "eltwise: op 8 needs c3");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)a->n * a->h * a->w * (a->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, eltwise_kernel<T><<<grid_for(total), TPB, 0, st>>>(op, *a, (const T*)b, b_ld, (const T*)c3, c3_ld,
-                                                                                (const T*)d4, d4_ld, alpha, beta, gamma, *y);)
+  YAD_DISPATCH_DTYPE(dtype, eltwise_kernel<T><<<grid_for(total), TPB, 0, st>>>(op, *a, (const T*)b, b_ld, (const T*)c3, c3_ld, (const T*)d4, d4_ld,
+                                                                                alpha, beta, gamma, alpha_dev, beta_dev, gamma_dev, *y);)
   YAD_LAUNCH_CHECK("eltwise");
   return 0;
+}
+
+int yad_eltwise(int op, const yad_tensor* a, const void* b, int b_ld, const void* c3, int c3_ld, const void* d4, int d4_ld,
+                float alpha, float beta, float gamma, const yad_tensor* y, int dtype, void* stream) {
+  return yad_eltwise_dev(op, a, b, b_ld, c3, c3_ld, d4, d4_ld, alpha, beta, gamma, nullptr, nullptr, nullptr, y, dtype, stream);
 }
 
 int yad_group_mean(const yad_tensor* x, int s, const yad_tensor* y, int dtype, void* stream) {

@@ -1,0 +1,387 @@
+// Weight-gradient kernels of the training path and the deformable-convolution column helpers.
+//   conv wgrad : dW[co][tap][ci] += sum over output pixels m of dy[m][co] * x[pix(m, tap)][ci]   (GEMM with K = n*ho*wo, split-K + fp32 atomics)
+//                bf16: mma.sync.m16n8k16 with both operands read through transposed ldmatrix (the reduction axis is the pixel axis,
+//                which is the strided one in NHWC); fp32: SIMT reference twin.
+//   dwconv wgrad, deform_col (modulated bilinear sampling -> column tensor) and its backward.
+#include "common.cuh"
+
+namespace {
+
+struct WgGeom {
+  int n, hi, wi, cin, ho, wo, cout;
+  int kh, kw, stride, pad_h, pad_w;
+  int x_ld, dy_ld;
+  int64_t M;        // n*ho*wo
+  int64_t per;      // pixels per split
+};
+
+__device__ __forceinline__ int64_t in_pixel(const WgGeom& g, int64_t m, int ky, int kx) {
+  const int ox = (int)(m % g.wo);
+  const int oy = (int)((m / g.wo) % g.ho);
+  const int img = (int)(m / ((int64_t)g.wo * g.ho));
+  const int iy = oy * g.stride - g.pad_h + ky, ix = ox * g.stride - g.pad_w + kx;
+  if (iy < 0 || iy >= g.hi || ix < 0 || ix >= g.wi) return -1;
+  return ((int64_t)img * g.hi + iy) * g.wi + ix;
+}
+
+// ---- SIMT twin (fp32 or bf16 storage, fp32 FMA): 64 co x 64 ci tile, 32 pixels per step, 4x4 outputs per thread ----------------
+constexpr int SB_P = 32, SB_C = 64;
+template <typename T>
+__global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ dy, WgGeom g, float* __restrict__ dw) {
+  __shared__ __align__(16) float sA[SB_P][SB_C + 4];  // dy[pixel][co]
+  __shared__ __align__(16) float sB[SB_P][SB_C + 4];  // x[pixel][ci]
+  const int ntaps = g.kh * g.kw;
+  const int tap = blockIdx.x % ntaps, ci0 = (blockIdx.x / ntaps) * SB_C, co0 = blockIdx.y * SB_C;
+  const int ky = tap / g.kw, kx = tap % g.kw;
+  const int64_t m0 = (int64_t)blockIdx.z * g.per, m1 = min(g.M, m0 + g.per);
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int lp = tid >> 3, lo = (tid & 7) * 8;  // loader: pixel lp (0..31), channel octet lo
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+  for (int64_t mb = m0; mb < m1; mb += SB_P) {
+    const int64_t m = mb + lp;
+    float a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a[i] = 0.f; b[i] = 0.f; }
+    if (m < m1) {
+      if (co0 + lo < g.cout) load8(dy + m * g.dy_ld + co0 + lo, a);
+      const int64_t ip = in_pixel(g, m, ky, kx);
+      if (ip >= 0 && ci0 + lo < g.cin) load8(x + ip * g.x_ld + ci0 + lo, b);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; i++) { sA[lp][lo + i] = a[i]; sB[lp][lo + i] = b[i]; }
+    __syncthreads();
+#pragma unroll 8
+    for (int p = 0; p < SB_P; p++) {
+      const float4 av = *reinterpret_cast<const float4*>(&sA[p][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&sB[p][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= g.cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int ci = ci0 + tx * 4 + j;
+      if (ci < g.cin) atomicAdd(&dw[((int64_t)co * ntaps + tap) * g.cin + ci], acc[i][j]);
+    }
+  }
+}
+
+// ---- tensor-core kernel (bf16): 64 co x 64 ci tile per CTA, 64 pixels per step; 4 warps x (16 co x 64 ci) ----------------------------
+constexpr int WG_P = 64, WG_PITCH = 72;
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+__global__ void __launch_bounds__(128) conv_wgrad_mma_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, WgGeom g, float* __restrict__ dw) {
+  __shared__ __align__(16) bf16 sA[2][WG_P * WG_PITCH];  // dy[pixel][co]
+  __shared__ __align__(16) bf16 sB[2][WG_P * WG_PITCH];  // x[pixel][ci]
+  const int ntaps = g.kh * g.kw;
+  const int tap = blockIdx.x % ntaps, ci0 = (blockIdx.x / ntaps) * 64, co0 = blockIdx.y * 64;
+  const int ky = tap / g.kw, kx = tap % g.kw;
+  const int64_t m0 = (int64_t)blockIdx.z * g.per, m1 = min(g.M, m0 + g.per);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float acc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc[j][i] = 0.f;
+  const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(&sA[0][0]), b_base = (uint32_t)__cvta_generic_to_shared(&sB[0][0]);
+  constexpr uint32_t BUF_BYTES = WG_P * WG_PITCH * 2;
+  uint4 ra[4], rb[4];  // register-staged next tile: 64 pixels x 8 chunks / 128 threads = 4 chunks per thread per operand
+  auto fetch = [&](int64_t mb) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int ch = tid + q * 128, row = ch >> 3, cc = (ch & 7) * 8;
+      const int64_t m = mb + row;
+      ra[q] = make_uint4(0u, 0u, 0u, 0u);
+      rb[q] = ra[q];
+      if (m < m1) {
+        if (co0 + cc < g.cout) ra[q] = *reinterpret_cast<const uint4*>(dy + m * g.dy_ld + co0 + cc);
+        const int64_t ip = in_pixel(g, m, ky, kx);
+        if (ip >= 0 && ci0 + cc < g.cin) rb[q] = *reinterpret_cast<const uint4*>(x + ip * g.x_ld + ci0 + cc);
+      }
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int ch = tid + q * 128, row = ch >> 3, cc = (ch & 7) * 8;
+      *reinterpret_cast<uint4*>(&sA[buf][row * WG_PITCH + cc]) = ra[q];
+      *reinterpret_cast<uint4*>(&sB[buf][row * WG_PITCH + cc]) = rb[q];
+    }
+  };
+  int buf = 0;
+  if (m0 < m1) {
+    fetch(m0);
+    stash(0);
+  }
+  __syncthreads();
+  for (int64_t mb = m0; mb < m1; mb += WG_P) {
+    const bool more = mb + WG_P < m1;
+    if (more) fetch(mb + WG_P);  // global loads in flight while the tensor cores work on the current tile
+    const uint32_t a_addr = a_base + buf * BUF_BYTES, b_addr = b_base + buf * BUF_BYTES;
+#pragma unroll
+    for (int ks = 0; ks < WG_P / 16; ks++) {
+      uint32_t a[4];
+      {
+        const int mat = lane >> 3, r = lane & 7, mi = mat & 1, kj = mat >> 1;
+        ldsm_x4_trans(a, a_addr + (uint32_t)(((ks * 16 + kj * 8 + r) * WG_PITCH + warp * 16 + mi * 8) * 2));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, b_addr + (uint32_t)(((ks * 16 + (lane & 15)) * WG_PITCH + j * 8) * 2));
+        mma_bf16_16816(acc[j], a, b0, b1);
+      }
+    }
+    if (more) stash(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  const int gq = lane >> 2, q4 = lane & 3;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int co = co0 + warp * 16 + gq + (i >> 1) * 8;
+      const int ci = ci0 + j * 8 + 2 * q4 + (i & 1);
+      if (co < g.cout && ci < g.cin) atomicAdd(&dw[((int64_t)co * ntaps + tap) * g.cin + ci], acc[j][i]);
+    }
+  }
+}
+
+// ---- depthwise wgrad: grid (taps, chunks); dW[tap][c] += sum_p dy[p][c] * x[p + tap][c] -----------------------------------------------
+template <typename T>
+__global__ void dwconv_wgrad_kernel(yad_tensor x, yad_tensor dy, int k, float* __restrict__ dw) {
+  extern __shared__ float sm[];
+  const int c = x.c, oct = c >> 3, r = k >> 1, tap = blockIdx.x, ky = tap / k, kx = tap % k;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int64_t npix = (int64_t)x.n * x.h * x.w;
+  const int64_t per = (npix + gridDim.y - 1) / gridDim.y, p0 = blockIdx.y * per, p1 = min(npix, p0 + per);
+  const int64_t items = (p1 - p0) * oct;
+  for (int64_t it = threadIdx.x; it < items; it += blockDim.x) {
+    const int64_t p = p0 + it / oct;
+    const int o = (int)(it % oct) * 8;
+    const int px = (int)(p % x.w), py = (int)((p / x.w) % x.h);
+    const int iy = py + ky - r, ix = px + kx - r;
+    if (iy < 0 || iy >= x.h || ix < 0 || ix >= x.w) continue;
+    float v[8], gg[8];
+    load8(reinterpret_cast<const T*>(x.ptr) + (p + (int64_t)(ky - r) * x.w + (kx - r)) * x.ld + o, v);
+    load8(reinterpret_cast<const T*>(dy.ptr) + p * dy.ld + o, gg);
+#pragma unroll
+    for (int i = 0; i < 8; i++) atomicAdd(&sm[o + i], v[i] * gg[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&dw[(int64_t)tap * c + i], sm[i]);
+}
+
+// ---- modulated deformable sampling (DCNv2, 3x3, stride 1, pad 1, one offset group) ---------------------------------------------------------
+struct Sample {
+  bool valid;
+  int y0, x0;
+  float ly, lx, mk;
+};
+template <typename T>
+__device__ __forceinline__ Sample dcn_sample(const T* __restrict__ om, int tap, int oy, int ox, int h, int w) {
+  Sample s;
+  const int ky = tap / 3, kx = tap % 3;
+  const float dy = ld1(om + 2 * tap), dx = ld1(om + 2 * tap + 1);
+  s.mk = sigmoidf_(ld1(om + 18 + tap));
+  const float py = (float)(oy - 1 + ky) + dy, px = (float)(ox - 1 + kx) + dx;
+  s.valid = py > -1.f && px > -1.f && py < (float)h && px < (float)w;
+  const float fy = floorf(py), fx = floorf(px);
+  s.y0 = (int)fy; s.x0 = (int)fx;
+  s.ly = py - fy; s.lx = px - fx;
+  return s;
+}
+
+// col[n, y, x, tap*C + c] = mask * bilinear(x)   (same arithmetic as the deformable mode of yad_conv2d)
+template <typename T>
+__global__ void deform_col_kernel(yad_tensor x, const T* __restrict__ om, int om_ld, yad_tensor col) {
+  const int C = x.c, oct = C >> 3;
+  const int64_t total = (int64_t)x.n * x.h * x.w * 9 * oct;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(it % oct) * 8;
+    const int tap = (int)((it / oct) % 9);
+    const int64_t p = it / ((int64_t)oct * 9);
+    const int ox = (int)(p % x.w), oy = (int)((p / x.w) % x.h), n = (int)(p / ((int64_t)x.w * x.h));
+    const Sample s = dcn_sample(om + p * om_ld, tap, oy, ox, x.h, x.w);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = 0.f;
+    if (s.valid) {
+      const float wgt[4] = {(1.f - s.ly) * (1.f - s.lx), (1.f - s.ly) * s.lx, s.ly * (1.f - s.lx), s.ly * s.lx};
+#pragma unroll
+      for (int c4 = 0; c4 < 4; c4++) {
+        const int yy = s.y0 + (c4 >> 1), xx = s.x0 + (c4 & 1);
+        if (yy >= 0 && yy < x.h && xx >= 0 && xx < x.w) {
+          float t[8];
+          load8(reinterpret_cast<const T*>(x.ptr) + (((int64_t)n * x.h + yy) * x.w + xx) * x.ld + o, t);
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] += wgt[c4] * t[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] *= s.mk;
+    }
+    store8(reinterpret_cast<T*>(col.ptr) + p * col.ld + tap * C + o, v);
+  }
+}
+
+// backward of deform_col: `oct` lanes (C/8, a power of two <= 32) cooperate on one (pixel, tap).
+// dx_f: fp32 dense (n,h,w,C) accumulated with atomics; dom: NHWC view (>= 27 channels, 32 allocated): [2t] d(dy), [2t+1] d(dx), [18+t] d(mask logit)
+template <typename T>
+__global__ void deform_col_bwd_kernel(yad_tensor x, const T* __restrict__ om, int om_ld, yad_tensor dcol, float* __restrict__ dx_f, yad_tensor dom) {
+  const int C = x.c, oct = C >> 3;
+  const int64_t groups = (int64_t)x.n * x.h * x.w * 9;
+  const int gpb = blockDim.x / oct;  // (pixel, tap) groups per block
+  const int sub = threadIdx.x % oct, gl = threadIdx.x / oct;
+  for (int64_t base = (int64_t)blockIdx.x * gpb; base < groups; base += (int64_t)gridDim.x * gpb) {  // block-uniform trip count (shuffles below)
+    const bool active = base + gl < groups;
+    const int64_t gi = active ? base + gl : groups - 1;
+    const int tap = (int)(gi % 9);
+    const int64_t p = gi / 9;
+    const int ox = (int)(p % x.w), oy = (int)((p / x.w) % x.h), n = (int)(p / ((int64_t)x.w * x.h));
+    const Sample s = dcn_sample(om + p * om_ld, tap, oy, ox, x.h, x.w);
+    const int o = sub * 8;
+    float dmk = 0.f, dpy = 0.f, dpx = 0.f;
+    if (s.valid && active) {
+      float g[8];
+      load8(reinterpret_cast<const T*>(dcol.ptr) + p * dcol.ld + tap * C + o, g);
+      const float wgt[4] = {(1.f - s.ly) * (1.f - s.lx), (1.f - s.ly) * s.lx, s.ly * (1.f - s.lx), s.ly * s.lx};
+      const float wy[4] = {-(1.f - s.lx), -s.lx, (1.f - s.lx), s.lx};  // d wgt / d ly
+      const float wx[4] = {-(1.f - s.ly), (1.f - s.ly), -s.ly, s.ly};  // d wgt / d lx
+#pragma unroll
+      for (int c4 = 0; c4 < 4; c4++) {
+        const int yy = s.y0 + (c4 >> 1), xx = s.x0 + (c4 & 1);
+        if (yy >= 0 && yy < x.h && xx >= 0 && xx < x.w) {
+          const int64_t q = ((int64_t)n * x.h + yy) * x.w + xx;
+          float t[8];
+          load8(reinterpret_cast<const T*>(x.ptr) + q * x.ld + o, t);
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            dmk = fmaf(g[i] * wgt[c4], t[i], dmk);
+            dpy = fmaf(g[i] * wy[c4], t[i], dpy);
+            dpx = fmaf(g[i] * wx[c4], t[i], dpx);
+            atomicAdd(&dx_f[q * C + o + i], g[i] * s.mk * wgt[c4]);
+          }
+        }
+      }
+    }
+    for (int d = oct >> 1; d > 0; d >>= 1) {
+      dmk += __shfl_xor_sync(0xffffffffu, dmk, d);
+      dpy += __shfl_xor_sync(0xffffffffu, dpy, d);
+      dpx += __shfl_xor_sync(0xffffffffu, dpx, d);
+    }
+    if (sub == 0 && active) {
+      T* d = reinterpret_cast<T*>(dom.ptr) + p * dom.ld;
+      st1(d + 2 * tap, dpy * s.mk);
+      st1(d + 2 * tap + 1, dpx * s.mk);
+      st1(d + 18 + tap, dmk * s.mk * (1.f - s.mk));
+      if (tap == 0)
+        for (int i = 27; i < dom.c; i++) st1(d + i, 0.f);
+    }
+  }
+}
+
+int grid_for(int64_t items, int tpb) {
+  int64_t g = (items + tpb - 1) / tpb;
+  const int64_t cap = 148 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" {
+
+/* Weight gradient of yad_conv2d's NORMAL mode: dw fp32 [cout][kh*kw][cin] += ...; the caller zeroes dw once per step (gradients of a
+ * weight shared by several calls accumulate).  impl: 0 = auto (tensor cores for bf16), 1 = SIMT. */
+int yad_conv_wgrad(const yad_tensor* x, const yad_tensor* dy, const yad_conv_desc* d, float* dw, int dtype, void* stream) {
+  YAD_CHECK(d->mode == YAD_CONV_NORMAL, "conv_wgrad: only the normal mode (transposed / deformable convolutions are expressed through it)");
+  YAD_CHECK(x->n == dy->n && x->c % 8 == 0 && dy->c % 8 == 0 && x->ld % 8 == 0 && dy->ld % 8 == 0, "conv_wgrad: bad views");
+  YAD_CHECK(dy->h == (x->h + 2 * d->pad_h - d->kh) / d->stride + 1 && dy->w == (x->w + 2 * d->pad_w - d->kw) / d->stride + 1,
+            "conv_wgrad: dy %dx%d does not match x %dx%d k%dx%d s%d", dy->h, dy->w, x->h, x->w, d->kh, d->kw, d->stride);
+  WgGeom g;
+  g.n = x->n; g.hi = x->h; g.wi = x->w; g.cin = x->c; g.ho = dy->h; g.wo = dy->w; g.cout = dy->c;
+  g.kh = d->kh; g.kw = d->kw; g.stride = d->stride; g.pad_h = d->pad_h; g.pad_w = d->pad_w;
+  g.x_ld = x->ld; g.dy_ld = dy->ld;
+  g.M = (int64_t)g.n * g.ho * g.wo;
+  const int ntaps = g.kh * g.kw;
+  const int tiles = cdiv(g.cin, 64) * ntaps * cdiv(g.cout, 64);
+  const bool mma = dtype == YAD_BF16 && d->impl != 1;
+  const int step = mma ? WG_P : SB_P;
+  int splits = cdiv(148 * 6, tiles);
+  const int64_t max_splits = (g.M + step * 4 - 1) / (step * 4);
+  if (splits > max_splits) splits = (int)max_splits;
+  if (splits < 1) splits = 1;
+  g.per = ((g.M + splits - 1) / splits + step - 1) / step * step;
+  splits = (int)((g.M + g.per - 1) / g.per);
+  dim3 grid(cdiv(g.cin, 64) * ntaps, cdiv(g.cout, 64), splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mma) {
+    conv_wgrad_mma_kernel<<<grid, 128, 0, st>>>((const bf16*)x->ptr, (const bf16*)dy->ptr, g, dw);
+  } else {
+    YAD_DISPATCH_DTYPE(dtype, conv_wgrad_simt_kernel<T><<<grid, 256, 0, st>>>((const T*)x->ptr, (const T*)dy->ptr, g, dw);)
+  }
+  YAD_LAUNCH_CHECK("conv_wgrad");
+  return 0;
+}
+
+/* dw fp32 [k*k][c] += ... (accumulating) */
+int yad_dwconv_wgrad(const yad_tensor* x, const yad_tensor* dy, int k, float* dw, int dtype, void* stream) {
+  YAD_CHECK(x->n == dy->n && x->h == dy->h && x->w == dy->w && x->c == dy->c && x->c % 8 == 0, "dwconv_wgrad: shape mismatch");
+  const int64_t npix = (int64_t)x->n * x->h * x->w;
+  int chunks = (int)((npix * (x->c / 8) + 256 * 16 - 1) / (256 * 16));
+  chunks = chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks);
+  dim3 grid(k * k, chunks);
+  YAD_DISPATCH_DTYPE(dtype, dwconv_wgrad_kernel<T><<<grid, 256, x->c * sizeof(float), (cudaStream_t)stream>>>(*x, *dy, k, dw);)
+  YAD_LAUNCH_CHECK("dwconv_wgrad");
+  return 0;
+}
+
+int yad_deform_col(const yad_tensor* x, const yad_tensor* offmask, const yad_tensor* col, int dtype, void* stream) {
+  YAD_CHECK(col->c == 9 * x->c && col->n == x->n && col->h == x->h && col->w == x->w && offmask->c >= 27 && x->c % 8 == 0,
+            "deform_col: col must be (n,h,w,9*c) and offmask have >= 27 channels");
+  const int64_t total = (int64_t)x->n * x->h * x->w * 9 * (x->c / 8);
+  YAD_DISPATCH_DTYPE(dtype, deform_col_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, (const T*)offmask->ptr, offmask->ld, *col);)
+  YAD_LAUNCH_CHECK("deform_col");
+  return 0;
+}
+
+/* dx_f: fp32 dense (n,h,w,c), zeroed by this call */
+int yad_deform_col_bwd(const yad_tensor* x, const yad_tensor* offmask, const yad_tensor* dcol, float* dx_f, const yad_tensor* doffmask, int dtype,
+                       void* stream) {
+  const int oct = x->c / 8;
+  YAD_CHECK(dcol->c == 9 * x->c && offmask->c >= 27 && doffmask->c >= 27 && x->c % 8 == 0 && (oct & (oct - 1)) == 0 && oct <= 32,
+            "deform_col_bwd: channel count %d must be 8 * a power of two <= 256", x->c);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(dx_f, 0, sizeof(float) * (int64_t)x->n * x->h * x->w * x->c, st);
+  const int64_t groups = (int64_t)x->n * x->h * x->w * 9;
+  const int gpb = 256 / oct;
+  YAD_DISPATCH_DTYPE(dtype, deform_col_bwd_kernel<T><<<grid_for(groups, gpb), 256, 0, st>>>(*x, (const T*)offmask->ptr, offmask->ld, *dcol, dx_f, *doffmask);)
+  YAD_LAUNCH_CHECK("deform_col_bwd");
+  return 0;
+}
+
+}  // extern "C"
