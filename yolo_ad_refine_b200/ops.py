@@ -283,3 +283,149 @@ def nms(pred, conf_thres, iou_thres, classes_mask, agnostic, multi_label, max_de
     assert pred.dtype == torch.float32 and pred.is_contiguous()
     _call("yad_nms", _p(pred), b, ch - 4, n, conf_thres, iou_thres, _p(classes_mask), int(agnostic), int(multi_label), max_det, max_nms,
                         max_wh, _p(out), _p(out_idx), _p(out_count), _p(workspace), stream_ptr())
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# training path (include/yad.h, "Training path"): thin wrappers, same conventions as above
+# ----------------------------------------------------------------------------------------------------------------------
+def _fp(t):
+    """device pointer of an fp32 tensor / tensor view (or None)"""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def eltwise_dev(op, a, b, y, c3=None, d4=None, alpha=1.0, beta=1.0, gamma=1.0, pa=None, pb=None, pg=None):
+    bp, bld = _ap(b)
+    cp, cld = _ap(c3)
+    dp, dld = _ap(d4)
+    _call("yad_eltwise_dev", op, a.yt(), bp, bld, cp, cld, dp, dld, alpha, beta, gamma, _fp(pa), _fp(pb), _fp(pg), y.yt(), dt(a.dtype), stream_ptr())
+    return y
+
+
+def conv_wgrad(x, dy, dw, kh=1, kw=1, stride=1, pad_h=0, pad_w=0, impl=0):
+    d = YadConvDesc(CONV_NORMAL, kh, kw, stride, pad_h, pad_w, None, 0, impl)
+    meta = None
+    if PROFILE is not None:
+        meta = dict(flops=2.0 * dy.n * dy.h * dy.w * dy.c * kh * kw * x.c, bytes=0, shape=f"wgrad {x.c}->{dy.c} k{kh}x{kw} s{stride} out{dy.h}x{dy.w} n{x.n}")
+    _call("yad_conv_wgrad", x.yt(), dy.yt(), C.byref(d), _fp(dw), dt(x.dtype), stream_ptr(), meta=meta)
+
+
+def dwconv_wgrad(x, dy, k, dw):
+    _call("yad_dwconv_wgrad", x.yt(), dy.yt(), k, _fp(dw), dt(x.dtype), stream_ptr())
+
+
+def colsum(a, out, b=None):
+    bp, bld = _ap(b)
+    _call("yad_colsum", a.yt(), bp, bld, _fp(out), dt(a.dtype), stream_ptr())
+
+
+def dot(a, b, out, scale=1.0, per_image=False, img_div=None):
+    bp, bld = _ap(b)
+    _call("yad_dot", a.yt(), bp, bld, int(per_image), scale, _fp(img_div), _fp(out), dt(a.dtype), stream_ptr())
+
+
+def dot_pixel(a, b, y):
+    bp, bld = _ap(b)
+    _call("yad_dot_pixel", a.yt(), bp, bld, y.yt(), dt(a.dtype), stream_ptr())
+
+
+def norm_bwd(x, dy, stats, groups, gamma, beta, eps, act, sums, dgamma, dbeta, dx, acc):
+    _call("yad_norm_bwd", x.yt(), dy.yt(), _fp(stats), groups, _fp(gamma), _fp(beta), eps, act, _fp(sums), _fp(dgamma), _fp(dbeta), dx.yt(), int(acc),
+          dt(x.dtype), stream_ptr())
+
+
+def bn_running_update(stats, c, count, momentum, rmean, rvar):
+    _call("yad_bn_running_update", _fp(stats), c, float(count), momentum, _fp(rmean), _fp(rvar), stream_ptr())
+
+
+def act_bwd(y, dy, act, dx, acc):
+    _call("yad_act_bwd", y.yt(), dy.yt(), act, dx.yt(), int(acc), dt(y.dtype), stream_ptr())
+
+
+def bcast_add(dx, acc, img=None, s_img=0.0, row=None, s_row=0.0, col=None, s_col=0.0):
+    _call("yad_bcast_add", dx.yt(), _fp(img), s_img, None if row is None else row.yt(), s_row, None if col is None else col.yt(), s_col, int(acc),
+          dt(dx.dtype), stream_ptr())
+
+
+def rowcol_gate_bwd(x, gh, gw, dy, dx, acc, dgh, dgw):
+    _call("yad_rowcol_gate_bwd", None if x is None else x.yt(), gh.yt(), gw.yt(), dy.yt(), None if dx is None else dx.yt(), int(acc), dgh.yt(),
+          dgw.yt(), dt(dy.dtype), stream_ptr())
+
+
+def mlca_bwd(x, dy, local, att, wg, wl, ksize, datt, dlocal, dG, dwg, dwl, dx, acc, local_size=5, local_weight=0.5):
+    _call("yad_mlca_bwd", x.yt(), dy.yt(), _fp(local), _fp(att), _fp(wg), _fp(wl), ksize, local_weight, local_size, _fp(datt), _fp(dlocal), _fp(dG),
+          _fp(dwg), _fp(dwl), dx.yt(), int(acc), dt(x.dtype), stream_ptr())
+
+
+def maxpool5_bwd(x, dy_t, dy_f, dx_f):
+    p, ld = _ap(dy_t)
+    _call("yad_maxpool5_bwd", x.yt(), p, ld, _fp(dy_f), _fp(dx_f), dt(x.dtype), stream_ptr())
+
+
+def cast_acc(src, y, acc, scale=1.0):
+    _call("yad_cast_acc", _fp(src), scale, y.yt(), int(acc), dt(y.dtype), stream_ptr())
+
+
+def pool_upsample_bwd(dy, s, dpool, dx, acc):
+    _call("yad_pool_upsample_bwd", dy.yt(), s, _fp(dpool), dx.yt(), int(acc), dt(dy.dtype), stream_ptr())
+
+
+def gate_mlp_bwd(g, w1, b1, w2, b2, kind, dout, dg, dw1, db1, dw2, db2):
+    n, c = g.shape
+    hidden, nout = w1.shape[0], w2.shape[0]
+    _call("yad_gate_mlp_bwd", _fp(g), _fp(w1), _fp(b1), _fp(w2), _fp(b2), n, c, hidden, nout, kind, _fp(dout), _fp(dg), _fp(dw1), _fp(db1), _fp(dw2),
+          _fp(db2), stream_ptr())
+
+
+def adt_bwd(x, dy, imp, alphas, weight, dx, acc, dimp, dalpha, dweight, dbias):
+    _call("yad_adt_bwd", x.yt(), dy.yt(), _fp(imp), _fp(alphas), _fp(weight), dx.yt(), int(acc), _fp(dimp), _fp(dalpha), _fp(dweight), _fp(dbias),
+          dt(x.dtype), stream_ptr())
+
+
+def gelu_gate_bwd(a, b, dy, da, db, acc):
+    _call("yad_gelu_gate_bwd", a.yt(), C.c_void_p(b.ptr), b.ld, dy.yt(), da.yt(), C.c_void_p(db.ptr), db.ld, int(acc), dt(a.dtype), stream_ptr())
+
+
+def scale_img(a, s, y, acc=0):
+    _call("yad_scale_img", a.yt(), _fp(s), y.yt(), int(acc), dt(a.dtype), stream_ptr())
+    return y
+
+
+def group_mean_bwd(dy, s, dx, acc=0):
+    _call("yad_group_mean_bwd", dy.yt(), s, dx.yt(), int(acc), dt(dy.dtype), stream_ptr())
+
+
+def patch_filter_bwd(x, dy, m, alpha, dx_f, dm):
+    _call("yad_patch_filter_bwd", x.yt(), dy.yt(), _fp(m), alpha, _fp(dx_f), _fp(dm), dt(x.dtype), stream_ptr())
+
+
+def tssa_bwd(qkv, temps, heads, dout, tok_offset, dqkv, dtemps):
+    _call("yad_tssa_bwd", qkv.yt(), _fp(temps), heads, dout.yt(), tok_offset, dqkv.yt(), _fp(dtemps), dt(qkv.dtype), stream_ptr())
+
+
+def mha_bwd(qkv, heads, out, dout, dqkv, lse_d):
+    _call("yad_mha_bwd", qkv.yt(), heads, out.yt(), dout.yt(), dqkv.yt(), _fp(lse_d), dt(qkv.dtype), stream_ptr())
+
+
+def deform_col(x, offmask, col):
+    _call("yad_deform_col", x.yt(), offmask.yt(), col.yt(), dt(x.dtype), stream_ptr())
+    return col
+
+
+def deform_col_bwd(x, offmask, dcol, dx_f, doffmask):
+    _call("yad_deform_col_bwd", x.yt(), offmask.yt(), dcol.yt(), _fp(dx_f), doffmask.yt(), dt(x.dtype), stream_ptr())
+
+
+def head_pack(level, anchor0, n_anchors, reg_ch, nc, distri, logits):
+    _call("yad_head_pack", level.yt(), anchor0, n_anchors, reg_ch, nc, _fp(distri), _fp(logits), dt(level.dtype), stream_ptr())
+
+
+def head_unpack(gd, gl, scale, anchor0, n_anchors, reg_ch, nc, level):
+    _call("yad_head_unpack", _fp(gd), _fp(gl), scale, anchor0, n_anchors, reg_ch, nc, level.yt(), dt(level.dtype), stream_ptr())
+
+
+def fusion_weights(p, k, w=None, dw=None, dp=None):
+    _call("yad_fusion_weights", _fp(p), k, _fp(w), _fp(dw), _fp(dp), stream_ptr())
+
+
+def small_gemm(a, b, c, m, n, k, trans_a=False, acc=False):
+    _call("yad_small_gemm", _fp(a), _fp(b), _fp(c), m, n, k, int(trans_a), int(acc), stream_ptr())
