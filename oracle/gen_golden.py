@@ -225,9 +225,59 @@ def gen_train_step():
     np.savez_compressed(os.path.join(GOLD, "train_step.npz"), **d)
 
 
+OPT_HYP = dict(lr=0.01, momentum=0.937, weight_decay=5e-4, steps=2)
+
+
+def gen_opt_step():
+    """Two optimizer steps of the live reference on one batch: BaseTrainer.build_optimizer's own parameter grouping + torch.optim.SGD
+    (engine/trainer.py:754-808), clip_grad_norm_(10) + step (trainer.py:580-588), ModelEMA.update (utils/torch_utils.py:511-541).
+    Stores sampled parameter / EMA DELTAS (after - before): pins oracle/optim.py and the yad_sgd_step / yad_ema_update kernels."""
+    from types import SimpleNamespace
+    from oracle.cases import TRAIN_STEP_CASES, train_step_inputs
+    from ultralytics.engine.trainer import BaseTrainer
+    from ultralytics.utils.torch_utils import ModelEMA
+    m, _ = build_reference_model(fuse=False)
+    m.args = _Args()
+    m.train()
+    for p_ in m.parameters():
+        p_.requires_grad_(True)
+    m.model[-1].dfl.conv.weight.requires_grad_(False)  # block.py:72
+    h = OPT_HYP
+    opt = BaseTrainer.build_optimizer(SimpleNamespace(args=SimpleNamespace(warmup_bias_lr=0.1)), m, name="SGD", lr=h["lr"], momentum=h["momentum"],
+                                      decay=h["weight_decay"], iterations=1e5)
+    ema = ModelEMA(m)
+    img, bi, cl, bb = train_step_inputs(**TRAIN_STEP_CASES["b2_160"])
+    batch = dict(img=torch.from_numpy(img), batch_idx=torch.from_numpy(bi), cls=torch.from_numpy(cl), bboxes=torch.from_numpy(bb))
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    d = {}
+    for step in range(h["steps"]):
+        m.criterion = None
+        m.model[-1].shape = None
+        loss, items = m.loss(batch)
+        loss.backward()
+        norm = torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=10.0)
+        opt.step()
+        opt.zero_grad()
+        ema.update(m)
+        d[f"loss{step}"] = np.float64(loss.item())
+        d[f"gradnorm{step}"] = np.float64(norm.item())
+        print("opt step", step, "loss", loss.item(), "grad norm", norm.item())
+    sd1, sde = m.state_dict(), ema.ema.state_dict()
+    for k, v in sd1.items():
+        if not v.dtype.is_floating_point:
+            continue
+        pos = sample_positions(v.numel(), 16)
+        d[f"{k}|delta"] = (v.double() - sd0[k].double()).numpy().reshape(-1)[pos]
+        d[f"{k}|ema_delta"] = (sde[k].double() - sd0[k].double()).numpy().reshape(-1)[pos]
+        d[f"{k}|delta_norm"] = np.float64((v.double() - sd0[k].double()).norm().item())
+    np.savez_compressed(os.path.join(GOLD, "opt_step.npz"), **d)
+
+
 def main():
     if sys.argv[1:] == ["train_step"]:
         return gen_train_step()
+    if sys.argv[1:] == ["opt_step"]:
+        return gen_opt_step()
     m, spec = build_reference_model()
     sd = synth.make_state_dict_np(seed=1, spec=spec)
     with open(os.path.join(GOLD, "state_checksum.json"), "w") as f:

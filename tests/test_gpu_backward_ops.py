@@ -1,0 +1,167 @@
+"""GPU parity of the backward building blocks against torch autograd of the same operator (fp32 torch-CUDA reference, computed from the SAME
+rounded inputs): convolution weight gradients (yad_conv_wgrad: SIMT fp32, SIMT bf16, mma.sync bf16) and input gradients (yad_conv2d on dy
+with the permuted weight layouts of train_params.TrainParams.conv) for every geometry the model uses; depthwise; normalisation backward."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util_gpu import DEV, rel_err
+from yolo_ad_refine_b200 import ops
+from yolo_ad_refine_b200.ops import Act
+from yolo_ad_refine_b200.train_params import TrainParams
+
+pytestmark = pytest.mark.gpu
+# the torch-CUDA reference must be true fp32 (cuDNN / cuBLAS default to TF32 for convolutions)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+# (cin, cout, kh, kw, stride, n, h, w)
+GEOMS = [
+    (8, 16, 3, 3, 2, 2, 32, 32),      # layer 0 (3 -> 8 padded input channels)
+    (16, 32, 3, 3, 2, 2, 16, 24),
+    (64, 64, 3, 3, 1, 2, 20, 12),
+    (128, 64, 3, 3, 1, 3, 10, 10),
+    (64, 32, 1, 1, 1, 2, 20, 20),
+    (192, 128, 1, 1, 1, 2, 9, 7),
+    (256, 256, 7, 1, 1, 4, 20, 1),    # ELA_HSFPN Conv1d(k=7) on the (n, L, 1, c) view
+    (64, 27, 3, 3, 1, 2, 10, 10),     # offset / mask conv (27 -> 32 padded outputs)
+    (32, 1, 3, 3, 1, 2, 10, 10),      # cls_prob (1 -> 8 padded outputs)
+    (576, 64, 1, 1, 1, 2, 10, 10),    # deformable conv on its column tensor
+]
+
+
+def _tp(w, b, dtype):
+    sd = {"w": w, "b": b}
+    return TrainParams(sd, dtype, DEV)
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+@pytest.mark.parametrize("mode", ["fp32", "bf16_simt", "bf16_tc"])
+def test_conv_wgrad_dgrad(geom, mode):
+    cin, cout, kh, kw, stride, n, h, w = geom
+    dtype = torch.float32 if mode == "fp32" else torch.bfloat16
+    impl = 0 if mode == "bf16_tc" else 1
+    rs = np.random.RandomState(cin * 7 + cout)
+    wt = torch.from_numpy(rs.standard_normal((cout, cin, kh, kw)).astype(np.float32) * 0.1)
+    tp = _tp(wt, torch.zeros(cout), dtype)
+    x = torch.from_numpy(rs.standard_normal((n, cin, h, w)).astype(np.float32)).to(DEV).to(dtype)
+    ph, pw = kh // 2, kw // 2
+    ho, wo = (h + 2 * ph - kh) // stride + 1, (w + 2 * pw - kw) // stride + 1
+    dy = torch.from_numpy(rs.standard_normal((n, cout, ho, wo)).astype(np.float32)).to(DEV).to(dtype)
+    # reference: torch autograd in fp32 from the rounded operands
+    xr = x.float().requires_grad_(True)
+    wr = wt.to(DEV).to(dtype).float().requires_grad_(True)
+    F.conv2d(xr, wr, None, stride, (ph, pw)).backward(dy.float())
+    xa, dya = Act.from_nchw(x, dtype), Act.from_nchw(dy, dtype)
+    W = tp.conv("w", "fwd")
+    Wd = tp.conv("w", "dgrad" if stride == 1 else "dgrad_t")
+    tp.zero_grad()
+    ops.conv_wgrad(xa, dya, W.gw, kh, kw, stride, ph, pw, impl=impl)
+    tp.unpack_grads()
+    tol = 1e-3 if dtype == torch.float32 else 4e-3  # fp32 accumulation everywhere; bf16: products of exactly representable operands
+    assert rel_err(tp.g("w").cpu().numpy(), wr.grad.cpu().numpy()) < tol
+    dx = Act.empty(n, h, w, xa.c, dtype, DEV)
+    if stride == 1:
+        ops.conv2d(dya, Wd.w, dx, kh=kh, kw=kw, stride=1, pad_h=kh - 1 - ph, pad_w=kw - 1 - pw, impl=impl)
+    else:
+        ops.conv2d(dya, Wd.w, dx, kh=kh, kw=kw, stride=2, pad_h=ph, pad_w=pw, mode=ops.CONV_TRANSPOSED, impl=impl)
+    got = dx.nchw().float().cpu().numpy()[:, :cin]
+    assert rel_err(got, xr.grad.cpu().numpy()) < (1e-3 if dtype == torch.float32 else 1.5e-2)  # bf16: the stored dx is rounded once
+    # accumulate form (epilogue add aliasing the output)
+    if stride == 1:
+        ops.conv2d(dya, Wd.w, dx, kh=kh, kw=kw, stride=1, pad_h=kh - 1 - ph, pad_w=kw - 1 - pw, add=dx, impl=impl)
+        got2 = dx.nchw().float().cpu().numpy()[:, :cin]
+        assert rel_err(got2, 2 * xr.grad.cpu().numpy()) < (1e-3 if dtype == torch.float32 else 3e-2)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16_simt", "bf16_tc"])
+def test_conv_transpose_wgrad_dgrad(mode):
+    """nn.ConvTranspose2d(c, c, 3, 2, 1, 1) of the neck (yaml layers 13 / 20)"""
+    dtype = torch.float32 if mode == "fp32" else torch.bfloat16
+    impl = 0 if mode == "bf16_tc" else 1
+    rs = np.random.RandomState(3)
+    ci, co, n, h, w = 64, 32, 2, 10, 12
+    wt = torch.from_numpy(rs.standard_normal((ci, co, 3, 3)).astype(np.float32) * 0.1)
+    tp = _tp(wt, torch.zeros(co), dtype)
+    x = torch.from_numpy(rs.standard_normal((n, ci, h, w)).astype(np.float32)).to(DEV).to(dtype)
+    dy = torch.from_numpy(rs.standard_normal((n, co, 2 * h, 2 * w)).astype(np.float32)).to(DEV).to(dtype)
+    xr = x.float().requires_grad_(True)
+    wr = wt.to(DEV).to(dtype).float().requires_grad_(True)
+    yr = F.conv_transpose2d(xr, wr, None, 2, 1, 1)
+    yr.backward(dy.float())
+    xa, dya = Act.from_nchw(x, dtype), Act.from_nchw(dy, dtype)
+    Wf, Wt = tp.conv("w", "convT_fwd"), tp.conv("w", "convT_dgrad")
+    y = Act.empty(n, 2 * h, 2 * w, co, dtype, DEV)
+    ops.conv2d(xa, Wf.w, y, kh=3, kw=3, stride=2, pad_h=1, pad_w=1, mode=ops.CONV_TRANSPOSED, impl=impl)
+    assert rel_err(y.nchw().float().cpu().numpy(), yr.detach().cpu().numpy()) < (1e-3 if dtype == torch.float32 else 1.5e-2)
+    tp.zero_grad()
+    ops.conv_wgrad(dya, xa, Wt.gw, 3, 3, 2, 1, 1, impl=impl)
+    tp.unpack_grads()
+    assert rel_err(tp.g("w").cpu().numpy(), wr.grad.cpu().numpy()) < (1e-3 if dtype == torch.float32 else 4e-3)
+    dx = Act.empty(n, h, w, ci, dtype, DEV)
+    ops.conv2d(dya, Wt.w, dx, kh=3, kw=3, stride=2, pad_h=1, pad_w=1, impl=impl)
+    assert rel_err(dx.nchw().float().cpu().numpy(), xr.grad.cpu().numpy()) < (1e-3 if dtype == torch.float32 else 1.5e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("k", [3, 7])
+def test_dwconv_backward(dtype, k):
+    rs = np.random.RandomState(k)
+    c, n, h, w = 128, 2, 20, 20
+    wt = torch.from_numpy(rs.standard_normal((c, 1, k, k)).astype(np.float32) * 0.2)
+    tp = _tp(wt, torch.zeros(c), dtype)
+    x = torch.from_numpy(rs.standard_normal((n, c, h, w)).astype(np.float32)).to(DEV).to(dtype)
+    dy = torch.from_numpy(rs.standard_normal((n, c, h, w)).astype(np.float32)).to(DEV).to(dtype)
+    xr, wr = x.float().requires_grad_(True), wt.to(DEV).requires_grad_(True)
+    F.conv2d(xr, wr, None, 1, k // 2, groups=c).backward(dy.float())
+    xa, dya = Act.from_nchw(x, dtype), Act.from_nchw(dy, dtype)
+    _, gw = tp.f32("w", "dw")
+    wflip, _ = tp.f32("w", "dw_flip")
+    tp.zero_grad()
+    ops.dwconv_wgrad(xa, dya, k, gw)
+    tp.unpack_grads()
+    assert rel_err(tp.g("w").cpu().numpy(), wr.grad.cpu().numpy()) < 1e-3
+    dx = ops.dwconv(dya, wflip, Act.empty(n, h, w, c, dtype, DEV), k=k)
+    assert rel_err(dx.nchw().float().cpu().numpy(), xr.grad.cpu().numpy()) < (1e-3 if dtype == torch.float32 else 1.5e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("kind", ["bn_silu", "bn_gelu", "bn_hswish", "gn_silu", "gn_sigmoid", "gn_none"])
+def test_norm_backward(dtype, kind):
+    """yad_norm_bwd against autograd of F.batch_norm(training=True) / F.group_norm followed by the activation"""
+    rs = np.random.RandomState(11)
+    c, n, h, w = 64, 3, 12, 10
+    x = torch.from_numpy(rs.standard_normal((n, c, h, w)).astype(np.float32) * 2 + 0.5).to(DEV).to(dtype)
+    dy = torch.from_numpy(rs.standard_normal((n, c, h, w)).astype(np.float32)).to(DEV).to(dtype)
+    gamma = torch.from_numpy(rs.uniform(0.5, 1.5, c).astype(np.float32)).to(DEV)
+    beta = torch.from_numpy(rs.standard_normal(c).astype(np.float32) * 0.3).to(DEV)
+    norm, actn = kind.split("_")
+    act = dict(silu=ops.ACT_SILU, gelu=ops.ACT_GELU, hswish=ops.ACT_HARDSWISH, sigmoid=ops.ACT_SIGMOID, none=ops.ACT_NONE)[actn]
+    fn = dict(silu=F.silu, gelu=F.gelu, hswish=F.hardswish, sigmoid=torch.sigmoid, none=lambda t: t)[actn]
+    xr, gr, br = x.float().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    eps = 1e-3 if norm == "bn" else 1e-5
+    u = F.batch_norm(xr, None, None, gr, br, True, 0.0, eps) if norm == "bn" else F.group_norm(xr, 16, gr, br, eps)
+    yr = fn(u)
+    yr.backward(dy.float())
+    xa, dya = Act.from_nchw(x, dtype), Act.from_nchw(dy, dtype)
+    xv, dyv = (xa.reshape(1, n * h, w), dya.reshape(1, n * h, w)) if norm == "bn" else (xa, dya)
+    groups = c if norm == "bn" else 16
+    stats = torch.empty((xv.n, groups, 2), dtype=torch.float64, device=DEV)
+    y = Act.empty(xv.n, xv.h, xv.w, c, dtype, DEV)
+    ops.group_norm(xv, y, stats, groups, gamma, beta, eps, act)
+    tol = 1e-3 if dtype == torch.float32 else 1.5e-2
+    assert rel_err(y.reshape(n, h, w).nchw().float().cpu().numpy(), yr.detach().cpu().numpy()) < tol
+    dgam, dbet = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+    dx = Act.empty(xv.n, xv.h, xv.w, c, dtype, DEV)
+    ops.norm_bwd(xv, dyv, stats, groups, gamma, beta, eps, act, torch.empty_like(stats), dgam, dbet, dx, 0)
+    assert rel_err(dx.reshape(n, h, w).nchw().float().cpu().numpy(), xr.grad.cpu().numpy()) < tol
+    assert rel_err(dgam.cpu().numpy(), gr.grad.cpu().numpy()) < 2e-3
+    assert rel_err(dbet.cpu().numpy(), br.grad.cpu().numpy()) < 2e-3
+    if norm == "bn":  # running statistics (momentum 0.03, unbiased variance)
+        rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+        ops.bn_running_update(stats, c, n * h * w, 0.03, rm, rv)
+        rm_r, rv_r = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+        F.batch_norm(x.float(), rm_r, rv_r, None, None, True, 0.03, eps)
+        np.testing.assert_allclose(rm.cpu().numpy(), rm_r.cpu().numpy(), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(rv.cpu().numpy(), rv_r.cpu().numpy(), rtol=1e-4, atol=1e-6)

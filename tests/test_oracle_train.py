@@ -69,3 +69,39 @@ def test_train_step_matches_reference(gold, state_dict, name):
     for k, v in bn_upd.items():
         np.testing.assert_allclose(v.numpy().reshape(-1)[:8], g[f"{name}|{k}|buf"], rtol=1e-4, atol=1e-6, err_msg=k)
     assert len(bn_upd) > 50
+
+
+def test_optimizer_step_matches_reference(gold, state_dict):
+    """oracle/optim.py (clip + SGD nesterov + EMA) driven by oracle.model.train_step_grads for two steps, against the live reference's two
+    steps (tests/golden/opt_step.npz): sampled parameter / EMA deltas."""
+    import json
+    import os
+    from conftest import GOLD
+    from oracle import model as om
+    from oracle import optim as oo
+    g = gold("opt_step.npz")
+    groups = json.load(open(os.path.join(GOLD, "optimizer_groups.json")))
+    img, bi, cl, bb = [torch.from_numpy(a) for a in cases.train_step_inputs(**cases.TRAIN_STEP_CASES["b2_160"])]
+    sd = {k: v.clone() for k, v in state_dict.items()}
+    ema = {k: v.clone() for k, v in state_dict.items()}
+    bufs = {}
+    for step in range(2):
+        loss, _, grads, bn_upd, _ = om.train_step_grads(sd, img, bi, cl, bb)
+        assert abs(loss.item() - float(g[f"loss{step}"])) < 2e-4 * abs(float(g[f"loss{step}"]))
+        params = {k: sd[k] for k in grads}
+        norm = oo.sgd_step(params, grads, bufs, groups)
+        assert abs(norm - float(g[f"gradnorm{step}"])) < 1e-3 * float(g[f"gradnorm{step}"])
+        sd.update(bn_upd)
+        oo.ema_update(ema, sd, step + 1)
+    checked = 0
+    for k, v in sd.items():
+        if not v.dtype.is_floating_point:
+            continue
+        pos = cases.sample_positions(v.numel(), 16)
+        dn = float(g[f"{k}|delta_norm"])
+        atol = 2e-2 * dn / np.sqrt(v.numel()) + 2e-7 * (float(v.abs().max()) + 1e-3)  # deltas are quantised by the fp32 ulp of the parameter
+        np.testing.assert_allclose((v.double() - state_dict[k].double()).numpy().reshape(-1)[pos], g[f"{k}|delta"], rtol=2e-2, atol=atol, err_msg=k)
+        np.testing.assert_allclose((ema[k].double() - state_dict[k].double()).numpy().reshape(-1)[pos], g[f"{k}|ema_delta"], rtol=2e-2,
+                                   atol=atol, err_msg=k)
+        checked += 1
+    assert checked > 400

@@ -804,7 +804,9 @@ int yad_gn_stats(const yad_tensor* x, int groups, double* stats, int dtype, void
   cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * x->n, st);
   int64_t hw = (int64_t)x->h * x->w;
   int chunks = (int)((hw * (x->c / 8) + TPB * 8 - 1) / (TPB * 8));
-  chunks = chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks);
+  // the grid is sized for the whole launch: a batch-statistics BatchNorm arrives as ONE image (n = 1) and still has to fill 148 SMs
+  const int cap_s = x->n >= 16 ? 64 : 1184 / x->n;
+  chunks = chunks < 1 ? 1 : (chunks > cap_s ? cap_s : chunks);
   dim3 grid(chunks, x->n);
   YAD_DISPATCH_DTYPE(dtype, gn_stats_kernel<T><<<grid, TPB, 2 * x->c * sizeof(float), st>>>(*x, groups, stats);)
   YAD_LAUNCH_CHECK("gn_stats");
@@ -820,7 +822,8 @@ int yad_gn_apply(const yad_tensor* x, const double* stats, int groups, const flo
   cudaStream_t st = (cudaStream_t)stream;
   int64_t items = (int64_t)x->h * x->w * (x->c / 8);
   int gx = (int)((items + TPB * 4 - 1) / (TPB * 4));
-  gx = gx < 1 ? 1 : (gx > 256 ? 256 : gx);
+  const int cap_a = x->n >= 8 ? 256 : 2368 / x->n;
+  gx = gx < 1 ? 1 : (gx > cap_a ? cap_a : gx);
   dim3 grid(gx, x->n);
   YAD_DISPATCH_DTYPE(dtype, gn_apply_kernel<T><<<grid, TPB, 2 * x->c * sizeof(float), st>>>(*x, stats, groups, gamma, beta, eps, act,
                                                                                                (const T*)add, add_ld, *y);)

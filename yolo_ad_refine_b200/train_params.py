@@ -162,6 +162,20 @@ class TrainParams:
             n0, n2, s0, s2, flip, grad = b, a, taps, b * taps, 0, False
         elif kind == "convT_dgrad":
             n0, n2, s0, s2, flip, grad = a, b, b * taps, taps, 0, True
+        elif kind == "col_dgrad":
+            # input gradient of a convolution applied to a tap-major column tensor (deformable conv, training.py): [t*ci + i][co], one table
+            # entry per tap
+            p0, p2 = _pad8(b), _pad8(a)
+            assert p0 == b, "col_dgrad: input channels must be a multiple of 8"
+            size = taps * p0 * p2
+            off = self._top_t
+            self._top_t += _pad8(size)
+            assert self._top_t <= self.arena_t.numel(), "packed weight arena exhausted"
+            for t in range(taps):
+                self._entries.append((self.off[key] + t, off + t * p0 * p2, b, 1, a, p0, p2, taps, 0, b * taps, 0, 0, False))
+            self._packed[ck] = PackedW(self.arena_t[off:off + size].view(taps * p0, 1, p2), None, 1, 1, taps * p0, p2)
+            self._registered(taps)
+            return self._packed[ck]
         else:
             raise ValueError(kind)
         p0, p2 = _pad8(n0), _pad8(n2)
@@ -173,7 +187,7 @@ class TrainParams:
         w = self.arena_t[off:off + size].view(p0, taps, p2)
         gw = self.arena_g[off:off + size].view(p0, taps, p2) if grad else None
         self._packed[ck] = PackedW(w, gw, kh, kw, p0, p2)
-        self._tables = None
+        self._registered(1)
         return self._packed[ck]
 
     def f32(self, key, kind="pad"):
@@ -187,7 +201,7 @@ class TrainParams:
             n = math.prod(s)
             n0, n1, n2, p0, p2, s0, s1, s2 = 1, 1, n, 1, _pad8(n), 0, 0, 1
             shape = (p2,)
-        elif kind == "dw":
+        elif kind in ("dw", "dw_flip"):  # dw_flip: taps reversed = the depthwise conv that computes the input gradient
             c, taps = s[0], s[2] * s[3]
             n0, n1, n2, p0, p2, s0, s1, s2 = 1, taps, c, 1, c, 0, 1, taps
             shape = (taps, c)
@@ -197,10 +211,28 @@ class TrainParams:
         off = self._top_f
         self._top_f += _pad8(size)
         assert self._top_f <= self.arena_f.numel(), "fp32 packed arena exhausted"
-        self._entries.append((self.off[key], off, n0, n1, n2, p0, p2, s0, s1, s2, 0, 1, True))
+        self._entries.append((self.off[key], off, n0, n1, n2, p0, p2, s0, s1, s2, int(kind == "dw_flip"), 1, kind != "dw_flip"))
         self._packed[ck] = (self.arena_f[off:off + size].view(shape), self.arena_gf[off:off + size].view(shape))
-        self._tables = None
+        self._registered(1)
         return self._packed[ck]
+
+    def _registered(self, count):
+        """a layout registered while a step is being traced is filled right away (its table entries alone), so the first forward already
+        sees packed weights; from then on pack() refreshes every layout in one launch"""
+        self._tables = None
+        t, n, mx = self._table(self._entries[-count:])
+        ops._call("yad_permute_pack", C.c_void_p(t.data_ptr()), n, mx, ops._fp(self.flat), ops._fp(self.arena_t), ops._fp(self.arena_f),
+                  ops.dt(self.dtype), ops.stream_ptr())
+        self._keep = getattr(self, "_keep", []) + [t]  # the table must outlive the asynchronous launch
+
+    def _table(self, rows):
+        arr = (YadPermuteEntry * max(len(rows), 1))()
+        mx = 1
+        for i, r in enumerate(rows):
+            arr[i] = YadPermuteEntry(*r[:12])
+            mx = max(mx, r[5] * r[3] * r[6])
+        t = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+        return t, len(rows), mx
 
     def _build_tables(self):
         def table(rows):
