@@ -120,6 +120,56 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def measure_training(args, world, rank, sd, dtype, W, barrier):
+    """BASELINE.json configs[3]: one training step (train()-mode forward + TaskAlignedAssigner + v8DetectionLoss + full backward + gradient
+    all-reduce over NCCL when N > 1 + clip / SGD / EMA), `train_batch` images per GPU (weak scaling).  Device-timed, max over ranks.  The e2e
+    figure adds, per step, the H2D copy of the pinned fp32 image batch + targets and the D2H read of the loss items."""
+    from yolo_ad_refine_b200 import ops, parallel, synth
+    from yolo_ad_refine_b200.trainer import TrainEngine
+    B = args.train_batch
+    eng = TrainEngine(sd, dtype=dtype, world_size=world)
+    img_host = torch.from_numpy(synth.make_images(B, args.imgsz, args.imgsz, seed=200 + rank)).pin_memory()
+    tg_host = [torch.from_numpy(a).pin_memory() for a in synth.make_targets(B, seed=300 + rank, max_per_img=8, empty_images=())]
+    img = img_host.cuda()
+    tg = [t.cuda() for t in tg_host]
+    loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
+    l0 = ops.LAUNCHES
+    eng.step(img, *tg)
+    launches = ops.LAUNCHES - l0
+
+    def timed(fn, k):
+        for _ in range(max(W, 3)):
+            fn()
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(k):
+            fn()
+        e.record()
+        barrier()
+        return parallel.max_over_ranks(s.elapsed_time(e), device="cuda") / k
+
+    ms = timed(lambda: eng.step(img, *tg), args.train_steps)
+
+    def e2e_step():
+        d_img = img_host.to("cuda", non_blocking=True)
+        d_tg = [t.to("cuda", non_blocking=True) for t in tg_host]
+        out4 = eng.step(d_img, *d_tg)
+        loss_host.copy_(out4, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_ms = timed(e2e_step, args.train_steps)
+    out = {"metric": "train img/s (forward + loss + backward + optimizer)", "value": world * B / (ms / 1000.0), "unit": "img/s",
+           "ms_per_step": ms, "batch_per_gpu": B, "global_batch": world * B, "steps": args.train_steps, "launches_per_step": launches,
+           "scaling": "weak", "exchange": "none (1 GPU)" if world == 1 else f"NCCL all-reduce of the {eng.tp.total * 4 / 1e6:.1f} MB fp32 gradient arena",
+           "e2e": {"value": world * B / (e2e_ms / 1000.0), "unit": "img/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": img_host.numel() * 4 + sum(t.numel() * 4 for t in tg_host), "d2h_bytes_per_step": 16},
+           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "loss": [float(v) for v in loss_host]}
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -131,6 +181,8 @@ def main():
     ap.add_argument("--imgsz", type=int, default=640)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=128, help="images per GPU of the training-step measurement (0 = skip)")
+    ap.add_argument("--train-steps", type=int, default=5)
     ap.add_argument("--profile-json", default=None, help="write the per-entry-point CUDA-event profile of one eager step here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -230,6 +282,8 @@ def main():
     if args.profile_json and rank == 0:
         json.dump({"eager_ms": eager_ms, "graph_ms_per_step": ms_per_step, "entries": prof}, open(args.profile_json, "w"), indent=1)
 
+    train = measure_training(args, world, rank, sd, dtype, W, barrier) if args.train_batch > 0 else None
+
     line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"YOLO-AD-Refine (yolo11-701 yaml, scale n) inference batch {args.batch}/GPU at {args.imgsz}x{args.imgsz}, "
@@ -238,6 +292,8 @@ def main():
                        "l2": "inputs + activations of one step (>1 GB) exceed the 126 MB L2; no explicit flush"},
             "e2e": e2e, "gpu_launches": eng.launches_per_step * args.steps, "launches_per_step": eng.launches_per_step,
             "clocks": clk.summary(), "roofline": roofline}
+    if train is not None:
+        line["train"] = train
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             v, cores = cpu_path_img_per_s(2, args.imgsz, reps=2)

@@ -152,9 +152,10 @@ def dwconv(x, w, y, bias=None, scale=None, shift=None, k=3, act=ACT_NONE, gate_s
 def group_norm(x, y, stats, groups, gamma, beta, eps=1e-5, act=ACT_NONE, add=None, stats_ready=False):
     """stats: double (n, groups, 2) scratch; stats_ready: already filled by the producing conv's fused epilogue"""
     if not stats_ready:
-        _call("yad_gn_stats", x.yt(), groups, _p(stats), dt(x.dtype), stream_ptr())
+        _call("yad_gn_stats", x.yt(), groups, _p(stats), dt(x.dtype), stream_ptr(), meta=_m(x, 1) if PROFILE is not None else None)
     adp, ald = _ap(add)
-    _call("yad_gn_apply", x.yt(), _p(stats), groups, _p(gamma), _p(beta), eps, act, adp, ald, y.yt(), dt(x.dtype), stream_ptr())
+    _call("yad_gn_apply", x.yt(), _p(stats), groups, _p(gamma), _p(beta), eps, act, adp, ald, y.yt(), dt(x.dtype), stream_ptr(),
+          meta=_m(x, 2 + (add is not None)) if PROFILE is not None else None)
     return y
 
 
@@ -293,11 +294,19 @@ def _fp(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _m(a, passes=1):
+    """profile metadata of a memory-bound op on view `a`: `passes` = algorithmic number of full-tensor reads + writes"""
+    if PROFILE is None:
+        return None
+    return dict(flops=0.0, bytes=passes * a.n * a.h * a.w * a.c * a.buf.element_size(), shape=f"{a.n}x{a.h}x{a.w}x{a.c}")
+
+
 def eltwise_dev(op, a, b, y, c3=None, d4=None, alpha=1.0, beta=1.0, gamma=1.0, pa=None, pb=None, pg=None):
     bp, bld = _ap(b)
     cp, cld = _ap(c3)
     dp, dld = _ap(d4)
-    _call("yad_eltwise_dev", op, a.yt(), bp, bld, cp, cld, dp, dld, alpha, beta, gamma, _fp(pa), _fp(pb), _fp(pg), y.yt(), dt(a.dtype), stream_ptr())
+    _call("yad_eltwise_dev", op, a.yt(), bp, bld, cp, cld, dp, dld, alpha, beta, gamma, _fp(pa), _fp(pb), _fp(pg), y.yt(), dt(a.dtype), stream_ptr(),
+          meta=_m(a, 2 + (b is not None) + (c3 is not None)))
     return y
 
 
@@ -310,12 +319,12 @@ def conv_wgrad(x, dy, dw, kh=1, kw=1, stride=1, pad_h=0, pad_w=0, impl=0):
 
 
 def dwconv_wgrad(x, dy, k, dw):
-    _call("yad_dwconv_wgrad", x.yt(), dy.yt(), k, _fp(dw), dt(x.dtype), stream_ptr())
+    _call("yad_dwconv_wgrad", x.yt(), dy.yt(), k, _fp(dw), dt(x.dtype), stream_ptr(), meta=_m(x, 2))
 
 
 def colsum(a, out, b=None):
     bp, bld = _ap(b)
-    _call("yad_colsum", a.yt(), bp, bld, _fp(out), dt(a.dtype), stream_ptr())
+    _call("yad_colsum", a.yt(), bp, bld, _fp(out), dt(a.dtype), stream_ptr(), meta=_m(a, 1 + (b is not None)))
 
 
 def dot(a, b, out, scale=1.0, per_image=False, img_div=None):
@@ -330,7 +339,7 @@ def dot_pixel(a, b, y):
 
 def norm_bwd(x, dy, stats, groups, gamma, beta, eps, act, sums, dgamma, dbeta, dx, acc):
     _call("yad_norm_bwd", x.yt(), dy.yt(), _fp(stats), groups, _fp(gamma), _fp(beta), eps, act, _fp(sums), _fp(dgamma), _fp(dbeta), dx.yt(), int(acc),
-          dt(x.dtype), stream_ptr())
+          dt(x.dtype), stream_ptr(), meta=_m(x, 3))
 
 
 def bn_running_update(stats, c, count, momentum, rmean, rvar):

@@ -1,5 +1,7 @@
-"""Multi-GPU plumbing for the inference path: it shards by image with NO data-path collective, one process per GPU.
-torch.distributed is used only for the rendezvous, the barrier around the timed region and the max-over-ranks reduction of the timing."""
+"""Multi-GPU plumbing, one process per GPU.  Inference shards by image with NO data-path collective: torch.distributed
+is used only for the rendezvous, the barrier around the timed region and the max-over-ranks reduction of the timing.  Training has one real
+exchange step per iteration -- the reference's DistributedDataParallel gradient all-reduce (engine/trainer.py:279) -- done here as ONE
+all-reduce of the flat fp32 gradient arena, plus DDP's rank-0 broadcast of the BatchNorm buffers."""
 import os
 
 import torch
@@ -49,3 +51,14 @@ def sum_over_ranks(value, device="cpu"):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def exchange_gradients(tp, group=None):
+    """DDP semantics of the reference trainer on the flat arenas of train_params.TrainParams: gradients are averaged by DDP and the loss is
+    multiplied by world_size (engine/trainer.py:394), i.e. the applied gradient is the SUM over ranks; module buffers (BatchNorm running
+    statistics) follow rank 0 (DistributedDataParallel(broadcast_buffers=True), its default)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    dist.all_reduce(tp.grad, op=dist.ReduceOp.SUM, group=group)
+    if tp.btotal:
+        dist.broadcast(tp.bufs, src=0, group=group)

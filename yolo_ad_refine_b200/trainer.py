@@ -69,9 +69,8 @@ class TrainEngine:
     def exchange(self):
         """DDP gradient exchange (sum over ranks) + rank-0 BatchNorm buffers"""
         if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.tp.grad, group=self.pg)
-            dist.broadcast(self.tp.bufs, src=0, group=self.pg)
+            from .parallel import exchange_gradients
+            exchange_gradients(self.tp, self.pg)
 
     def step(self, img, batch_idx, cls, bboxes, lr=None):
         out4 = self.forward_backward(img, batch_idx, cls, bboxes)
