@@ -28,6 +28,10 @@ GEOMS = [
     (64, 27, 3, 3, 1, 2, 10, 10),     # offset / mask conv (27 -> 32 padded outputs)
     (32, 1, 3, 3, 1, 2, 10, 10),      # cls_prob (1 -> 8 padded outputs)
     (576, 64, 1, 1, 1, 2, 10, 10),    # deformable conv on its column tensor
+    (16, 8, 3, 3, 1, 2, 40, 40),      # small-channel wgrad path (cin, cout <= 32): ragged 8 x 32 tiles
+    (32, 32, 3, 3, 1, 3, 40, 24),
+    (32, 16, 3, 3, 1, 1, 9, 7),
+    (8, 32, 3, 3, 2, 2, 48, 80),
 ]
 
 
@@ -165,3 +169,29 @@ def test_norm_backward(dtype, kind):
         F.batch_norm(x.float(), rm_r, rv_r, None, None, True, 0.03, eps)
         np.testing.assert_allclose(rm.cpu().numpy(), rm_r.cpu().numpy(), rtol=1e-4, atol=1e-6)
         np.testing.assert_allclose(rv.cpu().numpy(), rv_r.cpu().numpy(), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("T", [150, 1200])
+def test_mha_backward(dtype, T):
+    """yad_mha_bwd (fp32: SIMT kernels; bf16: flash-style mma.sync kernels) against autograd of softmax(q k^T / sqrt(d)) v, 2 heads x 64"""
+    rs = np.random.RandomState(T)
+    n, heads, c = 2, 2, 128
+    qkv = torch.from_numpy(rs.standard_normal((n, T, 3 * c)).astype(np.float32)).to(DEV).to(dtype)
+    dout = torch.from_numpy(rs.standard_normal((n, T, c)).astype(np.float32)).to(DEV).to(dtype)
+    ref_in = qkv.float().requires_grad_(True)
+    q, k, v = [t.view(n, T, heads, 64).transpose(1, 2) for t in ref_in.split(c, -1)]
+    att = torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1)
+    o_ref = (att @ v).transpose(1, 2).reshape(n, T, c)
+    o_ref.backward(dout.float())
+    qa = Act(qkv.view(n, 1, T, 3 * c).contiguous())
+    out = ops.mha(qa, heads, Act.empty(n, 1, T, c, dtype, DEV))
+    tol = 1e-3 if dtype == torch.float32 else 2e-2
+    assert rel_err(out.torch().float().cpu().numpy().reshape(n, T, c), o_ref.detach().cpu().numpy()) < tol
+    dq = Act.empty(n, 1, T, 3 * c, dtype, DEV)
+    ops.mha_bwd(qa, heads, out, Act(dout.view(n, 1, T, c).contiguous()), dq, torch.empty((n * heads, T, 2), dtype=torch.float32, device=DEV))
+    got = dq.torch().float().cpu().numpy().reshape(n, T, 3 * c)
+    ref = ref_in.grad.cpu().numpy()
+    for i, name in enumerate("qkv"):
+        e = rel_err(got[..., i * c:(i + 1) * c], ref[..., i * c:(i + 1) * c])
+        assert e < (2e-3 if dtype == torch.float32 else 3e-2), (name, e)

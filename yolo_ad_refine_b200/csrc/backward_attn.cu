@@ -271,6 +271,247 @@ __global__ void __launch_bounds__(128) mha_bwd_dkv_kernel(const T* __restrict__ 
   }
 }
 
+
+// ---- tensor-core MHA backward (bf16): flash-attention style, mma.sync.m16n8k16 (bf16 -> fp32), nothing of size T x T is materialised -----------
+//   kernel 1 (dq):  CTA = 64 query rows (4 warps x 16).  Pass 0 streams the keys once for the row statistics lse2 = log2(sum exp(s)) (in the
+//                   exp2 domain) and D = dO . O; pass 1 streams K, V again: S = Q K^T, dP = dO V^T, dS = P o (dP - D), dQ += dS K.
+//   kernel 2 (dkv): CTA = 64 key rows.  Streams Q, dO tiles: S^T = K Q^T, P^T, dV += P^T dO, dP^T = V dO^T, dS^T, dK += dS^T Q.
+//   Operand fragments follow the forward kernel (attention.cu): row-major tiles in shared memory with a conflict-free pitch, B fragments
+//   through ldmatrix (x2 for [n][k] tiles, x2.trans for [k][n] tiles), P / dS re-packed from accumulators to A fragments in registers.
+constexpr int BA_T = 64, BA_PITCH = 72;
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm2(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm2t(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// A fragments (16 rows x 64 cols) of a row-major global matrix: rows r0 = row0 + g, r1 = r0 + 8 (zero when >= Tn)
+__device__ __forceinline__ void load_afrag(const bf16* base, int64_t ld, int row0, int Tn, int g, int q4, uint32_t (&a)[4][4]) {
+  const int r0 = row0 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int kt = 0; kt < 4; kt++) {
+    const int col = kt * 16 + 2 * q4;
+    a[kt][0] = r0 < Tn ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r0 * ld + col) : 0u;
+    a[kt][1] = r1 < Tn ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r1 * ld + col) : 0u;
+    a[kt][2] = r0 < Tn ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r0 * ld + col + 8) : 0u;
+    a[kt][3] = r1 < Tn ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r1 * ld + col + 8) : 0u;
+  }
+}
+// stage a 64 x 64 tile (rows row0.., zero beyond Tn) of a row-major global matrix into shared memory [64][BA_PITCH]
+__device__ __forceinline__ void stage_tile(const bf16* src, int64_t ld, int row0, int Tn, bf16* dst, int tid) {
+  for (int ch = tid; ch < BA_T * 8; ch += 128) {
+    const int row = ch >> 3, cc = (ch & 7) * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row0 + row < Tn) v = *reinterpret_cast<const uint4*>(src + (int64_t)(row0 + row) * ld + cc);
+    *reinterpret_cast<uint4*>(dst + row * BA_PITCH + cc) = v;
+  }
+}
+// acc[j] (16 x 8 tile j of a 16 x 64 product) = A(16 x 64 frags) * tile^T, tile = [64 n][64 k] row-major in shared memory
+__device__ __forceinline__ void mm_nt(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile_addr, int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc[j][i] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < 4; kt++) {
+      uint32_t b0, b1;
+      ldsm2(b0, b1, tile_addr + (uint32_t)(((j * 8 + (lane & 7)) * BA_PITCH + kt * 16 + ((lane >> 3) & 1) * 8) * 2));
+      mma16816(acc[j], a[kt], b0, b1);
+    }
+  }
+}
+// acc[j] += A(16 x 64 frags over the tile's rows) * tile, tile = [64 k][64 n] row-major in shared memory
+__device__ __forceinline__ void mm_nn_acc(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile_addr, int lane) {
+#pragma unroll
+  for (int kt = 0; kt < 4; kt++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      uint32_t b0, b1;
+      ldsm2t(b0, b1, tile_addr + (uint32_t)(((kt * 16 + (lane & 15)) * BA_PITCH + j * 8) * 2));
+      mma16816(acc[j], a[kt], b0, b1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) mha_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, int64_t ld, int Tn, int c, int heads,
+                                                             const bf16* __restrict__ out, int64_t out_ld, const bf16* __restrict__ dout,
+                                                             int64_t dout_ld, float scale, float scale_log2e, bf16* __restrict__ dqkv, int64_t dld,
+                                                             float* __restrict__ lse_d) {
+  __shared__ __align__(16) bf16 Ks[BA_T * BA_PITCH];
+  __shared__ __align__(16) bf16 Vs[BA_T * BA_PITCH];
+  const int n = blockIdx.y / heads, h = blockIdx.y % heads;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
+  const bf16* base = qkv + (int64_t)n * Tn * ld + h * HD;
+  const bf16* obase = out + (int64_t)n * Tn * out_ld + h * HD;
+  const bf16* gbase = dout + (int64_t)n * Tn * dout_ld + h * HD;
+  const int q0 = blockIdx.x * BA_T + warp * 16, r0 = q0 + g, r1 = r0 + 8;
+  uint32_t qa[4][4], ga[4][4];
+  load_afrag(base, ld, q0, Tn, g, q4, qa);
+  load_afrag(gbase, dout_ld, q0, Tn, g, q4, ga);
+  // D = dO . O for rows r0, r1 (each lane holds 16 of the 64 columns of both rows)
+  float D0 = 0.f, D1 = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < 4; kt++) {
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+      const int col = kt * 16 + 2 * q4 + hh * 8;
+      if (r0 < Tn) {
+        const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(obase + (int64_t)r0 * out_ld + col);
+        const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(&ga[kt][hh * 2]);
+        D0 += __bfloat162float(o2.x) * __bfloat162float(g2.x) + __bfloat162float(o2.y) * __bfloat162float(g2.y);
+      }
+      if (r1 < Tn) {
+        const __nv_bfloat162 o2 = *reinterpret_cast<const __nv_bfloat162*>(obase + (int64_t)r1 * out_ld + col);
+        const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(&ga[kt][hh * 2 + 1]);
+        D1 += __bfloat162float(o2.x) * __bfloat162float(g2.x) + __bfloat162float(o2.y) * __bfloat162float(g2.y);
+      }
+    }
+  }
+  D0 += __shfl_xor_sync(0xffffffffu, D0, 1); D0 += __shfl_xor_sync(0xffffffffu, D0, 2);
+  D1 += __shfl_xor_sync(0xffffffffu, D1, 1); D1 += __shfl_xor_sync(0xffffffffu, D1, 2);
+  const uint32_t ks_addr = (uint32_t)__cvta_generic_to_shared(Ks), vs_addr = (uint32_t)__cvta_generic_to_shared(Vs);
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f, lse0 = INFINITY, lse1 = INFINITY;
+  float dq[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) dq[j][i] = 0.f;
+  for (int pass = 0; pass < 2; pass++) {
+    for (int k0 = 0; k0 < Tn; k0 += BA_T) {
+      __syncthreads();
+      stage_tile(base + c, ld, k0, Tn, Ks, tid);
+      if (pass) stage_tile(base + 2 * c, ld, k0, Tn, Vs, tid);
+      __syncthreads();
+      float s[8][4];
+      mm_nt(s, qa, ks_addr, lane);
+      if (pass == 0) {
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int key = k0 + j * 8 + 2 * q4;
+          if (key >= Tn) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+          if (key + 1 >= Tn) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+          mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+          mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        l0 *= exp2f((m0 - mn0) * scale_log2e);
+        l1 *= exp2f((m1 - mn1) * scale_log2e);
+        const float mb0 = mn0 * scale_log2e, mb1 = mn1 * scale_log2e;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          l0 += exp2f(fmaf(s[j][0], scale_log2e, -mb0)) + exp2f(fmaf(s[j][1], scale_log2e, -mb0));
+          l1 += exp2f(fmaf(s[j][2], scale_log2e, -mb1)) + exp2f(fmaf(s[j][3], scale_log2e, -mb1));
+        }
+        m0 = mn0; m1 = mn1;
+      } else {
+        float dp[8][4];
+        mm_nt(dp, ga, vs_addr, lane);
+        uint32_t dsa[4][4];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int key = k0 + j * 8 + 2 * q4;
+          const bool v0 = key < Tn, v1 = key + 1 < Tn;
+          const float p0 = v0 ? exp2f(fmaf(s[j][0], scale_log2e, -lse0)) : 0.f, p1 = v1 ? exp2f(fmaf(s[j][1], scale_log2e, -lse0)) : 0.f;
+          const float p2 = v0 ? exp2f(fmaf(s[j][2], scale_log2e, -lse1)) : 0.f, p3 = v1 ? exp2f(fmaf(s[j][3], scale_log2e, -lse1)) : 0.f;
+          dsa[j >> 1][(j & 1) * 2 + 0] = pack2(p0 * (dp[j][0] - D0), p1 * (dp[j][1] - D0));
+          dsa[j >> 1][(j & 1) * 2 + 1] = pack2(p2 * (dp[j][2] - D1), p3 * (dp[j][3] - D1));
+        }
+        mm_nn_acc(dq, dsa, ks_addr, lane);
+      }
+    }
+    if (pass == 0) {
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      lse0 = r0 < Tn ? m0 * scale_log2e + log2f(l0) : INFINITY;
+      lse1 = r1 < Tn ? m1 * scale_log2e + log2f(l1) : INFINITY;
+      if (q4 == 0) {
+        if (r0 < Tn) { lse_d[((int64_t)blockIdx.y * Tn + r0) * 2] = lse0; lse_d[((int64_t)blockIdx.y * Tn + r0) * 2 + 1] = D0; }
+        if (r1 < Tn) { lse_d[((int64_t)blockIdx.y * Tn + r1) * 2] = lse1; lse_d[((int64_t)blockIdx.y * Tn + r1) * 2 + 1] = D1; }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int col = h * HD + j * 8 + 2 * q4;
+    if (r0 < Tn) *reinterpret_cast<uint32_t*>(dqkv + ((int64_t)n * Tn + r0) * dld + col) = pack2(dq[j][0] * scale, dq[j][1] * scale);
+    if (r1 < Tn) *reinterpret_cast<uint32_t*>(dqkv + ((int64_t)n * Tn + r1) * dld + col) = pack2(dq[j][2] * scale, dq[j][3] * scale);
+  }
+}
+
+__global__ void __launch_bounds__(128) mha_bwd_dkv_mma_kernel(const bf16* __restrict__ qkv, int64_t ld, int Tn, int c, int heads,
+                                                              const bf16* __restrict__ dout, int64_t dout_ld, float scale, float scale_log2e,
+                                                              const float* __restrict__ lse_d, bf16* __restrict__ dqkv, int64_t dld) {
+  __shared__ __align__(16) bf16 Qs[BA_T * BA_PITCH];
+  __shared__ __align__(16) bf16 Gs[BA_T * BA_PITCH];
+  __shared__ float Ls[BA_T], Ds[BA_T];
+  const int n = blockIdx.y / heads, h = blockIdx.y % heads;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
+  const bf16* base = qkv + (int64_t)n * Tn * ld + h * HD;
+  const bf16* gbase = dout + (int64_t)n * Tn * dout_ld + h * HD;
+  const int k0 = blockIdx.x * BA_T + warp * 16, r0 = k0 + g, r1 = r0 + 8;
+  uint32_t ka[4][4], va[4][4];
+  load_afrag(base + c, ld, k0, Tn, g, q4, ka);
+  load_afrag(base + 2 * c, ld, k0, Tn, g, q4, va);
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) { dk[j][i] = 0.f; dv[j][i] = 0.f; }
+  const uint32_t qs_addr = (uint32_t)__cvta_generic_to_shared(Qs), gs_addr = (uint32_t)__cvta_generic_to_shared(Gs);
+  for (int q0 = 0; q0 < Tn; q0 += BA_T) {
+    __syncthreads();
+    stage_tile(base, ld, q0, Tn, Qs, tid);
+    stage_tile(gbase, dout_ld, q0, Tn, Gs, tid);
+    if (tid < BA_T) {
+      const int t = q0 + tid;
+      Ls[tid] = t < Tn ? lse_d[((int64_t)blockIdx.y * Tn + t) * 2] : INFINITY;  // invalid query column -> P = 0
+      Ds[tid] = t < Tn ? lse_d[((int64_t)blockIdx.y * Tn + t) * 2 + 1] : 0.f;
+    }
+    __syncthreads();
+    float st[8][4], dpt[8][4];
+    mm_nt(st, ka, qs_addr, lane);   // S^T = K Q^T
+    mm_nt(dpt, va, gs_addr, lane);  // dP^T = V dO^T
+    uint32_t pta[4][4], dsta[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int qc = j * 8 + 2 * q4;
+      const float L0 = Ls[qc], L1 = Ls[qc + 1], E0 = Ds[qc], E1 = Ds[qc + 1];
+      const float p0 = exp2f(fmaf(st[j][0], scale_log2e, -L0)), p1 = exp2f(fmaf(st[j][1], scale_log2e, -L1));
+      const float p2 = exp2f(fmaf(st[j][2], scale_log2e, -L0)), p3 = exp2f(fmaf(st[j][3], scale_log2e, -L1));
+      pta[j >> 1][(j & 1) * 2 + 0] = pack2(p0, p1);
+      pta[j >> 1][(j & 1) * 2 + 1] = pack2(p2, p3);
+      dsta[j >> 1][(j & 1) * 2 + 0] = pack2(p0 * (dpt[j][0] - E0), p1 * (dpt[j][1] - E1));
+      dsta[j >> 1][(j & 1) * 2 + 1] = pack2(p2 * (dpt[j][2] - E0), p3 * (dpt[j][3] - E1));
+    }
+    mm_nn_acc(dv, pta, gs_addr, lane);   // dV += P^T dO
+    mm_nn_acc(dk, dsta, qs_addr, lane);  // dK += dS^T Q
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int col = h * HD + j * 8 + 2 * q4;
+    if (r0 < Tn) {
+      *reinterpret_cast<uint32_t*>(dqkv + ((int64_t)n * Tn + r0) * dld + c + col) = pack2(dk[j][0] * scale, dk[j][1] * scale);
+      *reinterpret_cast<uint32_t*>(dqkv + ((int64_t)n * Tn + r0) * dld + 2 * c + col) = pack2(dv[j][0], dv[j][1]);
+    }
+    if (r1 < Tn) {
+      *reinterpret_cast<uint32_t*>(dqkv + ((int64_t)n * Tn + r1) * dld + c + col) = pack2(dk[j][2] * scale, dk[j][3] * scale);
+      *reinterpret_cast<uint32_t*>(dqkv + ((int64_t)n * Tn + r1) * dld + 2 * c + col) = pack2(dv[j][2], dv[j][3]);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -304,6 +545,16 @@ int yad_mha_bwd(const yad_tensor* qkv, int heads, const yad_tensor* out, const y
   YAD_CHECK(out->n == qkv->n && out->h * out->w == Tn && dout->h * dout->w == Tn && dqkv->h * dqkv->w == Tn, "mha_bwd: token count mismatch");
   cudaStream_t st = (cudaStream_t)stream;
   const float scale = 1.0f / sqrtf((float)HD);
+  if (dtype == YAD_BF16) {  // tensor-core path
+    dim3 g2((Tn + BA_T - 1) / BA_T, qkv->n * heads);
+    const float sl2 = scale * 1.44269504088896340736f;
+    mha_bwd_dq_mma_kernel<<<g2, 128, 0, st>>>((const bf16*)qkv->ptr, qkv->ld, Tn, c, heads, (const bf16*)out->ptr, out->ld, (const bf16*)dout->ptr,
+                                              dout->ld, scale, sl2, (bf16*)dqkv->ptr, dqkv->ld, lse_d);
+    mha_bwd_dkv_mma_kernel<<<g2, 128, 0, st>>>((const bf16*)qkv->ptr, qkv->ld, Tn, c, heads, (const bf16*)dout->ptr, dout->ld, scale, sl2, lse_d,
+                                               (bf16*)dqkv->ptr, dqkv->ld);
+    YAD_LAUNCH_CHECK("mha_bwd");
+    return 0;
+  }
   dim3 grid((Tn + RB - 1) / RB, qkv->n * heads);
   YAD_DISPATCH_DTYPE(dtype, {
     mha_bwd_dq_kernel<T><<<grid, 128, 0, st>>>((const T*)qkv->ptr, qkv->ld, Tn, c, heads, (const T*)out->ptr, out->ld, (const T*)dout->ptr, dout->ld,

@@ -170,6 +170,101 @@ __global__ void __launch_bounds__(128) conv_wgrad_mma_kernel(const bf16* __restr
   }
 }
 
+
+// ---- small-channel 3x3 wgrad (cin, cout <= 32; the first layers and the head's narrow convs): HBM-bound, so every operand byte is read ONCE.
+//   A persistent CTA walks tiles of 8 x 32 output pixels of one image: the input patch (with its 1-pixel halo; stride 1 or 2) and the dy tile
+//   are staged in shared memory with 128-bit loads (zero-filled padding / ragged edges), then all 9 taps are accumulated from the same staged
+//   data: warp (kg, ng) owns the 8-channel input group ng for all taps (9 n-tiles x MT m-tiles of mma.sync.m16n8k16 accumulators in
+//   registers) and every KW-th 16-pixel k-step.  One shared-memory reduction + one global atomic per weight per CTA at the very end.
+constexpr int WS_TH = 8, WS_TW = 32, WS_THREADS = 256;
+__host__ __device__ constexpr int ws_pitch(int c) { return ((c >> 3) & 1) ? c + 16 : c + 8; }  // odd number of 16-byte slots per row: conflict-free ldmatrix
+
+template <int MT>
+__global__ void __launch_bounds__(WS_THREADS, 2) conv_wgrad_small_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, WgGeom g,
+                                                                          float* __restrict__ dw, int tiles_x, int tiles_y, int total_tiles) {
+  extern __shared__ __align__(16) uint8_t ws_smem[];
+  const int s = g.stride;
+  const int PH = (WS_TH - 1) * s + 3, PW = (WS_TW - 1) * s + 3;
+  const int cpitch = ws_pitch(g.cin), dpitch = ws_pitch(MT * 16);
+  bf16* patch = reinterpret_cast<bf16*>(ws_smem);
+  bf16* dys = patch + (size_t)PH * PW * cpitch;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NW = g.cin >> 3, KW = 8 / NW;  // NW in {1, 2, 4}
+  const int ng = warp % NW, kg = warp / NW;
+  float acc[9][MT][4];
+#pragma unroll
+  for (int t = 0; t < 9; t++)
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+      for (int i = 0; i < 4; i++) acc[t][m][i] = 0.f;
+  // the dy staging area is zeroed once: channel columns >= cout (padding up to MT*16) are never written afterwards
+  for (int i = tid; i < WS_TH * WS_TW * dpitch / 8; i += WS_THREADS) reinterpret_cast<uint4*>(dys)[i] = make_uint4(0u, 0u, 0u, 0u);
+  const uint32_t patch_s = (uint32_t)__cvta_generic_to_shared(patch), dys_s = (uint32_t)__cvta_generic_to_shared(dys);
+  const int coct = g.cin >> 3, doct = g.cout >> 3;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, img = tile / (tiles_x * tiles_y);
+    const int oy0 = ty * WS_TH, ox0 = tx * WS_TW;
+    const int iy0 = oy0 * s - g.pad_h, ix0 = ox0 * s - g.pad_w;
+    __syncthreads();  // previous tile fully consumed
+    for (int ch = tid; ch < PH * PW * coct; ch += WS_THREADS) {
+      const int oc = ch % coct, pp = ch / coct, px = pp % PW, py = pp / PW;
+      const int iy = iy0 + py, ix = ix0 + px;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (iy >= 0 && iy < g.hi && ix >= 0 && ix < g.wi) v = *reinterpret_cast<const uint4*>(x + (((int64_t)img * g.hi + iy) * g.wi + ix) * g.x_ld + oc * 8);
+      *reinterpret_cast<uint4*>(patch + (size_t)pp * cpitch + oc * 8) = v;
+    }
+    for (int ch = tid; ch < WS_TH * WS_TW * doct; ch += WS_THREADS) {
+      const int oc = ch % doct, pp = ch / doct, px = pp % WS_TW, py = pp / WS_TW;
+      const int oy = oy0 + py, ox = ox0 + px;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (oy < g.ho && ox < g.wo) v = *reinterpret_cast<const uint4*>(dy + (((int64_t)img * g.ho + oy) * g.wo + ox) * g.dy_ld + oc * 8);
+      *reinterpret_cast<uint4*>(dys + (size_t)pp * dpitch + oc * 8) = v;
+    }
+    __syncthreads();
+    for (int kk = kg; kk < WS_TH * WS_TW / 16; kk += KW) {
+      const int py = kk / (WS_TW / 16), px0 = (kk % (WS_TW / 16)) * 16;
+      if (oy0 + py >= g.ho || ox0 + px0 >= g.wo) continue;  // warp-uniform: this k-step holds only zero dy
+      uint32_t a[MT][4];
+      {
+        const int mat = lane >> 3, r = lane & 7, mi = mat & 1, kj = mat >> 1;
+#pragma unroll
+        for (int m = 0; m < MT; m++) ldsm_x4_trans(a[m], dys_s + (uint32_t)(((py * WS_TW + px0 + kj * 8 + r) * dpitch + m * 16 + mi * 8) * 2));
+      }
+      const int r16 = lane & 15;
+#pragma unroll
+      for (int t = 0; t < 9; t++) {
+        const int ky = t / 3, kx = t % 3;
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, patch_s + (uint32_t)((((py * s + ky) * PW + (px0 + r16) * s + kx) * cpitch + ng * 8) * 2));
+#pragma unroll
+        for (int m = 0; m < MT; m++) mma_bf16_16816(acc[t][m], a[m], b0, b1);
+      }
+    }
+  }
+  // cross-warp reduction in shared memory (reusing the patch area), then one global atomic per weight
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(ws_smem);
+  const int nw = MT * 16 * 9 * g.cin;
+  for (int i = tid; i < nw; i += WS_THREADS) red[i] = 0.f;
+  __syncthreads();
+  const int gq = lane >> 2, q4 = lane & 3;
+#pragma unroll
+  for (int t = 0; t < 9; t++)
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int co = m * 16 + gq + (i >> 1) * 8, ci = ng * 8 + 2 * q4 + (i & 1);
+        atomicAdd(&red[(co * 9 + t) * g.cin + ci], acc[t][m][i]);
+      }
+  __syncthreads();
+  for (int i = tid; i < nw; i += WS_THREADS) {
+    const int co = i / (9 * g.cin);
+    if (co < g.cout && red[i] != 0.f) atomicAdd(&dw[i], red[i]);
+  }
+}
+
 // ---- depthwise wgrad: grid (taps, chunks); dW[tap][c] += sum_p dy[p][c] * x[p + tap][c] -----------------------------------------------
 template <typename T>
 __global__ void dwconv_wgrad_kernel(yad_tensor x, yad_tensor dy, int k, float* __restrict__ dw) {
@@ -330,6 +425,31 @@ int yad_conv_wgrad(const yad_tensor* x, const yad_tensor* dy, const yad_conv_des
   const int ntaps = g.kh * g.kw;
   const int tiles = cdiv(g.cin, 64) * ntaps * cdiv(g.cout, 64);
   const bool mma = dtype == YAD_BF16 && d->impl != 1;
+  if (mma && d->kh == 3 && d->kw == 3 && d->pad_h == 1 && d->pad_w == 1 && (d->stride == 1 || d->stride == 2) && x->c <= 32 && dy->c <= 32 &&
+      (x->c == 8 || x->c == 16 || x->c == 32)) {
+    // small-channel path: every byte of x and dy is read once, all 9 taps from one staged tile
+    const int s = d->stride;
+    const int tiles_x = cdiv(g.wo, WS_TW), tiles_y = cdiv(g.ho, WS_TH), total = g.n * tiles_x * tiles_y;
+    const int MT = dy->c > 16 ? 2 : 1;
+    const int PH = (WS_TH - 1) * s + 3, PW = (WS_TW - 1) * s + 3;
+    size_t smem = (size_t)PH * PW * ws_pitch(x->c) * 2 + (size_t)WS_TH * WS_TW * ws_pitch(MT * 16) * 2;
+    const size_t red = (size_t)MT * 16 * 9 * x->c * 4;
+    if (smem < red) smem = red;
+    int grid = 148 * 2;
+    if (grid > total) grid = total;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (MT == 2) {
+      static bool attr2 = false;
+      if (!attr2) { cudaFuncSetAttribute(conv_wgrad_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr2 = true; }
+      conv_wgrad_small_kernel<2><<<grid, WS_THREADS, smem, st>>>((const bf16*)x->ptr, (const bf16*)dy->ptr, g, dw, tiles_x, tiles_y, total);
+    } else {
+      static bool attr1 = false;
+      if (!attr1) { cudaFuncSetAttribute(conv_wgrad_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr1 = true; }
+      conv_wgrad_small_kernel<1><<<grid, WS_THREADS, smem, st>>>((const bf16*)x->ptr, (const bf16*)dy->ptr, g, dw, tiles_x, tiles_y, total);
+    }
+    YAD_LAUNCH_CHECK("conv_wgrad (small-channel)");
+    return 0;
+  }
   const int step = mma ? WG_P : SB_P;
   int splits = cdiv(148 * 6, tiles);
   const int64_t max_splits = (g.M + step * 4 - 1) / (step * 4);
