@@ -114,8 +114,23 @@ __global__ void norm_bwd_reduce_kernel(yad_tensor x, yad_tensor dy, const double
         b[i] = fmaf(gg, xh, b[i]);
       }
     }
+    // lanes of a warp that own the same octet (lane % oct equal) combine with shuffles first: 32 / oct times fewer shared-memory atomics
+    if (oct <= 16 && (32 % oct) == 0) {
+      for (int d = oct; d < 32; d <<= 1) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) { atomicAdd(&sA[o + i], a[i]); atomicAdd(&sB[o + i], b[i]); }
+        for (int i = 0; i < 8; i++) {
+          a[i] += __shfl_xor_sync(0xffffffffu, a[i], d);
+          b[i] += __shfl_xor_sync(0xffffffffu, b[i], d);
+        }
+      }
+      if ((threadIdx.x & 31) < oct) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) { atomicAdd(&sA[o + i], a[i]); atomicAdd(&sB[o + i], b[i]); }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) { atomicAdd(&sA[o + i], a[i]); atomicAdd(&sB[o + i], b[i]); }
+    }
   } else {
     for (int64_t it = threadIdx.x; it < items; it += blockDim.x) {
       const int64_t p = p0 + it / oct;
@@ -1007,15 +1022,17 @@ int yad_norm_bwd(const yad_tensor* x, const yad_tensor* dy, const double* stats,
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups * x->n, st);
   const int64_t hw = (int64_t)x->h * x->w;
-  int chunks = (int)((hw * (x->c / 8) + TPB * 8 - 1) / (TPB * 8));
-  chunks = chunks < 1 ? 1 : (chunks > 592 ? 592 : chunks);
-  if (x->n > 1 && chunks > 64) chunks = 64;
+  // grids are sized for the whole launch (about 8 CTAs per SM in total), not per image: the per-CTA prologue (statistics -> mean / rstd per
+  // channel) and epilogue (shared -> global atomics) are amortised over >= 16 pixel-octets per thread
+  int chunks = (int)((hw * (x->c / 8) + TPB * 16 - 1) / (TPB * 16));
+  const int cap1 = 1184 / x->n > 1 ? 1184 / x->n : 1;
+  chunks = chunks < 1 ? 1 : (chunks > cap1 ? cap1 : chunks);
   const size_t smem = 4 * x->c * sizeof(float);
   YAD_CHECK(smem <= 48 * 1024, "norm_bwd: too many channels (%d)", x->c);
   dim3 g1(chunks, x->n);
-  int gx = (int)((hw * (x->c / 8) + TPB * 4 - 1) / (TPB * 4));
-  gx = gx < 1 ? 1 : (gx > 1184 ? 1184 : gx);
-  if (x->n > 1 && gx > 256) gx = 256;
+  int gx = (int)((hw * (x->c / 8) + TPB * 8 - 1) / (TPB * 8));
+  const int cap2 = 2368 / x->n > 1 ? 2368 / x->n : 1;
+  gx = gx < 1 ? 1 : (gx > cap2 ? cap2 : gx);
   dim3 g2(gx, x->n);
   YAD_DISPATCH_DTYPE(dtype, {
     norm_bwd_reduce_kernel<T><<<g1, TPB, smem, st>>>(*x, *dy, stats, groups, gamma, beta, eps, act, sums, dgamma, dbeta);

@@ -265,30 +265,45 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_wgrad_small_kernel(const b
   }
 }
 
-// ---- depthwise wgrad: grid (taps, chunks); dW[tap][c] += sum_p dy[p][c] * x[p + tap][c] -----------------------------------------------
-template <typename T>
-__global__ void dwconv_wgrad_kernel(yad_tensor x, yad_tensor dy, int k, float* __restrict__ dw) {
-  extern __shared__ float sm[];
-  const int c = x.c, oct = c >> 3, r = k >> 1, tap = blockIdx.x, ky = tap / k, kx = tap % k;
-  for (int i = threadIdx.x; i < c; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
+// ---- depthwise wgrad: dW[tap][c] += sum_p dy[p][c] * x[p + tap][c].  A thread owns (8-channel octet, kernel row ky, pixel lane) and keeps the k
+//      taps of its row in registers while it strides over the CTA's pixel chunk: dy is read once per kernel row, the k x k neighbourhood of x
+//      comes from L1/L2; one global atomic per (tap, channel) per thread at the end (warp-shuffle pre-reduction when lanes share an octet).
+template <typename T, int K>
+__global__ void __launch_bounds__(256) dwconv_wgrad_kernel(yad_tensor x, yad_tensor dy, float* __restrict__ dw) {
+  const int c = x.c, oct = c >> 3, r = K >> 1;
+  const int per_pix = oct * K, lanes = blockDim.x / per_pix;
+  const int tid = threadIdx.x;
+  const int o = (tid % oct) * 8, ky = (tid / oct) % K, pl = tid / per_pix;
   const int64_t npix = (int64_t)x.n * x.h * x.w;
-  const int64_t per = (npix + gridDim.y - 1) / gridDim.y, p0 = blockIdx.y * per, p1 = min(npix, p0 + per);
-  const int64_t items = (p1 - p0) * oct;
-  for (int64_t it = threadIdx.x; it < items; it += blockDim.x) {
-    const int64_t p = p0 + it / oct;
-    const int o = (int)(it % oct) * 8;
-    const int px = (int)(p % x.w), py = (int)((p / x.w) % x.h);
-    const int iy = py + ky - r, ix = px + kx - r;
-    if (iy < 0 || iy >= x.h || ix < 0 || ix >= x.w) continue;
-    float v[8], gg[8];
-    load8(reinterpret_cast<const T*>(x.ptr) + (p + (int64_t)(ky - r) * x.w + (kx - r)) * x.ld + o, v);
-    load8(reinterpret_cast<const T*>(dy.ptr) + p * dy.ld + o, gg);
+  const int64_t per = (npix + gridDim.x - 1) / gridDim.x, p0 = blockIdx.x * per, p1 = min(npix, p0 + per);
+  float acc[K][8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) atomicAdd(&sm[o + i], v[i] * gg[i]);
+  for (int t = 0; t < K; t++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[t][i] = 0.f;
+  if (pl < lanes) {
+    for (int64_t p = p0 + pl; p < p1; p += lanes) {
+      const int px = (int)(p % x.w), py = (int)((p / x.w) % x.h);
+      const int iy = py + ky - r;
+      if (iy < 0 || iy >= x.h) continue;
+      float gg[8];
+      load8(reinterpret_cast<const T*>(dy.ptr) + p * dy.ld + o, gg);
+      const T* xrow = reinterpret_cast<const T*>(x.ptr) + (p + (int64_t)(ky - r) * x.w - r) * x.ld + o;
+#pragma unroll
+      for (int t = 0; t < K; t++) {
+        const int ix = px + t - r;
+        if (ix < 0 || ix >= x.w) continue;
+        float v[8];
+        load8(xrow + (int64_t)t * x.ld, v);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[t][i] = fmaf(v[i], gg[i], acc[t][i]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < K; t++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) atomicAdd(&dw[(int64_t)(ky * K + t) * c + o + i], acc[t][i]);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&dw[(int64_t)tap * c + i], sm[i]);
 }
 
 // ---- modulated deformable sampling (DCNv2, 3x3, stride 1, pad 1, one offset group) ---------------------------------------------------------
@@ -374,13 +389,17 @@ __global__ void deform_col_bwd_kernel(yad_tensor x, const T* __restrict__ om, in
           const int64_t q = ((int64_t)n * x.h + yy) * x.w + xx;
           float t[8];
           load8(reinterpret_cast<const T*>(x.ptr) + q * x.ld + o, t);
+          const float wm = s.mk * wgt[c4];
 #pragma unroll
           for (int i = 0; i < 8; i++) {
             dmk = fmaf(g[i] * wgt[c4], t[i], dmk);
             dpy = fmaf(g[i] * wy[c4], t[i], dpy);
             dpx = fmaf(g[i] * wx[c4], t[i], dpx);
-            atomicAdd(&dx_f[q * C + o + i], g[i] * s.mk * wgt[c4]);
           }
+          // 128-bit vector reductions (red.global.add.v4.f32, sm_90+): 2 instead of 8 atomics per corner
+          float4* dst = reinterpret_cast<float4*>(dx_f + q * C + o);
+          atomicAdd(dst, make_float4(g[0] * wm, g[1] * wm, g[2] * wm, g[3] * wm));
+          atomicAdd(dst + 1, make_float4(g[4] * wm, g[5] * wm, g[6] * wm, g[7] * wm));
         }
       }
     }
@@ -471,11 +490,17 @@ int yad_conv_wgrad(const yad_tensor* x, const yad_tensor* dy, const yad_conv_des
 /* dw fp32 [k*k][c] += ... (accumulating) */
 int yad_dwconv_wgrad(const yad_tensor* x, const yad_tensor* dy, int k, float* dw, int dtype, void* stream) {
   YAD_CHECK(x->n == dy->n && x->h == dy->h && x->w == dy->w && x->c == dy->c && x->c % 8 == 0, "dwconv_wgrad: shape mismatch");
+  YAD_CHECK((k == 3 || k == 7) && (x->c / 8) * k <= 256, "dwconv_wgrad: k = %d with %d channels is not built (k in {3, 7}, c/8*k <= 256)", k, x->c);
   const int64_t npix = (int64_t)x->n * x->h * x->w;
-  int chunks = (int)((npix * (x->c / 8) + 256 * 16 - 1) / (256 * 16));
-  chunks = chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks);
-  dim3 grid(k * k, chunks);
-  YAD_DISPATCH_DTYPE(dtype, dwconv_wgrad_kernel<T><<<grid, 256, x->c * sizeof(float), (cudaStream_t)stream>>>(*x, *dy, k, dw);)
+  const int lanes = 256 / ((x->c / 8) * k);
+  int64_t want = (npix + (int64_t)lanes * 16 - 1) / ((int64_t)lanes * 16);  // >= 16 pixels per thread before the final atomics
+  int grid = (int)(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k == 3) {
+    YAD_DISPATCH_DTYPE(dtype, dwconv_wgrad_kernel<T, 3><<<grid, 256, 0, st>>>(*x, *dy, dw);)
+  } else {
+    YAD_DISPATCH_DTYPE(dtype, dwconv_wgrad_kernel<T, 7><<<grid, 256, 0, st>>>(*x, *dy, dw);)
+  }
   YAD_LAUNCH_CHECK("dwconv_wgrad");
   return 0;
 }
