@@ -214,7 +214,8 @@ int yad_eltwise_dev(int op, const yad_tensor* a, const void* b, int b_ld, const 
 
 /* conv weight gradient (autograd of F.conv2d w.r.t. weight): dw fp32 [cout][kh*kw][cin] += sum_m dy[m][co] * x[pix(m,tap)][ci].
  * NORMAL mode geometry only (kh, kw, stride, pad of `d`; d->impl 1 = SIMT twin); ConvTranspose2d / deformable weights go through it with
- * swapped operands / the column tensor.  bf16: mma.sync tensor cores; split-K with fp32 atomics. */
+ * swapped operands / the column tensor.  bf16, d->impl 0: tcgen05 / TMEM with TMA-fed MN-major operands (stride 1, cin % 64 == 0), a single-pass
+ * mma.sync kernel for <= 32 channels, mma.sync split-K otherwise; d->impl 3 forces the mma.sync kernels.  fp32 atomics into dw. */
 int yad_conv_wgrad(const yad_tensor* x, const yad_tensor* dy, const yad_conv_desc* d, float* dw, int dtype, void* stream);
 /* depthwise weight gradient: dw fp32 [k*k][c] += sum_p dy[p][c] * x[p + tap][c] */
 int yad_dwconv_wgrad(const yad_tensor* x, const yad_tensor* dy, int k, float* dw, int dtype, void* stream);

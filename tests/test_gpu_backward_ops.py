@@ -32,6 +32,9 @@ GEOMS = [
     (32, 32, 3, 3, 1, 3, 40, 24),
     (32, 16, 3, 3, 1, 1, 9, 7),
     (8, 32, 3, 3, 2, 2, 48, 80),
+    (128, 128, 3, 3, 1, 2, 40, 40),   # tcgen05 wgrad: 3 M-tile groups x pixel splits
+    (128, 256, 1, 1, 1, 3, 20, 20),
+    (64, 80, 1, 1, 1, 2, 16, 24),     # cout not a multiple of 64: second dy box partly zero-filled
 ]
 
 
@@ -41,11 +44,13 @@ def _tp(w, b, dtype):
 
 
 @pytest.mark.parametrize("geom", GEOMS)
-@pytest.mark.parametrize("mode", ["fp32", "bf16_simt", "bf16_tc"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16_simt", "bf16_tc", "bf16_mma"])
 def test_conv_wgrad_dgrad(geom, mode):
+    """bf16_tc: impl 0 = tcgen05 / TMEM wgrad where eligible (stride 1, cin % 64 == 0), else the mma.sync kernels; bf16_mma: impl 3 forces
+    the mma.sync wgrad kernels (and the thread-gathered tcgen05 conv for the input gradient)"""
     cin, cout, kh, kw, stride, n, h, w = geom
     dtype = torch.float32 if mode == "fp32" else torch.bfloat16
-    impl = 0 if mode == "bf16_tc" else 1
+    impl = {"bf16_tc": 0, "bf16_mma": 3}.get(mode, 1)
     rs = np.random.RandomState(cin * 7 + cout)
     wt = torch.from_numpy(rs.standard_normal((cout, cin, kh, kw)).astype(np.float32) * 0.1)
     tp = _tp(wt, torch.zeros(cout), dtype)

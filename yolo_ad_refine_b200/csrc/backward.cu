@@ -42,6 +42,22 @@ __device__ __forceinline__ float act_grad(float u, int act) {
   }
 }
 
+// compile-time activation variant for the hot normalisation kernels: no per-element branch, ex2.approx / rcp.approx sigmoid (~2 ulp)
+template <int ACT>
+__device__ __forceinline__ float act_grad_ct(float u) {
+  if constexpr (ACT == YAD_ACT_SILU) {
+    const float s = sigmoid_fast(u);
+    return s * fmaf(u, 1.0f - s, 1.0f);
+  } else if constexpr (ACT == YAD_ACT_SIGMOID) {
+    const float s = sigmoid_fast(u);
+    return s * (1.0f - s);
+  } else if constexpr (ACT == YAD_ACT_NONE) {
+    return 1.0f;
+  } else {
+    return act_grad(u, ACT);
+  }
+}
+
 int grid_for(int64_t items, int tpb = TPB) {
   int64_t g = (items + tpb - 1) / tpb;
   const int64_t cap = 148 * 16;
@@ -67,8 +83,8 @@ int check_view(const yad_tensor* t, const char* what) {
 // pass 1: g = dy * act'(u);  sums[n][grp] += (sum g*gamma, sum g*gamma*xhat);  dgamma[c] += sum g*xhat;  dbeta[c] += sum g
 // pass 2: dx = rstd * (g*gamma - S1/cnt - xhat * S2/cnt)
 // ------------------------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void norm_bwd_reduce_kernel(yad_tensor x, yad_tensor dy, const double* __restrict__ stats, int groups, const float* __restrict__ gamma,
+template <typename T, int ACT>
+__global__ void __launch_bounds__(TPB, 3) norm_bwd_reduce_kernel(yad_tensor x, yad_tensor dy, const double* __restrict__ stats, int groups, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float eps, int act, double* __restrict__ sums,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
   extern __shared__ float sm[];  // mean[c], rstd[c], A[c], B[c]
@@ -99,17 +115,36 @@ __global__ void norm_bwd_reduce_kernel(yad_tensor x, yad_tensor dy, const double
   const int step = fixed ? blockDim.x / oct : 1;
   if (fixed) {
     const int o = (threadIdx.x % oct) * 8, lane = threadIdx.x / oct;
-    float a[8], b[8];
+    float a[8], b[8], c1[8], c2[8], ga[8], be[8];  // per-channel constants live in registers: xhat = v*c1 - c2, u = xhat*ga + be
 #pragma unroll
-    for (int i = 0; i < 8; i++) { a[i] = 0.f; b[i] = 0.f; }
-    for (int64_t p = p0 + lane; p < p1; p += step) {
+    for (int i = 0; i < 8; i++) {
+      a[i] = 0.f; b[i] = 0.f;
+      c1[i] = srstd[o + i]; c2[i] = smean[o + i] * srstd[o + i]; ga[i] = gamma[o + i]; be[i] = beta[o + i];
+    }
+    int64_t p = p0 + lane;
+    for (; p + step < p1; p += 2 * step) {  // two pixels per trip: four 128-bit loads in flight
+      float v[8], g[8], v2[8], g2[8];
+      load8(xb + p * x.ld + o, v);
+      load8(gb + p * dy.ld + o, g);
+      load8(xb + (p + step) * x.ld + o, v2);
+      load8(gb + (p + step) * dy.ld + o, g2);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float xh = fmaf(v[i], c1[i], -c2[i]), xh2 = fmaf(v2[i], c1[i], -c2[i]);
+        const float gg = g[i] * act_grad_ct<ACT>(fmaf(xh, ga[i], be[i]));
+        const float gg2 = g2[i] * act_grad_ct<ACT>(fmaf(xh2, ga[i], be[i]));
+        a[i] += gg + gg2;
+        b[i] = fmaf(gg, xh, fmaf(gg2, xh2, b[i]));
+      }
+    }
+    for (; p < p1; p += step) {
       float v[8], g[8];
       load8(xb + p * x.ld + o, v);
       load8(gb + p * dy.ld + o, g);
 #pragma unroll
       for (int i = 0; i < 8; i++) {
-        const float xh = (v[i] - smean[o + i]) * srstd[o + i];
-        const float gg = g[i] * act_grad(fmaf(xh, gamma[o + i], beta[o + i]), act);
+        const float xh = fmaf(v[i], c1[i], -c2[i]);
+        const float gg = g[i] * act_grad_ct<ACT>(fmaf(xh, ga[i], be[i]));
         a[i] += gg;
         b[i] = fmaf(gg, xh, b[i]);
       }
@@ -141,7 +176,7 @@ __global__ void norm_bwd_reduce_kernel(yad_tensor x, yad_tensor dy, const double
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         const float xh = (v[i] - smean[o + i]) * srstd[o + i];
-        const float gg = g[i] * act_grad(fmaf(xh, gamma[o + i], beta[o + i]), act);
+        const float gg = g[i] * act_grad_ct<ACT>(fmaf(xh, gamma[o + i], beta[o + i]));
         atomicAdd(&sA[o + i], gg);
         atomicAdd(&sB[o + i], gg * xh);
       }
@@ -164,8 +199,8 @@ __global__ void norm_bwd_reduce_kernel(yad_tensor x, yad_tensor dy, const double
   }
 }
 
-template <typename T>
-__global__ void norm_bwd_apply_kernel(yad_tensor x, yad_tensor dy, const double* __restrict__ stats, const double* __restrict__ sums, int groups,
+template <typename T, int ACT>
+__global__ void __launch_bounds__(TPB, 3) norm_bwd_apply_kernel(yad_tensor x, yad_tensor dy, const double* __restrict__ stats, const double* __restrict__ sums, int groups,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act, yad_tensor dx, int acc) {
   extern __shared__ float sm[];  // mean[c], rstd[c], k1[c] = S1/cnt, k2[c] = S2/cnt
   const int c = x.c, n = blockIdx.y, oct = c >> 3, cpg = c / groups;
@@ -189,6 +224,30 @@ __global__ void norm_bwd_apply_kernel(yad_tensor x, yad_tensor dy, const double*
   const T* xb = reinterpret_cast<const T*>(x.ptr) + (int64_t)n * hw * x.ld;
   const T* gb = reinterpret_cast<const T*>(dy.ptr) + (int64_t)n * hw * dy.ld;
   T* ob = reinterpret_cast<T*>(dx.ptr) + (int64_t)n * hw * dx.ld;
+  if ((blockDim.x % oct) == 0) {
+    // thread -> fixed octet; per-channel constants in registers: xhat = v*c1 - c2, u = xhat*ga + be, dx = gg*A - E - xhat*F
+    const int o = (threadIdx.x % oct) * 8, lane = threadIdx.x / oct, ppb = blockDim.x / oct;
+    float c1[8], c2[8], ga[8], be[8], A[8], E[8], F[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      c1[i] = srstd[o + i]; c2[i] = smean[o + i] * srstd[o + i]; ga[i] = gamma[o + i]; be[i] = beta[o + i];
+      A[i] = srstd[o + i] * ga[i]; E[i] = srstd[o + i] * k1[o + i]; F[i] = srstd[o + i] * k2[o + i];
+    }
+    const int64_t stride = (int64_t)gridDim.x * ppb;
+    for (int64_t p = (int64_t)blockIdx.x * ppb + lane; p < hw; p += stride) {
+      float v[8], g[8];
+      load8(xb + p * x.ld + o, v);
+      load8(gb + p * dy.ld + o, g);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float xh = fmaf(v[i], c1[i], -c2[i]);
+        const float gg = g[i] * act_grad_ct<ACT>(fmaf(xh, ga[i], be[i]));
+        v[i] = fmaf(gg, A[i], -fmaf(xh, F[i], E[i]));
+      }
+      store8_acc(ob + p * dx.ld + o, v, acc);
+    }
+    return;
+  }
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = it / oct;
     const int o = (int)(it - p * oct) * 8;
@@ -198,7 +257,7 @@ __global__ void norm_bwd_apply_kernel(yad_tensor x, yad_tensor dy, const double*
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       const float xh = (v[i] - smean[o + i]) * srstd[o + i];
-      const float gg = g[i] * act_grad(fmaf(xh, gamma[o + i], beta[o + i]), act);
+      const float gg = g[i] * act_grad_ct<ACT>(fmaf(xh, gamma[o + i], beta[o + i]));
       v[i] = srstd[o + i] * (gg * gamma[o + i] - k1[o + i] - xh * k2[o + i]);
     }
     store8_acc(ob + p * dx.ld + o, v, acc);
@@ -1034,10 +1093,23 @@ int yad_norm_bwd(const yad_tensor* x, const yad_tensor* dy, const double* stats,
   const int cap2 = 2368 / x->n > 1 ? 2368 / x->n : 1;
   gx = gx < 1 ? 1 : (gx > cap2 ? cap2 : gx);
   dim3 g2(gx, x->n);
+#define NORM_BWD_LAUNCH(A)                                                                                                          \
+  case A:                                                                                                                           \
+    norm_bwd_reduce_kernel<T, A><<<g1, TPB, smem, st>>>(*x, *dy, stats, groups, gamma, beta, eps, act, sums, dgamma, dbeta);         \
+    norm_bwd_apply_kernel<T, A><<<g2, TPB, smem, st>>>(*x, *dy, stats, sums, groups, gamma, beta, eps, act, *dx, acc);               \
+    break;
   YAD_DISPATCH_DTYPE(dtype, {
-    norm_bwd_reduce_kernel<T><<<g1, TPB, smem, st>>>(*x, *dy, stats, groups, gamma, beta, eps, act, sums, dgamma, dbeta);
-    norm_bwd_apply_kernel<T><<<g2, TPB, smem, st>>>(*x, *dy, stats, sums, groups, gamma, beta, eps, act, *dx, acc);
+    switch (act) {
+      NORM_BWD_LAUNCH(YAD_ACT_NONE)
+      NORM_BWD_LAUNCH(YAD_ACT_SILU)
+      NORM_BWD_LAUNCH(YAD_ACT_RELU)
+      NORM_BWD_LAUNCH(YAD_ACT_SIGMOID)
+      NORM_BWD_LAUNCH(YAD_ACT_GELU)
+      NORM_BWD_LAUNCH(YAD_ACT_HARDSWISH)
+      default: yad_set_error("norm_bwd: unknown activation %d", act); return 1;
+    }
   })
+#undef NORM_BWD_LAUNCH
   YAD_LAUNCH_CHECK("norm_bwd");
   return 0;
 }

@@ -427,6 +427,8 @@ int grid_for(int64_t items, int tpb) {
 
 }  // namespace
 
+int yad_conv_wgrad_tc(const yad_tensor* x, const yad_tensor* dy, const yad_conv_desc* d, float* dw, void* stream);  // wgrad_tc.cu
+
 extern "C" {
 
 /* Weight gradient of yad_conv2d's NORMAL mode: dw fp32 [cout][kh*kw][cin] += ...; the caller zeroes dw once per step (gradients of a
@@ -468,6 +470,10 @@ int yad_conv_wgrad(const yad_tensor* x, const yad_tensor* dy, const yad_conv_des
     }
     YAD_LAUNCH_CHECK("conv_wgrad (small-channel)");
     return 0;
+  }
+  if (mma && d->impl == 0) {  // tcgen05 / TMEM path (stride 1, cin % 64 == 0); -1 = geometry not covered
+    const int r = yad_conv_wgrad_tc(x, dy, d, dw, stream);
+    if (r >= 0) return r;
   }
   const int step = mma ? WG_P : SB_P;
   int splits = cdiv(148 * 6, tiles);

@@ -1,0 +1,324 @@
+// tcgen05 / TMEM weight-gradient kernel of the training path (autograd of F.conv2d w.r.t. its weight).
+//
+//   dW[co][tap][ci] = sum over output pixels m of dy[m][co] * x[pix(m, tap)][ci]        (stride-1 convolutions, cin % 64 == 0)
+//
+// As a GEMM the reduction axis is the PIXEL axis, which is the strided one in NHWC: both operands are "MN-major" for the tensor core
+// (channels contiguous, pixels strided).  tcgen05.mma takes MN-major operands straight from shared memory (instruction descriptor bits 15/16),
+// and an NHWC box fetched by TMA with SWIZZLE_128B -- 64 channels x (BH x BW pixels) -- IS the canonical MN-major SWIZZLE_128B layout
+// (rows of 128 B = 64 channels of one pixel, 8-pixel atoms of 1024 B), so no transposition is ever materialised:
+//
+//   D[128 rows][N cols] (TMEM, fp32)  +=  A[128][K=16 px] * B[K=16 px][N]
+//     A rows  = two "row groups" (tap, 64-channel group of cin): two x boxes of the SAME pixel patch (shifted by the tap; conv padding and
+//               ragged edges = TMA zero fill), 64 channels each, LBO = one box apart
+//     B cols  = the cout channels of the dy box of that pixel patch (64-channel groups, LBO = one box apart)
+//
+// CTA (mg, s): M-tile group mg (up to 512 / N accumulators of 128 x N live in TMEM for the whole kernel) x split s of the pixel tiles.
+//   warp 0 / lane 0 : TMA producer -- per pixel tile one dy load + one x load per row group into a 2-3 stage mbarrier ring
+//   warp 1 / lane 0 : tcgen05.mma issuer (KB/16 K-steps per M-tile and stage), tcgen05.commit frees the stage; warp 1 owns the TMEM allocation
+//   warps 2-5       : epilogue after the last pixel tile: tcgen05.ld -> fp32 red.global.add into dW (lanes = consecutive ci: coalesced)
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int WT_THREADS = 192;
+constexpr int WT_MAX_RG = 16;   // row groups (tap, 64-channel group) per CTA
+constexpr int WT_MAX_TAPS = 9;
+
+struct WtParams {
+  int n, h, w, cin, cout;       // stride-1 geometry: output grid == input grid
+  int ntaps, G;                 // G = cin / 64
+  int dy[WT_MAX_TAPS], dx[WT_MAX_TAPS];
+  int bw, bh, kb;               // pixel patch of one K block: kb = bw * bh (multiple of 16, <= 128)
+  int tiles_x, tiles_y, total_tiles;
+  int RG;                       // total row groups = ntaps * G
+  int rg_per_cta;               // row groups handled by one CTA (even, except possibly the tail group)
+  int mgroups, splits;
+  int n_groups;                 // 64-channel groups of the dy box (ceil(cout / 64))
+  int stages, tmem_cols;
+  float* dw;
+};
+
+// ---- PTX wrappers (same conventions as conv_tc.cu) -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; spin++) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();  // a protocol bug must fault, never hang the GPU
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+               "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// MN-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in
+// 16-byte units): start >> 4 | LBO (bytes between 64-element groups of the M/N axis) >> 4 << 16 | SBO (bytes between 8-row K atoms = 1024) >> 4
+// << 32 | version 1 << 46 | layout SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b_format BF16 (1) @7/@10, A and B MN-major (1) @15/@16, N >> 3 @17, M = 128 >> 4 @24
+__device__ __forceinline__ uint32_t make_idesc_mn(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(WT_THREADS) wgrad_tc_kernel(const __grid_constant__ WtParams p, const __grid_constant__ CUtensorMap tmX,
+                                                             const __grid_constant__ CUtensorMap tmDy) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t box_bytes = (uint32_t)p.kb * 128u;  // one 64-channel box of the pixel patch
+  const int mg = blockIdx.x % p.mgroups, split = blockIdx.x / p.mgroups;
+  const int rg0 = mg * p.rg_per_cta;
+  const int nrg = min(p.rg_per_cta, p.RG - rg0);     // row groups of this CTA
+  const int nmt = (nrg + 1) >> 1;                    // M-tiles (two row groups each)
+  const int slots = 2 * ((p.rg_per_cta + 1) >> 1);   // x boxes reserved per stage (even: the last M-tile may read one stale box)
+  const uint32_t stage_bytes = (uint32_t)(p.n_groups + slots) * box_bytes;
+  const uint32_t bars = base + (uint32_t)p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (p.stages + s); };
+  const uint32_t done_bar = bars + 8u * (2 * p.stages);
+  const uint32_t tmem_ptr_addr = done_bar + 8u;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // this CTA's pixel tiles
+  const int t_begin = (int)(((int64_t)p.total_tiles * split) / p.splits), t_end = (int)(((int64_t)p.total_tiles * (split + 1)) / p.splits);
+  const int per_img = p.tiles_x * p.tiles_y;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDy) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)(p.n_groups + nrg) * box_bytes;
+      uint32_t it = 0;
+      for (int tile = t_begin; tile < t_end; tile++, it++) {
+        const int img = tile / per_img, r = tile - img * per_img;
+        const int ty0 = (r / p.tiles_x) * p.bh, tx0 = (r % p.tiles_x) * p.bw;
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1u;
+        const uint32_t st = base + s * stage_bytes;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), tx_bytes);
+        for (int g = 0; g < p.n_groups; g++) tma_load_4d(st + g * box_bytes, &tmDy, full_bar(s), g * 64, tx0, ty0, img);
+        for (int j = 0; j < nrg; j++) {
+          const int rg = rg0 + j, tap = rg / p.G, cg = rg - tap * p.G;
+          tma_load_4d(st + (p.n_groups + j) * box_bytes, &tmX, full_bar(s), cg * 64, tx0 + p.dx[tap], ty0 + p.dy[tap], img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_mn(p.cout);
+      uint32_t it = 0;
+      for (int tile = t_begin; tile < t_end; tile++, it++) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t st = base + s * stage_bytes;
+        const uint32_t b_s = st, a_s = st + p.n_groups * box_bytes;
+        for (int mt = 0; mt < nmt; mt++) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(mt * p.cout);
+          for (int k = 0; k < p.kb / 16; k++) {
+            const uint64_t ad = make_sdesc_mn(a_s + (uint32_t)(2 * mt) * box_bytes + (uint32_t)k * 2048u, box_bytes);
+            const uint64_t bd = make_sdesc_mn(b_s + (uint32_t)k * 2048u, box_bytes);
+            umma_f16(d_tmem, ad, bd, idesc, (it | (uint32_t)k) ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(done_bar);
+    }
+    __syncwarp();
+    tc_fence_before();
+  } else if (t_end > t_begin) {
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read (warps 2..5 -> 2, 3, 0, 1)
+    const int row = quarter * 32 + lane;
+    mbar_wait(done_bar, 0u);
+    tc_fence_after();
+    for (int mt = 0; mt < nmt; mt++) {
+      const int j = 2 * mt + (row >> 6);  // row group inside the CTA
+      const bool valid = j < nrg;
+      const int rg = rg0 + (valid ? j : 0), tap = rg / p.G, cg = rg - tap * p.G;
+      const int ci = cg * 64 + (row & 63);
+      float* dst = p.dw + (int64_t)tap * p.cin + ci;  // + co * ntaps * cin
+      for (int c0 = 0; c0 < p.cout; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * p.cout + c0), v);
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const float f = __uint_as_float(v[i]);
+            if (f != 0.f) atomicAdd(dst + (int64_t)(c0 + i) * p.ntaps * p.cin, f);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// NHWC view (n, h, w, c; pixel stride ld) as a 4-D bf16 tensor map, box = 64 channels x bw x bh x 1, SWIZZLE_128B, zero fill out of bounds
+int make_nhwc_map(CUtensorMap* tm, const yad_tensor* t, int bw, int bh) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return 1;
+  cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
+  cuuint64_t strides[3] = {(cuuint64_t)t->ld * 2, (cuuint64_t)t->w * t->ld * 2, (cuuint64_t)t->h * t->w * t->ld * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1}, es[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1;
+}
+
+// pixel patch (bw x bh, a multiple of 16 pixels, at most kb_max) that wastes the fewest zero-filled pixels on an (h, w) map
+void pick_patch_k(int h, int w, int kb_max, int* bw_out, int* bh_out) {
+  double best = -1;
+  int best_area = 0;
+  *bw_out = 16; *bh_out = 1;
+  for (int bw = 1; bw <= (w < 256 ? w : 256); bw++) {
+    for (int bh = 1; bh <= (h < 256 ? h : 256) && bw * bh <= kb_max; bh++) {
+      const int area = bw * bh;
+      if (area % 16) continue;
+      const int tx = (w + bw - 1) / bw, ty = (h + bh - 1) / bh;
+      const double eff = (double)h * w / ((double)tx * ty * area);
+      if (eff > best + 1e-9 || (eff > best - 1e-9 && area > best_area)) { best = eff; best_area = area; *bw_out = bw; *bh_out = bh; }
+    }
+  }
+}
+
+}  // namespace
+
+// Returns 0 when the launch was issued, 1 on error, -1 when the geometry is not covered by this kernel (the caller falls back to mma.sync).
+int yad_conv_wgrad_tc(const yad_tensor* x, const yad_tensor* dy, const yad_conv_desc* d, float* dw, void* stream) {
+  if (d->stride != 1 || d->kh * d->kw > WT_MAX_TAPS || d->pad_h != d->kh / 2 || d->pad_w != d->kw / 2) return -1;
+  if (x->c % 64 != 0 || dy->c % 16 != 0 || dy->c > 256 || dy->c < 16) return -1;
+  if (x->h != dy->h || x->w != dy->w || (int64_t)x->h * x->w < 16) return -1;
+  if (((uintptr_t)x->ptr & 15) || ((uintptr_t)dy->ptr & 15)) return -1;
+  static int sm100 = -1;
+  if (sm100 < 0) {
+    int dev = 0, major = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    sm100 = major == 10 ? 1 : 0;
+  }
+  if (!sm100 || !get_encode()) return -1;
+  WtParams p;
+  p.n = x->n; p.h = x->h; p.w = x->w; p.cin = x->c; p.cout = dy->c;
+  p.ntaps = d->kh * d->kw;
+  p.G = x->c / 64;
+  for (int t = 0; t < p.ntaps; t++) { p.dy[t] = t / d->kw - d->pad_h; p.dx[t] = t % d->kw - d->pad_w; }
+  p.RG = p.ntaps * p.G;
+  p.n_groups = (p.cout + 63) / 64;
+  // M-tiles per CTA: all accumulators (128 x cout fp32 each) stay in TMEM (512 columns)
+  const int mtiles = (p.RG + 1) / 2;
+  int mpc = 512 / p.cout;
+  if (mpc > WT_MAX_RG / 2) mpc = WT_MAX_RG / 2;
+  if (mpc > mtiles) mpc = mtiles;
+  p.mgroups = (mtiles + mpc - 1) / mpc;
+  mpc = (mtiles + p.mgroups - 1) / p.mgroups;  // balance the groups
+  p.rg_per_cta = 2 * mpc;
+  int cols = mpc * p.cout, tc = 32;
+  while (tc < cols) tc <<= 1;
+  p.tmem_cols = tc;
+  // pixel patch / pipeline depth: stage = (dy groups + x boxes) * kb * 128 B
+  const int boxes = p.n_groups + p.rg_per_cta;
+  int kb_max = 128;
+  while (kb_max > 32 && 2 * boxes * kb_max * 128 > 200 * 1024) kb_max >>= 1;
+  pick_patch_k(p.h, p.w, kb_max, &p.bw, &p.bh);
+  p.kb = p.bw * p.bh;
+  if (p.kb % 16 || 2 * boxes * p.kb * 128 > 200 * 1024) return -1;
+  p.stages = (200 * 1024) / (boxes * p.kb * 128);
+  if (p.stages > 4) p.stages = 4;
+  p.tiles_x = (p.w + p.bw - 1) / p.bw;
+  p.tiles_y = (p.h + p.bh - 1) / p.bh;
+  p.total_tiles = p.n * p.tiles_x * p.tiles_y;
+  p.splits = 148 / p.mgroups;
+  if (p.splits > p.total_tiles) p.splits = p.total_tiles;
+  if (p.splits < 1) p.splits = 1;
+  p.dw = dw;
+  CUtensorMap tmX, tmDy;
+  if (make_nhwc_map(&tmX, x, p.bw, p.bh) || make_nhwc_map(&tmDy, dy, p.bw, p.bh)) return -1;
+  const size_t smem = (size_t)p.stages * boxes * p.kb * 128 + 8 * (2 * p.stages + 1) + 16 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr = true;
+  }
+  wgrad_tc_kernel<<<p.mgroups * p.splits, WT_THREADS, smem, (cudaStream_t)stream>>>(p, tmX, tmDy);
+  YAD_LAUNCH_CHECK("conv_wgrad (tcgen05)");
+  return 0;
+}
