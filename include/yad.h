@@ -101,11 +101,12 @@ int yad_rowcol_gate(const yad_tensor* x, const yad_tensor* gh, const yad_tensor*
 /* adaptive_avg_pool to (h/s, w/s) followed by bilinear upsample back, align_corners=False (block.py:2451-2457) */
 int yad_pool_upsample(const yad_tensor* x, int s, const yad_tensor* y, int dtype, void* stream);
 
-/* -- MLCA (block.py:1540-1584). local: fp32 [n][ls*ls][c] workspace, att: fp32 [n][ls*ls][c] (ls = local_size = 5).
+/* -- MLCA (block.py:1540-1584). local: fp32 [n][ls*ls][c] workspace, att: fp32 [n][ls*ls][c] (ls = local_size = 5), scratch: fp32 [n][c]
+ *    (per-image global-branch gates; the reference pools them over the BATCH axis, block.py:1575-1579).
  *    yad_mlca_apply: y = x * adaptive_avg_pool(att -> (h,w)) (+ add) */
 int yad_mlca_pool(const yad_tensor* x, float* local, int local_size, int dtype, void* stream);
 int yad_mlca_att(const float* local, const float* w_global, const float* w_local, int ksize, float local_weight, int n, int c,
-                 int local_size, float* att, void* stream);
+                 int local_size, float* att, float* scratch, void* stream);
 int yad_mlca_apply(const yad_tensor* x, const float* att, int local_size, const void* add, int add_ld, const yad_tensor* y, int dtype,
                    void* stream);
 

@@ -35,6 +35,11 @@ GEOMS = [
     (128, 128, 3, 3, 1, 2, 40, 40),   # tcgen05 wgrad: 3 M-tile groups x pixel splits
     (128, 256, 1, 1, 1, 3, 20, 20),
     (64, 80, 1, 1, 1, 2, 16, 24),     # cout not a multiple of 64: second dy box partly zero-filled
+    (64, 128, 3, 3, 2, 2, 40, 40),    # stride 2 through the TMA traversal stride
+    (128, 128, 3, 3, 2, 2, 20, 28),
+    (32, 64, 3, 3, 1, 2, 24, 40),     # cin < 64: partial channel group, zero-filled by TMA
+    (96, 128, 1, 1, 1, 2, 20, 20),
+    (48, 64, 1, 1, 1, 1, 33, 17),     # flat 1x1 with a ragged pixel count
 ]
 
 

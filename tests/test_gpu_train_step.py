@@ -101,5 +101,5 @@ def test_training_is_deterministic_in_shape_and_repeatable(state_dict):
     a = eng.forward_backward(*inp, update_bn=False).cpu().numpy()
     ga = eng.tp.grad.clone()
     b = eng.forward_backward(*inp, update_bn=False).cpu().numpy()
-    np.testing.assert_allclose(a, b, rtol=1e-5)
+    np.testing.assert_allclose(a, b, rtol=1e-4)  # statistics and loss sums use floating-point atomics: the summation order varies run to run
     assert float((eng.tp.grad - ga).norm() / ga.norm()) < 1e-3  # atomics reorder fp32 sums, nothing else may differ

@@ -49,7 +49,7 @@ SIGNATURES = {
     "yad_rowcol_gate": (i32, [TP, TP, TP, TP, i32, vp]),
     "yad_pool_upsample": (i32, [TP, i32, TP, i32, vp]),
     "yad_mlca_pool": (i32, [TP, vp, i32, i32, vp]),
-    "yad_mlca_att": (i32, [vp, vp, vp, i32, f32, i32, i32, i32, vp, vp]),
+    "yad_mlca_att": (i32, [vp, vp, vp, i32, f32, i32, i32, i32, vp, vp, vp]),
     "yad_mlca_apply": (i32, [TP, vp, i32, vp, i32, TP, i32, vp]),
     "yad_gate_mlp": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
     "yad_adt_apply": (i32, [TP, vp, vp, vp, vp, TP, i32, vp]),

@@ -445,36 +445,41 @@ __global__ void mlca_pool_kernel(yad_tensor x, float* __restrict__ local, int ls
 // G: the reference reshapes the global branch to a 3-D (c, b, 1) tensor before `adaptive_avg_pool2d(.., [ls, ls])` (block.py:1575-1579),
 // so the pool runs over the BATCH axis: G[i][c] = mean over images b in [floor(i*B/ls), ceil((i+1)*B/ls)) of sigmoid(conv1d_k(glob_b))[c],
 // shared by every image (for B == 1 this is the plain per-image broadcast).  Reproduced as is.
-__global__ void mlca_att_kernel(const float* __restrict__ local, const float* __restrict__ wg, const float* __restrict__ wl, int k, float lw,
+// pass 1 (one CTA per image): sg[b][ch] = sigmoid(conv1d_k(mean of the image's ls x ls bins))[ch]
+__global__ void mlca_glob_kernel(const float* __restrict__ local, const float* __restrict__ wg, int k, int c, int ls, float* __restrict__ sg) {
+  extern __shared__ float sm[];  // glob[c]
+  const int nb = ls * ls, b = blockIdx.x, len = nb * c, r = (k - 1) / 2;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s = 0.f;
+    for (int q = 0; q < nb; q++) s += local[(int64_t)b * len + q * c + ch];
+    sm[ch] = s / (float)nb;
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < k; j++) {
+      int q = ch + j - r;
+      if (q >= 0 && q < c) s = fmaf(wg[j], sm[q], s);
+    }
+    sg[(int64_t)b * c + ch] = sigmoidf_(s);
+  }
+}
+
+// pass 2 (one CTA per image): G from sg (batch-axis bins, in image order as the single-kernel version summed them), local branch, blend
+__global__ void mlca_att_kernel(const float* __restrict__ local, const float* __restrict__ sg, const float* __restrict__ wl, int k, float lw,
                                 int c, int ls, int batch, float* __restrict__ att) {
-  extern __shared__ float sm[];  // seq[nb*c], glob[c], G[ls*c]
+  extern __shared__ float sm[];  // seq[nb*c], G[ls*c]
   const int nb = ls * ls;
   float* seq = sm;
-  float* glob = sm + nb * c;
-  float* G = glob + c;
+  float* G = sm + nb * c;
   const int n = blockIdx.x, len = nb * c, r = (k - 1) / 2;
   for (int i = threadIdx.x; i < len; i += blockDim.x) seq[i] = local[(int64_t)n * len + i];
-  for (int i = threadIdx.x; i < ls * c; i += blockDim.x) G[i] = 0.f;
-  for (int b = 0; b < batch; b++) {
-    __syncthreads();
-    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-      float s = 0.f;
-      for (int q = 0; q < nb; q++) s += local[(int64_t)b * len + q * c + ch];
-      glob[ch] = s / (float)nb;
-    }
-    __syncthreads();
-    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-      float s = 0.f;
-      for (int j = 0; j < k; j++) {
-        int q = ch + j - r;
-        if (q >= 0 && q < c) s = fmaf(wg[j], glob[q], s);
-      }
-      const float sg = sigmoidf_(s);
-      for (int i = 0; i < ls; i++) {
-        const int b0 = bin_start(i, batch, ls), b1 = bin_end(i, batch, ls);
-        if (b >= b0 && b < b1) G[i * c + ch] += sg / (float)(b1 - b0);
-      }
-    }
+  for (int i = threadIdx.x; i < ls * c; i += blockDim.x) {
+    const int bi = i / c, ch = i - bi * c;
+    const int b0 = bin_start(bi, batch, ls), b1 = bin_end(bi, batch, ls);
+    float s = 0.f;
+    for (int b = b0; b < b1; b++) s += sg[(int64_t)b * c + ch] / (float)(b1 - b0);
+    G[i] = s;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < len; i += blockDim.x) {
@@ -935,12 +940,14 @@ int yad_mlca_pool(const yad_tensor* x, float* local, int local_size, int dtype, 
 }
 
 int yad_mlca_att(const float* local, const float* w_global, const float* w_local, int ksize, float local_weight, int n, int c,
-                 int local_size, float* att, void* stream) {
+                 int local_size, float* att, float* scratch, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int nb = local_size * local_size;
-  size_t smem = (size_t)(nb * c + c + local_size * c) * sizeof(float);
+  size_t smem = (size_t)(nb * c + local_size * c) * sizeof(float);
   YAD_CHECK(smem <= 48 * 1024, "mlca_att: %d channels need %zu B of shared memory", c, smem);
-  mlca_att_kernel<<<n, 256, smem, st>>>(local, w_global, w_local, ksize, local_weight, c, local_size, n, att);
+  YAD_CHECK(scratch != nullptr, "mlca_att: scratch (fp32 [n][c]) is required");
+  mlca_glob_kernel<<<n, 128, c * sizeof(float), st>>>(local, w_global, ksize, c, local_size, scratch);
+  mlca_att_kernel<<<n, 256, smem, st>>>(local, scratch, w_local, ksize, local_weight, c, local_size, n, att);
   YAD_LAUNCH_CHECK("mlca_att");
   return 0;
 }

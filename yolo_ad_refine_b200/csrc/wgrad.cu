@@ -299,11 +299,19 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(yad_tensor x, yad_ten
         for (int i = 0; i < 8; i++) acc[t][i] = fmaf(v[i], gg[i], acc[t][i]);
       }
     }
+  }
+  // pixel lanes of the CTA combine in shared memory, then one global atomic per (tap, channel) per CTA
+  extern __shared__ float dws[];  // [K*K][c]
+  for (int i = tid; i < K * K * c; i += blockDim.x) dws[i] = 0.f;
+  __syncthreads();
+  if (pl < lanes) {
 #pragma unroll
     for (int t = 0; t < K; t++)
 #pragma unroll
-      for (int i = 0; i < 8; i++) atomicAdd(&dw[(int64_t)(ky * K + t) * c + o + i], acc[t][i]);
+      for (int i = 0; i < 8; i++) atomicAdd(&dws[(ky * K + t) * c + o + i], acc[t][i]);
   }
+  __syncthreads();
+  for (int i = tid; i < K * K * c; i += blockDim.x) atomicAdd(&dw[i], dws[i]);
 }
 
 // ---- modulated deformable sampling (DCNv2, 3x3, stride 1, pad 1, one offset group) ---------------------------------------------------------
@@ -500,12 +508,14 @@ int yad_dwconv_wgrad(const yad_tensor* x, const yad_tensor* dy, int k, float* dw
   const int64_t npix = (int64_t)x->n * x->h * x->w;
   const int lanes = 256 / ((x->c / 8) * k);
   int64_t want = (npix + (int64_t)lanes * 16 - 1) / ((int64_t)lanes * 16);  // >= 16 pixels per thread before the final atomics
-  int grid = (int)(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
+  int grid = (int)(want < 1 ? 1 : (want > 148 * 2 ? 148 * 2 : want));
+  const size_t smem = (size_t)k * k * x->c * sizeof(float);
+  YAD_CHECK(smem <= 48 * 1024, "dwconv_wgrad: k = %d with %d channels needs %zu B of shared memory", k, x->c, smem);
   cudaStream_t st = (cudaStream_t)stream;
   if (k == 3) {
-    YAD_DISPATCH_DTYPE(dtype, dwconv_wgrad_kernel<T, 3><<<grid, 256, 0, st>>>(*x, *dy, dw);)
+    YAD_DISPATCH_DTYPE(dtype, dwconv_wgrad_kernel<T, 3><<<grid, 256, smem, st>>>(*x, *dy, dw);)
   } else {
-    YAD_DISPATCH_DTYPE(dtype, dwconv_wgrad_kernel<T, 7><<<grid, 256, 0, st>>>(*x, *dy, dw);)
+    YAD_DISPATCH_DTYPE(dtype, dwconv_wgrad_kernel<T, 7><<<grid, 256, smem, st>>>(*x, *dy, dw);)
   }
   YAD_LAUNCH_CHECK("dwconv_wgrad");
   return 0;

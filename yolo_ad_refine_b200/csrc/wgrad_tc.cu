@@ -1,6 +1,6 @@
 // tcgen05 / TMEM weight-gradient kernel of the training path (autograd of F.conv2d w.r.t. its weight).
 //
-//   dW[co][tap][ci] = sum over output pixels m of dy[m][co] * x[pix(m, tap)][ci]        (stride-1 convolutions, cin % 64 == 0)
+//   dW[co][tap][ci] = sum over output pixels m of dy[m][co] * x[pix(m, tap)][ci]        (stride 1 or 2; any cin >= 16, cout % 16 == 0, <= 256)
 //
 // As a GEMM the reduction axis is the PIXEL axis, which is the strided one in NHWC: both operands are "MN-major" for the tensor core
 // (channels contiguous, pixels strided).  tcgen05.mma takes MN-major operands straight from shared memory (instruction descriptor bits 15/16),
@@ -27,7 +27,8 @@ constexpr int WT_MAX_RG = 16;   // row groups (tap, 64-channel group) per CTA
 constexpr int WT_MAX_TAPS = 9;
 
 struct WtParams {
-  int n, h, w, cin, cout;       // stride-1 geometry: output grid == input grid
+  int n, h, w, cin, cout;       // (n, h, w) = OUTPUT pixel grid; input pixel = stride * output pixel + tap offset
+  int stride;
   int ntaps, G;                 // G = cin / 64
   int dy[WT_MAX_TAPS], dx[WT_MAX_TAPS];
   int bw, bh, kb;               // pixel patch of one K block: kb = bw * bh (multiple of 16, <= 128)
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(WT_THREADS) wgrad_tc_kernel(const __grid_const
         for (int g = 0; g < p.n_groups; g++) tma_load_4d(st + g * box_bytes, &tmDy, full_bar(s), g * 64, tx0, ty0, img);
         for (int j = 0; j < nrg; j++) {
           const int rg = rg0 + j, tap = rg / p.G, cg = rg - tap * p.G;
-          tma_load_4d(st + (p.n_groups + j) * box_bytes, &tmX, full_bar(s), cg * 64, tx0 + p.dx[tap], ty0 + p.dy[tap], img);
+          tma_load_4d(st + (p.n_groups + j) * box_bytes, &tmX, full_bar(s), cg * 64, p.stride * tx0 + p.dx[tap], p.stride * ty0 + p.dy[tap], img);
         }
       }
     }
@@ -195,11 +196,12 @@ __global__ void __launch_bounds__(WT_THREADS) wgrad_tc_kernel(const __grid_const
       const bool valid = j < nrg;
       const int rg = rg0 + (valid ? j : 0), tap = rg / p.G, cg = rg - tap * p.G;
       const int ci = cg * 64 + (row & 63);
+      const bool ok = valid && ci < p.cin;  // rows beyond cin hold the TMA zero fill of a partial 64-channel group
       float* dst = p.dw + (int64_t)tap * p.cin + ci;  // + co * ntaps * cin
       for (int c0 = 0; c0 < p.cout; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * p.cout + c0), v);
-        if (valid) {
+        if (ok) {
 #pragma unroll
           for (int i = 0; i < 16; i++) {
             const float f = __uint_as_float(v[i]);
@@ -232,14 +234,15 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// NHWC view (n, h, w, c; pixel stride ld) as a 4-D bf16 tensor map, box = 64 channels x bw x bh x 1, SWIZZLE_128B, zero fill out of bounds
-int make_nhwc_map(CUtensorMap* tm, const yad_tensor* t, int bw, int bh) {
+// NHWC view (n, h, w, c; pixel stride ld) as a 4-D bf16 tensor map, SWIZZLE_128B, zero fill out of bounds.  The box delivers 64 channels x bw x bh
+// pixels taken every `step`-th pixel in x and y (TMA traversal stride): a stride-2 convolution's input patch arrives already decimated.
+int make_nhwc_map(CUtensorMap* tm, const void* ptr, int64_t n, int64_t h, int64_t w, int c, int ld, int bw, int bh, int step) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return 1;
-  cuuint64_t dims[4] = {(cuuint64_t)t->c, (cuuint64_t)t->w, (cuuint64_t)t->h, (cuuint64_t)t->n};
-  cuuint64_t strides[3] = {(cuuint64_t)t->ld * 2, (cuuint64_t)t->w * t->ld * 2, (cuuint64_t)t->h * t->w * t->ld * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1}, es[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t->ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(bw * step), (cuuint32_t)(bh * step), 1}, es[4] = {1, (cuuint32_t)step, (cuuint32_t)step, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 1;
 }
@@ -254,7 +257,8 @@ void pick_patch_k(int h, int w, int kb_max, int* bw_out, int* bh_out) {
       const int area = bw * bh;
       if (area % 16) continue;
       const int tx = (w + bw - 1) / bw, ty = (h + bh - 1) / bh;
-      const double eff = (double)h * w / ((double)tx * ty * area);
+      // useful pixels per fetched pixel, discounted for small K blocks (per-stage TMA / barrier overhead)
+      const double eff = (double)h * w / ((double)tx * ty * area) * (area >= 64 ? 1.0 : 0.5 + area / 128.0);
       if (eff > best + 1e-9 || (eff > best - 1e-9 && area > best_area)) { best = eff; best_area = area; *bw_out = bw; *bh_out = bh; }
     }
   }
@@ -264,9 +268,23 @@ void pick_patch_k(int h, int w, int kb_max, int* bw_out, int* bh_out) {
 
 // Returns 0 when the launch was issued, 1 on error, -1 when the geometry is not covered by this kernel (the caller falls back to mma.sync).
 int yad_conv_wgrad_tc(const yad_tensor* x, const yad_tensor* dy, const yad_conv_desc* d, float* dw, void* stream) {
-  if (d->stride != 1 || d->kh * d->kw > WT_MAX_TAPS || d->pad_h != d->kh / 2 || d->pad_w != d->kw / 2) return -1;
-  if (x->c % 64 != 0 || dy->c % 16 != 0 || dy->c > 256 || dy->c < 16) return -1;
-  if (x->h != dy->h || x->w != dy->w || (int64_t)x->h * x->w < 16) return -1;
+  const int st = d->stride;
+  if ((st != 1 && st != 2) || d->kh * d->kw > WT_MAX_TAPS || d->pad_h != d->kh / 2 || d->pad_w != d->kw / 2) return -1;
+  if (dy->c > 256 && dy->c % 16 == 0) {  // more than one N tile: one launch per channel window of dy (a view) and the matching rows of dW
+    for (int c0 = 0; c0 < dy->c;) {
+      int cn = dy->c - c0;
+      if (cn > 256) cn = (cn >= 384) ? 192 : cn / 2 / 16 * 16;
+      yad_tensor part = *dy;
+      part.ptr = (void*)((bf16*)dy->ptr + c0);
+      part.c = cn;
+      const int r = yad_conv_wgrad_tc(x, &part, d, dw + (int64_t)c0 * d->kh * d->kw * x->c, stream);
+      if (r != 0) return c0 == 0 ? r : 1;
+      c0 += cn;
+    }
+    return 0;
+  }
+  if (x->c < 16 || x->c % 8 != 0 || dy->c % 16 != 0 || dy->c > 256 || dy->c < 16) return -1;
+  if (dy->h != (x->h + 2 * d->pad_h - d->kh) / st + 1 || dy->w != (x->w + 2 * d->pad_w - d->kw) / st + 1) return -1;
   if (((uintptr_t)x->ptr & 15) || ((uintptr_t)dy->ptr & 15)) return -1;
   static int sm100 = -1;
   if (sm100 < 0) {
@@ -277,10 +295,16 @@ int yad_conv_wgrad_tc(const yad_tensor* x, const yad_tensor* dy, const yad_conv_
   }
   if (!sm100 || !get_encode()) return -1;
   WtParams p;
-  p.n = x->n; p.h = x->h; p.w = x->w; p.cin = x->c; p.cout = dy->c;
+  p.cin = x->c; p.cout = dy->c; p.stride = st;
   p.ntaps = d->kh * d->kw;
-  p.G = x->c / 64;
+  p.G = (x->c + 63) / 64;
   for (int t = 0; t < p.ntaps; t++) { p.dy[t] = t / d->kw - d->pad_h; p.dx[t] = t % d->kw - d->pad_w; }
+  // 1x1: the pixel axis is one flat axis (no neighbourhood) -> (1, 1, n*h*w) grid, full 128-pixel K blocks whatever the map size
+  const bool flat = p.ntaps == 1 && st == 1;
+  int64_t gn = dy->n, gh = dy->h, gw = dy->w, xn = x->n, xh = x->h, xw = x->w;
+  if (flat) { gw = gn * gh * gw; gn = 1; gh = 1; xw = gw; xn = 1; xh = 1; }
+  if (gh * gw < 16 || gw > (1ll << 31) - 1) return -1;
+  p.n = (int)gn; p.h = (int)gh; p.w = (int)gw;
   p.RG = p.ntaps * p.G;
   p.n_groups = (p.cout + 63) / 64;
   // M-tiles per CTA: all accumulators (128 x cout fp32 each) stay in TMEM (512 columns)
@@ -298,7 +322,9 @@ int yad_conv_wgrad_tc(const yad_tensor* x, const yad_tensor* dy, const yad_conv_
   const int boxes = p.n_groups + p.rg_per_cta;
   int kb_max = 128;
   while (kb_max > 32 && 2 * boxes * kb_max * 128 > 200 * 1024) kb_max >>= 1;
-  pick_patch_k(p.h, p.w, kb_max, &p.bw, &p.bh);
+  if (flat) { p.bw = kb_max; p.bh = 1; }
+  else pick_patch_k(p.h, p.w < 128 ? p.w : 128, kb_max, &p.bw, &p.bh);
+  if (st == 2 && (p.bw > 128 || p.bh > 128)) return -1;  // TMA box dimension limit (256) with traversal stride 2
   p.kb = p.bw * p.bh;
   if (p.kb % 16 || 2 * boxes * p.kb * 128 > 200 * 1024) return -1;
   p.stages = (200 * 1024) / (boxes * p.kb * 128);
@@ -311,7 +337,8 @@ int yad_conv_wgrad_tc(const yad_tensor* x, const yad_tensor* dy, const yad_conv_
   if (p.splits < 1) p.splits = 1;
   p.dw = dw;
   CUtensorMap tmX, tmDy;
-  if (make_nhwc_map(&tmX, x, p.bw, p.bh) || make_nhwc_map(&tmDy, dy, p.bw, p.bh)) return -1;
+  if (make_nhwc_map(&tmX, x->ptr, xn, xh, xw, x->c, x->ld, p.bw, p.bh, st) || make_nhwc_map(&tmDy, dy->ptr, gn, gh, gw, dy->c, dy->ld, p.bw, p.bh, 1))
+    return -1;
   const size_t smem = (size_t)p.stages * boxes * p.kb * 128 + 8 * (2 * p.stages + 1) + 16 + 1024;
   static bool attr = false;
   if (!attr) {

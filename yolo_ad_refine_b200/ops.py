@@ -16,7 +16,7 @@ _DT = {torch.float32: F32, torch.bfloat16: BF16}
 # number of libyad kernel launches issued through this module (bench.py reports it as gpu_launches)
 LAUNCHES = 0
 # per-launch multiplicity of the multi-kernel entry points
-_MULTI = {"yad_nms": 6, "yad_tal_assign": 2, "yad_gn_stats": 1}
+_MULTI = {"yad_nms": 6, "yad_tal_assign": 2, "yad_gn_stats": 1, "yad_mlca_att": 2, "yad_norm_bwd": 2, "yad_mha_bwd": 2, "yad_mlca_bwd": 4}
 
 
 # when set to a dict, every entry point is bracketed by CUDA events on the launching stream: name -> [(start, end, meta), ...]
@@ -186,7 +186,8 @@ def mlca(x, y, w_global, w_local, ksize, local, att, local_size=5, local_weight=
     """y = x * MLCA_attention(x) (+ add); local/att: fp32 (n, ls*ls, c) scratch"""
     L = lib()
     _call("yad_mlca_pool", x.yt(), _p(local), local_size, dt(x.dtype), stream_ptr())
-    _call("yad_mlca_att", _p(local), _p(w_global), _p(w_local), ksize, local_weight, x.n, x.c, local_size, _p(att), stream_ptr())
+    scratch = torch.empty((x.n, x.c), dtype=torch.float32, device=att.device)
+    _call("yad_mlca_att", _p(local), _p(w_global), _p(w_local), ksize, local_weight, x.n, x.c, local_size, _p(att), _p(scratch), stream_ptr())
     adp, ald = _ap(add)
     _call("yad_mlca_apply", x.yt(), _p(att), local_size, adp, ald, y.yt(), dt(x.dtype), stream_ptr())
     return y
