@@ -123,12 +123,14 @@ def run_reference(args):
 def measure_training(args, world, rank, sd, dtype, W, barrier):
     """BASELINE.json configs[3]: one training step (train()-mode forward + TaskAlignedAssigner + v8DetectionLoss + full backward + gradient
     all-reduce over NCCL when N > 1 + clip / SGD / EMA), `train_batch` images per GPU (weak scaling).  Device-timed, max over ranks.  The e2e
-    figure adds, per step, the H2D copy of the pinned fp32 image batch + targets and the D2H read of the loss items."""
+    figure adds, per step, the H2D copy of the pinned uint8 image batch + targets and the D2H read of the loss items."""
     from yolo_ad_refine_b200 import ops, parallel, synth
     from yolo_ad_refine_b200.trainer import TrainEngine
     B = args.train_batch
     eng = TrainEngine(sd, dtype=dtype, world_size=world)
-    img_host = torch.from_numpy(synth.make_images(B, args.imgsz, args.imgsz, seed=200 + rank)).pin_memory()
+    # uint8 images, as the reference's dataloader delivers them (the /255 happens on the device: models/yolo/detect/train.py:56-59)
+    rs = np.random.RandomState(200 + rank)
+    img_host = torch.from_numpy(rs.randint(0, 256, (B, 3, args.imgsz, args.imgsz), dtype=np.uint8)).pin_memory()
     tg_host = [torch.from_numpy(a).pin_memory() for a in synth.make_targets(B, seed=300 + rank, max_per_img=8, empty_images=())]
     img = img_host.cuda()
     tg = [t.cuda() for t in tg_host]
@@ -163,7 +165,7 @@ def measure_training(args, world, rank, sd, dtype, W, barrier):
            "ms_per_step": ms, "batch_per_gpu": B, "global_batch": world * B, "steps": args.train_steps, "launches_per_step": launches,
            "scaling": "weak", "exchange": "none (1 GPU)" if world == 1 else f"NCCL all-reduce of the {eng.tp.total * 4 / 1e6:.1f} MB fp32 gradient arena",
            "e2e": {"value": world * B / (e2e_ms / 1000.0), "unit": "img/s", "ms_per_step": e2e_ms,
-                   "h2d_bytes_per_step": img_host.numel() * 4 + sum(t.numel() * 4 for t in tg_host), "d2h_bytes_per_step": 16},
+                   "h2d_bytes_per_step": img_host.numel() + sum(t.numel() * 4 for t in tg_host), "d2h_bytes_per_step": 16},
            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "loss": [float(v) for v in loss_host]}
     del eng
     torch.cuda.empty_cache()

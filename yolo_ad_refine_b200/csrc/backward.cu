@@ -1051,18 +1051,24 @@ __global__ void fusion_weights_kernel(const float* __restrict__ p, int k, float*
   }
 }
 
-// C[m][n] (+)= sum_k A[m][k] * B[n][k] (trans_a = 0)   or   sum_k A[k][m] * B[k][n] (trans_a = 1); tiny parameter-sized matrices only
-__global__ void small_gemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K, int trans_a,
-                                  int acc) {
+// C[m][n] (+)= sum_k A[m][k] * B[n][k] (trans_a = 0)   or   sum_k A[k][m] * B[k][n] (trans_a = 1); tiny parameter-sized matrices only.
+// trans_a = 0: thread per output, n fastest (B rows are short: K <= a few dozen).  trans_a = 1 (long K): grid (n, K chunks), threads over m so
+// that A[k][m] is read coalesced; partial sums meet in C through atomics (the caller passes acc = 1 semantics: C is accumulated).
+__global__ void small_gemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K, int acc) {
   const int64_t total = (int64_t)M * N;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
     const int m = (int)(it / N), n = (int)(it % N);
     float s = 0.f;
-    if (trans_a)
-      for (int k = 0; k < K; k++) s = fmaf(A[(int64_t)k * M + m], B[(int64_t)k * N + n], s);
-    else
-      for (int k = 0; k < K; k++) s = fmaf(A[(int64_t)m * K + k], B[(int64_t)n * K + k], s);
+    for (int k = 0; k < K; k++) s = fmaf(A[(int64_t)m * K + k], B[(int64_t)n * K + k], s);
     C[it] = acc ? C[it] + s : s;
+  }
+}
+__global__ void small_gemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K, int chunk) {
+  const int n = blockIdx.x, k0 = blockIdx.y * chunk, k1 = min(K, k0 + chunk);
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    float s = 0.f;
+    for (int k = k0; k < k1; k++) s = fmaf(A[(int64_t)k * M + m], B[(int64_t)k * N + n], s);
+    atomicAdd(&C[(int64_t)m * N + n], s);
   }
 }
 
@@ -1357,7 +1363,15 @@ int yad_fusion_weights(const float* p, int k, float* w, const float* dw, float* 
 }
 
 int yad_small_gemm(const float* a, const float* b, float* c, int m, int n, int k, int trans_a, int acc, void* stream) {
-  small_gemm_kernel<<<grid_for((int64_t)m * n), TPB, 0, (cudaStream_t)stream>>>(a, b, c, m, n, k, trans_a, acc);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (trans_a) {
+    if (!acc) cudaMemsetAsync(c, 0, sizeof(float) * (size_t)m * n, st);
+    const int chunk = 128;
+    dim3 grid(n, (k + chunk - 1) / chunk);
+    small_gemm_tn_kernel<<<grid, 128, 0, st>>>(a, b, c, m, n, k, chunk);
+  } else {
+    small_gemm_kernel<<<grid_for((int64_t)m * n), TPB, 0, st>>>(a, b, c, m, n, k, acc);
+  }
   YAD_LAUNCH_CHECK("small_gemm");
   return 0;
 }

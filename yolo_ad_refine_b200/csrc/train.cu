@@ -95,27 +95,37 @@ __device__ __forceinline__ S nwd_sim(S ax1, S ay1, S ax2, S ay2, float bx1, floa
 // =====================================================================================================================
 // loss_decode: (B,N,4*reg_max) logits -> boxes (grid units and pixels); class logits -> sigmoid
 // =====================================================================================================================
-__global__ void loss_decode_kernel(const float* __restrict__ distri, const float* __restrict__ logits, const float* __restrict__ anc,
-                                   const float* __restrict__ stride_t, int64_t total, int N, int nc, int reg_max, float* __restrict__ boxes,
-                                   float* __restrict__ boxes_px, float* __restrict__ sig) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int a = (int)(i % N);
-    const float* d = distri + i * 4 * reg_max;
-    float e[4];
-    for (int s = 0; s < 4; s++) {
-      float m = -INFINITY;
-      for (int k = 0; k < reg_max; k++) m = fmaxf(m, d[s * reg_max + k]);
-      float sum = 0.f, ex = 0.f;
-      for (int k = 0; k < reg_max; k++) { float p = expf(d[s * reg_max + k] - m); sum += p; ex = fmaf(p, (float)k, ex); }
-      e[s] = ex / sum;
+// 4 lanes per anchor (one per box side): each lane reads its 16 contiguous DFL logits as four 128-bit loads, so a warp sweeps 2 KB of
+// contiguous memory; the four expectations meet through shuffles and lane 0 of the quad writes both boxes.
+__global__ void loss_decode_kernel(const float* __restrict__ distri, const float* __restrict__ anc, const float* __restrict__ stride_t, int64_t total,
+                                   int N, int reg_max, float* __restrict__ boxes, float* __restrict__ boxes_px) {
+  const int64_t quads = total * 4;
+  for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x; q0 < quads; q0 += (int64_t)gridDim.x * blockDim.x) {  // block-uniform trip count
+    const int64_t q = q0 + threadIdx.x;
+    const bool ok = q < quads;
+    const int64_t i = ok ? q >> 2 : total - 1;
+    const int s = (int)(q & 3);
+    const float* d = distri + (i * 4 + s) * reg_max;
+    float m = -INFINITY;
+    for (int k = 0; k < reg_max; k++) m = fmaxf(m, d[k]);
+    float sum = 0.f, ex = 0.f;
+    for (int k = 0; k < reg_max; k++) { float p = expf(d[k] - m); sum += p; ex = fmaf(p, (float)k, ex); }
+    const float e = ex / sum;
+    const int lane = threadIdx.x & 31, base = lane & ~3;
+    const float e0 = __shfl_sync(0xffffffffu, e, base), e1 = __shfl_sync(0xffffffffu, e, base + 1);
+    const float e2 = __shfl_sync(0xffffffffu, e, base + 2), e3 = __shfl_sync(0xffffffffu, e, base + 3);
+    if (ok && s == 0) {
+      const int a = (int)(i % N);
+      const float ax = anc[2 * a], ay = anc[2 * a + 1], st = stride_t[a];
+      const float b0 = ax - e0, b1 = ay - e1, b2 = ax + e2, b3 = ay + e3;
+      reinterpret_cast<float4*>(boxes)[i] = make_float4(b0, b1, b2, b3);
+      reinterpret_cast<float4*>(boxes_px)[i] = make_float4(b0 * st, b1 * st, b2 * st, b3 * st);
     }
-    const float ax = anc[2 * a], ay = anc[2 * a + 1], st = stride_t[a];
-    const float b0 = ax - e[0], b1 = ay - e[1], b2 = ax + e[2], b3 = ay + e[3];
-    reinterpret_cast<float4*>(boxes)[i] = make_float4(b0, b1, b2, b3);
-    reinterpret_cast<float4*>(boxes_px)[i] = make_float4(b0 * st, b1 * st, b2 * st, b3 * st);
-    if (sig)
-      for (int c = 0; c < nc; c++) sig[i * nc + c] = sigmoidf_(logits[i * nc + c]);
   }
+}
+
+__global__ void loss_sigmoid_kernel(const float* __restrict__ logits, int64_t count, float* __restrict__ sig) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) sig[i] = sigmoidf_(logits[i]);
 }
 
 // =====================================================================================================================
@@ -466,8 +476,8 @@ int yad_loss_decode(const float* pred_distri, const float* pred_logits, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = (int64_t)batch * n_anchors;
   if (total == 0) return 0;
-  loss_decode_kernel<<<grid_for(total, 128), 128, 0, st>>>(pred_distri, pred_logits, anc, stride_t, total, n_anchors, nc, reg_max, pred_bboxes,
-                                                           pred_bboxes_px, pred_scores_sig);
+  loss_decode_kernel<<<grid_for(total * 4, 128), 128, 0, st>>>(pred_distri, anc, stride_t, total, n_anchors, reg_max, pred_bboxes, pred_bboxes_px);
+  if (pred_scores_sig) loss_sigmoid_kernel<<<grid_for(total * nc, 256), 256, 0, st>>>(pred_logits, total * nc, pred_scores_sig);
   YAD_LAUNCH_CHECK("loss_decode");
   return 0;
 }

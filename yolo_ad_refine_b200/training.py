@@ -20,6 +20,25 @@ from .weights import BN_EPS, GN_EPS, gn_groups
 BN_MOMENTUM = 0.03  # utils/torch_utils.py:426-436 initialize_weights
 
 
+def _subtract(r, m):
+    """rectangle r minus rectangle m; rectangles are (row0, row1, ch0, ch1) windows of one gradient buffer"""
+    r0, r1, c0, c1 = r
+    q0, q1, d0, d1 = m
+    if q0 >= r1 or q1 <= r0 or d0 >= c1 or d1 <= c0:
+        return [r]
+    out = []
+    if q0 > r0:
+        out.append((r0, q0, c0, c1))
+    if q1 < r1:
+        out.append((q1, r1, c0, c1))
+    a0, a1 = max(r0, q0), min(r1, q1)
+    if d0 > c0:
+        out.append((a0, a1, c0, d0))
+    if d1 < c1:
+        out.append((a0, a1, d1, c1))
+    return out
+
+
 class Graph:
     """one training step's tape + buffer helpers"""
 
@@ -44,27 +63,57 @@ class Graph:
 
     # ---- gradients ------------------------------------------------------------------------------------------------------
     def grad(self, a):
-        """gradient view of an activation view (zero-initialised on first use)"""
+        """gradient view of an activation view, for WRITING (uninitialised memory: pair it with mark(), which says whether to accumulate)"""
         st = a.buf.untyped_storage()
         key = st.data_ptr()
         if key not in self._g:
-            self._g[key] = (torch.zeros(st.nbytes() // a.buf.element_size(), dtype=a.dtype, device=a.device), a.buf)
+            self._g[key] = (torch.empty(st.nbytes() // a.buf.element_size(), dtype=a.dtype, device=a.device), a.buf)
         flat = self._g[key][0]
         off = a.buf.storage_offset()
         return Act(flat[off:off + a.buf.numel()].view(a.buf.shape), a.c0, a.c)
+
+    def gin(self, a):
+        """gradient view of an activation view, for READING: whatever part of the window no consumer has written is zero (an output nobody
+        used) and is zero-filled now."""
+        ga = self.grad(a)
+        key, win = self._window(a)
+        rem = self._uncovered(key, win)
+        if rem:
+            self._zero(key, a.ld, rem)
+            self._w.setdefault(key, []).extend(rem)
+        return ga
 
     def _window(self, a):
         ld = a.ld
         r0 = a.buf.storage_offset() // ld
         return a.buf.untyped_storage().data_ptr(), (r0, r0 + a.buf.numel() // ld, a.c0, a.c0 + a.c)
 
+    def _uncovered(self, key, win):
+        rem = [win]
+        for m in self._w.get(key, ()):
+            rem = [piece for r in rem for piece in _subtract(r, m)]
+            if not rem:
+                break
+        return rem
+
+    def _zero(self, key, ld, rects):
+        view = self._g[key][0].view(-1, ld)
+        for r0, r1, c0, c1 in rects:
+            view[r0:r1, c0:c1].zero_()
+
     def mark(self, a):
-        """-> 1 when (part of) the gradient window of activation `a` already holds data (accumulate), else 0 (write); marks it written"""
-        key, (r0, r1, c0, c1) = self._window(a)
-        ws = self._w.setdefault(key, [])
-        hit = any(r0 < q1 and q0 < r1 and c0 < d1 and d0 < c1 for q0, q1, d0, d1 in ws)
-        ws.append((r0, r1, c0, c1))
-        return int(hit)
+        """Declare a write to the gradient window of activation `a`.  Returns 0 when nothing of the window holds data yet (the caller writes),
+        1 when it does (the caller accumulates); a partly written window has its unwritten remainder zero-filled first, so accumulating is
+        always safe.  Gradient buffers are never memset wholesale."""
+        key, win = self._window(a)
+        rem = self._uncovered(key, win)
+        self._w.setdefault(key, []).append(win)
+        if rem == [win]:
+            return 0
+        if rem:
+            self.grad(a)  # make sure the buffer exists
+            self._zero(key, a.ld, rem)
+        return 1
 
     def accumulate(self, a, src, alpha=1.0, alpha_dev=None):
         """grad(a) (+)= alpha * src"""
@@ -114,7 +163,7 @@ def conv(g, x, wkey, bkey=None, stride=1, mode=CONV_NORMAL, act=ACT_NONE, out=No
                impl=g.conv_impl, gn_stats=gn_stats, gn_groups=groups)
 
     def bwd():
-        dy = g.grad(y)
+        dy = g.gin(y)
         if add is not None:
             g.accumulate(add, dy)
         if act != ACT_NONE:
@@ -174,7 +223,7 @@ def norm_act(g, t, wkey, bkey, groups, eps, act, out=None, add=None, stats=None,
         ops.bn_running_update(stats, t.c, t.n * t.h * t.w, BN_MOMENTUM, tp.buf(bn + ".running_mean"), tp.buf(bn + ".running_var"))
 
     def bwd():
-        dy = g.grad(y)
+        dy = g.gin(y)
         if add is not None:
             g.accumulate(add, dy)
         dt = g.grad(t)
@@ -210,7 +259,7 @@ def dwconv(g, x, wkey, bkey, k, out=None, add=None):
     ops.dwconv(x, w, y, bias=b, k=k, add=add)
 
     def bwd():
-        dy = g.grad(y)
+        dy = g.gin(y)
         if add is not None:
             g.accumulate(add, dy)
         if gb is not None:
@@ -230,7 +279,7 @@ def mul_add(g, a, b, c3=None, out=None):
     ops.eltwise_dev(4, a, b, y, c3=c3)
 
     def bwd():
-        dy = g.grad(y)
+        dy = g.gin(y)
         if c3 is not None:
             g.accumulate(c3, dy)
         for u, v in ((a, b), (b, a)):
@@ -250,7 +299,7 @@ def scale_add(g, a, skey, c3=None, out=None, index=0):
     ops.eltwise_dev(5, a, None, y, c3=c3, pa=s)
 
     def bwd():
-        dy = g.grad(y)
+        dy = g.gin(y)
         if c3 is not None:
             g.accumulate(c3, dy)
         ops.dot(dy, a, gs)
@@ -262,7 +311,7 @@ def scale_add(g, a, skey, c3=None, out=None, index=0):
 
 def copy(g, a, out):
     ops.eltwise_dev(5, a, None, out)
-    g.tape.append(lambda: g.accumulate(a, g.grad(out)))
+    g.tape.append(lambda: g.accumulate(a, g.gin(out)))
     return out
 
 
@@ -278,7 +327,7 @@ def mlca(g, p, x, out, add=None):
     ops.mlca(x, out, wg, wl, k, local, att, 5, 0.5, add)
 
     def bwd():
-        dy = g.grad(out)
+        dy = g.gin(out)
         if add is not None:
             g.accumulate(add, dy)
         dx = g.grad(x)
@@ -337,7 +386,7 @@ def sppf(g, p, x):
         carry = None
         for i in (2, 1, 0):  # gradient of pool output i+1 -> pool input i
             nxt = g.f32(x.n, x.h, x.w, c, zero=True)
-            ops.maxpool5_bwd(y[i], g.grad(y[i + 1]), carry, nxt)
+            ops.maxpool5_bwd(y[i], g.gin(y[i + 1]), carry, nxt)
             carry = nxt
         ops.cast_acc(carry, g.grad(y[0]), g.mark(y[0]))
 
@@ -366,7 +415,7 @@ def ela_hsfpn(g, p, x, flag=True):
     def bwd_mean():
         dx = g.grad(x)
         acc = g.mark(x)
-        ops.bcast_add(dx, acc, row=g.grad(rows), s_row=1.0 / w, col=g.grad(cols), s_col=1.0 / h)
+        ops.bcast_add(dx, acc, row=g.gin(rows), s_row=1.0 / w, col=g.gin(cols), s_col=1.0 / h)
 
     g.tape.append(bwd_mean)
     if h == w:
@@ -377,7 +426,7 @@ def ela_hsfpn(g, p, x, flag=True):
     ops.rowcol_gate(x if flag else None, gh, gw, out)
 
     def bwd_gate():
-        dy = g.grad(out)
+        dy = g.gin(out)
         g.mark(gh), g.mark(gw)
         if flag:
             dx = g.grad(x)
@@ -400,7 +449,7 @@ def fusion_bifpn(g, p, xs):
     ops.eltwise_dev(0, xs[0], xs[1], y, pa=w[0:], pb=w[1:])
 
     def bwd():
-        dy = g.grad(y)
+        dy = g.gin(y)
         dw = g.f32(8, zero=True)
         for i in range(2):
             ops.dot(dy, xs[i], dw[i:])
@@ -449,7 +498,7 @@ def adaptive_dynamic_tanh(g, p, x):
         dx = g.grad(x)
         acc = g.mark(x)
         dimp, davg = g.f32(x.n, 3), g.f32(x.n, x.c)
-        ops.adt_bwd(x, g.grad(y), imp, tp.p(p + ".alphas").reshape(-1), tp.p(p + ".weight"), dx, acc, dimp, tp.g(p + ".alphas"), tp.g(p + ".weight"),
+        ops.adt_bwd(x, g.gin(y), imp, tp.p(p + ".alphas").reshape(-1), tp.p(p + ".weight"), dx, acc, dimp, tp.g(p + ".alphas"), tp.g(p + ".weight"),
                     tp.g(p + ".bias"))
         ops.gate_mlp_bwd(avg, w1, tp.p(b1), w2, tp.p(b2), 1, dimp, davg, tp.g(k1), tp.g(b1), tp.g(k2), tp.g(b2))
         ops.bcast_add(dx, 1, img=davg, s_img=1.0 / (x.h * x.w))
@@ -464,7 +513,7 @@ def pool_upsample(g, x, s):
     def bwd():
         dx = g.grad(x)
         acc = g.mark(x)
-        ops.pool_upsample_bwd(g.grad(y), s, g.f32(x.n, x.h // s, x.w // s, x.c), dx, acc)
+        ops.pool_upsample_bwd(g.gin(y), s, g.f32(x.n, x.h // s, x.w // s, x.c), dx, acc)
 
     g.tape.append(bwd)
     return y
@@ -485,7 +534,7 @@ def cross_scale_attention_tssa(g, p, x, identity, rw_key, heads=2, scales=(1, 2,
 
         def bwd(qkv=qkv, i=i):
             g.mark(qkv)
-            ops.tssa_bwd(qkv, temps[i], heads, g.grad(st), i * T, g.grad(qkv), dtemps[i])
+            ops.tssa_bwd(qkv, temps[i], heads, g.gin(st), i * T, g.grad(qkv), dtemps[i])
 
         g.tape.append(bwd)
     q = p + ".cross_scale_fusion"
@@ -494,14 +543,14 @@ def cross_scale_attention_tssa(g, p, x, identity, rw_key, heads=2, scales=(1, 2,
 
     def bwd_mha():
         g.mark(qkv2)
-        ops.mha_bwd(qkv2, heads, ao, g.grad(ao), g.grad(qkv2), g.f32(n * heads, S * T, 2))
+        ops.mha_bwd(qkv2, heads, ao, g.gin(ao), g.grad(qkv2), g.f32(n * heads, S * T, 2))
 
     g.tape.append(bwd_mha)
     po = conv(g, ao, q + ".out_proj.weight", q + ".out_proj.bias")
     am = ops.group_mean(po, S, g.act(n, h, w, c))
 
     def bwd_mean():
-        ops.group_mean_bwd(g.grad(am), S, g.grad(po), g.mark(po))
+        ops.group_mean_bwd(g.gin(am), S, g.grad(po), g.mark(po))
 
     g.tape.append(bwd_mean)
     to = conv(g, am, p + ".to_out.0.weight", p + ".to_out.0.bias")
@@ -535,7 +584,7 @@ def edffn(g, p, x, residual, rw_key, out=None):
 
     def bwd_gate():
         g.mark(d)
-        ops.gelu_gate_bwd(d1, d2, g.grad(gt), g.grad(d1), g.grad(d2), 0)
+        ops.gelu_gate_bwd(d1, d2, g.gin(gt), g.grad(d1), g.grad(d2), 0)
 
     g.tape.append(bwd_gate)
     o = conv(g, gt, p + ".project_out.weight")
@@ -549,7 +598,7 @@ def edffn(g, p, x, residual, rw_key, out=None):
 
     def bwd_filter():
         dxf, dm = g.f32(n, h, w, c), g.f32(4096, c, zero=True)
-        ops.patch_filter_bwd(o, g.grad(f), m, 1.0, dxf, dm)
+        ops.patch_filter_bwd(o, g.gin(f), m, 1.0, dxf, dm)
         ops.cast_acc(dxf, g.grad(o), g.mark(o))
         ops.small_gemm(dm, basis, tp.g(p + ".fft").reshape(c, 40), c, 40, 4096, trans_a=True, acc=True)
 
@@ -603,7 +652,7 @@ def coord_att(g, p, x):
     ops.rowcol_mean(x, rows, cols)
 
     def bwd_mean():
-        ops.bcast_add(g.grad(x), 1, row=g.grad(rows), s_row=1.0 / w, col=g.grad(cols), s_col=1.0 / h)
+        ops.bcast_add(g.grad(x), g.mark(x), row=g.gin(rows), s_row=1.0 / w, col=g.gin(cols), s_col=1.0 / h)
 
     g.tape.append(bwd_mean)
     t = conv(g, means, p + ".conv1.weight", p + ".conv1.bias")
@@ -618,7 +667,7 @@ def coord_att(g, p, x):
         g.mark(gh), g.mark(gw)
         dx = g.grad(x)
         acc = g.mark(x)
-        ops.rowcol_gate_bwd(x, gh, gw, g.grad(y), dx, acc, g.grad(gh), g.grad(gw))
+        ops.rowcol_gate_bwd(x, gh, gw, g.gin(y), dx, acc, g.grad(gh), g.grad(gw))
 
     g.tape.append(bwd_gate)
     return y
@@ -638,7 +687,7 @@ def deform_conv_gn(g, p, x, om):
     ops.conv2d(col, W.w, t, impl=g.conv_impl, gn_stats=stats, gn_groups=16)
 
     def bwd():
-        dt = g.grad(t)
+        dt = g.gin(t)
         ops.conv_wgrad(col, dt, W.gw, impl=g.conv_impl)
         dcol = ops.conv2d(dt, Wd.w, g.act(n, h, w, 9 * c), impl=g.conv_impl)
         dxf = g.f32(n, h, w, c)
@@ -689,7 +738,7 @@ def ayhead_level(g, p, x, i):
     ops.eltwise_dev(2, cls_e, cp, z)
 
     def bwd_gate():
-        dz = g.grad(z)
+        dz = g.gin(z)
         dc = g.grad(cls_e)
         acc = g.mark(cls_e)
         ops.eltwise_dev(8 if acc else 2, dz, cp, dc, c3=dc if acc else None)
@@ -707,12 +756,14 @@ def ayhead_level(g, p, x, i):
 
 # ---- whole model ---------------------------------------------------------------------------------------------------------------
 def forward_model(g, img):
-    """train()-mode forward of z-yaml/yolo11-701-YOLO-AD-Refine.yaml (nn/tasks.py:141-168); img fp32 (n, 3, H, W) in [0, 1] on the device.
+    """train()-mode forward of z-yaml/yolo11-701-YOLO-AD-Refine.yaml (nn/tasks.py:141-168); img fp32 (n, 3, H, W) in [0, 1] or uint8 in [0, 255],
+    on the device.
     Returns the three raw head outputs (head.py:1178-1179) as NHWC views (n, h, w, 4*reg_max + nc)."""
     n, _, H, W = img.shape
     assert H % 32 == 0 and W % 32 == 0, "image size must be a multiple of the maximum stride 32"
     L = {}
-    x0 = ops.nchw_to_nhwc(img, g.act(n, H, W, 8))
+    # uint8 batches carry the trainer's device-side `.float() / 255` (models/yolo/detect/train.py:56-59 preprocess_batch) fused into the layout pass
+    x0 = ops.u8_to_nhwc(img, g.act(n, H, W, 8)) if img.dtype == torch.uint8 else ops.nchw_to_nhwc(img, g.act(n, H, W, 8))
     L[0] = conv_bn_act(g, "model.0", x0, 2, need_dx=False)
     L[1] = conv_bn_act(g, "model.1", L[0], 2)
     L[2] = c3k2(g, "model.2", L[1])
