@@ -42,8 +42,9 @@ def test_umma_gemm_selftest(m, n, k):
                                              (128, 512, 1, 1, 10), (64, 64, 3, 1, 80), (128, 128, 3, 1, 40), (64, 64, 3, 1, 13),
                                              (96, 128, 1, 1, 21), (128, 64, 3, 1, 20), (16, 32, 3, 2, 64), (64, 64, 3, 2, 32), (128, 256, 3, 2, 20),
                                              (32, 32, 3, 1, 40), (16, 8, 3, 1, 32), (8, 16, 3, 1, 32), (32, 64, 1, 1, 16), (16, 16, 1, 1, 24),
-                                             (128, 128, 3, 2, 18)])
-@pytest.mark.parametrize("impl", [2, 3])  # 2 = TMA-fed where eligible, 3 = thread-gathered operands
+                                             (128, 128, 3, 2, 18), (8, 8, 3, 1, 45), (32, 16, 3, 2, 50), (32, 32, 3, 2, 22)])
+@pytest.mark.parametrize("impl", [0, 2, 3])  # 0 = auto (single-pass mma.sync kernel for 3x3 with <= 32 channels, else as 2), 2 = tcgen05,
+# TMA-fed where eligible, 3 = tcgen05 with thread-gathered operands
 def test_conv_tc_bias_silu_add(cin, cout, k, s, hw, impl):
     g = torch.Generator().manual_seed(cin * 1000 + cout)
     x = q(torch.randn(2, cin, hw, hw, generator=g))

@@ -16,6 +16,7 @@ int yad_conv2d_simt(const yad_tensor* x, const void* w, const yad_conv_desc* d, 
                     void* stream);
 int yad_conv2d_tc(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream);
 int yad_conv2d_tc_supported(const yad_tensor* x, const yad_conv_desc* d, const yad_tensor* y);
+int yad_conv2d_small(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream);
 
 extern "C" {
 
@@ -33,6 +34,10 @@ int yad_conv2d(const yad_tensor* x, const void* w, const yad_conv_desc* d, const
                void* stream) {
   YAD_CHECK(x && w && d && e && y && x->ptr && y->ptr, "conv2d: null argument");
   int impl = d->impl;
+  if (impl == 0 && dtype == YAD_BF16) {  // HBM-bound 3x3 convolutions with <= 32 channels: single-pass mma.sync kernel (conv_small.cu)
+    const int r = yad_conv2d_small(x, w, d, e, y, stream);
+    if (r >= 0) return r;
+  }
   if (impl == 0) impl = (dtype == YAD_BF16 && yad_conv2d_tc_supported(x, d, y)) ? 2 : 1;
   if (impl == 2 || impl == 3) {
     YAD_CHECK(dtype == YAD_BF16, "conv2d: the tcgen05 path is bf16 only");

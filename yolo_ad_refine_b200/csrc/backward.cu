@@ -444,6 +444,31 @@ __global__ void rowcol_gate_bwd_g_kernel(yad_tensor x, bool has_x, yad_tensor gh
   __syncthreads();
   const int idx = blockIdx.x, count = is_col ? dy.h : dy.w;
   const int64_t items = (int64_t)count * oct;
+  if ((blockDim.x % oct) == 0) {  // thread -> fixed octet: register accumulation, one shared-memory atomic per channel per thread
+    const int o = (threadIdx.x % oct) * 8, step = blockDim.x / oct;
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = 0.f;
+    for (int j = threadIdx.x / oct; j < count; j += step) {
+      const int py = is_col ? j : idx, px = is_col ? idx : j;
+      float g[8], w[8];
+      load8(reinterpret_cast<const T*>(dy.ptr) + pix_off(dy, n, py, px) + o, g);
+      if (is_col)
+        load8(reinterpret_cast<const T*>(gh.ptr) + ((int64_t)n * dy.h + py) * gh.ld + o, w);
+      else
+        load8(reinterpret_cast<const T*>(gw.ptr) + ((int64_t)n * dy.w + px) * gw.ld + o, w);
+      if (has_x) {
+        float v[8];
+        load8(reinterpret_cast<const T*>(x.ptr) + pix_off(x, n, py, px) + o, v);
+#pragma unroll
+        for (int i = 0; i < 8; i++) g[i] *= v[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = fmaf(g[i], w[i], s[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) atomicAdd(&sm[o + i], s[i]);
+  } else
   for (int64_t it = threadIdx.x; it < items; it += blockDim.x) {
     const int j = (int)(it / oct), o = (int)(it % oct) * 8;
     const int py = is_col ? j : idx, px = is_col ? idx : j;
@@ -1144,7 +1169,9 @@ int yad_colsum(const yad_tensor* a, const void* b, int b_ld, float* out, int dty
   const int64_t npix = (int64_t)a->n * a->h * a->w;
   int blocks = (int)((npix * (a->c / 8) + TPB * 8 - 1) / (TPB * 8));
   blocks = blocks < 1 ? 1 : (blocks > 592 ? 592 : blocks);
-  YAD_DISPATCH_DTYPE(dtype, colsum_kernel<T><<<blocks, TPB, a->c * sizeof(float), (cudaStream_t)stream>>>(*a, (const T*)b, b_ld, out);)
+  const int oct = a->c / 8;
+  const int tpb = oct <= TPB ? oct * (TPB / oct) : TPB;  // a multiple of the octet count: every thread keeps one octet in registers
+  YAD_DISPATCH_DTYPE(dtype, colsum_kernel<T><<<blocks, tpb, a->c * sizeof(float), (cudaStream_t)stream>>>(*a, (const T*)b, b_ld, out);)
   YAD_LAUNCH_CHECK("colsum");
   return 0;
 }
