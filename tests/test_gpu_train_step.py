@@ -103,3 +103,18 @@ def test_training_is_deterministic_in_shape_and_repeatable(state_dict):
     b = eng.forward_backward(*inp, update_bn=False).cpu().numpy()
     np.testing.assert_allclose(a, b, rtol=1e-4)  # statistics and loss sums use floating-point atomics: the summation order varies run to run
     assert float((eng.tp.grad - ga).norm() / ga.norm()) < 1e-3  # atomics reorder fp32 sums, nothing else may differ
+
+
+def test_uint8_images_match_float_images(state_dict):
+    """uint8 batches (what the reference's dataloader delivers; /255 on the device, models/yolo/detect/train.py:56-59) give the step of the
+    equivalent float batch"""
+    rs = np.random.RandomState(3)
+    u8 = torch.from_numpy(rs.randint(0, 256, (2, 3, 160, 160), dtype=np.uint8)).cuda()
+    from oracle import synth
+    bi, cl, bb = [torch.from_numpy(a) for a in synth.make_targets(2, seed=6, max_per_img=5, empty_images=())]
+    eng = TrainEngine(state_dict, dtype=torch.float32, conv_impl=1)
+    a = eng.forward_backward(u8, bi, cl, bb, update_bn=False).cpu().numpy()
+    ga = eng.tp.grad.clone()
+    b = eng.forward_backward(u8.float() / 255.0, bi, cl, bb, update_bn=False).cpu().numpy()
+    np.testing.assert_allclose(a, b, rtol=1e-4)
+    assert float((eng.tp.grad - ga).norm() / ga.norm()) < 1e-3
