@@ -205,3 +205,37 @@ def test_mha_backward(dtype, T):
     for i, name in enumerate("qkv"):
         e = rel_err(got[..., i * c:(i + 1) * c], ref[..., i * c:(i + 1) * c])
         assert e < (2e-3 if dtype == torch.float32 else 3e-2), (name, e)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("hw", [(12, 20), (8, 8)])
+def test_deform_col_forward_backward(dtype, hw):
+    """yad_deform_col / yad_deform_col_bwd (DCNv2 sampling as a column tensor) against autograd of the oracle's modulated deformable conv
+    (oracle.model.deform_conv3x3, pinned to torchvision.ops.deform_conv2d): output, d(input), d(offsets), d(mask logits)"""
+    from oracle.model import deform_conv3x3
+    h, w = hw
+    rs = np.random.RandomState(h * w)
+    n, c, co = 2, 64, 16
+    x = torch.from_numpy(rs.standard_normal((n, c, h, w)).astype(np.float32)).to(dtype).float()
+    om = torch.from_numpy(rs.standard_normal((n, 27, h, w)).astype(np.float32) * 1.5).to(dtype).float()
+    wt = torch.from_numpy(rs.standard_normal((co, c, 3, 3)).astype(np.float32) * 0.1)
+    dy = torch.from_numpy(rs.standard_normal((n, co, h, w)).astype(np.float32))
+    xr, omr = x.clone().requires_grad_(True), om.clone().requires_grad_(True)
+    y_ref = deform_conv3x3(xr, omr[:, :18], omr[:, 18:].sigmoid(), wt)
+    y_ref.backward(dy)
+    xa, oma = Act.from_nchw(x.to(DEV), dtype), Act.from_nchw(om.to(DEV), dtype)  # 27 -> 32 channels
+    col = ops.deform_col(xa, oma, Act.empty(n, h, w, 9 * c, dtype, DEV))
+    colt = col.torch().float().cpu().view(n, h, w, 9, c)
+    y = torch.einsum("nhwtc,otc->nohw", colt, wt.permute(0, 2, 3, 1).reshape(co, 9, c))
+    tol = 1e-3 if dtype == torch.float32 else 2e-2
+    assert rel_err(y.numpy(), y_ref.detach().numpy()) < tol
+    dcol = torch.einsum("nohw,otc->nhwtc", dy, wt.permute(0, 2, 3, 1).reshape(co, 9, c)).reshape(n, h, w, 9 * c)
+    dcol_a = Act(dcol.to(DEV).to(dtype).contiguous())
+    dxf = torch.empty((n, h, w, c), dtype=torch.float32, device=DEV)
+    dom = Act.empty(n, h, w, 32, dtype, DEV)
+    ops.deform_col_bwd(xa, oma, dcol_a, dxf, dom)
+    tolb = 2e-3 if dtype == torch.float32 else 4e-2
+    assert rel_err(dxf.permute(0, 3, 1, 2).cpu().numpy(), xr.grad.numpy()) < tolb
+    got = dom.nchw().float().cpu().numpy()
+    assert rel_err(got[:, :27], omr.grad.numpy()) < tolb
+    assert float(np.abs(got[:, 27:]).max()) == 0.0

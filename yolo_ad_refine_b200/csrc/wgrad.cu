@@ -334,16 +334,29 @@ __device__ __forceinline__ Sample dcn_sample(const T* __restrict__ om, int tap, 
   return s;
 }
 
-// col[n, y, x, tap*C + c] = mask * bilinear(x)   (same arithmetic as the deformable mode of yad_conv2d)
+// pixel q of the tile-major order (8 x 8 tiles, so that the gathers of a CTA share their neighbourhood in L1) -> (n, oy, ox); false = padding
+__device__ __forceinline__ bool tile_pixel(uint32_t q, int h, int w, int tiles_x, int tiles_per_img, int* n, int* oy, int* ox) {
+  const uint32_t tile = q >> 6, r = q & 63;
+  const uint32_t img = tile / (uint32_t)tiles_per_img, t = tile - img * (uint32_t)tiles_per_img;
+  const uint32_t ty = t / (uint32_t)tiles_x, tx = t - ty * (uint32_t)tiles_x;
+  *n = (int)img;
+  *oy = (int)(ty * 8 + (r >> 3));
+  *ox = (int)(tx * 8 + (r & 7));
+  return *oy < h && *ox < w;
+}
+
+// col[n, y, x, tap*C + c] = mask * bilinear(x)   (same arithmetic as the deformable mode of yad_conv2d).
+// thread = (octet, tap, pixel lane): the block strides over pixels in tile-major order; all index arithmetic is 32-bit.
 template <typename T>
-__global__ void deform_col_kernel(yad_tensor x, const T* __restrict__ om, int om_ld, yad_tensor col) {
-  const int C = x.c, oct = C >> 3;
-  const int64_t total = (int64_t)x.n * x.h * x.w * 9 * oct;
-  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
-    const int o = (int)(it % oct) * 8;
-    const int tap = (int)((it / oct) % 9);
-    const int64_t p = it / ((int64_t)oct * 9);
-    const int ox = (int)(p % x.w), oy = (int)((p / x.w) % x.h), n = (int)(p / ((int64_t)x.w * x.h));
+__global__ void deform_col_kernel(yad_tensor x, const T* __restrict__ om, int om_ld, yad_tensor col, int tiles_x, int tiles_per_img, uint32_t npix_t) {
+  const int C = x.c, oct = C >> 3, per_pix = 9 * oct;
+  const int lanes = blockDim.x / per_pix;
+  const int o = (threadIdx.x % oct) * 8, tap = (threadIdx.x / oct) % 9, pl = threadIdx.x / per_pix;
+  if (pl >= lanes) return;
+  for (uint32_t q = blockIdx.x * lanes + pl; q < npix_t; q += gridDim.x * lanes) {
+    int n, oy, ox;
+    if (!tile_pixel(q, x.h, x.w, tiles_x, tiles_per_img, &n, &oy, &ox)) continue;
+    const int64_t p = ((int64_t)n * x.h + oy) * x.w + ox;
     const Sample s = dcn_sample(om + p * om_ld, tap, oy, ox, x.h, x.w);
     float v[8];
 #pragma unroll
@@ -524,8 +537,14 @@ int yad_dwconv_wgrad(const yad_tensor* x, const yad_tensor* dy, int k, float* dw
 int yad_deform_col(const yad_tensor* x, const yad_tensor* offmask, const yad_tensor* col, int dtype, void* stream) {
   YAD_CHECK(col->c == 9 * x->c && col->n == x->n && col->h == x->h && col->w == x->w && offmask->c >= 27 && x->c % 8 == 0,
             "deform_col: col must be (n,h,w,9*c) and offmask have >= 27 channels");
-  const int64_t total = (int64_t)x->n * x->h * x->w * 9 * (x->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, deform_col_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*x, (const T*)offmask->ptr, offmask->ld, *col);)
+  const int per_pix = 9 * (x->c / 8);
+  YAD_CHECK(per_pix <= 1024, "deform_col: %d channels are too many", x->c);
+  const int tiles_x = (x->w + 7) / 8, tiles_per_img = tiles_x * ((x->h + 7) / 8);
+  const int64_t npix_t = (int64_t)x->n * tiles_per_img * 64;
+  YAD_CHECK(npix_t * 9 < (1ll << 32), "deform_col: tensor too large for 32-bit indexing");
+  const int lanes = per_pix <= 288 ? 288 / per_pix : 1, tpb = lanes * per_pix;
+  YAD_DISPATCH_DTYPE(dtype, deform_col_kernel<T><<<grid_for(npix_t, lanes), tpb, 0, (cudaStream_t)stream>>>(*x, (const T*)offmask->ptr, offmask->ld, *col,
+                                                                                                          tiles_x, tiles_per_img, (uint32_t)npix_t);)
   YAD_LAUNCH_CHECK("deform_col");
   return 0;
 }
