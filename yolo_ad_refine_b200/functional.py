@@ -14,9 +14,10 @@ from .weights import GN_EPS, ConvW, edffn_spectral_matrix, fold_bn, gn_groups
 class Ctx:
     """Execution context: prepared weights + allocation helpers (torch caching allocator = plumbing)."""
 
-    def __init__(self, P, conv_impl=0, parallel_levels=True):
+    def __init__(self, P, conv_impl=0, parallel_levels=True, dcn_col=False):
         self.P, self.dtype, self.device, self.conv_impl = P, P.dtype, P.device, conv_impl
         self.parallel_levels = parallel_levels
+        self.dcn_col = dcn_col  # deformable conv as column tensor + 1x1 GEMM (False: the gathered-operand deformable mode of yad_conv2d)
         self._side = []
 
     def side_streams(self, n):
@@ -306,7 +307,16 @@ def ayhead_level(ctx, p, x, i):
     # DyDCNv2 head.py:751-782 (offsets / mask from `feat`, head.py:1155-1159) + GroupNorm(16) + CoordAtt
     om = conv(ctx, feat, P.conv(p + ".spatial_conv_offset.weight", p + ".spatial_conv_offset.bias"))
     dstats = ctx.f64(n, 16, 2)
-    ra = conv(ctx, reg2, P.conv(p + ".DyDCNV2.conv.weight"), mode=ops.CONV_DEFORM, offmask=om, gn_stats=dstats, gn_groups=16)
+    dw = P.conv(p + ".DyDCNV2.conv.weight")
+    if ctx.dcn_col:
+        # sampled, mask-weighted column tensor once (elementwise gather at full occupancy), then a plain 1x1 GEMM on the TMA-fed tcgen05 path:
+        # [co][9][ci] weights are [co][1][9*ci] for the tap-major column tensor.  Faster in isolation than the gathered-operand deformable mode
+        # (0.47 vs 0.82 ms at 80x80, batch 64) but not inside the step, where the pyramid levels overlap on parallel graph branches and the 9x
+        # wider temporary costs bandwidth (8.00 vs 7.95 ms): off by default, the training path uses it (its backward needs the column tensor).
+        col = ops.deform_col(reg2, om, ctx.act(n, h, w, 9 * fc))
+        ra = ops.conv2d(col, dw.w, ctx.act(n, h, w, dw.cout), impl=ctx.conv_impl, gn_stats=dstats, gn_groups=16)
+    else:
+        ra = conv(ctx, reg2, dw, mode=ops.CONV_DEFORM, offmask=om, gn_stats=dstats, gn_groups=16)
     ra = ops.group_norm(ra, ctx.act(n, h, w, fc), dstats, 16, P.f32(p + ".DyDCNV2.norm.weight"), P.f32(p + ".DyDCNV2.norm.bias"),
                         GN_EPS, ACT_NONE, stats_ready=True)
     reg_e = coord_att(ctx, p + ".coord_attention_reg", ra)
