@@ -118,3 +118,72 @@ def test_uint8_images_match_float_images(state_dict):
     b = eng.forward_backward(u8.float() / 255.0, bi, cl, bb, update_bn=False).cpu().numpy()
     np.testing.assert_allclose(a, b, rtol=1e-4)
     assert float((eng.tp.grad - ga).norm() / ga.norm()) < 1e-3
+
+
+def test_train_step_without_targets_matches_oracle(state_dict):
+    """a batch with no ground-truth boxes at all (utils/loss.py:392-408 -> empty targets, tal.py:62-70): only the classification term is alive"""
+    from oracle import model as om
+    img, _, _, _ = cases.train_step_inputs(**cases.TRAIN_STEP_CASES["b2_160"])
+    bi, cl, bb = torch.zeros(0), torch.zeros(0, 1), torch.zeros(0, 4)
+    loss_ref, items_ref, grads_ref, _, _ = om.train_step_grads(state_dict, torch.from_numpy(img), bi, cl, bb)
+    eng = TrainEngine(state_dict, dtype=torch.float32, conv_impl=1)
+    out4 = eng.forward_backward(torch.from_numpy(img).cuda(), bi, cl, bb).cpu().numpy()
+    assert np.isfinite(out4).all()
+    assert abs(out4[3] - float(loss_ref)) < 1e-4 * abs(float(loss_ref))
+    assert out4[0] == 0.0 and out4[2] == 0.0
+    for k in ("model.33.cv3.weight", "model.2.cv1.conv.weight", "model.10.m.0.attn.to_out.0.weight"):
+        gr, rf = eng.tp.g(k).cpu(), grads_ref[k]
+        assert float((gr - rf).norm() / rf.norm()) < 1e-2, k
+    assert float(eng.tp.g("model.33.cv2.weight").abs().max()) == 0.0  # the box branch receives no gradient
+
+
+def test_backward_is_the_derivative_of_the_forward(state_dict):
+    """Size-independent property (no oracle): for a fixed random cotangent R on the three raw head outputs, the whole-model backward must give
+    the derivative of S(w) = sum(outputs(w) * R): along a random parameter direction d, (S(w + e d) - S(w - e d)) / (2 e) == <grad, d>.
+    (The detection loss itself is not used here: its targets are assignment-dependent constants for autograd, so a finite difference of the
+    loss is not its gradient; the loss kernels have their own parity tests.)  fp32 build, 320 x 320, batch 4, batch-statistics BatchNorm."""
+    from oracle import synth
+    from yolo_ad_refine_b200 import training as T
+    img = torch.from_numpy(synth.make_images(4, 320, 320, seed=9)).cuda()
+    eng = TrainEngine(state_dict, dtype=torch.float32, conv_impl=1)
+    tp = eng.tp
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    cot = None
+
+    def run(backward):
+        nonlocal cot
+        tp.zero_grad()
+        tp.pack()
+        g = T.Graph(tp, 1, update_bn=False)
+        outs, _ = T.forward_model(g, img)
+        if cot is None:
+            cot = [torch.randn(o.torch().shape, generator=gen, device="cuda") for o in outs]
+        s = sum(float((o.torch().double() * r.double()).sum()) for o, r in zip(outs, cot))
+        if backward:
+            for o, r in zip(outs, cot):
+                g.mark(o)
+                g.grad(o).torch().copy_(r)
+            g.backward()
+            tp.unpack_grads()
+        return s
+
+    run(True)
+    grad = tp.grad.clone()
+    w0 = tp.flat.clone()
+    head = torch.zeros(tp.total, device="cuda")
+    for k in tp.keys:
+        if k.startswith("model.33."):
+            head[tp.off[k]:tp.off[k] + int(np.prod(tp.shape[k], dtype=np.int64))] = 1.0
+    # (direction mask, step, tolerance): the network is strongly non-linear in its early layers (33 layers, batch-statistics BatchNorm), so the
+    # central difference converges slowly there (measured: 23.4k, 39.5k, 44.3k, 47.7k for e = 3e-3 .. 1e-4 against <grad, d> = 47.4k); fp32
+    # rounding of S (and the run-to-run order of the statistics atomics) forbids smaller steps, hence the loose bound on the all-layer direction
+    for mask, eps, tol in ((torch.ones_like(head), 3e-4, 0.12), (head, 1e-3, 0.04)):
+        d = torch.randn(tp.total, generator=gen, device="cuda") * mask * (tp.group != 255) * tp.flat.abs().clamp_min(1e-3)  # relative perturbation
+        vals = []
+        for sgn in (1.0, -1.0):
+            tp.flat.copy_(w0 + sgn * eps * d)
+            vals.append(run(False))
+        tp.flat.copy_(w0)
+        fd = (vals[0] - vals[1]) / (2 * eps)
+        an = float((grad.double() * d.double()).sum())
+        assert abs(fd - an) < tol * abs(an), (fd, an)
