@@ -142,3 +142,17 @@ def test_bf16_engine_other_sizes_track_fp32(state_dict, size, batch):
     assert a.shape == b.shape == (batch, 84, (size // 8) ** 2 + (size // 16) ** 2 + (size // 32) ** 2)
     assert float((a[:, 4:] - b[:, 4:]).abs().mean()) < 0.01
     assert float((a[:, :4] - b[:, :4]).abs().mean() / a[:, :4].abs().mean()) < 0.03
+
+
+def test_1280_fp32_matches_oracle_and_nms_is_exact(state_dict):
+    """BASELINE.json configs[4] (inference at 1280 x 1280, batch-sharded): fp32 build against the CPU oracle on one image -- y (1, 84, 33600)
+    within 1e-3 relative (north_star), NMS rows bit-exact given the same y"""
+    from oracle import postprocess as op
+    img = torch.from_numpy(synth.make_images(1, 1280, 1280, seed=4))
+    y_ref, _ = om.forward(state_dict, img)
+    eng = RefineEngine(state_dict, batch=1, imgsz=1280, dtype=torch.float32, conv_impl=1, nms_args=dict(conf_thres=0.25, iou_thres=0.7, max_det=300))
+    y, _ = eng.forward(img)
+    assert tuple(y.shape) == (1, 84, 33600)
+    assert float((y.cpu() - y_ref).abs().max() / y_ref.abs().max()) < 1e-3
+    det = eng.detect(img)
+    np.testing.assert_array_equal(det[0].cpu().numpy(), op.non_max_suppression(y.cpu().numpy(), 0.25, 0.7, max_det=300)[0])
