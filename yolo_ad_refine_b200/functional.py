@@ -93,10 +93,24 @@ def c3k(ctx, p, x, out, attention=False):
     """nn/modules/block.py:256-270 C3.forward / :742-750 C3k / :1596-1600 C3k_MLCA (n = 2 bottlenecks)"""
     c_ = ctx.P.conv_bn(p + ".cv1").cout
     cat = ctx.act(x.n, x.h, x.w, 2 * c_)
+    done = None
+    if ctx.parallel_levels:  # cv2(x) is independent of the bottleneck chain: a parallel graph branch
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        br = ctx.side_streams(4)[3]
+        br.wait_event(fork)
+        with torch.cuda.stream(br):
+            conv_bn_act(ctx, p + ".cv2", x, out=cat.slice(c_, c_))
+            done = torch.cuda.Event()
+            done.record(br)
+    else:
+        conv_bn_act(ctx, p + ".cv2", x, out=cat.slice(c_, c_))
     a = conv_bn_act(ctx, p + ".cv1", x)
     a = bottleneck(ctx, p + ".m.0", a, attention=attention)
     bottleneck(ctx, p + ".m.1", a, out=cat.slice(0, c_), attention=attention)
-    conv_bn_act(ctx, p + ".cv2", x, out=cat.slice(c_, c_))
+    if done is not None:
+        torch.cuda.current_stream().wait_event(done)
     return conv_bn_act(ctx, p + ".cv3", cat, out=out)
 
 
@@ -204,10 +218,30 @@ def cross_scale_attention_tssa(ctx, p, x, identity, rw, heads=2, scales=(1, 2, 4
     T = h * w
     st = ctx.act(n, len(scales) * T, 1, c)
     temps = P.misc(p + ".temps", lambda: P.f32(p + ".temps").reshape(len(scales), heads).contiguous())
-    for i, s in enumerate(scales):
+    def scale_branch(i, s):
         xs = x if s == 1 else ops.pool_upsample(x, s, ctx.act(n, h, w, c))
         qkv = conv(ctx, xs, P.conv(f"{p}.qkv_projections.{i}.weight"))
         ops.tssa(qkv, temps[i], heads, st, i * T)
+
+    if ctx.parallel_levels and len(scales) > 1:  # the scales are independent (disjoint token ranges of `st`): parallel graph branches
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        side = ctx.side_streams(2 + len(scales) - 1)[2:]
+        joins = []
+        for i in range(1, len(scales)):
+            side[i - 1].wait_event(fork)
+            with torch.cuda.stream(side[i - 1]):
+                scale_branch(i, scales[i])
+                ev = torch.cuda.Event()
+                ev.record(side[i - 1])
+                joins.append(ev)
+        scale_branch(0, scales[0])
+        for ev in joins:
+            cur.wait_event(ev)
+    else:
+        for i, s in enumerate(scales):
+            scale_branch(i, s)
     q = p + ".cross_scale_fusion"
     qkv2 = conv(ctx, st, P.conv(q + ".in_proj_weight", q + ".in_proj_bias"))
     ao = ops.mha(qkv2, heads, ctx.act(n, len(scales) * T, 1, c))
@@ -302,8 +336,30 @@ def ayhead_level(ctx, p, x, i):
     conv(ctx, reg, P.conv(q + ".reg_to_cls.weight", q + ".reg_to_cls.bias"), out=crc.slice(fc, fc))
     cls2 = conv(ctx, crc, P.conv(q + ".cls_gate.0.weight", q + ".cls_gate.0.bias"), act=ACT_SIGMOID, mul=crc.slice(fc, fc), add=cls)
     reg2 = conv(ctx, crr, P.conv(q + ".reg_gate.0.weight", q + ".reg_gate.0.bias"), act=ACT_SIGMOID, mul=crr.slice(fc, fc), add=reg)
-    # ResidualBlockGN head.py:1031-1047
-    cls_e = conv_gn_act(ctx, p + ".rep_block_cls.conv2", conv_gn_act(ctx, p + ".rep_block_cls.conv1", cls2), add=cls2)
+    # the classification tail (ResidualBlockGN + cls_prob) and the regression tail (DyDCNv2 + CoordAtt) are independent: the former runs on a
+    # side stream of this level (a parallel branch of the captured graph)
+    branch = None
+    if ctx.parallel_levels:
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        branch = ctx.side_streams(7 + i)[4 + i]
+        branch.wait_event(fork)
+
+    def cls_tail():
+        # ResidualBlockGN head.py:1031-1047
+        ce = conv_gn_act(ctx, p + ".rep_block_cls.conv2", conv_gn_act(ctx, p + ".rep_block_cls.conv1", cls2), add=cls2)
+        # cls_prob head.py:1168-1169
+        c1 = conv(ctx, feat, P.conv(p + ".cls_prob_conv.0.weight", p + ".cls_prob_conv.0.bias"), act=ACT_RELU)
+        return ce, conv(ctx, c1, P.conv(p + ".cls_prob_conv.2.weight", p + ".cls_prob_conv.2.bias"), act=ACT_SIGMOID)  # channel 0 of 8
+
+    if branch is not None:
+        with torch.cuda.stream(branch):
+            cls_e, cp = cls_tail()
+            cls_done = torch.cuda.Event()
+            cls_done.record(branch)
+    else:
+        cls_e, cp = cls_tail()
     # DyDCNv2 head.py:751-782 (offsets / mask from `feat`, head.py:1155-1159) + GroupNorm(16) + CoordAtt
     om = conv(ctx, feat, P.conv(p + ".spatial_conv_offset.weight", p + ".spatial_conv_offset.bias"))
     dstats = ctx.f64(n, 16, 2)
@@ -320,9 +376,8 @@ def ayhead_level(ctx, p, x, i):
     ra = ops.group_norm(ra, ctx.act(n, h, w, fc), dstats, 16, P.f32(p + ".DyDCNV2.norm.weight"), P.f32(p + ".DyDCNV2.norm.bias"),
                         GN_EPS, ACT_NONE, stats_ready=True)
     reg_e = coord_att(ctx, p + ".coord_attention_reg", ra)
-    # cls_prob head.py:1168-1169
-    cp = conv(ctx, feat, P.conv(p + ".cls_prob_conv.0.weight", p + ".cls_prob_conv.0.bias"), act=ACT_RELU)
-    cp = conv(ctx, cp, P.conv(p + ".cls_prob_conv.2.weight", p + ".cls_prob_conv.2.bias"), act=ACT_SIGMOID)  # channel 0 of 8
+    if branch is not None:
+        torch.cuda.current_stream().wait_event(cls_done)
     cv2, cv3 = P.conv(p + ".cv2.weight", p + ".cv2.bias"), P.conv(p + ".cv3.weight", p + ".cv3.bias")
     out = ctx.act(n, h, w, cv2.cout + cv3.cout)
     conv(ctx, reg_e, cv2, out=out.slice(0, cv2.cout), alpha=P.scalar(f"{p}.scale.{i}.scale"))
@@ -400,8 +455,33 @@ def forward_model(ctx, img, decode=True, keep_layers=False):
     L[2] = c3k2(ctx, "model.2", L[1])
     L[3] = conv_bn_act(ctx, "model.3", L[2], 2)
     L[4] = c3k2(ctx, "model.4", L[3])
+    # the neck's lateral gates ELA_HSFPN(L4) / ELA_HSFPN(L6) (yaml layers 21 / 14) depend only on the backbone maps: they run on side streams
+    # (graph branches) next to the latency-bound 20x20 tail of the backbone and are joined where the neck consumes them
+    side = ctx.side_streams(2) if ctx.parallel_levels else None
+    joins = {}
+
+    def fork(idx, stream, fn):
+        if side is None:
+            L[idx] = fn()
+            return
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        stream.wait_event(ev)
+        with torch.cuda.stream(stream):
+            L[idx] = fn()
+            done = torch.cuda.Event()
+            done.record(stream)
+        joins[idx] = done
+
+    def join(idx):
+        if idx in joins:
+            torch.cuda.current_stream().wait_event(joins.pop(idx))
+
+    fork(21, side[0] if side else None, lambda: ela_hsfpn(ctx, "model.21", L[4], True))
     L[5] = conv_bn_act(ctx, "model.5", L[4], 2)
     L[6] = c3k2(ctx, "model.6", L[5], True, True)
+    fork(14, side[1] if side else None, lambda: ela_hsfpn(ctx, "model.14", L[6], True))
     L[7] = conv_bn_act(ctx, "model.7", L[6], 2)
     L[8] = c3k2(ctx, "model.8", L[7], True, True)
     L[9] = sppf(ctx, "model.9", L[8])
@@ -411,13 +491,13 @@ def forward_model(ctx, img, decode=True, keep_layers=False):
     L[11] = ela_hsfpn(ctx, "model.11", L[10], True)
     L[12] = conv(ctx, L[11], P.conv("model.12.weight", "model.12.bias"))
     L[13] = conv(ctx, L[12], P.conv("model.13.weight", "model.13.bias", stride=2, transposed=True), mode=ops.CONV_TRANSPOSED)
-    L[14] = ela_hsfpn(ctx, "model.14", L[6], True)
     L[16] = ela_hsfpn(ctx, "model.16", L[13], False)
+    join(14)
     L[18] = conv(ctx, L[14], P.conv("model.15.weight", "model.15.bias"), mul=L[16], add=L[13])  # Multiply (17) + Add (18)
     L[19] = c3k2(ctx, "model.19", L[18], False, True)
     L[20] = conv(ctx, L[19], P.conv("model.20.weight", "model.20.bias", stride=2, transposed=True), mode=ops.CONV_TRANSPOSED)
-    L[21] = ela_hsfpn(ctx, "model.21", L[4], True)
     L[23] = ela_hsfpn(ctx, "model.23", L[20], False)
+    join(21)
     L[25] = conv(ctx, L[21], P.conv("model.22.weight", "model.22.bias"), mul=L[23], add=L[20])  # Multiply (24) + Add (25)
     L[26] = c3k2(ctx, "model.26", L[25], False, True)
     L[27] = conv_bn_act(ctx, "model.27", L[26], 2)
