@@ -191,8 +191,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 __global__ void __launch_bounds__(128) mha_mma_kernel(const bf16* __restrict__ qkv, int64_t ld, int Tn, int c, int heads, bf16* __restrict__ out,
                                                       int64_t out_ld, float scale_log2e) {
-  __shared__ __align__(16) bf16 Ks[FA_K * FA_PITCH];
-  __shared__ __align__(16) bf16 Vs[FA_K * FA_PITCH];
+  __shared__ __align__(16) bf16 Ks[2][FA_K * FA_PITCH];  // double buffer: tile k + 1 streams in (cp.async) while tile k is consumed
+  __shared__ __align__(16) bf16 Vs[2][FA_K * FA_PITCH];
   const int n = blockIdx.y / heads, h = blockIdx.y % heads;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
   const bf16* base = qkv + (int64_t)n * Tn * ld + h * HD;
@@ -213,21 +213,26 @@ __global__ void __launch_bounds__(128) mha_mma_kernel(const bf16* __restrict__ q
 #pragma unroll
     for (int i = 0; i < 4; i++) o[j][i] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  const uint32_t ks_addr = (uint32_t)__cvta_generic_to_shared(Ks), vs_addr = (uint32_t)__cvta_generic_to_shared(Vs);
-
-  for (int k0 = 0; k0 < Tn; k0 += FA_K) {
-    __syncthreads();
-    for (int ch = tid; ch < FA_K * 8; ch += 128) {  // 64 rows x 8 chunks of 16 bytes, 8 lanes per row
+  const uint32_t ks_base = (uint32_t)__cvta_generic_to_shared(&Ks[0][0]), vs_base = (uint32_t)__cvta_generic_to_shared(&Vs[0][0]);
+  constexpr uint32_t BUF = FA_K * FA_PITCH * 2;
+  auto stage = [&](int k0, int buf) {  // 64 rows x 8 chunks of 16 bytes, 8 lanes per row; rows beyond Tn are zero-filled (src-size 0)
+    for (int ch = tid; ch < FA_K * 8; ch += 128) {
       const int row = ch >> 3, cc = (ch & 7) * 8;
-      uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
-      if (k0 + row < Tn) {
-        kv = *reinterpret_cast<const uint4*>(base + (int64_t)(k0 + row) * ld + c + cc);
-        vv = *reinterpret_cast<const uint4*>(base + (int64_t)(k0 + row) * ld + 2 * c + cc);
-      }
-      *reinterpret_cast<uint4*>(Ks + row * FA_PITCH + cc) = kv;
-      *reinterpret_cast<uint4*>(Vs + row * FA_PITCH + cc) = vv;
+      const bool ok = k0 + row < Tn;
+      const bf16* g = base + (int64_t)(ok ? k0 + row : Tn - 1) * ld + cc;
+      const uint32_t off = (uint32_t)((row * FA_PITCH + cc) * 2) + buf * BUF;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ks_base + off), "l"(g + c), "r"(ok ? 16 : 0) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vs_base + off), "l"(g + 2 * c), "r"(ok ? 16 : 0) : "memory");
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(0, 0);
+  for (int k0 = 0, it = 0; k0 < Tn; k0 += FA_K, it++) {
+    const int buf = it & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // tile `it` has landed; everybody is done with tile it - 1, whose buffer is refilled now
+    if (k0 + FA_K < Tn) stage(k0 + FA_K, buf ^ 1);
+    const uint32_t ks_addr = ks_base + buf * BUF, vs_addr = vs_base + buf * BUF;
     // S = Q K^T : 8 key tiles of 8
     float s[8][4];
 #pragma unroll

@@ -315,6 +315,19 @@ __device__ __forceinline__ void stage_tile(const bf16* src, int64_t ld, int row0
     *reinterpret_cast<uint4*>(dst + row * BA_PITCH + cc) = v;
   }
 }
+// asynchronous variant (cp.async, 16 B per request, zero fill beyond Tn): the next tile streams in while the tensor cores work on the current one
+__device__ __forceinline__ void stage_tile_async(const bf16* src, int64_t ld, int row0, int Tn, uint32_t dst_addr, int tid) {
+  for (int ch = tid; ch < BA_T * 8; ch += 128) {
+    const int row = ch >> 3, cc = (ch & 7) * 8;
+    const bool ok = row0 + row < Tn;
+    const bf16* g = src + (int64_t)(ok ? row0 + row : Tn - 1) * ld + cc;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_addr + (uint32_t)((row * BA_PITCH + cc) * 2)), "l"(g), "r"(ok ? 16 : 0)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // acc[j] (16 x 8 tile j of a 16 x 64 product) = A(16 x 64 frags) * tile^T, tile = [64 n][64 k] row-major in shared memory
 __device__ __forceinline__ void mm_nt(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile_addr, int lane) {
 #pragma unroll
@@ -346,8 +359,8 @@ __global__ void __launch_bounds__(128) mha_bwd_dq_mma_kernel(const bf16* __restr
                                                              const bf16* __restrict__ out, int64_t out_ld, const bf16* __restrict__ dout,
                                                              int64_t dout_ld, float scale, float scale_log2e, bf16* __restrict__ dqkv, int64_t dld,
                                                              float* __restrict__ lse_d) {
-  __shared__ __align__(16) bf16 Ks[BA_T * BA_PITCH];
-  __shared__ __align__(16) bf16 Vs[BA_T * BA_PITCH];
+  __shared__ __align__(16) bf16 Ks[2][BA_T * BA_PITCH];
+  __shared__ __align__(16) bf16 Vs[2][BA_T * BA_PITCH];
   const int n = blockIdx.y / heads, h = blockIdx.y % heads;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
   const bf16* base = qkv + (int64_t)n * Tn * ld + h * HD;
@@ -378,19 +391,29 @@ __global__ void __launch_bounds__(128) mha_bwd_dq_mma_kernel(const bf16* __restr
   }
   D0 += __shfl_xor_sync(0xffffffffu, D0, 1); D0 += __shfl_xor_sync(0xffffffffu, D0, 2);
   D1 += __shfl_xor_sync(0xffffffffu, D1, 1); D1 += __shfl_xor_sync(0xffffffffu, D1, 2);
-  const uint32_t ks_addr = (uint32_t)__cvta_generic_to_shared(Ks), vs_addr = (uint32_t)__cvta_generic_to_shared(Vs);
+  const uint32_t ks_base = (uint32_t)__cvta_generic_to_shared(&Ks[0][0]), vs_base = (uint32_t)__cvta_generic_to_shared(&Vs[0][0]);
+  constexpr uint32_t BUF = BA_T * BA_PITCH * 2;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f, lse0 = INFINITY, lse1 = INFINITY;
   float dq[8][4];
 #pragma unroll
   for (int j = 0; j < 8; j++)
 #pragma unroll
     for (int i = 0; i < 4; i++) dq[j][i] = 0.f;
-  for (int pass = 0; pass < 2; pass++) {
-    for (int k0 = 0; k0 < Tn; k0 += BA_T) {
-      __syncthreads();
-      stage_tile(base + c, ld, k0, Tn, Ks, tid);
-      if (pass) stage_tile(base + 2 * c, ld, k0, Tn, Vs, tid);
-      __syncthreads();
+  const int nt = (Tn + BA_T - 1) / BA_T;  // the two passes form one sequence of 2 * nt tiles through a double buffer
+  stage_tile_async(base + c, ld, 0, Tn, ks_base, tid);
+  cp_async_commit();
+  for (int it = 0; it < 2 * nt; it++) {
+    const int pass = it >= nt, k0 = (pass ? it - nt : it) * BA_T, buf = it & 1;
+    cp_async_wait_all();
+    __syncthreads();  // tile `it` has landed; everybody is done with tile it - 1, whose buffer is refilled below
+    if (it + 1 < 2 * nt) {
+      const int np = it + 1 >= nt, nk0 = (np ? it + 1 - nt : it + 1) * BA_T;
+      stage_tile_async(base + c, ld, nk0, Tn, ks_base + (buf ^ 1) * BUF, tid);
+      if (np) stage_tile_async(base + 2 * c, ld, nk0, Tn, vs_base + (buf ^ 1) * BUF, tid);
+      cp_async_commit();
+    }
+    const uint32_t ks_addr = ks_base + buf * BUF, vs_addr = vs_base + buf * BUF;
+    {
       float s[8][4];
       mm_nt(s, qa, ks_addr, lane);
       if (pass == 0) {
@@ -431,7 +454,7 @@ __global__ void __launch_bounds__(128) mha_bwd_dq_mma_kernel(const bf16* __restr
         mm_nn_acc(dq, dsa, ks_addr, lane);
       }
     }
-    if (pass == 0) {
+    if (it == nt - 1) {
       l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
       l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
       lse0 = r0 < Tn ? m0 * scale_log2e + log2f(l0) : INFINITY;
@@ -453,9 +476,9 @@ __global__ void __launch_bounds__(128) mha_bwd_dq_mma_kernel(const bf16* __restr
 __global__ void __launch_bounds__(128) mha_bwd_dkv_mma_kernel(const bf16* __restrict__ qkv, int64_t ld, int Tn, int c, int heads,
                                                               const bf16* __restrict__ dout, int64_t dout_ld, float scale, float scale_log2e,
                                                               const float* __restrict__ lse_d, bf16* __restrict__ dqkv, int64_t dld) {
-  __shared__ __align__(16) bf16 Qs[BA_T * BA_PITCH];
-  __shared__ __align__(16) bf16 Gs[BA_T * BA_PITCH];
-  __shared__ float Ls[BA_T], Ds[BA_T];
+  __shared__ __align__(16) bf16 Qs[2][BA_T * BA_PITCH];
+  __shared__ __align__(16) bf16 Gs[2][BA_T * BA_PITCH];
+  __shared__ float Ls[2][BA_T], Ds[2][BA_T];
   const int n = blockIdx.y / heads, h = blockIdx.y % heads;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
   const bf16* base = qkv + (int64_t)n * Tn * ld + h * HD;
@@ -469,17 +492,27 @@ __global__ void __launch_bounds__(128) mha_bwd_dkv_mma_kernel(const bf16* __rest
   for (int j = 0; j < 8; j++)
 #pragma unroll
     for (int i = 0; i < 4; i++) { dk[j][i] = 0.f; dv[j][i] = 0.f; }
-  const uint32_t qs_addr = (uint32_t)__cvta_generic_to_shared(Qs), gs_addr = (uint32_t)__cvta_generic_to_shared(Gs);
-  for (int q0 = 0; q0 < Tn; q0 += BA_T) {
-    __syncthreads();
-    stage_tile(base, ld, q0, Tn, Qs, tid);
-    stage_tile(gbase, dout_ld, q0, Tn, Gs, tid);
+  const uint32_t qs_base = (uint32_t)__cvta_generic_to_shared(&Qs[0][0]), gs_base = (uint32_t)__cvta_generic_to_shared(&Gs[0][0]);
+  constexpr uint32_t BUF = BA_T * BA_PITCH * 2;
+  auto stage = [&](int q0, int buf) {
+    stage_tile_async(base, ld, q0, Tn, qs_base + buf * BUF, tid);
+    stage_tile_async(gbase, dout_ld, q0, Tn, gs_base + buf * BUF, tid);
+    cp_async_commit();
     if (tid < BA_T) {
       const int t = q0 + tid;
-      Ls[tid] = t < Tn ? lse_d[((int64_t)blockIdx.y * Tn + t) * 2] : INFINITY;  // invalid query column -> P = 0
-      Ds[tid] = t < Tn ? lse_d[((int64_t)blockIdx.y * Tn + t) * 2 + 1] : 0.f;
+      Ls[buf][tid] = t < Tn ? lse_d[((int64_t)blockIdx.y * Tn + t) * 2] : INFINITY;  // invalid query column -> P = 0
+      Ds[buf][tid] = t < Tn ? lse_d[((int64_t)blockIdx.y * Tn + t) * 2 + 1] : 0.f;
     }
-    __syncthreads();
+  };
+  stage(0, 0);
+  for (int q0 = 0, it = 0; q0 < Tn; q0 += BA_T, it++) {
+    const int buf = it & 1;
+    cp_async_wait_all();
+    __syncthreads();  // tile `it` has landed; the other buffer is free
+    if (q0 + BA_T < Tn) stage(q0 + BA_T, buf ^ 1);
+    const uint32_t qs_addr = qs_base + buf * BUF, gs_addr = gs_base + buf * BUF;
+    const float* Lb = Ls[buf];
+    const float* Db = Ds[buf];
     float st[8][4], dpt[8][4];
     mm_nt(st, ka, qs_addr, lane);   // S^T = K Q^T
     mm_nt(dpt, va, gs_addr, lane);  // dP^T = V dO^T
@@ -487,7 +520,7 @@ __global__ void __launch_bounds__(128) mha_bwd_dkv_mma_kernel(const bf16* __rest
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       const int qc = j * 8 + 2 * q4;
-      const float L0 = Ls[qc], L1 = Ls[qc + 1], E0 = Ds[qc], E1 = Ds[qc + 1];
+      const float L0 = Lb[qc], L1 = Lb[qc + 1], E0 = Db[qc], E1 = Db[qc + 1];
       const float p0 = exp2f(fmaf(st[j][0], scale_log2e, -L0)), p1 = exp2f(fmaf(st[j][1], scale_log2e, -L1));
       const float p2 = exp2f(fmaf(st[j][2], scale_log2e, -L0)), p3 = exp2f(fmaf(st[j][3], scale_log2e, -L1));
       pta[j >> 1][(j & 1) * 2 + 0] = pack2(p0, p1);
