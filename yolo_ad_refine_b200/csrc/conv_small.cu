@@ -33,7 +33,7 @@ __device__ __forceinline__ void cs_ldsm2(uint32_t& r0, uint32_t& r1, uint32_t ad
 }
 
 template <int NT>  // n-tiles of 8 output channels (cout = 8 * NT)
-__global__ void __launch_bounds__(CS_THREADS, 2) conv_small_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+__global__ void __launch_bounds__(CS_THREADS) conv_small_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
                                                                     CsGeom g, const float* __restrict__ bias, int act, const bf16* __restrict__ add,
                                                                     int add_ld) {
   extern __shared__ __align__(16) uint8_t cs_smem[];
@@ -41,8 +41,9 @@ __global__ void __launch_bounds__(CS_THREADS, 2) conv_small_kernel(const bf16* _
   const int PH = (CS_TH - 1) * s + 3, PW = (CS_TW - 1) * s + 3;
   const int cpitch = cs_pitch(g.cin);
   const int K = 9 * g.cin, kpad = g.ksteps * 16, wpitch = kpad + 8;  // (kpad + 8) * 2 B = odd multiple of 16 B: conflict-free ldmatrix rows
-  bf16* patch = reinterpret_cast<bf16*>(cs_smem);
-  bf16* ws = patch + (size_t)PH * PW * cpitch;
+  bf16* patch = reinterpret_cast<bf16*>(cs_smem);              // two patch buffers: tile i + 1 streams in (cp.async) while tile i is computed
+  const uint32_t patch_elems = (uint32_t)PH * PW * cpitch;
+  bf16* ws = patch + 2 * (size_t)patch_elems;
   bf16* outs = ws + (size_t)NT * 8 * wpitch;  // [256 px][cout + 8]
   const int opitch = NT * 8 + 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -53,22 +54,63 @@ __global__ void __launch_bounds__(CS_THREADS, 2) conv_small_kernel(const bf16* _
     if (k8 < K) v = *reinterpret_cast<const uint4*>(w + (size_t)co * K + k8);
     *reinterpret_cast<uint4*>(ws + (size_t)co * wpitch + k8) = v;
   }
-  const uint32_t patch_s = (uint32_t)__cvta_generic_to_shared(patch), ws_s = (uint32_t)__cvta_generic_to_shared(ws);
+  const uint32_t patch_s0 = (uint32_t)__cvta_generic_to_shared(patch), ws_s = (uint32_t)__cvta_generic_to_shared(ws);
   const int coct = g.cin >> 3, kgroups = 9 * coct;  // number of 8-wide K groups that carry data
   const int g4 = lane >> 2, q4 = lane & 3;
-  for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+  // The chunk geometry of the staging loop does not depend on the tile: each thread keeps its (row, column, offsets) slots in registers, so
+  // that per tile a slot costs two adds, the bounds test and one cp.async (the kernel was issue-bound on index arithmetic before).
+  constexpr int MAXS = 9;  // 17 x 65 x 2 chunks / 256 threads
+  int sl_py[MAXS], sl_px[MAXS], sl_g[MAXS];
+  uint32_t sl_s[MAXS];
+  const int nchunks = PH * PW * coct;
+#pragma unroll
+  for (int j = 0; j < MAXS; j++) {
+    const int ch = tid + j * CS_THREADS;
+    const int oc = ch % coct, pp = ch / coct, px = pp % PW, py = pp / PW;
+    sl_py[j] = ch < nchunks ? py : -100000;  // fails every bounds test
+    sl_px[j] = px;
+    sl_g[j] = (py * g.wi + px) * g.x_ld + oc * 8;
+    sl_s[j] = (uint32_t)((pp * cpitch + oc * 8) * 2);
+  }
+  auto stage = [&](int tile, int buf) {  // haloed input patch of `tile` -> patch buffer `buf`, zero-filled outside the image (src-size 0)
+    const int tx = tile % g.tiles_x, ty = (tile / g.tiles_x) % g.tiles_y, img = tile / (g.tiles_x * g.tiles_y);
+    const int iy0 = ty * CS_TH * s - 1, ix0 = tx * CS_TW * s - 1;
+    const uint32_t dst0 = patch_s0 + (uint32_t)buf * patch_elems * 2u;
+    const bf16* xb = x + (((int64_t)img * g.hi + iy0) * g.wi + ix0) * g.x_ld;
+#pragma unroll
+    for (int j = 0; j < MAXS; j++) {
+      if (j * CS_THREADS < nchunks) {
+        const int iy = iy0 + sl_py[j], ix = ix0 + sl_px[j];
+        const bool ok = (unsigned)iy < (unsigned)g.hi && (unsigned)ix < (unsigned)g.wi;
+        const bf16* src = ok ? xb + sl_g[j] : x;
+        if (sl_py[j] > -100000)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + sl_s[j]), "l"(src), "r"(ok ? 16 : 0) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // ldmatrix.x4 row addresses of the A fragments: matrix m = lane >> 3 -> pixel half (m & 1), K group (m >> 1); row r = lane & 7.  The offset of
+  // K step ks (its (tap, 8-channel group) for this lane's K half) is tile-independent: one register per K step.
+  constexpr int MAXK = 18;  // 9 * 32 / 16
+  const int mrow = (lane & 7) + ((lane >> 3) & 1) * 8, mk = lane >> 4;
+  uint32_t koff[MAXK];
+#pragma unroll
+  for (int ks = 0; ks < MAXK; ks++) {
+    int kg = ks * 2 + mk;
+    if (kg >= kgroups) kg = kgroups - 1;  // K padding: the weight rows are zero there, any finite operand will do
+    const int tap = kg / coct, cg = kg - tap * coct, ky = tap / 3, kx = tap - ky * 3;
+    koff[ks] = (uint32_t)(((ky * PW + kx) * cpitch + cg * 8) * 2);
+  }
+  if ((int)blockIdx.x < g.total_tiles) stage(blockIdx.x, 0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, it++) {
     const int tx = tile % g.tiles_x, ty = (tile / g.tiles_x) % g.tiles_y, img = tile / (g.tiles_x * g.tiles_y);
     const int oy0 = ty * CS_TH, ox0 = tx * CS_TW;
-    const int iy0 = oy0 * s - 1, ix0 = ox0 * s - 1;
-    __syncthreads();  // previous tile's staging area drained
-    for (int ch = tid; ch < PH * PW * coct; ch += CS_THREADS) {
-      const int oc = ch % coct, pp = ch / coct, px = pp % PW, py = pp / PW;
-      const int iy = iy0 + py, ix = ix0 + px;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (iy >= 0 && iy < g.hi && ix >= 0 && ix < g.wi) v = *reinterpret_cast<const uint4*>(x + (((int64_t)img * g.hi + iy) * g.wi + ix) * g.x_ld + oc * 8);
-      *reinterpret_cast<uint4*>(patch + (size_t)pp * cpitch + oc * 8) = v;
-    }
-    __syncthreads();
+    const int buf = it & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // this tile's patch has landed; the previous tile (other patch buffer, output staging) is fully drained
+    if (tile + (int)gridDim.x < g.total_tiles) stage(tile + gridDim.x, buf ^ 1);
+    const uint32_t patch_s = patch_s0 + (uint32_t)buf * patch_elems * 2u;
     // each warp: two 16-pixel segments (tile row = warp, x halves 0 / 1)
 #pragma unroll
     for (int half = 0; half < 2; half++) {
@@ -79,14 +121,12 @@ __global__ void __launch_bounds__(CS_THREADS, 2) conv_small_kernel(const bf16* _
 #pragma unroll
         for (int i = 0; i < 4; i++) acc[j][i] = 0.f;
       if (oy0 + py < g.ho && ox0 + px0 < g.wo) {
-        // ldmatrix.x4 row addresses: matrix m = lane >> 3 -> pixel half (m & 1), K group (m >> 1); row r = lane & 7
-        const int mrow = (lane & 7) + ((lane >> 3) & 1) * 8, mk = lane >> 4;
-        for (int ks = 0; ks < g.ksteps; ks++) {
-          int kg = ks * 2 + mk;
-          if (kg >= kgroups) kg = kgroups - 1;  // K padding: the weight rows are zero there, any finite operand will do
-          const int tap = kg / coct, cg = kg - tap * coct, ky = tap / 3, kx = tap - ky * 3;
+        const uint32_t a_row = patch_s + (uint32_t)(((py * s * PW) + (px0 + mrow) * s) * cpitch * 2);
+#pragma unroll
+        for (int ks = 0; ks < MAXK; ks++) {
+          if (ks >= g.ksteps) break;
           uint32_t a[4];
-          cs_ldsm4(a, patch_s + (uint32_t)((((py * s + ky) * PW + (px0 + mrow) * s + kx) * cpitch + cg * 8) * 2));
+          cs_ldsm4(a, a_row + koff[ks]);
 #pragma unroll
           for (int j = 0; j < NT; j++) {
             uint32_t b0, b1;
@@ -108,9 +148,12 @@ __global__ void __launch_bounds__(CS_THREADS, 2) conv_small_kernel(const bf16* _
       }
     }
     __syncthreads();
-    // coalesced 128-bit stores (+ residual add, applied to the bf16-rounded conv output like the tcgen05 epilogue does)
-    for (int ch = tid; ch < CS_TH * CS_TW * NT; ch += CS_THREADS) {
-      const int oc = ch % NT, pp = ch / NT, px = pp % CS_TW, py = pp / CS_TW;
+    // coalesced 128-bit stores (+ residual add, applied to the bf16-rounded conv output like the tcgen05 epilogue does): slot j of a thread is
+    // chunk tid + 256 j = (pixel, 8-channel group); NT is a power of two, so the decomposition is shifts
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      const int ch = tid + j * CS_THREADS;
+      const int oc = ch & (NT - 1), pp = ch / NT, px = pp & (CS_TW - 1), py = pp / CS_TW;
       const int oy = oy0 + py, ox = ox0 + px;
       if (oy >= g.ho || ox >= g.wo) continue;
       const int64_t pix = ((int64_t)img * g.ho + oy) * g.wo + ox;
@@ -147,8 +190,8 @@ int yad_conv2d_small(const yad_tensor* x, const void* w, const yad_conv_desc* d,
   g.ksteps = (9 * g.cin + 15) / 16;
   const int s = d->stride, NT = y->c / 8;
   const int PH = (CS_TH - 1) * s + 3, PW = (CS_TW - 1) * s + 3;
-  const size_t smem = (size_t)PH * PW * cs_pitch(x->c) * 2 + (size_t)y->c * (g.ksteps * 16 + 8) * 2 + (size_t)CS_TH * CS_TW * (y->c + 8) * 2;
-  if (smem > 100 * 1024) return -1;
+  const size_t smem = 2 * (size_t)PH * PW * cs_pitch(x->c) * 2 + (size_t)y->c * (g.ksteps * 16 + 8) * 2 + (size_t)CS_TH * CS_TW * (y->c + 8) * 2;
+  if (smem > 160 * 1024) return -1;
   int grid = 148 * 2;
   if (grid > g.total_tiles) grid = g.total_tiles;
   cudaStream_t st = (cudaStream_t)stream;
@@ -159,7 +202,7 @@ int yad_conv2d_small(const yad_tensor* x, const void* w, const yad_conv_desc* d,
 #define CS_LAUNCH(N)                                                                                                        \
   {                                                                                                                         \
     static bool attr = false;                                                                                               \
-    if (!attr) { cudaFuncSetAttribute(conv_small_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
+    if (!attr) { cudaFuncSetAttribute(conv_small_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; } \
     conv_small_kernel<N><<<grid, CS_THREADS, smem, st>>>(xp, wp, yp, g, e->bias, e->act, addp, e->add_ld);                 \
   }
   if (NT == 1) CS_LAUNCH(1) else if (NT == 2) CS_LAUNCH(2) else CS_LAUNCH(4)

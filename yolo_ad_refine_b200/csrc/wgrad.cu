@@ -180,14 +180,16 @@ constexpr int WS_TH = 8, WS_TW = 32, WS_THREADS = 256;
 __host__ __device__ constexpr int ws_pitch(int c) { return ((c >> 3) & 1) ? c + 16 : c + 8; }  // odd number of 16-byte slots per row: conflict-free ldmatrix
 
 template <int MT>
-__global__ void __launch_bounds__(WS_THREADS, 2) conv_wgrad_small_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, WgGeom g,
+__global__ void __launch_bounds__(WS_THREADS) conv_wgrad_small_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, WgGeom g,
                                                                           float* __restrict__ dw, int tiles_x, int tiles_y, int total_tiles) {
   extern __shared__ __align__(16) uint8_t ws_smem[];
   const int s = g.stride;
   const int PH = (WS_TH - 1) * s + 3, PW = (WS_TW - 1) * s + 3;
   const int cpitch = ws_pitch(g.cin), dpitch = ws_pitch(MT * 16);
+  // two (patch, dy tile) buffer pairs: tile i + 1 streams in through cp.async while tile i feeds the tensor cores
+  const uint32_t patch_elems = (uint32_t)PH * PW * cpitch, dy_elems = (uint32_t)WS_TH * WS_TW * dpitch, pair_elems = patch_elems + dy_elems;
   bf16* patch = reinterpret_cast<bf16*>(ws_smem);
-  bf16* dys = patch + (size_t)PH * PW * cpitch;
+  bf16* dys = patch + patch_elems;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NW = g.cin >> 3, KW = 8 / NW;  // NW in {1, 2, 4}
   const int ng = warp % NW, kg = warp / NW;
@@ -198,30 +200,71 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_wgrad_small_kernel(const b
     for (int m = 0; m < MT; m++)
 #pragma unroll
       for (int i = 0; i < 4; i++) acc[t][m][i] = 0.f;
-  // the dy staging area is zeroed once: channel columns >= cout (padding up to MT*16) are never written afterwards
-  for (int i = tid; i < WS_TH * WS_TW * dpitch / 8; i += WS_THREADS) reinterpret_cast<uint4*>(dys)[i] = make_uint4(0u, 0u, 0u, 0u);
-  const uint32_t patch_s = (uint32_t)__cvta_generic_to_shared(patch), dys_s = (uint32_t)__cvta_generic_to_shared(dys);
+  // both dy staging areas are zeroed once: channel columns >= cout (padding up to MT*16) are never written afterwards
+  for (int b = 0; b < 2; b++)
+    for (int i = tid; i < WS_TH * WS_TW * dpitch / 8; i += WS_THREADS) reinterpret_cast<uint4*>(dys + (size_t)b * pair_elems)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  const uint32_t patch_s0 = (uint32_t)__cvta_generic_to_shared(patch), dys_s0 = (uint32_t)__cvta_generic_to_shared(dys);
   const int coct = g.cin >> 3, doct = g.cout >> 3;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  // tile-independent chunk geometry lives in registers (see conv_small.cu): per tile a slot costs two adds, the bounds test and one cp.async
+  constexpr int MAXS = 9, MAXD = 4;  // 17 x 65 x 2 patch chunks / 256 threads; 256 x 4 dy chunks / 256 threads
+  int sl_py[MAXS], sl_px[MAXS], sl_g[MAXS], dl_py[MAXD], dl_px[MAXD], dl_g[MAXD];
+  uint32_t sl_s[MAXS], dl_s[MAXD];
+  const int nchunks = PH * PW * coct, dchunks = WS_TH * WS_TW * doct;
+#pragma unroll
+  for (int j = 0; j < MAXS; j++) {
+    const int ch = tid + j * WS_THREADS;
+    const int oc = ch % coct, pp = ch / coct, px = pp % PW, py = pp / PW;
+    sl_py[j] = ch < nchunks ? py : -100000;  // fails every bounds test
+    sl_px[j] = px;
+    sl_g[j] = (py * g.wi + px) * g.x_ld + oc * 8;
+    sl_s[j] = (uint32_t)((pp * cpitch + oc * 8) * 2);
+  }
+#pragma unroll
+  for (int j = 0; j < MAXD; j++) {
+    const int ch = tid + j * WS_THREADS;
+    const int oc = ch % doct, pp = ch / doct, px = pp % WS_TW, py = pp / WS_TW;
+    dl_py[j] = ch < dchunks ? py : 100000;
+    dl_px[j] = px;
+    dl_g[j] = (py * g.wo + px) * g.dy_ld + oc * 8;
+    dl_s[j] = (uint32_t)((pp * dpitch + oc * 8) * 2);
+  }
+  auto stage = [&](int tile, int buf) {  // zero fill (src-size 0) for the conv padding and ragged tile edges
     const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, img = tile / (tiles_x * tiles_y);
     const int oy0 = ty * WS_TH, ox0 = tx * WS_TW;
     const int iy0 = oy0 * s - g.pad_h, ix0 = ox0 * s - g.pad_w;
-    __syncthreads();  // previous tile fully consumed
-    for (int ch = tid; ch < PH * PW * coct; ch += WS_THREADS) {
-      const int oc = ch % coct, pp = ch / coct, px = pp % PW, py = pp / PW;
-      const int iy = iy0 + py, ix = ix0 + px;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (iy >= 0 && iy < g.hi && ix >= 0 && ix < g.wi) v = *reinterpret_cast<const uint4*>(x + (((int64_t)img * g.hi + iy) * g.wi + ix) * g.x_ld + oc * 8);
-      *reinterpret_cast<uint4*>(patch + (size_t)pp * cpitch + oc * 8) = v;
+    const uint32_t pdst = patch_s0 + (uint32_t)buf * pair_elems * 2u, ddst = dys_s0 + (uint32_t)buf * pair_elems * 2u;
+    const bf16* xb = x + (((int64_t)img * g.hi + iy0) * g.wi + ix0) * g.x_ld;
+    const bf16* db = dy + (((int64_t)img * g.ho + oy0) * g.wo + ox0) * g.dy_ld;
+#pragma unroll
+    for (int j = 0; j < MAXS; j++) {
+      if (j * WS_THREADS < nchunks && sl_py[j] > -100000) {
+        const int iy = iy0 + sl_py[j], ix = ix0 + sl_px[j];
+        const bool ok = (unsigned)iy < (unsigned)g.hi && (unsigned)ix < (unsigned)g.wi;
+        const bf16* src = ok ? xb + sl_g[j] : x;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(pdst + sl_s[j]), "l"(src), "r"(ok ? 16 : 0) : "memory");
+      }
     }
-    for (int ch = tid; ch < WS_TH * WS_TW * doct; ch += WS_THREADS) {
-      const int oc = ch % doct, pp = ch / doct, px = pp % WS_TW, py = pp / WS_TW;
-      const int oy = oy0 + py, ox = ox0 + px;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (oy < g.ho && ox < g.wo) v = *reinterpret_cast<const uint4*>(dy + (((int64_t)img * g.ho + oy) * g.wo + ox) * g.dy_ld + oc * 8);
-      *reinterpret_cast<uint4*>(dys + (size_t)pp * dpitch + oc * 8) = v;
+#pragma unroll
+    for (int j = 0; j < MAXD; j++) {
+      if (j * WS_THREADS < dchunks && dl_py[j] < 100000) {
+        const bool ok = oy0 + dl_py[j] < g.ho && ox0 + dl_px[j] < g.wo;
+        const bf16* src = ok ? db + dl_g[j] : dy;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ddst + dl_s[j]), "l"(src), "r"(ok ? 16 : 0) : "memory");
+      }
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((int)blockIdx.x < total_tiles) stage(blockIdx.x, 0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y;
+    const int oy0 = ty * WS_TH, ox0 = tx * WS_TW;
+    const int buf = it & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // this tile has landed; everybody is done with the previous one (the other buffer pair)
+    if (tile + (int)gridDim.x < total_tiles) stage(tile + gridDim.x, buf ^ 1);
+    const uint32_t patch_s = patch_s0 + (uint32_t)buf * pair_elems * 2u, dys_s = dys_s0 + (uint32_t)buf * pair_elems * 2u;
     for (int kk = kg; kk < WS_TH * WS_TW / 16; kk += KW) {
       const int py = kk / (WS_TW / 16), px0 = (kk % (WS_TW / 16)) * 16;
       if (oy0 + py >= g.ho || ox0 + px0 >= g.wo) continue;  // warp-uniform: this k-step holds only zero dy
@@ -474,7 +517,7 @@ int yad_conv_wgrad(const yad_tensor* x, const yad_tensor* dy, const yad_conv_des
     const int tiles_x = cdiv(g.wo, WS_TW), tiles_y = cdiv(g.ho, WS_TH), total = g.n * tiles_x * tiles_y;
     const int MT = dy->c > 16 ? 2 : 1;
     const int PH = (WS_TH - 1) * s + 3, PW = (WS_TW - 1) * s + 3;
-    size_t smem = (size_t)PH * PW * ws_pitch(x->c) * 2 + (size_t)WS_TH * WS_TW * ws_pitch(MT * 16) * 2;
+    size_t smem = 2 * ((size_t)PH * PW * ws_pitch(x->c) * 2 + (size_t)WS_TH * WS_TW * ws_pitch(MT * 16) * 2);
     const size_t red = (size_t)MT * 16 * 9 * x->c * 4;
     if (smem < red) smem = red;
     int grid = 148 * 2;
@@ -482,11 +525,11 @@ int yad_conv_wgrad(const yad_tensor* x, const yad_tensor* dy, const yad_conv_des
     cudaStream_t st = (cudaStream_t)stream;
     if (MT == 2) {
       static bool attr2 = false;
-      if (!attr2) { cudaFuncSetAttribute(conv_wgrad_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr2 = true; }
+      if (!attr2) { cudaFuncSetAttribute(conv_wgrad_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr2 = true; }
       conv_wgrad_small_kernel<2><<<grid, WS_THREADS, smem, st>>>((const bf16*)x->ptr, (const bf16*)dy->ptr, g, dw, tiles_x, tiles_y, total);
     } else {
       static bool attr1 = false;
-      if (!attr1) { cudaFuncSetAttribute(conv_wgrad_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr1 = true; }
+      if (!attr1) { cudaFuncSetAttribute(conv_wgrad_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr1 = true; }
       conv_wgrad_small_kernel<1><<<grid, WS_THREADS, smem, st>>>((const bf16*)x->ptr, (const bf16*)dy->ptr, g, dw, tiles_x, tiles_y, total);
     }
     YAD_LAUNCH_CHECK("conv_wgrad (small-channel)");
