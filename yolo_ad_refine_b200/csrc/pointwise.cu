@@ -66,12 +66,32 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const IN* __restrict__ i
   const int ho = y.h, wo = y.w;
   const int b = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * 128;
   const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy - 1;
-  for (int i = threadIdx.x; i < cin * 3 * TW; i += blockDim.x) {
-    const int col = i % TW, r = (i / TW) % 3, ci = i / (3 * TW);
-    const int iy = iy0 + r, ix = ix0 + col;
-    float v = 0.f;
-    if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = (float)img[((int64_t)(b * cin + ci) * h + iy) * w + ix];
-    tile[i] = v;
+  if (sizeof(IN) == 1 && (w & 3) == 0 && ((uintptr_t)img & 3) == 0) {
+    // uint8 images: aligned 32-bit loads of 4 pixels (the tile starts at ix0 = 2 ox0 - 1; words start at 2 ox0 - 4), 66 words per row instead
+    // of 257 byte loads -- the kernel was issue-bound on this staging loop
+    constexpr int WPR = 66;
+    const int wx0 = 2 * ox0 - 4;
+    for (int i = threadIdx.x; i < cin * 3 * WPR; i += blockDim.x) {
+      const int wd = i % WPR, rr = i / WPR, r = rr % 3, ci = rr / 3;
+      const int iy = iy0 + r, ixw = wx0 + 4 * wd;
+      uint32_t word = 0u;
+      if (iy >= 0 && iy < h && ixw >= 0 && ixw < w)
+        word = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(img) + ((int64_t)(b * cin + ci) * h + iy) * w + ixw);
+      float* dst = tile + rr * TW;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int col = 4 * wd + k - 3;  // tile column of pixel ixw + k
+        if (col >= 0 && col < TW) dst[col] = (float)((word >> (8 * k)) & 0xffu);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < cin * 3 * TW; i += blockDim.x) {
+      const int col = i % TW, r = (i / TW) % 3, ci = i / (3 * TW);
+      const int iy = iy0 + r, ix = ix0 + col;
+      float v = 0.f;
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = (float)img[((int64_t)(b * cin + ci) * h + iy) * w + ix];
+      tile[i] = v;
+    }
   }
   __syncthreads();
   const int ox = ox0 + threadIdx.x;
