@@ -220,6 +220,7 @@ def main():
         s.record()
         for _ in range(k):
             fn()
+        eng.join()  # the NMS of the last batches runs on the engine's second stream: the closing event waits for it
         e.record()
         barrier()
         return parallel.max_over_ranks(s.elapsed_time(e), device="cuda")
@@ -254,6 +255,7 @@ def main():
            "h2d_bytes_per_step": host_u8.numel(), "d2h_bytes_per_step": det_host.numel() * 4 + cnt_host.numel() * 4}
 
     # ---- roofline of the dominant kernel: one instrumented eager step, CUDA events around every libyad entry point
+    torch.cuda.synchronize()
     ops.PROFILE = {}
     eng._run()
     torch.cuda.synchronize()
@@ -291,6 +293,7 @@ def main():
             "config": {"workload": f"YOLO-AD-Refine (yolo11-701 yaml, scale n) inference batch {args.batch}/GPU at {args.imgsz}x{args.imgsz}, "
                                    "forward + DFL decode + NMS(conf .25, iou .7, max_det 300), random-init synthetic weights",
                        "global_batch": world * args.batch, "parallelism": f"batch-sharded replicas x{world}, no collective",
+                       "pipeline": "forward + decode of batch i + 1 overlaps the NMS of batch i (two CUDA graphs, two streams, double-buffered predictions)",
                        "l2": "inputs + activations of one step (>1 GB) exceed the 126 MB L2; no explicit flush"},
             "e2e": e2e, "gpu_launches": eng.launches_per_step * args.steps, "launches_per_step": eng.launches_per_step,
             "clocks": clk.summary(), "roofline": roofline}

@@ -11,8 +11,12 @@ from .weights import prepare
 
 
 class RefineEngine:
+    """use_graph: the hot path is captured in CUDA graphs.  pipeline_nms: forward + decode and NMS are two graphs on two streams with
+    double-buffered predictions, so the NMS of batch i (one CTA per image: a low-occupancy tail) runs under the forward pass of batch i + 1.
+    step() then only ENQUEUES a batch; join() (called by forward / detect / detect_many) orders the current stream after its results."""
+
     def __init__(self, state_dict, batch, imgsz=640, dtype=torch.bfloat16, device="cuda", nc=80, reg_max=16, strides=(8, 16, 32),
-                 use_graph=True, conv_impl=0, nms_args=None, input_u8=False):
+                 use_graph=True, conv_impl=0, nms_args=None, input_u8=False, pipeline_nms=True):
         if not torch.cuda.is_available():
             raise RuntimeError("RefineEngine needs a CUDA device: the YOLO-AD-Refine hot path has no CPU fallback")
         ops.lib()  # fail loudly now if libyad.so is missing
@@ -27,6 +31,8 @@ class RefineEngine:
         self.launches_per_step = None
         self._out = None
         self.use_graph = use_graph
+        self.pipeline_nms = pipeline_nms and use_graph
+        self._i = 0
 
     # -- one eager pass of the hot path on the static input buffer
     def _run(self):
@@ -44,32 +50,77 @@ class RefineEngine:
                 self.launches_per_step = ops.LAUNCHES - before
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        if self.use_graph:
+        if self.pipeline_nms:
+            self._nms_stream = torch.cuda.Stream(device=self.device)
+            self._gf, self._gn, self._bufs = [], [], []
+            self._ev_f = [torch.cuda.Event() for _ in range(2)]
+            self._ev_n = [torch.cuda.Event() for _ in range(2)]
+            for b in range(2):  # two buffer sets: predictions of batch i are read by its NMS while batch i + 1 is being computed
+                gf = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gf):
+                    y, feats = Fn.forward_model(self.ctx, self.img)
+                gn = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gn):
+                    det, det_idx, count = nms_raw(y, **self.nms_args)
+                self._gf.append(gf)
+                self._gn.append(gn)
+                self._bufs.append((y, feats, det, det_idx, count))
+                self._ev_n[b].record(torch.cuda.current_stream())
+            self.graph = self._gf[0]
+            self._out = self._bufs[0]
+        elif self.use_graph:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._out = self._run()
             self.graph = g
 
     def step(self):
-        """forward + decode + NMS on the current contents of self.img; returns device tensors (static across calls when graphed)."""
+        """forward + decode + NMS on the current contents of self.img; returns device tensors (static across calls when graphed).
+        With pipeline_nms the batch is only enqueued: call join() before reading the results on the current stream."""
         if self._out is None:
             self._capture()
-        if self.graph is not None:
+        if self.pipeline_nms:
+            b = self._i & 1
+            self._i += 1
+            main = torch.cuda.current_stream()
+            main.wait_event(self._ev_n[b])       # the NMS that last read this buffer set (two batches ago) is done
+            self._gf[b].replay()
+            self._ev_f[b].record(main)
+            with torch.cuda.stream(self._nms_stream):
+                self._nms_stream.wait_event(self._ev_f[b])
+                self._gn[b].replay()
+                self._ev_n[b].record(self._nms_stream)
+            self._last = b
+            self._out = self._bufs[b]
+        elif self.graph is not None:
             self.graph.replay()
         else:
             self._out = self._run()
         return self._out
 
+    def last_prediction(self):
+        """y (B, 4 + nc, N) of the most recent step (valid after join()); the detections of that step are the NMS of exactly this tensor"""
+        return self._out[0]
+
+    def join(self):
+        """order the current stream after every batch enqueued so far (no-op without pipeline_nms)"""
+        if self.pipeline_nms and self._i:
+            main = torch.cuda.current_stream()
+            main.wait_event(self._ev_n[0])
+            main.wait_event(self._ev_n[1])
+
     def forward(self, img):
         """img: (B, 3, H, W) float tensor in [0,1] (host or device).  Returns (y (B,4+nc,N) fp32, [raw (B,144,H,W) views])."""
         self.img.copy_(img, non_blocking=True)
         y, feats, *_ = self.step()
+        self.join()
         return y, [f.nchw() for f in feats]
 
     def detect(self, img):
         """Full hot path.  Returns the reference's NMS output: list (B) of (k, 6) tensors [x1,y1,x2,y2,conf,cls]."""
         self.img.copy_(img, non_blocking=True)
         _, _, det, _, count = self.step()
+        self.join()
         counts = count.tolist()
         return [det[i, :k] for i, k in enumerate(counts)]
 
@@ -110,6 +161,7 @@ class RefineEngine:
             self.img.copy_(self._staging[i % 2], non_blocking=True)  # device-to-device into the graph's static input
             self._free[i % 2].record(main)
             _, _, det, _, count = self.step()
+            self.join()
             det_host.copy_(det, non_blocking=True)
             cnt_host.copy_(count, non_blocking=True)
             main.synchronize()  # the caller reads this batch's detections on the host
