@@ -151,6 +151,7 @@ class RefineEngine:
         it = iter(host_batches)
         nxt = next(it, None)
         i = 0
+        pending = None
         if nxt is not None:
             enqueue(0, nxt)
         while nxt is not None:
@@ -161,9 +162,29 @@ class RefineEngine:
             self.img.copy_(self._staging[i % 2], non_blocking=True)  # device-to-device into the graph's static input
             self._free[i % 2].record(main)
             _, _, det, _, count = self.step()
-            self.join()
+            if self.pipeline_nms:
+                # software pipeline: batch i is only enqueued here; the detections handed to the caller are those of batch i - 1, read back on
+                # the NMS stream while batch i computes (results arrive in order, one batch late; the last one is flushed after the loop)
+                if pending is not None:
+                    yield self._read_back(pending, det_host, cnt_host)
+                pending = self._last
+            else:
+                det_host.copy_(det, non_blocking=True)
+                cnt_host.copy_(count, non_blocking=True)
+                main.synchronize()  # the caller reads this batch's detections on the host
+                yield det_host, cnt_host
+            i += 1
+        if pending is not None:
+            yield self._read_back(pending, det_host, cnt_host)
+
+    def _read_back(self, b, det_host, cnt_host):
+        """D2H copy of buffer set b's detections on the NMS stream (ordered after its NMS), then a host wait on that stream only"""
+        _, _, det, _, count = self._bufs[b]
+        with torch.cuda.stream(self._nms_stream):
+            self._nms_stream.wait_event(self._ev_n[b])
             det_host.copy_(det, non_blocking=True)
             cnt_host.copy_(count, non_blocking=True)
-            main.synchronize()  # the caller reads this batch's detections on the host
-            yield det_host, cnt_host
-            i += 1
+            done = torch.cuda.Event()
+            done.record(self._nms_stream)
+        done.synchronize()
+        return det_host, cnt_host
