@@ -161,12 +161,29 @@ def measure_training(args, world, rank, sd, dtype, W, barrier):
         torch.cuda.current_stream().synchronize()
 
     e2e_ms = timed(e2e_step, args.train_steps)
+    # roofline of the training step's dominant kernels, measured live: one instrumented step, CUDA events around every libyad entry point
+    torch.cuda.synchronize()
+    ops.PROFILE = {}
+    eng.step(img, *tg)
+    torch.cuda.synchronize()
+    prof = {k: (sum(a.elapsed_time(b) for a, b, _ in v), sum(m["flops"] for _, _, m in v if m), len(v)) for k, v in ops.PROFILE.items()}
+    ops.PROFILE = None
+    tot_ms = sum(v[0] for v in prof.values())
+    pk = peaks()
+    roof = {}
+    for key, label in (("yad_conv_wgrad", "weight gradients: wgrad_tc_kernel (tcgen05 / TMEM, TMA-fed MN-major operands) + small-channel / split-K mma.sync kernels"),
+                       ("yad_conv2d", "forward convolutions + input gradients: conv_tma_kernel / conv_tc_kernel / conv_small_kernel")):
+        ms_k, fl, n = prof[key]
+        roof[key] = {"kernel": label, "bound": "tensor", "achieved": fl / (ms_k / 1000.0) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": fl / (ms_k / 1000.0) / 1e12 / pk["tf_sustained"], "launches": n, "ms": ms_k, "share_of_step": ms_k / tot_ms,
+                     "traffic": None, "note": "most launches are HBM-bound (1x1 wgrad reads 5.6 TB/s = 86 % of the measured HBM peak, profiles/r1_ncu_wgrad_tc.json)"}
     out = {"metric": "train img/s (forward + loss + backward + optimizer)", "value": world * B / (ms / 1000.0), "unit": "img/s",
            "ms_per_step": ms, "batch_per_gpu": B, "global_batch": world * B, "steps": args.train_steps, "launches_per_step": launches,
            "scaling": "weak", "exchange": "none (1 GPU)" if world == 1 else f"NCCL all-reduce of the {eng.tp.total * 4 / 1e6:.1f} MB fp32 gradient arena",
            "e2e": {"value": world * B / (e2e_ms / 1000.0), "unit": "img/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": img_host.numel() + sum(t.numel() * 4 for t in tg_host), "d2h_bytes_per_step": 16},
-           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "loss": [float(v) for v in loss_host]}
+           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "loss": [float(v) for v in loss_host], "roofline": roof,
+           "profile_ms": {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:12]}}
     del eng
     torch.cuda.empty_cache()
     return out

@@ -122,19 +122,22 @@ __global__ void __launch_bounds__(TPB, 3) norm_bwd_reduce_kernel(yad_tensor x, y
       c1[i] = srstd[o + i]; c2[i] = smean[o + i] * srstd[o + i]; ga[i] = gamma[o + i]; be[i] = beta[o + i];
     }
     int64_t p = p0 + lane;
-    for (; p + step < p1; p += 2 * step) {  // two pixels per trip: four 128-bit loads in flight
-      float v[8], g[8], v2[8], g2[8];
-      load8(xb + p * x.ld + o, v);
-      load8(gb + p * dy.ld + o, g);
-      load8(xb + (p + step) * x.ld + o, v2);
-      load8(gb + (p + step) * dy.ld + o, g2);
+    for (; p + 3 * step < p1; p += 4 * step) {  // four pixels per trip: eight 128-bit loads in flight (latency-bound otherwise)
+      float v[4][8], g[4][8];
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const float xh = fmaf(v[i], c1[i], -c2[i]), xh2 = fmaf(v2[i], c1[i], -c2[i]);
-        const float gg = g[i] * act_grad_ct<ACT>(fmaf(xh, ga[i], be[i]));
-        const float gg2 = g2[i] * act_grad_ct<ACT>(fmaf(xh2, ga[i], be[i]));
-        a[i] += gg + gg2;
-        b[i] = fmaf(gg, xh, fmaf(gg2, xh2, b[i]));
+      for (int u = 0; u < 4; u++) {
+        load8(xb + (p + u * step) * x.ld + o, v[u]);
+        load8(gb + (p + u * step) * dy.ld + o, g[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const float xh = fmaf(v[u][i], c1[i], -c2[i]);
+          const float gg = g[u][i] * act_grad_ct<ACT>(fmaf(xh, ga[i], be[i]));
+          a[i] += gg;
+          b[i] = fmaf(gg, xh, b[i]);
+        }
       }
     }
     for (; p < p1; p += step) {
@@ -234,7 +237,25 @@ __global__ void __launch_bounds__(TPB, 3) norm_bwd_apply_kernel(yad_tensor x, ya
       A[i] = srstd[o + i] * ga[i]; E[i] = srstd[o + i] * k1[o + i]; F[i] = srstd[o + i] * k2[o + i];
     }
     const int64_t stride = (int64_t)gridDim.x * ppb;
-    for (int64_t p = (int64_t)blockIdx.x * ppb + lane; p < hw; p += stride) {
+    int64_t p = (int64_t)blockIdx.x * ppb + lane;
+    for (; p + stride < hw; p += 2 * stride) {  // two pixels per trip: four 128-bit loads in flight (the kernel is latency-bound otherwise)
+      float v[8], g[8], v2[8], g2[8];
+      load8(xb + p * x.ld + o, v);
+      load8(gb + p * dy.ld + o, g);
+      load8(xb + (p + stride) * x.ld + o, v2);
+      load8(gb + (p + stride) * dy.ld + o, g2);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float xh = fmaf(v[i], c1[i], -c2[i]), xh2 = fmaf(v2[i], c1[i], -c2[i]);
+        const float gg = g[i] * act_grad_ct<ACT>(fmaf(xh, ga[i], be[i]));
+        const float gg2 = g2[i] * act_grad_ct<ACT>(fmaf(xh2, ga[i], be[i]));
+        v[i] = fmaf(gg, A[i], -fmaf(xh, F[i], E[i]));
+        v2[i] = fmaf(gg2, A[i], -fmaf(xh2, F[i], E[i]));
+      }
+      store8_acc(ob + p * dx.ld + o, v, acc);
+      store8_acc(ob + (p + stride) * dx.ld + o, v2, acc);
+    }
+    for (; p < hw; p += stride) {
       float v[8], g[8];
       load8(xb + p * x.ld + o, v);
       load8(gb + p * dy.ld + o, g);
