@@ -187,3 +187,15 @@ def test_backward_is_the_derivative_of_the_forward(state_dict):
         fd = (vals[0] - vals[1]) / (2 * eps)
         an = float((grad.double() * d.double()).sum())
         assert abs(fd - an) < tol * abs(an), (fd, an)
+
+
+def test_gradient_accumulation_adds_up(state_dict):
+    """zero_grad=False: two forward / backward passes on two half batches leave the sum of their gradients (accumulate > 1 in the reference)"""
+    from oracle import synth
+    img = torch.from_numpy(synth.make_images(2, 160, 160, seed=12)).cuda()
+    bi, cl, bb = [torch.from_numpy(a) for a in synth.make_targets(2, seed=13, max_per_img=4, empty_images=())]
+    eng = TrainEngine(state_dict, dtype=torch.float32, conv_impl=1)
+    eng.forward_backward(img, bi, cl, bb, update_bn=False)
+    g1 = eng.tp.grad.clone()
+    eng.forward_backward(img, bi, cl, bb, update_bn=False, zero_grad=False)
+    assert float((eng.tp.grad - 2 * g1).norm() / (2 * g1).norm()) < 1e-3

@@ -61,3 +61,19 @@ def test_optimizer_groups_match_reference(gold, state_dict):
     for k, grp in ref.items():
         if k in state_dict and not is_frozen(k):
             assert optimizer_group(k) == grp, k
+
+
+def test_checkpoint_roundtrip(state_dict):
+    """flat arenas + counters survive checkpoint() / load_checkpoint(); state_dict() views follow the reference's keys"""
+    tp = TrainParams(state_dict, torch.float32, "cpu")
+    tp.flat.add_(0.5)
+    tp.mom.fill_(0.25)
+    tp.steps, tp.ema_updates = 7, 7
+    ck = tp.checkpoint()
+    tp2 = TrainParams(state_dict, torch.float32, "cpu")
+    tp2.load_checkpoint(ck)
+    assert torch.equal(tp2.flat, tp.flat) and torch.equal(tp2.mom, tp.mom) and tp2.steps == 7 and tp2.ema_updates == 7
+    sd = tp2.state_dict()
+    assert set(k for k in state_dict if state_dict[k].dtype.is_floating_point) <= set(sd)
+    k = "model.0.conv.weight"
+    assert torch.allclose(sd[k], state_dict[k].float() + 0.5)

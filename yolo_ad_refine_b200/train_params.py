@@ -133,6 +133,18 @@ class TrainParams:
         out.update({k: v.clone() for k, v in self.other.items()})
         return out
 
+    def checkpoint(self):
+        """everything a resumed run needs (the reference's `last.pt` keeps model, EMA, optimizer state and the EMA update count,
+        engine/trainer.py:485-515): flat fp32 arenas as CPU tensors + counters; the key / offset table is implied by the state-dict order"""
+        return dict(flat=self.flat.cpu(), mom=self.mom.cpu(), ema=self.ema.cpu(), bufs=self.bufs.cpu(), ema_bufs=self.ema_bufs.cpu(),
+                    steps=self.steps, ema_updates=self.ema_updates, keys=list(self.keys), total=self.total)
+
+    def load_checkpoint(self, ck):
+        assert ck["keys"] == self.keys and ck["total"] == self.total, "checkpoint was written for a different parameter layout"
+        for name in ("flat", "mom", "ema", "bufs", "ema_bufs"):
+            getattr(self, name).copy_(ck[name])
+        self.steps, self.ema_updates = int(ck["steps"]), int(ck["ema_updates"])
+
     # ---- kernel layouts ---------------------------------------------------------------------------------------------
     def _wshape(self, key):
         s = self.shape[key]

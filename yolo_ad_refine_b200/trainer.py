@@ -35,11 +35,17 @@ class TrainEngine:
             self._anchors[shapes] = (a.to(self.device), s.to(self.device))
         return self._anchors[shapes]
 
-    def forward_backward(self, img, batch_idx, cls, bboxes, update_bn=True, keep=False):
-        """img fp32 (B, 3, H, W) in [0, 1] on the device; targets as in the reference's batch dict (utils/loss.py:443-446).
-        Leaves the gradients in tp.grad (reference state-dict layout) and returns out4 = [box, cls, dfl, total * B] (device, fp32)."""
+    def forward_backward(self, img, batch_idx, cls, bboxes, update_bn=True, keep=False, zero_grad=True):
+        """img fp32 (B, 3, H, W) in [0, 1] or uint8 in [0, 255], on the device; targets as in the reference's batch dict (utils/loss.py:443-446).
+        Leaves the gradients in tp.grad (reference state-dict layout) and returns out4 = [box, cls, dfl, total * B] (device, fp32).
+        zero_grad=False accumulates onto the gradients of the previous call (the reference's `accumulate = max(round(nbs / batch), 1)`,
+        engine/trainer.py:372-375: several forward / backward passes per optimizer step)."""
         tp = self.tp
-        tp.zero_grad()
+        if zero_grad:
+            tp.zero_grad()
+        else:  # the packed weight-gradient scratch of the previous call has already been folded into tp.grad
+            tp.arena_g[:max(tp._top_t, 8)].zero_()
+            tp.arena_gf[:max(tp._top_f, 8)].zero_()
         tp.pack()
         g = T.Graph(tp, self.conv_impl, update_bn)
         outs, layers = T.forward_model(g, img)
