@@ -48,7 +48,7 @@ typedef struct {
   /* optional fused GroupNorm statistics of the conv output (after scale / bias / act / alpha, before mul / add): stats double
    * [n][gn_groups][2] += (sum, sum of squares); yad_conv2d zeroes the buffer itself.  Used by Conv_GN (nn/modules/head.py:1265-1279). */
   double* gn_stats;
-  int32_t gn_groups;
+  int32_t gn_groups; /* 0 with gn_stats set: per-channel statistics over the WHOLE batch, double [cout][2] (train-mode BatchNorm, conv.py:50) */
 } yad_epilogue;
 
 typedef struct {

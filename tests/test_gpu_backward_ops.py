@@ -239,3 +239,25 @@ def test_deform_col_forward_backward(dtype, hw):
     got = dom.nchw().float().cpu().numpy()
     assert rel_err(got[:, :27], omr.grad.numpy()) < tolb
     assert float(np.abs(got[:, 27:]).max()) == 0.0
+
+
+@pytest.mark.parametrize("geom", [(64, 64, 3, 1, 4, 20, 20), (128, 256, 1, 1, 3, 20, 12), (64, 128, 3, 2, 2, 40, 40), (48, 96, 1, 1, 2, 16, 24)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_conv_fused_batch_statistics(geom, mode):
+    """gn_groups = 0: per-channel (sum, sum of squares) over the whole batch accumulated in the conv epilogue (train-mode BatchNorm) equal the
+    stand-alone statistics kernel run on the stored conv output"""
+    cin, cout, k, stride, n, h, w = geom
+    dtype = torch.float32 if mode == "fp32" else torch.bfloat16
+    rs = np.random.RandomState(cin + cout)
+    from yolo_ad_refine_b200.weights import pack_conv
+    wt = torch.from_numpy(rs.standard_normal((cout, cin, k, k)).astype(np.float32) / (cin * k * k) ** 0.5)
+    cw = pack_conv(wt, None, dtype, DEV, stride)
+    x = Act.from_nchw(torch.from_numpy(rs.standard_normal((n, cin, h, w)).astype(np.float32) + 0.3).to(DEV), dtype)
+    ho, wo = (h + 2 * (k // 2) - k) // stride + 1, (w + 2 * (k // 2) - k) // stride + 1
+    y = Act.empty(n, ho, wo, cout, dtype, DEV)
+    fused = torch.empty((1, cout, 2), dtype=torch.float64, device=DEV)
+    ops.conv2d(x, cw.w, y, kh=k, kw=k, stride=stride, pad_h=k // 2, pad_w=k // 2, impl=1 if mode == "fp32" else 0, gn_stats=fused, gn_groups=0)
+    ref = torch.empty_like(fused)
+    ops._call("yad_gn_stats", y.reshape(1, n * ho, wo).yt(), cout, ops._p(ref), ops.dt(dtype), ops.stream_ptr())
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(fused.cpu().numpy(), ref.cpu().numpy(), rtol=2e-5, atol=1e-3)

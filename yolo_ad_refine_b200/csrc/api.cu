@@ -50,6 +50,12 @@ int yad_conv2d(const yad_tensor* x, const void* w, const yad_conv_desc* d, const
     YAD_CHECK(e->mul == nullptr && e->add == nullptr, "conv2d: fused GroupNorm statistics cannot be combined with mul / add");
     int r = yad_conv2d_simt(x, w, d, &e2, y, dtype, stream);
     if (r) return r;
+    if (e->gn_groups == 0) {  // batch statistics (train-mode BatchNorm): the batch as one image, one channel per group
+      yad_tensor flat = *y;
+      flat.n = 1;
+      flat.h = y->n * y->h;
+      return yad_gn_stats(&flat, y->c, e->gn_stats, dtype, stream);
+    }
     return yad_gn_stats(y, e->gn_groups, e->gn_stats, dtype, stream);
   }
   return yad_conv2d_simt(x, w, d, e, y, dtype, stream);

@@ -40,6 +40,7 @@ struct TcParams {
   int n_tile, stages, tmem_cols, pipe_bytes;
   int out_f32;
   int cout_real;  // channel count GroupNorm statistics are defined over (= cout of the view)
+  int bn_stats;   // 1: e.gn_stats is double [cout][2] = per-channel (sum, sum of squares) over the WHOLE batch (train-mode BatchNorm)
   yad_epilogue e;
 };
 
@@ -192,6 +193,52 @@ __device__ __forceinline__ void gn_accumulate(const TcParams& p, const float (&v
   else gn_accumulate_t<16>(p, v, co, dp, img);
 }
 
+// Per-channel batch statistics (train-mode BatchNorm) fused into phase 2 of the epilogue: in phase 2 a lane owns 8 fixed channels of a 64-column
+// chunk and sweeps rows, so its partial sums accumulate in registers across rows AND across the tiles of a persistent CTA; they meet once,
+// at the end (or when the CTA moves to another column tile): shuffle reduction over the lanes that share the channels, then one double
+// atomicAdd pair per channel per warp.  The sums are taken over the bf16-rounded values that are stored (what the BatchNorm kernels read back).
+struct BnAcc {
+  float s[2][8], q[2][8];  // [64-column chunk of this warp's column range][channel]
+  int n0;                  // column tile the sums belong to (-1: empty)
+};
+__device__ __forceinline__ void bn_acc_clear(BnAcc& a) {
+#pragma unroll
+  for (int c = 0; c < 2; c++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a.s[c][i] = 0.f; a.q[c][i] = 0.f; }
+  a.n0 = -1;
+}
+__device__ __forceinline__ void bn_acc_flush(const TcParams& p, BnAcc& a, int lane, int col_begin, int col_end) {
+  if (a.n0 < 0) return;  // warp-uniform
+#pragma unroll
+  for (int ci = 0; ci < 2; ci++) {
+    const int c0 = col_begin + ci * 64;
+    if (c0 >= col_end) break;
+    const int cw = min(64, col_end - c0), cpr = cw >> 3, rpp = 32 / cpr;
+    const int rr = lane / cpr, ch = (lane - rr * cpr) * 8, co = a.n0 + c0 + ch;
+    const bool pow2 = (cpr & (cpr - 1)) == 0;
+    if (pow2) {
+      for (int d = cpr; d < 32; d <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          a.s[ci][i] += __shfl_xor_sync(0xffffffffu, a.s[ci][i], d);
+          a.q[ci][i] += __shfl_xor_sync(0xffffffffu, a.q[ci][i], d);
+        }
+      }
+    }
+    if ((pow2 ? rr == 0 : rr < rpp) && co < p.cout) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (co + i < p.cout_real) {
+          atomicAdd(&p.e.gn_stats[(int64_t)(co + i) * 2], (double)a.s[ci][i]);
+          atomicAdd(&p.e.gn_stats[(int64_t)(co + i) * 2 + 1], (double)a.q[ci][i]);
+        }
+      }
+    }
+  }
+  bn_acc_clear(a);
+}
+
 constexpr int STG_ROW = 144;            // bytes per staged row: 64 bf16 + 16 (16-byte aligned rows, conflict-free 128-bit accesses)
 constexpr int STG_WARP = 32 * STG_ROW;  // staging bytes per epilogue warp
 
@@ -200,8 +247,9 @@ constexpr int STG_WARP = 32 * STG_ROW;  // staging bytes per epilogue warp
 //   in a per-warp smem staging tile; phase 2 (lanes sweep each row contiguously): optional mul / add, 128-bit coalesced stores.
 //   (The conv output is rounded to bf16 before mul / add -- exactly what the unfused bf16 reference path materialises.)
 // dp = destination pixel index of this thread's row (or -1), img = its image (for img_scale).
+template <bool BN>
 __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_acc, int quarter, int lane, uint8_t* stg, int* drow, int dp, int img,
-                                              int n0, int col_begin, int col_end) {
+                                              int n0, int col_begin, int col_end, BnAcc& bn) {
   const yad_epilogue& e = p.e;
   float sc = 1.0f;
   if (dp >= 0) {
@@ -245,7 +293,7 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_a
 #pragma unroll
         for (int i = 0; i < 16; i++) v[i] *= e.alpha;
       }
-      if (e.gn_stats) gn_accumulate(p, v, co, dp, img);
+      if (!BN && e.gn_stats) gn_accumulate(p, v, co, dp, img);
       float lo[8], hi[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) { lo[i] = v[i]; hi[i] = v[8 + i]; }
@@ -259,11 +307,27 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_a
     const int cpr = cw >> 3, rpp = 32 / cpr;
     const int rr = lane / cpr, ch = (lane - rr * cpr) * 8;
     const int co = n0 + c0 + ch;
+    const int bci = (c0 - col_begin) >> 6;
+    if (BN && bn.n0 != n0) {  // warp-uniform: this CTA moved to another column tile
+      bn_acc_flush(p, bn, lane, col_begin, col_end);
+      bn.n0 = n0;
+    }
     if (rr < rpp && co < p.cout) {
       for (int row = rr; row < 32; row += rpp) {
         const int d = drow[row];
         if (d < 0) continue;
         uint4 u = *reinterpret_cast<const uint4*>(stg + row * STG_ROW + ch * 2);
+        if (BN) {  // static indices only: the accumulators must stay in registers
+          float bv[8];
+          bf8_to_f(u, bv);
+          if (bci == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) { bn.s[0][i] += bv[i]; bn.q[0][i] = fmaf(bv[i], bv[i], bn.q[0][i]); }
+          } else if (bci == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) { bn.s[1][i] += bv[i]; bn.q[1][i] = fmaf(bv[i], bv[i], bn.q[1][i]); }
+          }
+        }
         if (e.mul || e.add) {
           float v[8];
           bf8_to_f(u, v);
@@ -461,7 +525,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
         const int my = r / p.wm, mx = r - my * p.wm;
         dp = (img * p.ho + p.os * my + p.py) * p.wo + (p.os * mx + p.px);
       }
-      epilogue_warp(p, tmem_base, warp, lane, stg, drow, dp, img, n0, 0, p.n_tile);
+      BnAcc bn;  // unused: batch statistics are fused on the TMA-fed kernel only (the host runs yad_gn_stats after this kernel otherwise)
+      epilogue_warp<false>(p, tmem_base, warp, lane, stg, drow, dp, img, n0, 0, p.n_tile, bn);
     }
     tc_fence_before();
   } else {
@@ -535,6 +600,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
                : "memory");
 }
 
+template <bool BN>  // BN: fused per-channel batch statistics (train-mode BatchNorm); a separate instantiation keeps the inference kernel lean
 __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_constant__ TmaParams tp, const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB) {
   // Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA producer runs ahead across tile boundaries and the
@@ -638,6 +704,8 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
     const int csplit = ((p.n_tile / 16 + 1) / 2) * 16;
     const int col_begin = half ? csplit : 0, col_end = half ? p.n_tile : csplit;
     int i = 0;
+    BnAcc bn;
+    bn_acc_clear(bn);
     for (int tile = blockIdx.x; tile < tp.total_tiles; tile += gridDim.x, i++) {
       const int mt = tile / tp.tiles_n, n0 = (tile - mt * tp.tiles_n) * p.n_tile;
       int dp = -1, img = 0;
@@ -654,11 +722,12 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
       const int acc = i % acc_stages;
       mbar_wait(tfull_bar(acc), ((uint32_t)(i / acc_stages)) & 1u);
       tc_fence_after();
-      epilogue_warp(p, tmem_base + (uint32_t)(acc * p.n_tile), quarter, lane, stg, drow, dp, img, n0, col_begin, col_end);
+      epilogue_warp<BN>(p, tmem_base + (uint32_t)(acc * p.n_tile), quarter, lane, stg, drow, dp, img, n0, col_begin, col_end, bn);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));  // all epilogue warps -> accumulator free
     }
+    if (BN) bn_acc_flush(p, bn, lane, col_begin, col_end);
   }
   __syncthreads();
   if (warp == 1) {
@@ -807,7 +876,8 @@ int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaFuncSetAttribute(conv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
       yad_set_error("conv2d_tma: cannot raise the dynamic shared memory limit");
       num_sms = 0;
       return 2;
@@ -821,7 +891,10 @@ int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
   if (per_sm < 1) per_sm = 1;
   int grid = num_sms * per_sm;
   if (grid > tp.total_tiles) grid = tp.total_tiles;
-  conv_tma_kernel<<<grid, TMA_THREADS, smem, st>>>(tp, tmA, tmB);
+  if (p.bn_stats)
+    conv_tma_kernel<true><<<grid, TMA_THREADS, smem, st>>>(tp, tmA, tmB);
+  else
+    conv_tma_kernel<false><<<grid, TMA_THREADS, smem, st>>>(tp, tmA, tmB);
   YAD_LAUNCH_CHECK("conv2d_tma");
   (void)d;
   return 0;
@@ -896,7 +969,12 @@ int yad_conv2d_tc(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
   p.cout_real = y->c;
   YAD_CHECK(x->n == y->n, "conv2d: batch mismatch %d vs %d", x->n, y->n);
   cudaStream_t st = (cudaStream_t)stream;
-  if (e->gn_stats) {
+  if (e->gn_stats && e->gn_groups == 0) {  // train-mode BatchNorm: per-channel statistics over the whole batch, double [cout][2]
+    YAD_CHECK(d->mode != YAD_CONV_TRANSPOSED && !e->mul && !e->add, "conv2d: fused BatchNorm statistics: plain / deformable convolutions without mul / add");
+    YAD_CHECK(y->c <= 512, "conv2d: fused BatchNorm statistics support up to 512 output channels");
+    p.bn_stats = 1;
+    cudaMemsetAsync(e->gn_stats, 0, sizeof(double) * 2 * y->c, st);
+  } else if (e->gn_stats) {
     const int cpg = e->gn_groups > 0 ? y->c / e->gn_groups : 0;
     YAD_CHECK(e->gn_groups > 0 && y->c % e->gn_groups == 0 && (cpg == 4 || cpg == 8 || cpg == 16),
               "conv2d: fused GroupNorm statistics need 4, 8 or 16 channels per group (got %d channels / %d groups)", y->c, e->gn_groups);
@@ -917,6 +995,16 @@ int yad_conv2d_tc(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
     p.ntaps = d->kh * d->kw;
     for (int t = 0; t < p.ntaps; t++) { p.dy[t] = t / d->kw - d->pad_h; p.dx[t] = t % d->kw - d->pad_w; p.wtap[t] = t; }
     if (d->impl != 3 && tma_supported(x, d, y)) return launch_tma(p, d, st);
+    if (p.bn_stats) {  // batch statistics are fused on the TMA-fed kernel only: thread-gathered kernel first, stand-alone statistics after it
+      p.bn_stats = 0;
+      p.e.gn_stats = nullptr;
+      const int r = launch(p, (int64_t)x->n * p.hm * p.wm, st);
+      if (r) return r;
+      yad_tensor flat = *y;
+      flat.n = 1;
+      flat.h = y->n * y->h;
+      return yad_gn_stats(&flat, y->c, e->gn_stats, YAD_BF16, stream);
+    }
     return launch(p, (int64_t)x->n * p.hm * p.wm, st);
   }
   if (d->mode == YAD_CONV_TRANSPOSED) {

@@ -237,8 +237,14 @@ def norm_act(g, t, wkey, bkey, groups, eps, act, out=None, add=None, stats=None,
 
 def conv_bn_act(g, p, x, stride=1, out=None, add=None, need_dx=True):
     """nn/modules/conv.py:36-51 Conv.forward in train(): conv(bias=False) -> BatchNorm2d(batch statistics) -> SiLU (+ residual)"""
-    t = conv(g, x, p + ".conv.weight", stride=stride, need_dx=need_dx)
-    return norm_act(g, t, p + ".bn.weight", p + ".bn.bias", 0, BN_EPS, ACT_SILU, out=out, add=add, bn=p + ".bn")
+    co, _, kh, _ = g.tp.shape[p + ".conv.weight"]
+    if kh == 3 and x.c <= 32 and co <= 32:  # small-channel 3x3: the single-pass conv_small kernel (no fused statistics) + yad_gn_stats
+        t = conv(g, x, p + ".conv.weight", stride=stride, need_dx=need_dx)
+        return norm_act(g, t, p + ".bn.weight", p + ".bn.bias", 0, BN_EPS, ACT_SILU, out=out, add=add, bn=p + ".bn")
+    # per-channel batch statistics accumulated in the convolution's epilogue (gn_groups = 0): saves one full read of the conv output
+    stats = g.f64(1, (co + 7) // 8 * 8, 2)
+    t = conv(g, x, p + ".conv.weight", stride=stride, need_dx=need_dx, gn_stats=stats, groups=0)
+    return norm_act(g, t, p + ".bn.weight", p + ".bn.bias", 0, BN_EPS, ACT_SILU, out=out, add=add, stats=stats, bn=p + ".bn")
 
 
 def conv_gn_act(g, p, x, out=None, add=None, act=ACT_SILU, img_scale=None):
