@@ -16,9 +16,17 @@ class Ctx:
 
     def __init__(self, P, conv_impl=0, parallel_levels=True, dcn_col=False):
         self.P, self.dtype, self.device, self.conv_impl = P, P.dtype, P.device, conv_impl
-        self.parallel_levels = parallel_levels
+        self._parallel = parallel_levels
         self.dcn_col = dcn_col  # deformable conv as column tensor + 1x1 GEMM (False: the gathered-operand deformable mode of yad_conv2d)
         self._side = []
+
+    @property
+    def parallel_levels(self):
+        """Independent branches (pyramid levels, lateral gates, TSSA scales, ...) are forked onto side streams ONLY while a CUDA graph is being
+        captured: there they become parallel graph branches over the capture's private memory pool.  In eager mode everything stays on one
+        stream -- a tensor allocated on a side stream and consumed on the main stream could be recycled by the caching allocator while the
+        main stream still reads it (it tracks only the allocating stream)."""
+        return self._parallel and torch.cuda.is_current_stream_capturing()
 
     def side_streams(self, n):
         while len(self._side) < n:
