@@ -157,3 +157,20 @@ def test_1280_fp32_matches_oracle_and_nms_is_exact(state_dict):
     det = eng.detect(img)
     # detect() runs its own step (forward replays agree to rounding, not bit for bit): compare with the NMS of exactly that step's y
     np.testing.assert_array_equal(det[0].cpu().numpy(), op.non_max_suppression(eng.last_prediction().cpu().numpy(), 0.25, 0.7, max_det=300)[0])
+
+
+def test_full_size_batch64_detections_are_the_nms_of_the_engine_predictions(state_dict):
+    """BASELINE.json configs[1] size (batch 64, 640 x 640, bf16): size-independent check of the post-processing half at full size -- the
+    detections the pipelined engine hands out are bit for bit the reference-order NMS (oracle) of the predictions y of that same step; y is
+    finite and the raw head outputs have the expected shapes."""
+    from oracle import postprocess as op
+    eng = RefineEngine(state_dict, batch=64, imgsz=640, dtype=torch.bfloat16, nms_args=dict(conf_thres=0.25, iou_thres=0.7, max_det=300), input_u8=True)
+    rs = np.random.RandomState(5)
+    img = torch.from_numpy(rs.randint(0, 256, (64, 3, 640, 640), dtype=np.uint8))
+    for _ in range(3):  # alternate the two buffer sets of the pipelined engine
+        det = eng.detect(img)
+    y = eng.last_prediction()
+    assert tuple(y.shape) == (64, 84, 8400) and bool(torch.isfinite(y).all())
+    ref = op.non_max_suppression(y.cpu().numpy(), 0.25, 0.7, max_det=300)
+    for i in range(64):
+        np.testing.assert_array_equal(det[i].cpu().numpy(), ref[i])
