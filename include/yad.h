@@ -199,7 +199,7 @@ int yad_loss_finalize(const double* sums, float box_gain, float cls_gain, float 
 
 /* =====================================================================================================================
  * Training path: backward kernels of every operator above + optimizer.  The reference's
- * backward is PyTorch autograd over the same modules (engine/trainer.py:389-401 loss.backward(); optimizer_step :580-588).
+ * backward is PyTorch autograd over the same modules (engine/trainer.py:382-397 loss.backward(); optimizer_step :580-588).
  * Conventions: activation gradients are written (acc = 0) or accumulated (acc = 1: dx += ...) in the activation dtype;
  * parameter gradients are ACCUMULATED into fp32 buffers that the caller zeroes once per step.
  * dgrad of a convolution is yad_conv2d itself on the gradient with permuted weights (stride 1: flipped taps; stride 2:

@@ -51,7 +51,7 @@ def _grad_worker(rank, world, port, q):
 
 
 def test_two_rank_gloo_gradient_exchange():
-    """training's one collective: SUM all-reduce of the flat gradient arena, rank-0 BatchNorm buffers (DDP semantics, trainer.py:279,394)"""
+    """training's one collective: SUM all-reduce of the flat gradient arena, rank-0 BatchNorm buffers (DDP semantics, trainer.py:273,387)"""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 31500 + os.getpid() % 2000

@@ -1,6 +1,6 @@
 """Multi-GPU plumbing, one process per GPU.  Inference shards by image with NO data-path collective: torch.distributed
 is used only for the rendezvous, the barrier around the timed region and the max-over-ranks reduction of the timing.  Training has one real
-exchange step per iteration -- the reference's DistributedDataParallel gradient all-reduce (engine/trainer.py:279) -- done here as ONE
+exchange step per iteration -- the reference's DistributedDataParallel gradient all-reduce (engine/trainer.py:273) -- done here as ONE
 all-reduce of the flat fp32 gradient arena, plus DDP's rank-0 broadcast of the BatchNorm buffers."""
 import os
 
@@ -55,7 +55,7 @@ def sum_over_ranks(value, device="cpu"):
 
 def exchange_gradients(tp, group=None):
     """DDP semantics of the reference trainer on the flat arenas of train_params.TrainParams: gradients are averaged by DDP and the loss is
-    multiplied by world_size (engine/trainer.py:394), i.e. the applied gradient is the SUM over ranks; module buffers (BatchNorm running
+    multiplied by world_size (engine/trainer.py:387), i.e. the applied gradient is the SUM over ranks; module buffers (BatchNorm running
     statistics) follow rank 0 (DistributedDataParallel(broadcast_buffers=True), its default)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return

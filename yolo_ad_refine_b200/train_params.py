@@ -135,7 +135,7 @@ class TrainParams:
 
     def checkpoint(self):
         """everything a resumed run needs (the reference's `last.pt` keeps model, EMA, optimizer state and the EMA update count,
-        engine/trainer.py:485-515): flat fp32 arenas as CPU tensors + counters; the key / offset table is implied by the state-dict order"""
+        engine/trainer.py:507-540): flat fp32 arenas as CPU tensors + counters; the key / offset table is implied by the state-dict order"""
         return dict(flat=self.flat.cpu(), mom=self.mom.cpu(), ema=self.ema.cpu(), bufs=self.bufs.cpu(), ema_bufs=self.ema_bufs.cpu(),
                     steps=self.steps, ema_updates=self.ema_updates, keys=list(self.keys), total=self.total)
 

@@ -1,9 +1,9 @@
 """TrainEngine: one training step of YOLO-AD-Refine on one GPU -- train()-mode forward, v8DetectionLoss (TaskAlignedAssigner + CIoU/NWD + DFL +
 SlideLoss-BCE), the full backward pass, gradient exchange, clip + SGD(nesterov) + EMA -- all as libyad.so kernels.
 
-Mirrors engine/trainer.py:380-401 (forward, loss, backward) and :580-588 (optimizer_step: unscale, clip_grad_norm_(10), step, zero_grad, EMA).
-Multi-GPU: one process per GPU; the reference wraps the model in DistributedDataParallel (trainer.py:279), which
-broadcasts rank 0's BatchNorm buffers before each forward and averages gradients, and multiplies the loss by world_size (trainer.py:394), so
+Mirrors engine/trainer.py:382-397 (forward, loss, backward) and :580-588 (optimizer_step: unscale, clip_grad_norm_(10), step, zero_grad, EMA).
+Multi-GPU: one process per GPU; the reference wraps the model in DistributedDataParallel (trainer.py:273), which
+broadcasts rank 0's BatchNorm buffers before each forward and averages gradients, and multiplies the loss by world_size (trainer.py:387), so
 the applied gradient is the SUM over ranks.  Here the flat fp32 gradient arena is all-reduced (SUM) in ONE NCCL call.
 """
 import torch
@@ -39,7 +39,7 @@ class TrainEngine:
         """img fp32 (B, 3, H, W) in [0, 1] or uint8 in [0, 255], on the device; targets as in the reference's batch dict (utils/loss.py:443-446).
         Leaves the gradients in tp.grad (reference state-dict layout) and returns out4 = [box, cls, dfl, total * B] (device, fp32).
         zero_grad=False accumulates onto the gradients of the previous call (the reference's `accumulate = max(round(nbs / batch), 1)`,
-        engine/trainer.py:372-375: several forward / backward passes per optimizer step)."""
+        engine/trainer.py:305,373: several forward / backward passes per optimizer step)."""
         tp = self.tp
         if zero_grad:
             tp.zero_grad()

@@ -1,7 +1,7 @@
 """Training path of the YOLO-AD-Refine model: the train()-mode forward (batch-statistics BatchNorm, unfolded
 weights), the detection loss and the complete backward pass, expressed as calls into libyad.so.
 
-The reference's backward is PyTorch autograd over its nn.Modules (engine/trainer.py:389-401 `self.loss, self.loss_items = self.model(batch)`
+The reference's backward is PyTorch autograd over its nn.Modules (engine/trainer.py:382-397 `self.loss, self.loss_items = self.model(batch)`
 -> `scaler.scale(self.loss).backward()`).  Here every forward primitive appends its hand-written backward (a closure over libyad kernels) to
 a tape; `Graph.backward()` replays the tape in reverse.  This file contains no arithmetic: PyTorch allocates buffers and owns the streams.
 
