@@ -128,7 +128,7 @@ def measure_training(args, world, rank, sd, dtype, W, barrier):
     from yolo_ad_refine_b200.trainer import TrainEngine
     B = args.train_batch
     eng = TrainEngine(sd, dtype=dtype, world_size=world)
-    # uint8 images, as the reference's dataloader delivers them (the /255 happens on the device: models/yolo/detect/train.py:56-59)
+    # uint8 images, as the reference's dataloader delivers them (the /255 happens on the device: models/yolo/detect/train.py:57-59)
     rs = np.random.RandomState(200 + rank)
     img_host = torch.from_numpy(rs.randint(0, 256, (B, 3, args.imgsz, args.imgsz), dtype=np.uint8)).pin_memory()
     tg_host = [torch.from_numpy(a).pin_memory() for a in synth.make_targets(B, seed=300 + rank, max_per_img=8, empty_images=())]

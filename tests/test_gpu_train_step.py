@@ -106,7 +106,7 @@ def test_training_is_deterministic_in_shape_and_repeatable(state_dict):
 
 
 def test_uint8_images_match_float_images(state_dict):
-    """uint8 batches (what the reference's dataloader delivers; /255 on the device, models/yolo/detect/train.py:56-59) give the step of the
+    """uint8 batches (what the reference's dataloader delivers; /255 on the device, models/yolo/detect/train.py:57-59) give the step of the
     equivalent float batch"""
     rs = np.random.RandomState(3)
     u8 = torch.from_numpy(rs.randint(0, 256, (2, 3, 160, 160), dtype=np.uint8)).cuda()

@@ -768,7 +768,7 @@ def forward_model(g, img):
     n, _, H, W = img.shape
     assert H % 32 == 0 and W % 32 == 0, "image size must be a multiple of the maximum stride 32"
     L = {}
-    # uint8 batches carry the trainer's device-side `.float() / 255` (models/yolo/detect/train.py:56-59 preprocess_batch) fused into the layout pass
+    # uint8 batches carry the trainer's device-side `.float() / 255` (models/yolo/detect/train.py:57-59 preprocess_batch) fused into the layout pass
     x0 = ops.u8_to_nhwc(img, g.act(n, H, W, 8)) if img.dtype == torch.uint8 else ops.nchw_to_nhwc(img, g.act(n, H, W, 8))
     L[0] = conv_bn_act(g, "model.0", x0, 2, need_dx=False)
     L[1] = conv_bn_act(g, "model.1", L[0], 2)
