@@ -1,4 +1,5 @@
-"""BASELINE.json configs[4] on one rank: inference at 1280 x 1280, batch 4 per GPU (batch 32 sharded over 8 GPUs) -- parity of the fp32 build
+"""TEST INFRASTRUCTURE (uses the CPU oracle as the checker; lives under tests/ for that reason, run it by hand on the GPU box).
+BASELINE.json configs[4] on one rank: inference at 1280 x 1280, batch 4 per GPU (batch 32 sharded over 8 GPUs) -- parity of the fp32 build
 against the CPU oracle on one image, then bf16 throughput of the per-GPU shard."""
 import os
 import sys

@@ -1,8 +1,9 @@
-"""Debug / evidence tool (GPU box): one full training forward + backward through libyad.so against the CPU oracle (oracle.model.train_step_grads,
+"""TEST INFRASTRUCTURE (uses the CPU oracle as the checker; lives under tests/ for that reason, run it by hand on the GPU box).
+Debug / evidence tool (GPU box): one full training forward + backward through libyad.so against the CPU oracle (oracle.model.train_step_grads,
 pinned to the live reference by tests/golden/train_step.npz): head outputs, loss, EVERY parameter gradient, BatchNorm buffer updates.
 Prints the relative L2 error per parameter so that a wrong backward kernel shows up at the first parameter it touches.
 
-    python tools/train_debug.py [case] [fp32|bf16] [json out]
+    python tests/train_debug.py [case] [fp32|bf16] [json out]
 """
 import json
 import os

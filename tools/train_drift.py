@@ -12,7 +12,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle import synth  # noqa: E402
+from yolo_ad_refine_b200 import synth  # noqa: E402
 from yolo_ad_refine_b200.trainer import TrainEngine  # noqa: E402
 
 
