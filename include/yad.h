@@ -313,6 +313,10 @@ int yad_permute_unpack(const yad_permute_entry* table_dev, int n_entries, int64_
 int yad_sqnorm(const float* x, int64_t n, double* out, void* stream);
 int yad_sgd_step(float* params, const float* grads, float* momentum_buf, const uint8_t* group, int64_t n, const float* lr3_host,
                  const float* wd3_host, float momentum, float max_norm, const double* norm_sq, int first_step, void* stream);
+/* clip_grad_norm_(max_norm) + torch.optim.AdamW(betas = (beta1, beta2), eps) with the same three groups: the optimizer the reference's
+ * `optimizer=auto` picks for runs shorter than 10,000 iterations (engine/trainer.py:773-782, 805).  step counts from 1. */
+int yad_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const uint8_t* group, int64_t n, const float* lr3_host,
+                   const float* wd3_host, float beta1, float beta2, float eps, int step, float max_norm, const double* norm_sq, void* stream);
 int yad_ema_update(float* ema, const float* params, int64_t n, float decay, void* stream);
 
 

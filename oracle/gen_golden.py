@@ -226,9 +226,10 @@ def gen_train_step():
 
 
 OPT_HYP = dict(lr=0.01, momentum=0.937, weight_decay=5e-4, steps=2)
+ADAMW_LR = 1e-3
 
 
-def gen_opt_step():
+def gen_opt_step(name="SGD", out="opt_step.npz"):
     """Two optimizer steps of the live reference on one batch: BaseTrainer.build_optimizer's own parameter grouping + torch.optim.SGD
     (engine/trainer.py:754-808), clip_grad_norm_(10) + step (trainer.py:580-588), ModelEMA.update (utils/torch_utils.py:511-541).
     Stores sampled parameter / EMA DELTAS (after - before): pins oracle/optim.py and the yad_sgd_step / yad_ema_update kernels."""
@@ -242,8 +243,10 @@ def gen_opt_step():
     for p_ in m.parameters():
         p_.requires_grad_(True)
     m.model[-1].dfl.conv.weight.requires_grad_(False)  # block.py:72
-    h = OPT_HYP
-    opt = BaseTrainer.build_optimizer(SimpleNamespace(args=SimpleNamespace(warmup_bias_lr=0.1)), m, name="SGD", lr=h["lr"], momentum=h["momentum"],
+    h = dict(OPT_HYP)
+    if name == "AdamW":
+        h["lr"] = ADAMW_LR
+    opt = BaseTrainer.build_optimizer(SimpleNamespace(args=SimpleNamespace(warmup_bias_lr=0.1)), m, name=name, lr=h["lr"], momentum=h["momentum"],
                                       decay=h["weight_decay"], iterations=1e5)
     ema = ModelEMA(m)
     img, bi, cl, bb = train_step_inputs(**TRAIN_STEP_CASES["b2_160"])
@@ -270,7 +273,7 @@ def gen_opt_step():
         d[f"{k}|delta"] = (v.double() - sd0[k].double()).numpy().reshape(-1)[pos]
         d[f"{k}|ema_delta"] = (sde[k].double() - sd0[k].double()).numpy().reshape(-1)[pos]
         d[f"{k}|delta_norm"] = np.float64((v.double() - sd0[k].double()).norm().item())
-    np.savez_compressed(os.path.join(GOLD, "opt_step.npz"), **d)
+    np.savez_compressed(os.path.join(GOLD, out), **d)
 
 
 def main():
@@ -278,6 +281,8 @@ def main():
         return gen_train_step()
     if sys.argv[1:] == ["opt_step"]:
         return gen_opt_step()
+    if sys.argv[1:] == ["opt_step_adamw"]:
+        return gen_opt_step("AdamW", "opt_step_adamw.npz")
     m, spec = build_reference_model()
     sd = synth.make_state_dict_np(seed=1, spec=spec)
     with open(os.path.join(GOLD, "state_checksum.json"), "w") as f:

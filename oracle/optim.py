@@ -40,3 +40,24 @@ def ema_update(ema, model_sd, updates, decay=0.9999, tau=2000.0):
         if v.dtype.is_floating_point:
             v.mul_(d).add_((1 - d) * model_sd[k])
     return d
+
+
+def adamw_step(params, grads, state, groups, step, lr=1e-3, betas=(0.937, 0.999), eps=1e-8, weight_decay=5e-4, max_norm=10.0):
+    """torch.optim.AdamW as BaseTrainer.build_optimizer configures it (engine/trainer.py:805: betas = (momentum, 0.999); decoupled weight decay on
+    group 0 only).  state: {key: (exp_avg, exp_avg_sq)}; step counts from 1.  Pinned by tests/golden/opt_step_adamw.npz."""
+    coef, total = clip_coef(grads, max_norm)
+    b1, b2 = betas
+    for k, p in params.items():
+        g = grads.get(k)
+        if g is None:
+            continue
+        g = g * coef
+        if k not in state:
+            state[k] = (torch.zeros_like(p), torch.zeros_like(p))
+        m, v = state[k]
+        p.mul_(1 - lr * (weight_decay if groups[k] == 0 else 0.0))
+        m.mul_(b1).add_((1 - b1) * g)
+        v.mul_(b2).add_((1 - b2) * g * g)
+        denom = v.sqrt() / math.sqrt(1 - b2 ** step) + eps
+        p.sub_((lr / (1 - b1 ** step)) * m / denom)
+    return total

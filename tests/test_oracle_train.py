@@ -105,3 +105,35 @@ def test_optimizer_step_matches_reference(gold, state_dict):
                                    atol=atol, err_msg=k)
         checked += 1
     assert checked > 400
+
+
+def test_adamw_step_matches_reference(gold, state_dict):
+    """oracle/optim.py adamw_step (clip + AdamW with the reference's groups) for two steps against the live reference
+    (tests/golden/opt_step_adamw.npz: BaseTrainer.build_optimizer(name="AdamW", lr=1e-3))"""
+    import json
+    import os
+    from conftest import GOLD
+    from oracle import model as om
+    from oracle import optim as oo
+    g = gold("opt_step_adamw.npz")
+    groups = json.load(open(os.path.join(GOLD, "optimizer_groups.json")))
+    img, bi, cl, bb = [torch.from_numpy(a) for a in cases.train_step_inputs(**cases.TRAIN_STEP_CASES["b2_160"])]
+    sd = {k: v.clone() for k, v in state_dict.items()}
+    state = {}
+    for step in range(2):
+        loss, _, grads, bn_upd, _ = om.train_step_grads(sd, img, bi, cl, bb)
+        assert abs(loss.item() - float(g[f"loss{step}"])) < 5e-4 * abs(float(g[f"loss{step}"]))
+        oo.adamw_step({k: sd[k] for k in grads}, grads, state, groups, step + 1, lr=1e-3)
+        sd.update(bn_upd)
+    checked = 0
+    for k, v in sd.items():
+        if not v.dtype.is_floating_point or k.endswith(("running_mean", "running_var")):
+            continue
+        if k.endswith((".conv.bias", ".conv1.bias", ".temps")):
+            continue  # exact gradient 0 (a bias in front of a batch-statistics BatchNorm; the TSSA temperatures): Adam amplifies rounding noise
+        pos = cases.sample_positions(v.numel(), 16)
+        dn = float(g[f"{k}|delta_norm"])
+        atol = 5e-2 * dn / np.sqrt(v.numel()) + 2e-7 * (float(v.abs().max()) + 1e-3)
+        np.testing.assert_allclose((v.double() - state_dict[k].double()).numpy().reshape(-1)[pos], g[f"{k}|delta"], rtol=5e-2, atol=atol, err_msg=k)
+        checked += 1
+    assert checked > 300

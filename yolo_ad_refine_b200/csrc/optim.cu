@@ -65,6 +65,31 @@ __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__
   }
 }
 
+// torch.nn.utils.clip_grad_norm_(max_norm) followed by torch.optim.AdamW (decoupled weight decay) with per-group lr / weight decay:
+// p *= 1 - lr wd;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+__global__ void adamw_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                  const uint8_t* __restrict__ group, int64_t n, float lr0, float lr1, float lr2, float wd0, float wd1, float wd2,
+                                  float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float max_norm, const double* __restrict__ norm_sq) {
+  float coef = 1.0f;
+  if (max_norm > 0.f && norm_sq) {
+    const float nrm = (float)sqrt(*norm_sq);
+    coef = fminf(max_norm / (nrm + 1e-6f), 1.0f);
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int gr = group[i];
+    if (gr > 2) continue;  // frozen
+    const float lr = gr == 0 ? lr0 : (gr == 1 ? lr1 : lr2), wd = gr == 0 ? wd0 : (gr == 1 ? wd1 : wd2);
+    const float gi = g[i] * coef;
+    float w = p[i] * (1.0f - lr * wd);
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    w -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    p[i] = w;
+  }
+}
+
 __global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ p, int64_t n, float d) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     ema[i] = d * ema[i] + (1.0f - d) * p[i];
@@ -111,6 +136,17 @@ int yad_sgd_step(float* params, const float* grads, float* momentum_buf, const u
   sgd_step_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(params, grads, momentum_buf, group, n, lr3_host[0], lr3_host[1], lr3_host[2],
                                                                     wd3_host[0], wd3_host[1], wd3_host[2], momentum, max_norm, norm_sq, first_step);
   YAD_LAUNCH_CHECK("sgd_step");
+  return 0;
+}
+
+int yad_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const uint8_t* group, int64_t n, const float* lr3_host,
+                   const float* wd3_host, float beta1, float beta2, float eps, int step, float max_norm, const double* norm_sq, void* stream) {
+  YAD_CHECK(step >= 1, "adamw_step: step counts from 1");
+  const float bc1 = 1.0f - powf(beta1, (float)step), bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+  adamw_step_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, group, n, lr3_host[0], lr3_host[1], lr3_host[2],
+                                                                      wd3_host[0], wd3_host[1], wd3_host[2], beta1, beta2, eps, bc1, bc2_sqrt, max_norm,
+                                                                      norm_sq);
+  YAD_LAUNCH_CHECK("adamw_step");
   return 0;
 }
 

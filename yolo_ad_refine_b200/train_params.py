@@ -285,15 +285,26 @@ class TrainParams:
                 ops._call("yad_permute_unpack", C.c_void_p(t.data_ptr()), n, mx, ops._fp(arena), ops._fp(self.grad), ops.stream_ptr())
 
     # ---- optimizer (engine/trainer.py:580-588) --------------------------------------------------------------------------
-    def optimizer_step(self, lr=0.01, bias_lr=None, momentum=0.937, weight_decay=5e-4, max_norm=10.0, ema_decay=0.9999, ema_tau=2000.0):
-        """clip_grad_norm_(max_norm) + SGD(nesterov) over the flat arenas, then ModelEMA.update (parameters and BatchNorm buffers)"""
+    def optimizer_step(self, lr=0.01, bias_lr=None, momentum=0.937, weight_decay=5e-4, max_norm=10.0, ema_decay=0.9999, ema_tau=2000.0,
+                       optimizer="SGD", beta2=0.999, eps=1e-8):
+        """clip_grad_norm_(max_norm) + the optimizer step over the flat arenas, then ModelEMA.update (parameters and BatchNorm buffers).
+        optimizer: "SGD" (nesterov, momentum) or "AdamW" (betas = (momentum, beta2)): the two BaseTrainer.build_optimizer creates for this model
+        (engine/trainer.py:773-808)."""
         self.norm_sq.zero_()
         st = ops.stream_ptr()
         ops._call("yad_sqnorm", ops._fp(self.grad), self.total, ops._fp(self.norm_sq), st)
         lr3 = (C.c_float * 3)(lr, lr, lr if bias_lr is None else bias_lr)
         wd3 = (C.c_float * 3)(weight_decay, 0.0, 0.0)
-        ops._call("yad_sgd_step", ops._fp(self.flat), ops._fp(self.grad), ops._fp(self.mom), C.c_void_p(self.group.data_ptr()), self.total, lr3, wd3,
-                  momentum, max_norm, ops._fp(self.norm_sq), int(self.steps == 0), st)
+        if optimizer == "SGD":
+            ops._call("yad_sgd_step", ops._fp(self.flat), ops._fp(self.grad), ops._fp(self.mom), C.c_void_p(self.group.data_ptr()), self.total, lr3,
+                      wd3, momentum, max_norm, ops._fp(self.norm_sq), int(self.steps == 0), st)
+        elif optimizer == "AdamW":
+            if not hasattr(self, "mom2"):
+                self.mom2 = torch.zeros_like(self.mom)  # second-moment arena (the first moment reuses the momentum arena)
+            ops._call("yad_adamw_step", ops._fp(self.flat), ops._fp(self.grad), ops._fp(self.mom), ops._fp(self.mom2), C.c_void_p(self.group.data_ptr()),
+                      self.total, lr3, wd3, momentum, beta2, eps, self.steps + 1, max_norm, ops._fp(self.norm_sq), st)
+        else:
+            raise NotImplementedError(f"optimizer {optimizer!r}: SGD and AdamW are built")
         self.steps += 1
         if ema_decay > 0:
             self.ema_updates += 1

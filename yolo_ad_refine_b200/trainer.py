@@ -17,14 +17,14 @@ from .train_params import TrainParams
 
 class TrainEngine:
     def __init__(self, state_dict, dtype=torch.bfloat16, device="cuda", conv_impl=0, nc=80, reg_max=16, strides=(8, 16, 32),
-                 gains=(7.5, 0.5, 1.5), topk=10, lr=0.01, momentum=0.937, weight_decay=5e-4, process_group=None, world_size=1):
+                 gains=(7.5, 0.5, 1.5), topk=10, lr=0.01, momentum=0.937, weight_decay=5e-4, process_group=None, world_size=1, optimizer="SGD"):
         if not torch.cuda.is_available():
             raise RuntimeError("TrainEngine needs a CUDA device: the YOLO-AD-Refine training path has no CPU fallback")
         ops.lib()
         self.device = torch.device(device)
         self.tp = TrainParams(state_dict, dtype, self.device)
         self.conv_impl, self.nc, self.reg_max, self.strides, self.gains, self.topk = conv_impl, nc, reg_max, strides, gains, topk
-        self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
+        self.lr, self.momentum, self.weight_decay, self.optimizer = lr, momentum, weight_decay, optimizer
         self.pg, self.world_size = process_group, world_size
         self._anchors = {}
         self.last = None
@@ -81,5 +81,5 @@ class TrainEngine:
     def step(self, img, batch_idx, cls, bboxes, lr=None):
         out4 = self.forward_backward(img, batch_idx, cls, bboxes)
         self.exchange()
-        self.tp.optimizer_step(lr=self.lr if lr is None else lr, momentum=self.momentum, weight_decay=self.weight_decay)
+        self.tp.optimizer_step(lr=self.lr if lr is None else lr, momentum=self.momentum, weight_decay=self.weight_decay, optimizer=self.optimizer)
         return out4
