@@ -87,3 +87,29 @@ def tal_inputs():
         gt_labels[b, :n, 0] = rs.randint(0, nc, n)
         mask_gt[b, :n] = 1
     return pd_scores, pd_bboxes, anc_px, gt_labels, gt_bboxes, mask_gt
+
+
+# pre-processing cases: (source h, source w, target size, auto / minimum-rectangle, seed)
+PREPROCESS_CASES = {
+    "vga_to_160": (480, 640, 160, False, 60),
+    "hd_to_160_auto": (720, 1280, 160, True, 61),
+    "odd_to_192": (333, 500, 192, False, 62),
+    "upscale_to_128": (50, 40, 128, False, 63),
+    "same_size": (160, 160, 160, False, 64),
+    "portrait_auto": (641, 480, 160, True, 65),
+    "tiny": (7, 9, 64, False, 66),
+}
+
+
+def preprocess_image(h, w, seed):
+    """uint8 HWC 'BGR' image with structure (gradients + noise), so that interpolation errors are visible"""
+    rs = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([(xx * 255 // max(w - 1, 1)), (yy * 255 // max(h - 1, 1)), ((xx + yy) * 255 // max(h + w - 2, 1))], -1)
+    return np.clip(base + rs.randint(-40, 41, (h, w, 3)), 0, 255).astype(np.uint8)
+
+
+def scale_boxes_inputs(seed=70, n=64):
+    rs = np.random.RandomState(seed)
+    b = rs.uniform(-20, 700, (n, 4)).astype(np.float32)
+    return np.concatenate([np.minimum(b[:, :2], b[:, 2:]), np.maximum(b[:, :2], b[:, 2:])], 1)

@@ -276,7 +276,27 @@ def gen_opt_step(name="SGD", out="opt_step.npz"):
     np.savez_compressed(os.path.join(GOLD, out), **d)
 
 
+def gen_preprocess():
+    """LetterBox + the predictor's BGR->RGB / HWC->CHW step (engine/predictor.py:115-133, 144-156) and scale_boxes (utils/ops.py:88-123) of the
+    live reference (cv2 %s) on the seeded images of oracle/cases.py: pins oracle/preprocess.py and the yad_letterbox / yad_scale_boxes kernels."""
+    import cv2
+    from oracle.cases import PREPROCESS_CASES, preprocess_image, scale_boxes_inputs
+    from ultralytics.data.augment import LetterBox
+    d = {"cv2_version": np.array(cv2.__version__)}
+    for name, (h, w, size, auto, seed) in PREPROCESS_CASES.items():
+        img = preprocess_image(h, w, seed)
+        lb = LetterBox((size, size), auto=auto, stride=32)(image=img)
+        chw = np.ascontiguousarray(np.stack([lb])[..., ::-1].transpose((0, 3, 1, 2)))[0]  # predictor.py:127-129
+        d[name] = chw
+        boxes = torch.from_numpy(scale_boxes_inputs(seed + 100) * (size / 640.0))
+        d[name + "_boxes"] = ref_ops.scale_boxes(chw.shape[1:], boxes.clone(), (h, w)).numpy()
+        print("preprocess", name, chw.shape)
+    np.savez_compressed(os.path.join(GOLD, "preprocess.npz"), **d)
+
+
 def main():
+    if sys.argv[1:] == ["preprocess"]:
+        return gen_preprocess()
     if sys.argv[1:] == ["train_step"]:
         return gen_train_step()
     if sys.argv[1:] == ["opt_step"]:
