@@ -168,6 +168,29 @@ int yad_nms(const float* pred, int batch, int nc, int n_anchors, float conf_thre
             int agnostic, int multi_label, int max_det, int max_nms, float max_wh, float* out, int32_t* out_idx, int32_t* out_count,
             void* workspace, void* stream);
 
+/* -- f1: image pre-processing and box post-scaling on the device.
+ *    One descriptor per image; the HOST fills it with the reference's own scalar geometry (LetterBox.__call__, data/augment.py:1558-1586:
+ *    ratio, new_unpad, top / left borders; scale_boxes, utils/ops.py:104-112: gain, pad) -- yolo_ad_refine_b200/preprocess.py does. */
+typedef struct {
+  const uint8_t* src;                 /* DEVICE pointer: source image, HWC uint8 (BGR, as cv2.imread delivers it), 3 channels */
+  int32_t src_h, src_w, src_pitch;    /* pitch = bytes per source row */
+  int32_t new_w, new_h;               /* LetterBox new_unpad: size of the resized image inside the padded output */
+  int32_t top, left;                  /* LetterBox borders: output row / column of the resized image's first pixel */
+  float gain, pad_x, pad_y;           /* scale_boxes: boxes = (boxes - pad) / gain, then clipped to [0, src_w] x [0, src_h] */
+} yad_image_desc;
+
+/*    yad_letterbox replaces LetterBox.__call__ (data/augment.py:1475-1600: cv2.resize INTER_LINEAR + cv2.copyMakeBorder value 114) and
+ *    BasePredictor.preprocess' host half (engine/predictor.py:127-129: stack, BGR -> RGB when swap_rb, HWC -> CHW).  cv2's 8-bit INTER_LINEAR is
+ *    fixed-point arithmetic (11-bit coefficients, two truncating shifts); the kernel reproduces it BIT FOR BIT, so the tensor the model sees equals
+ *    the reference's.  desc: DEVICE array [batch].  out: uint8 (batch, 3, out_h, out_w) NCHW, out_w a multiple of 4 -- what yad_stem_conv /
+ *    yad_u8_to_nhwc take (the /255 stays folded into the stem weights). */
+int yad_letterbox(const yad_image_desc* desc, int batch, uint8_t* out, int out_h, int out_w, int pad_value, int swap_rb, void* stream);
+
+/*    yad_scale_boxes replaces scale_boxes + clip_boxes (utils/ops.py:88-123, 315-334; called per image by DetectionPredictor.construct_result,
+ *    models/yolo/detect/predict.py:36-41) for a whole batch of NMS outputs: det fp32 [batch][max_det][row_ld] rows starting with x1,y1,x2,y2,
+ *    modified in place for rows < count[b] (count NULL: all max_det rows).  fp32 sub / div / clamp in the reference's order. */
+int yad_scale_boxes(float* det, int row_ld, const int32_t* count, int batch, int max_det, const yad_image_desc* desc, void* stream);
+
 /* -- a12: TaskAlignedAssigner.forward (utils/tal.py:38-88): one CTA per (image, gt) for the top-k, one CTA per image for the rest.
  *    pd_scores fp32 (B,N,nc) sigmoid scores, pd_bboxes fp32 (B,N,4) xyxy px, anc fp32 (N,2) px, gt_labels fp32 (B,M), gt_bboxes
  *    fp32 (B,M,4), mask_gt fp32 (B,M).  Outputs: target_labels int64 (B,N), target_bboxes fp32 (B,N,4), target_scores fp32 (B,N,nc),

@@ -98,7 +98,14 @@ PREPROCESS_CASES = {
     "same_size": (160, 160, 160, False, 64),
     "portrait_auto": (641, 480, 160, True, 65),
     "tiny": (7, 9, 64, False, 66),
+    "half": (256, 320, 160, False, 67),          # exact 2x: cv2 switches INTER_LINEAR to its INTER_AREA fast path, same bytes
+    "wide_to_160": (90, 400, 160, False, 68),
+    "tall_to_160": (301, 77, 160, False, 69),
 }
+# ragged batch: images of different sizes that letterbox to the same 160 x 160 tensor (one yad_letterbox launch)
+PREPROCESS_BATCH = ["vga_to_160", "same_size", "half", "wide_to_160", "tall_to_160"]
+# random (source h, source w) -> 96 x 96 sweep: the fixture stores only a CRC32 of the reference's bytes per case
+PREPROCESS_SWEEP = [(int(h), int(w), 200 + i) for i, (h, w) in enumerate(np.random.RandomState(7).randint(5, 700, (48, 2)))]
 
 
 def preprocess_image(h, w, seed):

@@ -291,6 +291,13 @@ def gen_preprocess():
         boxes = torch.from_numpy(scale_boxes_inputs(seed + 100) * (size / 640.0))
         d[name + "_boxes"] = ref_ops.scale_boxes(chw.shape[1:], boxes.clone(), (h, w)).numpy()
         print("preprocess", name, chw.shape)
+    import zlib
+    from oracle.cases import PREPROCESS_SWEEP
+    crc = []
+    for h, w, seed in PREPROCESS_SWEEP:
+        lb = LetterBox((96, 96), auto=False, stride=32)(image=preprocess_image(h, w, seed))
+        crc.append(zlib.crc32(np.ascontiguousarray(lb[..., ::-1].transpose(2, 0, 1)).tobytes()))
+    d["sweep_crc"] = np.array(crc, np.uint32)
     np.savez_compressed(os.path.join(GOLD, "preprocess.npz"), **d)
 
 

@@ -31,6 +31,11 @@ class YadPermuteEntry(C.Structure):
                 ("p2", C.c_int64), ("s0", C.c_int64), ("s1", C.c_int64), ("s2", C.c_int64), ("flip", C.c_int32), ("dst_f32", C.c_int32)]
 
 
+class YadImageDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("src_h", C.c_int32), ("src_w", C.c_int32), ("src_pitch", C.c_int32), ("new_w", C.c_int32),
+                ("new_h", C.c_int32), ("top", C.c_int32), ("left", C.c_int32), ("gain", C.c_float), ("pad_x", C.c_float), ("pad_y", C.c_float)]
+
+
 TP = C.POINTER(YadTensor)
 vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -65,6 +70,8 @@ SIGNATURES = {
                          C.POINTER(f32), i32, i32, i32, i32, vp, vp, i32, vp]),
     "yad_nms_workspace_bytes": (i64, [i32, i32, i32, i32, i32]),
     "yad_nms": (i32, [vp, i32, i32, i32, f32, f32, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
+    "yad_letterbox": (i32, [vp, i32, vp, i32, i32, i32, i32, vp]),
+    "yad_scale_boxes": (i32, [vp, i32, vp, i32, i32, vp, vp]),
     "yad_tal_workspace_bytes": (i64, [i32, i32, i32]),
     "yad_tal_assign": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "yad_loss_decode": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),

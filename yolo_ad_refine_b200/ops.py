@@ -287,6 +287,22 @@ def nms(pred, conf_thres, iou_thres, classes_mask, agnostic, multi_label, max_de
                         max_wh, _p(out), _p(out_idx), _p(out_count), _p(workspace), stream_ptr())
 
 
+def letterbox(desc, batch, out, out_h, out_w, pad_value=114, swap_rb=True):
+    """desc: uint8 device tensor holding `batch` yad_image_desc records; out: contiguous uint8 (>= batch, 3, out_h, out_w) device tensor"""
+    assert desc.is_cuda and desc.dtype == torch.uint8 and desc.numel() >= batch * 48 and out.is_cuda and out.dtype == torch.uint8
+    _call("yad_letterbox", _p(desc), batch, _p(out), out_h, out_w, pad_value, int(swap_rb), stream_ptr())
+
+
+def scale_boxes(det, count, desc, row_ld=None):
+    """det: fp32 (B, max_det, row) device tensor (rows x1, y1, x2, y2, ...), scaled and clipped in place for rows < count[b] (count None: all)"""
+    assert det.is_cuda and det.dtype == torch.float32 and det.dim() == 3
+    b, max_det, row = det.shape
+    row_ld = row_ld or det.stride(1)
+    assert (b <= 1 or det.stride(0) == max_det * row_ld) and det.stride(2) == 1
+    assert desc.is_cuda and desc.numel() >= b * 48 and (count is None or (count.dtype == torch.int32 and count.numel() >= b))
+    _call("yad_scale_boxes", _p(det), row_ld, _p(count), b, max_det, _p(desc), stream_ptr())
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # training path (include/yad.h, "Training path"): thin wrappers, same conventions as above
 # ----------------------------------------------------------------------------------------------------------------------
