@@ -120,3 +120,36 @@ def scale_boxes_inputs(seed=70, n=64):
     rs = np.random.RandomState(seed)
     b = rs.uniform(-20, 700, (n, 4)).astype(np.float32)
     return np.concatenate([np.minimum(b[:, :2], b[:, 2:]), np.maximum(b[:, :2], b[:, 2:])], 1)
+
+
+# validator matching cases: name -> (n detections, m labels, nc, jitter px, seed)
+MATCH_CASES = {
+    "typical": (120, 18, 5, 6.0, 80),
+    "crowded": (300, 64, 3, 10.0, 81),
+    "no_labels": (40, 0, 5, 4.0, 82),
+    "no_detections": (0, 12, 5, 4.0, 83),
+    "single_pair": (1, 1, 1, 2.0, 84),
+    "many_classes": (200, 40, 80, 5.0, 85),
+    "one_label_many_dets": (60, 1, 1, 8.0, 86),
+}
+
+
+def match_inputs(n, m, nc, jitter, seed):
+    """detections (n, 6) sorted by confidence descending (as NMS returns them) scattered around m ground-truth boxes; continuous fp32 -> no IoU ties"""
+    rs = np.random.RandomState(seed)
+    c = rs.uniform(60, 580, (m, 2))
+    wh = rs.uniform(20, 160, (m, 2))
+    gt = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    gt_cls = rs.randint(0, nc, m).astype(np.float32)
+    det = np.zeros((n, 6), np.float32)
+    if n:
+        if m:
+            src = rs.randint(0, m, n)
+            det[:, :4] = gt[src] + rs.normal(0, jitter, (n, 4))
+            det[:, 5] = np.where(rs.rand(n) < 0.8, gt_cls[src], rs.randint(0, nc, n))
+        else:
+            c = rs.uniform(60, 580, (n, 2))
+            det[:, :4] = np.concatenate([c - 30, c + 30], 1)
+            det[:, 5] = rs.randint(0, nc, n)
+        det[:, 4] = np.sort(rs.uniform(0.001, 1, n))[::-1]
+    return det.astype(np.float32), gt, gt_cls

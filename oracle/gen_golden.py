@@ -301,7 +301,27 @@ def gen_preprocess():
     np.savez_compressed(os.path.join(GOLD, "preprocess.npz"), **d)
 
 
+def gen_match():
+    """DetectionValidator._process_batch (models/yolo/detect/val.py:209-227 -> box_iou, utils/metrics.py:52-71 -> BaseValidator.match_predictions,
+    engine/validator.py:221-261) of the live reference on the seeded cases of oracle/cases.py: pins oracle/metrics.py and yad_match_predictions."""
+    from types import SimpleNamespace
+    from oracle.cases import MATCH_CASES, match_inputs
+    from ultralytics.engine.validator import BaseValidator
+    from ultralytics.utils.metrics import box_iou
+    me = SimpleNamespace(iouv=torch.linspace(0.5, 0.95, 10))
+    d = {}
+    for name, args in MATCH_CASES.items():
+        det, gt, gt_cls = (torch.from_numpy(a) for a in match_inputs(*args))
+        iou = box_iou(gt, det[:, :4])
+        d[name] = BaseValidator.match_predictions(me, det[:, 5], gt_cls, iou).numpy()
+        d[name + "_iou"] = iou.numpy()
+        print("match", name, d[name].shape, int(d[name].sum()))
+    np.savez_compressed(os.path.join(GOLD, "match_cases.npz"), **d)
+
+
 def main():
+    if sys.argv[1:] == ["match"]:
+        return gen_match()
     if sys.argv[1:] == ["preprocess"]:
         return gen_preprocess()
     if sys.argv[1:] == ["train_step"]:

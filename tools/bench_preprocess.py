@@ -2,7 +2,7 @@
 (`yad_letterbox`) and scale_boxes of a (64, 300, 6) NMS output (`yad_scale_boxes`).  Device-timed with CUDA events; one JSON line:
   value      images/s of the letterbox kernel alone, sources resident in HBM
   e2e        images/s through DevicePreprocessor.__call__ with the frames in pinned HOST memory (H2D of the raw frames inside the timed region)
-  roofline   algorithmic bytes (every source byte read once + 3 bytes written per output pixel) / kernel time vs the measured HBM peak
+  roofline   algorithmic bytes (every source pixel the taps address read once + 3 bytes written per output pixel) / kernel time vs the measured HBM peak
   cpu_baseline   the reference's own host path for the same frames: cv2.resize(INTER_LINEAR) + cv2.copyMakeBorder + stack / BGR->RGB / CHW
                  (LetterBox.__call__, data/augment.py:1588-1594; engine/predictor.py:127-129), timed on the box's host cores
 usage: python tools/bench_preprocess.py [--reps 50] [--batch 64] [--src 720x1280]"""
@@ -58,7 +58,7 @@ def timed(fn, reps):
 # the device buffer `desc` points into belongs to staging set 0; keep `pre` idle while the kernel-only loop runs
 ms_kernel = timed(lambda: ops.letterbox(desc, B, out, S, S, 114, True), args.reps)
 nw, nh, *_ = letterbox_params((sh, sw), S)
-alg_bytes = B * (sh * sw * 3 + 3 * S * S)
+alg_bytes = B * (min(sh * sw, 4 * nw * nh) * 3 + 3 * S * S)  # source pixels the 2 x 2 taps address (all of them up to a 2x reduction) + the output
 shapes = [f.shape[:2] for f in frames]
 for _ in range(2):  # fill both pinned staging sets once: the frames count as "decoded into pinned memory" (no host-side copy in the timed loop)
     vs = pre.staging_views(shapes)

@@ -12,10 +12,10 @@
 
 namespace {
 
-// tap indices and 11-bit coefficients of destination index d (cv::resize, INTER_LINEAR, CV_8U).  The source coordinate is evaluated in double
-// and rounded to float exactly as OpenCV does; the explicit _rn intrinsics keep nvcc from contracting the multiply-subtract into an FMA.
-__device__ __forceinline__ void linear_taps(int d, int src, int dst, bool horizontal, int& s0, int& s1, int& a0, int& a1) {
-  const double scale = __ddiv_rn((double)src, (double)dst);
+// tap indices and 11-bit coefficients of destination index d (cv::resize, INTER_LINEAR, CV_8U); scale = src / dst in double.  The source
+// coordinate is evaluated in double and rounded to float exactly as OpenCV does; the explicit _rn intrinsics keep nvcc from contracting the
+// multiply-subtract into an FMA.
+__device__ __forceinline__ void linear_taps(int d, int src, double scale, bool horizontal, int& s0, int& s1, int& a0, int& a1) {
   float f = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);
   int s = (int)floorf(f);
   f = __fsub_rn(f, (float)s);
@@ -29,41 +29,61 @@ __device__ __forceinline__ void linear_taps(int d, int src, int dst, bool horizo
   s1 = min(max(s + 1, 0), src - 1);
 }
 
+constexpr int LB_ROWS = 4;  // output rows per thread: the horizontal taps (the double-precision part) are computed once and reused
+
 __global__ void __launch_bounds__(128) letterbox_kernel(const yad_image_desc* __restrict__ desc, uint8_t* __restrict__ out, int out_h, int out_w,
                                                         int pad_value, int swap_rb) {
-  const int n = blockIdx.z, y = blockIdx.y;
+  const int n = blockIdx.z, y_begin = blockIdx.y * LB_ROWS;
   const int x0 = (blockIdx.x * 128 + threadIdx.x) * 4;
   if (x0 >= out_w) return;
   const yad_image_desc d = desc[n];
   const uint32_t pv = (uint32_t)(pad_value & 0xff) * 0x01010101u;
-  uint32_t o[3] = {pv, pv, pv};
-  const int yy = y - d.top;
-  if (yy >= 0 && yy < d.new_h && x0 + 3 >= d.left && x0 < d.left + d.new_w) {
-    int sy0, sy1, b0, b1;
-    linear_taps(yy, d.src_h, d.new_h, false, sy0, sy1, b0, b1);
-    const uint8_t* __restrict__ r0 = d.src + (int64_t)sy0 * d.src_pitch;
-    const uint8_t* __restrict__ r1 = d.src + (int64_t)sy1 * d.src_pitch;
+  const int64_t plane = (int64_t)out_h * out_w;
+  uint8_t* p = out + (int64_t)n * 3 * plane + x0;
+  const bool in_x = x0 + 3 >= d.left && x0 < d.left + d.new_w;
+  int o0[4], o1[4], a0[4], a1[4];  // byte offsets of the two taps inside a source row, their coefficients (0 / 0 outside the resized region)
+  if (in_x) {
+    const double sx = __ddiv_rn((double)d.src_w, (double)d.new_w);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int xx = x0 + i - d.left;
+      o0[i] = -1;
       if (xx < 0 || xx >= d.new_w) continue;
-      int sx0, sx1, a0, a1;
-      linear_taps(xx, d.src_w, d.new_w, true, sx0, sx1, a0, a1);
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        const int S0 = (int)__ldg(r0 + sx0 * 3 + c) * a0 + (int)__ldg(r0 + sx1 * 3 + c) * a1;
-        const int S1 = (int)__ldg(r1 + sx0 * 3 + c) * a0 + (int)__ldg(r1 + sx1 * 3 + c) * a1;
-        int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
-        v = min(max(v, 0), 255);
-        const int cc = swap_rb ? 2 - c : c;
-        o[cc] = (o[cc] & ~(0xffu << (8 * i))) | ((uint32_t)v << (8 * i));
-      }
+      int s0, s1;
+      linear_taps(xx, d.src_w, sx, true, s0, s1, a0[i], a1[i]);
+      o0[i] = s0 * 3;
+      o1[i] = s1 * 3;
     }
   }
-  const int64_t plane = (int64_t)out_h * out_w;
-  uint8_t* p = out + (int64_t)n * 3 * plane + (int64_t)y * out_w + x0;
+  const double sy = __ddiv_rn((double)d.src_h, (double)d.new_h);
 #pragma unroll
-  for (int c = 0; c < 3; c++) *reinterpret_cast<uint32_t*>(p + c * plane) = o[c];
+  for (int r = 0; r < LB_ROWS; r++) {
+    const int y = y_begin + r;
+    if (y >= out_h) break;
+    uint32_t o[3] = {pv, pv, pv};
+    const int yy = y - d.top;
+    if (in_x && yy >= 0 && yy < d.new_h) {
+      int sy0, sy1, b0, b1;
+      linear_taps(yy, d.src_h, sy, false, sy0, sy1, b0, b1);
+      const uint8_t* __restrict__ r0 = d.src + (int64_t)sy0 * d.src_pitch;
+      const uint8_t* __restrict__ r1 = d.src + (int64_t)sy1 * d.src_pitch;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (o0[i] < 0) continue;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const int S0 = (int)__ldg(r0 + o0[i] + c) * a0[i] + (int)__ldg(r0 + o1[i] + c) * a1[i];
+          const int S1 = (int)__ldg(r1 + o0[i] + c) * a0[i] + (int)__ldg(r1 + o1[i] + c) * a1[i];
+          int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+          v = min(max(v, 0), 255);
+          const int cc = swap_rb ? 2 - c : c;
+          o[cc] = (o[cc] & ~(0xffu << (8 * i))) | ((uint32_t)v << (8 * i));
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) *reinterpret_cast<uint32_t*>(p + c * plane + (int64_t)y * out_w) = o[c];
+  }
 }
 
 __global__ void scale_boxes_kernel(float* __restrict__ det, int row_ld, const int32_t* __restrict__ count, int max_det,
@@ -93,7 +113,7 @@ int yad_letterbox(const yad_image_desc* desc, int batch, uint8_t* out, int out_h
   YAD_CHECK(out_w > 0 && out_w % 4 == 0, "letterbox: out_w %d must be a positive multiple of 4", out_w);
   YAD_CHECK(((uintptr_t)out & 3) == 0, "letterbox: out must be 4-byte aligned");
   if (batch == 0) return 0;
-  const dim3 grid(cdiv(out_w / 4, 128), out_h, batch);
+  const dim3 grid(cdiv(out_w / 4, 128), cdiv(out_h, LB_ROWS), batch);
   letterbox_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(desc, out, out_h, out_w, pad_value, swap_rb);
   YAD_LAUNCH_CHECK("letterbox");
   return 0;

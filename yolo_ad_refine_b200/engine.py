@@ -125,22 +125,23 @@ class RefineEngine:
         return [det[i, :k] for i, k in enumerate(counts)]
 
     def detect_images(self, images):
-        """`predict()` for a list of up to `batch` HWC uint8 BGR images (what the reference's loaders hand to BasePredictor.preprocess):
+        """`predict()` for a list of exactly `batch` HWC uint8 BGR images (what the reference's loaders hand to BasePredictor.preprocess):
         device LetterBox + BGR->RGB + CHW (yad_letterbox) straight into the engine's static uint8 input -> forward -> decode -> NMS -> scale_boxes
         back to every source image's own coordinates (yad_scale_boxes; models/yolo/detect/predict.py:36-41).  Returns the list of (k, 6) tensors
-        [x1, y1, x2, y2, conf, cls] the reference wraps into `Results`.  Needs an engine built with input_u8=True."""
+        [x1, y1, x2, y2, conf, cls] the reference wraps into `Results`.  Needs an engine built with input_u8=True.  The list must fill the engine's
+        batch: MLCA's global branch pools over the batch axis (block.py:1575-1579), so a partly stale static input would change every image's result."""
         if self.img.dtype != torch.uint8:
             raise RuntimeError("detect_images needs an engine built with input_u8=True")
-        if not 0 < len(images) <= self.batch:
-            raise ValueError(f"expected 1..{self.batch} images, got {len(images)}")
+        if len(images) != self.batch:
+            raise ValueError(f"expected {self.batch} images (the engine's batch), got {len(images)}")
         if not hasattr(self, "_pre"):
             from .preprocess import DevicePreprocessor
             self._pre = DevicePreprocessor((self.h, self.w), stride=max(self.strides), auto=False, device=self.device)
         pb = self._pre(images, out=self.img)
         _, _, det, _, count = self.step()
         self.join()
-        ops.scale_boxes(det[:len(images)], count, pb.desc)
-        counts = count[:len(images)].tolist()
+        ops.scale_boxes(det, count, pb.desc)
+        counts = count.tolist()
         return [det[i, :k] for i, k in enumerate(counts)]
 
     def detect_many(self, host_batches, det_host=None, cnt_host=None):
