@@ -153,3 +153,52 @@ def match_inputs(n, m, nc, jitter, seed):
             det[:, 5] = rs.randint(0, nc, n)
         det[:, 4] = np.sort(rs.uniform(0.001, 1, n))[::-1]
     return det.astype(np.float32), gt, gt_cls
+
+
+# validation-set cases (update_metrics -> get_stats -> ap_per_class): name -> (images, nc, max detections / image,
+# max labels / image, jitter px, seed)
+VAL_CASES = {
+    "small": (6, 3, 40, 6, 5.0, 90),
+    "coco_like": (48, 80, 300, 24, 6.0, 91),
+    "few_classes_many_dets": (32, 4, 300, 40, 9.0, 92),
+    "sparse": (12, 20, 12, 3, 4.0, 93),
+}
+
+
+def val_inputs(n_img, nc, max_det, max_lab, jitter, seed, imgsz=640):
+    """A seeded validation set in the layout DetectionValidator.update_metrics sees (models/yolo/detect/val.py:126-176): per image the NMS output
+    in letterboxed-image pixels (k_i, 6) sorted by confidence, the labels as normalised xywh of the letterboxed image + batch_idx + cls (the
+    collated batch dict), ori_shape and ratio_pad = ((gain, gain), (left, top)) as data/base.py:295 + LetterBox (data/augment.py:1590-1591) set them.
+    Some images have no labels, some no detections.  Continuous fp32 coordinates and confidences: no ties."""
+    rs = np.random.RandomState(seed)
+    dets, ori, ratio_pad, bboxes, cls, bidx = [], [], [], [], [], []
+    for i in range(n_img):
+        h0, w0 = int(rs.randint(240, 1100)), int(rs.randint(240, 1100))
+        gain = min(imgsz / h0, imgsz / w0)
+        nw, nh = int(round(w0 * gain)), int(round(h0 * gain))
+        left, top = int(round((imgsz - nw) / 2 - 0.1)), int(round((imgsz - nh) / 2 - 0.1))
+        m = 0 if i % 7 == 3 else int(rs.randint(1, max_lab + 1))
+        n = 0 if i % 11 == 5 else int(rs.randint(1, max_det + 1))
+        c = np.stack([rs.uniform(left + 20, left + nw - 20, m), rs.uniform(top + 20, top + nh - 20, m)], 1)
+        wh = rs.uniform(12, 0.45 * min(nw, nh), (m, 2))
+        gt = np.concatenate([c - wh / 2, c + wh / 2], 1)
+        gt_cls = rs.randint(0, nc, m)
+        det = np.zeros((n, 6), np.float32)
+        if n:
+            if m:
+                src = rs.randint(0, m, n)
+                det[:, :4] = gt[src] + rs.normal(0, jitter, (n, 4))
+                det[:, 5] = np.where(rs.rand(n) < 0.75, gt_cls[src], rs.randint(0, nc, n))
+            else:
+                cc = rs.uniform(60, 580, (n, 2))
+                det[:, :4] = np.concatenate([cc - 30, cc + 30], 1)
+                det[:, 5] = rs.randint(0, nc, n)
+            det[:, 4] = np.sort(rs.uniform(0.001, 1, n))[::-1]
+        dets.append(det.astype(np.float32))
+        ori.append((h0, w0))
+        ratio_pad.append(((gain, gain), (left, top)))
+        bboxes.append(np.concatenate([(gt[:, :2] + gt[:, 2:]) / 2, gt[:, 2:] - gt[:, :2]], 1) / imgsz)
+        cls.append(gt_cls)
+        bidx.append(np.full(m, i))
+    return dict(dets=dets, ori_shape=ori, ratio_pad=ratio_pad, bboxes=np.concatenate(bboxes).astype(np.float32),
+                cls=np.concatenate(cls).astype(np.float32), batch_idx=np.concatenate(bidx).astype(np.int64), imgsz=imgsz)

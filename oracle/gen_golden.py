@@ -319,9 +319,52 @@ def gen_match():
     np.savez_compressed(os.path.join(GOLD, "match_cases.npz"), **d)
 
 
+def gen_val():
+    """The live reference's validation statistics on the seeded sets of oracle/cases.py: DetectionValidator._prepare_batch / _prepare_pred /
+    _process_batch per image exactly as update_metrics drives them (models/yolo/detect/val.py:104-176), then ap_per_class (utils/metrics.py:1144-1231)
+    on the concatenated stats as get_stats / DetMetrics.process do (val.py:183-191).  Pins oracle/metrics.py and the yad_val_* kernels."""
+    from types import SimpleNamespace
+    from oracle.cases import VAL_CASES, val_inputs
+    from ultralytics.engine.validator import BaseValidator
+    from ultralytics.models.yolo.detect.val import DetectionValidator
+    from ultralytics.utils.metrics import ap_per_class
+    me = SimpleNamespace(iouv=torch.linspace(0.5, 0.95, 10), device=torch.device("cpu"))
+    me.match_predictions = lambda *a: BaseValidator.match_predictions(me, *a)
+    d = {}
+    for name, args in VAL_CASES.items():
+        v = val_inputs(*args)
+        batch = dict(batch_idx=torch.from_numpy(v["batch_idx"]), cls=torch.from_numpy(v["cls"])[:, None], bboxes=torch.from_numpy(v["bboxes"]),
+                     ori_shape=v["ori_shape"], ratio_pad=v["ratio_pad"], img=torch.zeros(len(v["dets"]), 3, v["imgsz"], v["imgsz"]))
+        tp, conf, pcls, tcls, labels = [], [], [], [], []
+        for si, det in enumerate(v["dets"]):
+            pb = DetectionValidator._prepare_batch(me, si, batch)
+            cls, bbox = pb.pop("cls"), pb.pop("bbox")
+            labels.append(bbox.numpy().reshape(-1, 4))
+            if len(det) == 0:
+                if len(cls):
+                    tcls.append(cls.numpy())
+                continue
+            predn = DetectionValidator._prepare_pred(me, torch.from_numpy(det), pb)
+            t = DetectionValidator._process_batch(me, predn, bbox, cls).numpy() if len(cls) else np.zeros((len(det), 10), bool)
+            tp.append(t), conf.append(predn[:, 4].numpy()), pcls.append(predn[:, 5].numpy()), tcls.append(cls.numpy())
+        tp, conf, pcls, tcls = np.concatenate(tp), np.concatenate(conf), np.concatenate(pcls), np.concatenate(tcls)
+        r = ap_per_class(tp, conf, pcls, tcls)
+        d[name + "_labels"] = np.concatenate(labels)
+        d[name + "_tp"] = np.packbits(tp, axis=0)
+        d[name + "_n"] = np.array(len(tp))
+        for k, a in zip(("tpn", "fpn", "p", "r", "f1", "ap", "classes", "p_curve", "r_curve", "f1_curve"), r[:10]):
+            d[f"{name}_{k}"] = np.asarray(a)[:, ::8] if k.endswith("curve") else np.asarray(a)   # curves: every 8th of the 1000 columns
+        from ultralytics.utils.metrics import smooth
+        d[name + "_f1_index"] = np.array(smooth(r[9].mean(0), 0.1).argmax())
+        print("val", name, tp.shape, "mAP50 %.4f mAP %.4f" % (r[5][:, 0].mean(), r[5].mean()))
+    np.savez_compressed(os.path.join(GOLD, "val_cases.npz"), **d)
+
+
 def main():
     if sys.argv[1:] == ["match"]:
         return gen_match()
+    if sys.argv[1:] == ["val"]:
+        return gen_val()
     if sys.argv[1:] == ["preprocess"]:
         return gen_preprocess()
     if sys.argv[1:] == ["train_step"]:
