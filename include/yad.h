@@ -191,6 +191,34 @@ int yad_letterbox(const yad_image_desc* desc, int batch, uint8_t* out, int out_h
  *    modified in place for rows < count[b] (count NULL: all max_det rows).  fp32 sub / div / clamp in the reference's order. */
 int yad_scale_boxes(float* det, int row_ld, const int32_t* count, int batch, int max_det, const yad_image_desc* desc, void* stream);
 
+/* -- f2: validator statistics on the device.
+ *    yad_val_labels replaces DetectionValidator._prepare_batch (models/yolo/detect/val.py:104-116): labels of a whole batch, normalised xywh of the
+ *    letterboxed image (m, 4) + batch_idx int32 (m) -> xyxy pixels of the native image (xywh2xyxy utils/ops.py:425-431, x imgsz, scale_boxes with
+ *    ratio_pad :112-123 = desc[b].gain / pad_x / pad_y, clip_boxes :327-331 to desc[b].src_w / src_h).  fp32 in the reference's operation order.
+ *    yad_val_match replaces DetectionValidator._process_batch (val.py:209-227) = box_iou (utils/metrics.py:52-71) + BaseValidator.match_predictions
+ *    (engine/validator.py:221-261, numpy branch) for every image of a batched NMS output (det / count as yad_nms + yad_scale_boxes leave them):
+ *    gt_xyxy fp32 (M, 4), gt_cls fp32 (M) grouped by image with gt_offset int32 [batch + 1]; iouv fp32 [niou] (niou <= 12);
+ *    correct uint8 [batch][max_det][niou], rows < count[b] written (all zero for an image without labels).  Equal IoUs of one detection with two
+ *    labels go to the lower label index (the reference's unstable argsort leaves them unspecified).  max_labels_per_image sizes the shared memory.
+ *    stat_conf / stat_cls fp32 [batch][max_det] (both or neither NULL): the conf / pred_cls rows update_metrics appends to its statistics
+ *    (val.py:152-153); padding rows >= count[b] get class -1 and an all-zero correct row, which yad_val_ap ignores. */
+int yad_val_labels(const float* bboxes_xywhn, const int32_t* batch_idx, int m, int img_h, int img_w, const yad_image_desc* desc, float* out_xyxy,
+                   void* stream);
+int yad_val_match(const float* det, int row_ld, const int32_t* count, int batch, int max_det, const float* gt_xyxy, const float* gt_cls,
+                  const int32_t* gt_offset, int max_labels_per_image, const float* iouv, int niou, uint8_t* correct, float* stat_conf,
+                  float* stat_cls, void* stream);
+/*    yad_val_ap replaces ap_per_class (utils/metrics.py:1144-1231; compute_ap :1112-1141; smooth :1054-1059) on the concatenated statistics of a
+ *    validation run (DetectionValidator.get_stats, val.py:183-191): tp uint8 (n, niou), conf fp32 (n), pred_cls fp32 (n), target_cls fp32 (m).
+ *    Outputs are indexed by CLASS ID 0..nc-1 (the reference compacts to the classes that have labels: nt[c] > 0): ap fp64 (nc, niou),
+ *    p_curve / r_curve / f1_curve fp64 (nc, 1000), nt int32 (nc) labels per class, summary fp64 (nc, 5) = p, r, f1, tp, fp at the max-F1 index,
+ *    f1_index int32.  fp64 arithmetic in numpy's order (np.interp's index rule, np.trapz's pairwise sum); equal confidences keep their input
+ *    order (stable sort; np.argsort leaves them unspecified).  The ordering step is cub::DeviceRadixSort on (class, confidence) keys.
+ *    workspace: yad_val_ap_workspace_bytes(n, nc, niou) bytes (-1 on error). */
+int64_t yad_val_ap_workspace_bytes(int64_t n, int nc, int niou);
+int yad_val_ap(const uint8_t* tp, const float* conf, const float* pred_cls, int64_t n, const float* target_cls, int64_t m, int nc, int niou,
+               double eps, double* ap, double* p_curve, double* r_curve, double* f1_curve, int32_t* nt, double* summary, int32_t* f1_index,
+               void* workspace, void* stream);
+
 /* -- a12: TaskAlignedAssigner.forward (utils/tal.py:38-88): one CTA per (image, gt) for the top-k, one CTA per image for the rest.
  *    pd_scores fp32 (B,N,nc) sigmoid scores, pd_bboxes fp32 (B,N,4) xyxy px, anc fp32 (N,2) px, gt_labels fp32 (B,M), gt_bboxes
  *    fp32 (B,M,4), mask_gt fp32 (B,M).  Outputs: target_labels int64 (B,N), target_bboxes fp32 (B,N,4), target_scores fp32 (B,N,nc),

@@ -72,6 +72,10 @@ SIGNATURES = {
     "yad_nms": (i32, [vp, i32, i32, i32, f32, f32, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
     "yad_letterbox": (i32, [vp, i32, vp, i32, i32, i32, i32, vp]),
     "yad_scale_boxes": (i32, [vp, i32, vp, i32, i32, vp, vp]),
+    "yad_val_labels": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
+    "yad_val_match": (i32, [vp, i32, vp, i32, i32, vp, vp, vp, i32, vp, i32, vp, vp, vp, vp]),
+    "yad_val_ap_workspace_bytes": (i64, [i64, i32, i32]),
+    "yad_val_ap": (i32, [vp, vp, vp, i64, vp, i64, i32, i32, C.c_double, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "yad_tal_workspace_bytes": (i64, [i32, i32, i32]),
     "yad_tal_assign": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "yad_loss_decode": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),

@@ -303,6 +303,47 @@ def scale_boxes(det, count, desc, row_ld=None):
     _call("yad_scale_boxes", _p(det), row_ld, _p(count), b, max_det, _p(desc), stream_ptr())
 
 
+def val_labels(bboxes_xywhn, batch_idx, img_hw, desc, out):
+    """bboxes_xywhn fp32 (m, 4), batch_idx int32 (m), desc: yad_image_desc table (uint8 device tensor) -> out fp32 (m, 4) native-image xyxy"""
+    m = bboxes_xywhn.shape[0]
+    assert bboxes_xywhn.is_cuda and bboxes_xywhn.dtype == torch.float32 and bboxes_xywhn.is_contiguous() and out.is_contiguous()
+    assert batch_idx.is_cuda and batch_idx.dtype == torch.int32 and batch_idx.numel() == m and out.shape == (m, 4) and out.dtype == torch.float32
+    _call("yad_val_labels", _p(bboxes_xywhn), _p(batch_idx), m, int(img_hw[0]), int(img_hw[1]), _p(desc), _p(out), stream_ptr())
+
+
+def val_match(det, count, gt_xyxy, gt_cls, gt_offset, max_labels_per_image, iouv, correct, stat_conf=None, stat_cls=None):
+    """det fp32 (B, max_det, >= 6), count int32 (B) or None, gt_* grouped by image through gt_offset int32 (B + 1), iouv fp32 (niou)
+    -> correct uint8 (B, max_det, niou)"""
+    b, max_det, _ = det.shape
+    assert det.is_cuda and det.dtype == torch.float32 and det.stride(2) == 1 and (b <= 1 or det.stride(0) == max_det * det.stride(1))
+    assert gt_offset.dtype == torch.int32 and gt_offset.numel() == b + 1 and iouv.dtype == torch.float32 and correct.dtype == torch.uint8
+    assert correct.is_contiguous() and correct.shape == (b, max_det, iouv.numel())
+    assert gt_xyxy.dtype == torch.float32 and gt_cls.dtype == torch.float32 and gt_xyxy.is_contiguous() and gt_cls.is_contiguous()
+    assert count is None or (count.dtype == torch.int32 and count.numel() >= b)
+    for t in (stat_conf, stat_cls):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == b * max_det)
+    _call("yad_val_match", _p(det), det.stride(1), _p(count), b, max_det, _p(gt_xyxy), _p(gt_cls), _p(gt_offset), int(max_labels_per_image), _p(iouv),
+          iouv.numel(), _p(correct), _p(stat_conf), _p(stat_cls), stream_ptr())
+
+
+def val_ap_workspace_bytes(n, nc, niou):
+    r = int(lib().yad_val_ap_workspace_bytes(n, nc, niou))
+    if r < 0:
+        raise RuntimeError("yad_val_ap_workspace_bytes failed")
+    return r
+
+
+def val_ap(tp, conf, pred_cls, target_cls, nc, eps, ap, p_curve, r_curve, f1_curve, nt, summary, f1_index, workspace):
+    n, niou = tp.shape
+    assert tp.dtype == torch.uint8 and tp.is_contiguous() and conf.dtype == torch.float32 and pred_cls.dtype == torch.float32
+    assert conf.numel() == n and pred_cls.numel() == n and target_cls.dtype == torch.float32
+    assert ap.dtype == torch.float64 and ap.shape == (nc, niou) and all(t.dtype == torch.float64 and t.shape == (nc, 1000) and t.is_contiguous()
+                                                                       for t in (p_curve, r_curve, f1_curve))
+    assert nt.dtype == torch.int32 and nt.numel() == nc and summary.dtype == torch.float64 and summary.shape == (nc, 5) and f1_index.dtype == torch.int32
+    _call("yad_val_ap", _p(tp), _p(conf), _p(pred_cls), n, _p(target_cls), target_cls.numel(), nc, niou, float(eps), _p(ap), _p(p_curve), _p(r_curve),
+          _p(f1_curve), _p(nt), _p(summary), _p(f1_index), _p(workspace), stream_ptr())
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # training path (include/yad.h, "Training path"): thin wrappers, same conventions as above
 # ----------------------------------------------------------------------------------------------------------------------
