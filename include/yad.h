@@ -64,6 +64,9 @@ typedef struct {
 
 const char* yad_last_error(void);
 int yad_version(void);
+/* Programmatic dependent launch (griddepcontrol) between consecutive kernels of a stream: OFF by default (environment YAD_PDL=1 or yad_set_pdl(1) turns it on);
+ * returns the previous setting.  Takes effect for launches (and graph captures) made after the call. */
+int yad_set_pdl(int enabled);
 /* 1 when the running device is sm_100 (tcgen05 path usable) */
 int yad_device_is_sm100(void);
 

@@ -43,6 +43,7 @@ vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
     "yad_last_error": (C.c_char_p, []),
     "yad_version": (i32, []),
+    "yad_set_pdl": (i32, [i32]),
     "yad_device_is_sm100": (i32, []),
     "yad_conv2d": (i32, [TP, vp, C.POINTER(YadConvDesc), C.POINTER(YadEpilogue), TP, i32, vp]),
     "yad_dwconv": (i32, [TP, vp, vp, vp, vp, i32, i32, i32, vp, i32, TP, i32, vp]),

@@ -1,5 +1,6 @@
 // libyad.so: error plumbing, version / device queries and the conv dispatcher.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -12,6 +13,15 @@ void yad_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static int g_pdl = -1;
+int yad_pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("YAD_PDL");
+    g_pdl = (e && e[0] == '1') ? 1 : 0;  // measured neutral on the graph-replayed steps: off unless asked for
+  }
+  return g_pdl;
+}
+
 int yad_conv2d_simt(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, int dtype,
                     void* stream);
 int yad_conv2d_tc(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream);
@@ -22,6 +32,11 @@ extern "C" {
 
 const char* yad_last_error(void) { return g_err; }
 int yad_version(void) { return 100; }
+int yad_set_pdl(int enabled) {
+  const int old = yad_pdl_enabled();
+  g_pdl = enabled ? 1 : 0;
+  return old;
+}
 
 int yad_device_is_sm100(void) {
   int dev = 0, major = 0;

@@ -9,6 +9,7 @@ namespace {
 template <typename T>
 __global__ void tssa_kernel(const T* __restrict__ qkv, int64_t ld, int Tn, int c, int heads, const float* __restrict__ temps,
                             T* __restrict__ out, int64_t out_ld, int Tout, int tok_off) {
+  pdl_sync();
   extern __shared__ float sm[];  // pi[Tn], dots[d], red[32]
   const int d = c / heads, n = blockIdx.x / heads, h = blockIdx.x % heads;
   float* pi = sm;
@@ -88,6 +89,7 @@ constexpr int HD = 64, QB = 128, KB = 32;
 template <typename T>
 __global__ void __launch_bounds__(QB) mha_kernel(const T* __restrict__ qkv, int64_t ld, int Tn, int c, int heads, T* __restrict__ out,
                                                  int64_t out_ld, float scale) {
+  pdl_sync();
   __shared__ __align__(16) float Ks[KB][HD];
   __shared__ __align__(16) float Vs[KB][HD];
   const int n = blockIdx.y / heads, h = blockIdx.y % heads;
@@ -191,6 +193,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 __global__ void __launch_bounds__(128) mha_mma_kernel(const bf16* __restrict__ qkv, int64_t ld, int Tn, int c, int heads, bf16* __restrict__ out,
                                                       int64_t out_ld, float scale_log2e) {
+  pdl_sync();
   __shared__ __align__(16) bf16 Ks[2][FA_K * FA_PITCH];  // double buffer: tile k + 1 streams in (cp.async) while tile k is consumed
   __shared__ __align__(16) bf16 Vs[2][FA_K * FA_PITCH];
   const int n = blockIdx.y / heads, h = blockIdx.y % heads;
@@ -312,7 +315,7 @@ int yad_tssa(const yad_tensor* qkv, const float* temps, int heads, const yad_ten
   cudaStream_t st = (cudaStream_t)stream;
   YAD_DISPATCH_DTYPE(dtype, {
     if (smem > 48 * 1024) cudaFuncSetAttribute(tssa_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    tssa_kernel<T><<<qkv->n * heads, 256, smem, st>>>((const T*)qkv->ptr, qkv->ld, Tn, c, heads, temps, (T*)out->ptr, out->ld, Tout,
+    YAD_LAUNCH(tssa_kernel<T>, qkv->n * heads, 256, smem, st, (const T*)qkv->ptr, qkv->ld, Tn, c, heads, temps, (T*)out->ptr, out->ld, Tout,
                                                      out_token_offset);
   })
   YAD_LAUNCH_CHECK("tssa");
@@ -327,12 +330,12 @@ int yad_mha(const yad_tensor* qkv, int heads, const yad_tensor* out, int dtype, 
   const float scale = 1.0f / sqrtf((float)HD);
   if (dtype == YAD_BF16) {  // tensor-core path
     dim3 g2((Tn + FA_Q - 1) / FA_Q, qkv->n * heads);
-    mha_mma_kernel<<<g2, 128, 0, st>>>((const bf16*)qkv->ptr, qkv->ld, Tn, c, heads, (bf16*)out->ptr, out->ld, scale * 1.44269504088896340736f);
+    YAD_LAUNCH(mha_mma_kernel, g2, 128, 0, st, (const bf16*)qkv->ptr, qkv->ld, Tn, c, heads, (bf16*)out->ptr, out->ld, scale * 1.44269504088896340736f);
     YAD_LAUNCH_CHECK("mha");
     return 0;
   }
   dim3 grid((Tn + QB - 1) / QB, qkv->n * heads);
-  YAD_DISPATCH_DTYPE(dtype, mha_kernel<T><<<grid, QB, 0, st>>>((const T*)qkv->ptr, qkv->ld, Tn, c, heads, (T*)out->ptr, out->ld, scale);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(mha_kernel<T>, grid, QB, 0, st, (const T*)qkv->ptr, qkv->ld, Tn, c, heads, (T*)out->ptr, out->ld, scale);)
   YAD_LAUNCH_CHECK("mha");
   return 0;
 }

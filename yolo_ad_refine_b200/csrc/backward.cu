@@ -87,6 +87,7 @@ template <typename T, int ACT>
 __global__ void __launch_bounds__(TPB, 3) norm_bwd_reduce_kernel(yad_tensor x, yad_tensor dy, const double* __restrict__ stats, int groups, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float eps, int act, double* __restrict__ sums,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_sync();
   extern __shared__ float sm[];  // mean[c], rstd[c], A[c], B[c]
   const int c = x.c, n = blockIdx.y, oct = c >> 3, cpg = c / groups;
   const int64_t hw = (int64_t)x.h * x.w;
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(TPB, 3) norm_bwd_reduce_kernel(yad_tensor x, y
 template <typename T, int ACT>
 __global__ void __launch_bounds__(TPB, 3) norm_bwd_apply_kernel(yad_tensor x, yad_tensor dy, const double* __restrict__ stats, const double* __restrict__ sums, int groups,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act, yad_tensor dx, int acc) {
+  pdl_sync();
   extern __shared__ float sm[];  // mean[c], rstd[c], k1[c] = S1/cnt, k2[c] = S2/cnt
   const int c = x.c, n = blockIdx.y, oct = c >> 3, cpg = c / groups;
   const int64_t hw = (int64_t)x.h * x.w;
@@ -288,6 +290,7 @@ __global__ void __launch_bounds__(TPB, 3) norm_bwd_apply_kernel(yad_tensor x, ya
 // BatchNorm running statistics (nn.BatchNorm2d in train(): momentum update with the unbiased batch variance)
 __global__ void bn_running_kernel(const double* __restrict__ stats, int c, double cnt, float momentum, float* __restrict__ rmean,
                                   float* __restrict__ rvar) {
+  pdl_sync();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   const double mean = stats[ch * 2] / cnt;
@@ -300,6 +303,7 @@ __global__ void bn_running_kernel(const double* __restrict__ stats, int c, doubl
 // dx = dy * f'(.) expressed with the OUTPUT y (sigmoid: y(1-y); relu: y > 0) -- conv epilogue activations keep only y
 template <typename T>
 __global__ void act_bwd_kernel(yad_tensor y, yad_tensor dy, int act, yad_tensor dx, int acc) {
+  pdl_sync();
   const int oct = y.c >> 3;
   const int64_t total = (int64_t)y.n * y.h * y.w * oct;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
@@ -320,6 +324,7 @@ __global__ void act_bwd_kernel(yad_tensor y, yad_tensor dy, int act, yad_tensor 
 // out[c] += sum over all pixels of a[p][c] (* b[p][c] when b != null).  Bias gradients, per-channel parameter gradients.
 template <typename T>
 __global__ void colsum_kernel(yad_tensor a, const T* __restrict__ b, int b_ld, float* __restrict__ out) {
+  pdl_sync();
   extern __shared__ float sm[];
   const int c = a.c, oct = c >> 3;
   for (int i = threadIdx.x; i < c; i += blockDim.x) sm[i] = 0.f;
@@ -370,6 +375,7 @@ __global__ void colsum_kernel(yad_tensor a, const T* __restrict__ b, int b_ld, f
 template <typename T>
 __global__ void dot_kernel(yad_tensor a, const T* __restrict__ b, int b_ld, int per_image, float scale, const float* __restrict__ img_div,
                            float* __restrict__ out) {
+  pdl_sync();
   __shared__ float red[32];
   const int oct = a.c >> 3, n = blockIdx.y;
   const int64_t hw = (int64_t)a.h * a.w;
@@ -396,6 +402,7 @@ __global__ void dot_kernel(yad_tensor a, const T* __restrict__ b, int b_ld, int 
 // y[p][0] = sum_c a[p][c] * b[p][c], y[p][1..7] = 0   (gradient of a per-pixel scalar gate; y is an 8-channel view)
 template <typename T>
 __global__ void dot_pixel_kernel(yad_tensor a, const T* __restrict__ b, int b_ld, yad_tensor y) {
+  pdl_sync();
   const int64_t npix = (int64_t)a.n * a.h * a.w;
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int64_t p = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); p < npix; p += (int64_t)gridDim.x * wpb) {
@@ -419,6 +426,7 @@ __global__ void dot_pixel_kernel(yad_tensor a, const T* __restrict__ b, int b_ld
 template <typename T>
 __global__ void bcast_add_kernel(yad_tensor dx, const float* __restrict__ img, float s_img, const T* __restrict__ row, int row_ld, float s_row,
                                  const T* __restrict__ col, int col_ld, float s_col, int acc) {
+  pdl_sync();
   const int oct = dx.c >> 3;
   const int64_t total = (int64_t)dx.n * dx.h * dx.w * oct;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
@@ -456,6 +464,7 @@ __global__ void bcast_add_kernel(yad_tensor dx, const float* __restrict__ img, f
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void rowcol_gate_bwd_g_kernel(yad_tensor x, bool has_x, yad_tensor gh, yad_tensor gw, yad_tensor dy, yad_tensor dgh, yad_tensor dgw) {
+  pdl_sync();
   extern __shared__ float sm[];
   const int n = blockIdx.y, c = dy.c, oct = c >> 3;
   const bool is_col = blockIdx.z == 1;
@@ -516,6 +525,7 @@ __global__ void rowcol_gate_bwd_g_kernel(yad_tensor x, bool has_x, yad_tensor gh
 
 template <typename T>
 __global__ void rowcol_gate_bwd_x_kernel(yad_tensor gh, yad_tensor gw, yad_tensor dy, yad_tensor dx, int acc) {
+  pdl_sync();
   const int oct = dy.c >> 3;
   const int64_t total = (int64_t)dy.n * dy.h * dy.w * oct;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
@@ -539,6 +549,7 @@ __global__ void rowcol_gate_bwd_x_kernel(yad_tensor gh, yad_tensor gw, yad_tenso
 // grid (25, n): datt[n][bin][c] = sum over pixels p whose un-pool range contains `bin` of dy[p] * x[p] / cnt(p)
 template <typename T>
 __global__ void mlca_bwd_datt_kernel(yad_tensor x, yad_tensor dy, int ls, float* __restrict__ datt) {
+  pdl_sync();
   extern __shared__ float sm[];
   const int n = blockIdx.y, c = x.c, oct = c >> 3, bin = blockIdx.x, by = bin / ls, bx = bin % ls;
   for (int i = threadIdx.x; i < c; i += blockDim.x) sm[i] = 0.f;
@@ -571,6 +582,7 @@ __global__ void mlca_bwd_datt_kernel(yad_tensor x, yad_tensor dy, int ls, float*
 // dwl[j] += sum dzl[i] * seq[i+j-r]; dlocal[n][q] = sum_j wl[j] dzl[q-j+r];  dG[by][c] += (1-lw) * sum_bx datt[n][by,bx][c]
 __global__ void mlca_att_bwd_a_kernel(const float* __restrict__ local, const float* __restrict__ datt, const float* __restrict__ wl, int k, float lw,
                                       int c, int ls, float* __restrict__ dlocal, float* __restrict__ dwl, float* __restrict__ dG) {
+  pdl_sync();
   extern __shared__ float sm[];  // seq[len], dzl[len], red[32]
   const int nb = ls * ls, len = nb * c, n = blockIdx.x, r = (k - 1) / 2;
   float* seq = sm;
@@ -617,6 +629,7 @@ __global__ void mlca_att_bwd_a_kernel(const float* __restrict__ local, const flo
 // adaptive-pool range over the BATCH axis (reference behaviour, block.py:1575-1579).  dsg[b][c] = sum_{by: b in R(by)} dG[by][c]/|R(by)|
 __global__ void mlca_att_bwd_b_kernel(const float* __restrict__ local, const float* __restrict__ dG, const float* __restrict__ wg, int k, int c, int ls,
                                       int batch, float* __restrict__ dlocal, float* __restrict__ dwg) {
+  pdl_sync();
   extern __shared__ float sm[];  // glob[c], dzg[c], red[32]
   const int nb = ls * ls, len = nb * c, b = blockIdx.x, r = (k - 1) / 2;
   float* glob = sm;
@@ -666,6 +679,7 @@ __global__ void mlca_att_bwd_b_kernel(const float* __restrict__ local, const flo
 // dx (+)= dy * a[p] + sum over pool bins containing p of dlocal[bin] / cnt(bin)
 template <typename T>
 __global__ void mlca_bwd_apply_kernel(yad_tensor dy, const float* __restrict__ att, const float* __restrict__ dlocal, int ls, yad_tensor dx, int acc) {
+  pdl_sync();
   const int oct = dy.c >> 3, c = dy.c;
   const int64_t total = (int64_t)dy.n * dy.h * dy.w * oct;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
@@ -712,6 +726,7 @@ __global__ void mlca_bwd_apply_kernel(yad_tensor dy, const float* __restrict__ a
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void maxpool5_bwd_kernel(yad_tensor x, const T* __restrict__ dy_t, int dy_ld, const float* __restrict__ dy_f, float* __restrict__ dx_f) {
+  pdl_sync();
   const int c = x.c;
   const int64_t total = (int64_t)x.n * x.h * x.w * c;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
@@ -736,6 +751,7 @@ __global__ void maxpool5_bwd_kernel(yad_tensor x, const T* __restrict__ dy_t, in
 // y (+)= scale * x_f32 (dense fp32 NHWC with c channels) -> activation dtype view
 template <typename T>
 __global__ void cast_acc_kernel(const float* __restrict__ src, float scale, yad_tensor y, int acc) {
+  pdl_sync();
   const int oct = y.c >> 3;
   const int64_t total = (int64_t)y.n * y.h * y.w * oct;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
@@ -754,6 +770,7 @@ __global__ void cast_acc_kernel(const float* __restrict__ src, float scale, yad_
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void pool_upsample_bwd_scatter_kernel(yad_tensor dy, int s, float* __restrict__ dpool) {
+  pdl_sync();
   const int c = dy.c, oct = c >> 3;
   const int hp = dy.h / s, wp = dy.w / s;
   const float sy = (float)hp / (float)dy.h, sx = (float)wp / (float)dy.w;
@@ -781,6 +798,7 @@ __global__ void pool_upsample_bwd_scatter_kernel(yad_tensor dy, int s, float* __
 
 template <typename T>
 __global__ void pool_upsample_bwd_gather_kernel(const float* __restrict__ dpool, int s, yad_tensor dx, int acc) {
+  pdl_sync();
   const int c = dx.c, oct = c >> 3;
   const int hp = dx.h / s, wp = dx.w / s;
   const int64_t total = (int64_t)dx.n * dx.h * dx.w * oct;
@@ -816,6 +834,7 @@ __global__ void gate_mlp_bwd_kernel(const float* __restrict__ g, const float* __
                                     const float* __restrict__ w2, const float* __restrict__ b2, int c, int hidden, int nout, int kind,
                                     const float* __restrict__ dout, float* __restrict__ dg, float* __restrict__ dw1, float* __restrict__ db1,
                                     float* __restrict__ dw2, float* __restrict__ db2) {
+  pdl_sync();
   extern __shared__ float sm[];  // hid[hidden], o[nout], dz[nout], dhid[hidden]
   float* hid = sm;
   float* o = sm + hidden;
@@ -880,6 +899,7 @@ template <typename T>
 __global__ void adt_bwd_kernel(yad_tensor x, yad_tensor dy, const float* __restrict__ imp, const float* __restrict__ alphas,
                                const float* __restrict__ weight, yad_tensor dx, int acc, float* __restrict__ dimp, float* __restrict__ dalpha,
                                float* __restrict__ dweight, float* __restrict__ dbias) {
+  pdl_sync();
   extern __shared__ float sm[];  // dw[c], db[c], red[32]
   __shared__ float red[32];
   const int c = x.c, oct = c >> 3, n = blockIdx.y;
@@ -929,6 +949,7 @@ __global__ void adt_bwd_kernel(yad_tensor x, yad_tensor dy, const float* __restr
 // gelu gate (EDFFN): forward y = gelu(a) * b is yad_eltwise op 7; backward: da (+)= dy * b * gelu'(a), db (+)= dy * gelu(a)
 template <typename T>
 __global__ void gelu_gate_bwd_kernel(yad_tensor a, const T* __restrict__ b, int b_ld, yad_tensor dy, yad_tensor da, const T* db_c, int db_ld, int acc) {
+  pdl_sync();
   T* db = const_cast<T*>(db_c);
   const int oct = a.c >> 3;
   const int64_t total = (int64_t)a.n * a.h * a.w * oct;
@@ -952,6 +973,7 @@ __global__ void gelu_gate_bwd_kernel(yad_tensor a, const T* __restrict__ b, int 
 // y (+)= a * s[n]  (per-image fp32 scale)
 template <typename T>
 __global__ void scale_img_kernel(yad_tensor a, const float* __restrict__ s, yad_tensor y, int acc) {
+  pdl_sync();
   const int oct = a.c >> 3;
   const int64_t hw = (int64_t)a.h * a.w, total = (int64_t)a.n * hw * oct;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
@@ -969,6 +991,7 @@ __global__ void scale_img_kernel(yad_tensor a, const float* __restrict__ s, yad_
 // dx[(n*s + g)*T + t] (+)= dy[n*T + t] / s
 template <typename T>
 __global__ void group_mean_bwd_kernel(yad_tensor dy, int s, yad_tensor dx, int acc) {
+  pdl_sync();
   const int oct = dy.c >> 3, Tn = dy.w * dy.h;
   const int64_t total = (int64_t)dx.n * dx.h * dx.w * oct;
   const float inv = 1.0f / (float)s;
@@ -990,6 +1013,7 @@ __global__ void group_mean_bwd_kernel(yad_tensor dy, int s, yad_tensor dx, int a
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void patch_filter_bwd_x_kernel(yad_tensor dy, const float* __restrict__ m, float alpha, float* __restrict__ dx_f) {
+  pdl_sync();
   const int c = dy.c, n = blockIdx.y;
   const int wp = (dy.w + 7) / 8;
   const int pr = blockIdx.x / wp, pc = blockIdx.x % wp;
@@ -1015,6 +1039,7 @@ __global__ void patch_filter_bwd_x_kernel(yad_tensor dy, const float* __restrict
 // dM[o][i][ch] += alpha * sum over (n, patch) of dy[o] * in[i].  grid (c), block 256: thread t owns (o, i) pairs t, t+256, ...
 template <typename T>
 __global__ void patch_filter_bwd_m_kernel(yad_tensor x, yad_tensor dy, float alpha, float* __restrict__ dm) {
+  pdl_sync();
   __shared__ float sin[64], sg[64];
   const int ch = blockIdx.x, c = x.c;
   const int hp = (x.h + 7) / 8, wp = (x.w + 7) / 8;
@@ -1054,6 +1079,7 @@ __global__ void patch_filter_bwd_m_kernel(yad_tensor x, yad_tensor dy, float alp
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void head_pack_kernel(yad_tensor lv, int a0, int N, int nd, int nc, float* __restrict__ distri, float* __restrict__ logits) {
+  pdl_sync();
   const int oct = lv.c >> 3, hw = lv.h * lv.w;
   const int64_t total = (int64_t)lv.n * hw * oct;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
@@ -1070,6 +1096,7 @@ __global__ void head_pack_kernel(yad_tensor lv, int a0, int N, int nd, int nc, f
 template <typename T>
 __global__ void head_unpack_kernel(const float* __restrict__ gd, const float* __restrict__ gl, float scale, int a0, int N, int nd, int nc,
                                    yad_tensor lv) {
+  pdl_sync();
   const int oct = lv.c >> 3, hw = lv.h * lv.w;
   const int64_t total = (int64_t)lv.n * hw * oct;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
@@ -1086,6 +1113,7 @@ __global__ void head_unpack_kernel(const float* __restrict__ gd, const float* __
 
 // Fusion('bifpn') weights (block.py:1532-1534): w = relu(p) / (sum relu(p) + 1e-4).  Single thread; k <= 8.
 __global__ void fusion_weights_kernel(const float* __restrict__ p, int k, float* __restrict__ w, const float* __restrict__ dw, float* __restrict__ dp) {
+  pdl_sync();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float r[8], s = 1e-4f;
   for (int i = 0; i < k; i++) { r[i] = fmaxf(p[i], 0.f); s += r[i]; }
@@ -1101,6 +1129,7 @@ __global__ void fusion_weights_kernel(const float* __restrict__ p, int k, float*
 // trans_a = 0: thread per output, n fastest (B rows are short: K <= a few dozen).  trans_a = 1 (long K): grid (n, K chunks), threads over m so
 // that A[k][m] is read coalesced; partial sums meet in C through atomics (the caller passes acc = 1 semantics: C is accumulated).
 __global__ void small_gemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K, int acc) {
+  pdl_sync();
   const int64_t total = (int64_t)M * N;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
     const int m = (int)(it / N), n = (int)(it % N);
@@ -1110,6 +1139,7 @@ __global__ void small_gemm_kernel(const float* __restrict__ A, const float* __re
   }
 }
 __global__ void small_gemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K, int chunk) {
+  pdl_sync();
   const int n = blockIdx.x, k0 = blockIdx.y * chunk, k1 = min(K, k0 + chunk);
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
     float s = 0.f;
@@ -1147,8 +1177,8 @@ int yad_norm_bwd(const yad_tensor* x, const yad_tensor* dy, const double* stats,
   dim3 g2(gx, x->n);
 #define NORM_BWD_LAUNCH(A)                                                                                                          \
   case A:                                                                                                                           \
-    norm_bwd_reduce_kernel<T, A><<<g1, TPB, smem, st>>>(*x, *dy, stats, groups, gamma, beta, eps, act, sums, dgamma, dbeta);         \
-    norm_bwd_apply_kernel<T, A><<<g2, TPB, smem, st>>>(*x, *dy, stats, sums, groups, gamma, beta, eps, act, *dx, acc);               \
+    YAD_LAUNCH((norm_bwd_reduce_kernel<T, A>), g1, TPB, smem, st, *x, *dy, stats, groups, gamma, beta, eps, act, sums, dgamma, dbeta);         \
+    YAD_LAUNCH((norm_bwd_apply_kernel<T, A>), g2, TPB, smem, st, *x, *dy, stats, sums, groups, gamma, beta, eps, act, *dx, acc);               \
     break;
   YAD_DISPATCH_DTYPE(dtype, {
     switch (act) {
@@ -1167,7 +1197,7 @@ int yad_norm_bwd(const yad_tensor* x, const yad_tensor* dy, const double* stats,
 }
 
 int yad_bn_running_update(const double* stats, int c, double count, float momentum, float* running_mean, float* running_var, void* stream) {
-  bn_running_kernel<<<cdiv(c, 128), 128, 0, (cudaStream_t)stream>>>(stats, c, count, momentum, running_mean, running_var);
+  YAD_LAUNCH(bn_running_kernel, cdiv(c, 128), 128, 0, (cudaStream_t)stream, stats, c, count, momentum, running_mean, running_var);
   YAD_LAUNCH_CHECK("bn_running_update");
   return 0;
 }
@@ -1180,7 +1210,7 @@ int yad_act_bwd(const yad_tensor* y, const yad_tensor* dy, int act, const yad_te
   SAME_SHAPE(y, dx, "act_bwd");
   YAD_CHECK(act == YAD_ACT_SIGMOID || act == YAD_ACT_RELU, "act_bwd: only sigmoid / relu are expressible from the output (act %d)", act);
   const int64_t total = (int64_t)y->n * y->h * y->w * (y->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, act_bwd_kernel<T><<<grid_for(total), TPB, 0, (cudaStream_t)stream>>>(*y, *dy, act, *dx, acc);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(act_bwd_kernel<T>, grid_for(total), TPB, 0, (cudaStream_t)stream, *y, *dy, act, *dx, acc);)
   YAD_LAUNCH_CHECK("act_bwd");
   return 0;
 }
@@ -1192,7 +1222,7 @@ int yad_colsum(const yad_tensor* a, const void* b, int b_ld, float* out, int dty
   blocks = blocks < 1 ? 1 : (blocks > 592 ? 592 : blocks);
   const int oct = a->c / 8;
   const int tpb = oct <= TPB ? oct * (TPB / oct) : TPB;  // a multiple of the octet count: every thread keeps one octet in registers
-  YAD_DISPATCH_DTYPE(dtype, colsum_kernel<T><<<blocks, tpb, a->c * sizeof(float), (cudaStream_t)stream>>>(*a, (const T*)b, b_ld, out);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(colsum_kernel<T>, blocks, tpb, a->c * sizeof(float), (cudaStream_t)stream, *a, (const T*)b, b_ld, out);)
   YAD_LAUNCH_CHECK("colsum");
   return 0;
 }
@@ -1203,7 +1233,7 @@ int yad_dot(const yad_tensor* a, const void* b, int b_ld, int per_image, float s
   int gx = (int)((items + TPB * 8 - 1) / (TPB * 8));
   gx = gx < 1 ? 1 : (gx > 296 ? 296 : gx);
   dim3 grid(gx, per_image ? a->n : 1);
-  YAD_DISPATCH_DTYPE(dtype, dot_kernel<T><<<grid, TPB, 0, (cudaStream_t)stream>>>(*a, (const T*)b, b_ld, per_image, scale, img_div, out);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(dot_kernel<T>, grid, TPB, 0, (cudaStream_t)stream, *a, (const T*)b, b_ld, per_image, scale, img_div, out);)
   YAD_LAUNCH_CHECK("dot");
   return 0;
 }
@@ -1213,7 +1243,7 @@ int yad_dot_pixel(const yad_tensor* a, const void* b, int b_ld, const yad_tensor
   CHECK_VIEW(y, "dot_pixel y");
   YAD_CHECK(y->c == 8 && y->n == a->n && y->h == a->h && y->w == a->w, "dot_pixel: y must be an 8-channel view of the same pixels");
   const int64_t npix = (int64_t)a->n * a->h * a->w;
-  YAD_DISPATCH_DTYPE(dtype, dot_pixel_kernel<T><<<grid_for(npix, 8), TPB, 0, (cudaStream_t)stream>>>(*a, (const T*)b, b_ld, *y);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(dot_pixel_kernel<T>, grid_for(npix, 8), TPB, 0, (cudaStream_t)stream, *a, (const T*)b, b_ld, *y);)
   YAD_LAUNCH_CHECK("dot_pixel");
   return 0;
 }
@@ -1222,7 +1252,7 @@ int yad_bcast_add(const yad_tensor* dx, const float* img, float s_img, const yad
                   int acc, int dtype, void* stream) {
   CHECK_VIEW(dx, "bcast_add");
   const int64_t total = (int64_t)dx->n * dx->h * dx->w * (dx->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, bcast_add_kernel<T><<<grid_for(total), TPB, 0, (cudaStream_t)stream>>>(
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(bcast_add_kernel<T>, grid_for(total), TPB, 0, (cudaStream_t)stream, 
       *dx, img, s_img, row ? (const T*)row->ptr : nullptr, row ? row->ld : 0, s_row, col ? (const T*)col->ptr : nullptr, col ? col->ld : 0, s_col, acc);)
   YAD_LAUNCH_CHECK("bcast_add");
   return 0;
@@ -1240,8 +1270,8 @@ int yad_rowcol_gate_bwd(const yad_tensor* x, const yad_tensor* gh, const yad_ten
   yad_tensor xx = x ? *x : *dy;
   const int64_t total = (int64_t)dy->n * dy->h * dy->w * (dy->c / 8);
   YAD_DISPATCH_DTYPE(dtype, {
-    rowcol_gate_bwd_g_kernel<T><<<grid, 128, dy->c * sizeof(float), st>>>(xx, x != nullptr, *gh, *gw, *dy, *dgh, *dgw);
-    if (x && dx) rowcol_gate_bwd_x_kernel<T><<<grid_for(total), TPB, 0, st>>>(*gh, *gw, *dy, *dx, acc);
+    YAD_LAUNCH(rowcol_gate_bwd_g_kernel<T>, grid, 128, dy->c * sizeof(float), st, xx, x != nullptr, *gh, *gw, *dy, *dgh, *dgw);
+    if (x && dx) YAD_LAUNCH(rowcol_gate_bwd_x_kernel<T>, grid_for(total), TPB, 0, st, *gh, *gw, *dy, *dx, acc);
   })
   YAD_LAUNCH_CHECK("rowcol_gate_bwd");
   return 0;
@@ -1264,10 +1294,10 @@ int yad_mlca_bwd(const yad_tensor* x, const yad_tensor* dy, const float* local, 
   YAD_CHECK(smem_a <= 48 * 1024, "mlca_bwd: %d channels need %zu B of shared memory", c, smem_a);
   const int64_t total = (int64_t)x->n * x->h * x->w * (c / 8);
   YAD_DISPATCH_DTYPE(dtype, {
-    mlca_bwd_datt_kernel<T><<<g1, 128, c * sizeof(float), st>>>(*x, *dy, local_size, datt);
-    mlca_att_bwd_a_kernel<<<x->n, 256, smem_a, st>>>(local, datt, w_local, ksize, local_weight, c, local_size, dlocal, dw_local, dG);
-    mlca_att_bwd_b_kernel<<<x->n, 128, (2 * c + 32) * sizeof(float), st>>>(local, dG, w_global, ksize, c, local_size, x->n, dlocal, dw_global);
-    mlca_bwd_apply_kernel<T><<<grid_for(total), TPB, 0, st>>>(*dy, att, dlocal, local_size, *dx, acc);
+    YAD_LAUNCH(mlca_bwd_datt_kernel<T>, g1, 128, c * sizeof(float), st, *x, *dy, local_size, datt);
+    YAD_LAUNCH(mlca_att_bwd_a_kernel, x->n, 256, smem_a, st, local, datt, w_local, ksize, local_weight, c, local_size, dlocal, dw_local, dG);
+    YAD_LAUNCH(mlca_att_bwd_b_kernel, x->n, 128, (2 * c + 32) * sizeof(float), st, local, dG, w_global, ksize, c, local_size, x->n, dlocal, dw_global);
+    YAD_LAUNCH(mlca_bwd_apply_kernel<T>, grid_for(total), TPB, 0, st, *dy, att, dlocal, local_size, *dx, acc);
   })
   YAD_LAUNCH_CHECK("mlca_bwd");
   return 0;
@@ -1276,7 +1306,7 @@ int yad_mlca_bwd(const yad_tensor* x, const yad_tensor* dy, const float* local, 
 int yad_maxpool5_bwd(const yad_tensor* x, const void* dy_t, int dy_ld, const float* dy_f, float* dx_f, int dtype, void* stream) {
   CHECK_VIEW(x, "maxpool5_bwd");
   const int64_t total = (int64_t)x->n * x->h * x->w * x->c;
-  YAD_DISPATCH_DTYPE(dtype, maxpool5_bwd_kernel<T><<<grid_for(total), TPB, 0, (cudaStream_t)stream>>>(*x, (const T*)dy_t, dy_ld, dy_f, dx_f);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(maxpool5_bwd_kernel<T>, grid_for(total), TPB, 0, (cudaStream_t)stream, *x, (const T*)dy_t, dy_ld, dy_f, dx_f);)
   YAD_LAUNCH_CHECK("maxpool5_bwd");
   return 0;
 }
@@ -1284,7 +1314,7 @@ int yad_maxpool5_bwd(const yad_tensor* x, const void* dy_t, int dy_ld, const flo
 int yad_cast_acc(const float* src, float scale, const yad_tensor* y, int acc, int dtype, void* stream) {
   CHECK_VIEW(y, "cast_acc");
   const int64_t total = (int64_t)y->n * y->h * y->w * (y->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, cast_acc_kernel<T><<<grid_for(total), TPB, 0, (cudaStream_t)stream>>>(src, scale, *y, acc);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(cast_acc_kernel<T>, grid_for(total), TPB, 0, (cudaStream_t)stream, src, scale, *y, acc);)
   YAD_LAUNCH_CHECK("cast_acc");
   return 0;
 }
@@ -1299,8 +1329,8 @@ int yad_pool_upsample_bwd(const yad_tensor* dy, int s, float* dpool, const yad_t
   cudaMemsetAsync(dpool, 0, sizeof(float) * dy->n * hp * wp * dy->c, st);
   const int64_t total = (int64_t)dy->n * dy->h * dy->w * (dy->c / 8);
   YAD_DISPATCH_DTYPE(dtype, {
-    pool_upsample_bwd_scatter_kernel<T><<<grid_for(total), TPB, 0, st>>>(*dy, s, dpool);
-    pool_upsample_bwd_gather_kernel<T><<<grid_for(total), TPB, 0, st>>>(dpool, s, *dx, acc);
+    YAD_LAUNCH(pool_upsample_bwd_scatter_kernel<T>, grid_for(total), TPB, 0, st, *dy, s, dpool);
+    YAD_LAUNCH(pool_upsample_bwd_gather_kernel<T>, grid_for(total), TPB, 0, st, dpool, s, *dx, acc);
   })
   YAD_LAUNCH_CHECK("pool_upsample_bwd");
   return 0;
@@ -1308,7 +1338,7 @@ int yad_pool_upsample_bwd(const yad_tensor* dy, int s, float* dpool, const yad_t
 
 int yad_gate_mlp_bwd(const float* g, const float* w1, const float* b1, const float* w2, const float* b2, int n, int c, int hidden, int nout,
                      int kind, const float* dout, float* dg, float* dw1, float* db1, float* dw2, float* db2, void* stream) {
-  gate_mlp_bwd_kernel<<<n, 128, (2 * hidden + 2 * nout) * sizeof(float), (cudaStream_t)stream>>>(g, w1, b1, w2, b2, c, hidden, nout, kind, dout, dg,
+  YAD_LAUNCH(gate_mlp_bwd_kernel, n, 128, (2 * hidden + 2 * nout) * sizeof(float), (cudaStream_t)stream, g, w1, b1, w2, b2, c, hidden, nout, kind, dout, dg,
                                                                                                   dw1, db1, dw2, db2);
   YAD_LAUNCH_CHECK("gate_mlp_bwd");
   return 0;
@@ -1327,7 +1357,7 @@ int yad_adt_bwd(const yad_tensor* x, const yad_tensor* dy, const float* imp, con
   int chunks = (int)((hw * (x->c / 8) + TPB * 4 - 1) / (TPB * 4));
   chunks = chunks < 1 ? 1 : (chunks > 32 ? 32 : chunks);
   dim3 grid(chunks, x->n);
-  YAD_DISPATCH_DTYPE(dtype, adt_bwd_kernel<T><<<grid, TPB, 2 * x->c * sizeof(float), st>>>(*x, *dy, imp, alphas, weight, *dx, acc, dimp, dalpha,
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(adt_bwd_kernel<T>, grid, TPB, 2 * x->c * sizeof(float), st, *x, *dy, imp, alphas, weight, *dx, acc, dimp, dalpha,
                                                                                             dweight, dbias);)
   YAD_LAUNCH_CHECK("adt_bwd");
   return 0;
@@ -1339,7 +1369,7 @@ int yad_gelu_gate_bwd(const yad_tensor* a, const void* b, int b_ld, const yad_te
   CHECK_VIEW(dy, "gelu_gate_bwd dy");
   CHECK_VIEW(da, "gelu_gate_bwd da");
   const int64_t total = (int64_t)a->n * a->h * a->w * (a->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, gelu_gate_bwd_kernel<T><<<grid_for(total), TPB, 0, (cudaStream_t)stream>>>(*a, (const T*)b, b_ld, *dy, *da, (const T*)db,
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(gelu_gate_bwd_kernel<T>, grid_for(total), TPB, 0, (cudaStream_t)stream, *a, (const T*)b, b_ld, *dy, *da, (const T*)db,
                                                                                                         db_ld, acc);)
   YAD_LAUNCH_CHECK("gelu_gate_bwd");
   return 0;
@@ -1350,7 +1380,7 @@ int yad_scale_img(const yad_tensor* a, const float* s, const yad_tensor* y, int 
   CHECK_VIEW(y, "scale_img y");
   SAME_SHAPE(a, y, "scale_img");
   const int64_t total = (int64_t)a->n * a->h * a->w * (a->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, scale_img_kernel<T><<<grid_for(total), TPB, 0, (cudaStream_t)stream>>>(*a, s, *y, acc);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(scale_img_kernel<T>, grid_for(total), TPB, 0, (cudaStream_t)stream, *a, s, *y, acc);)
   YAD_LAUNCH_CHECK("scale_img");
   return 0;
 }
@@ -1360,7 +1390,7 @@ int yad_group_mean_bwd(const yad_tensor* dy, int s, const yad_tensor* dx, int ac
   CHECK_VIEW(dx, "group_mean_bwd dx");
   YAD_CHECK(dx->n == dy->n && dx->c == dy->c && (int64_t)dx->h * dx->w == (int64_t)s * dy->h * dy->w, "group_mean_bwd: shape mismatch");
   const int64_t total = (int64_t)dx->n * dx->h * dx->w * (dx->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, group_mean_bwd_kernel<T><<<grid_for(total), TPB, 0, (cudaStream_t)stream>>>(*dy, s, *dx, acc);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(group_mean_bwd_kernel<T>, grid_for(total), TPB, 0, (cudaStream_t)stream, *dy, s, *dx, acc);)
   YAD_LAUNCH_CHECK("group_mean_bwd");
   return 0;
 }
@@ -1375,8 +1405,8 @@ int yad_patch_filter_bwd(const yad_tensor* x, const yad_tensor* dy, const float*
   dim3 grid(((x->h + 7) / 8) * ((x->w + 7) / 8), x->n);
   int tpb = x->c < 128 ? ((x->c + 31) / 32) * 32 : 128;
   YAD_DISPATCH_DTYPE(dtype, {
-    patch_filter_bwd_x_kernel<T><<<grid, tpb, 0, st>>>(*dy, m, alpha, dx_f);
-    if (dm) patch_filter_bwd_m_kernel<T><<<x->c, 256, 0, st>>>(*x, *dy, alpha, dm);
+    YAD_LAUNCH(patch_filter_bwd_x_kernel<T>, grid, tpb, 0, st, *dy, m, alpha, dx_f);
+    if (dm) YAD_LAUNCH(patch_filter_bwd_m_kernel<T>, x->c, 256, 0, st, *x, *dy, alpha, dm);
   })
   YAD_LAUNCH_CHECK("patch_filter_bwd");
   return 0;
@@ -1387,7 +1417,7 @@ int yad_head_pack(const yad_tensor* level, int anchor0, int n_anchors, int reg_c
   YAD_CHECK(level->c == reg_ch + nc && reg_ch % 8 == 0 && nc % 8 == 0, "head_pack: level has %d channels, expected %d + %d (multiples of 8)", level->c,
             reg_ch, nc);
   const int64_t total = (int64_t)level->n * level->h * level->w * (level->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, head_pack_kernel<T><<<grid_for(total), TPB, 0, (cudaStream_t)stream>>>(*level, anchor0, n_anchors, reg_ch, nc, distri, logits);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(head_pack_kernel<T>, grid_for(total), TPB, 0, (cudaStream_t)stream, *level, anchor0, n_anchors, reg_ch, nc, distri, logits);)
   YAD_LAUNCH_CHECK("head_pack");
   return 0;
 }
@@ -1397,7 +1427,7 @@ int yad_head_unpack(const float* grad_distri, const float* grad_logits, float sc
   CHECK_VIEW(level, "head_unpack");
   YAD_CHECK(level->c == reg_ch + nc && reg_ch % 8 == 0 && nc % 8 == 0, "head_unpack: level has %d channels, expected %d + %d", level->c, reg_ch, nc);
   const int64_t total = (int64_t)level->n * level->h * level->w * (level->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, head_unpack_kernel<T><<<grid_for(total), TPB, 0, (cudaStream_t)stream>>>(grad_distri, grad_logits, scale, anchor0, n_anchors,
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(head_unpack_kernel<T>, grid_for(total), TPB, 0, (cudaStream_t)stream, grad_distri, grad_logits, scale, anchor0, n_anchors,
                                                                                                       reg_ch, nc, *level);)
   YAD_LAUNCH_CHECK("head_unpack");
   return 0;
@@ -1405,7 +1435,7 @@ int yad_head_unpack(const float* grad_distri, const float* grad_logits, float sc
 
 int yad_fusion_weights(const float* p, int k, float* w, const float* dw, float* dp, void* stream) {
   YAD_CHECK(k >= 1 && k <= 8, "fusion_weights: k = %d", k);
-  fusion_weights_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, k, w, dw, dp);
+  YAD_LAUNCH(fusion_weights_kernel, 1, 32, 0, (cudaStream_t)stream, p, k, w, dw, dp);
   YAD_LAUNCH_CHECK("fusion_weights");
   return 0;
 }
@@ -1416,9 +1446,9 @@ int yad_small_gemm(const float* a, const float* b, float* c, int m, int n, int k
     if (!acc) cudaMemsetAsync(c, 0, sizeof(float) * (size_t)m * n, st);
     const int chunk = 128;
     dim3 grid(n, (k + chunk - 1) / chunk);
-    small_gemm_tn_kernel<<<grid, 128, 0, st>>>(a, b, c, m, n, k, chunk);
+    YAD_LAUNCH(small_gemm_tn_kernel, grid, 128, 0, st, a, b, c, m, n, k, chunk);
   } else {
-    small_gemm_kernel<<<grid_for((int64_t)m * n), TPB, 0, st>>>(a, b, c, m, n, k, acc);
+    YAD_LAUNCH(small_gemm_kernel, grid_for((int64_t)m * n), TPB, 0, st, a, b, c, m, n, k, acc);
   }
   YAD_LAUNCH_CHECK("small_gemm");
   return 0;

@@ -12,6 +12,7 @@ template <typename T>
 __global__ void tssa_bwd_kernel(const T* __restrict__ qkv, int64_t ld, int Tn, int c, int heads, const float* __restrict__ temps,
                                 const T* __restrict__ dout, int64_t dout_ld, int Tout, int tok_off, T* __restrict__ dqkv, int64_t dld,
                                 float* __restrict__ dtemps) {
+  pdl_sync();
   extern __shared__ float sm[];  // pi[Tn], st[Tn], dpi[Tn], dots[d], dattn[d], red[32]
   const int d = c / heads, n = blockIdx.x / heads, h = blockIdx.x % heads;
   float* pi = sm;
@@ -143,6 +144,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) mha_bwd_dq_kernel(const T* __restrict__ qkv, int64_t ld, int Tn, int c, int heads, const T* __restrict__ out,
                                                          int64_t out_ld, const T* __restrict__ dout, int64_t dout_ld, float scale,
                                                          T* __restrict__ dqkv, int64_t dld, float* __restrict__ lse_d) {
+  pdl_sync();
   __shared__ __align__(16) float Ks[KB][HD];
   __shared__ __align__(16) float Vs[KB][HD];
   const int n = blockIdx.y / heads, h = blockIdx.y % heads;
@@ -219,6 +221,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) mha_bwd_dkv_kernel(const T* __restrict__ qkv, int64_t ld, int Tn, int c, int heads, const T* __restrict__ dout,
                                                           int64_t dout_ld, float scale, const float* __restrict__ lse_d, T* __restrict__ dqkv,
                                                           int64_t dld) {
+  pdl_sync();
   __shared__ __align__(16) float Qs[RB][HD];
   __shared__ __align__(16) float Gs[RB][HD];
   __shared__ float Ls[RB], Ds[RB];
@@ -359,6 +362,7 @@ __global__ void __launch_bounds__(128) mha_bwd_dq_mma_kernel(const bf16* __restr
                                                              const bf16* __restrict__ out, int64_t out_ld, const bf16* __restrict__ dout,
                                                              int64_t dout_ld, float scale, float scale_log2e, bf16* __restrict__ dqkv, int64_t dld,
                                                              float* __restrict__ lse_d) {
+  pdl_sync();
   __shared__ __align__(16) bf16 Ks[2][BA_T * BA_PITCH];
   __shared__ __align__(16) bf16 Vs[2][BA_T * BA_PITCH];
   const int n = blockIdx.y / heads, h = blockIdx.y % heads;
@@ -476,6 +480,7 @@ __global__ void __launch_bounds__(128) mha_bwd_dq_mma_kernel(const bf16* __restr
 __global__ void __launch_bounds__(128) mha_bwd_dkv_mma_kernel(const bf16* __restrict__ qkv, int64_t ld, int Tn, int c, int heads,
                                                               const bf16* __restrict__ dout, int64_t dout_ld, float scale, float scale_log2e,
                                                               const float* __restrict__ lse_d, bf16* __restrict__ dqkv, int64_t dld) {
+  pdl_sync();
   __shared__ __align__(16) bf16 Qs[2][BA_T * BA_PITCH];
   __shared__ __align__(16) bf16 Gs[2][BA_T * BA_PITCH];
   __shared__ float Ls[2][BA_T], Ds[2][BA_T];
@@ -563,7 +568,7 @@ int yad_tssa_bwd(const yad_tensor* qkv, const float* temps, int heads, const yad
   cudaStream_t st = (cudaStream_t)stream;
   YAD_DISPATCH_DTYPE(dtype, {
     if (smem > 48 * 1024) cudaFuncSetAttribute(tssa_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    tssa_bwd_kernel<T><<<qkv->n * heads, 256, smem, st>>>((const T*)qkv->ptr, qkv->ld, Tn, c, heads, temps, (const T*)dout->ptr, dout->ld, Tout,
+    YAD_LAUNCH(tssa_bwd_kernel<T>, qkv->n * heads, 256, smem, st, (const T*)qkv->ptr, qkv->ld, Tn, c, heads, temps, (const T*)dout->ptr, dout->ld, Tout,
                                                          out_token_offset, (T*)dqkv->ptr, dqkv->ld, dtemps);
   })
   YAD_LAUNCH_CHECK("tssa_bwd");
@@ -581,18 +586,18 @@ int yad_mha_bwd(const yad_tensor* qkv, int heads, const yad_tensor* out, const y
   if (dtype == YAD_BF16) {  // tensor-core path
     dim3 g2((Tn + BA_T - 1) / BA_T, qkv->n * heads);
     const float sl2 = scale * 1.44269504088896340736f;
-    mha_bwd_dq_mma_kernel<<<g2, 128, 0, st>>>((const bf16*)qkv->ptr, qkv->ld, Tn, c, heads, (const bf16*)out->ptr, out->ld, (const bf16*)dout->ptr,
+    YAD_LAUNCH(mha_bwd_dq_mma_kernel, g2, 128, 0, st, (const bf16*)qkv->ptr, qkv->ld, Tn, c, heads, (const bf16*)out->ptr, out->ld, (const bf16*)dout->ptr,
                                               dout->ld, scale, sl2, (bf16*)dqkv->ptr, dqkv->ld, lse_d);
-    mha_bwd_dkv_mma_kernel<<<g2, 128, 0, st>>>((const bf16*)qkv->ptr, qkv->ld, Tn, c, heads, (const bf16*)dout->ptr, dout->ld, scale, sl2, lse_d,
+    YAD_LAUNCH(mha_bwd_dkv_mma_kernel, g2, 128, 0, st, (const bf16*)qkv->ptr, qkv->ld, Tn, c, heads, (const bf16*)dout->ptr, dout->ld, scale, sl2, lse_d,
                                                (bf16*)dqkv->ptr, dqkv->ld);
     YAD_LAUNCH_CHECK("mha_bwd");
     return 0;
   }
   dim3 grid((Tn + RB - 1) / RB, qkv->n * heads);
   YAD_DISPATCH_DTYPE(dtype, {
-    mha_bwd_dq_kernel<T><<<grid, 128, 0, st>>>((const T*)qkv->ptr, qkv->ld, Tn, c, heads, (const T*)out->ptr, out->ld, (const T*)dout->ptr, dout->ld,
+    YAD_LAUNCH(mha_bwd_dq_kernel<T>, grid, 128, 0, st, (const T*)qkv->ptr, qkv->ld, Tn, c, heads, (const T*)out->ptr, out->ld, (const T*)dout->ptr, dout->ld,
                                               scale, (T*)dqkv->ptr, dqkv->ld, lse_d);
-    mha_bwd_dkv_kernel<T><<<grid, 128, 0, st>>>((const T*)qkv->ptr, qkv->ld, Tn, c, heads, (const T*)dout->ptr, dout->ld, scale, lse_d,
+    YAD_LAUNCH(mha_bwd_dkv_kernel<T>, grid, 128, 0, st, (const T*)qkv->ptr, qkv->ld, Tn, c, heads, (const T*)dout->ptr, dout->ld, scale, lse_d,
                                                (T*)dqkv->ptr, dqkv->ld);
   })
   YAD_LAUNCH_CHECK("mha_bwd");

@@ -30,6 +30,36 @@ void yad_set_error(const char* fmt, ...);
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Every kernel of the library starts with pdl_sync() (kernels with an on-chip prologue -- barrier init, TMEM allocation, tensor-map prefetch --
+// call it after that prologue): `griddepcontrol.wait` blocks until the grids this launch depends on have completed and their memory is visible,
+// `griddepcontrol.launch_dependents` lets the NEXT kernel of the stream be scheduled while this one is still running, so that its launch latency
+// and prologue hide under this kernel's tail.  Launches go through YAD_LAUNCH, which sets the programmatic-stream-serialization attribute
+// (a no-op when the predecessor is not a kernel).  Correct by construction: no kernel touches global memory before its own wait, and a wait
+// covers the whole chain because each predecessor finished only after its own wait.  The attribute is OFF by default (measured neutral); yad_set_pdl(1) / YAD_PDL=1 turns it on.
+int yad_pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  pdl_wait();
+  pdl_trigger();
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t yad_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = yad_pdl_enabled();
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);
+}
+#define YAD_LAUNCH(kernel, grid, block, smem, st, ...) yad_launch(kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
+
 // ---- vector access: 8 consecutive channels ------------------------------------------------------
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   float4 a = *reinterpret_cast<const float4*>(p);

@@ -59,6 +59,7 @@ __device__ __forceinline__ void gather8(const T* __restrict__ x, const T* __rest
 template <typename T>
 __global__ void __launch_bounds__(NTHREADS) conv_simt_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ om,
                                                              T* __restrict__ y, ConvGeom g, yad_epilogue e) {
+  pdl_sync();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -159,7 +160,7 @@ int yad_conv2d_simt(const yad_tensor* x, const void* w, const yad_conv_desc* d, 
   int64_t M = (int64_t)g.n * g.ho * g.wo;
   dim3 grid(cdiv(M, BM), cdiv(g.cout, BN));
   cudaStream_t st = (cudaStream_t)stream;
-  YAD_DISPATCH_DTYPE(dtype, conv_simt_kernel<T><<<grid, NTHREADS, 0, st>>>((const T*)x->ptr, (const T*)w, (const T*)d->offmask, (T*)y->ptr, g, *e);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(conv_simt_kernel<T>, grid, NTHREADS, 0, st, (const T*)x->ptr, (const T*)w, (const T*)d->offmask, (T*)y->ptr, g, *e);)
   YAD_LAUNCH_CHECK("conv2d_simt");
   return 0;
 }

@@ -36,6 +36,7 @@ template <int NT>  // n-tiles of 8 output channels (cout = 8 * NT)
 __global__ void __launch_bounds__(CS_THREADS) conv_small_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
                                                                     CsGeom g, const float* __restrict__ bias, int act, const bf16* __restrict__ add,
                                                                     int add_ld) {
+  pdl_sync();
   extern __shared__ __align__(16) uint8_t cs_smem[];
   const int s = g.stride;
   const int PH = (CS_TH - 1) * s + 3, PW = (CS_TW - 1) * s + 3;
@@ -203,7 +204,7 @@ int yad_conv2d_small(const yad_tensor* x, const void* w, const yad_conv_desc* d,
   {                                                                                                                         \
     static bool attr = false;                                                                                               \
     if (!attr) { cudaFuncSetAttribute(conv_small_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; } \
-    conv_small_kernel<N><<<grid, CS_THREADS, smem, st>>>(xp, wp, yp, g, e->bias, e->act, addp, e->add_ld);                 \
+    YAD_LAUNCH(conv_small_kernel<N>, grid, CS_THREADS, smem, st, xp, wp, yp, g, e->bias, e->act, addp, e->add_ld);                 \
   }
   if (NT == 1) CS_LAUNCH(1) else if (NT == 2) CS_LAUNCH(2) else CS_LAUNCH(4)
 #undef CS_LAUNCH

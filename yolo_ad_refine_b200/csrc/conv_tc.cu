@@ -334,6 +334,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_sync();  // on-chip prologue done; from here on the kernel reads what its predecessors wrote
 
   if (warp < 4) {
     // ================= producer =================
@@ -572,6 +573,7 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_sync();  // on-chip prologue done; from here on the kernel reads what its predecessors wrote
 
   if (warp == 0) {
     if (lane == 0) {
@@ -810,9 +812,9 @@ int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
   int grid = num_sms * per_sm;
   if (grid > tp.total_tiles) grid = tp.total_tiles;
   if (p.bn_stats)
-    conv_tma_kernel<true><<<grid, TMA_THREADS, smem, st>>>(tp, tmA, tmB);
+    YAD_LAUNCH(conv_tma_kernel<true>, grid, TMA_THREADS, smem, st, tp, tmA, tmB);
   else
-    conv_tma_kernel<false><<<grid, TMA_THREADS, smem, st>>>(tp, tmA, tmB);
+    YAD_LAUNCH(conv_tma_kernel<false>, grid, TMA_THREADS, smem, st, tp, tmA, tmB);
   YAD_LAUNCH_CHECK("conv2d_tma");
   (void)d;
   return 0;
@@ -858,9 +860,9 @@ int launch(TcParams& p, int64_t M, cudaStream_t st) {
   }
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((p.cout + p.n_tile - 1) / p.n_tile));
   if (p.deform)
-    conv_tc_kernel<true><<<grid, NTHREADS, smem, st>>>(p);
+    YAD_LAUNCH(conv_tc_kernel<true>, grid, NTHREADS, smem, st, p);
   else
-    conv_tc_kernel<false><<<grid, NTHREADS, smem, st>>>(p);
+    YAD_LAUNCH(conv_tc_kernel<false>, grid, NTHREADS, smem, st, p);
   YAD_LAUNCH_CHECK("conv2d_tc");
   return 0;
 }

@@ -11,6 +11,7 @@ namespace {
 template <typename T>
 __global__ void permute_pack_kernel(const yad_permute_entry* __restrict__ tab, const float* __restrict__ src, T* __restrict__ dst_t,
                                     float* __restrict__ dst_f) {
+  pdl_sync();
   const yad_permute_entry e = tab[blockIdx.y];
   const int64_t total = e.p0 * e.n1 * e.p2;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
@@ -26,6 +27,7 @@ __global__ void permute_pack_kernel(const yad_permute_entry* __restrict__ tab, c
 
 // grads_torch[src index] += packed_f32[dst index]
 __global__ void permute_unpack_kernel(const yad_permute_entry* __restrict__ tab, const float* __restrict__ packed, float* __restrict__ grads) {
+  pdl_sync();
   const yad_permute_entry e = tab[blockIdx.y];
   const int64_t total = e.n0 * e.n1 * e.n2;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
@@ -36,6 +38,7 @@ __global__ void permute_unpack_kernel(const yad_permute_entry* __restrict__ tab,
 }
 
 __global__ void sqnorm_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ out) {
+  pdl_sync();
   __shared__ float red[32];
   float s = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s = fmaf(x[i], x[i], s);
@@ -47,6 +50,7 @@ __global__ void sqnorm_kernel(const float* __restrict__ x, int64_t n, double* __
 __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, const uint8_t* __restrict__ group,
                                 int64_t n, float lr0, float lr1, float lr2, float wd0, float wd1, float wd2, float momentum, float max_norm,
                                 const double* __restrict__ norm_sq, int first) {
+  pdl_sync();
   float coef = 1.0f;
   if (max_norm > 0.f && norm_sq) {
     const float nrm = (float)sqrt(*norm_sq);
@@ -70,6 +74,7 @@ __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__
 __global__ void adamw_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                   const uint8_t* __restrict__ group, int64_t n, float lr0, float lr1, float lr2, float wd0, float wd1, float wd2,
                                   float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float max_norm, const double* __restrict__ norm_sq) {
+  pdl_sync();
   float coef = 1.0f;
   if (max_norm > 0.f && norm_sq) {
     const float nrm = (float)sqrt(*norm_sq);
@@ -91,6 +96,7 @@ __global__ void adamw_step_kernel(float* __restrict__ p, const float* __restrict
 }
 
 __global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ p, int64_t n, float d) {
+  pdl_sync();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     ema[i] = d * ema[i] + (1.0f - d) * p[i];
 }
@@ -110,7 +116,7 @@ int yad_permute_pack(const yad_permute_entry* table_dev, int n_entries, int64_t 
   int gx = (int)((max_elems + 255) / 256);
   gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
   dim3 grid(gx, n_entries);
-  YAD_DISPATCH_DTYPE(dtype, permute_pack_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(table_dev, src, (T*)dst_t, dst_f32);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(permute_pack_kernel<T>, grid, 256, 0, (cudaStream_t)stream, table_dev, src, (T*)dst_t, dst_f32);)
   YAD_LAUNCH_CHECK("permute_pack");
   return 0;
 }
@@ -120,20 +126,20 @@ int yad_permute_unpack(const yad_permute_entry* table_dev, int n_entries, int64_
   int gx = (int)((max_elems + 255) / 256);
   gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
   dim3 grid(gx, n_entries);
-  permute_unpack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table_dev, packed, grads);
+  YAD_LAUNCH(permute_unpack_kernel, grid, 256, 0, (cudaStream_t)stream, table_dev, packed, grads);
   YAD_LAUNCH_CHECK("permute_unpack");
   return 0;
 }
 
 int yad_sqnorm(const float* x, int64_t n, double* out, void* stream) {
-  sqnorm_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  YAD_LAUNCH(sqnorm_kernel, blocks_for(n), 256, 0, (cudaStream_t)stream, x, n, out);
   YAD_LAUNCH_CHECK("sqnorm");
   return 0;
 }
 
 int yad_sgd_step(float* params, const float* grads, float* momentum_buf, const uint8_t* group, int64_t n, const float* lr3_host,
                  const float* wd3_host, float momentum, float max_norm, const double* norm_sq, int first_step, void* stream) {
-  sgd_step_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(params, grads, momentum_buf, group, n, lr3_host[0], lr3_host[1], lr3_host[2],
+  YAD_LAUNCH(sgd_step_kernel, blocks_for(n), 256, 0, (cudaStream_t)stream, params, grads, momentum_buf, group, n, lr3_host[0], lr3_host[1], lr3_host[2],
                                                                     wd3_host[0], wd3_host[1], wd3_host[2], momentum, max_norm, norm_sq, first_step);
   YAD_LAUNCH_CHECK("sgd_step");
   return 0;
@@ -143,7 +149,7 @@ int yad_adamw_step(float* params, const float* grads, float* exp_avg, float* exp
                    const float* wd3_host, float beta1, float beta2, float eps, int step, float max_norm, const double* norm_sq, void* stream) {
   YAD_CHECK(step >= 1, "adamw_step: step counts from 1");
   const float bc1 = 1.0f - powf(beta1, (float)step), bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
-  adamw_step_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, group, n, lr3_host[0], lr3_host[1], lr3_host[2],
+  YAD_LAUNCH(adamw_step_kernel, blocks_for(n), 256, 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, group, n, lr3_host[0], lr3_host[1], lr3_host[2],
                                                                       wd3_host[0], wd3_host[1], wd3_host[2], beta1, beta2, eps, bc1, bc2_sqrt, max_norm,
                                                                       norm_sq);
   YAD_LAUNCH_CHECK("adamw_step");
@@ -151,7 +157,7 @@ int yad_adamw_step(float* params, const float* grads, float* exp_avg, float* exp
 }
 
 int yad_ema_update(float* ema, const float* params, int64_t n, float decay, void* stream) {
-  ema_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(ema, params, n, decay);
+  YAD_LAUNCH(ema_kernel, blocks_for(n), 256, 0, (cudaStream_t)stream, ema, params, n, decay);
   YAD_LAUNCH_CHECK("ema_update");
   return 0;
 }

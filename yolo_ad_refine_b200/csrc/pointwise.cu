@@ -13,6 +13,7 @@ __device__ __forceinline__ int64_t pix_off(const yad_tensor& t, int n, int y, in
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int c_src, yad_tensor y) {
+  pdl_sync();
   int64_t hw = (int64_t)y.h * y.w, total = (int64_t)y.n * hw;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
     int64_t n = p / hw, r = p - n * hw;
@@ -29,6 +30,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int c_src, ya
 // uint8 NCHW image -> NHWC * scale (the reference does H2D of the uint8 batch and then /255 on the device, engine/predictor.py:129-133)
 template <typename T>
 __global__ void u8_to_nhwc_kernel(const uint8_t* __restrict__ src, int c_src, float scale, yad_tensor y) {
+  pdl_sync();
   int64_t hw = (int64_t)y.h * y.w, total = (int64_t)y.n * hw;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
     int64_t n = p / hw, r = p - n * hw;
@@ -51,6 +53,7 @@ __global__ void u8_to_nhwc_kernel(const uint8_t* __restrict__ src, int c_src, fl
 template <typename T, typename IN, int COUT>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const IN* __restrict__ img, int n, int h, int w, int cin, const float* __restrict__ wgt,
                                                         const float* __restrict__ bias, int act, yad_tensor y) {
+  pdl_sync();
   // grid (ceil(wo / 128), ho, n): one CTA = 128 consecutive output pixels of one output row.  The 3 input rows x (2*128 + 1) columns x cin
   // it needs are staged in shared memory with coalesced loads (zero-filled outside the image); weights are broadcast reads.
   extern __shared__ float sw[];  // weights [9*cin][COUT], bias [COUT], input tile [cin][3][257]
@@ -132,6 +135,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const IN* __restrict__ i
 // grid (chunks, n).  stats[n][g][2] += (sum, sumsq) in double.
 template <typename T>
 __global__ void gn_stats_kernel(yad_tensor x, int groups, double* __restrict__ stats) {
+  pdl_sync();
   extern __shared__ float sm[];  // [2][c]
   const int c = x.c, n = blockIdx.y, oct = c >> 3;
   float* ssum = sm;
@@ -194,6 +198,7 @@ __global__ void gn_stats_kernel(yad_tensor x, int groups, double* __restrict__ s
 template <typename T>
 __global__ void gn_apply_kernel(yad_tensor x, const double* __restrict__ stats, int groups, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int act, const T* __restrict__ add, int add_ld, yad_tensor y) {
+  pdl_sync();
   extern __shared__ float sm[];  // scale[c], shift[c]
   const int c = x.c, n = blockIdx.y, oct = c >> 3, cpg = c / groups;
   const int64_t hw = (int64_t)x.h * x.w;
@@ -237,6 +242,7 @@ template <typename T>
 __global__ void dwconv_kernel(yad_tensor x, const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ scale,
                               const float* __restrict__ shift, int k, int act, int gate_split, const T* __restrict__ add, int add_ld,
                               yad_tensor y) {
+  pdl_sync();
   const int cw = x.c;                              // weight channel count
   const int cout = gate_split > 0 ? gate_split : x.c;
   const int oct = cout >> 3, r = k >> 1;
@@ -296,6 +302,7 @@ __global__ void dwconv_kernel(yad_tensor x, const float* __restrict__ w, const f
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void sppf_pool_kernel(yad_tensor x, yad_tensor y1, yad_tensor y2, yad_tensor y3) {
+  pdl_sync();
   const int oct = x.c >> 3;
   const int64_t total = (int64_t)x.n * x.h * x.w * oct;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
@@ -369,6 +376,7 @@ __device__ __forceinline__ void block_pixel_sum(const yad_tensor& x, int64_t cou
 // grid (splits, n): out[n][c] += partial mean (out zeroed by the launcher)
 template <typename T>
 __global__ void gap_kernel(yad_tensor x, float* __restrict__ out) {
+  pdl_sync();
   extern __shared__ float sm[];
   const int n = blockIdx.y, c = x.c, oct = c >> 3;
   for (int i = threadIdx.x; i < c; i += blockDim.x) sm[i] = 0.f;
@@ -400,6 +408,7 @@ __global__ void gap_kernel(yad_tensor x, float* __restrict__ out) {
 // grid (L, n, 2): z=0 -> row y=blockIdx.x: mean over x ; z=1 -> column x=blockIdx.x: mean over y
 template <typename T>
 __global__ void rowcol_mean_kernel(yad_tensor x, yad_tensor rowmean, yad_tensor colmean) {
+  pdl_sync();
   extern __shared__ float sm[];
   const int n = blockIdx.y, c = x.c;
   const bool is_col = blockIdx.z == 1;
@@ -419,6 +428,7 @@ __global__ void rowcol_mean_kernel(yad_tensor x, yad_tensor rowmean, yad_tensor 
 
 template <typename T>
 __global__ void rowcol_gate_kernel(yad_tensor x, bool has_x, yad_tensor gh, yad_tensor gw, yad_tensor y) {
+  pdl_sync();
   const int oct = y.c >> 3;
   const int64_t total = (int64_t)y.n * y.h * y.w * oct;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
@@ -449,6 +459,7 @@ __device__ __forceinline__ int bin_end(int i, int in, int out) { return (int)(((
 // grid (25, n): local[n][bin][c] = adaptive average of bin (block.py:1559 local_arv_pool)
 template <typename T>
 __global__ void mlca_pool_kernel(yad_tensor x, float* __restrict__ local, int ls) {
+  pdl_sync();
   extern __shared__ float sm[];
   const int n = blockIdx.y, c = x.c, bin = blockIdx.x, by = bin / ls, bx = bin % ls;
   for (int i = threadIdx.x; i < c; i += blockDim.x) sm[i] = 0.f;
@@ -467,6 +478,7 @@ __global__ void mlca_pool_kernel(yad_tensor x, float* __restrict__ local, int ls
 // shared by every image (for B == 1 this is the plain per-image broadcast).  Reproduced as is.
 // pass 1 (one CTA per image): sg[b][ch] = sigmoid(conv1d_k(mean of the image's ls x ls bins))[ch]
 __global__ void mlca_glob_kernel(const float* __restrict__ local, const float* __restrict__ wg, int k, int c, int ls, float* __restrict__ sg) {
+  pdl_sync();
   extern __shared__ float sm[];  // glob[c]
   const int nb = ls * ls, b = blockIdx.x, len = nb * c, r = (k - 1) / 2;
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
@@ -488,6 +500,7 @@ __global__ void mlca_glob_kernel(const float* __restrict__ local, const float* _
 // pass 2 (one CTA per image): G from sg (batch-axis bins, in image order as the single-kernel version summed them), local branch, blend
 __global__ void mlca_att_kernel(const float* __restrict__ local, const float* __restrict__ sg, const float* __restrict__ wl, int k, float lw,
                                 int c, int ls, int batch, float* __restrict__ att) {
+  pdl_sync();
   extern __shared__ float sm[];  // seq[nb*c], G[ls*c]
   const int nb = ls * ls;
   float* seq = sm;
@@ -515,6 +528,7 @@ __global__ void mlca_att_kernel(const float* __restrict__ local, const float* __
 // y = x * adaptive_avg_pool2d(att (ls x ls) -> (h, w)) (+ add)   (block.py:1581-1583)
 template <typename T>
 __global__ void mlca_apply_kernel(yad_tensor x, const float* __restrict__ att, int ls, const T* __restrict__ add, int add_ld, yad_tensor y) {
+  pdl_sync();
   const int oct = x.c >> 3, c = x.c;
   const int64_t total = (int64_t)x.n * x.h * x.w * oct;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
@@ -552,6 +566,7 @@ __global__ void mlca_apply_kernel(yad_tensor x, const float* __restrict__ att, i
 // adaptive_avg_pool2d(x, (h/s, w/s)) -> bilinear upsample to (h, w), align_corners=False (block.py:2451-2457)
 template <typename T>
 __global__ void pool_upsample_kernel(yad_tensor x, int s, yad_tensor y) {
+  pdl_sync();
   const int oct = x.c >> 3;
   const int hp = x.h / s, wp = x.w / s;
   const float sy = (float)hp / (float)x.h, sx = (float)wp / (float)x.w;
@@ -598,6 +613,7 @@ __global__ void pool_upsample_kernel(yad_tensor x, int s, yad_tensor y) {
 __global__ void gate_mlp_kernel(const float* __restrict__ g, const float* __restrict__ w1, const float* __restrict__ b1,
                                 const float* __restrict__ w2, const float* __restrict__ b2, int c, int hidden, int nout, int kind,
                                 float* __restrict__ out) {
+  pdl_sync();
   extern __shared__ float sm[];  // hid[hidden], o[nout]
   float* hid = sm;
   float* o = sm + hidden;
@@ -631,6 +647,7 @@ __global__ void gate_mlp_kernel(const float* __restrict__ g, const float* __rest
 template <typename T>
 __global__ void adt_apply_kernel(yad_tensor x, const float* __restrict__ imp, const float* __restrict__ alphas, const float* __restrict__ weight,
                                  const float* __restrict__ bias, yad_tensor y) {
+  pdl_sync();
   const int oct = x.c >> 3;
   const int64_t hw = (int64_t)x.h * x.w, total = (int64_t)x.n * hw * oct;
   const float a0 = alphas[0], a1 = alphas[1], a2 = alphas[2];
@@ -659,6 +676,7 @@ template <typename T>
 __global__ void eltwise_kernel(int op, yad_tensor a, const T* __restrict__ b, int b_ld, const T* __restrict__ c3, int c3_ld,
                                const T* __restrict__ d4, int d4_ld, float alpha, float beta, float gamma, const float* __restrict__ pa,
                                const float* __restrict__ pb, const float* __restrict__ pg, yad_tensor y) {
+  pdl_sync();
   if (pa) alpha = *pa;  // coefficients that are model parameters stay on the device (training path)
   if (pb) beta = *pb;
   if (pg) gamma = *pg;
@@ -722,6 +740,7 @@ __global__ void eltwise_kernel(int op, yad_tensor a, const T* __restrict__ b, in
 // mean over s token groups: x (n,1,s*T,c) -> y (n,1,T,c)
 template <typename T>
 __global__ void group_mean_kernel(yad_tensor x, int s, yad_tensor y) {
+  pdl_sync();
   const int oct = y.c >> 3, Tn = y.w * y.h;
   const int64_t total = (int64_t)y.n * Tn * oct;
   const float inv = 1.0f / (float)s;
@@ -747,6 +766,7 @@ __global__ void group_mean_kernel(yad_tensor x, int s, yad_tensor y) {
 // EDFFN 8x8 patch spectral filter as a per-channel 64x64 matrix (block.py:2398-2413); grid (patches, n), block = c threads
 template <typename T>
 __global__ void patch_filter_kernel(yad_tensor x, const float* __restrict__ m, float alpha, const T* __restrict__ add, int add_ld, yad_tensor y) {
+  pdl_sync();
   const int c = x.c, n = blockIdx.y;
   const int wp = (x.w + 7) / 8;
   const int pr = blockIdx.x / wp, pc = blockIdx.x % wp;
@@ -801,7 +821,7 @@ int yad_nchw_to_nhwc(const float* src, int c_src, const yad_tensor* y, int dtype
   YAD_CHECK(c_src <= y->c, "nchw_to_nhwc: c_src %d > c %d", c_src, y->c);
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)y->n * y->h * y->w;
-  YAD_DISPATCH_DTYPE(dtype, nchw_to_nhwc_kernel<T><<<grid_for(total), TPB, 0, st>>>(src, c_src, *y);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(nchw_to_nhwc_kernel<T>, grid_for(total), TPB, 0, st, src, c_src, *y);)
   YAD_LAUNCH_CHECK("nchw_to_nhwc");
   return 0;
 }
@@ -811,7 +831,7 @@ int yad_u8_to_nhwc(const uint8_t* src, int c_src, const yad_tensor* y, float sca
   YAD_CHECK(c_src <= y->c, "u8_to_nhwc: c_src %d > c %d", c_src, y->c);
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)y->n * y->h * y->w;
-  YAD_DISPATCH_DTYPE(dtype, u8_to_nhwc_kernel<T><<<grid_for(total), TPB, 0, st>>>(src, c_src, scale, *y);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(u8_to_nhwc_kernel<T>, grid_for(total), TPB, 0, st, src, c_src, scale, *y);)
   YAD_LAUNCH_CHECK("u8_to_nhwc");
   return 0;
 }
@@ -828,9 +848,9 @@ int yad_stem_conv(const void* img, int img_is_u8, int n, int h, int w, int cin, 
   YAD_CHECK(y->h <= 65535 && n <= 65535, "stem_conv: grid too large");
   YAD_DISPATCH_DTYPE(dtype, {
     if (img_is_u8)
-      stem_conv_kernel<T, uint8_t, 16><<<grid, 128, smem, st>>>((const uint8_t*)img, n, h, w, cin, wgt, bias, act, *y);
+      YAD_LAUNCH((stem_conv_kernel<T, uint8_t, 16>), grid, 128, smem, st, (const uint8_t*)img, n, h, w, cin, wgt, bias, act, *y);
     else
-      stem_conv_kernel<T, float, 16><<<grid, 128, smem, st>>>((const float*)img, n, h, w, cin, wgt, bias, act, *y);
+      YAD_LAUNCH((stem_conv_kernel<T, float, 16>), grid, 128, smem, st, (const float*)img, n, h, w, cin, wgt, bias, act, *y);
   })
   YAD_LAUNCH_CHECK("stem_conv");
   return 0;
@@ -847,7 +867,7 @@ int yad_gn_stats(const yad_tensor* x, int groups, double* stats, int dtype, void
   const int cap_s = 1184 / x->n > 1 ? 1184 / x->n : 1;
   chunks = chunks < 1 ? 1 : (chunks > cap_s ? cap_s : chunks);
   dim3 grid(chunks, x->n);
-  YAD_DISPATCH_DTYPE(dtype, gn_stats_kernel<T><<<grid, TPB, 2 * x->c * sizeof(float), st>>>(*x, groups, stats);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(gn_stats_kernel<T>, grid, TPB, 2 * x->c * sizeof(float), st, *x, groups, stats);)
   YAD_LAUNCH_CHECK("gn_stats");
   return 0;
 }
@@ -864,7 +884,7 @@ int yad_gn_apply(const yad_tensor* x, const double* stats, int groups, const flo
   const int cap_a = 2368 / x->n > 1 ? 2368 / x->n : 1;
   gx = gx < 1 ? 1 : (gx > cap_a ? cap_a : gx);
   dim3 grid(gx, x->n);
-  YAD_DISPATCH_DTYPE(dtype, gn_apply_kernel<T><<<grid, TPB, 2 * x->c * sizeof(float), st>>>(*x, stats, groups, gamma, beta, eps, act,
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(gn_apply_kernel<T>, grid, TPB, 2 * x->c * sizeof(float), st, *x, stats, groups, gamma, beta, eps, act,
                                                                                                (const T*)add, add_ld, *y);)
   YAD_LAUNCH_CHECK("gn_apply");
   return 0;
@@ -879,7 +899,7 @@ int yad_dwconv(const yad_tensor* x, const float* w, const float* bias, const flo
   YAD_CHECK(gate_split > 0 ? (x->c == 2 * gate_split && y->c == gate_split) : (x->c == y->c), "dwconv: channel mismatch");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)y->n * y->h * y->w * (y->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, dwconv_kernel<T><<<grid_for(total, 128), 128, 0, st>>>(*x, w, bias, scale, shift, k, act, gate_split,
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(dwconv_kernel<T>, grid_for(total, 128), 128, 0, st, *x, w, bias, scale, shift, k, act, gate_split,
                                                                                     (const T*)add, add_ld, *y);)
   YAD_LAUNCH_CHECK("dwconv");
   return 0;
@@ -893,7 +913,7 @@ int yad_sppf_pool(const yad_tensor* x, const yad_tensor* y1, const yad_tensor* y
   SAME_SHAPE(x, y1, "sppf");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)x->n * x->h * x->w * (x->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, sppf_pool_kernel<T><<<grid_for(total, 128), 128, 0, st>>>(*x, *y1, *y2, *y3);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(sppf_pool_kernel<T>, grid_for(total, 128), 128, 0, st, *x, *y1, *y2, *y3);)
   YAD_LAUNCH_CHECK("sppf_pool");
   return 0;
 }
@@ -906,7 +926,7 @@ int yad_gap(const yad_tensor* x, float* out, int dtype, void* stream) {
   int splits = (int)((hw * (x->c / 8) + TPB * 8 - 1) / (TPB * 8));
   splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
   dim3 grid(splits, x->n);
-  YAD_DISPATCH_DTYPE(dtype, gap_kernel<T><<<grid, TPB, x->c * sizeof(float), st>>>(*x, out);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(gap_kernel<T>, grid, TPB, x->c * sizeof(float), st, *x, out);)
   YAD_LAUNCH_CHECK("gap");
   return 0;
 }
@@ -920,7 +940,7 @@ int yad_rowcol_mean(const yad_tensor* x, const yad_tensor* rowmean, const yad_te
   dim3 grid(x->h > x->w ? x->h : x->w, x->n, 2);
   int tpb = (x->c / 8) * 8;  // 8 pixel lanes per octet
   tpb = tpb < 64 ? 64 : (tpb > 256 ? 256 : tpb);
-  YAD_DISPATCH_DTYPE(dtype, rowcol_mean_kernel<T><<<grid, tpb, x->c * sizeof(float), st>>>(*x, *rowmean, *colmean);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(rowcol_mean_kernel<T>, grid, tpb, x->c * sizeof(float), st, *x, *rowmean, *colmean);)
   YAD_LAUNCH_CHECK("rowcol_mean");
   return 0;
 }
@@ -933,7 +953,7 @@ int yad_rowcol_gate(const yad_tensor* x, const yad_tensor* gh, const yad_tensor*
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)y->n * y->h * y->w * (y->c / 8);
   yad_tensor xx = x ? *x : *y;
-  YAD_DISPATCH_DTYPE(dtype, rowcol_gate_kernel<T><<<grid_for(total), TPB, 0, st>>>(xx, x != nullptr, *gh, *gw, *y);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(rowcol_gate_kernel<T>, grid_for(total), TPB, 0, st, xx, x != nullptr, *gh, *gw, *y);)
   YAD_LAUNCH_CHECK("rowcol_gate");
   return 0;
 }
@@ -945,7 +965,7 @@ int yad_pool_upsample(const yad_tensor* x, int s, const yad_tensor* y, int dtype
   YAD_CHECK(s >= 1 && x->h / s >= 1 && x->w / s >= 1, "pool_upsample: scale %d too large for %dx%d", s, x->h, x->w);
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)x->n * x->h * x->w * (x->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, pool_upsample_kernel<T><<<grid_for(total, 128), 128, 0, st>>>(*x, s, *y);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(pool_upsample_kernel<T>, grid_for(total, 128), 128, 0, st, *x, s, *y);)
   YAD_LAUNCH_CHECK("pool_upsample");
   return 0;
 }
@@ -954,7 +974,7 @@ int yad_mlca_pool(const yad_tensor* x, float* local, int local_size, int dtype, 
   CHECK_VIEW(x, "mlca_pool");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(local_size * local_size, x->n);
-  YAD_DISPATCH_DTYPE(dtype, mlca_pool_kernel<T><<<grid, 128, x->c * sizeof(float), st>>>(*x, local, local_size);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(mlca_pool_kernel<T>, grid, 128, x->c * sizeof(float), st, *x, local, local_size);)
   YAD_LAUNCH_CHECK("mlca_pool");
   return 0;
 }
@@ -966,8 +986,8 @@ int yad_mlca_att(const float* local, const float* w_global, const float* w_local
   size_t smem = (size_t)(nb * c + local_size * c) * sizeof(float);
   YAD_CHECK(smem <= 48 * 1024, "mlca_att: %d channels need %zu B of shared memory", c, smem);
   YAD_CHECK(scratch != nullptr, "mlca_att: scratch (fp32 [n][c]) is required");
-  mlca_glob_kernel<<<n, 128, c * sizeof(float), st>>>(local, w_global, ksize, c, local_size, scratch);
-  mlca_att_kernel<<<n, 256, smem, st>>>(local, scratch, w_local, ksize, local_weight, c, local_size, n, att);
+  YAD_LAUNCH(mlca_glob_kernel, n, 128, c * sizeof(float), st, local, w_global, ksize, c, local_size, scratch);
+  YAD_LAUNCH(mlca_att_kernel, n, 256, smem, st, local, scratch, w_local, ksize, local_weight, c, local_size, n, att);
   YAD_LAUNCH_CHECK("mlca_att");
   return 0;
 }
@@ -979,7 +999,7 @@ int yad_mlca_apply(const yad_tensor* x, const float* att, int local_size, const 
   SAME_SHAPE(x, y, "mlca_apply");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)x->n * x->h * x->w * (x->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, mlca_apply_kernel<T><<<grid_for(total), TPB, 0, st>>>(*x, att, local_size, (const T*)add, add_ld, *y);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(mlca_apply_kernel<T>, grid_for(total), TPB, 0, st, *x, att, local_size, (const T*)add, add_ld, *y);)
   YAD_LAUNCH_CHECK("mlca_apply");
   return 0;
 }
@@ -987,7 +1007,7 @@ int yad_mlca_apply(const yad_tensor* x, const float* att, int local_size, const 
 int yad_gate_mlp(const float* g, const float* w1, const float* b1, const float* w2, const float* b2, int n, int c, int hidden,
                  int nout, int kind, float* out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  gate_mlp_kernel<<<n, 128, (hidden + nout) * sizeof(float), st>>>(g, w1, b1, w2, b2, c, hidden, nout, kind, out);
+  YAD_LAUNCH(gate_mlp_kernel, n, 128, (hidden + nout) * sizeof(float), st, g, w1, b1, w2, b2, c, hidden, nout, kind, out);
   YAD_LAUNCH_CHECK("gate_mlp");
   return 0;
 }
@@ -999,7 +1019,7 @@ int yad_adt_apply(const yad_tensor* x, const float* imp, const float* alphas, co
   SAME_SHAPE(x, y, "adt_apply");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)x->n * x->h * x->w * (x->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, adt_apply_kernel<T><<<grid_for(total), TPB, 0, st>>>(*x, imp, alphas, weight, bias, *y);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(adt_apply_kernel<T>, grid_for(total), TPB, 0, st, *x, imp, alphas, weight, bias, *y);)
   YAD_LAUNCH_CHECK("adt_apply");
   return 0;
 }
@@ -1015,7 +1035,7 @@ int yad_eltwise_dev(int op, const yad_tensor* a, const void* b, int b_ld, const 
   YAD_CHECK(op != 8 || c3, "eltwise: op 8 needs c3");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)a->n * a->h * a->w * (a->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, eltwise_kernel<T><<<grid_for(total), TPB, 0, st>>>(op, *a, (const T*)b, b_ld, (const T*)c3, c3_ld, (const T*)d4, d4_ld,
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(eltwise_kernel<T>, grid_for(total), TPB, 0, st, op, *a, (const T*)b, b_ld, (const T*)c3, c3_ld, (const T*)d4, d4_ld,
                                                                                 alpha, beta, gamma, alpha_dev, beta_dev, gamma_dev, *y);)
   YAD_LAUNCH_CHECK("eltwise");
   return 0;
@@ -1032,7 +1052,7 @@ int yad_group_mean(const yad_tensor* x, int s, const yad_tensor* y, int dtype, v
   YAD_CHECK(x->n == y->n && x->c == y->c && (int64_t)x->h * x->w == (int64_t)s * y->h * y->w, "group_mean: shape mismatch");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)y->n * y->h * y->w * (y->c / 8);
-  YAD_DISPATCH_DTYPE(dtype, group_mean_kernel<T><<<grid_for(total), TPB, 0, st>>>(*x, s, *y);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(group_mean_kernel<T>, grid_for(total), TPB, 0, st, *x, s, *y);)
   YAD_LAUNCH_CHECK("group_mean");
   return 0;
 }
@@ -1047,7 +1067,7 @@ int yad_patch_filter(const yad_tensor* x, const float* m, float alpha, const voi
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(((x->h + 7) / 8) * ((x->w + 7) / 8), x->n);
   int tpb = x->c < 128 ? ((x->c + 31) / 32) * 32 : 128;
-  YAD_DISPATCH_DTYPE(dtype, patch_filter_kernel<T><<<grid, tpb, 0, st>>>(*x, m, alpha, (const T*)add, add_ld, *y);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(patch_filter_kernel<T>, grid, tpb, 0, st, *x, m, alpha, (const T*)add, add_ld, *y);)
   YAD_LAUNCH_CHECK("patch_filter");
   return 0;
 }

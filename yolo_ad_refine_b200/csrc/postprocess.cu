@@ -24,6 +24,7 @@ constexpr int DA = 32;  // anchors per block
 template <typename T>
 __global__ void __launch_bounds__(128) decode_kernel(DecodeLevels L, int nc, int reg_max, const float* __restrict__ proj, float* __restrict__ y,
                                                      int N) {
+  pdl_sync();
   extern __shared__ float tile[];  // [DA anchors][no + 1] (odd pitch: conflict-free column reads), then dist[4][DA]
   const int no = 4 * reg_max + nc, pitch = no + 1;
   float* dist = tile + DA * pitch;
@@ -163,6 +164,7 @@ __device__ __forceinline__ bool class_ok(const uint8_t* cm, int c) { return cm =
 template <bool MULTI>
 __global__ void __launch_bounds__(CH) nms_count_kernel(const float* __restrict__ pred, int nc, int N, float conf, const uint8_t* __restrict__ cm,
                                                        NmsWs ws) {
+  pdl_sync();
   __shared__ int red[33];
   const int b = blockIdx.y, a = blockIdx.x * CH + threadIdx.x;
   const float* pb = pred + (int64_t)b * (4 + nc) * N;
@@ -210,6 +212,7 @@ __device__ __forceinline__ void for_each_score(const float* pb, const float* bes
 template <bool MULTI>
 __global__ void __launch_bounds__(1024) nms_select_kernel(const float* __restrict__ pred, int nc, int N, float conf,
                                                           const uint8_t* __restrict__ cm, int max_nms, NmsWs ws) {
+  pdl_sync();
   __shared__ int hist[256];
   __shared__ int red[33];
   __shared__ uint32_t s_prefix;
@@ -255,6 +258,7 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const float* __restric
 template <bool MULTI>
 __global__ void __launch_bounds__(CH) nms_count2_kernel(const float* __restrict__ pred, int nc, int N, float conf, const uint8_t* __restrict__ cm,
                                                         NmsWs ws) {
+  pdl_sync();
   __shared__ int red[33];
   const int b = blockIdx.y, a = blockIdx.x * CH + threadIdx.x;
   const uint32_t Tk = (uint32_t)ws.meta[b * 4 + 1];
@@ -283,6 +287,7 @@ __global__ void __launch_bounds__(CH) nms_count2_kernel(const float* __restrict_
 template <bool MULTI>
 __global__ void __launch_bounds__(CH) nms_gather_kernel(const float* __restrict__ pred, int nc, int N, float conf, const uint8_t* __restrict__ cm,
                                                         NmsWs ws) {
+  pdl_sync();
   __shared__ int red[33];
   __shared__ int s_base[2];
   const int b = blockIdx.y, a = blockIdx.x * CH + threadIdx.x;
@@ -351,6 +356,7 @@ __global__ void __launch_bounds__(CH) nms_gather_kernel(const float* __restrict_
 // K5: per-image bitonic sort of the 64-bit keys (ascending = score descending, index ascending)
 constexpr int SORT_SMEM = 4096;
 __global__ void __launch_bounds__(1024) nms_sort_kernel(NmsWs ws) {
+  pdl_sync();
   __shared__ uint64_t sk[SORT_SMEM];
   const int b = blockIdx.x;
   const int n = ws.meta[b * 4 + 3];
@@ -395,6 +401,7 @@ __device__ __forceinline__ bool iou_gt(const float4& a, float area_a, const floa
 // K6: greedy suppression, one block (256 threads) per image
 __global__ void __launch_bounds__(256) nms_greedy_kernel(NmsWs ws, float iou_thres, int agnostic, float max_wh, int max_det,
                                                          float* __restrict__ out, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_count) {
+  pdl_sync();
   extern __shared__ float4 kept[];                 // [max_det] offset boxes, then float areas[max_det]
   float* kept_area = reinterpret_cast<float*>(kept + max_det);
   __shared__ float4 cb[64];
@@ -527,7 +534,7 @@ int yad_decode(const void* const* lvl_ptr_host, const int64_t* lvl_sb_host, cons
   YAD_CHECK(smem <= 48 * 1024, "decode: %d channels per anchor need %zu B of shared memory", no, smem);
   dim3 grid((N + DA - 1) / DA, batch);
   cudaStream_t st = (cudaStream_t)stream;
-  YAD_DISPATCH_DTYPE(dtype, decode_kernel<T><<<grid, 128, smem, st>>>(L, nc, reg_max, proj, y, N);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(decode_kernel<T>, grid, 128, smem, st, L, nc, reg_max, proj, y, N);)
   YAD_LAUNCH_CHECK("decode");
   return 0;
 }
@@ -555,19 +562,19 @@ int yad_nms(const float* pred, int batch, int nc, int n_anchors, float conf_thre
   carve(ws, (char*)workspace, batch, n_anchors, nc, multi_label, max_nms);
   dim3 gc(ws.nchunks, batch);
   if (multi_label) {
-    nms_count_kernel<true><<<gc, CH, 0, st>>>(pred, nc, n_anchors, conf_thres, classes_mask, ws);
-    nms_select_kernel<true><<<batch, 1024, 0, st>>>(pred, nc, n_anchors, conf_thres, classes_mask, max_nms, ws);
-    nms_count2_kernel<true><<<gc, CH, 0, st>>>(pred, nc, n_anchors, conf_thres, classes_mask, ws);
-    nms_gather_kernel<true><<<gc, CH, 0, st>>>(pred, nc, n_anchors, conf_thres, classes_mask, ws);
+    YAD_LAUNCH(nms_count_kernel<true>, gc, CH, 0, st, pred, nc, n_anchors, conf_thres, classes_mask, ws);
+    YAD_LAUNCH(nms_select_kernel<true>, batch, 1024, 0, st, pred, nc, n_anchors, conf_thres, classes_mask, max_nms, ws);
+    YAD_LAUNCH(nms_count2_kernel<true>, gc, CH, 0, st, pred, nc, n_anchors, conf_thres, classes_mask, ws);
+    YAD_LAUNCH(nms_gather_kernel<true>, gc, CH, 0, st, pred, nc, n_anchors, conf_thres, classes_mask, ws);
   } else {
-    nms_count_kernel<false><<<gc, CH, 0, st>>>(pred, nc, n_anchors, conf_thres, classes_mask, ws);
-    nms_select_kernel<false><<<batch, 1024, 0, st>>>(pred, nc, n_anchors, conf_thres, classes_mask, max_nms, ws);
-    nms_count2_kernel<false><<<gc, CH, 0, st>>>(pred, nc, n_anchors, conf_thres, classes_mask, ws);
-    nms_gather_kernel<false><<<gc, CH, 0, st>>>(pred, nc, n_anchors, conf_thres, classes_mask, ws);
+    YAD_LAUNCH(nms_count_kernel<false>, gc, CH, 0, st, pred, nc, n_anchors, conf_thres, classes_mask, ws);
+    YAD_LAUNCH(nms_select_kernel<false>, batch, 1024, 0, st, pred, nc, n_anchors, conf_thres, classes_mask, max_nms, ws);
+    YAD_LAUNCH(nms_count2_kernel<false>, gc, CH, 0, st, pred, nc, n_anchors, conf_thres, classes_mask, ws);
+    YAD_LAUNCH(nms_gather_kernel<false>, gc, CH, 0, st, pred, nc, n_anchors, conf_thres, classes_mask, ws);
   }
-  nms_sort_kernel<<<batch, 1024, 0, st>>>(ws);
+  YAD_LAUNCH(nms_sort_kernel, batch, 1024, 0, st, ws);
   size_t smem = (size_t)max_det * (sizeof(float4) + sizeof(float));
-  nms_greedy_kernel<<<batch, 256, smem, st>>>(ws, iou_thres, agnostic, max_wh, max_det, out, out_idx, out_count);
+  YAD_LAUNCH(nms_greedy_kernel, batch, 256, smem, st, ws, iou_thres, agnostic, max_wh, max_det, out, out_idx, out_count);
   YAD_LAUNCH_CHECK("nms");
   return 0;
 }

@@ -33,6 +33,7 @@ constexpr int LB_ROWS = 4;  // output rows per thread: the horizontal taps (the 
 
 __global__ void __launch_bounds__(128) letterbox_kernel(const yad_image_desc* __restrict__ desc, uint8_t* __restrict__ out, int out_h, int out_w,
                                                         int pad_value, int swap_rb) {
+  pdl_sync();
   const int n = blockIdx.z, y_begin = blockIdx.y * LB_ROWS;
   const int x0 = (blockIdx.x * 128 + threadIdx.x) * 4;
   if (x0 >= out_w) return;
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(128) letterbox_kernel(const yad_image_desc* __
 
 __global__ void scale_boxes_kernel(float* __restrict__ det, int row_ld, const int32_t* __restrict__ count, int max_det,
                                    const yad_image_desc* __restrict__ desc) {
+  pdl_sync();
   const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   const int k = count ? min(count[b], max_det) : max_det;
   if (i >= k) return;
@@ -114,7 +116,7 @@ int yad_letterbox(const yad_image_desc* desc, int batch, uint8_t* out, int out_h
   YAD_CHECK(((uintptr_t)out & 3) == 0, "letterbox: out must be 4-byte aligned");
   if (batch == 0) return 0;
   const dim3 grid(cdiv(out_w / 4, 128), cdiv(out_h, LB_ROWS), batch);
-  letterbox_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(desc, out, out_h, out_w, pad_value, swap_rb);
+  YAD_LAUNCH(letterbox_kernel, grid, 128, 0, (cudaStream_t)stream, desc, out, out_h, out_w, pad_value, swap_rb);
   YAD_LAUNCH_CHECK("letterbox");
   return 0;
 }
@@ -125,7 +127,7 @@ int yad_scale_boxes(float* det, int row_ld, const int32_t* count, int batch, int
   YAD_CHECK(batch >= 0 && batch <= 65535 && max_det >= 0, "scale_boxes: batch %d / max_det %d out of range", batch, max_det);
   if (batch == 0 || max_det == 0) return 0;
   const dim3 grid(cdiv(max_det, 128), batch);
-  scale_boxes_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(det, row_ld, count, max_det, desc);
+  YAD_LAUNCH(scale_boxes_kernel, grid, 128, 0, (cudaStream_t)stream, det, row_ld, count, max_det, desc);
   YAD_LAUNCH_CHECK("scale_boxes");
   return 0;
 }

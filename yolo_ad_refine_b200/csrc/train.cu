@@ -99,6 +99,7 @@ __device__ __forceinline__ S nwd_sim(S ax1, S ay1, S ax2, S ay2, float bx1, floa
 // contiguous memory; the four expectations meet through shuffles and lane 0 of the quad writes both boxes.
 __global__ void loss_decode_kernel(const float* __restrict__ distri, const float* __restrict__ anc, const float* __restrict__ stride_t, int64_t total,
                                    int N, int reg_max, float* __restrict__ boxes, float* __restrict__ boxes_px) {
+  pdl_sync();
   const int64_t quads = total * 4;
   for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x; q0 < quads; q0 += (int64_t)gridDim.x * blockDim.x) {  // block-uniform trip count
     const int64_t q = q0 + threadIdx.x;
@@ -125,6 +126,7 @@ __global__ void loss_decode_kernel(const float* __restrict__ distri, const float
 }
 
 __global__ void loss_sigmoid_kernel(const float* __restrict__ logits, int64_t count, float* __restrict__ sig) {
+  pdl_sync();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) sig[i] = sigmoidf_(logits[i]);
 }
 
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(256) tal_topk_kernel(const float* __restrict__
                                                        const float* __restrict__ anc, const float* __restrict__ gt_labels,
                                                        const float* __restrict__ gt_bboxes, const float* __restrict__ mask_gt, int N, int nc, int M,
                                                        int topk, float alpha, float beta, float eps, TalWs ws) {
+  pdl_sync();
   extern __shared__ float metric[];  // [N]
   __shared__ float rv[8];
   __shared__ int ri[8];
@@ -223,6 +226,7 @@ __global__ void __launch_bounds__(512) tal_assign_kernel(const float* __restrict
                                                          float alpha, float beta, float eps, TalWs ws, int64_t* __restrict__ target_labels,
                                                          float* __restrict__ target_bboxes, float* __restrict__ target_scores,
                                                          uint8_t* __restrict__ fg_mask, int64_t* __restrict__ target_gt_idx, double* __restrict__ sums) {
+  pdl_sync();
   extern __shared__ int pos[];  // pos_align[M], pos_ov[M] as float bits
   __shared__ float red[32];
   int* pos_align = pos;
@@ -293,6 +297,7 @@ __global__ void __launch_bounds__(512) tal_assign_kernel(const float* __restrict
 }
 
 __global__ void tal_empty_kernel(int64_t total, int nc, int64_t* target_labels, int64_t* target_gt_idx, uint8_t* fg_mask) {
+  pdl_sync();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     target_labels[i] = nc;  // bg_idx (tal.py:62-70)
     target_gt_idx[i] = 0;
@@ -323,6 +328,7 @@ __global__ void __launch_bounds__(256) loss_bbox_kernel(const float* __restrict_
                                                         const float* __restrict__ tscores, const uint8_t* __restrict__ fg, int64_t total, int N,
                                                         int nc, int reg_max, double* __restrict__ sums, float box_gain, float dfl_gain,
                                                         float batch_scale, float* __restrict__ grad_distri) {
+  pdl_sync();
   __shared__ float red[32];
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   const float tss = fmaxf((float)sums[5], 1.0f);
@@ -391,6 +397,7 @@ __global__ void __launch_bounds__(256) loss_bbox_kernel(const float* __restrict_
 // SlideLoss(BCEWithLogits) over (B,N,nc), forward + backward (utils/loss.py:25-42, 510-515)
 __global__ void __launch_bounds__(256) loss_cls_kernel(const float* __restrict__ logits, const float* __restrict__ targets, int64_t count,
                                                        double* __restrict__ sums, float cls_gain, float batch_scale, float* __restrict__ grad) {
+  pdl_sync();
   __shared__ float red[32];
   float a = sums[4] > 0.0 ? (float)(sums[3] / sums[4]) : -1.0f;
   if (a < 0.2f) a = 0.2f;
@@ -411,6 +418,7 @@ __global__ void __launch_bounds__(256) loss_cls_kernel(const float* __restrict__
 
 // loss_items[3] = (box, cls, dfl) with gains; total[0] = sum * batch  (utils/loss.py:419-424, 517-519)
 __global__ void loss_finalize_kernel(const double* __restrict__ sums, float box_gain, float cls_gain, float dfl_gain, float batch, float* __restrict__ out) {
+  pdl_sync();
   const double tss = sums[5] > 1.0 ? sums[5] : 1.0;
   // the reference keeps target_scores_sum in fp32
   const float tssf = fmaxf((float)sums[5], 1.0f);
@@ -451,7 +459,7 @@ int yad_tal_assign(const float* pd_scores, const float* pd_bboxes, const float* 
   cudaMemsetAsync(target_scores, 0, sizeof(float) * total * nc, st);
   if (M == 0) {  // tal.py:62-70
     cudaMemsetAsync(target_bboxes, 0, sizeof(float) * total * 4, st);
-    tal_empty_kernel<<<grid_for(total, 256), 256, 0, st>>>(total, nc, target_labels, target_gt_idx, fg_mask);
+    YAD_LAUNCH(tal_empty_kernel, grid_for(total, 256), 256, 0, st, total, nc, target_labels, target_gt_idx, fg_mask);
     YAD_LAUNCH_CHECK("tal_empty");
     return 0;
   }
@@ -463,9 +471,9 @@ int yad_tal_assign(const float* pd_scores, const float* pd_bboxes, const float* 
   YAD_CHECK(smem <= 200 * 1024, "tal: %d anchors do not fit in shared memory", N);
   if (smem > 48 * 1024) cudaFuncSetAttribute(tal_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 g1(M, B);
-  tal_topk_kernel<<<g1, 256, smem, st>>>(pd_scores, pd_bboxes, anc, gt_labels, gt_bboxes, mask_gt, N, nc, M, topk, alpha, beta, eps, ws);
+  YAD_LAUNCH(tal_topk_kernel, g1, 256, smem, st, pd_scores, pd_bboxes, anc, gt_labels, gt_bboxes, mask_gt, N, nc, M, topk, alpha, beta, eps, ws);
   YAD_LAUNCH_CHECK("tal_topk");
-  tal_assign_kernel<<<B, 512, sizeof(int) * 2 * M, st>>>(pd_scores, pd_bboxes, anc, gt_labels, gt_bboxes, mask_gt, N, nc, M, alpha, beta, eps, ws,
+  YAD_LAUNCH(tal_assign_kernel, B, 512, sizeof(int) * 2 * M, st, pd_scores, pd_bboxes, anc, gt_labels, gt_bboxes, mask_gt, N, nc, M, alpha, beta, eps, ws,
                                                           target_labels, target_bboxes, target_scores, fg_mask, target_gt_idx, sums);
   YAD_LAUNCH_CHECK("tal_assign");
   return 0;
@@ -476,8 +484,8 @@ int yad_loss_decode(const float* pred_distri, const float* pred_logits, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = (int64_t)batch * n_anchors;
   if (total == 0) return 0;
-  loss_decode_kernel<<<grid_for(total * 4, 128), 128, 0, st>>>(pred_distri, anc, stride_t, total, n_anchors, reg_max, pred_bboxes, pred_bboxes_px);
-  if (pred_scores_sig) loss_sigmoid_kernel<<<grid_for(total * nc, 256), 256, 0, st>>>(pred_logits, total * nc, pred_scores_sig);
+  YAD_LAUNCH(loss_decode_kernel, grid_for(total * 4, 128), 128, 0, st, pred_distri, anc, stride_t, total, n_anchors, reg_max, pred_bboxes, pred_bboxes_px);
+  if (pred_scores_sig) YAD_LAUNCH(loss_sigmoid_kernel, grid_for(total * nc, 256), 256, 0, st, pred_logits, total * nc, pred_scores_sig);
   YAD_LAUNCH_CHECK("loss_decode");
   return 0;
 }
@@ -490,7 +498,7 @@ int yad_loss_bbox(const float* pred_distri, const float* pred_bboxes, const floa
   if (total == 0) return 0;
   YAD_CHECK(reg_max >= 2, "loss_bbox: DFL needs reg_max >= 2");
   if (grad_distri) cudaMemsetAsync(grad_distri, 0, sizeof(float) * total * 4 * reg_max, st);
-  loss_bbox_kernel<<<grid_for(total, 256), 256, 0, st>>>(pred_distri, pred_bboxes, anc, stride_t, target_bboxes_px, target_scores, fg_mask, total,
+  YAD_LAUNCH(loss_bbox_kernel, grid_for(total, 256), 256, 0, st, pred_distri, pred_bboxes, anc, stride_t, target_bboxes_px, target_scores, fg_mask, total,
                                                          n_anchors, nc, reg_max, sums, box_gain, dfl_gain, (float)batch, grad_distri);
   YAD_LAUNCH_CHECK("loss_bbox");
   return 0;
@@ -501,13 +509,13 @@ int yad_loss_cls(const float* pred_logits, const float* target_scores, int batch
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t count = (int64_t)batch * n_anchors * nc;
   if (count == 0) return 0;
-  loss_cls_kernel<<<grid_for(count, 256), 256, 0, st>>>(pred_logits, target_scores, count, sums, cls_gain, (float)batch, grad_logits);
+  YAD_LAUNCH(loss_cls_kernel, grid_for(count, 256), 256, 0, st, pred_logits, target_scores, count, sums, cls_gain, (float)batch, grad_logits);
   YAD_LAUNCH_CHECK("loss_cls");
   return 0;
 }
 
 int yad_loss_finalize(const double* sums, float box_gain, float cls_gain, float dfl_gain, int batch, float* out4, void* stream) {
-  loss_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sums, box_gain, cls_gain, dfl_gain, (float)batch, out4);
+  YAD_LAUNCH(loss_finalize_kernel, 1, 1, 0, (cudaStream_t)stream, sums, box_gain, cls_gain, dfl_gain, (float)batch, out4);
   YAD_LAUNCH_CHECK("loss_finalize");
   return 0;
 }

@@ -28,6 +28,7 @@ __device__ __forceinline__ int64_t in_pixel(const WgGeom& g, int64_t m, int ky, 
 constexpr int SB_P = 32, SB_C = 64;
 template <typename T>
 __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ dy, WgGeom g, float* __restrict__ dw) {
+  pdl_sync();
   __shared__ __align__(16) float sA[SB_P][SB_C + 4];  // dy[pixel][co]
   __shared__ __align__(16) float sB[SB_P][SB_C + 4];  // x[pixel][ci]
   const int ntaps = g.kh * g.kw;
@@ -93,6 +94,7 @@ __device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, uint32
 }
 
 __global__ void __launch_bounds__(128) conv_wgrad_mma_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, WgGeom g, float* __restrict__ dw) {
+  pdl_sync();
   __shared__ __align__(16) bf16 sA[2][WG_P * WG_PITCH];  // dy[pixel][co]
   __shared__ __align__(16) bf16 sB[2][WG_P * WG_PITCH];  // x[pixel][ci]
   const int ntaps = g.kh * g.kw;
@@ -182,6 +184,7 @@ __host__ __device__ constexpr int ws_pitch(int c) { return ((c >> 3) & 1) ? c + 
 template <int MT>
 __global__ void __launch_bounds__(WS_THREADS) conv_wgrad_small_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, WgGeom g,
                                                                           float* __restrict__ dw, int tiles_x, int tiles_y, int total_tiles) {
+  pdl_sync();
   extern __shared__ __align__(16) uint8_t ws_smem[];
   const int s = g.stride;
   const int PH = (WS_TH - 1) * s + 3, PW = (WS_TW - 1) * s + 3;
@@ -313,6 +316,7 @@ __global__ void __launch_bounds__(WS_THREADS) conv_wgrad_small_kernel(const bf16
 //      comes from L1/L2; one global atomic per (tap, channel) per thread at the end (warp-shuffle pre-reduction when lanes share an octet).
 template <typename T, int K>
 __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(yad_tensor x, yad_tensor dy, float* __restrict__ dw) {
+  pdl_sync();
   const int c = x.c, oct = c >> 3, r = K >> 1;
   const int per_pix = oct * K, lanes = blockDim.x / per_pix;
   const int tid = threadIdx.x;
@@ -392,6 +396,7 @@ __device__ __forceinline__ bool tile_pixel(uint32_t q, int h, int w, int tiles_x
 // thread = (octet, tap, pixel lane): the block strides over pixels in tile-major order; all index arithmetic is 32-bit.
 template <typename T>
 __global__ void deform_col_kernel(yad_tensor x, const T* __restrict__ om, int om_ld, yad_tensor col, int tiles_x, int tiles_per_img, uint32_t npix_t) {
+  pdl_sync();
   const int C = x.c, oct = C >> 3, per_pix = 9 * oct;
   const int lanes = blockDim.x / per_pix;
   const int o = (threadIdx.x % oct) * 8, tap = (threadIdx.x / oct) % 9, pl = threadIdx.x / per_pix;
@@ -427,6 +432,7 @@ __global__ void deform_col_kernel(yad_tensor x, const T* __restrict__ om, int om
 // dx_f: fp32 dense (n,h,w,C) accumulated with atomics; dom: NHWC view (>= 27 channels, 32 allocated): [2t] d(dy), [2t+1] d(dx), [18+t] d(mask logit)
 template <typename T>
 __global__ void deform_col_bwd_kernel(yad_tensor x, const T* __restrict__ om, int om_ld, yad_tensor dcol, float* __restrict__ dx_f, yad_tensor dom) {
+  pdl_sync();
   const int C = x.c, oct = C >> 3;
   const int64_t groups = (int64_t)x.n * x.h * x.w * 9;
   const int gpb = blockDim.x / oct;  // (pixel, tap) groups per block
@@ -526,11 +532,11 @@ int yad_conv_wgrad(const yad_tensor* x, const yad_tensor* dy, const yad_conv_des
     if (MT == 2) {
       static bool attr2 = false;
       if (!attr2) { cudaFuncSetAttribute(conv_wgrad_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr2 = true; }
-      conv_wgrad_small_kernel<2><<<grid, WS_THREADS, smem, st>>>((const bf16*)x->ptr, (const bf16*)dy->ptr, g, dw, tiles_x, tiles_y, total);
+      YAD_LAUNCH(conv_wgrad_small_kernel<2>, grid, WS_THREADS, smem, st, (const bf16*)x->ptr, (const bf16*)dy->ptr, g, dw, tiles_x, tiles_y, total);
     } else {
       static bool attr1 = false;
       if (!attr1) { cudaFuncSetAttribute(conv_wgrad_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr1 = true; }
-      conv_wgrad_small_kernel<1><<<grid, WS_THREADS, smem, st>>>((const bf16*)x->ptr, (const bf16*)dy->ptr, g, dw, tiles_x, tiles_y, total);
+      YAD_LAUNCH(conv_wgrad_small_kernel<1>, grid, WS_THREADS, smem, st, (const bf16*)x->ptr, (const bf16*)dy->ptr, g, dw, tiles_x, tiles_y, total);
     }
     YAD_LAUNCH_CHECK("conv_wgrad (small-channel)");
     return 0;
@@ -549,9 +555,9 @@ int yad_conv_wgrad(const yad_tensor* x, const yad_tensor* dy, const yad_conv_des
   dim3 grid(cdiv(g.cin, 64) * ntaps, cdiv(g.cout, 64), splits);
   cudaStream_t st = (cudaStream_t)stream;
   if (mma) {
-    conv_wgrad_mma_kernel<<<grid, 128, 0, st>>>((const bf16*)x->ptr, (const bf16*)dy->ptr, g, dw);
+    YAD_LAUNCH(conv_wgrad_mma_kernel, grid, 128, 0, st, (const bf16*)x->ptr, (const bf16*)dy->ptr, g, dw);
   } else {
-    YAD_DISPATCH_DTYPE(dtype, conv_wgrad_simt_kernel<T><<<grid, 256, 0, st>>>((const T*)x->ptr, (const T*)dy->ptr, g, dw);)
+    YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(conv_wgrad_simt_kernel<T>, grid, 256, 0, st, (const T*)x->ptr, (const T*)dy->ptr, g, dw);)
   }
   YAD_LAUNCH_CHECK("conv_wgrad");
   return 0;
@@ -569,9 +575,9 @@ int yad_dwconv_wgrad(const yad_tensor* x, const yad_tensor* dy, int k, float* dw
   YAD_CHECK(smem <= 48 * 1024, "dwconv_wgrad: k = %d with %d channels needs %zu B of shared memory", k, x->c, smem);
   cudaStream_t st = (cudaStream_t)stream;
   if (k == 3) {
-    YAD_DISPATCH_DTYPE(dtype, dwconv_wgrad_kernel<T, 3><<<grid, 256, smem, st>>>(*x, *dy, dw);)
+    YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH((dwconv_wgrad_kernel<T, 3>), grid, 256, smem, st, *x, *dy, dw);)
   } else {
-    YAD_DISPATCH_DTYPE(dtype, dwconv_wgrad_kernel<T, 7><<<grid, 256, smem, st>>>(*x, *dy, dw);)
+    YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH((dwconv_wgrad_kernel<T, 7>), grid, 256, smem, st, *x, *dy, dw);)
   }
   YAD_LAUNCH_CHECK("dwconv_wgrad");
   return 0;
@@ -586,7 +592,7 @@ int yad_deform_col(const yad_tensor* x, const yad_tensor* offmask, const yad_ten
   const int64_t npix_t = (int64_t)x->n * tiles_per_img * 64;
   YAD_CHECK(npix_t * 9 < (1ll << 32), "deform_col: tensor too large for 32-bit indexing");
   const int lanes = per_pix <= 288 ? 288 / per_pix : 1, tpb = lanes * per_pix;
-  YAD_DISPATCH_DTYPE(dtype, deform_col_kernel<T><<<grid_for(npix_t, lanes), tpb, 0, (cudaStream_t)stream>>>(*x, (const T*)offmask->ptr, offmask->ld, *col,
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(deform_col_kernel<T>, grid_for(npix_t, lanes), tpb, 0, (cudaStream_t)stream, *x, (const T*)offmask->ptr, offmask->ld, *col,
                                                                                                           tiles_x, tiles_per_img, (uint32_t)npix_t);)
   YAD_LAUNCH_CHECK("deform_col");
   return 0;
@@ -602,7 +608,7 @@ int yad_deform_col_bwd(const yad_tensor* x, const yad_tensor* offmask, const yad
   cudaMemsetAsync(dx_f, 0, sizeof(float) * (int64_t)x->n * x->h * x->w * x->c, st);
   const int64_t groups = (int64_t)x->n * x->h * x->w * 9;
   const int gpb = 256 / oct;
-  YAD_DISPATCH_DTYPE(dtype, deform_col_bwd_kernel<T><<<grid_for(groups, gpb), 256, 0, st>>>(*x, (const T*)offmask->ptr, offmask->ld, *dcol, dx_f, *doffmask);)
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(deform_col_bwd_kernel<T>, grid_for(groups, gpb), 256, 0, st, *x, (const T*)offmask->ptr, offmask->ld, *dcol, dx_f, *doffmask);)
   YAD_LAUNCH_CHECK("deform_col_bwd");
   return 0;
 }

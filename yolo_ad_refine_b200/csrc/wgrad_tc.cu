@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(WT_THREADS) wgrad_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_sync();  // on-chip prologue done; from here on the kernel reads what its predecessors wrote
 
   if (warp == 0) {
     if (lane == 0) {
@@ -278,7 +279,7 @@ int yad_conv_wgrad_tc(const yad_tensor* x, const yad_tensor* dy, const yad_conv_
     cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
-  wgrad_tc_kernel<<<p.mgroups * p.splits, WT_THREADS, smem, (cudaStream_t)stream>>>(p, tmX, tmDy);
+  YAD_LAUNCH(wgrad_tc_kernel, p.mgroups * p.splits, WT_THREADS, smem, (cudaStream_t)stream, p, tmX, tmDy);
   YAD_LAUNCH_CHECK("conv_wgrad (tcgen05)");
   return 0;
 }
