@@ -152,6 +152,13 @@ int yad_u8_to_nhwc(const uint8_t* src, int c_src, const yad_tensor* y, float sca
 int yad_stem_conv(const void* img, int img_is_u8, int n, int h, int w, int cin, const float* wgt, const float* bias, int act,
                   const yad_tensor* y, int dtype, void* stream);
 
+/* -- f3, Mona adapter (nn/modules/mona.py:36-64): y = LayerNorm_c(x) * gamma + x * gammax, LayerNorm2d (:5-10) over the
+ *    channels of every pixel (biased variance, eps inside the square root), weight / bias / gamma / gammax fp32 [c], c <= 1024.  The rest of Mona
+ *    runs on yad_conv2d (project1, projector + identity folded into its weights with GELU, project2 + residual) and yad_dwconv (the three depthwise
+ *    convolutions of MonaOp :12-34 merged into one 7x7 kernel). */
+int yad_ln_mix(const yad_tensor* x, const float* weight, const float* bias, const float* gamma, const float* gammax, float eps,
+               const yad_tensor* y, int dtype, void* stream);
+
 /* -- a9: fused DFL softmax-expectation + make_anchors + dist2bbox(xywh) + x stride + class sigmoid
  *    (head.py:1181-1204,1236-1252; block.py:78-81; utils/tal.py:303-327).
  *    levels: nl raw head outputs; element (b, ch, anchor a of level l) at lvl_ptr[l][b*lvl_sb[l] + ch*lvl_sc[l] + a*lvl_sa[l]]

@@ -360,7 +360,26 @@ def gen_val():
     np.savez_compressed(os.path.join(GOLD, "val_cases.npz"), **d)
 
 
+def gen_mona():
+    """Mona.forward of the live reference (nn/modules/mona.py:36-64, eval mode) on the seeded parameters / inputs of oracle/mona.py: pins the oracle
+    restatement and, through it, yad_ln_mix + the fused composition of yolo_ad_refine_b200.functional.mona."""
+    from oracle.mona import MONA_CASES, make_input, make_state
+    from ultralytics.nn.modules.mona import Mona
+    d = {}
+    for name, (c, n, h, w, seed) in MONA_CASES.items():
+        m = Mona(c).eval()
+        missing = m.load_state_dict(make_state(c, seed), strict=True)
+        with torch.no_grad():
+            y = m(make_input(c, n, h, w, seed))
+        d[name] = y.numpy() if h * w < 100 else y.numpy()[:, :, ::2, ::2]   # larger maps: every other row / column
+        d[name + "_keys"] = np.array(sorted(m.state_dict().keys()))
+        print("mona", name, tuple(y.shape), float(y.abs().mean()), missing)
+    np.savez_compressed(os.path.join(GOLD, "mona.npz"), **d)
+
+
 def main():
+    if sys.argv[1:] == ["mona"]:
+        return gen_mona()
     if sys.argv[1:] == ["match"]:
         return gen_match()
     if sys.argv[1:] == ["val"]:

@@ -1,0 +1,31 @@
+"""CPU: oracle/mona.py (Mona adapter restated from a state dict) against the fixtures written by the live reference (oracle/gen_golden.py mona), and
+the nn.Module mirror's state-dict keys against the reference's."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mona as om
+
+
+def _sub(y, h, w):
+    return y if h * w < 100 else y[:, :, ::2, ::2]
+
+
+@pytest.mark.parametrize("name", list(om.MONA_CASES))
+def test_mona_oracle_matches_reference(gold, name):
+    g = gold("mona.npz")
+    c, n, h, w, seed = om.MONA_CASES[name]
+    y = om.mona_forward(om.make_state(c, seed), om.make_input(c, n, h, w, seed)).numpy()
+    np.testing.assert_allclose(_sub(y, h, w), g[name], rtol=2e-5, atol=2e-5)
+
+
+def test_mona_module_state_dict_keys(gold):
+    from yolo_ad_refine_b200.modules import Mona
+    g = gold("mona.npz")
+    m = Mona(128)
+    assert sorted(m.state_dict().keys()) == list(g["c128_20_keys"])
+    ref = om.make_state(128, 1)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.items()}
+    m.load_state_dict(ref, strict=True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.eval()(torch.zeros(1, 128, 8, 8))  # no CPU fallback

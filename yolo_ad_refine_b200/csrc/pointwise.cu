@@ -405,6 +405,56 @@ __global__ void gap_kernel(yad_tensor x, float* __restrict__ out) {
   for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&out[(int64_t)n * c + i], sm[i] * inv);
 }
 
+// LayerNorm over the channels of every pixel mixed with the input: y = LN(x) * gamma + x * gammax  (Mona.forward, nn/modules/mona.py:55 with
+// LayerNorm2d :5-10).  g = lanes per pixel (power of two >= c / 8, at most 32): a warp normalises 32 / g pixels, each lane holds up to four
+// 8-channel vectors in registers, mean and the centred second moment are reduced with xor shuffles inside the lane group.
+template <typename T>
+__global__ void __launch_bounds__(256) ln_mix_kernel(yad_tensor x, const float* __restrict__ w, const float* __restrict__ b,
+                                                     const float* __restrict__ gamma, const float* __restrict__ gammax, float eps, yad_tensor y, int g) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31, sub = lane & (g - 1), oct = x.c >> 3;
+  const int64_t npix = (int64_t)x.n * x.h * x.w;
+  const int64_t pix = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 / g) + lane / g;
+  const bool valid = pix < npix;
+  const T* xp = reinterpret_cast<const T*>(x.ptr) + (valid ? pix : 0) * x.ld;
+  float v[4][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int o = sub + k * g;
+    if (valid && o < oct) {
+      load8(xp + o * 8, v[k]);
+#pragma unroll
+      for (int i = 0; i < 8; i++) s += v[k][i];
+    }
+  }
+  for (int d = g >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  const float mean = s / (float)x.c;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (valid && sub + k * g < oct) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) { const float dlt = v[k][i] - mean; q = fmaf(dlt, dlt, q); }
+    }
+  }
+  for (int d = g >> 1; d > 0; d >>= 1) q += __shfl_xor_sync(0xffffffffu, q, d);
+  const float rstd = 1.0f / sqrtf(q / (float)x.c + eps);
+  if (!valid) return;
+  T* yp = reinterpret_cast<T*>(y.ptr) + pix * y.ld;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int o = sub + k * g;
+    if (o < oct) {
+      float wv[8], bv[8], gv[8], xv[8], r[8];
+      load8(w + o * 8, wv); load8(b + o * 8, bv); load8(gamma + o * 8, gv); load8(gammax + o * 8, xv);
+#pragma unroll
+      for (int i = 0; i < 8; i++) r[i] = fmaf(fmaf((v[k][i] - mean) * rstd, wv[i], bv[i]), gv[i], v[k][i] * xv[i]);
+      store8(yp + o * 8, r);
+    }
+  }
+}
+
 // grid (L, n, 2): z=0 -> row y=blockIdx.x: mean over x ; z=1 -> column x=blockIdx.x: mean over y
 template <typename T>
 __global__ void rowcol_mean_kernel(yad_tensor x, yad_tensor rowmean, yad_tensor colmean) {
@@ -928,6 +978,23 @@ int yad_gap(const yad_tensor* x, float* out, int dtype, void* stream) {
   dim3 grid(splits, x->n);
   YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(gap_kernel<T>, grid, TPB, x->c * sizeof(float), st, *x, out);)
   YAD_LAUNCH_CHECK("gap");
+  return 0;
+}
+
+int yad_ln_mix(const yad_tensor* x, const float* weight, const float* bias, const float* gamma, const float* gammax, float eps,
+               const yad_tensor* y, int dtype, void* stream) {
+  CHECK_VIEW(x, "ln_mix x");
+  CHECK_VIEW(y, "ln_mix y");
+  SAME_SHAPE(x, y, "ln_mix");
+  YAD_CHECK(weight && bias && gamma && gammax, "ln_mix: null parameter");
+  YAD_CHECK(x->c <= 1024, "ln_mix: at most 1024 channels (got %d)", x->c);
+  int g = 1;
+  while (g < 32 && g * 8 < x->c) g <<= 1;
+  const int64_t npix = (int64_t)x->n * x->h * x->w;
+  if (npix == 0) return 0;
+  const int64_t per_block = 8 * (32 / g);
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(ln_mix_kernel<T>, cdiv(npix, per_block), 256, 0, (cudaStream_t)stream, *x, weight, bias, gamma, gammax, eps, *y, g);)
+  YAD_LAUNCH_CHECK("ln_mix");
   return 0;
 }
 

@@ -171,6 +171,43 @@ def ela_hsfpn(ctx, p, x, flag=True, out=None):
     return ops.rowcol_gate(x if flag else None, gh, gw, out)
 
 
+def mona(ctx, p, x, out=None):
+    """nn/modules/mona.py:36-64 Mona.forward (eval: dropout is the identity), five launches:
+      x1 = LayerNorm2d(x) * gamma + x * gammax                        yad_ln_mix
+      p1 = project1(x1)                                               1x1 conv C -> 64
+      s  = (conv1 + conv2 + conv3)(p1) / 3 + p1                       ONE 7x7 depthwise conv: the 3x3 / 5x5 / 7x7 kernels of MonaOp (:12-34) share
+                                                                      their centre, so their mean is a single zero-padded 7x7 kernel (+1 at the
+                                                                      centre tap for the identity), folded once on the host in fp32
+      g  = gelu(s + projector(s))                                     1x1 conv 64 -> 64 with weights W + I, GELU in the epilogue
+      y  = x + project2(g)                                            1x1 conv 64 -> C, residual in the epilogue"""
+    P = ctx.P
+    n, h, w, c = x.n, x.h, x.w, x.c
+
+    def merged_dw():
+        k7 = P.sd[p + ".adapter_conv.conv3.weight"].float().clone()            # (64, 1, 7, 7)
+        k7[:, :, 1:6, 1:6] += P.sd[p + ".adapter_conv.conv2.weight"].float()
+        k7[:, :, 2:5, 2:5] += P.sd[p + ".adapter_conv.conv1.weight"].float()
+        k7 /= 3.0
+        k7[:, :, 3, 3] += 1.0
+        b = (P.sd[p + ".adapter_conv.conv1.bias"].float() + P.sd[p + ".adapter_conv.conv2.bias"].float()
+             + P.sd[p + ".adapter_conv.conv3.bias"].float()) / 3.0
+        return k7.reshape(k7.shape[0], 49).t().contiguous().to(P.device), b.contiguous().to(P.device)
+
+    def projector_plus_identity():
+        wp = P.sd[p + ".adapter_conv.projector.weight"].float().clone()        # (64, 64, 1, 1)
+        wp[:, :, 0, 0] += torch.eye(wp.shape[0])
+        return wp
+
+    x1 = ops.ln_mix(x, P.f32(p + ".norm.weight"), P.f32(p + ".norm.bias"), P.misc(p + ".gamma", lambda: P.sd[p + ".gamma"].float().reshape(-1).contiguous().to(P.device)),
+                    P.misc(p + ".gammax", lambda: P.sd[p + ".gammax"].float().reshape(-1).contiguous().to(P.device)), 1e-5, ctx.act(n, h, w, c))
+    p1 = conv(ctx, x1, P.conv(p + ".project1.weight", p + ".project1.bias"))
+    dw, db = P.misc(p + ".adapter_dw", merged_dw)
+    s = ops.dwconv(p1, dw, ctx.act(n, h, w, p1.c), bias=db, k=7)
+    cwp = P.conv_raw(p + ".adapter_conv.projector+I", P.misc(p + ".adapter_pw", projector_plus_identity), P.sd[p + ".adapter_conv.projector.bias"].float())
+    g = conv(ctx, s, cwp, act=ops.ACT_GELU)
+    return conv(ctx, g, P.conv(p + ".project2.weight", p + ".project2.bias"), out=out, add=x)
+
+
 def fusion_bifpn(ctx, p, xs):
     """nn/modules/block.py:1532-1535 Fusion('bifpn') for two inputs"""
     w = torch.relu(ctx.P.sd[p + ".fusion_weight"].float())

@@ -278,6 +278,37 @@ class ELA_HSFPN(YadModule):
         return Fn.ela_hsfpn(self._ctx(a), "m", a, self.flag).nchw()
 
 
+class MonaOp(_Holder):
+    """nn/modules/mona.py:12-34 (parameter holder; Mona runs the fused forward)"""
+
+    def __init__(self, in_features):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_features, in_features, kernel_size=3, padding=1, groups=in_features)
+        self.conv2 = nn.Conv2d(in_features, in_features, kernel_size=5, padding=2, groups=in_features)
+        self.conv3 = nn.Conv2d(in_features, in_features, kernel_size=7, padding=3, groups=in_features)
+        self.projector = nn.Conv2d(in_features, in_features, kernel_size=1)
+
+
+class Mona(YadModule):
+    """nn/modules/mona.py:36-64 Mona(in_dim): same constructor, attribute and state-dict key names (project1, project2, adapter_conv.*, norm, gamma,
+    gammax).  SURVEY.md section 8f rank 3: the adapter of the C2TSSA_DYT_Mona_EDFFN sibling yamls; not part of the 701 yaml."""
+
+    def __init__(self, in_dim):
+        super().__init__()
+        self.project1 = nn.Conv2d(in_dim, 64, 1)
+        self.project2 = nn.Conv2d(64, in_dim, 1)
+        self.dropout = nn.Dropout(p=0.1)
+        self.adapter_conv = MonaOp(64)
+        self.norm = nn.LayerNorm(in_dim)
+        self.gamma = nn.Parameter(torch.ones(in_dim, 1, 1) * 1e-6)
+        self.gammax = nn.Parameter(torch.ones(in_dim, 1, 1))
+
+    def forward(self, x, hw_shapes=None):
+        self._check_eval()
+        a = as_act(x)
+        return Fn.mona(self._ctx(a), "m", a).nchw()
+
+
 class Multiply(nn.Module):
     """nn/modules/block.py:1442-1447"""
 

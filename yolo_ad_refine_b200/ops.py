@@ -159,6 +159,15 @@ def group_norm(x, y, stats, groups, gamma, beta, eps=1e-5, act=ACT_NONE, add=Non
     return y
 
 
+def ln_mix(x, weight, bias, gamma, gammax, eps, y):
+    """y = LayerNorm_c(x) * gamma + x * gammax (Mona, nn/modules/mona.py:55)"""
+    for t in (weight, bias, gamma, gammax):
+        assert t.dtype == torch.float32 and t.is_cuda and t.numel() == x.c
+    _call("yad_ln_mix", x.yt(), _p(weight), _p(bias), _p(gamma), _p(gammax), float(eps), y.yt(), dt(x.dtype), stream_ptr(),
+          meta=_m(x, 2) if PROFILE is not None else None)
+    return y
+
+
 def sppf_pool(x, y1, y2, y3):
     _call("yad_sppf_pool", x.yt(), y1.yt(), y2.yt(), y3.yt(), dt(x.dtype), stream_ptr())
 
