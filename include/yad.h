@@ -159,6 +159,11 @@ int yad_stem_conv(const void* img, int img_is_u8, int n, int h, int w, int cin, 
 int yad_ln_mix(const yad_tensor* x, const float* weight, const float* bias, const float* gamma, const float* gammax, float eps,
                const yad_tensor* y, int dtype, void* stream);
 
+/*    AttentionTSSA.forward (nn/modules/block.py:1646-1683) between its two Linear layers (which run on yad_conv2d): w = the projected tokens
+ *    (n, h, w, c) with c = heads * head_dim, temp fp32 [heads].  Token-axis L2 normalisation, softmax ACROSS THE HEADS of each token, the
+ *    per-channel attention 1 / (1 + dots) and out = -w * Pi * attn, all statistics in fp32; one CTA per image. */
+int yad_attention_tssa(const yad_tensor* w, const float* temp, int heads, const yad_tensor* out, int dtype, void* stream);
+
 /* -- a9: fused DFL softmax-expectation + make_anchors + dist2bbox(xywh) + x stride + class sigmoid
  *    (head.py:1181-1204,1236-1252; block.py:78-81; utils/tal.py:303-327).
  *    levels: nl raw head outputs; element (b, ch, anchor a of level l) at lvl_ptr[l][b*lvl_sb[l] + ch*lvl_sc[l] + a*lvl_sa[l]]

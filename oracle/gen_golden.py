@@ -377,7 +377,33 @@ def gen_mona():
     np.savez_compressed(os.path.join(GOLD, "mona.npz"), **d)
 
 
+def gen_mona_block():
+    """C2TSSA_DYT_Mona_EDFFN.forward of the live reference (nn/modules/block.py:1685-1709, eval) on seeded parameters: pins oracle/mona.py's block
+    restatement (DynamicTanh, AttentionTSSA, Mona, EDFFN inside the C2PSA split) and yad_attention_tssa + the fused composition.  The seeded state
+    dicts are stored with the outputs (their key set and shapes come from the reference module)."""
+    from oracle.mona import BLOCK_CASES, make_block_state, make_input
+    from ultralytics.nn.modules.block import C2TSSA_DYT_Mona_EDFFN
+    d, shapes = {}, {}
+    for name, (c, nb, n, h, w, seed) in BLOCK_CASES.items():
+        m = C2TSSA_DYT_Mona_EDFFN(c, c, nb).eval()
+        for mod in m.modules():  # what initialize_weights does to every BatchNorm2d of a DetectionModel (utils/torch_utils.py:426-436)
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.eps, mod.momentum = 1e-3, 0.03
+        shapes[name] = {k: list(v.shape) for k, v in m.state_dict().items()}
+        sd = make_block_state(shapes[name], seed)
+        m.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            y = m(make_input(c, n, h, w, seed))
+        d[name] = y.numpy()[:, ::4]   # every fourth channel
+        print("mona block", name, tuple(y.shape), float(y.abs().mean()), len(sd), "keys")
+    np.savez_compressed(os.path.join(GOLD, "mona_block.npz"), **d)
+    with open(os.path.join(GOLD, "mona_block_spec.json"), "w") as f:
+        json.dump(shapes, f)
+
+
 def main():
+    if sys.argv[1:] == ["mona_block"]:
+        return gen_mona_block()
     if sys.argv[1:] == ["mona"]:
         return gen_mona()
     if sys.argv[1:] == ["match"]:

@@ -85,3 +85,55 @@ def test_mona_full_size_batch64_residual_property():
     m.load_state_dict(sd)
     y = m(x.to(DEV)).float().cpu()
     check(y[17:18], om.mona_forward(sd, x[17:18].float()), torch.bfloat16)
+
+
+# ---- AttentionTSSA kernel and the C2TSSA_DYT_Mona_EDFFN block ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES, ids=["fp32", "bf16"])
+@pytest.mark.parametrize("c,heads,n,h,w", [(128, 2, 2, 20, 20), (64, 1, 1, 7, 9), (256, 4, 3, 5, 5), (128, 2, 1, 80, 80), (512, 8, 1, 3, 3), (128, 16, 1, 6, 6)])
+def test_attention_tssa_kernel_matches_oracle(dtype, c, heads, n, h, w):
+    g = torch.Generator().manual_seed(c + heads + h)
+    x = torch.randn(n, c, h, w, generator=g)
+    xa = to_act(x, dtype)
+    xr = from_act(xa)
+    temp = 0.5 + torch.rand(heads, 1, generator=g)
+    sd = {"a.qkv.weight": torch.eye(c), "a.temp": temp, "a.to_out.0.weight": torch.eye(c), "a.to_out.0.bias": torch.zeros(c)}
+    ref = om.attention_tssa(sd, "a", xr.flatten(2).permute(0, 2, 1), heads).permute(0, 2, 1).reshape(n, c, h, w)
+    y = ops.attention_tssa(xa, temp.reshape(-1).to(DEV), heads, Act.empty(n, h, w, c, dtype, DEV))
+    assert rel_err(from_act(y), ref) < (2e-5 if dtype == torch.float32 else 6e-3)
+
+
+def test_attention_tssa_argument_errors():
+    x = Act.empty(1, 4, 4, 72, torch.float32, DEV)
+    with pytest.raises(RuntimeError, match="head_dim"):
+        ops.attention_tssa(x, torch.ones(5, device=DEV), 5, Act.empty(1, 4, 4, 72, torch.float32, DEV))
+    x = Act.empty(1, 300, 300, 128, torch.float32, DEV)
+    with pytest.raises(RuntimeError, match="shared memory"):
+        ops.attention_tssa(x, torch.ones(2, device=DEV), 2, Act.empty(1, 300, 300, 128, torch.float32, DEV))
+
+
+def _block_case(name):
+    import json
+    import os
+    from conftest import GOLD
+    spec = json.load(open(os.path.join(GOLD, "mona_block_spec.json")))[name]
+    c, nb, n, h, w, seed = om.BLOCK_CASES[name]
+    return om.make_block_state(spec, seed), om.make_input(c, n, h, w, seed), nb, c
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["fp32", "bf16"])
+@pytest.mark.parametrize("name", list(om.BLOCK_CASES))
+def test_c2tssa_dyt_mona_edffn_matches_reference_golden(gold, name, dtype):
+    """bf16: each TSSAlock_DYT_Mona_EDFFN is ~25 materialised tensors deep; stated tolerance per stacked block: max 8e-2 / mean 1e-2 (relative to
+    the mean magnitude) against the oracle on the bf16-rounded input"""
+    from yolo_ad_refine_b200.modules import C2TSSA_DYT_Mona_EDFFN
+    sd, x, nb, c = _block_case(name)
+    m = C2TSSA_DYT_Mona_EDFFN(c, c, nb).eval()
+    m.load_state_dict(sd, strict=True)
+    y = m(x.to(DEV).to(dtype)).float().cpu()
+    want = om.c2tssa_dyt_mona_edffn({"m." + k: v for k, v in sd.items()}, x.to(dtype).float(), nb)
+    if dtype == torch.float32:
+        assert rel_err(y, want) < 1e-3
+        assert rel_err(y[:, ::4], gold("mona_block.npz")[name]) < 1e-3  # the live reference's output
+    else:
+        assert rel_err(y, want) < 8e-2 * nb
+        assert float((y - want).abs().mean() / want.abs().mean()) < 1e-2 * nb

@@ -29,3 +29,27 @@ def test_mona_module_state_dict_keys(gold):
     m.load_state_dict(ref, strict=True)
     with pytest.raises(RuntimeError, match="CUDA"):
         m.eval()(torch.zeros(1, 128, 8, 8))  # no CPU fallback
+
+
+def _block_case(name):
+    import json, os
+    from conftest import GOLD
+    spec = json.load(open(os.path.join(GOLD, "mona_block_spec.json")))[name]
+    c, nb, n, h, w, seed = om.BLOCK_CASES[name]
+    return om.make_block_state(spec, seed), om.make_input(c, n, h, w, seed), nb, spec
+
+
+@pytest.mark.parametrize("name", list(om.BLOCK_CASES))
+def test_mona_block_oracle_matches_reference(gold, name):
+    sd, x, nb, _ = _block_case(name)
+    y = om.c2tssa_dyt_mona_edffn({"m." + k: v for k, v in sd.items()}, x, nb).numpy()
+    np.testing.assert_allclose(y[:, ::4], gold("mona_block.npz")[name], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["c256_n1_20", "c256_n2_ragged"])
+def test_mona_block_module_state_dict_keys(name):
+    from yolo_ad_refine_b200.modules import C2TSSA_DYT_Mona_EDFFN
+    sd, _, nb, spec = _block_case(name)
+    m = C2TSSA_DYT_Mona_EDFFN(256, 256, nb)
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == spec
+    m.load_state_dict(sd, strict=True)

@@ -68,6 +68,7 @@ SIGNATURES = {
     "yad_u8_to_nhwc": (i32, [vp, i32, TP, f32, i32, vp]),
     "yad_stem_conv": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, TP, i32, vp]),
     "yad_ln_mix": (i32, [TP, vp, vp, vp, vp, f32, TP, i32, vp]),
+    "yad_attention_tssa": (i32, [TP, vp, i32, TP, i32, vp]),
     "yad_decode": (i32, [C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                          C.POINTER(f32), i32, i32, i32, i32, vp, vp, i32, vp]),
     "yad_nms_workspace_bytes": (i64, [i32, i32, i32, i32, i32]),

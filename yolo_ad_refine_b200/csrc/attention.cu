@@ -300,6 +300,108 @@ __global__ void __launch_bounds__(128) mha_mma_kernel(const bf16* __restrict__ q
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// AttentionTSSA (nn/modules/block.py:1646-1683, the ToST token-statistics attention of the C2TSSA_DYT_Mona_EDFFN sibling blocks; SURVEY.md
+// section 8f rank 3) on the projected tokens w = qkv(x), one CTA per image, fp32 statistics in shared memory:
+//   pass 1  norm2[ch]  = sum_t w[t][ch]^2                                  (F.normalize over the TOKEN axis, :1670)
+//   pass 2  s[t][h]    = temp[h] * sum_{ch in head h} w^2 / max(norm, 1e-12)^2
+//           Pi[t][h]   = softmax over the HEADS (nn.Softmax(dim=1), :1653, 1674);  pisum[h] = sum_t Pi
+//   pass 3  dots[ch]   = sum_t Pi[t][h(ch)] * w^2 / (pisum[h] + 1e-8)       (:1676)
+//   pass 4  out[t][ch] = -w * Pi[t][h] / (1 + dots[ch])                     (:1677-1680)
+// The token matrix of one image (T x c bf16, 100 KB at 20x20x128) stays in L2 between the passes.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int AT_THREADS = 512;
+
+template <typename T>
+__global__ void __launch_bounds__(AT_THREADS) attention_tssa_kernel(const T* __restrict__ w, int64_t ld, int Tn, int c, int heads,
+                                                                     const float* __restrict__ temp, T* __restrict__ out, int64_t out_ld) {
+  pdl_sync();
+  extern __shared__ float at_sm[];
+  float* norm2 = at_sm;            // [c]   -> later 1 / max(norm, eps)^2
+  float* dots = norm2 + c;         // [c]
+  float* pisum = dots + c;         // [heads]
+  float* pi = pisum + heads;       // [Tn * heads]
+  const int tid = threadIdx.x, oct = c >> 3, o = (tid % oct) * 8, tl = tid / oct, step = AT_THREADS / oct;
+  const int dh = c / heads, hd = o / dh;  // the 8 channels of a thread lie inside one head (dh % 8 == 0)
+  const T* wp = w + (int64_t)blockIdx.x * Tn * ld;
+  T* op = out + (int64_t)blockIdx.x * Tn * out_ld;
+  for (int i = tid; i < 2 * c + heads + Tn * heads; i += AT_THREADS) at_sm[i] = 0.f;
+  __syncthreads();
+  float acc[8];
+  // pass 1
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = 0.f;
+  for (int t = tl; t < Tn; t += step) {
+    float v[8];
+    load8(wp + (int64_t)t * ld + o, v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = fmaf(v[i], v[i], acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) atomicAdd(&norm2[o + i], acc[i]);
+  __syncthreads();
+  for (int i = tid; i < c; i += AT_THREADS) {
+    const float nrm = fmaxf(sqrtf(norm2[i]), 1e-12f);
+    norm2[i] = 1.0f / (nrm * nrm);
+  }
+  __syncthreads();
+  // pass 2: per-token, per-head statistic
+  {
+    float inv[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) inv[i] = norm2[o + i];
+    const float tmp = temp[hd];
+    for (int t = tl; t < Tn; t += step) {
+      float v[8], sx = 0.f;
+      load8(wp + (int64_t)t * ld + o, v);
+#pragma unroll
+      for (int i = 0; i < 8; i++) sx = fmaf(v[i] * v[i], inv[i], sx);
+      atomicAdd(&pi[t * heads + hd], sx * tmp);
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < Tn; t += AT_THREADS) {  // softmax across the heads of one token
+    float mx = -INFINITY, se = 0.f;
+    for (int h = 0; h < heads; h++) mx = fmaxf(mx, pi[t * heads + h]);
+    for (int h = 0; h < heads; h++) se += expf(pi[t * heads + h] - mx);
+    for (int h = 0; h < heads; h++) {
+      const float pv = expf(pi[t * heads + h] - mx) / se;
+      pi[t * heads + h] = pv;
+      atomicAdd(&pisum[h], pv);
+    }
+  }
+  __syncthreads();
+  // pass 3
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = 0.f;
+  for (int t = tl; t < Tn; t += step) {
+    float v[8];
+    load8(wp + (int64_t)t * ld + o, v);
+    const float pv = pi[t * heads + hd];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = fmaf(pv * v[i], v[i], acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) atomicAdd(&dots[o + i], acc[i]);
+  __syncthreads();
+  // pass 4
+  {
+    const float ps = 1.0f / (pisum[hd] + 1e-8f);
+    float att[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) att[i] = -1.0f / (1.0f + dots[o + i] * ps);
+    for (int t = tl; t < Tn; t += step) {
+      float v[8];
+      load8(wp + (int64_t)t * ld + o, v);
+      const float pv = pi[t * heads + hd];
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = v[i] * pv * att[i];
+      store8(op + (int64_t)t * out_ld + o, v);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -337,6 +439,26 @@ int yad_mha(const yad_tensor* qkv, int heads, const yad_tensor* out, int dtype, 
   dim3 grid((Tn + QB - 1) / QB, qkv->n * heads);
   YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(mha_kernel<T>, grid, QB, 0, st, (const T*)qkv->ptr, qkv->ld, Tn, c, heads, (T*)out->ptr, out->ld, scale);)
   YAD_LAUNCH_CHECK("mha");
+  return 0;
+}
+
+int yad_attention_tssa(const yad_tensor* w, const float* temp, int heads, const yad_tensor* out, int dtype, void* stream) {
+  YAD_CHECK(w && out && temp && w->ptr && out->ptr, "attention_tssa: null argument");
+  const int c = w->c, Tn = w->h * w->w;
+  YAD_CHECK(out->n == w->n && out->h == w->h && out->w == w->w && out->c == c, "attention_tssa: shape mismatch");
+  YAD_CHECK(c % 8 == 0 && w->ld % 8 == 0 && out->ld % 8 == 0, "attention_tssa: channels / strides must be multiples of 8");
+  YAD_CHECK(heads >= 1 && c % heads == 0 && (c / heads) % 8 == 0, "attention_tssa: head_dim = %d / %d must be a multiple of 8", c, heads);
+  YAD_CHECK(AT_THREADS % (c / 8) == 0, "attention_tssa: c / 8 = %d must divide %d", c / 8, AT_THREADS);
+  if (w->n == 0 || Tn == 0) return 0;
+  const size_t smem = sizeof(float) * ((size_t)2 * c + heads + (size_t)Tn * heads);
+  YAD_CHECK(smem <= 200 * 1024, "attention_tssa: %d tokens x %d heads need %zu bytes of shared memory (limit 200 KB)", Tn, heads, smem);
+  cudaStream_t st = (cudaStream_t)stream;
+  YAD_DISPATCH_DTYPE(dtype, {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(attention_tssa_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    YAD_LAUNCH(attention_tssa_kernel<T>, w->n, AT_THREADS, smem, st, (const T*)w->ptr, (int64_t)w->ld, Tn, c, heads, temp, (T*)out->ptr,
+               (int64_t)out->ld);
+  })
+  YAD_LAUNCH_CHECK("attention_tssa");
   return 0;
 }
 

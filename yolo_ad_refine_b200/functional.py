@@ -208,6 +208,46 @@ def mona(ctx, p, x, out=None):
     return conv(ctx, g, P.conv(p + ".project2.weight", p + ".project2.bias"), out=out, add=x)
 
 
+def dynamic_tanh(ctx, p, x):
+    """nn/modules/block.py:1624-1641 DynamicTanh(channels_last=False): tanh(alpha * x) * weight + bias = the one-branch case of yad_adt_apply
+    (importance 1, 0, 0 and alphas alpha, 0, 0)"""
+    P = ctx.P
+    imp = P.misc(f"dyt.imp.{x.n}", lambda: torch.tensor([[1.0, 0.0, 0.0]] * x.n, dtype=torch.float32).to(P.device))
+    alphas = P.misc(p + ".al3", lambda: torch.tensor([P.scalar(p + ".alpha"), 0.0, 0.0], dtype=torch.float32).to(P.device))
+    return ops.adt_apply(x, imp, alphas, P.f32(p + ".weight"), P.f32(p + ".bias"), ctx.act(x.n, x.h, x.w, x.c))
+
+
+def attention_tssa(ctx, p, x, heads, add=None, out=None):
+    """nn/modules/block.py:1646-1683 AttentionTSSA on the (n, h*w, c) tokens of an NHWC map: qkv Linear (no bias) -> yad_attention_tssa -> to_out
+    Linear (+ bias), with the block's residual in the last epilogue"""
+    P = ctx.P
+    wq = conv(ctx, x, P.conv(p + ".qkv.weight"))
+    temp = P.misc(p + ".temp1d", lambda: P.f32(p + ".temp").reshape(-1).contiguous())
+    att = ops.attention_tssa(wq, temp, heads, ctx.act(x.n, x.h, x.w, x.c))
+    return conv(ctx, att, P.conv(p + ".to_out.0.weight", p + ".to_out.0.bias"), out=out, add=add)
+
+
+def tssa_dyt_mona_edffn(ctx, p, x, heads, out=None):
+    """nn/modules/block.py:1685-1703 TSSAlock_DYT_Mona_EDFFN.forward (shortcut=True):
+    x += attn(dyt1(x)); x = mona1(x); x += ffn(dyt2(x)); x = mona2(x)"""
+    t = attention_tssa(ctx, p + ".attn", dynamic_tanh(ctx, p + ".dyt1", x), heads, add=x)
+    t = mona(ctx, p + ".mona1", t)
+    o, m = edffn(ctx, p + ".ffn", dynamic_tanh(ctx, p + ".dyt2", t), t, None)
+    t = ops.patch_filter(o, m, ctx.act(t.n, t.h, t.w, t.c), alpha=1.0, add=t)
+    return mona(ctx, p + ".mona2", t, out=out)
+
+
+def c2tssa_dyt_mona_edffn(ctx, p, x, n=1):
+    """nn/modules/block.py:1705-1709 C2TSSA_DYT_Mona_EDFFN + C2PSA.forward :1045-1049 (split, n blocks on b, concat-free cv2)"""
+    c = ctx.P.conv_bn(p + ".cv1").cout // 2
+    ab = conv_bn_act(ctx, p + ".cv1", x)
+    b = ab.slice(c, c)
+    cur = b
+    for i in range(n):
+        cur = tssa_dyt_mona_edffn(ctx, f"{p}.m.{i}", cur, heads=c // 64, out=b if i == n - 1 else None)
+    return conv_bn_act(ctx, p + ".cv2", ab)
+
+
 def fusion_bifpn(ctx, p, xs):
     """nn/modules/block.py:1532-1535 Fusion('bifpn') for two inputs"""
     w = torch.relu(ctx.P.sd[p + ".fusion_weight"].float())

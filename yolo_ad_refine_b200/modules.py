@@ -309,6 +309,60 @@ class Mona(YadModule):
         return Fn.mona(self._ctx(a), "m", a).nchw()
 
 
+class DynamicTanh(_Holder):
+    """nn/modules/block.py:1624-1641 (parameter holder)"""
+
+    def __init__(self, normalized_shape, channels_last=False, alpha_init_value=0.5):
+        super().__init__()
+        assert not channels_last
+        self.alpha = nn.Parameter(torch.ones(1) * alpha_init_value)
+        self.weight = nn.Parameter(torch.ones(normalized_shape))
+        self.bias = nn.Parameter(torch.zeros(normalized_shape))
+
+
+class AttentionTSSA(_Holder):
+    """nn/modules/block.py:1646-1663 (parameter holder)"""
+
+    def __init__(self, dim, num_heads=8):
+        super().__init__()
+        self.heads = num_heads
+        self.qkv = nn.Linear(dim, dim, bias=False)
+        self.temp = nn.Parameter(torch.ones(num_heads, 1))
+        self.to_out = nn.Sequential(nn.Linear(dim, dim), nn.Dropout(0.0))
+
+
+class TSSAlock_DYT_Mona_EDFFN(_Holder):
+    """nn/modules/block.py:1685-1694 (parameter holder; C2TSSA_DYT_Mona_EDFFN runs the fused forward)"""
+
+    def __init__(self, c, attn_ratio=0.5, num_heads=4, shortcut=True):
+        super().__init__()
+        assert shortcut
+        self.ffn = _EDFFN(c)
+        self.dyt1, self.dyt2 = DynamicTanh(c), DynamicTanh(c)
+        self.mona1, self.mona2 = Mona(c), Mona(c)
+        self.attn = AttentionTSSA(c, num_heads=num_heads)
+
+
+class C2TSSA_DYT_Mona_EDFFN(YadModule):
+    """nn/modules/block.py:1705-1709 (C2PSA base :1010-1049): C2TSSA_DYT_Mona_EDFFN(c1, c2, n=1, e=0.5) -- layer 10 of the yolo11-mona / 687 / 689 /
+    697 sibling yamls.  Same constructor, attribute and state-dict key names as the reference."""
+
+    def __init__(self, c1, c2, n=1, e=0.5):
+        super().__init__()
+        assert c1 == c2
+        self.c = int(c1 * e)
+        assert self.c % 64 == 0, "head_dim is 64: the hidden width must be a multiple of 64"
+        self.n = n
+        self.cv1 = _conv_holder(c1, 2 * self.c, 1, 1)
+        self.cv2 = _conv_holder(2 * self.c, c1, 1)
+        self.m = nn.Sequential(*(TSSAlock_DYT_Mona_EDFFN(self.c, attn_ratio=0.5, num_heads=self.c // 64) for _ in range(n)))
+
+    def forward(self, x):
+        self._check_eval()
+        a = as_act(x)
+        return Fn.c2tssa_dyt_mona_edffn(self._ctx(a), "m", a, self.n).nchw()
+
+
 class Multiply(nn.Module):
     """nn/modules/block.py:1442-1447"""
 

@@ -168,6 +168,13 @@ def ln_mix(x, weight, bias, gamma, gammax, eps, y):
     return y
 
 
+def attention_tssa(w, temp, heads, out):
+    """AttentionTSSA between its Linear layers (nn/modules/block.py:1666-1682): w, out (n, h, w, c) token maps; temp fp32 [heads]"""
+    assert temp.dtype == torch.float32 and temp.is_cuda and temp.numel() == heads
+    _call("yad_attention_tssa", w.yt(), _p(temp), heads, out.yt(), dt(w.dtype), stream_ptr(), meta=_m(w, 5) if PROFILE is not None else None)
+    return out
+
+
 def sppf_pool(x, y1, y2, y3):
     _call("yad_sppf_pool", x.yt(), y1.yt(), y2.yt(), y3.yt(), dt(x.dtype), stream_ptr())
 
