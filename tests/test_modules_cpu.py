@@ -55,6 +55,7 @@ def test_plugin_rebinds_reference_names_and_parse_model_builds_mirrors():
     try:
         done = plugin.install()
         assert "nn.tasks.C3k2_MLCA" in done and "utils.ops.non_max_suppression" in done and "nn.tasks.AYHead" in done
+        assert "nn.tasks.C2TSSA_DYT_Mona_EDFFN" in done and "nn.modules.mona.Mona" in done and tasks.C2TSSA_DYT_Mona_EDFFN is M.C2TSSA_DYT_Mona_EDFFN
         m = tasks.DetectionModel("/root/reference/z-yaml/yolo11-701-YOLO-AD-Refine.yaml", ch=3, nc=80, verbose=False)
         plugin.convert_model(m)
         assert type(m.model[6]) is M.C3k2_MLCA and type(m.model[33]) is M.AYHead and type(m.model[13]) is M.YadConvTranspose2d

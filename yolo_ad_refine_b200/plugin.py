@@ -16,7 +16,9 @@ from . import modules as M
 from . import postprocess as ypost
 from . import tal as ytal
 
-BLOCKS = ["Conv", "C3k2", "C3k2_MLCA", "SPPF", "C2PTSSA", "C2ProgressiveTSSA_Fusion", "ELA_HSFPN", "Multiply", "Add", "Fusion"]
+BLOCKS = ["Conv", "C3k2", "C3k2_MLCA", "SPPF", "C2PTSSA", "C2ProgressiveTSSA_Fusion", "ELA_HSFPN", "Multiply", "Add", "Fusion",
+          # layer 10 of the yolo11-mona / 687 / 689 / 697 sibling yamls
+          "C2TSSA_DYT_Mona_EDFFN", "TSSAlock_DYT_Mona_EDFFN", "DynamicTanh", "AttentionTSSA", "Mona", "MonaOp"]
 HEADS = ["AYHead", "AYHead1"]
 
 
@@ -39,6 +41,8 @@ def install(ultralytics_pkg="ultralytics"):
         bind("nn.modules", name, obj)
         bind("nn.modules.block", name, obj)  # unpickling of checkpoints
     bind("nn.modules.conv", "Conv", M.Conv)
+    bind("nn.modules.mona", "Mona", M.Mona)
+    bind("nn.modules.mona", "MonaOp", M.MonaOp)
     for name in HEADS:
         bind("nn.tasks", name, M.AYHead)
         bind("nn.modules", name, M.AYHead)
