@@ -13,6 +13,8 @@
 // modulated deformable 3x3 (bilinear gather in the producer).
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -520,6 +522,66 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
 //   warp 1 / lane 0 : tcgen05.mma issuer (same as above); warp 1 also owns the TMEM allocation.
 //   warps 2-9       : epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter split the tile's columns).
 // =====================================================================================================================
+// Epilogue of one warp through a TMA store (1x1 convolutions, rows = consecutive pixels): phase 1 as in epilogue_warp, but the bf16 tile is staged
+// in the shared-memory image of a (store_cols channels x 32 rows) box of the output tensor map -- rows of 2 * store_cols bytes, 16-byte chunks XOR-ed
+// with address bits [7, 10) as SWIZZLE_32B / 64B / 128B prescribe (conflict-free 128-bit stores) -- and lane 0 hands the box to the TMA unit.
+// Rows beyond the last pixel and channels beyond cout are clipped by the unit.  The staging tile is reused only after the previous store has
+// finished reading it (cp.async.bulk.wait_group.read), which in steady state happened a whole tile ago.
+__device__ __forceinline__ void epilogue_warp_tma(const TcParams& p, const CUtensorMap* tmY, uint32_t tmem_acc, int quarter, int lane, uint32_t stg_addr,
+                                                  uint8_t* stg, int row0, int dp, int img, int n0, int col_begin, int col_end, int store_cols) {
+  const yad_epilogue& e = p.e;
+  float sc = 1.0f;
+  if (dp >= 0) {
+    if (e.img_scale) sc = e.img_scale[img];
+    if (e.pix_scale) sc *= __bfloat162float(reinterpret_cast<const bf16*>(e.pix_scale)[(int64_t)dp * e.pix_scale_ld]);
+  }
+  const uint32_t lane_base = ((uint32_t)(quarter * 32)) << 16;
+  const uint32_t row_bytes = 2u * (uint32_t)store_cols, swz_mask = (row_bytes >> 4) - 1u;  // 1 / 3 / 7
+  const uint32_t row_off = (uint32_t)lane * row_bytes;
+  for (int c0 = col_begin; c0 < col_end; c0 += store_cols) {
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+    for (int q0 = 0; q0 < store_cols; q0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_acc + lane_base + (uint32_t)(c0 + q0), r);
+      const int co = n0 + c0 + q0;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+      if (e.bias && co + 16 <= p.cout) {
+#pragma unroll
+        for (int i4 = 0; i4 < 4; i4++) {
+          const float4 b4 = *reinterpret_cast<const float4*>(e.bias + co + 4 * i4);
+          v[4 * i4] = fmaf(v[4 * i4], sc, b4.x); v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], sc, b4.y);
+          v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], sc, b4.z); v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], sc, b4.w);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = fmaf(v[i], sc, (e.bias && co + i < p.cout) ? e.bias[co + i] : 0.f);
+      }
+      apply_act_bf16_n<16>(v, e.act);
+      if (e.alpha != 1.0f) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] *= e.alpha;
+      }
+      if (e.gn_stats) gn_accumulate(p, v, co, dp, img);
+      float lo[8], hi[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) { lo[i] = v[i]; hi[i] = v[8 + i]; }
+      const uint32_t a0 = stg_addr + row_off + (uint32_t)q0 * 2u, a1 = a0 + 16u;
+      const uint32_t o0 = (a0 ^ (((a0 >> 7) & swz_mask) << 4)) - stg_addr, o1 = (a1 ^ (((a1 >> 7) & swz_mask) << 4)) - stg_addr;
+      *reinterpret_cast<uint4*>(stg + o0) = f_to_bf8(lo);
+      *reinterpret_cast<uint4*>(stg + o1) = f_to_bf8(hi);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmY, stg_addr, n0 + c0, row0);
+      tma_store_commit();
+    }
+  }
+}
+
 constexpr int TMA_EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each takes half of the tile's columns
 constexpr int TMA_THREADS = 64 + 32 * TMA_EPI_WARPS;
 
@@ -530,13 +592,15 @@ struct TmaParams {
   int a_bytes;          // bytes TMA writes per A box
   int tiles_n, total_tiles, acc_stages;
   int bk;               // K elements per chunk: 16 / 32 / 64 (smem row = 2*bk bytes, SWIZZLE_32B / 64B / 128B)
+  int store_cols;       // > 0: the epilogue leaves through TMA (1x1 convolutions without mul / add / batch statistics): every epilogue warp stages its
+                        //      32 rows x store_cols channels (16 / 32 / 64) in the swizzle of the output map and one lane issues a bulk tensor store
   int s2;               // stride-2 mode: 5-D parity-split map, coordinates (cpx[t] + ci, tx0 + dx[t], tpy[t], ty0 + dy[t], img)
   int cpx[MAX_TAPS], tpy[MAX_TAPS];
 };
 
 template <bool BN>  // BN: fused per-channel batch statistics (train-mode BatchNorm); a separate instantiation keeps the inference kernel lean
 __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_constant__ TmaParams tp, const __grid_constant__ CUtensorMap tmA,
-                                                               const __grid_constant__ CUtensorMap tmB) {
+                                                               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY) {
   // Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA producer runs ahead across tile boundaries and the
   // accumulator is double-buffered in TMEM (when 2 * N_TILE <= 512 columns), so loads, MMAs and the epilogue of consecutive tiles overlap.
   extern __shared__ uint8_t smem_raw[];
@@ -567,6 +631,7 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (tp.store_cols) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
   }
   if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
   tc_fence_before();
@@ -657,12 +722,17 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
       const int acc = i % acc_stages;
       mbar_wait(tfull_bar(acc), ((uint32_t)(i / acc_stages)) & 1u);
       tc_fence_after();
-      epilogue_warp<BN>(p, tmem_base + (uint32_t)(acc * p.n_tile), quarter, lane, stg, drow, dp, img, n0, col_begin, col_end, bn);
+      if (!BN && tp.store_cols)
+        epilogue_warp_tma(p, &tmY, tmem_base + (uint32_t)(acc * p.n_tile), quarter, lane, base + stg_off + (uint32_t)(ew * STG_WARP), stg,
+                          mt * BM + quarter * 32, dp, img, n0, col_begin, col_end, tp.store_cols);
+      else
+        epilogue_warp<BN>(p, tmem_base + (uint32_t)(acc * p.n_tile), quarter, lane, stg, drow, dp, img, n0, col_begin, col_end, bn);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));  // all epilogue warps -> accumulator free
     }
     if (BN) bn_acc_flush(p, bn, lane, col_begin, col_end);
+    if (!BN && tp.store_cols && lane == 0) tma_store_wait_read();  // shared memory must outlive the last bulk store's read
   }
   __syncthreads();
   if (warp == 1) {
@@ -790,6 +860,22 @@ int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
   }
   tp.tiles_n = (p.cout + p.n_tile - 1) / p.n_tile;
   tp.total_tiles = tiles_m * tp.tiles_n;
+  CUtensorMap tmY;
+  memset(&tmY, 0, sizeof(tmY));
+  {
+    static int store_env = -1;
+    if (store_env < 0) { const char* ev = getenv("YAD_CONV_TMA_STORE"); store_env = (ev && ev[0] == '0') ? 0 : 1; }
+    const int csplit = ((p.n_tile / 16 + 1) / 2) * 16;  // the column split of the two warps of a TMEM lane quarter (conv_tma_kernel)
+    const int sc = csplit > 64 ? 64 : csplit;
+    if (store_env && !tp.patch && !p.e.mul && !p.e.add && !p.bn_stats && !p.out_f32 && (sc == 16 || sc == 32 || sc == 64) && csplit % sc == 0 &&
+        p.n_tile - csplit == csplit && ((uintptr_t)p.y & 15) == 0) {
+      const int64_t M = (int64_t)p.n * p.ho * p.wo;
+      uint64_t dims[2] = {(uint64_t)p.cout, (uint64_t)M}, strides[1] = {(uint64_t)p.y_ld * 2};
+      uint32_t box[2] = {(uint32_t)sc, 32};
+      if (make_map(&tmY, p.y, 2, dims, strides, box, sc)) return 1;
+      tp.store_cols = sc;
+    }
+  }
   tp.p = p;
   static int num_sms = 0;
   if (!num_sms) {
@@ -812,9 +898,9 @@ int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
   int grid = num_sms * per_sm;
   if (grid > tp.total_tiles) grid = tp.total_tiles;
   if (p.bn_stats)
-    YAD_LAUNCH(conv_tma_kernel<true>, grid, TMA_THREADS, smem, st, tp, tmA, tmB);
+    YAD_LAUNCH(conv_tma_kernel<true>, grid, TMA_THREADS, smem, st, tp, tmA, tmB, tmY);
   else
-    YAD_LAUNCH(conv_tma_kernel<false>, grid, TMA_THREADS, smem, st, tp, tmA, tmB);
+    YAD_LAUNCH(conv_tma_kernel<false>, grid, TMA_THREADS, smem, st, tp, tmA, tmB, tmY);
   YAD_LAUNCH_CHECK("conv2d_tma");
   (void)d;
   return 0;
