@@ -573,6 +573,35 @@ __device__ __forceinline__ void epilogue_warp_tma(const TcParams& p, const CUten
       *reinterpret_cast<uint4*>(stg + o0) = f_to_bf8(lo);
       *reinterpret_cast<uint4*>(stg + o1) = f_to_bf8(hi);
     }
+    if (e.mul || e.add) {  // phase 2 on the staged tile: lanes sweep each row contiguously, the operands are read with 128-bit coalesced loads
+      __syncwarp();
+      const int cpr = store_cols >> 3, rpp = 32 / cpr;  // 2 / 4 / 8 lanes per row
+      const int rr = lane / cpr, ch = (lane - rr * cpr) * 8, co = n0 + c0 + ch;
+      const int64_t M = (int64_t)p.n * p.ho * p.wo;
+      if (co < p.cout) {
+        for (int row = rr; row < 32; row += rpp) {
+          const int64_t d = (int64_t)row0 + row;
+          if (d >= M) break;
+          const uint32_t a = stg_addr + (uint32_t)row * row_bytes + (uint32_t)ch * 2u;
+          uint4* cell = reinterpret_cast<uint4*>(stg + ((a ^ (((a >> 7) & swz_mask) << 4)) - stg_addr));
+          float v[8];
+          bf8_to_f(*cell, v);
+          if (e.mul) {
+            float mv[8];
+            bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.mul) + d * e.mul_ld + co), mv);
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] *= mv[i];
+          }
+          if (e.add) {
+            float adv[8];
+            bf8_to_f(ldg16(reinterpret_cast<const bf16*>(e.add) + d * e.add_ld + co), adv);
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] += adv[i];
+          }
+          *cell = f_to_bf8(v);
+        }
+      }
+    }
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
@@ -592,7 +621,7 @@ struct TmaParams {
   int a_bytes;          // bytes TMA writes per A box
   int tiles_n, total_tiles, acc_stages;
   int bk;               // K elements per chunk: 16 / 32 / 64 (smem row = 2*bk bytes, SWIZZLE_32B / 64B / 128B)
-  int store_cols;       // > 0: the epilogue leaves through TMA (1x1 convolutions without mul / add / batch statistics): every epilogue warp stages its
+  int store_cols;       // > 0: the epilogue leaves through TMA (1x1 convolutions without fused batch statistics): every epilogue warp stages its
                         //      32 rows x store_cols channels (16 / 32 / 64) in the swizzle of the output map and one lane issues a bulk tensor store
   int s2;               // stride-2 mode: 5-D parity-split map, coordinates (cpx[t] + ci, tx0 + dx[t], tpy[t], ty0 + dy[t], img)
   int cpx[MAX_TAPS], tpy[MAX_TAPS];
@@ -867,7 +896,7 @@ int launch_tma(TcParams& p, const yad_conv_desc* d, cudaStream_t st) {
     if (store_env < 0) { const char* ev = getenv("YAD_CONV_TMA_STORE"); store_env = (ev && ev[0] == '0') ? 0 : 1; }
     const int csplit = ((p.n_tile / 16 + 1) / 2) * 16;  // the column split of the two warps of a TMEM lane quarter (conv_tma_kernel)
     const int sc = csplit > 64 ? 64 : csplit;
-    if (store_env && !tp.patch && !p.e.mul && !p.e.add && !p.bn_stats && !p.out_f32 && (sc == 16 || sc == 32 || sc == 64) && csplit % sc == 0 &&
+    if (store_env && !tp.patch && !p.bn_stats && !p.out_f32 && (sc == 16 || sc == 32 || sc == 64) && csplit % sc == 0 &&
         p.n_tile - csplit == csplit && ((uintptr_t)p.y & 15) == 0) {
       const int64_t M = (int64_t)p.n * p.ho * p.wo;
       uint64_t dims[2] = {(uint64_t)p.cout, (uint64_t)M}, strides[1] = {(uint64_t)p.y_ld * 2};
