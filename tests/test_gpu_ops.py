@@ -118,6 +118,21 @@ def test_dwconv(dtype, k, gate):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("k", [3, 5, 7])
+def test_dwconv_row_strips(dtype, k):
+    """register-tiled depthwise kernel on a shape whose CTAs walk several row strips (grid.y < number of strips) with a ragged last strip"""
+    g = torch.Generator().manual_seed(40 + k)
+    n, c, h, w_ = 40, 256, 38, 13
+    x = q(torch.randn(n, c, h, w_, generator=g), dtype)
+    w = torch.randn(c, 1, k, k, generator=g) / k
+    b = torch.randn(c, generator=g) * 0.1
+    ref = F.conv2d(x, w, b, 1, k // 2, groups=c)
+    wk = w.reshape(c, k * k).t().contiguous().to(DEV)
+    out = ops.dwconv(to_act(x, dtype), wk, Act.empty(n, h, w_, c, dtype, DEV), bias=b.to(DEV), k=k)
+    assert rel_err(from_act(out), ref) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("c,groups,hw", [(128, 16, 20), (64, 16, 10), (64, 16, 41), (32, 8, 6)])
 def test_group_norm_silu_add(dtype, c, groups, hw):
     g = torch.Generator().manual_seed(c + hw)

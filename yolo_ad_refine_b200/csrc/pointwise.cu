@@ -297,6 +297,193 @@ __global__ void dwconv_kernel(yad_tensor x, const float* __restrict__ w, const f
   }
 }
 
+// Row-tiled depthwise K x K (the ungated case): a thread owns 8 channels of PX adjacent output pixels of one row.  Per kernel row it keeps the K
+// weight vectors in registers and streams the K + PX - 1 input columns once, so a 7x7 output costs (7 weight + 10 input) / 4 vector accesses per
+// kernel row instead of 7 + 7 (the L1 wavefront count, which bounds dwconv_kernel at k = 7, drops 3.5x).  Channel octets fastest -> every warp
+// load is made of full 128-byte segments.
+template <typename T, int K, int PX>
+__global__ void __launch_bounds__(128) dwconv_row_kernel(yad_tensor x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                         const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                                         const T* __restrict__ add, int add_ld, yad_tensor y, int groups_x, int total) {
+  pdl_sync();
+  constexpr int R = K / 2;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= total) return;
+  const int c = x.c, oct = c >> 3;
+  const int o = (item % oct) * 8;
+  int g = item / oct;
+  const int px0 = (g % groups_x) * PX;
+  g /= groups_x;
+  const int py = g % x.h, n = g / x.h;
+  const T* xb = reinterpret_cast<const T*>(x.ptr) + (int64_t)n * x.h * x.w * x.ld + o;
+  float acc[PX][8];
+  {
+    float bv[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) bv[i] = 0.f;
+    if (bias) load8(bias + o, bv);
+#pragma unroll
+    for (int p = 0; p < PX; p++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[p][i] = bv[i];
+  }
+#pragma unroll
+  for (int ky = 0; ky < K; ky++) {
+    const int iy = py + ky - R;
+    if (iy < 0 || iy >= x.h) continue;
+    float wr[K][8];
+#pragma unroll
+    for (int dx = 0; dx < K; dx++) load8(w + (ky * K + dx) * c + o, wr[dx]);
+    const T* xr = xb + (int64_t)iy * x.w * x.ld;
+#pragma unroll
+    for (int j = 0; j < K + PX - 1; j++) {
+      const int ix = px0 + j - R;
+      if (ix < 0 || ix >= x.w) continue;
+      float xv[8];
+      load8(xr + (int64_t)ix * x.ld, xv);
+#pragma unroll
+      for (int p = 0; p < PX; p++) {
+        const int dx = j - p;  // static after unrolling
+        if (dx < 0 || dx >= K) continue;
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[p][i] = fmaf(xv[i], wr[dx][i], acc[p][i]);
+      }
+    }
+  }
+  float sc[8], sh[8];
+  if (scale) { load8(scale + o, sc); load8(shift + o, sh); }
+#pragma unroll
+  for (int p = 0; p < PX; p++) {
+    if (px0 + p >= x.w) break;
+    if (scale) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[p][i] = fmaf(acc[p][i], sc[i], sh[i]);
+    }
+    apply_act_n<8>(acc[p], act);
+    const int64_t d = ((int64_t)n * x.h + py) * x.w + px0 + p;
+    if (add) {
+      float a[8];
+      load8(add + d * add_ld + o, a);
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[p][i] += a[i];
+    }
+    store8(reinterpret_cast<T*>(y.ptr) + d * y.ld + o, acc[p]);
+  }
+}
+
+// Shared-memory tiled depthwise K x K (ungated): a CTA owns a TH x TW output tile of one image and CC channels (64 bytes of T).  Phase 1 copies the
+// haloed (TH + K - 1) x (TW + K - 1) x CC input tile (zeros outside the image) and the K*K x CC weights to shared memory with 128-bit loads that
+// are all in flight together; phase 2 is dwconv_row_kernel's inner loop on shared memory (a thread = 8 channels x PX adjacent outputs, the K
+// weights of a kernel row in registers).  The K-fold re-read of every input row moves from L2 (whose latency bound dwconv_row_kernel, above all
+// on the 20x20 maps where a whole image is one tile) to shared memory.  Pixel pitch = 64 + 16 bytes: the two pixel groups of a quarter warp
+// (PX pixels apart) fall on disjoint banks.
+constexpr int DWS_PX = 4;
+constexpr int DWS_THREADS = 256;
+template <typename T, int K>
+__global__ void __launch_bounds__(DWS_THREADS, 2) dwconv_smem_kernel(yad_tensor x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                                  const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                                                  const T* __restrict__ add, int add_ld, yad_tensor y, int th, int tw,
+                                                                  int tiles_x, int tiles_y) {
+  constexpr int R = K / 2, CC = 64 / (int)sizeof(T), OCT = CC / 8, PITCH = 80, PIX_T = PITCH / (int)sizeof(T);
+  extern __shared__ __align__(16) uint8_t dws_sm[];
+  const int groups_x = (tw + DWS_PX - 1) / DWS_PX;
+  const int iw = groups_x * DWS_PX + K - 1, ih = th + K - 1;  // whole pixel groups: the inner loop never reads past the staged tile
+  float* wsm = reinterpret_cast<float*>(dws_sm);                       // [K*K][CC]
+  uint8_t* xsm = dws_sm + K * K * CC * sizeof(float);                  // [ih][iw] pixels of PITCH bytes
+  int b = blockIdx.x;
+  const int c0 = (b % (x.c / CC)) * CC;
+  b /= x.c / CC;
+  const int tx0 = (b % tiles_x) * tw;
+  b /= tiles_x;
+  const int ty0 = (b % tiles_y) * th, n = b / tiles_y;
+  for (int i = threadIdx.x; i < K * K * (CC / 4); i += blockDim.x) {
+    const int t = i / (CC / 4), q = i - t * (CC / 4);
+    reinterpret_cast<float4*>(wsm)[i] = *reinterpret_cast<const float4*>(w + t * x.c + c0 + q * 4);
+  }
+  pdl_sync();
+  const uint8_t* xb = reinterpret_cast<const uint8_t*>(reinterpret_cast<const T*>(x.ptr) + (int64_t)n * x.h * x.w * x.ld + c0);
+  const int64_t pix_bytes = (int64_t)x.ld * sizeof(T);
+#pragma unroll 4
+  for (int v = threadIdx.x; v < ih * iw * 4; v += blockDim.x) {
+    const int pix = v >> 2, part = v & 3;
+    const int r = pix / iw, cx = pix - r * iw;
+    const int iy = ty0 + r - R, ix = tx0 + cx - R;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < x.h && ix >= 0 && ix < x.w) val = *reinterpret_cast<const uint4*>(xb + ((int64_t)iy * x.w + ix) * pix_bytes + part * 16);
+    *reinterpret_cast<uint4*>(xsm + pix * PITCH + part * 16) = val;
+  }
+  __syncthreads();
+  for (int item = threadIdx.x; item < th * groups_x * OCT; item += blockDim.x) {
+    const int oi = item % OCT;
+    const int g = item / OCT;
+    const int ry = g / groups_x, rx0 = (g - ry * groups_x) * DWS_PX;
+    const int o = c0 + oi * 8;
+    const int oy = ty0 + ry;
+    if (oy >= x.h || tx0 + rx0 >= x.w) continue;
+    float acc[DWS_PX][8];
+    {
+      float bv[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) bv[i] = 0.f;
+      if (bias) load8(bias + o, bv);
+#pragma unroll
+      for (int p = 0; p < DWS_PX; p++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[p][i] = bv[i];
+    }
+#pragma unroll 1  // one kernel row per trip keeps the loop body (K + PX - 1 loads, K * PX * 8 FMAs) inside the instruction cache
+    for (int ky = 0; ky < K; ky++) {
+      float wr[K][8];
+#pragma unroll
+      for (int dx = 0; dx < K; dx++) load8(wsm + (ky * K + dx) * CC + oi * 8, wr[dx]);
+      const T* xr = reinterpret_cast<const T*>(xsm) + ((ry + ky) * iw + rx0) * PIX_T + oi * 8;
+#pragma unroll
+      for (int j = 0; j < K + DWS_PX - 1; j++) {
+        float xv[8];
+        load8(xr + j * PIX_T, xv);
+#pragma unroll
+        for (int p = 0; p < DWS_PX; p++) {
+          const int dx = j - p;  // static after unrolling
+          if (dx < 0 || dx >= K) continue;
+#pragma unroll
+          for (int i = 0; i < 8; i++) acc[p][i] = fmaf(xv[i], wr[dx][i], acc[p][i]);
+        }
+      }
+    }
+    float sc[8], sh[8];
+    if (scale) { load8(scale + o, sc); load8(shift + o, sh); }
+#pragma unroll
+    for (int p = 0; p < DWS_PX; p++) {
+      const int ox = tx0 + rx0 + p;
+      if (rx0 + p >= tw || ox >= x.w) break;
+      if (scale) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[p][i] = fmaf(acc[p][i], sc[i], sh[i]);
+      }
+      apply_act_n<8>(acc[p], act);
+      const int64_t d = ((int64_t)n * x.h + oy) * x.w + ox;
+      if (add) {
+        float a[8];
+        load8(add + d * add_ld + o, a);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[p][i] += a[i];
+      }
+      store8(reinterpret_cast<T*>(y.ptr) + d * y.ld + o, acc[p]);
+    }
+  }
+}
+
+// tile edge for a map edge: whole edge up to 24, else the edge in [12, 24] that wastes the fewest rows (ties -> larger)
+inline int dws_tile(int n) {
+  if (n <= 24) return n;
+  int best = 24, waste = 1 << 30;
+  for (int t = 24; t >= 12; t--) {
+    const int wst = (n + t - 1) / t * t - n;
+    if (wst < waste) { waste = wst; best = t; }
+  }
+  return best;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // SPPF: 5x5 / 9x9 / 13x13 max windows (= three chained 5x5 s1 p2 max-pools with -inf padding)
 // ------------------------------------------------------------------------------------------------------------------
@@ -949,6 +1136,52 @@ int yad_dwconv(const yad_tensor* x, const float* w, const float* bias, const flo
   YAD_CHECK(gate_split > 0 ? (x->c == 2 * gate_split && y->c == gate_split) : (x->c == y->c), "dwconv: channel mismatch");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)y->n * y->h * y->w * (y->c / 8);
+  static int row_env = -1;
+  if (row_env < 0) { const char* ev = getenv("YAD_DWCONV_ROW"); row_env = ev ? atoi(ev) : 1; }  // 0: dwconv_kernel, 1: shared-memory tiles, 2: dwconv_row_kernel
+  if (row_env && gate_split == 0 && total > 0 && ((((uintptr_t)w) | ((uintptr_t)bias) | ((uintptr_t)scale) | ((uintptr_t)shift)) & 15) == 0) {
+    const int cc = 64 / (dtype == YAD_BF16 ? 2 : 4);
+    if (row_env != 2 && y->c % cc == 0) {
+      const int th = dws_tile(y->h), tw = dws_tile(y->w);
+      const int tiles_y = (y->h + th - 1) / th, tiles_x = (y->w + tw - 1) / tw;
+      const int64_t ctas = (int64_t)y->n * tiles_y * tiles_x * (y->c / cc);
+      const size_t smem = (size_t)k * k * cc * sizeof(float) + (size_t)(th + k - 1) * ((tw + DWS_PX - 1) / DWS_PX * DWS_PX + k - 1) * 80;
+      // threads: the tile's items (8 channels x 4 pixels) spread evenly over the fewest passes of at most 256 threads
+      const int items = th * ((tw + DWS_PX - 1) / DWS_PX) * (cc / 8), passes = (items + DWS_THREADS - 1) / DWS_THREADS;
+      const int threads = ((items + passes - 1) / passes + 31) / 32 * 32;
+      if (ctas < ((int64_t)1 << 31)) {
+#define DW_SMEM(KK)                                                                                                               \
+  YAD_DISPATCH_DTYPE(dtype, {                                                                                                     \
+    static bool attr = false;                                                                                                     \
+    if (!attr) { cudaFuncSetAttribute(dwconv_smem_kernel<T, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; } \
+    YAD_LAUNCH((dwconv_smem_kernel<T, KK>), (unsigned)ctas, threads, smem, st, *x, w, bias, scale, shift, act, (const T*)add, add_ld, *y, th, \
+               tw, tiles_x, tiles_y);                                                                                             \
+  })
+        if (k == 3) { DW_SMEM(3) } else if (k == 5) { DW_SMEM(5) } else { DW_SMEM(7) }
+#undef DW_SMEM
+        YAD_LAUNCH_CHECK("dwconv");
+        return 0;
+      }
+    }
+    // PX adjacent outputs per thread, as many as still leave >= 16 warps per SM (small maps keep their parallelism)
+    const int64_t rows = (int64_t)y->n * y->h * (y->c / 8);
+    int px = 4;
+    while (px > 1 && rows * ((y->w + px - 1) / px) < (int64_t)148 * 16 * 32) px >>= 1;
+    const int groups_x = (y->w + px - 1) / px;
+    const int64_t items = rows * groups_x;
+    if (px > 1 && items < ((int64_t)1 << 31)) {
+#define DW_ROW(KK, PP)                                                                                                          \
+  YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH((dwconv_row_kernel<T, KK, PP>), (unsigned)((items + 127) / 128), 128, 0, st, *x, w, bias, scale, shift, \
+                                       act, (const T*)add, add_ld, *y, groups_x, (int)items);)
+      if (px == 4) {
+        if (k == 3) { DW_ROW(3, 4) } else if (k == 5) { DW_ROW(5, 4) } else { DW_ROW(7, 4) }
+      } else {
+        if (k == 3) { DW_ROW(3, 2) } else if (k == 5) { DW_ROW(5, 2) } else { DW_ROW(7, 2) }
+      }
+#undef DW_ROW
+      YAD_LAUNCH_CHECK("dwconv");
+      return 0;
+    }
+  }
   YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(dwconv_kernel<T>, grid_for(total, 128), 128, 0, st, *x, w, bias, scale, shift, k, act, gate_split,
                                                                                     (const T*)add, add_ld, *y);)
   YAD_LAUNCH_CHECK("dwconv");
