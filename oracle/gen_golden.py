@@ -401,7 +401,34 @@ def gen_mona_block():
         json.dump(shapes, f)
 
 
+def gen_psa_block():
+    """C2PSA.forward of the live reference (nn/modules/block.py:874-964, 1010-1049, eval) on seeded parameters: pins oracle/psa.py (Attention with
+    its per-head [q | k | v] interleave and key_dim = head_dim / 2, PSABlock, the C2PSA split) and, through it, the yad_mha-based composition of
+    yolo_ad_refine_b200.functional.c2psa.  Key sets and shapes come from the reference module."""
+    from oracle.mona import make_block_state, make_input
+    from oracle.psa import PSA_CASES
+    from ultralytics.nn.modules.block import C2PSA
+    d, shapes = {}, {}
+    for name, (c, nb, n, h, w, seed) in PSA_CASES.items():
+        m = C2PSA(c, c, nb).eval()
+        for mod in m.modules():  # what initialize_weights does to every BatchNorm2d of a DetectionModel (utils/torch_utils.py:426-436)
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.eps, mod.momentum = 1e-3, 0.03
+        shapes[name] = {k: list(v.shape) for k, v in m.state_dict().items()}
+        sd = make_block_state(shapes[name], seed)
+        m.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            y = m(make_input(c, n, h, w, seed))
+        d[name] = y.numpy()[:, ::4]   # every fourth channel
+        print("psa block", name, tuple(y.shape), float(y.abs().mean()), len(sd), "keys")
+    np.savez_compressed(os.path.join(GOLD, "psa_block.npz"), **d)
+    with open(os.path.join(GOLD, "psa_block_spec.json"), "w") as f:
+        json.dump(shapes, f)
+
+
 def main():
+    if sys.argv[1:] == ["psa_block"]:
+        return gen_psa_block()
     if sys.argv[1:] == ["mona_block"]:
         return gen_mona_block()
     if sys.argv[1:] == ["mona"]:

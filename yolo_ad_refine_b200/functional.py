@@ -248,6 +248,72 @@ def c2tssa_dyt_mona_edffn(ctx, p, x, n=1):
     return conv_bn_act(ctx, p + ".cv2", ab)
 
 
+def psa_attention(ctx, p, x, heads, add=None, out=None):
+    """nn/modules/block.py:874-925 Attention(dim, num_heads, attn_ratio=0.5).forward on an NHWC map, head_dim 64 (C2PSA builds num_heads = c // 64):
+    qkv 1x1 (+ folded BN) -> softmax(q^T k * key_dim^-0.5) v per head on yad_mha -> + pe(v) (depthwise 3x3 + BN) -> proj 1x1 (+ the block's residual
+    in its epilogue).  The reference interleaves [q | k | v] per head with key_dim = head_dim / 2; the qkv rows are re-ordered at weight-packing
+    time into the [Q | K | V] thirds yad_mha reads, q / k zero-padded to 64 channels per head (zero channels add nothing to q . k) and the q rows
+    scaled by sqrt(64 / key_dim) so that the kernel's 1 / sqrt(64) becomes key_dim^-0.5."""
+    P = ctx.P
+    n, h, w, c = x.n, x.h, x.w, x.c
+    hd = c // heads
+    assert hd == 64, "psa_attention: head_dim 64 only (yad_mha)"
+
+    def fold_qkv():
+        wq, bq = P.sd[p + ".qkv.conv.weight"].float(), None
+        if p + ".qkv.bn.weight" in P.sd:
+            wq, bq = fold_bn(wq, P.sd[p + ".qkv.bn.weight"].float(), P.sd[p + ".qkv.bn.bias"].float(), P.sd[p + ".qkv.bn.running_mean"].float(),
+                             P.sd[p + ".qkv.bn.running_var"].float(), P.sd.get(p + ".qkv.conv.bias"))
+        else:
+            bq = P.sd[p + ".qkv.conv.bias"].float()
+        kd = (wq.shape[0] // heads - hd) // 2
+        per = 2 * kd + hd
+        wn, bn = torch.zeros(3 * c, c, 1, 1), torch.zeros(3 * c)
+        qs = (hd / kd) ** 0.5
+        for i in range(heads):
+            src = i * per
+            wn[i * hd:i * hd + kd], bn[i * hd:i * hd + kd] = wq[src:src + kd] * qs, bq[src:src + kd] * qs
+            wn[c + i * hd:c + i * hd + kd], bn[c + i * hd:c + i * hd + kd] = wq[src + kd:src + 2 * kd], bq[src + kd:src + 2 * kd]
+            wn[2 * c + i * hd:2 * c + (i + 1) * hd], bn[2 * c + i * hd:2 * c + (i + 1) * hd] = wq[src + 2 * kd:src + per], bq[src + 2 * kd:src + per]
+        return wn, bn
+
+    wn, bn = P.misc(p + ".qkv#mha", fold_qkv)
+    qkv = conv(ctx, x, P.conv_raw(p + ".qkv#mha", wn, bn))
+    att = ops.mha(qkv, heads, ctx.act(n, h, w, c))
+
+    def fold_pe():
+        wp, bp = P.sd[p + ".pe.conv.weight"].float(), None
+        if p + ".pe.bn.weight" in P.sd:
+            wp, bp = fold_bn(wp, P.sd[p + ".pe.bn.weight"].float(), P.sd[p + ".pe.bn.bias"].float(), P.sd[p + ".pe.bn.running_mean"].float(),
+                             P.sd[p + ".pe.bn.running_var"].float(), P.sd.get(p + ".pe.conv.bias"))
+        else:
+            bp = P.sd[p + ".pe.conv.bias"].float()
+        return wp.reshape(c, 9).t().contiguous().to(P.device), bp.contiguous().to(P.device)
+
+    wpe, bpe = P.misc(p + ".pe#dw", fold_pe)
+    t = ops.dwconv(qkv.slice(2 * c, c), wpe, ctx.act(n, h, w, c), bias=bpe, k=3, add=att)  # pe(v) + attention output
+    return conv(ctx, t, P.conv_bn(p + ".proj"), out=out, add=add)
+
+
+def psablock(ctx, p, x, heads, out=None):
+    """nn/modules/block.py:928-964 PSABlock.forward (shortcut=True): x = x + attn(x); x = x + ffn(x)"""
+    t = psa_attention(ctx, p + ".attn", x, heads, add=x)
+    f = conv(ctx, t, ctx.P.conv_bn(p + ".ffn.0"), act=ACT_SILU)
+    return conv(ctx, f, ctx.P.conv_bn(p + ".ffn.1"), out=out, add=t)
+
+
+def c2psa(ctx, p, x, n=1):
+    """nn/modules/block.py:1010-1049 C2PSA.forward: cv1 -> split (a, b) -> n PSABlocks on b -> cv2 over [a | b] (no concat buffer: b is written back
+    into its half of cv1's output)"""
+    c = ctx.P.conv_bn(p + ".cv1").cout // 2
+    ab = conv_bn_act(ctx, p + ".cv1", x)
+    b = ab.slice(c, c)
+    cur = b
+    for i in range(n):
+        cur = psablock(ctx, f"{p}.m.{i}", cur, heads=c // 64, out=b if i == n - 1 else None)
+    return conv_bn_act(ctx, p + ".cv2", ab)
+
+
 def fusion_bifpn(ctx, p, xs):
     """nn/modules/block.py:1532-1535 Fusion('bifpn') for two inputs"""
     w = torch.relu(ctx.P.sd[p + ".fusion_weight"].float())

@@ -363,6 +363,51 @@ class C2TSSA_DYT_Mona_EDFFN(YadModule):
         return Fn.c2tssa_dyt_mona_edffn(self._ctx(a), "m", a, self.n).nchw()
 
 
+class Attention(_Holder):
+    """nn/modules/block.py:874-925 Attention(dim, num_heads=8, attn_ratio=0.5) (parameter holder)"""
+
+    def __init__(self, dim, num_heads=8, attn_ratio=0.5):
+        super().__init__()
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        self.key_dim = int(self.head_dim * attn_ratio)
+        self.scale = self.key_dim ** -0.5
+        self.qkv = _conv_holder(dim, dim + 2 * self.key_dim * num_heads, 1)
+        self.proj = _conv_holder(dim, dim, 1)
+        self.pe = _conv_holder(dim, dim, 3, 1, g=dim)
+
+
+class PSABlock(_Holder):
+    """nn/modules/block.py:928-964 PSABlock(c, attn_ratio=0.5, num_heads=4, shortcut=True) (parameter holder; C2PSA runs the fused forward)"""
+
+    def __init__(self, c, attn_ratio=0.5, num_heads=4, shortcut=True):
+        super().__init__()
+        assert shortcut
+        self.attn = Attention(c, attn_ratio=attn_ratio, num_heads=num_heads)
+        self.ffn = nn.Sequential(_conv_holder(c, c * 2, 1), _conv_holder(c * 2, c, 1))
+        self.add = shortcut
+
+
+class C2PSA(YadModule):
+    """nn/modules/block.py:1010-1049 C2PSA(c1, c2, n=1, e=0.5): layer 10 of the stock yolo11 yaml and of the sibling ablation yamls that keep the
+    PSABlock attention.  Same constructor, attribute and state-dict key names as the reference."""
+
+    def __init__(self, c1, c2, n=1, e=0.5):
+        super().__init__()
+        assert c1 == c2
+        self.c = int(c1 * e)
+        assert self.c % 64 == 0, "head_dim is 64: the hidden width must be a multiple of 64"
+        self.n = n
+        self.cv1 = _conv_holder(c1, 2 * self.c, 1, 1)
+        self.cv2 = _conv_holder(2 * self.c, c1, 1)
+        self.m = nn.Sequential(*(PSABlock(self.c, attn_ratio=0.5, num_heads=self.c // 64) for _ in range(n)))
+
+    def forward(self, x):
+        self._check_eval()
+        a = as_act(x)
+        return Fn.c2psa(self._ctx(a), "m", a, self.n).nchw()
+
+
 class Multiply(nn.Module):
     """nn/modules/block.py:1442-1447"""
 

@@ -18,7 +18,9 @@ from . import tal as ytal
 
 BLOCKS = ["Conv", "C3k2", "C3k2_MLCA", "SPPF", "C2PTSSA", "C2ProgressiveTSSA_Fusion", "ELA_HSFPN", "Multiply", "Add", "Fusion",
           # layer 10 of the yolo11-mona / 687 / 689 / 697 sibling yamls
-          "C2TSSA_DYT_Mona_EDFFN", "TSSAlock_DYT_Mona_EDFFN", "DynamicTanh", "AttentionTSSA", "Mona", "MonaOp"]
+          "C2TSSA_DYT_Mona_EDFFN", "TSSAlock_DYT_Mona_EDFFN", "DynamicTanh", "AttentionTSSA", "Mona", "MonaOp",
+          # the stock yolo11 attention block the other sibling yamls keep at layer 10
+          "C2PSA", "PSABlock", "Attention"]
 HEADS = ["AYHead", "AYHead1"]
 
 
