@@ -426,7 +426,38 @@ def gen_psa_block():
         json.dump(shapes, f)
 
 
+def gen_sfa_block():
+    """C2SFA.forward of the live reference (nn/modules/block.py:2049-2202, 2358-2373, eval) on seeded parameters: pins oracle/psa.py's C2SFA
+    restatement and the composition yolo_ad_refine_b200.functional.c2sfa.  residual_weight1 / 2 are lifted to O(1) so that both branches carry weight."""
+    from oracle.mona import make_block_state, make_input
+    from oracle.psa import SFA_CASES
+    from ultralytics.nn.modules.block import C2SFA
+    d, shapes = {}, {}
+    for name, (c, nb, n, h, w, seed) in SFA_CASES.items():
+        m = C2SFA(c, c, nb).eval()
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.eps, mod.momentum = 1e-3, 0.03
+        shapes[name] = {k: list(v.shape) for k, v in m.state_dict().items()}
+        sd = sfa_state(shapes[name], seed)
+        m.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            y = m(make_input(c, n, h, w, seed))
+        d[name] = y.numpy()[:, ::4]   # every fourth channel
+        print("sfa block", name, tuple(y.shape), float(y.abs().mean()), len(sd), "keys")
+    np.savez_compressed(os.path.join(GOLD, "sfa_block.npz"), **d)
+    with open(os.path.join(GOLD, "sfa_block_spec.json"), "w") as f:
+        json.dump(shapes, f)
+
+
+def sfa_state(shapes, seed):
+    from oracle.psa import sfa_state as f
+    return f(shapes, seed)
+
+
 def main():
+    if sys.argv[1:] == ["sfa_block"]:
+        return gen_sfa_block()
     if sys.argv[1:] == ["psa_block"]:
         return gen_psa_block()
     if sys.argv[1:] == ["mona_block"]:

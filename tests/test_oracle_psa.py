@@ -41,3 +41,27 @@ def test_plugin_lists_psa_blocks():
     from yolo_ad_refine_b200 import plugin
     for name in ("C2PSA", "PSABlock", "Attention"):
         assert name in plugin.BLOCKS and hasattr(M, name)
+
+
+def _sfa_case(name):
+    spec = json.load(open(os.path.join(GOLD, "sfa_block_spec.json")))[name]
+    c, nb, n, h, w, seed = op.SFA_CASES[name]
+    return op.sfa_state(spec, seed), make_input(c, n, h, w, seed), nb, c, spec
+
+
+@pytest.mark.parametrize("name", list(op.SFA_CASES))
+def test_sfa_oracle_matches_reference(gold, name):
+    sd, x, nb, _, _ = _sfa_case(name)
+    y = op.c2sfa({"m." + k: v for k, v in sd.items()}, x, nb).numpy()
+    np.testing.assert_allclose(y[:, ::4], gold("sfa_block.npz")[name], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", list(op.SFA_CASES))
+def test_c2sfa_module_state_dict_keys(name):
+    from yolo_ad_refine_b200.modules import C2SFA
+    sd, _, nb, c, spec = _sfa_case(name)
+    m = C2SFA(c, c, nb)
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == spec
+    m.load_state_dict(sd, strict=True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.eval()(torch.zeros(1, c, 8, 8))  # no CPU fallback

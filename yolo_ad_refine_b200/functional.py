@@ -314,6 +314,49 @@ def c2psa(ctx, p, x, n=1):
     return conv_bn_act(ctx, p + ".cv2", ab)
 
 
+def simple_feature_processor(ctx, p, x, alpha=1.0):
+    """nn/modules/block.py:2080-2096 SimpleFeatureProcessor: GroupNorm(c // 32 groups) -> depthwise 3x3 (+ bias) -> GELU -> 1x1 (+ bias); alpha scales
+    the output in the last epilogue"""
+    P = ctx.P
+    n, h, w, c = x.n, x.h, x.w, x.c
+    g = max(1, c // 32)
+    t = ops.group_norm(x, ctx.act(n, h, w, c), ctx.f64(n, g, 2), g, P.f32(p + ".norm.weight"), P.f32(p + ".norm.bias"), GN_EPS, ACT_NONE)
+    dw, db, _ = P.dw(p + ".conv_dw.weight", p + ".conv_dw.bias")
+    t = ops.dwconv(t, dw, ctx.act(n, h, w, c), bias=db, k=3, act=ops.ACT_GELU)
+    return conv(ctx, t, P.conv(p + ".conv_pw.weight", p + ".conv_pw.bias"), alpha=alpha)
+
+
+def progressive_tssa_fusion0(ctx, p, x, out=None):
+    """nn/modules/block.py:2147-2202 ProgressiveTSSA_Fusion0.forward (shortcut=True):
+    x = x + SE(pre_attn_block(x)) * residual_weight1;  x = x + ffn(pre_ffn_block(x)) * residual_weight2.
+    SEBlock (:2049-2064) = t * sigmoid(W2 relu(W1 mean(t))): residual_weight1 rides on t through the 1x1 epilogue (and 1 / residual_weight1 on W1, so
+    that the gate still sees mean(t)); gate on yad_gap + yad_gate_mlp, gate * t + x in one yad_mlca_apply (local_size 1 = one gate per image)."""
+    P = ctx.P
+    n, h, w, c = x.n, x.h, x.w, x.c
+    rw1, rw2 = P.scalar(p + ".residual_weight1"), P.scalar(p + ".residual_weight2")
+    t = simple_feature_processor(ctx, p + ".pre_attn_block", x, alpha=rw1)
+    avg = ops.gap(t, ctx.f32(n, c))
+    w1 = P.misc(p + ".se1", lambda: (P.sd[p + ".attn.fc.0.weight"].float().reshape(-1, c) / (rw1 if rw1 != 0.0 else 1.0)).contiguous().to(P.device))
+    w2 = P.misc(p + ".se2", lambda: P.sd[p + ".attn.fc.2.weight"].float().reshape(c, -1).contiguous().to(P.device))
+    zb = P.misc(f"zeros.{c}", lambda: torch.zeros(c, dtype=torch.float32, device=P.device))
+    gate = ops.gate_mlp(avg, w1, zb, w2, zb, ctx.f32(n, c), kind=0)
+    y = ops.mlca_apply(t, gate, 1, ctx.act(n, h, w, c), add=x)
+    u = simple_feature_processor(ctx, p + ".pre_ffn_block", y)
+    f = conv(ctx, u, P.conv(p + ".ffn.cv1.weight"), act=ops.ACT_GELU)
+    return conv(ctx, f, P.conv(p + ".ffn.cv2.weight"), out=out, alpha=rw2, add=y)
+
+
+def c2sfa(ctx, p, x, n=1):
+    """nn/modules/block.py:2358-2373 C2SFA + C2PSA.forward :1045-1049 (split, n ProgressiveTSSA_Fusion0 blocks on b, concat-free cv2)"""
+    c = ctx.P.conv_bn(p + ".cv1").cout // 2
+    ab = conv_bn_act(ctx, p + ".cv1", x)
+    b = ab.slice(c, c)
+    cur = b
+    for i in range(n):
+        cur = progressive_tssa_fusion0(ctx, f"{p}.m.{i}", cur, out=b if i == n - 1 else None)
+    return conv_bn_act(ctx, p + ".cv2", ab)
+
+
 def fusion_bifpn(ctx, p, xs):
     """nn/modules/block.py:1532-1535 Fusion('bifpn') for two inputs"""
     w = torch.relu(ctx.P.sd[p + ".fusion_weight"].float())

@@ -408,6 +408,74 @@ class C2PSA(YadModule):
         return Fn.c2psa(self._ctx(a), "m", a, self.n).nchw()
 
 
+class SEBlock(_Holder):
+    """nn/modules/block.py:2049-2064 (parameter holder)"""
+
+    def __init__(self, c1, r=16):
+        super().__init__()
+        c_ = int(c1 / r)
+        self.avgpool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Sequential(nn.Conv2d(c1, c_, 1, bias=False), nn.ReLU(inplace=True), nn.Conv2d(c_, c1, 1, bias=False), nn.Sigmoid())
+
+
+class StandardFFN(_Holder):
+    """nn/modules/block.py:2066-2078 (parameter holder)"""
+
+    def __init__(self, c1, expansion=2, bias=False):
+        super().__init__()
+        assert not bias
+        c_ = int(c1 * expansion)
+        self.cv1 = nn.Conv2d(c1, c_, 1, bias=bias)
+        self.act = nn.GELU()
+        self.cv2 = nn.Conv2d(c_, c1, 1, bias=bias)
+
+
+class SimpleFeatureProcessor(_Holder):
+    """nn/modules/block.py:2080-2096 (parameter holder)"""
+
+    def __init__(self, c):
+        super().__init__()
+        self.norm = nn.GroupNorm(num_groups=max(1, c // 32), num_channels=c)
+        self.conv_dw = nn.Conv2d(c, c, 3, padding=1, groups=c)
+        self.act = nn.GELU()
+        self.conv_pw = nn.Conv2d(c, c, 1)
+
+
+class ProgressiveTSSA_Fusion0(_Holder):
+    """nn/modules/block.py:2147-2172 (parameter holder; C2SFA runs the fused forward)"""
+
+    def __init__(self, c, attn_ratio=0.5, num_heads=4, shortcut=True):
+        super().__init__()
+        assert shortcut
+        self.c, self.add = c, shortcut
+        self.pre_attn_block = SimpleFeatureProcessor(c)
+        self.attn = SEBlock(c)
+        self.pre_ffn_block = SimpleFeatureProcessor(c)
+        self.ffn = StandardFFN(c, expansion=2, bias=False)
+        self.residual_weight1 = nn.Parameter(torch.tensor(0.1))
+        self.residual_weight2 = nn.Parameter(torch.tensor(0.1))
+
+
+class C2SFA(YadModule):
+    """nn/modules/block.py:2358-2373 C2SFA(c1, c2, n=1, e=0.5) (C2PSA base :1010-1049): layer 10 of yolo11-hsfpn+C2SFA.yaml and two more sibling yamls
+    (SURVEY.md section 8f rank 3).  Same constructor, attribute and state-dict key names as the reference."""
+
+    def __init__(self, c1, c2, n=1, e=0.5):
+        super().__init__()
+        assert c1 == c2
+        self.c = int(c1 * e)
+        assert self.c % 32 == 0, "the hidden width must be a multiple of 32 (GroupNorm groups of 32 channels, 8-channel vectors)"
+        self.n = n
+        self.cv1 = _conv_holder(c1, 2 * self.c, 1, 1)
+        self.cv2 = _conv_holder(2 * self.c, c1, 1)
+        self.m = nn.Sequential(*(ProgressiveTSSA_Fusion0(self.c, num_heads=max(1, self.c // 64), shortcut=True) for _ in range(n)))
+
+    def forward(self, x):
+        self._check_eval()
+        a = as_act(x)
+        return Fn.c2sfa(self._ctx(a), "m", a, self.n).nchw()
+
+
 class Multiply(nn.Module):
     """nn/modules/block.py:1442-1447"""
 

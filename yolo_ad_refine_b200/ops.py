@@ -209,6 +209,14 @@ def mlca(x, y, w_global, w_local, ksize, local, att, local_size=5, local_weight=
     return y
 
 
+def mlca_apply(x, att, local_size, y, add=None):
+    """y = x * adaptive_avg_pool(att fp32 [n][local_size^2][c] -> (h, w)) (+ add); local_size 1 = one gate per (image, channel) (SEBlock)"""
+    assert att.dtype == torch.float32 and att.numel() == x.n * local_size * local_size * x.c
+    adp, ald = _ap(add)
+    _call("yad_mlca_apply", x.yt(), _p(att), local_size, adp, ald, y.yt(), dt(x.dtype), stream_ptr())
+    return y
+
+
 def gate_mlp(g, w1, b1, w2, b2, out, kind):
     n, c = g.shape
     hidden, nout = w1.shape[0], w2.shape[0]

@@ -20,7 +20,9 @@ BLOCKS = ["Conv", "C3k2", "C3k2_MLCA", "SPPF", "C2PTSSA", "C2ProgressiveTSSA_Fus
           # layer 10 of the yolo11-mona / 687 / 689 / 697 sibling yamls
           "C2TSSA_DYT_Mona_EDFFN", "TSSAlock_DYT_Mona_EDFFN", "DynamicTanh", "AttentionTSSA", "Mona", "MonaOp",
           # the stock yolo11 attention block the other sibling yamls keep at layer 10
-          "C2PSA", "PSABlock", "Attention"]
+          "C2PSA", "PSABlock", "Attention",
+          # yolo11-hsfpn+C2SFA.yaml and its copies
+          "C2SFA", "ProgressiveTSSA_Fusion0", "SimpleFeatureProcessor", "SEBlock", "StandardFFN"]
 HEADS = ["AYHead", "AYHead1"]
 
 
