@@ -291,3 +291,21 @@ def test_stem_conv(dtype, u8):
     wq = (w / 255.0 if u8 else w).permute(0, 2, 3, 1).reshape(16, -1).contiguous()
     y = ops.stem_conv(img.to(DEV), wq.to(DEV), b.to(DEV), Act.empty(2, 32, 48, 16, dtype, DEV))
     assert rel_err(from_act(y), ref) < tol(dtype)
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 640, 640), (3, 62, 304), (2, 34, 1040), (1, 8, 16), (2, 30, 300)])
+def test_stem_conv_tensor_core_u8(n, h, w):
+    """stem_tc_kernel (uint8 image, bf16 storage: mma.sync implicit GEMM) on whole / ragged 128-pixel row segments, odd output heights, image borders
+    and a map narrower than one MMA tile; f16 weights (11 bits) + bf16 output rounding: <= tol(bf16) against the fp32 convolution"""
+    g = torch.Generator().manual_seed(h + w)
+    img = torch.randint(0, 256, (n, 3, h, w), generator=g, dtype=torch.uint8)
+    wt = torch.randn(16, 3, 3, 3, generator=g) / 5
+    b = torch.randn(16, generator=g) * 0.1
+    ref = F.silu(F.conv2d(img.float() / 255.0, wt, b, 2, 1))
+    wq = (wt / 255.0).permute(0, 2, 3, 1).reshape(16, -1).contiguous()
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = ops.stem_conv(img.to(DEV), wq.to(DEV), b.to(DEV), Act.empty(n, ho, wo, 16, torch.bfloat16, DEV))
+    assert rel_err(from_act(y), ref) < tol(torch.bfloat16)
+    # the f16 tensor-core path against the fp32-weight SIMT kernel on the same input: they differ by the weight rounding only
+    y32 = ops.stem_conv(img.to(DEV), wq.to(DEV), b.to(DEV), Act.empty(n, ho, wo, 16, torch.float32, DEV))
+    assert rel_err(from_act(y), from_act(y32)) < tol(torch.bfloat16)

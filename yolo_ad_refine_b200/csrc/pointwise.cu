@@ -1,5 +1,7 @@
 // Memory-bound refinement-block kernels (NHWC, 128-bit vector access on 8 consecutive channels, smem staging and
 // warp-shuffle reductions where a reduction is involved).  Each entry point cites the reference operator it replaces.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -43,6 +45,43 @@ __global__ void u8_to_nhwc_kernel(const uint8_t* __restrict__ src, int c_src, fl
     }
   }
 }
+
+// packed 8-channel vectors: loads stay in their storage format (4 registers for bf16) until they are consumed, so that several can be in flight
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> { uint4 u; };
+template <> struct Raw8<float> { float4 a, b; };
+__device__ __forceinline__ void raw_load(const bf16* p, Raw8<bf16>& r) { r.u = *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void raw_load(const float* p, Raw8<float>& r) {
+  r.a = *reinterpret_cast<const float4*>(p);
+  r.b = *reinterpret_cast<const float4*>(p + 4);
+}
+__device__ __forceinline__ void raw_unpack(const Raw8<bf16>& r, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void raw_unpack(const Raw8<float>& r, float (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+__device__ __forceinline__ float tanh_approx_pw(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// bf16 storage: SiLU / sigmoid on one MUFU (tanh.approx, 2^-11 relative -- below the bf16 rounding of the result); fp32 storage keeps apply_act_n
+template <typename T, int N = 8>
+__device__ __forceinline__ void apply_act_store_n(float (&v)[N], int act) {
+  if (sizeof(T) == 2 && act == YAD_ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < N; i++) { const float h = 0.5f * v[i]; v[i] = fmaf(h, tanh_approx_pw(h), h); }
+  } else if (sizeof(T) == 2 && act == YAD_ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = fmaf(0.5f, tanh_approx_pw(0.5f * v[i]), 0.5f);
+  } else {
+    apply_act_n<N>(v, act);
+  }
+}
+
 
 // ------------------------------------------------------------------------------------------------------------------
 // Stem: layer 0 of the model (Conv 3->16, k3 s2 p1, BN folded, SiLU) straight from the NCHW image (uint8 or fp32) to NHWC.
@@ -129,6 +168,129 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const IN* __restrict__ i
   }
 }
 
+// Tensor-core stem for uint8 images with 3 channels and bf16 storage: the same Conv(3 -> 16, k3 s2 p1) + bias + activation as an implicit GEMM
+// M = 128 output pixels of one row per CTA (4 warps x 2 m16 tiles), N = 16 (2 n8 tiles), K = 27 zero-padded to 32 (2 k16 steps) on
+// mma.sync.m16n8k16 (f16 x f16 -> f32).  uint8 pixels are exact in f16 and reach the A fragments without a single I2F: two bytes are merged with
+// the f16 magic 0x6400 (= 1024.0, ulp 1) and one packed HSUB2 removes the 1024.  The weights arrive with the predictor's 1/255 folded in (fp32);
+// they are scaled back by 255 before the f16 rounding (keeps them far from the f16 subnormals) and the 1/255 moves to the epilogue.  The SIMT
+// kernel above spends 432 FFMA + 135 shared-memory loads per output pixel; this one 8 MMAs per 32 pixels, so the kernel is left with its
+// memory traffic (3 bytes in, 32 bytes out per output pixel).  The raw uint8 tile (9 rows x 264 bytes) is staged with aligned 32-bit loads; the
+// outputs leave through a per-warp staging tile as 128-bit coalesced stores.
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t u8x2_to_f16x2(uint32_t lo, uint32_t hi) {
+  uint32_t m = (lo | (hi << 16)) | 0x64006400u, r;
+  asm("sub.f16x2 %0, %1, %2;" : "=r"(r) : "r"(m), "r"(0x64006400u));
+  return r;
+}
+constexpr int STEM_ROWS = 8;  // output rows per CTA: weights / offsets set up once, the next row's tile streams in (cp.async) under the MMAs
+__global__ void __launch_bounds__(128) stem_tc_kernel(const uint8_t* __restrict__ img, int h, int w, const float* __restrict__ wgt,
+                                                      const float* __restrict__ bias, int act, yad_tensor y) {
+  // tile row = input pixels [2 ox0 - 16, 2 ox0 + 256) of one (channel, input row): 17 aligned 16-byte chunks (w % 16 == 0, host-checked), each
+  // entirely inside or outside the image, so the staging is one cp.async (zero-filling when outside) per chunk
+  constexpr int CPR = 17, TWB = CPR * 16, KR = 27, TILE = 9 * TWB;
+  __shared__ __align__(16) uint8_t tile[2][TILE];    // [ci * 3 + r][272 bytes] of input rows 2 oy - 1 + r
+  __shared__ __align__(16) uint32_t stg[4][32 * 8];  // per warp: 32 pixels x 16 bf16
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int ho = y.h, wo = y.w;
+  const int b = blockIdx.z, oy0 = blockIdx.y * STEM_ROWS, ox0 = blockIdx.x * 128;
+  const int rows = min(STEM_ROWS, ho - oy0);
+  // B fragments (weights, constant per thread) and this thread's 8 tile columns: K index = (ky * 3 + kx) * 3 + ci reads byte
+  // (ci * 3 + ky) * 272 + 2 m + 15 + kx of the tile; m = warp * 32 + g is folded in, (m16 tile, row half) stay immediate offsets
+  uint32_t bfr[2][2][2];
+  const uint8_t* ap[2][2][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ks++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int k0 = ks * 16 + 2 * q + 8 * j;
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) {
+        const int co = nt * 8 + g;
+        const float w0 = k0 < KR ? wgt[co * KR + k0] * 255.0f : 0.f, w1 = k0 + 1 < KR ? wgt[co * KR + k0 + 1] * 255.0f : 0.f;
+        const __half2 hw = __floats2half2_rn(w0, w1);
+        bfr[nt][ks][j] = *reinterpret_cast<const uint32_t*>(&hw);
+      }
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int k = k0 + e;  // columns >= 27 meet zero weights: any staged byte will do
+        const int tap = k < KR ? k / 3 : 0, ci = k < KR ? k - 3 * tap : 0, ky = tap / 3, kx = tap - 3 * ky;
+        ap[ks][j][e] = &tile[0][0] + (ci * 3 + ky) * TWB + 15 + kx + 2 * (warp * 32 + g);
+      }
+    }
+  float bv[2][2];
+#pragma unroll
+  for (int nt = 0; nt < 2; nt++) { bv[nt][0] = bias ? bias[nt * 8 + 2 * q] : 0.f; bv[nt][1] = bias ? bias[nt * 8 + 2 * q + 1] : 0.f; }
+  // staging role of this thread: chunks tid and tid + 128 of the 9 x 17
+  const int c0r = tid / CPR, c0c = tid - c0r * CPR, c1r = (tid + 128) / CPR, c1c = (tid + 128) - c1r * CPR;
+  const bool has1 = tid + 128 < 9 * CPR;
+  const int wx0 = 2 * ox0 - 16;
+  pdl_sync();
+  auto stage_chunk = [&](int rr, int cc, int iy0, int buf) {
+    const int ci = rr / 3, r = rr - 3 * ci, iy = iy0 + r, ix = wx0 + 16 * cc;
+    const bool in = iy >= 0 && iy < h && ix >= 0 && ix < w;
+    const uint8_t* src = in ? img + ((int64_t)(b * 3 + ci) * h + iy) * w + ix : img;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tile[buf][rr * TWB + cc * 16]);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(in ? 16 : 0) : "memory");
+  };
+  auto stage = [&](int oy, int buf) {
+    stage_chunk(c0r, c0c, 2 * oy - 1, buf);
+    if (has1) stage_chunk(c1r, c1c, 2 * oy - 1, buf);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // m16 tiles of this warp that hold at least one real pixel (the last CTA of a row is ragged)
+  const int mt_cnt = min(2, max(0, (wo - ox0 - warp * 32 + 15) / 16));
+  stage(oy0, 0);
+  for (int r = 0; r < rows; r++) {
+    const int oy = oy0 + r;
+    if (r + 1 < rows) {
+      stage(oy + 1, (r + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int boff = (r & 1) * TILE;
+    for (int mt = 0; mt < mt_cnt; mt++) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const uint8_t* p0 = ap[ks][j][0] + boff + mt * 32;
+          const uint8_t* p1 = ap[ks][j][1] + boff + mt * 32;
+          a[ks][2 * j] = u8x2_to_f16x2(p0[0], p1[0]);       // row g
+          a[ks][2 * j + 1] = u8x2_to_f16x2(p0[16], p1[16]);  // row g + 8
+        }
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16_16816(c, a[0], bfr[nt][0][0], bfr[nt][0][1]);
+        mma_f16_16816(c, a[1], bfr[nt][1][0], bfr[nt][1][1]);
+        float v[4];
+        v[0] = fmaf(c[0], 1.0f / 255.0f, bv[nt][0]); v[1] = fmaf(c[1], 1.0f / 255.0f, bv[nt][1]);
+        v[2] = fmaf(c[2], 1.0f / 255.0f, bv[nt][0]); v[3] = fmaf(c[3], 1.0f / 255.0f, bv[nt][1]);
+        apply_act_store_n<bf16, 4>(v, act);
+        const __nv_bfloat162 r0 = __floats2bfloat162_rn(v[0], v[1]), r1 = __floats2bfloat162_rn(v[2], v[3]);
+        stg[warp][(mt * 16 + g) * 8 + nt * 4 + q] = *reinterpret_cast<const uint32_t*>(&r0);
+        stg[warp][(mt * 16 + g + 8) * 8 + nt * 4 + q] = *reinterpret_cast<const uint32_t*>(&r1);
+      }
+    }
+    __syncwarp();
+    bf16* orow = reinterpret_cast<bf16*>(y.ptr) + (((int64_t)b * ho + oy) * wo + ox0 + warp * 32) * y.ld;
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+      const int chunk = lane + 32 * rr, px = chunk >> 1;
+      if (ox0 + warp * 32 + px < wo)
+        *reinterpret_cast<uint4*>(orow + (int64_t)px * y.ld + (chunk & 1) * 8) = *reinterpret_cast<const uint4*>(&stg[warp][px * 8 + (chunk & 1) * 4]);
+    }
+    __syncthreads();  // every warp is done with tile[r & 1] (the row after next lands there) and with its staging tile
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // GroupNorm statistics + apply
 // ------------------------------------------------------------------------------------------------------------------
@@ -192,42 +354,6 @@ __global__ void gn_stats_kernel(yad_tensor x, int groups, double* __restrict__ s
     for (int i = 0; i < cpg; i++) { a += (double)ssum[g * cpg + i]; b += (double)ssq[g * cpg + i]; }
     atomicAdd(&stats[((int64_t)n * groups + g) * 2 + 0], a);
     atomicAdd(&stats[((int64_t)n * groups + g) * 2 + 1], b);
-  }
-}
-
-// packed 8-channel vectors: loads stay in their storage format (4 registers for bf16) until they are consumed, so that several can be in flight
-template <typename T> struct Raw8;
-template <> struct Raw8<bf16> { uint4 u; };
-template <> struct Raw8<float> { float4 a, b; };
-__device__ __forceinline__ void raw_load(const bf16* p, Raw8<bf16>& r) { r.u = *reinterpret_cast<const uint4*>(p); }
-__device__ __forceinline__ void raw_load(const float* p, Raw8<float>& r) {
-  r.a = *reinterpret_cast<const float4*>(p);
-  r.b = *reinterpret_cast<const float4*>(p + 4);
-}
-__device__ __forceinline__ void raw_unpack(const Raw8<bf16>& r, float (&v)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.u);
-#pragma unroll
-  for (int i = 0; i < 4; i++) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
-}
-__device__ __forceinline__ void raw_unpack(const Raw8<float>& r, float (&v)[8]) {
-  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
-}
-__device__ __forceinline__ float tanh_approx_pw(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// bf16 storage: SiLU / sigmoid on one MUFU (tanh.approx, 2^-11 relative -- below the bf16 rounding of the result); fp32 storage keeps apply_act_n
-template <typename T>
-__device__ __forceinline__ void apply_act_store_n(float (&v)[8], int act) {
-  if (sizeof(T) == 2 && act == YAD_ACT_SILU) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) { const float h = 0.5f * v[i]; v[i] = fmaf(h, tanh_approx_pw(h), h); }
-  } else if (sizeof(T) == 2 && act == YAD_ACT_SIGMOID) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = fmaf(0.5f, tanh_approx_pw(0.5f * v[i]), 0.5f);
-  } else {
-    apply_act_n<8>(v, act);
   }
 }
 
@@ -1167,6 +1293,14 @@ int yad_stem_conv(const void* img, int img_is_u8, int n, int h, int w, int cin, 
   const size_t smem = (size_t)(9 * cin * 16 + 16 + cin * 3 * 257) * sizeof(float);
   const dim3 grid((y->w + 127) / 128, y->h, n);
   YAD_CHECK(y->h <= 65535 && n <= 65535, "stem_conv: grid too large");
+  static int stem_tc = -1;
+  if (stem_tc < 0) { const char* ev = getenv("YAD_STEM_TC"); stem_tc = (ev && ev[0] == '0') ? 0 : 1; }
+  if (stem_tc && img_is_u8 && dtype == YAD_BF16 && cin == 3 && (w & 15) == 0 && ((uintptr_t)img & 15) == 0 && (y->ld % 8) == 0) {
+    const dim3 grid_tc((y->w + 127) / 128, (y->h + STEM_ROWS - 1) / STEM_ROWS, n);
+    YAD_LAUNCH(stem_tc_kernel, grid_tc, 128, 0, st, (const uint8_t*)img, h, w, wgt, bias, act, *y);
+    YAD_LAUNCH_CHECK("stem_conv");
+    return 0;
+  }
   YAD_DISPATCH_DTYPE(dtype, {
     if (img_is_u8)
       YAD_LAUNCH((stem_conv_kernel<T, uint8_t, 16>), grid, 128, smem, st, (const uint8_t*)img, n, h, w, cin, wgt, bias, act, *y);
