@@ -255,19 +255,20 @@ def test_tssa_and_mha(dtype, T):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("hw", [20, 16, 10])
-def test_patch_filter(dtype, hw):
-    g = torch.Generator().manual_seed(hw)
-    x = q(torch.randn(2, 16, hw, hw, generator=g), dtype)
-    add = q(torch.randn(2, 16, hw, hw, generator=g), dtype)
-    fft = 1.0 + 0.1 * torch.randn(16, 1, 1, 8, 5, generator=g)
+@pytest.mark.parametrize("hw,n,c", [(20, 2, 16), (16, 2, 16), (10, 2, 16),
+                                    (20, 9, 24), (13, 17, 40), (8, 70, 8)])  # >= 64 patches in the batch: the matrix-resident kernel
+def test_patch_filter(dtype, hw, n, c):
+    g = torch.Generator().manual_seed(hw + n)
+    x = q(torch.randn(n, c, hw, hw, generator=g), dtype)
+    add = q(torch.randn(n, c, hw, hw, generator=g), dtype)
+    fft = 1.0 + 0.1 * torch.randn(c, 1, 1, 8, 5, generator=g)
     hn = (8 - hw % 8) % 8
     xp = F.pad(x, (0, hn, 0, hn), mode="reflect")
     H = xp.shape[2]
-    p = xp.view(2, 16, H // 8, 8, H // 8, 8).permute(0, 1, 2, 4, 3, 5)
+    p = xp.view(n, c, H // 8, 8, H // 8, 8).permute(0, 1, 2, 4, 3, 5)
     p = torch.fft.irfft2(torch.fft.rfft2(p) * fft, s=(8, 8))
-    ref = add + 0.4 * p.permute(0, 1, 2, 4, 3, 5).reshape(2, 16, H, H)[:, :, :hw, :hw]
-    y = ops.patch_filter(to_act(x, dtype), edffn_spectral_matrix(fft).to(DEV), Act.empty(2, hw, hw, 16, dtype, DEV), alpha=0.4, add=to_act(add, dtype))
+    ref = add + 0.4 * p.permute(0, 1, 2, 4, 3, 5).reshape(n, c, H, H)[:, :, :hw, :hw]
+    y = ops.patch_filter(to_act(x, dtype), edffn_spectral_matrix(fft).to(DEV), Act.empty(n, hw, hw, c, dtype, DEV), alpha=0.4, add=to_act(add, dtype))
     assert rel_err(from_act(y), ref) < tol(dtype)
 
 

@@ -1241,6 +1241,59 @@ __global__ void patch_filter_kernel(yad_tensor x, const float* __restrict__ m, f
   }
 }
 
+// The same filter with the matrix resident in shared memory: a CTA owns 8 channels (M[:, :, 8 ch] = 128 KB fp32, read from L2 once) and 64 patches
+// taken across the whole batch; a thread = one patch x one channel pair, its 64 x 2 inputs in registers, the matrix read as broadcast LDS.64 (one
+// wavefront per warp).  patch_filter_kernel re-reads the full 2 MB matrix for every (image, patch): 1.2 GB through L2 at batch 64 -- the L2
+// bandwidth, not the 0.6 GFLOP, set its 168 us.  grid (ceil(n * patches / 64), c / 8), 256 threads.
+template <typename T>
+__global__ void __launch_bounds__(256) patch_filter_smem_kernel(yad_tensor x, const float* __restrict__ m, float alpha, const T* __restrict__ add,
+                                                                int add_ld, yad_tensor y, int patches_total) {
+  extern __shared__ __align__(16) float pf_ms[];  // [64 * 64][8]
+  const int c = x.c, c0 = blockIdx.y * 8;
+  for (int idx = threadIdx.x; idx < 64 * 64 * 2; idx += 256) {
+    const int oi = idx >> 1, half = idx & 1;
+    reinterpret_cast<float4*>(pf_ms)[idx] = *reinterpret_cast<const float4*>(m + (int64_t)oi * c + c0 + half * 4);
+  }
+  pdl_sync();
+  const int cp = threadIdx.x & 3, gp = blockIdx.x * 64 + (threadIdx.x >> 2);
+  const int wp = (x.w + 7) / 8, ppi = ((x.h + 7) / 8) * wp;
+  const bool live = gp < patches_total;
+  const int n = live ? gp / ppi : 0, pt = live ? gp - n * ppi : 0, pr = pt / wp, pc = pt - pr * wp;
+  const int ch = c0 + 2 * cp;
+  float in[64][2];
+  if (live) {
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+      int yy = pr * 8 + (i >> 3), xx = pc * 8 + (i & 7);
+      if (yy >= x.h) yy = 2 * x.h - 2 - yy;  // F.pad(..., mode='reflect') on the bottom / right edge
+      if (xx >= x.w) xx = 2 * x.w - 2 - xx;
+      const T* src = reinterpret_cast<const T*>(x.ptr) + pix_off(x, n, yy, xx) + ch;
+      in[i][0] = ld1(src);
+      in[i][1] = ld1(src + 1);
+    }
+  }
+  __syncthreads();
+  if (!live) return;
+  const float* ms = pf_ms + 2 * cp;
+  for (int o = 0; o < 64; o++) {
+    const int yy = pr * 8 + (o >> 3), xx = pc * 8 + (o & 7);
+    if (yy >= x.h || xx >= x.w) continue;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+      const float2 mv = *reinterpret_cast<const float2*>(ms + (o * 64 + i) * 8);
+      s0 = fmaf(mv.x, in[i][0], s0);
+      s1 = fmaf(mv.y, in[i][1], s1);
+    }
+    const int64_t p = ((int64_t)n * x.h + yy) * x.w + xx;
+    float r0 = alpha * s0, r1 = alpha * s1;
+    if (add) { r0 += ld1(add + p * add_ld + ch); r1 += ld1(add + p * add_ld + ch + 1); }
+    T* dst = reinterpret_cast<T*>(y.ptr) + p * y.ld + ch;
+    st1(dst, r0);
+    st1(dst + 1, r1);
+  }
+}
+
 int grid_for(int64_t items, int tpb = TPB) {
   int64_t g = (items + tpb - 1) / tpb;
   const int64_t cap = 148 * 16;
@@ -1586,6 +1639,21 @@ int yad_patch_filter(const yad_tensor* x, const float* m, float alpha, const voi
   YAD_CHECK(((8 - x->h % 8) % 8) < x->h && ((8 - x->w % 8) % 8) < x->w, "patch_filter: reflect pad wider than the map (%dx%d)", x->h, x->w);
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(((x->h + 7) / 8) * ((x->w + 7) / 8), x->n);
+  static int pf_smem = -1;
+  if (pf_smem < 0) { const char* ev = getenv("YAD_PATCH_FILTER_SMEM"); pf_smem = (ev && ev[0] == '0') ? 0 : 1; }
+  const int64_t patches_total = (int64_t)grid.x * x->n;
+  // matrix-resident kernel once there are enough patches to amortise the 128 KB fill of a CTA (the batched inference / training shapes)
+  if (pf_smem && patches_total >= 64 && patches_total < ((int64_t)1 << 30) && (((uintptr_t)m) & 15) == 0 && x->c % 8 == 0) {
+    const size_t smem = 64 * 64 * 8 * sizeof(float);
+    const dim3 g2((unsigned)((patches_total + 63) / 64), x->c / 8);
+    YAD_DISPATCH_DTYPE(dtype, {
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(patch_filter_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+      YAD_LAUNCH(patch_filter_smem_kernel<T>, g2, 256, smem, st, *x, m, alpha, (const T*)add, add_ld, *y, (int)patches_total);
+    })
+    YAD_LAUNCH_CHECK("patch_filter");
+    return 0;
+  }
   int tpb = x->c < 128 ? ((x->c + 31) / 32) * 32 : 128;
   YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(patch_filter_kernel<T>, grid, tpb, 0, st, *x, m, alpha, (const T*)add, add_ld, *y);)
   YAD_LAUNCH_CHECK("patch_filter");
