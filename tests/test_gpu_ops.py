@@ -146,15 +146,17 @@ def test_group_norm_silu_add(dtype, c, groups, hw):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-def test_sppf_pool(dtype):
-    x = q(torch.randn(2, 32, 20, 20, generator=torch.Generator().manual_seed(1)), dtype)
-    cat = Act.empty(2, 20, 20, 128, dtype, DEV)
-    cat.buf[..., :32] = x.permute(0, 2, 3, 1).to(DEV)
-    ops.sppf_pool(cat.slice(0, 32), cat.slice(32, 32), cat.slice(64, 32), cat.slice(96, 32))
+@pytest.mark.parametrize("n,c,h,w", [(2, 32, 20, 20), (3, 48, 45, 23), (1, 16, 7, 5), (2, 16, 40, 40), (1, 24, 9, 9)])
+def test_sppf_pool(dtype, n, c, h, w):
+    """bit-exact (max is exact in any storage type); multi-tile maps, maps smaller than the 13x13 window, a channel count (24) off the tiled path"""
+    x = q(torch.randn(n, c, h, w, generator=torch.Generator().manual_seed(h)), dtype)
+    cat = Act.empty(n, h, w, 4 * c, dtype, DEV)
+    cat.buf[..., :c] = x.permute(0, 2, 3, 1).to(DEV)
+    ops.sppf_pool(cat.slice(0, c), cat.slice(c, c), cat.slice(2 * c, c), cat.slice(3 * c, c))
     y1 = F.max_pool2d(x, 5, 1, 2); y2 = F.max_pool2d(y1, 5, 1, 2); y3 = F.max_pool2d(y2, 5, 1, 2)
     got = from_act(cat)
     for i, r in enumerate((x, y1, y2, y3)):
-        np.testing.assert_array_equal(got[:, 32 * i:32 * i + 32].numpy(), r.numpy())
+        np.testing.assert_array_equal(got[:, c * i:c * i + c].numpy(), r.numpy())
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

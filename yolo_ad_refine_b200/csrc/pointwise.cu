@@ -734,6 +734,68 @@ __global__ void sppf_pool_kernel(yad_tensor x, yad_tensor y1, yad_tensor y2, yad
   }
 }
 
+// Tiled SPPF for bf16 storage: the three windows as what they are in the reference -- three chained 5x5 pools -- each one a horizontal and a
+// vertical 5-tap pass over a haloed tile in shared memory (packed bf16x2 max).  A CTA owns a T x T output tile (T <= 20) of one image and 16
+// channels; the (T + 12)^2 haloed tile is loaded once (-inf outside the image = the pools' padding); after stage k the outer 2k rows / columns
+// of the tile are stale, the centre never is (a map that is one tile needs no halo: the tile edge is the pools' own -inf padding).  30 shared-memory reads per output instead of the 275 global loads of sppf_pool_kernel.
+constexpr int SP_CC = 16, SP_HALO = 6, SP_TMAX = 20;
+__device__ __forceinline__ uint4 bf8_max(const uint4& a, const uint4& b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; i++) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+__global__ void __launch_bounds__(256) sppf_tile_kernel(yad_tensor x, yad_tensor y1, yad_tensor y2, yad_tensor y3, int T, int tiles_x, int tiles_y, int halo) {
+  extern __shared__ __align__(16) uint4 sp_sm[];  // A[TD * TD][2], B[TD * TD][2]
+  const int TD = T + 2 * halo, cells = TD * TD * 2;
+  uint4* A = sp_sm;
+  uint4* B = sp_sm + cells;
+  int b = blockIdx.x;
+  const int chunks = x.c / SP_CC, c0 = (b % chunks) * SP_CC;
+  b /= chunks;
+  const int tx0 = (b % tiles_x) * T;
+  b /= tiles_x;
+  const int ty0 = (b % tiles_y) * T, n = b / tiles_y;
+  pdl_sync();
+  const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);
+  for (int idx = threadIdx.x; idx < cells; idx += 256) {
+    const int pix = idx >> 1, part = idx & 1, ty = pix / TD, tx = pix - ty * TD;
+    const int iy = ty0 - halo + ty, ix = tx0 - halo + tx;
+    uint4 v = ninf;
+    if (iy >= 0 && iy < x.h && ix >= 0 && ix < x.w) v = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(x.ptr) + pix_off(x, n, iy, ix) + c0 + part * 8);
+    A[idx] = v;
+  }
+  __syncthreads();
+  for (int stage = 0; stage < 3; stage++) {
+    for (int idx = threadIdx.x; idx < cells; idx += 256) {  // horizontal 5-tap max: A -> B
+      const int pix = idx >> 1, ty = pix / TD, tx = pix - ty * TD;
+      uint4 v = A[idx];
+#pragma unroll
+      for (int d = -2; d <= 2; d++)
+        if (d != 0 && tx + d >= 0 && tx + d < TD) v = bf8_max(v, A[idx + 2 * d]);
+      B[idx] = v;
+    }
+    __syncthreads();
+    bf16* const yp = reinterpret_cast<bf16*>(stage == 0 ? y1.ptr : (stage == 1 ? y2.ptr : y3.ptr));
+    const int yld = stage == 0 ? y1.ld : (stage == 1 ? y2.ld : y3.ld);
+    for (int idx = threadIdx.x; idx < cells; idx += 256) {  // vertical 5-tap max: B -> A, the centre leaves for y_stage
+      const int pix = idx >> 1, part = idx & 1, ty = pix / TD, tx = pix - ty * TD;
+      uint4 v = B[idx];
+#pragma unroll
+      for (int d = -2; d <= 2; d++)
+        if (d != 0 && ty + d >= 0 && ty + d < TD) v = bf8_max(v, B[idx + 2 * d * TD]);
+      A[idx] = v;
+      const int oy = ty0 - halo + ty, ox = tx0 - halo + tx;
+      if (ty >= halo && ty < halo + T && tx >= halo && tx < halo + T && oy < x.h && ox < x.w)
+        *reinterpret_cast<uint4*>(yp + ((int64_t)(n * x.h + oy) * x.w + ox) * yld + c0 + part * 8) = v;
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // reductions over pixels: global average pool, row / column means, MLCA 5x5 adaptive pool
 // ------------------------------------------------------------------------------------------------------------------
@@ -1469,6 +1531,23 @@ int yad_sppf_pool(const yad_tensor* x, const yad_tensor* y1, const yad_tensor* y
   SAME_SHAPE(x, y1, "sppf");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)x->n * x->h * x->w * (x->c / 8);
+  static int sp_tile = -1;
+  if (sp_tile < 0) { const char* ev = getenv("YAD_SPPF_TILE"); sp_tile = (ev && ev[0] == '0') ? 0 : 1; }
+  if (sp_tile && dtype == YAD_BF16 && x->c % SP_CC == 0 && total > 0) {
+    // tile edge: the map edge when it fits, else the edge <= 20 with the fewest tiles
+    auto edge = [](int n) { const int t = (n + SP_TMAX - 1) / SP_TMAX; return (n + t - 1) / t; };
+    const int T = edge(x->h) > edge(x->w) ? edge(x->h) : edge(x->w);
+    const int tiles_y = (x->h + T - 1) / T, tiles_x = (x->w + T - 1) / T, halo = (tiles_y == 1 && tiles_x == 1) ? 0 : SP_HALO, TD = T + 2 * halo;
+    const int64_t ctas = (int64_t)x->n * tiles_y * tiles_x * (x->c / SP_CC);
+    const size_t smem = (size_t)TD * TD * 2 * 2 * sizeof(uint4);
+    if (ctas < ((int64_t)1 << 31)) {
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(sppf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 32 * 2 * 2 * 16); attr = true; }
+      YAD_LAUNCH(sppf_tile_kernel, (unsigned)ctas, 256, smem, st, *x, *y1, *y2, *y3, T, tiles_x, tiles_y, halo);
+      YAD_LAUNCH_CHECK("sppf_pool");
+      return 0;
+    }
+  }
   YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(sppf_pool_kernel<T>, grid_for(total, 128), 128, 0, st, *x, *y1, *y2, *y3);)
   YAD_LAUNCH_CHECK("sppf_pool");
   return 0;
