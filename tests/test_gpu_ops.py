@@ -186,6 +186,16 @@ def test_pool_upsample(dtype, hw, s):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("h,w,s", [(20, 20, 2), (20, 20, 4), (13, 22, 2), (9, 7, 4)])
+def test_pool_upsample_batched(dtype, h, w, s):
+    """batch 24 x 96 channels: the two-phase shared-memory kernel (>= 64 CTAs), incl. maps that s does not divide (ragged adaptive bins)"""
+    x = q(torch.randn(24, 96, h, w, generator=torch.Generator().manual_seed(h + s)), dtype)
+    ref = F.interpolate(F.adaptive_avg_pool2d(x, (h // s, w // s)), size=(h, w), mode="bilinear", align_corners=False)
+    y = ops.pool_upsample(to_act(x, dtype), s, Act.empty(24, h, w, 96, dtype, DEV))
+    assert rel_err(from_act(y), ref) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("c,hw", [(32, 40), (64, 20), (64, 10), (32, 13)])
 def test_mlca(dtype, c, hw):
     g = torch.Generator().manual_seed(c + hw)

@@ -1116,6 +1116,58 @@ __global__ void pool_upsample_kernel(yad_tensor x, int s, yad_tensor y) {
   }
 }
 
+// The same operator in two phases inside one CTA = (image, 32 channels): bin sums of the pooled map into shared memory (every input pixel read
+// once), then the bilinear blend from shared memory.  pool_upsample_kernel re-sums up to four s x s bins for every output pixel (16 - 64 global
+// loads each).  Same arithmetic in the same order (raw bin sums, weight / count applied in the blend): bit-identical results.
+constexpr int PU_CC = 32;
+template <typename T>
+__global__ void __launch_bounds__(256) pool_upsample_smem_kernel(yad_tensor x, int s, yad_tensor y) {
+  extern __shared__ __align__(16) float pu_sm[];  // [hp * wp][32] raw bin sums
+  pdl_sync();
+  const int chunks = x.c / PU_CC, n = blockIdx.x / chunks, c0 = (blockIdx.x - n * chunks) * PU_CC;
+  const int hp = x.h / s, wp = x.w / s;
+  for (int it = threadIdx.x; it < hp * wp * 4; it += 256) {
+    const int oi = it & 3, bin = it >> 2, by = bin / wp, bx = bin - by * wp;
+    const int y0 = bin_start(by, x.h, hp), y1 = bin_end(by, x.h, hp), x0 = bin_start(bx, x.w, wp), x1 = bin_end(bx, x.w, wp);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+    for (int yy = y0; yy < y1; yy++)
+      for (int xx = x0; xx < x1; xx++) {
+        float v[8];
+        load8(reinterpret_cast<const T*>(x.ptr) + pix_off(x, n, yy, xx) + c0 + oi * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] += v[i];
+      }
+    store8(pu_sm + bin * PU_CC + oi * 8, acc);
+  }
+  __syncthreads();
+  const float sy = (float)hp / (float)x.h, sx = (float)wp / (float)x.w;
+  for (int it = threadIdx.x; it < x.h * x.w * 4; it += 256) {
+    const int oi = it & 3, p = it >> 2, py = p / x.w, px = p - py * x.w;
+    const float fy = fmaxf(sy * ((float)py + 0.5f) - 0.5f, 0.f), fx = fmaxf(sx * ((float)px + 0.5f) - 0.5f, 0.f);
+    const int iy0 = (int)fy, ix0 = (int)fx;
+    const int iy1 = min(iy0 + 1, hp - 1), ix1 = min(ix0 + 1, wp - 1);
+    const float ly = fy - (float)iy0, lx = fx - (float)ix0;
+    float out[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int by = (q >> 1) ? iy1 : iy0, bx = (q & 1) ? ix1 : ix0;
+      const float wgt = ((q >> 1) ? ly : 1.f - ly) * ((q & 1) ? lx : 1.f - lx);
+      if (wgt == 0.f) continue;
+      const int cnt = (bin_end(by, x.h, hp) - bin_start(by, x.h, hp)) * (bin_end(bx, x.w, wp) - bin_start(bx, x.w, wp));
+      const float sc = wgt / (float)cnt;
+      float acc[8];
+      load8(pu_sm + (by * wp + bx) * PU_CC + oi * 8, acc);
+#pragma unroll
+      for (int i = 0; i < 8; i++) out[i] = fmaf(acc[i], sc, out[i]);
+    }
+    store8(reinterpret_cast<T*>(y.ptr) + pix_off(y, n, py, px) + c0 + oi * 8, out);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // tiny per-image MLPs and AdaptiveDynamicTanh
 // ------------------------------------------------------------------------------------------------------------------
@@ -1617,6 +1669,18 @@ int yad_pool_upsample(const yad_tensor* x, int s, const yad_tensor* y, int dtype
   YAD_CHECK(s >= 1 && x->h / s >= 1 && x->w / s >= 1, "pool_upsample: scale %d too large for %dx%d", s, x->h, x->w);
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)x->n * x->h * x->w * (x->c / 8);
+  const size_t pooled = (size_t)(x->h / s) * (x->w / s) * PU_CC * sizeof(float);
+  static int pu_smem = -1;
+  if (pu_smem < 0) { const char* ev = getenv("YAD_POOL_UPSAMPLE_SMEM"); pu_smem = (ev && ev[0] == '0') ? 0 : 1; }
+  if (pu_smem && x->c % PU_CC == 0 && pooled <= 64 * 1024 && (int64_t)x->n * (x->c / PU_CC) >= 64 && total > 0) {  // enough CTAs to fill the GPU
+    YAD_DISPATCH_DTYPE(dtype, {
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(pool_upsample_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
+      YAD_LAUNCH(pool_upsample_smem_kernel<T>, (unsigned)(x->n * (x->c / PU_CC)), 256, pooled, st, *x, s, *y);
+    })
+    YAD_LAUNCH_CHECK("pool_upsample");
+    return 0;
+  }
   YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(pool_upsample_kernel<T>, grid_for(total, 128), 128, 0, st, *x, s, *y);)
   YAD_LAUNCH_CHECK("pool_upsample");
   return 0;
