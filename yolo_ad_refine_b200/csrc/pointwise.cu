@@ -940,6 +940,39 @@ __global__ void rowcol_gate_kernel(yad_tensor x, bool has_x, yad_tensor gh, yad_
   pdl_sync();
   const int oct = y.c >> 3;
   const int64_t total = (int64_t)y.n * y.h * y.w * oct;
+  if (has_x && blockDim.x % oct == 0 && total < ((int64_t)1 << 31)) {
+    // as gn_apply_kernel: a thread keeps its channel octet, 32-bit pixel arithmetic, four packed loads of x in flight per trip
+    const int o = (threadIdx.x % oct) * 8, pstep = (int)(gridDim.x * blockDim.x) / oct, npix = y.n * y.h * y.w, hw = y.h * y.w;
+    const T* xp = reinterpret_cast<const T*>(x.ptr) + o;
+    T* yp = reinterpret_cast<T*>(y.ptr) + o;
+    auto gate = [&](int p, const float (&v)[8]) {
+      const int n = p / hw, r = p - n * hw, py = r / y.w, px = r - py * y.w;
+      float a[8], b[8];
+      load8(reinterpret_cast<const T*>(gh.ptr) + ((int64_t)n * y.h + py) * gh.ld + o, a);
+      load8(reinterpret_cast<const T*>(gw.ptr) + ((int64_t)n * y.w + px) * gw.ld + o, b);
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = v[i] * a[i] * b[i];
+      store8(yp + (int64_t)p * y.ld, a);
+    };
+    int p = (int)(blockIdx.x * blockDim.x + threadIdx.x) / oct;
+    for (; p + 3 * pstep < npix; p += 4 * pstep) {
+      Raw8<T> r[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) raw_load(xp + (int64_t)(p + u * pstep) * x.ld, r[u]);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        float v[8];
+        raw_unpack(r[u], v);
+        gate(p + u * pstep, v);
+      }
+    }
+    for (; p < npix; p += pstep) {
+      float v[8];
+      load8(xp + (int64_t)p * x.ld, v);
+      gate(p, v);
+    }
+    return;
+  }
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
     int o = (int)(it % oct) * 8;
     int64_t p = it / oct;
