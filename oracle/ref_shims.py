@@ -19,7 +19,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("YAD_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """/root/reference in the build container; oracle/_ref (the copy made by oracle/build_ref.py, git-ignored) on the GPU box"""
+    for cand in (os.environ.get("YAD_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "ultralytics")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 class _Anything:

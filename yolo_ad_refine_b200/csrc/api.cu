@@ -54,7 +54,7 @@ int yad_conv2d(const yad_tensor* x, const void* w, const yad_conv_desc* d, const
     if (r >= 0) return r;
   }
   if (impl == 0) impl = (dtype == YAD_BF16 && yad_conv2d_tc_supported(x, d, y)) ? 2 : 1;
-  if (impl == 2 || impl == 3) {
+  if (impl >= 2 && impl <= 5) {
     YAD_CHECK(dtype == YAD_BF16, "conv2d: the tcgen05 path is bf16 only");
     YAD_CHECK(yad_conv2d_tc_supported(x, d, y), "conv2d: shape not supported by the tcgen05 path");
     return yad_conv2d_tc(x, w, d, e, y, stream);

@@ -485,22 +485,27 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
     }
     tc_fence_before();
   } else {
-    // ================= MMA issuer: one elected thread =================
-    if ((tid & 31) == 0) {
+    // ================= MMA issuer: warp-uniform loop, the elected lane issues (tc_ptx.cuh) =================
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc(p.n_tile);
+      const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
       for (int kc = 0; kc < nk; kc++) {
         const int s = kc % p.stages;
-        const uint32_t ph = (uint32_t)(kc / p.stages) & 1u;
-        mbar_wait(full_bar(s), ph);
+        mbar_wait(full_bar(s), (uint32_t)(kc / p.stages) & 1u);
         tc_fence_after();
         const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
-        const uint64_t ad = make_sdesc(a_s), bd = make_sdesc(b_s);
-#pragma unroll
-        for (int k = 0; k < BK / 16; k++)  // advance 32 bytes (>> 4 = 2) along K inside the 128-byte swizzle row
-          umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
-        umma_commit(empty_bar(s));  // implies tcgen05.fence::before_thread_sync
+        const uint32_t a_lo = ((a_s & 0x3FFFFu) >> 4) | (1u << 16), b_lo = ((b_s & 0x3FFFFu) >> 4) | (1u << 16);
+        if (leader) {
+          if (kc == 0) umma_bf16<false>(tmem_base, pack64(a_lo, hi), pack64(b_lo, hi), idesc);
+          else umma_bf16<true>(tmem_base, pack64(a_lo, hi), pack64(b_lo, hi), idesc);
+          umma_bf16<true>(tmem_base, pack64(a_lo + 2u, hi), pack64(b_lo + 2u, hi), idesc);  // 32 bytes along K inside the 128-byte swizzle row
+          umma_bf16<true>(tmem_base, pack64(a_lo + 4u, hi), pack64(b_lo + 4u, hi), idesc);
+          umma_bf16<true>(tmem_base, pack64(a_lo + 6u, hi), pack64(b_lo + 6u, hi), idesc);
+          umma_commit(empty_bar(s));  // implies tcgen05.fence::before_thread_sync
+        }
       }
-      umma_commit(tmem_full_bar);
+      if (leader) umma_commit(tmem_full_bar);
     }
     __syncwarp();
     tc_fence_before();
@@ -670,7 +675,8 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
   pdl_sync();  // on-chip prologue done; from here on the kernel reads what its predecessors wrote
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // warp-uniform producer loop, the elected lane issues
+      const bool leader = elect_one();
       const uint32_t tx_bytes = (uint32_t)tp.a_bytes + b_bytes;
       uint32_t it = 0;  // running K-chunk counter across tiles
       for (int tile = blockIdx.x; tile < tp.total_tiles; tile += gridDim.x) {
@@ -688,20 +694,26 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
           const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
           const int t = kc / kpt, ci = (kc - t * kpt) * tp.bk;
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), tx_bytes);
-          if (tp.s2)
-            tma_load_5d(a_s, &tmA, full_bar(s), tp.cpx[t] + ci, tx0 + p.dx[t], tp.tpy[t], ty0 + p.dy[t], img);
-          else if (tp.patch)
-            tma_load_4d(a_s, &tmA, full_bar(s), ci, tx0 + p.dx[t], ty0 + p.dy[t], img);
-          else
-            tma_load_2d(a_s, &tmA, full_bar(s), ci, mt * BM);
-          tma_load_2d(b_s, &tmB, full_bar(s), p.wtap[t] * p.cin + ci, n0);
+          if (leader) {
+            mbar_expect_tx(full_bar(s), tx_bytes);
+            if (tp.s2)
+              tma_load_5d(a_s, &tmA, full_bar(s), tp.cpx[t] + ci, tx0 + p.dx[t], tp.tpy[t], ty0 + p.dy[t], img);
+            else if (tp.patch)
+              tma_load_4d(a_s, &tmA, full_bar(s), ci, tx0 + p.dx[t], ty0 + p.dy[t], img);
+            else
+              tma_load_2d(a_s, &tmA, full_bar(s), ci, mt * BM);
+            tma_load_2d(b_s, &tmB, full_bar(s), p.wtap[t] * p.cin + ci, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // warp-uniform issue loop (see tc_ptx.cuh): the whole warp walks it, the elected lane issues; two 32-bit adds per tcgen05.mma
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc(p.n_tile);
+      const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+      const uint32_t hi = ((8u * row_bytes) >> 4) | (1u << 14) | (layout << 29);
       uint32_t it = 0;
       int i = 0;
       for (int tile = blockIdx.x; tile < tp.total_tiles; tile += gridDim.x, i++) {
@@ -709,17 +721,21 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
         mbar_wait(tempty_bar(acc), (((uint32_t)(i / acc_stages)) & 1u) ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
+        const int ks = tp.bk / 16;
         for (int kc = 0; kc < nk; kc++, it++) {
           const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1u;
-          mbar_wait(full_bar(s), ph);
+          mbar_wait(full_bar(s), (it / p.stages) & 1u);
           tc_fence_after();
           const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
-          const uint64_t ad = make_sdesc_rb(a_s, row_bytes), bd = make_sdesc_rb(b_s, row_bytes);
-          for (int k = 0; k < tp.bk / 16; k++) umma_f16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) ? 1u : 0u);
-          umma_commit(empty_bar(s));
+          const uint32_t a_lo = ((a_s & 0x3FFFFu) >> 4) | (1u << 16), b_lo = ((b_s & 0x3FFFFu) >> 4) | (1u << 16);
+          if (leader) {
+            if (kc == 0) umma_bf16<false>(d_tmem, pack64(a_lo, hi), pack64(b_lo, hi), idesc);
+            else umma_bf16<true>(d_tmem, pack64(a_lo, hi), pack64(b_lo, hi), idesc);
+            for (int k = 1; k < ks; k++) umma_bf16<true>(d_tmem, pack64(a_lo + 2u * k, hi), pack64(b_lo + 2u * k, hi), idesc);
+            umma_commit(empty_bar(s));
+          }
         }
-        umma_commit(tfull_bar(acc));
+        if (leader) umma_commit(tfull_bar(acc));
       }
     }
     __syncwarp();
@@ -786,6 +802,10 @@ int make_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, 
 }
 
 int pick_n_tile(int cout);
+}  // namespace
+int yad_conv2d_v2_supported(const yad_tensor* x, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y);
+int yad_conv2d_v2(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream);
+namespace {
 
 // best (bw, bh) with bw * bh <= 128 for an (h, w) map: maximise useful pixels per 128-row MMA tile
 void pick_patch(int h, int w, int* bw_out, int* bh_out) {
@@ -1029,6 +1049,10 @@ int yad_conv2d_tc(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
     p.hm = y->h; p.wm = y->w; p.stride = d->stride; p.os = 1; p.py = 0; p.px = 0;
     p.ntaps = d->kh * d->kw;
     for (int t = 0; t < p.ntaps; t++) { p.dy[t] = t / d->kw - d->pad_h; p.dx[t] = t % d->kw - d->pad_w; p.wtap[t] = t; }
+    // impl 4: the resident-weight kernel of conv_v2.cu (error when the shape is not eligible); 5: conv_tma_kernel (the round-1 TMA kernel, A/B runs)
+    if (d->mode == YAD_CONV_NORMAL && d->impl != 3 && d->impl != 5 && !p.bn_stats && yad_conv2d_v2_supported(x, d, e, y))
+      return yad_conv2d_v2(x, w, d, e, y, stream);
+    YAD_CHECK(d->impl != 4, "conv2d: impl 4 (resident-weight tcgen05 kernel) does not support this shape / epilogue");
     if (d->impl != 3 && tma_supported(x, d, y)) return launch_tma(p, d, st);
     if (p.bn_stats) {  // batch statistics are fused on the TMA-fed kernel only: thread-gathered kernel first, stand-alone statistics after it
       p.bn_stats = 0;

@@ -1,0 +1,699 @@
+// Second-generation tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation): stride-1 1x1 and 3x3 (pad 1)
+// convolutions of yad_conv2d's NORMAL mode, the shapes that carry the inference step (nn/modules/conv.py:36-54 Conv.forward_fuse, the Conv_GN / 1x1
+// convolutions of nn/modules/head.py:1131-1175, the neck's lateral 1x1 of the yaml).  What changed against conv_tma_kernel (conv_tc.cu), and why
+// (profiles/r1_ncu_conv_s6.json: L2->SM traffic 13.6x the unique input on 3x3, 60 % integer / control instructions in the epilogue on 1x1):
+//
+//   * WEIGHTS ARE RESIDENT.  A persistent CTA loads the whole packed weight matrix [n tiles][taps][K chunks] once (one TMA box and one mbarrier per
+//     64-wide K chunk, so the first MMAs start as soon as the first chunk lands) and keeps it in shared memory for all of its tiles; the pipeline
+//     ring carries activations only.
+//   * 3x3: ONE HALOED PATCH PER K CHUNK.  The M tile is an 8 (x) by 16 (y) pixel rectangle of one image; the producer fetches the (8+2) x (16+2)
+//     pixel patch x 64 channels with a single 4-D box (conv padding = TMA zero fill) and the nine taps are nine UMMA A-descriptors into that one
+//     patch: start address shifted by ((dy+1) * pitch + (dx+1)) pixel rows of 128 bytes, stride-byte-offset = one patch row (every 8 consecutive
+//     M rows are the 8 pixels of one tile row), matrix-base-offset = (start >> 7) & 7 as the PTX ISA prescribes for SWIZZLE_128B operands that do
+//     not start on a 1024-byte boundary.  L2->SM traffic per tile drops from 9 A boxes + 9 B boxes to 1.4x the tile's own input.
+//   * LEAN EPILOGUE.  Activation, mul/add, GroupNorm statistics and per-row scales are template parameters; the bias sits in shared memory; one
+//     thread = one accumulator row: tcgen05.ld 32 columns, bias + activation, pack to bf16, 128-bit conflict-free stores into the swizzled image
+//     of a TMA store box, one bulk tensor store per (warp, piece) -- 2-D box for 1x1 (rows = consecutive pixels), 4-D box for 3x3 (4 tile rows of
+//     8 pixels; the unit clips ragged tiles).  The TMEM accumulator is released right after the last tcgen05.ld of a tile, before the stores.
+//     mul / add operands are applied on the staged tile in packed bf16x2 (row-contiguous 128-bit loads).  GroupNorm partial sums leave through a
+//     butterfly reduce-scatter (16 shuffles per 32 columns instead of 80) and one fp64 atomic per (group, statistic) and warp.
+//
+// Always SWIZZLE_128B with 64-channel (128-byte) rows: narrower inputs (cin 16 .. 48, K tails) are zero-filled by the TMA unit and only the
+// ceil(cin / 16) K steps that carry data are issued.
+#include <cuda.h>
+
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int V2_BM = 128;
+constexpr int V2_MAX_EPI_WARPS = 16;  // 8 (two per TMEM lane quarter) or 16 (four per quarter: twice the warps to hide the epilogue's latencies)
+constexpr int V2_MAX_THREADS = 64 + 32 * V2_MAX_EPI_WARPS;
+constexpr int V2_BH = 16, V2_BW = 8;   // 3x3 M tile: 16 rows of 8 pixels
+constexpr int V2_MAX_BCHUNKS = 32;     // resident weight chunks (one mbarrier each)
+constexpr int ACT_GENERIC = -1;        // activation chosen at run time (relu / gelu / hardswish)
+
+struct V2Params {
+  int n, hm, wm, hw;        // output grid per image (stride 1: = input grid)
+  int cin, cout;
+  int m_total;              // n * hm * wm
+  int n_tile, tiles_n, total_tiles;
+  int tiles_x, tiles_y;     // patch mode: tiles per image
+  int kpt, ntaps, pw;       // 64-wide K chunks per tap; taps; patch pitch in pixels
+  int tap_row[9];           // patch row (= pixel index inside the patch) the A descriptor of tap t starts at
+  int stages, acc_stages, tmem_cols;
+  uint32_t off_b, b_chunk_bytes, off_a, a_stage_bytes, a_tx_bytes, off_stg, stg_warp_bytes, off_bias, off_bars;
+  int sc, ew;               // columns per TMA store box (16 / 32 / 64); epilogue warps (8 / 16)
+  int bnd[5];               // column ranges [bnd[w], bnd[w + 1]) of the ew / 4 warps that share a TMEM lane quarter
+  const float* bias;
+  const float* img_scale;
+  const bf16* pix_scale;
+  int pix_scale_ld;
+  int act;
+  float alpha;
+  const bf16* mul;
+  int mul_ld;
+  const bf16* add;
+  int add_ld;
+  double* gn_stats;
+  int gn_groups, cpg;
+};
+
+// K-major SWIZZLE_128B matrix descriptor with an explicit stride-byte-offset (distance between 8-row groups) and the matrix base offset for
+// start addresses that are 128-byte but not 1024-byte aligned (tap-shifted views of the haloed patch)
+// The matrix-base-offset field (bits 49-51) stays 0: measured on B200 (tools/v2_tap_debug.py), the tensor core applies the 128-byte swizzle to the
+// ABSOLUTE shared-memory address bits [7, 10) -> [4, 7), exactly as the TMA unit does when it writes the box, so a descriptor may start on any
+// 128-byte row of a TMA-written tile and use any multiple of 128 bytes as its stride-byte-offset (1280 = a 10-pixel patch row works); setting the
+// field to (start >> 7) & 7 breaks every start that is not 1024-byte aligned.
+// The descriptor is kept as two 32-bit words so that the per-MMA arithmetic (K advance, tap shift, weight chunk) is one 32-bit add on the low word.
+__device__ __forceinline__ uint32_t v2_desc_hi(uint32_t sbo) { return (sbo >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint32_t v2_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t v2_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(V2_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2),
+               "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ float v2_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint4 lds16(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts16v(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+
+// Butterfly reduce-scatter of NV per-thread partial sums over the 32 lanes of a warp: afterwards a[0] of lane l holds the warp total of value
+// index l >> (5 - log2 NV); NV in {2, 4, 8, 16}.  NV - 1 + (5 - log2 NV) shuffles instead of 5 * NV.
+template <int W>
+__device__ __forceinline__ void rs_step(float* a, int lane, int off) {
+  if constexpr (W > 1) {
+    constexpr int H = W / 2;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+      const float send = up ? a[i] : a[i + H];
+      const float keep = up ? a[i + H] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  } else {
+    a[0] += __shfl_xor_sync(0xffffffffu, a[0], off);
+  }
+}
+template <int NV>
+__device__ __forceinline__ void reduce_scatter(float (&a)[NV], int lane) {
+  rs_step<NV>(a, lane, 16);
+  rs_step<(NV > 1 ? NV / 2 : 1)>(a, lane, 8);
+  rs_step<(NV > 2 ? NV / 4 : 1)>(a, lane, 4);
+  rs_step<(NV > 4 ? NV / 8 : 1)>(a, lane, 2);
+  rs_step<(NV > 8 ? NV / 16 : 1)>(a, lane, 1);
+}
+template <int U, int CPG>
+__device__ __forceinline__ void gn_unit(const V2Params& p, const float (&v)[U], bool valid, int lane, int img, bool uniform, int co) {
+  constexpr int NG = U / CPG, NV = 2 * NG;
+  float a[NV];
+#pragma unroll
+  for (int g = 0; g < NG; g++) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPG; i++) { const float x = valid ? v[g * CPG + i] : 0.f; s += x; q = fmaf(x, x, q); }
+    a[2 * g] = s; a[2 * g + 1] = q;
+  }
+  const int g0 = co / CPG;
+  if (uniform) {  // warp-uniform: all valid rows of this warp belong to image `img`
+    reduce_scatter<NV>(a, lane);
+    constexpr int SH = NV == 16 ? 1 : (NV == 8 ? 2 : (NV == 4 ? 3 : 4));
+    const int idx = lane >> SH;
+    if ((lane & ((1 << SH) - 1)) == 0 && g0 + (idx >> 1) < p.gn_groups) atomicAdd(&p.gn_stats[((int64_t)img * p.gn_groups + g0) * 2 + idx], (double)a[0]);
+  } else if (valid) {
+#pragma unroll
+    for (int i = 0; i < NV; i++)
+      if (g0 + (i >> 1) < p.gn_groups) atomicAdd(&p.gn_stats[((int64_t)img * p.gn_groups + g0) * 2 + i], (double)a[i]);
+  }
+}
+
+// One unit of U (16 / 32) accumulator columns of this thread's row: TMEM -> registers -> scale / bias / activation / alpha (-> GroupNorm partial
+// sums) -> bf16 -> swizzled staging row.  `first` : the staging tile is about to be overwritten for the first time since the last bulk store.
+template <int U, int ACT, bool GN, bool SCALE>
+__device__ __forceinline__ void epi_unit(const V2Params& p, uint32_t taddr, uint32_t bias_addr, float rsc, uint32_t row_addr, uint32_t ph, int cell0,
+                                         bool first, int lane, bool valid, int img, bool uniform, int co) {
+  uint32_t r[U];
+  tmem_ld16_nowait(taddr, r);
+  if constexpr (U == 32) tmem_ld16_nowait(taddr + 16u, r + 16);
+  tmem_ld_wait();
+  float v[U];
+#pragma unroll
+  for (int i = 0; i < U; i += 4) {
+    const float4 b = lds_f4(bias_addr + 4u * (uint32_t)i);
+    if constexpr (SCALE) {
+      v[i] = fmaf(__uint_as_float(r[i]), rsc, b.x); v[i + 1] = fmaf(__uint_as_float(r[i + 1]), rsc, b.y);
+      v[i + 2] = fmaf(__uint_as_float(r[i + 2]), rsc, b.z); v[i + 3] = fmaf(__uint_as_float(r[i + 3]), rsc, b.w);
+    } else {
+      v[i] = __uint_as_float(r[i]) + b.x; v[i + 1] = __uint_as_float(r[i + 1]) + b.y;
+      v[i + 2] = __uint_as_float(r[i + 2]) + b.z; v[i + 3] = __uint_as_float(r[i + 3]) + b.w;
+    }
+  }
+  if constexpr (ACT == YAD_ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < U; i++) { const float h = 0.5f * v[i]; v[i] = fmaf(h, v2_tanh(h), h); }
+  } else if constexpr (ACT == YAD_ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < U; i++) v[i] = fmaf(0.5f, v2_tanh(0.5f * v[i]), 0.5f);
+  } else if constexpr (ACT == ACT_GENERIC) {
+    if (p.act == YAD_ACT_SILU) {
+#pragma unroll
+      for (int i = 0; i < U; i++) { const float h = 0.5f * v[i]; v[i] = fmaf(h, v2_tanh(h), h); }
+    } else if (p.act == YAD_ACT_SIGMOID) {
+#pragma unroll
+      for (int i = 0; i < U; i++) v[i] = fmaf(0.5f, v2_tanh(0.5f * v[i]), 0.5f);
+    } else if (p.act != YAD_ACT_NONE) {
+      apply_act_n<U>(v, p.act);
+    }
+  }
+  if (p.alpha != 1.0f) {
+#pragma unroll
+    for (int i = 0; i < U; i++) v[i] *= p.alpha;
+  }
+  if constexpr (GN) {
+    if (p.gn_stats) {
+      if (p.cpg == 4) gn_unit<U, 4>(p, v, valid, lane, img, uniform, co);
+      else if (p.cpg == 8) gn_unit<U, 8>(p, v, valid, lane, img, uniform, co);
+      else gn_unit<U, 16>(p, v, valid, lane, img, uniform, co);
+    }
+  }
+  if (first) {
+    if (elect_one()) tma_store_wait_read();  // same lane that issued (and committed) the previous bulk store of this warp
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j < U / 8; j++) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+    sts16v(row_addr + ((((uint32_t)(cell0 + j)) ^ ph) << 4), u);
+  }
+}
+
+template <bool PATCH, int ACT, bool MULADD, bool GN, bool SCALE>
+__global__ void __launch_bounds__(V2_MAX_THREADS, 1) conv2_kernel(const __grid_constant__ V2Params p, const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + p.off_bars;
+  auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(p.stages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * p.stages + 2 + a); };
+  auto b_bar = [&](int i) { return bars + 8u * (uint32_t)(2 * p.stages + 4 + i); };
+  const uint32_t tmem_ptr_addr = bars + 8u * (uint32_t)(2 * p.stages + 4 + V2_MAX_BCHUNKS);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nbch = p.tiles_n * p.ntaps * p.kpt;
+  const int per_img = p.tiles_x * p.tiles_y;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (uint32_t)p.ew); }
+    for (int i = 0; i < nbch; i++) mbar_init(b_bar(i), 1);
+    fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  pdl_sync();  // on-chip prologue done; from here on the kernel reads what its predecessors wrote
+  {            // bias table (zeros without a bias): tiles_n * n_tile floats
+    float* bs = reinterpret_cast<float*>(smem_raw + (base + p.off_bias - raw));
+    const int nb = p.tiles_n * p.n_tile;
+    for (int i = tid; i < nb; i += (int)blockDim.x) bs[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ================= TMA producer (warp-uniform loop, the elected lane issues) =================
+    {
+      const bool leader = elect_one();
+      // resident weights: chunk (nt, t, c) = 64 K columns [t * cin + 64 c, +64) of the n_tile rows of column tile nt
+      for (int i = 0; i < nbch; i++) {
+        const int c = i % p.kpt, t = (i / p.kpt) % p.ntaps, nt = i / (p.kpt * p.ntaps);
+        if (leader) {
+          mbar_expect_tx(b_bar(i), p.b_chunk_bytes);
+          tma_load_2d(base + p.off_b + (uint32_t)i * p.b_chunk_bytes, &tmB, b_bar(i), t * p.cin + c * 64, nt * p.n_tile);
+        }
+      }
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.tiles_n;
+        int img = 0, ty0 = 0, tx0 = 0;
+        if (PATCH) {
+          img = mt / per_img;
+          const int r = mt - img * per_img;
+          ty0 = (r / p.tiles_x) * V2_BH;
+          tx0 = (r % p.tiles_x) * V2_BW;
+        }
+        for (int c = 0; c < p.kpt; c++, it++) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1u;
+          const uint32_t a_s = base + p.off_a + (uint32_t)s * p.a_stage_bytes;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          if (leader) {
+            mbar_expect_tx(full_bar(s), p.a_tx_bytes);
+            if (PATCH) tma_load_4d(a_s, &tmA, full_bar(s), c * 64, tx0 - 1, ty0 - 1, img);
+            else tma_load_2d(a_s, &tmA, full_bar(s), c * 64, mt * V2_BM);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    // The whole warp walks the loops (warp-uniform control flow keeps descriptors and barrier addresses in uniform registers); the lane chosen by
+    // elect.sync issues.  Per MMA: two 32-bit adds and the tcgen05.mma -- the first version (one divergent thread, 64-bit descriptor rebuilds,
+    // runtime accumulate predicate) needed ~200 issue cycles per MMA and was THE limiter of the 3x3 convolutions (profiles/r2_ncu_conv_v2.md).
+    {
+      const bool leader = elect_one();
+      const uint32_t idesc = v2_idesc(p.n_tile);
+      const uint32_t a_hi = v2_desc_hi(PATCH ? (uint32_t)p.pw * 128u : 1024u), b_hi = v2_desc_hi(1024u);
+      const uint32_t b_lo0 = v2_desc_lo(base + p.off_b), b_step = p.b_chunk_bytes >> 4;
+      uint32_t it = 0, seen = 0;
+      int i = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, i++) {
+        const int nt = tile % p.tiles_n;
+        const int acc = i % p.acc_stages;
+        mbar_wait(tempty_bar(acc), (((uint32_t)(i / p.acc_stages)) & 1u) ^ 1u);  // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
+        bool fresh = true;  // the next MMA overwrites the accumulator
+        for (int c = 0; c < p.kpt; c++, it++) {
+          const int s = it % p.stages;
+          mbar_wait(full_bar(s), (it / p.stages) & 1u);
+          tc_fence_after();
+          const uint32_t a_lo0 = v2_desc_lo(base + p.off_a + (uint32_t)s * p.a_stage_bytes);
+          const int krem = p.cin - c * 64;
+          const int ksteps = krem >= 64 ? 4 : (krem + 15) >> 4;
+          for (int t = 0; t < p.ntaps; t++) {
+            const int bi = (nt * p.ntaps + t) * p.kpt + c;
+            if (!((seen >> bi) & 1u)) {  // first use of this weight chunk: its TMA load must have landed
+              mbar_wait(b_bar(bi), 0u);
+              tc_fence_after();
+              seen |= 1u << bi;
+            }
+            const uint32_t a_lo = a_lo0 + (PATCH ? (uint32_t)p.tap_row[t] * 8u : 0u), b_lo = b_lo0 + (uint32_t)bi * b_step;
+            if (leader) {
+              if (fresh) umma_bf16<false>(d_tmem, pack64(a_lo, a_hi), pack64(b_lo, b_hi), idesc);
+              else umma_bf16<true>(d_tmem, pack64(a_lo, a_hi), pack64(b_lo, b_hi), idesc);
+              if (ksteps == 4) {
+                umma_bf16<true>(d_tmem, pack64(a_lo + 2u, a_hi), pack64(b_lo + 2u, b_hi), idesc);
+                umma_bf16<true>(d_tmem, pack64(a_lo + 4u, a_hi), pack64(b_lo + 4u, b_hi), idesc);
+                umma_bf16<true>(d_tmem, pack64(a_lo + 6u, a_hi), pack64(b_lo + 6u, b_hi), idesc);
+              } else {
+                for (int k = 1; k < ksteps; k++) umma_bf16<true>(d_tmem, pack64(a_lo + 2u * k, a_hi), pack64(b_lo + 2u * k, b_hi), idesc);
+              }
+            }
+            fresh = false;
+          }
+          if (leader) umma_commit(empty_bar(s));
+        }
+        if (leader) umma_commit(tfull_bar(acc));
+      }
+    }
+    __syncwarp();
+    tc_fence_before();
+  } else {
+    // ================= epilogue: 8 or 16 warps, TMEM lane quarter = warp & 3, the 2 / 4 warps of a quarter split the columns =================
+    const int q = warp & 3, ew = warp - 2, way = ew >> 2;
+    const int cb = p.bnd[way], ce = p.bnd[way + 1];
+    const uint32_t stg = base + p.off_stg + (uint32_t)ew * p.stg_warp_bytes;
+    const uint32_t RB = 2u * (uint32_t)p.sc, swz = (RB >> 4) - 1u;
+    const uint32_t row_addr = stg + (uint32_t)lane * RB;
+    const uint32_t ph = (row_addr >> 7) & swz;
+    const uint32_t bias_s = base + p.off_bias;
+    const uint32_t lane_base = ((uint32_t)(q * 32)) << 16;
+    // phase-2 geometry (mul / add on the staged piece): cpr lanes sweep one row
+    const int cpr = p.sc >> 3, rpp = 32 / cpr, rr0 = lane / cpr, cj = lane - rr0 * cpr;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, i++) {
+      const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n, n0 = nt * p.n_tile;
+      int img = 0, ty0 = 0, tx0 = 0, m_base = 0;
+      bool valid, uniform = true;
+      int dp = 0;
+      if (PATCH) {
+        img = mt / per_img;
+        const int r = mt - img * per_img;
+        ty0 = (r / p.tiles_x) * V2_BH;
+        tx0 = (r % p.tiles_x) * V2_BW;
+        const int oy = ty0 + 4 * q + (lane >> 3), ox = tx0 + (lane & 7);
+        valid = oy < p.hm && ox < p.wm;
+        dp = (img * p.hm + oy) * p.wm + ox;
+      } else {
+        m_base = mt * V2_BM + 32 * q;
+        dp = m_base + lane;
+        valid = dp < p.m_total;
+        if (GN || SCALE) {
+          const int img0 = m_base / p.hw, rem = m_base - img0 * p.hw;
+          uniform = rem + 32 <= p.hw;
+          img = img0 + ((rem + lane >= p.hw) ? 1 : 0);
+        }
+      }
+      float rsc = 1.0f;
+      if constexpr (SCALE) {
+        if (valid) {
+          if (p.img_scale) rsc = p.img_scale[img];
+          if (p.pix_scale) rsc *= __bfloat162float(p.pix_scale[(int64_t)dp * p.pix_scale_ld]);
+        }
+      }
+      const int acc = i % p.acc_stages;
+      mbar_wait(tfull_bar(acc), ((uint32_t)(i / p.acc_stages)) & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(acc * p.n_tile) + lane_base;
+      const bool store_ok = !PATCH || (ty0 + 4 * q < p.hm);  // warp-uniform: a patch-mode box entirely below the image is not issued
+      if (cb >= ce) {  // this warp owns no columns of so narrow a tile: hand the accumulator back at once
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+      for (int c0 = cb; c0 < ce; c0 += p.sc) {
+        if (p.sc >= 32) {
+          for (int u0 = 0; u0 < p.sc; u0 += 32)
+            epi_unit<32, ACT, GN, SCALE>(p, tacc + (uint32_t)(c0 + u0), bias_s + 4u * (uint32_t)(n0 + c0 + u0), rsc, row_addr, ph, u0 >> 3, u0 == 0, lane,
+                                         valid, img, uniform, n0 + c0 + u0);
+        } else {
+          epi_unit<16, ACT, GN, SCALE>(p, tacc + (uint32_t)c0, bias_s + 4u * (uint32_t)(n0 + c0), rsc, row_addr, ph, 0, true, lane, valid, img, uniform,
+                                       n0 + c0);
+        }
+        if (c0 + p.sc >= ce) {  // last TMEM read of this tile by this warp: hand the accumulator back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        if constexpr (MULADD) {
+          if (p.mul || p.add) {
+            __syncwarp();
+            const int co = n0 + c0 + cj * 8;
+            if (co < p.cout) {
+#pragma unroll 2
+              for (int row = rr0; row < 32; row += rpp) {
+                int64_t d;
+                bool ok;
+                if (PATCH) {
+                  const int oy = ty0 + 4 * q + (row >> 3), ox = tx0 + (row & 7);
+                  ok = oy < p.hm && ox < p.wm;
+                  d = (int64_t)(img * p.hm + oy) * p.wm + ox;
+                } else {
+                  d = (int64_t)m_base + row;
+                  ok = d < p.m_total;
+                }
+                if (!ok) continue;
+                const uint32_t ra = stg + (uint32_t)row * RB;
+                const uint32_t ca = ra + ((((uint32_t)cj) ^ ((ra >> 7) & swz)) << 4);
+                uint4 u = lds16(ca);
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+                if (p.mul && p.add) {
+                  const uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.mul + d * p.mul_ld + co));
+                  const uint4 av = __ldg(reinterpret_cast<const uint4*>(p.add + d * p.add_ld + co));
+                  const __nv_bfloat162* hm = reinterpret_cast<const __nv_bfloat162*>(&mv);
+                  const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&av);
+#pragma unroll
+                  for (int e = 0; e < 4; e++) h[e] = __hfma2(h[e], hm[e], ha[e]);
+                } else if (p.mul) {
+                  const uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.mul + d * p.mul_ld + co));
+                  const __nv_bfloat162* hm = reinterpret_cast<const __nv_bfloat162*>(&mv);
+#pragma unroll
+                  for (int e = 0; e < 4; e++) h[e] = __hmul2(h[e], hm[e]);
+                } else {
+                  const uint4 av = __ldg(reinterpret_cast<const uint4*>(p.add + d * p.add_ld + co));
+                  const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&av);
+#pragma unroll
+                  for (int e = 0; e < 4; e++) h[e] = __hadd2(h[e], ha[e]);
+                }
+                sts16v(ca, u);
+              }
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (store_ok) {  // warp-uniform
+          if (elect_one()) {
+            if (PATCH) tma_store_4d(&tmY, stg, n0 + c0, tx0, ty0 + 4 * q, img);
+            else tma_store_2d(&tmY, stg, n0 + c0, m_base);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (elect_one()) tma_store_wait_read();  // shared memory must outlive the last bulk store's read
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+int v2_make_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { yad_set_error("conv2d_v2: cuTensorMapEncodeTiled is unavailable"); return 1; }
+  cuuint64_t d[5], st[5];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; i++) st[i] = strides_bytes[i];
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { yad_set_error("conv2d_v2: cuTensorMapEncodeTiled failed with %d", (int)r); return 1; }
+  return 0;
+}
+
+int v2_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && e[0] ? atoi(e) : dflt;
+}
+
+template <bool PATCH, int ACT, bool MULADD, bool GN, bool SCALE>
+int v2_launch_t(const V2Params& p, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv2_kernel<PATCH, ACT, MULADD, GN, SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      yad_set_error("conv2d_v2: cannot raise the dynamic shared memory limit");
+      return 2;
+    }
+    attr_set = true;
+  }
+  YAD_LAUNCH((conv2_kernel<PATCH, ACT, MULADD, GN, SCALE>), grid, 64 + 32 * p.ew, smem, st, p, tmA, tmB, tmY);
+  YAD_LAUNCH_CHECK("conv2d_v2");
+  return 0;
+}
+
+template <bool PATCH>
+int v2_dispatch(const V2Params& p, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, int grid, size_t smem, cudaStream_t st) {
+  const bool muladd = p.mul || p.add, gn = p.gn_stats != nullptr, scale = p.img_scale || p.pix_scale;
+#define V2_CASE(ACT_, MA_, GN_, SC_) return v2_launch_t<PATCH, ACT_, MA_, GN_, SC_>(p, tmA, tmB, tmY, grid, smem, st)
+  if (!gn && !scale) {
+    if (p.act == YAD_ACT_SILU) { if (muladd) V2_CASE(YAD_ACT_SILU, true, false, false); else V2_CASE(YAD_ACT_SILU, false, false, false); }
+    if (p.act == YAD_ACT_NONE) { if (muladd) V2_CASE(YAD_ACT_NONE, true, false, false); else V2_CASE(YAD_ACT_NONE, false, false, false); }
+    if constexpr (!PATCH) {
+      if (p.act == YAD_ACT_SIGMOID) { if (muladd) V2_CASE(YAD_ACT_SIGMOID, true, false, false); else V2_CASE(YAD_ACT_SIGMOID, false, false, false); }
+    }
+  }
+  if (gn && !muladd && p.act == YAD_ACT_NONE) {
+    if (!scale) V2_CASE(YAD_ACT_NONE, false, true, false);
+    if constexpr (!PATCH) V2_CASE(YAD_ACT_NONE, false, true, true);
+  }
+  if constexpr (!PATCH) V2_CASE(ACT_GENERIC, true, true, true);
+  else if (!scale) V2_CASE(ACT_GENERIC, true, true, false);
+#undef V2_CASE
+  yad_set_error("conv2d_v2: no kernel variant for this epilogue");
+  return 1;
+}
+
+int pick_n_tile_v2(int cout) {
+  const int c16 = (cout + 15) / 16 * 16;
+  if (c16 <= 256) return c16;
+  const int tiles = (c16 + 255) / 256;
+  return ((c16 + tiles - 1) / tiles + 15) / 16 * 16;
+}
+
+}  // namespace
+
+// 0: not eligible (the caller falls back to conv_tma_kernel / conv_tc_kernel); fills the launch plan otherwise
+static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, V2Params* out, size_t* smem_out) {
+  if (d->mode != YAD_CONV_NORMAL || d->stride != 1) return 0;
+  const bool flat = d->kh == 1 && d->kw == 1 && d->pad_h == 0 && d->pad_w == 0;
+  const bool patch = d->kh == 3 && d->kw == 3 && d->pad_h == 1 && d->pad_w == 1;
+  if (!flat && !patch) return 0;
+  if (x->c < 16 || (x->c % 8) || (y->c % 8) || (x->ld % 8) || (y->ld % 8)) return 0;
+  if (((uintptr_t)x->ptr & 15) || ((uintptr_t)y->ptr & 15)) return 0;
+  if (y->h != x->h || y->w != x->w || y->n != x->n) return 0;
+  if (e->gn_stats && e->gn_groups == 0) return 0;  // fused batch statistics (train-mode BatchNorm) stay on conv_tma_kernel<true>
+  if (patch && (e->img_scale || e->pix_scale)) return 0;
+  if ((e->mul && ((uintptr_t)e->mul & 15 || e->mul_ld % 8)) || (e->add && ((uintptr_t)e->add & 15 || e->add_ld % 8))) return 0;
+  const int64_t M = (int64_t)x->n * x->h * x->w;
+  if (M + V2_BM >= (int64_t)1 << 31) return 0;
+  V2Params p;
+  memset(&p, 0, sizeof(p));
+  p.n = x->n; p.hm = y->h; p.wm = y->w; p.hw = y->h * y->w; p.cin = x->c; p.cout = y->c; p.m_total = (int)M;
+  p.n_tile = pick_n_tile_v2(p.cout);
+  p.tiles_n = (p.cout + p.n_tile - 1) / p.n_tile;
+  p.ntaps = patch ? 9 : 1;
+  p.kpt = (p.cin + 63) / 64;
+  if (p.tiles_n * p.ntaps * p.kpt > V2_MAX_BCHUNKS) return 0;
+  if (e->gn_stats) {
+    if (e->gn_groups <= 0 || y->c % e->gn_groups) return 0;
+    p.cpg = y->c / e->gn_groups;
+    if (p.cpg != 4 && p.cpg != 8 && p.cpg != 16) return 0;
+  }
+  p.acc_stages = (2 * p.n_tile <= 512) ? 2 : 1;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.acc_stages * p.n_tile) p.tmem_cols <<= 1;
+  static int ew_env = -1;
+  if (ew_env < 0) ew_env = v2_env("YAD_CONV2_EW", 0);
+  auto set_ew = [&](int ew) {
+    p.ew = ew;
+    const int ways = p.ew / 4, u16 = p.n_tile / 16;  // columns are dealt in units of 16, the first ways take the remainder
+    int at = 0;
+    for (int w = 0; w < ways; w++) { p.bnd[w] = at; at += 16 * (u16 / ways + (w < u16 % ways ? 1 : 0)); }
+    for (int w = ways; w <= 4; w++) p.bnd[w] = p.n_tile;
+    int sc = 64;  // store box width: the widest of 64 / 32 / 16 columns that divides every warp's range
+    for (int w = 0; w < ways; w++)
+      while (sc > 16 && ((p.bnd[w + 1] - p.bnd[w]) % sc)) sc >>= 1;
+    p.sc = sc;
+  };
+  set_ew(ew_env == 8 || ew_env == 16 ? ew_env : (p.n_tile > 64 ? 16 : 8));
+  if (patch) {
+    static int pw_env = -1;
+    if (pw_env < 0) pw_env = v2_env("YAD_CONV2_PW", 10);
+    p.pw = pw_env == 16 ? 16 : 10;
+    p.tiles_x = (p.wm + V2_BW - 1) / V2_BW;
+    p.tiles_y = (p.hm + V2_BH - 1) / V2_BH;
+    for (int t = 0; t < 9; t++) p.tap_row[t] = (t / 3) * p.pw + (t % 3);
+    p.a_tx_bytes = (uint32_t)(p.pw * (V2_BH + 2) * 128);
+    p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
+    p.total_tiles = p.n * p.tiles_x * p.tiles_y * p.tiles_n;
+  } else {
+    p.tiles_x = p.tiles_y = 1;
+    p.a_tx_bytes = V2_BM * 128;
+    p.a_stage_bytes = p.a_tx_bytes;
+    p.total_tiles = (int)((M + V2_BM - 1) / V2_BM) * p.tiles_n;
+  }
+  p.b_chunk_bytes = (uint32_t)p.n_tile * 128u;
+  const uint32_t b_total = (uint32_t)(p.tiles_n * p.ntaps * p.kpt) * p.b_chunk_bytes;
+  const uint32_t bias_bytes = ((uint32_t)(p.tiles_n * p.n_tile) * 4u + 127u) & ~127u;
+  const uint32_t budget = 227u * 1024u - 1024u;
+  const uint32_t max_stages = patch ? 4u : 8u, min_stages = patch ? 2u : 3u;
+  uint32_t stages = 0, stg_total = 0;
+  auto total = [&](uint32_t s) { return b_total + s * p.a_stage_bytes + stg_total + bias_bytes + 8u * (2u * s + 4u + V2_MAX_BCHUNKS) + 16u; };
+  for (int attempt = 0; attempt < 2; attempt++) {  // 16 epilogue warps need twice the staging: fall back to 8 when the pipeline would starve
+    p.stg_warp_bytes = 32u * (uint32_t)p.sc * 2u;  // 1024 / 2048 / 4096: every warp's staging tile starts on its swizzle period
+    stg_total = (uint32_t)p.ew * p.stg_warp_bytes;
+    stages = max_stages;
+    while (stages >= 2 && total(stages) > budget) stages--;
+    if (stages >= min_stages || p.ew == 8) break;
+    set_ew(8);
+  }
+  if (stages < 2) return 0;
+  p.stages = (int)stages;
+  p.off_b = 0;
+  p.off_a = b_total;
+  p.off_stg = p.off_a + stages * p.a_stage_bytes;
+  p.off_bias = p.off_stg + stg_total;
+  p.off_bars = p.off_bias + bias_bytes;
+  *smem_out = 1024 + total(stages);
+  p.bias = e->bias; p.img_scale = e->img_scale; p.pix_scale = (const bf16*)e->pix_scale; p.pix_scale_ld = e->pix_scale_ld;
+  p.act = e->act; p.alpha = e->alpha;
+  p.mul = (const bf16*)e->mul; p.mul_ld = e->mul_ld; p.add = (const bf16*)e->add; p.add_ld = e->add_ld;
+  p.gn_stats = e->gn_stats; p.gn_groups = e->gn_groups;
+  *out = p;
+  return patch ? 2 : 1;
+}
+
+int yad_conv2d_v2_supported(const yad_tensor* x, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y) {
+  static int on = -1;
+  if (on < 0) on = v2_env("YAD_CONV_V2", 1);
+  if (!on && d->impl != 4) return 0;
+  if (!get_encode()) return 0;
+  V2Params p;
+  size_t smem;
+  return v2_plan(x, d, e, y, &p, &smem);
+}
+
+// The caller (yad_conv2d_tc) has validated shapes and zeroed the GroupNorm statistics buffer.
+int yad_conv2d_v2(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream) {
+  V2Params p;
+  size_t smem = 0;
+  const int kind = v2_plan(x, d, e, y, &p, &smem);
+  YAD_CHECK(kind != 0, "conv2d_v2: shape / epilogue not supported by the resident-weight tcgen05 kernel");
+  const bool patch = kind == 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tmA, tmB, tmY;
+  const int w_row = d->kh * d->kw * x->c;
+  if (patch) {
+    uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
+    uint64_t strides[3] = {(uint64_t)x->ld * 2, (uint64_t)x->w * x->ld * 2, (uint64_t)x->h * x->w * x->ld * 2};
+    uint32_t box[4] = {64, (uint32_t)p.pw, (uint32_t)(V2_BH + 2), 1};
+    if (v2_make_map(&tmA, x->ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  } else {
+    uint64_t dims[2] = {(uint64_t)x->c, (uint64_t)p.m_total}, strides[1] = {(uint64_t)x->ld * 2};
+    uint32_t box[2] = {64, V2_BM};
+    if (v2_make_map(&tmA, x->ptr, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {
+    const int cout_rows = (y->c + 7) / 8 * 8;
+    uint64_t dims[2] = {(uint64_t)w_row, (uint64_t)cout_rows}, strides[1] = {(uint64_t)w_row * 2};
+    uint32_t box[2] = {64, (uint32_t)p.n_tile};
+    if (v2_make_map(&tmB, w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {
+    const CUtensorMapSwizzle sw = p.sc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.sc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    if (patch) {
+      uint64_t dims[4] = {(uint64_t)y->c, (uint64_t)y->w, (uint64_t)y->h, (uint64_t)y->n};
+      uint64_t strides[3] = {(uint64_t)y->ld * 2, (uint64_t)y->w * y->ld * 2, (uint64_t)y->h * y->w * y->ld * 2};
+      uint32_t box[4] = {(uint32_t)p.sc, V2_BW, 4, 1};
+      if (v2_make_map(&tmY, y->ptr, 4, dims, strides, box, sw)) return 1;
+    } else {
+      uint64_t dims[2] = {(uint64_t)y->c, (uint64_t)p.m_total}, strides[1] = {(uint64_t)y->ld * 2};
+      uint32_t box[2] = {(uint32_t)p.sc, 32};
+      if (v2_make_map(&tmY, y->ptr, 2, dims, strides, box, sw)) return 1;
+    }
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int grid = num_sms < p.total_tiles ? num_sms : p.total_tiles;
+  if (patch) return v2_dispatch<true>(p, tmA, tmB, tmY, grid, smem, st);
+  return v2_dispatch<false>(p, tmA, tmB, tmY, grid, smem, st);
+}

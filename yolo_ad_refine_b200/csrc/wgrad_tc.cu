@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(WT_THREADS) wgrad_tc_kernel(const __grid_const
   pdl_sync();  // on-chip prologue done; from here on the kernel reads what its predecessors wrote
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // warp-uniform producer loop, the elected lane issues (up to 18 TMA boxes per stage: a divergent single thread pays ~100 cycles for each)
+      const bool leader = elect_one();
       const uint32_t tx_bytes = (uint32_t)(p.n_groups + nrg) * box_bytes;
       uint32_t it = 0;
       for (int tile = t_begin; tile < t_end; tile++, it++) {
@@ -102,36 +103,43 @@ __global__ void __launch_bounds__(WT_THREADS) wgrad_tc_kernel(const __grid_const
         const uint32_t ph = (it / p.stages) & 1u;
         const uint32_t st = base + s * stage_bytes;
         mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), tx_bytes);
-        for (int g = 0; g < p.n_groups; g++) tma_load_4d(st + g * box_bytes, &tmDy, full_bar(s), g * 64, tx0, ty0, img);
+        if (leader) mbar_expect_tx(full_bar(s), tx_bytes);
+        for (int g = 0; g < p.n_groups; g++)
+          if (leader) tma_load_4d(st + g * box_bytes, &tmDy, full_bar(s), g * 64, tx0, ty0, img);
         for (int j = 0; j < nrg; j++) {
           const int rg = rg0 + j, tap = rg / p.G, cg = rg - tap * p.G;
-          tma_load_4d(st + (p.n_groups + j) * box_bytes, &tmX, full_bar(s), cg * 64, p.stride * tx0 + p.dx[tap], p.stride * ty0 + p.dy[tap], img);
+          if (leader) tma_load_4d(st + (p.n_groups + j) * box_bytes, &tmX, full_bar(s), cg * 64, p.stride * tx0 + p.dx[tap], p.stride * ty0 + p.dy[tap], img);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // warp-uniform issue loop (the whole warp walks it, the lane elect.sync picks issues): descriptor words stay in uniform registers and the
+    // per-MMA work is two 32-bit adds -- a single divergent thread needed ~200 issue cycles per tcgen05.mma
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc_mn(p.cout);
+      const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);        // SBO 1024 B, version 1, SWIZZLE_128B
+      const uint32_t lo_flags = ((box_bytes >> 4) & 0x3FFFu) << 16;               // LBO = one 64-channel box
       uint32_t it = 0;
       for (int tile = t_begin; tile < t_end; tile++, it++) {
         const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1u;
-        mbar_wait(full_bar(s), ph);
+        mbar_wait(full_bar(s), (it / p.stages) & 1u);
         tc_fence_after();
         const uint32_t st = base + s * stage_bytes;
-        const uint32_t b_s = st, a_s = st + p.n_groups * box_bytes;
+        const uint32_t b_lo = (((st) & 0x3FFFFu) >> 4) | lo_flags, a_lo0 = (((st + p.n_groups * box_bytes) & 0x3FFFFu) >> 4) | lo_flags;
+        const int ks = p.kb / 16;
         for (int mt = 0; mt < nmt; mt++) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(mt * p.cout);
-          for (int k = 0; k < p.kb / 16; k++) {
-            const uint64_t ad = make_sdesc_mn(a_s + (uint32_t)(2 * mt) * box_bytes + (uint32_t)k * 2048u, box_bytes);
-            const uint64_t bd = make_sdesc_mn(b_s + (uint32_t)k * 2048u, box_bytes);
-            umma_f16(d_tmem, ad, bd, idesc, (it | (uint32_t)k) ? 1u : 0u);
+          const uint32_t a_lo = a_lo0 + (uint32_t)(2 * mt) * (box_bytes >> 4);
+          if (leader) {
+            if (it == 0) umma_bf16<false>(d_tmem, pack64(a_lo, hi), pack64(b_lo, hi), idesc);
+            else umma_bf16<true>(d_tmem, pack64(a_lo, hi), pack64(b_lo, hi), idesc);
+            for (int k = 1; k < ks; k++) umma_bf16<true>(d_tmem, pack64(a_lo + 128u * k, hi), pack64(b_lo + 128u * k, hi), idesc);  // 2048 B per K step
           }
         }
-        umma_commit(empty_bar(s));
+        if (leader) umma_commit(empty_bar(s));
       }
-      umma_commit(done_bar);
+      if (leader) umma_commit(done_bar);
     }
     __syncwarp();
     tc_fence_before();

@@ -39,9 +39,10 @@ def preprocess_targets(batch_idx, cls, bboxes, batch_size, imgsz_hw, device):
 
 
 def detection_loss_raw(pred_distri, pred_scores, anchor_points, stride_tensor, gt_labels, gt_bboxes, mask_gt, gains=(7.5, 0.5, 1.5), topk=10,
-                       reg_max=16, want_grad=True):
+                       reg_max=16, want_grad=True, assign=None):
     """pred_distri (B,N,4*reg_max), pred_scores (B,N,nc) fp32 contiguous logits.  Returns (out4 = [box, cls, dfl, total*B], grad_distri,
-    grad_scores, aux)."""
+    grad_scores, aux).  assign: the `aux` of another call -- its (no-grad) TaskAlignedAssigner outputs are used instead of running the assigner,
+    which lets a lower-precision step be compared with an fp32 step on the SAME discrete targets (tests)."""
     B, N, nc = pred_scores.shape
     dev = pred_scores.device
     L = ops.lib()
@@ -56,7 +57,11 @@ def detection_loss_raw(pred_distri, pred_scores, anchor_points, stride_tensor, g
     check(L.yad_loss_decode(_p(pred_distri), _p(pred_scores), _p(anc), _p(stv), B, N, nc, reg_max, _p(boxes), _p(boxes_px), _p(sig), st),
           "yad_loss_decode")
     anc_px = (anc * stv[:, None]).contiguous()
-    tl, tb, ts, fg, tgi = tal_assign(sig, boxes_px, anc_px, gt_labels, gt_bboxes, mask_gt, topk, 0.5, 6.0, 1e-9, sums=sums)
+    if assign is None:
+        tl, tb, ts, fg, tgi = tal_assign(sig, boxes_px, anc_px, gt_labels, gt_bboxes, mask_gt, topk, 0.5, 6.0, 1e-9, sums=sums)
+    else:
+        tl, tb, ts, fg, tgi = (assign[k] for k in ("target_labels", "target_bboxes", "target_scores", "fg_mask", "target_gt_idx"))
+        sums[4], sums[5] = fg.sum().double(), ts.sum().double()  # what yad_tal_assign leaves there: positives, target_scores_sum
     fg_u8 = fg.to(torch.uint8)
     gd = torch.empty_like(pred_distri) if want_grad else None
     gs = torch.empty_like(pred_scores) if want_grad else None

@@ -7,7 +7,12 @@ _WS = {}
 
 
 def _workspace(nbytes, device):
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    """Scratch for one yad_nms call.  While a CUDA graph is being captured every call gets its OWN tensor from the capture's private pool (it lives
+    and dies with the graph, so a replay can never scribble on memory the caching allocator has handed to somebody else); eager calls share one
+    buffer per (device, stream) -- kernels of one stream are ordered, and a buffer that is outgrown is released in stream order."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
     ws = _WS.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
@@ -16,8 +21,9 @@ def _workspace(nbytes, device):
 
 
 def nms_raw(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False, max_det=300, nc=0,
-            max_nms=30000, max_wh=7680):
-    """Device-side NMS without the host read-back: returns (out (B,max_det,6) fp32, out_idx (B,max_det,2) int32, count (B,) int32)."""
+            max_nms=30000, max_wh=7680, ws=None):
+    """Device-side NMS without the host read-back: returns (out (B,max_det,6) fp32, out_idx (B,max_det,2) int32, count (B,) int32).
+    ws: optional caller-owned uint8 workspace of at least ops.nms_workspace_bytes(...) bytes."""
     assert prediction.is_cuda, "the YOLO-AD-Refine NMS runs on the GPU only (no CPU fallback)"
     if prediction.dtype != torch.float32 or not prediction.is_contiguous():
         prediction = prediction.float().contiguous()
@@ -33,7 +39,10 @@ def nms_raw(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=
     out = torch.empty((bs, max_det, 6), dtype=torch.float32, device=dev)
     out_idx = torch.empty((bs, max_det, 2), dtype=torch.int32, device=dev)
     count = torch.zeros((bs,), dtype=torch.int32, device=dev)
-    ws = _workspace(ops.nms_workspace_bytes(bs, n, nc, multi_label and nc > 1, max_nms), dev)
+    need = ops.nms_workspace_bytes(bs, n, nc, multi_label and nc > 1, max_nms)
+    if ws is None:
+        ws = _workspace(need, dev)
+    assert ws.is_cuda and ws.dtype == torch.uint8 and ws.numel() >= need, "nms_raw: workspace too small"
     ops.nms(prediction, float(conf_thres), float(iou_thres), cm, agnostic, multi_label, max_det, max_nms, float(max_wh), out, out_idx, count, ws)
     return out, out_idx, count
 

@@ -35,7 +35,7 @@ class TrainEngine:
             self._anchors[shapes] = (a.to(self.device), s.to(self.device))
         return self._anchors[shapes]
 
-    def forward_backward(self, img, batch_idx, cls, bboxes, update_bn=True, keep=False, zero_grad=True):
+    def forward_backward(self, img, batch_idx, cls, bboxes, update_bn=True, keep=False, zero_grad=True, assign=None):
         """img fp32 (B, 3, H, W) in [0, 1] or uint8 in [0, 255], on the device; targets as in the reference's batch dict (utils/loss.py:443-446).
         Leaves the gradients in tp.grad (reference state-dict layout) and returns out4 = [box, cls, dfl, total * B] (device, fp32).
         zero_grad=False accumulates onto the gradients of the previous call (the reference's `accumulate = max(round(nbs / batch), 1)`,
@@ -60,7 +60,8 @@ class TrainEngine:
             a0 += o.h * o.w
         anchors, stride_t = self._anchor(tuple((o.h, o.w) for o in outs))
         gt_labels, gt_bboxes, mask_gt = preprocess_targets(batch_idx, cls, bboxes, B, (img.shape[2], img.shape[3]), self.device)
-        out4, gd, gs, aux = detection_loss_raw(distri, logits, anchors, stride_t, gt_labels, gt_bboxes, mask_gt, self.gains, self.topk, self.reg_max)
+        out4, gd, gs, aux = detection_loss_raw(distri, logits, anchors, stride_t, gt_labels, gt_bboxes, mask_gt, self.gains, self.topk, self.reg_max,
+                                                  assign=assign)
         a0 = 0
         for o in outs:
             g.mark(o)
