@@ -1,0 +1,124 @@
+"""Row b of SURVEY.md section 8 on a GPU: the REFERENCE's own call stack -- `DetectionModel(yaml)` built by its `parse_model`, `_predict_once`
+routing (nn/tasks.py:141-168), `ops.non_max_suppression` looked up at call time (models/yolo/detect/predict.py:25) and the trainer's
+`model(batch)` -> `.backward()` (engine/trainer.py:382-394) -- with libyad-backed classes bound in by `plugin.install()`.  The reference comes from
+oracle/_ref (the copy oracle/build_ref.py makes; /root/reference in the build container); the tests skip when neither exists.
+
+Every scenario runs in its own interpreter: install() rebinds names inside the imported reference package, which must not leak into other tests."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+PRELUDE = r"""
+import json, os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch
+from oracle import ref_shims, synth
+assert ref_shims.available()
+ref_shims.install()
+import yolo_ad_refine_b200.plugin as yad
+bound = yad.install()
+from ultralytics.nn.tasks import DetectionModel
+from ultralytics.utils import ops as ref_ops
+from ultralytics.utils import IterableSimpleNamespace
+import yolo_ad_refine_b200.modules as M
+yaml = os.path.join(ref_shims.REFERENCE_ROOT, "z-yaml", "yolo11-701-YOLO-AD-Refine.yaml")
+model = DetectionModel(yaml, ch=3, nc=80, verbose=False)          # the reference's parse_model instantiates the libyad classes by name
+yad.convert_model(model)
+sd = synth.make_state_dict(seed=1)
+model.load_state_dict(sd, strict=True)
+GOLD = os.path.join(%(root)r, "tests", "golden")
+"""
+
+
+def _run(body):
+    from oracle import ref_shims
+    if not ref_shims.available():
+        pytest.skip("no reference tree (oracle/_ref or /root/reference)")
+    code = PRELUDE % {"root": ROOT} + body
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-3000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1]
+    return json.loads(line[7:])
+
+
+def test_reference_predict_stack_runs_libyad_and_matches_golden():
+    """DetectionModel.forward -> _predict_once over libyad modules, then the reference-side NMS call, against the fixture the pure reference wrote"""
+    res = _run(r"""
+assert isinstance(model.model[0], M.Conv) and isinstance(model.model[10], M.C2PTSSA) and isinstance(model.model[-1], M.AYHead)
+assert type(model.model[12]).__name__ == "YadConv2d" and type(model.model[13]).__name__ == "YadConvTranspose2d"
+model = model.eval().cuda()
+g = np.load(os.path.join(GOLD, "model_160.npz"))
+img = torch.from_numpy(synth.make_images(2, 160, 160, seed=2)).cuda()
+with torch.inference_mode():
+    y, feats = model(img)                                           # the reference's own forward / _predict_once
+    dets = ref_ops.non_max_suppression(y, 0.001, 0.7, max_det=300, multi_label=True, max_time_img=1e9)
+yy = y.float().cpu().numpy()
+err_cls = float(np.abs(yy[:, 4:] - g["y"][:, 4:]).max())
+err_box = float((np.abs(yy[:, :4] - g["y"][:, :4]) / (np.abs(g["y"][:, :4]) + 1.0)).max())
+g640 = np.load(os.path.join(GOLD, "model_640.npz"))
+img1 = torch.from_numpy(synth.make_images(1, 640, 640, seed=2)).cuda()
+model.model[-1].shape = None
+with torch.inference_mode():
+    y1, _ = model(img1)
+    d1 = ref_ops.non_max_suppression(y1, 0.25, 0.7, max_det=300, max_time_img=1e9)[0].cpu().numpy()
+ref = g640["nms_predict"]
+k = min(len(d1), len(ref), 50)
+print("RESULT " + json.dumps(dict(bound=len(bound), err_cls=err_cls, err_box=err_box, n_det=[int(d.shape[0]) for d in dets], n640=int(len(d1)), ref640=int(len(ref)),
+      cls_match=float((d1[:k, 5] == ref[:k, 5]).mean()) if k else 1.0,
+      score_err=float(np.abs(np.sort(d1[:k, 4])[::-1] - np.sort(ref[:k, 4])[::-1]).max()) if k else 0.0)))
+""")
+    assert res["bound"] > 60
+    assert res["err_cls"] < 1e-4 and res["err_box"] < 1e-3, res          # fp32 module path: the reference's numbers
+    assert abs(res["n640"] - res["ref640"]) <= max(3, res["ref640"] // 50) and res["cls_match"] > 0.9 and res["score_err"] < 2e-3, res
+
+
+def test_reference_trainer_step_through_model_batch_matches_reference_gradients():
+    """trainer semantics: loss, items = model(batch); loss.backward(); gradients land in the module parameters' .grad and equal the fixture written
+    by the pure reference (tests/golden/train_step.npz, case b2_160: fp32 SIMT build, same bar as tests/test_gpu_train_step.py); an SGD step of
+    torch.optim on those parameters then changes them, and BatchNorm buffers / num_batches_tracked moved."""
+    res = _run(r"""
+from oracle import cases
+model.args = IterableSimpleNamespace(box=7.5, cls=0.5, dfl=1.5)
+model = model.train().cuda()
+model.__dict__["_yad_train_dtype"] = torch.float32
+model.__dict__["_yad_conv_impl"] = 1
+g = np.load(os.path.join(GOLD, "train_step.npz"))
+img, bi, cl, bb = cases.train_step_inputs(**cases.TRAIN_STEP_CASES["b2_160"])
+batch = dict(img=torch.from_numpy(img).cuda(), batch_idx=torch.from_numpy(bi), cls=torch.from_numpy(cl), bboxes=torch.from_numpy(bb))
+rm0 = model.model[0].bn.running_mean.clone()
+opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9)
+opt.zero_grad()
+loss, items = model(batch)                                          # engine/trainer.py:384
+loss.backward()                                                      # :389
+name = "b2_160"
+worst, checked, missing = 0.0, 0, 0
+for k, p in model.named_parameters():
+    if f"{name}|{k}|none" in g.files:
+        continue
+    key = f"{name}|{k}|norm"
+    if key not in g.files:
+        continue
+    if p.grad is None:
+        missing += 1
+        continue
+    ref_norm = float(g[key])
+    if k.endswith((".conv.bias", ".conv1.bias")) and ref_norm < 1e-3:
+        continue
+    worst = max(worst, abs(float(p.grad.double().norm()) - ref_norm) / (ref_norm + 1e-6))
+    checked += 1
+w0 = model.model[0].conv.weight.detach().clone()
+opt.step()
+print("RESULT " + json.dumps(dict(loss=float(loss), loss_ref=float(g[f"{name}_loss"]), items=[float(v) for v in items], items_ref=[float(v) for v in g[f"{name}_items"]],
+      worst=worst, checked=checked, missing=missing, moved=float((model.model[0].conv.weight - w0).abs().max()),
+      bn_moved=float((model.model[0].bn.running_mean - rm0).abs().max()), tracked=int(model.model[0].bn.num_batches_tracked))))
+""")
+    assert abs(res["loss"] - res["loss_ref"]) < 1e-4 * abs(res["loss_ref"]), res
+    assert max(abs(a - b) / (abs(b) + 1e-6) for a, b in zip(res["items"], res["items_ref"])) < 1e-4, res
+    assert res["checked"] > 300 and res["missing"] == 0 and res["worst"] < 1e-2, res
+    assert res["moved"] > 0 and res["bn_moved"] > 0 and res["tracked"] == 1, res

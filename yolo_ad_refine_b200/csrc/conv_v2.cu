@@ -46,6 +46,7 @@ struct V2Params {
   int kpt, ntaps, pw;       // 64-wide K chunks per tap; taps; patch pitch in pixels
   int tap_row[9];           // patch row (= pixel index inside the patch) the A descriptor of tap t starts at
   int stages, acc_stages, tmem_cols;
+  int ksplit;               // 3x3: taps are dealt round-robin to `ksplit` accumulators (independent tcgen05.mma dependency chains), summed in the epilogue
   uint32_t off_b, b_chunk_bytes, off_a, a_stage_bytes, a_tx_bytes, off_stg, stg_warp_bytes, off_bias, off_bars;
   int sc, ew;               // columns per TMA store box (16 / 32 / 64); epilogue warps (8 / 16)
   int bnd[5];               // column ranges [bnd[w], bnd[w + 1]) of the ew / 4 warps that share a TMEM lane quarter
@@ -168,6 +169,14 @@ __device__ __forceinline__ void epi_unit(const V2Params& p, uint32_t taddr, uint
   tmem_ld16_nowait(taddr, r);
   if constexpr (U == 32) tmem_ld16_nowait(taddr + 16u, r + 16);
   tmem_ld_wait();
+  for (int sp = 1; sp < p.ksplit; sp++) {  // partial sums of the other tap groups (warp-uniform trip count)
+    uint32_t r2[U];
+    tmem_ld16_nowait(taddr + (uint32_t)(sp * p.n_tile), r2);
+    if constexpr (U == 32) tmem_ld16_nowait(taddr + (uint32_t)(sp * p.n_tile) + 16u, r2 + 16);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < U; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+  }
   float v[U];
 #pragma unroll
   for (int i = 0; i < U; i += 4) {
@@ -300,49 +309,75 @@ __global__ void __launch_bounds__(V2_MAX_THREADS, 1) conv2_kernel(const __grid_c
   } else if (warp == 1) {
     // ================= MMA issuer =================
     // The whole warp walks the loops (warp-uniform control flow keeps descriptors and barrier addresses in uniform registers); the lane chosen by
-    // elect.sync issues.  Per MMA: two 32-bit adds and the tcgen05.mma -- the first version (one divergent thread, 64-bit descriptor rebuilds,
-    // runtime accumulate predicate) needed ~200 issue cycles per MMA and was THE limiter of the 3x3 convolutions (profiles/r2_ncu_conv_v2.md).
+    // elect.sync issues.  Profile history (profiles/r2_ncu_conv_v2.md): one divergent thread rebuilding 64-bit descriptors needed ~200 issue cycles
+    // per tcgen05.mma and was THE limiter of the 3x3 convolutions; the warp-uniform loop still spent ~120 instructions per tap on index
+    // arithmetic.  Now the tap / K-step loops are fully unrolled with compile-time offsets: two 32-bit adds per MMA.
     {
       const bool leader = elect_one();
       const uint32_t idesc = v2_idesc(p.n_tile);
       const uint32_t a_hi = v2_desc_hi(PATCH ? (uint32_t)p.pw * 128u : 1024u), b_hi = v2_desc_hi(1024u);
       const uint32_t b_lo0 = v2_desc_lo(base + p.off_b), b_step = p.b_chunk_bytes >> 4;
-      uint32_t it = 0, seen = 0;
+      const uint32_t pw8 = (uint32_t)p.pw * 8u;                   // one patch row in descriptor units (16 bytes)
+      const uint32_t tstep = (uint32_t)p.kpt * b_step;            // weight chunks of consecutive taps
+      constexpr int NT = PATCH ? 9 : 1;
+      // every weight chunk must have landed before its first use: the first tile waits chunk by chunk (so its MMAs start under the weight
+      // load), later tiles never look at those barriers again
+      uint32_t it = 0;
       int i = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, i++) {
         const int nt = tile % p.tiles_n;
         const int acc = i % p.acc_stages;
         mbar_wait(tempty_bar(acc), (((uint32_t)(i / p.acc_stages)) & 1u) ^ 1u);  // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
-        bool fresh = true;  // the next MMA overwrites the accumulator
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.ksplit * p.n_tile);
+        const uint32_t nt_cols = (uint32_t)p.n_tile;
+        const int ks = p.ksplit;  // tap t accumulates into split t % ks; its first visit (chunk 0, t < ks) overwrites
+        const bool first_pass = i < p.tiles_n;  // the first visit of column tile nt (tiles of one CTA cycle through the column tiles)
         for (int c = 0; c < p.kpt; c++, it++) {
           const int s = it % p.stages;
           mbar_wait(full_bar(s), (it / p.stages) & 1u);
           tc_fence_after();
           const uint32_t a_lo0 = v2_desc_lo(base + p.off_a + (uint32_t)s * p.a_stage_bytes);
+          const int bi0 = nt * NT * p.kpt + c;                      // chunk of tap 0
+          const uint32_t b_lo_c = b_lo0 + (uint32_t)bi0 * b_step;
           const int krem = p.cin - c * 64;
           const int ksteps = krem >= 64 ? 4 : (krem + 15) >> 4;
-          for (int t = 0; t < p.ntaps; t++) {
-            const int bi = (nt * p.ntaps + t) * p.kpt + c;
-            if (!((seen >> bi) & 1u)) {  // first use of this weight chunk: its TMA load must have landed
-              mbar_wait(b_bar(bi), 0u);
+          const uint32_t acc0 = c > 0 ? 1u : 0u;                    // the first MMA of the tile overwrites the accumulator
+          if (first_pass) {
+            for (int t = 0; t < NT; t++) {
+              mbar_wait(b_bar(bi0 + t * p.kpt), 0u);
               tc_fence_after();
-              seen |= 1u << bi;
-            }
-            const uint32_t a_lo = a_lo0 + (PATCH ? (uint32_t)p.tap_row[t] * 8u : 0u), b_lo = b_lo0 + (uint32_t)bi * b_step;
-            if (leader) {
-              if (fresh) umma_bf16<false>(d_tmem, pack64(a_lo, a_hi), pack64(b_lo, b_hi), idesc);
-              else umma_bf16<true>(d_tmem, pack64(a_lo, a_hi), pack64(b_lo, b_hi), idesc);
-              if (ksteps == 4) {
-                umma_bf16<true>(d_tmem, pack64(a_lo + 2u, a_hi), pack64(b_lo + 2u, b_hi), idesc);
-                umma_bf16<true>(d_tmem, pack64(a_lo + 4u, a_hi), pack64(b_lo + 4u, b_hi), idesc);
-                umma_bf16<true>(d_tmem, pack64(a_lo + 6u, a_hi), pack64(b_lo + 6u, b_hi), idesc);
-              } else {
-                for (int k = 1; k < ksteps; k++) umma_bf16<true>(d_tmem, pack64(a_lo + 2u * k, a_hi), pack64(b_lo + 2u * k, b_hi), idesc);
+              const uint32_t a_lo = a_lo0 + (PATCH ? (uint32_t)(t / 3) * pw8 + (uint32_t)(t % 3) * 8u : 0u), b_lo = b_lo_c + (uint32_t)t * tstep;
+              if (leader) {
+                const uint32_t d = d_tmem + (uint32_t)(t % ks) * nt_cols;
+                umma_f16(d, pack64(a_lo, a_hi), pack64(b_lo, b_hi), idesc, t >= ks ? 1u : acc0);
+                for (int k = 1; k < ksteps; k++) umma_bf16<true>(d, pack64(a_lo + 2u * k, a_hi), pack64(b_lo + 2u * k, b_hi), idesc);
               }
             }
-            fresh = false;
+          } else if (ksteps == 4) {
+            if (leader) {
+#pragma unroll
+              for (int t = 0; t < NT; t++) {
+                const uint32_t a_lo = a_lo0 + (PATCH ? (uint32_t)(t / 3) * pw8 + (uint32_t)(t % 3) * 8u : 0u), b_lo = b_lo_c + (uint32_t)t * tstep;
+                const uint32_t d = d_tmem + (uint32_t)(t % ks) * nt_cols;
+                if (t < 4) umma_f16(d, pack64(a_lo, a_hi), pack64(b_lo, b_hi), idesc, t >= ks ? 1u : acc0);
+                else umma_bf16<true>(d, pack64(a_lo, a_hi), pack64(b_lo, b_hi), idesc);
+                umma_bf16<true>(d, pack64(a_lo + 2u, a_hi), pack64(b_lo + 2u, b_hi), idesc);
+                umma_bf16<true>(d, pack64(a_lo + 4u, a_hi), pack64(b_lo + 4u, b_hi), idesc);
+                umma_bf16<true>(d, pack64(a_lo + 6u, a_hi), pack64(b_lo + 6u, b_hi), idesc);
+              }
+            }
+          } else {
+            if (leader) {
+#pragma unroll
+              for (int t = 0; t < NT; t++) {
+                const uint32_t a_lo = a_lo0 + (PATCH ? (uint32_t)(t / 3) * pw8 + (uint32_t)(t % 3) * 8u : 0u), b_lo = b_lo_c + (uint32_t)t * tstep;
+                const uint32_t d = d_tmem + (uint32_t)(t % ks) * nt_cols;
+                if (t < 4) umma_f16(d, pack64(a_lo, a_hi), pack64(b_lo, b_hi), idesc, t >= ks ? 1u : acc0);
+                else umma_bf16<true>(d, pack64(a_lo, a_hi), pack64(b_lo, b_hi), idesc);
+                for (int k = 1; k < ksteps; k++) umma_bf16<true>(d, pack64(a_lo + 2u * k, a_hi), pack64(b_lo + 2u * k, b_hi), idesc);
+              }
+            }
           }
           if (leader) umma_commit(empty_bar(s));
         }
@@ -397,7 +432,7 @@ __global__ void __launch_bounds__(V2_MAX_THREADS, 1) conv2_kernel(const __grid_c
       const int acc = i % p.acc_stages;
       mbar_wait(tfull_bar(acc), ((uint32_t)(i / p.acc_stages)) & 1u);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t)(acc * p.n_tile) + lane_base;
+      const uint32_t tacc = tmem_base + (uint32_t)(acc * p.ksplit * p.n_tile) + lane_base;
       const bool store_ok = !PATCH || (ty0 + 4 * q < p.hm);  // warp-uniform: a patch-mode box entirely below the image is not issued
       if (cb >= ce) {  // this warp owns no columns of so narrow a tile: hand the accumulator back at once
         tc_fence_before();
@@ -574,9 +609,15 @@ static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilog
     p.cpg = y->c / e->gn_groups;
     if (p.cpg != 4 && p.cpg != 8 && p.cpg != 16) return 0;
   }
-  p.acc_stages = (2 * p.n_tile <= 512) ? 2 : 1;
+  {
+    static int ks_env = -1;
+    if (ks_env < 0) ks_env = v2_env("YAD_CONV2_KSPLIT", 1);
+    p.ksplit = 1;
+    if (patch && (ks_env == 2 || ks_env == 4) && 2 * ks_env * p.n_tile <= 512) p.ksplit = ks_env;
+  }
+  p.acc_stages = (2 * p.ksplit * p.n_tile <= 512) ? 2 : 1;
   p.tmem_cols = 32;
-  while (p.tmem_cols < p.acc_stages * p.n_tile) p.tmem_cols <<= 1;
+  while (p.tmem_cols < p.acc_stages * p.ksplit * p.n_tile) p.tmem_cols <<= 1;
   static int ew_env = -1;
   if (ew_env < 0) ew_env = v2_env("YAD_CONV2_EW", 0);
   auto set_ew = [&](int ew) {

@@ -4,7 +4,9 @@ Each class keeps the reference's constructor signature, attribute names and stat
 name and reference checkpoints load), but holds parameters only: `forward` hands NHWC views to libyad.so through functional.py.  There is no
 PyTorch arithmetic on the forward path and no CPU fallback.  Paths in docstrings are relative to /root/reference/ultralytics.
 
-Inference only in this round: a training-mode forward through these modules raises (the backward kernels of SURVEY section 8 row a15 are not built).
+Training: the reference calls `model(batch)` with the batch dict in training mode (engine/trainer.py:382-384); plugin.install() routes that call to
+bridge.TrainBridge, which runs the libyad training graph (training.py) on these modules' parameters and returns a loss whose backward fills their
+.grad.  A training-mode forward of a single module on a TENSOR has no libyad autograd node and raises.
 """
 import math
 
@@ -44,7 +46,9 @@ class YadModule(nn.Module):
     """Base: lazily prepares kernel-layout weights from the module's own state dict (prefix 'm.')."""
 
     def _ctx(self, x):
-        key = (x.dtype, x.device)
+        # the prepared (BN-folded, packed) weights are keyed by dtype, device AND the in-place version counters of every parameter / buffer, so an
+        # optimizer step, an EMA copy_ or model.fuse() can never leave inference running on stale weights
+        key = (x.dtype, x.device, sum(t._version for t in self.parameters()) + sum(t._version for t in self.buffers()))
         if getattr(self, "_yad_key", None) != key:
             sd = {"m." + k: v for k, v in self.state_dict().items()}
             self._yad_ctx = Fn.Ctx(prepare(sd, x.dtype, x.device))
@@ -61,8 +65,8 @@ class YadModule(nn.Module):
 
     def _check_eval(self):
         if self.training:
-            raise NotImplementedError("training-mode forward/backward through libyad.so is not built yet (SURVEY.md section 8 row a15); "
-                                      "call .eval() for inference")
+            raise NotImplementedError("a training-mode forward of one libyad module on a tensor has no autograd node: train through model(batch) "
+                                      "(plugin.install() binds DetectionModel.loss to bridge.TrainBridge) or TrainEngine; call .eval() for inference")
 
 
 # ---------------------------------------------------------------------------------------------------------------------------

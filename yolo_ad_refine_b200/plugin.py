@@ -6,11 +6,18 @@ through libyad.so without touching the reference's source.
     yad.install()                       # before building the model
     model = YOLO("z-yaml/yolo11-701-YOLO-AD-Refine.yaml", task="detect")
     yad.convert_model(model.model)      # swaps the yaml's plain nn.Conv2d / nn.ConvTranspose2d layers for libyad-backed twins
+
+Training keeps the reference's loop as it is (engine/trainer.py:382-397, 580-588: `self.model(batch)`, `.backward()`, clip, optimizer, EMA): install()
+also wraps `DetectionModel.loss` (nn/tasks.py:290-302) so that a training-mode `model(batch)` runs forward + TaskAlignedAssigner + v8DetectionLoss +
+the complete backward in libyad.so (bridge.TrainBridge) and returns a loss tensor whose `.backward()` hands every parameter its gradient.
+`YadDetectionTrainer` (below) is the reference's DetectionTrainer with exactly the two changes a libyad model needs: the yaml's plain torch
+layers are converted after the model is built, and AMP's fp16 autocast / GradScaler is off (activations are bf16 inside the kernels).
 """
 import importlib
 
 import torch.nn as nn
 
+from . import bridge as ybridge
 from . import loss as yloss
 from . import modules as M
 from . import postprocess as ypost
@@ -56,7 +63,36 @@ def install(ultralytics_pkg="ultralytics"):
     bind("utils.loss", "v8DetectionLoss", yloss.v8DetectionLoss)
     bind("utils.loss", "TaskAlignedAssigner", ytal.TaskAlignedAssigner)   # utils/loss.py:379
     bind("utils.tal", "TaskAlignedAssigner", ytal.TaskAlignedAssigner)
+    try:  # training-mode model(batch) -> libyad forward + loss + backward (bridge.py)
+        tasks = importlib.import_module(f"{ultralytics_pkg}.nn.tasks")
+        if not getattr(tasks.DetectionModel.loss, "_yad_wrapped", False):
+            tasks.DetectionModel.loss = ybridge.model_loss(tasks.DetectionModel.loss)
+            done.append("nn.tasks.DetectionModel.loss")
+    except Exception:
+        pass
     return done
+
+
+def make_trainer_class(ultralytics_pkg="ultralytics"):
+    """The reference's DetectionTrainer (models/yolo/detect/train.py) for a libyad-backed model: same data pipeline, loop, optimizer, EMA,
+    validation and checkpoints; get_model() converts the yaml's plain torch layers and AMP is forced off (bf16 lives inside the kernels, there is
+    no fp16 autocast to scale for).  Usage: `make_trainer_class()(overrides=dict(model=yaml, data=..., epochs=...)).train()` or
+    `YOLO(yaml).train(trainer=make_trainer_class(), ...)`."""
+    install(ultralytics_pkg)
+    det = importlib.import_module(f"{ultralytics_pkg}.models.yolo.detect")
+
+    class YadDetectionTrainer(det.DetectionTrainer):
+        def __init__(self, cfg=None, overrides=None, _callbacks=None):
+            overrides = dict(overrides or {})
+            overrides["amp"] = False
+            kw = {} if cfg is None else {"cfg": cfg}
+            super().__init__(overrides=overrides, _callbacks=_callbacks, **kw)
+
+        def get_model(self, cfg=None, weights=None, verbose=True):
+            model = super().get_model(cfg=cfg, weights=weights, verbose=verbose)
+            return convert_model(model)
+
+    return YadDetectionTrainer
 
 
 def convert_model(model):
