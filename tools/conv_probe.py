@@ -22,7 +22,7 @@ y = Act.empty(n, ho, ho, cw.cout, dt, dev)
 flops = 2.0 * n * ho * ho * cw.cout * k * k * cin
 byts = 2.0 * (x.buf.numel() + y.buf.numel() + cw.w.numel())
 deform = os.environ.get("DEFORM") == "1"
-om = Act(torch.randn(n, hw, hw, 32, device=dev).to(dt)) if deform else None
+om = Act((torch.randn(n, hw, hw, 32, device=dev) * float(os.environ.get("DEFORM_STD", "1.0"))).to(dt)) if deform else None
 mode = ops.CONV_DEFORM if deform else ops.CONV_NORMAL
 for impl in impls:
     for _ in range(3):

@@ -25,11 +25,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
 
-__global__ void __launch_bounds__(128, 1) bench(int M, int N, int nacc, int iters, int a_sbo, long long* out) {
+__global__ void __launch_bounds__(128, 1) bench(int M, int N, int nacc, int iters, int a_sbo, long long* out, int mode) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* p0 = smem_raw + (base - smem_u32(smem_raw));
-  for (int i = threadIdx.x; i < (64 + 48) * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(p0)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < (64 + 100) * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(p0)[i] = make_uint4(0, 0, 0, 0);
   __shared__ uint64_t bar;
   __shared__ uint32_t tptr;
   const int warp = threadIdx.x >> 5;
@@ -52,13 +52,28 @@ __global__ void __launch_bounds__(128, 1) bench(int M, int N, int nacc, int iter
     const uint32_t a_hi = ((uint32_t)a_sbo >> 4) | (1u << 14) | (2u << 29), b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t a_lo = ((base & 0x3FFFFu) >> 4) | (1u << 16), b_lo = (((base + 64 * 1024) & 0x3FFFFu) >> 4) | (1u << 16);
     long long t0 = clock64();
-    for (int i = 0; i < iters; i++) {
-      const uint32_t d = tmem + (uint32_t)((i % nacc) * N);
-      if (leader) {
-        umma(d, pack64(a_lo, a_hi), pack64(b_lo, b_hi), idesc);
-        umma(d, pack64(a_lo + 2, a_hi), pack64(b_lo + 2, b_hi), idesc);
-        umma(d, pack64(a_lo + 4, a_hi), pack64(b_lo + 4, b_hi), idesc);
-        umma(d, pack64(a_lo + 6, a_hi), pack64(b_lo + 6, b_hi), idesc);
+    if (mode == 0) {
+      for (int i = 0; i < iters; i++) {
+        const uint32_t d = tmem + (uint32_t)((i % nacc) * N);
+        if (leader) {
+          umma(d, pack64(a_lo, a_hi), pack64(b_lo, b_hi), idesc);
+          umma(d, pack64(a_lo + 2, a_hi), pack64(b_lo + 2, b_hi), idesc);
+          umma(d, pack64(a_lo + 4, a_hi), pack64(b_lo + 4, b_hi), idesc);
+          umma(d, pack64(a_lo + 6, a_hi), pack64(b_lo + 6, b_hi), idesc);
+        }
+      }
+    } else {
+      // conv-like: tap t reads A shifted by ((t / 3) * 10 + t % 3) pixel rows of 128 B and its own 8 KB weight chunk (mode 2: same weight chunk)
+      for (int i = 0; i < iters; i++) {
+        const int t = i % 9;
+        const uint32_t d = tmem + (uint32_t)((i % nacc) * N);
+        const uint32_t al = a_lo + (uint32_t)((t / 3) * 10 + t % 3) * 8u, bl = b_lo + (mode == 1 ? (uint32_t)t * (uint32_t)(N * 8) : 0u);
+        if (leader) {
+          umma(d, pack64(al, a_hi), pack64(bl, b_hi), idesc);
+          umma(d, pack64(al + 2, a_hi), pack64(bl + 2, b_hi), idesc);
+          umma(d, pack64(al + 4, a_hi), pack64(bl + 4, b_hi), idesc);
+          umma(d, pack64(al + 6, a_hi), pack64(bl + 6, b_hi), idesc);
+        }
       }
     }
     if (leader) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
@@ -77,14 +92,14 @@ __global__ void __launch_bounds__(128, 1) bench(int M, int N, int nacc, int iter
 int main() {
   long long* out;
   cudaMalloc(&out, 8);
-  cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+  cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024);
   const int iters = 2000;
   struct { int M, N, nacc, sbo; } cfg[] = {{128, 64, 1, 1024}, {128, 64, 2, 1024}, {128, 64, 4, 1024}, {128, 64, 1, 1280}, {128, 128, 1, 1024}, {128, 128, 2, 1024},
                                            {128, 256, 1, 1024}, {128, 256, 2, 1024}, {128, 32, 1, 1024}, {128, 16, 1, 1024}, {64, 64, 1, 1024}, {64, 128, 1, 1024},
                                            {64, 256, 1, 1024}, {64, 256, 2, 1024}, {64, 160, 1, 1024}, {128, 160, 1, 1024}, {128, 192, 1, 1024}};
   for (auto& c : cfg) {
     for (int grid : {1, 148}) {
-      bench<<<grid, 128, 120 * 1024>>>(c.M, c.N, c.nacc, iters, c.sbo, out);
+      bench<<<grid, 128, 180 * 1024>>>(c.M, c.N, c.nacc, iters, c.sbo, out, 0);
       cudaError_t e = cudaDeviceSynchronize();
       long long cyc = 0;
       cudaMemcpy(&cyc, out, 8, cudaMemcpyDeviceToHost);
@@ -93,5 +108,13 @@ int main() {
              (double)c.M * c.N * 16 / per, cudaGetErrorString(e));
     }
   }
+  for (int mode : {1, 2})
+    for (int sbo : {1024, 1280}) {
+      bench<<<148, 128, 180 * 1024>>>(128, 64, 1, iters, sbo, out, mode);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long cyc = 0;
+      cudaMemcpy(&cyc, out, 8, cudaMemcpyDeviceToHost);
+      printf("{\"conv_like_mode\": %d, \"M\": 128, \"N\": 64, \"a_sbo\": %d, \"cycles_per_mma\": %.1f, \"err\": \"%s\"}\n", mode, sbo, (double)cyc / (iters * 4.0), cudaGetErrorString(e));
+    }
   return 0;
 }

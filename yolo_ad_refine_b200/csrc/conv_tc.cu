@@ -805,6 +805,7 @@ int pick_n_tile(int cout);
 }  // namespace
 int yad_conv2d_v2_supported(const yad_tensor* x, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y);
 int yad_conv2d_v2(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream);
+int yad_conv2d_dcn_v2(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream);
 namespace {
 
 // best (bw, bh) with bw * bh <= 128 for an (h, w) map: maximise useful pixels per 128-row MMA tile
@@ -1052,6 +1053,10 @@ int yad_conv2d_tc(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
     // impl 4: the resident-weight kernel of conv_v2.cu (error when the shape is not eligible); 5: conv_tma_kernel (the round-1 TMA kernel, A/B runs)
     if (d->mode == YAD_CONV_NORMAL && d->impl != 3 && d->impl != 5 && !p.bn_stats && yad_conv2d_v2_supported(x, d, e, y))
       return yad_conv2d_v2(x, w, d, e, y, stream);
+    if (d->mode == YAD_CONV_DEFORM && d->impl != 3 && d->impl != 5 && !p.bn_stats) {  // fused shared-memory gather kernel (conv_v2.cu)
+      const int r = yad_conv2d_dcn_v2(x, w, d, e, y, stream);
+      if (r >= 0) return r;
+    }
     YAD_CHECK(d->impl != 4, "conv2d: impl 4 (resident-weight tcgen05 kernel) does not support this shape / epilogue");
     if (d->impl != 3 && tma_supported(x, d, y)) return launch_tma(p, d, st);
     if (p.bn_stats) {  // batch statistics are fused on the TMA-fed kernel only: thread-gathered kernel first, stand-alone statistics after it

@@ -46,9 +46,11 @@ struct V2Params {
   int kpt, ntaps, pw;       // 64-wide K chunks per tap; taps; patch pitch in pixels
   int tap_row[9];           // patch row (= pixel index inside the patch) the A descriptor of tap t starts at
   int stages, acc_stages, tmem_cols;
+  int dbg;                  // bring-up / profiling switch (YAD_CONV2_DBG): 1 = the MMA lane issues nothing, 2 = the epilogue skips its TMEM reads and math (results are garbage)
   int ksplit;               // 3x3: taps are dealt round-robin to `ksplit` accumulators (independent tcgen05.mma dependency chains), summed in the epilogue
   uint32_t off_b, b_chunk_bytes, off_a, a_stage_bytes, a_tx_bytes, off_stg, stg_warp_bytes, off_bias, off_bars;
-  int sc, ew;               // columns per TMA store box (16 / 32 / 64); epilogue warps (8 / 16)
+  int sc, ew, stg_bufs;     // columns per TMA store box (16 / 32 / 64); epilogue warps (8 / 16); staging tiles per warp (2: the bulk store of piece i
+                            // is still reading its tile while piece i + 1 is staged)
   int bnd[5];               // column ranges [bnd[w], bnd[w + 1]) of the ew / 4 warps that share a TMEM lane quarter
   const float* bias;
   const float* img_scale;
@@ -217,8 +219,11 @@ __device__ __forceinline__ void epi_unit(const V2Params& p, uint32_t taddr, uint
       else gn_unit<U, 16>(p, v, valid, lane, img, uniform, co);
     }
   }
-  if (first) {
-    if (elect_one()) tma_store_wait_read();  // same lane that issued (and committed) the previous bulk store of this warp
+  if (first) {  // the staging tile about to be overwritten: its last bulk store (one or two pieces ago) must have finished reading it
+    if (elect_one()) {  // the same lane issues, commits and waits
+      if (p.stg_bufs == 2) tma_store_wait_read1();
+      else tma_store_wait_read();
+    }
     __syncwarp();
   }
 #pragma unroll
@@ -228,6 +233,143 @@ __device__ __forceinline__ void epi_unit(const V2Params& p, uint32_t taddr, uint
 #pragma unroll
     for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
     sts16v(row_addr + ((((uint32_t)(cell0 + j)) ^ ph) << 4), u);
+  }
+}
+
+// The epilogue of one warp over all tiles of its CTA (shared by conv2_kernel and dcn2_kernel): TMEM -> scale / bias / activation (-> GroupNorm
+// partial sums) -> bf16 -> swizzled staging tile -> optional mul / add on the staged tile -> bulk tensor store.  tfull0 / tempty0: shared-memory
+// addresses of the accumulator-full / accumulator-empty mbarrier pairs.
+template <bool PATCH, int ACT, bool MULADD, bool GN, bool SCALE>
+__device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap* tmY, uint32_t base, uint32_t tmem_base, int warp, int lane, uint32_t tfull0,
+                                            uint32_t tempty0) {
+  const int per_img = p.tiles_x * p.tiles_y;
+  {
+    // ================= epilogue: 8 or 16 warps, TMEM lane quarter = warp & 3, the 2 / 4 warps of a quarter split the columns =================
+    const int q = warp & 3, ew = warp - 2, way = ew >> 2;
+    const int cb = p.bnd[way], ce = p.bnd[way + 1];
+    const uint32_t stg0 = base + p.off_stg + (uint32_t)(ew * p.stg_bufs) * p.stg_warp_bytes;
+    const uint32_t RB = 2u * (uint32_t)p.sc, swz = (RB >> 4) - 1u;
+    const uint32_t ph = (((uint32_t)lane * RB) >> 7) & swz;  // every staging tile starts on its swizzle period
+    uint32_t piece = 0;
+    const uint32_t bias_s = base + p.off_bias;
+    const uint32_t lane_base = ((uint32_t)(q * 32)) << 16;
+    // phase-2 geometry (mul / add on the staged piece): cpr lanes sweep one row
+    const int cpr = p.sc >> 3, rpp = 32 / cpr, rr0 = lane / cpr, cj = lane - rr0 * cpr;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, i++) {
+      const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n, n0 = nt * p.n_tile;
+      int img = 0, ty0 = 0, tx0 = 0, m_base = 0;
+      bool valid, uniform = true;
+      int dp = 0;
+      if (PATCH) {
+        img = mt / per_img;
+        const int r = mt - img * per_img;
+        ty0 = (r / p.tiles_x) * V2_BH;
+        tx0 = (r % p.tiles_x) * V2_BW;
+        const int oy = ty0 + 4 * q + (lane >> 3), ox = tx0 + (lane & 7);
+        valid = oy < p.hm && ox < p.wm;
+        dp = (img * p.hm + oy) * p.wm + ox;
+      } else {
+        m_base = mt * V2_BM + 32 * q;
+        dp = m_base + lane;
+        valid = dp < p.m_total;
+        if (GN || SCALE) {
+          const int img0 = m_base / p.hw, rem = m_base - img0 * p.hw;
+          uniform = rem + 32 <= p.hw;
+          img = img0 + ((rem + lane >= p.hw) ? 1 : 0);
+        }
+      }
+      float rsc = 1.0f;
+      if constexpr (SCALE) {
+        if (valid) {
+          if (p.img_scale) rsc = p.img_scale[img];
+          if (p.pix_scale) rsc *= __bfloat162float(p.pix_scale[(int64_t)dp * p.pix_scale_ld]);
+        }
+      }
+      const int acc = i % p.acc_stages;
+      mbar_wait((tfull0 + 8u * (uint32_t)acc), ((uint32_t)(i / p.acc_stages)) & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(acc * p.ksplit * p.n_tile) + lane_base;
+      const bool store_ok = !PATCH || (ty0 + 4 * q < p.hm);  // warp-uniform: a patch-mode box entirely below the image is not issued
+      if (cb >= ce) {  // this warp owns no columns of so narrow a tile: hand the accumulator back at once
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive((tempty0 + 8u * (uint32_t)acc));
+      }
+      for (int c0 = cb; c0 < ce; c0 += p.sc, piece++) {
+        const uint32_t stg = stg0 + (piece & (uint32_t)(p.stg_bufs - 1)) * p.stg_warp_bytes;
+        const uint32_t row_addr = stg + (uint32_t)lane * RB;
+        if (p.dbg & 2) {
+        } else if (p.sc >= 32) {
+          for (int u0 = 0; u0 < p.sc; u0 += 32)
+            epi_unit<32, ACT, GN, SCALE>(p, tacc + (uint32_t)(c0 + u0), bias_s + 4u * (uint32_t)(n0 + c0 + u0), rsc, row_addr, ph, u0 >> 3, u0 == 0, lane,
+                                         valid, img, uniform, n0 + c0 + u0);
+        } else {
+          epi_unit<16, ACT, GN, SCALE>(p, tacc + (uint32_t)c0, bias_s + 4u * (uint32_t)(n0 + c0), rsc, row_addr, ph, 0, true, lane, valid, img, uniform,
+                                       n0 + c0);
+        }
+        if (c0 + p.sc >= ce) {  // last TMEM read of this tile by this warp: hand the accumulator back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive((tempty0 + 8u * (uint32_t)acc));
+        }
+        if constexpr (MULADD) {
+          if (p.mul || p.add) {
+            __syncwarp();
+            const int co = n0 + c0 + cj * 8;
+            if (co < p.cout) {
+#pragma unroll 2
+              for (int row = rr0; row < 32; row += rpp) {
+                int64_t d;
+                bool ok;
+                if (PATCH) {
+                  const int oy = ty0 + 4 * q + (row >> 3), ox = tx0 + (row & 7);
+                  ok = oy < p.hm && ox < p.wm;
+                  d = (int64_t)(img * p.hm + oy) * p.wm + ox;
+                } else {
+                  d = (int64_t)m_base + row;
+                  ok = d < p.m_total;
+                }
+                if (!ok) continue;
+                const uint32_t ra = stg + (uint32_t)row * RB;
+                const uint32_t ca = ra + ((((uint32_t)cj) ^ ((ra >> 7) & swz)) << 4);
+                uint4 u = lds16(ca);
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+                if (p.mul && p.add) {
+                  const uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.mul + d * p.mul_ld + co));
+                  const uint4 av = __ldg(reinterpret_cast<const uint4*>(p.add + d * p.add_ld + co));
+                  const __nv_bfloat162* hm = reinterpret_cast<const __nv_bfloat162*>(&mv);
+                  const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&av);
+#pragma unroll
+                  for (int e = 0; e < 4; e++) h[e] = __hfma2(h[e], hm[e], ha[e]);
+                } else if (p.mul) {
+                  const uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.mul + d * p.mul_ld + co));
+                  const __nv_bfloat162* hm = reinterpret_cast<const __nv_bfloat162*>(&mv);
+#pragma unroll
+                  for (int e = 0; e < 4; e++) h[e] = __hmul2(h[e], hm[e]);
+                } else {
+                  const uint4 av = __ldg(reinterpret_cast<const uint4*>(p.add + d * p.add_ld + co));
+                  const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&av);
+#pragma unroll
+                  for (int e = 0; e < 4; e++) h[e] = __hadd2(h[e], ha[e]);
+                }
+                sts16v(ca, u);
+              }
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (store_ok) {  // warp-uniform
+          if (elect_one()) {
+            if (PATCH) tma_store_4d(tmY, stg, n0 + c0, tx0, ty0 + 4 * q, img);
+            else tma_store_2d(tmY, stg, n0 + c0, m_base);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (elect_one()) tma_store_wait_read();  // shared memory must outlive the last bulk store's read
   }
 }
 
@@ -313,7 +455,8 @@ __global__ void __launch_bounds__(V2_MAX_THREADS, 1) conv2_kernel(const __grid_c
     // per tcgen05.mma and was THE limiter of the 3x3 convolutions; the warp-uniform loop still spent ~120 instructions per tap on index
     // arithmetic.  Now the tap / K-step loops are fully unrolled with compile-time offsets: two 32-bit adds per MMA.
     {
-      const bool leader = elect_one();
+      const bool leader_lane = elect_one();
+      const bool leader = leader_lane && !(p.dbg & 1);
       const uint32_t idesc = v2_idesc(p.n_tile);
       const uint32_t a_hi = v2_desc_hi(PATCH ? (uint32_t)p.pw * 128u : 1024u), b_hi = v2_desc_hi(1024u);
       const uint32_t b_lo0 = v2_desc_lo(base + p.off_b), b_step = p.b_chunk_bytes >> 4;
@@ -379,137 +522,240 @@ __global__ void __launch_bounds__(V2_MAX_THREADS, 1) conv2_kernel(const __grid_c
               }
             }
           }
-          if (leader) umma_commit(empty_bar(s));
+          if (leader_lane) umma_commit(empty_bar(s));
         }
-        if (leader) umma_commit(tfull_bar(acc));
+        if (leader_lane) umma_commit(tfull_bar(acc));
       }
     }
     __syncwarp();
     tc_fence_before();
   } else {
-    // ================= epilogue: 8 or 16 warps, TMEM lane quarter = warp & 3, the 2 / 4 warps of a quarter split the columns =================
-    const int q = warp & 3, ew = warp - 2, way = ew >> 2;
-    const int cb = p.bnd[way], ce = p.bnd[way + 1];
-    const uint32_t stg = base + p.off_stg + (uint32_t)ew * p.stg_warp_bytes;
-    const uint32_t RB = 2u * (uint32_t)p.sc, swz = (RB >> 4) - 1u;
-    const uint32_t row_addr = stg + (uint32_t)lane * RB;
-    const uint32_t ph = (row_addr >> 7) & swz;
-    const uint32_t bias_s = base + p.off_bias;
-    const uint32_t lane_base = ((uint32_t)(q * 32)) << 16;
-    // phase-2 geometry (mul / add on the staged piece): cpr lanes sweep one row
-    const int cpr = p.sc >> 3, rpp = 32 / cpr, rr0 = lane / cpr, cj = lane - rr0 * cpr;
+    // ================= epilogue warps =================
+    v2_epilogue<PATCH, ACT, MULADD, GN, SCALE>(p, &tmY, base, tmem_base, warp, lane, tfull_bar(0), tempty_bar(0));
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// =====================================================================================================================
+// Modulated deformable 3x3 convolution (DCNv2; mmcv ModulatedDeformConv2d of DyDCNv2, nn/modules/head.py:751-782), 64 input channels.
+// conv_tc_kernel<DEFORM> gathered the four bilinear corners of every (pixel, tap) from global memory (4 x 9 x 128 B per pixel): 370 us at
+// 80x80, batch 64, bound by L1 / L2 gather traffic.  Here the M tile is the 8 x 16 pixel rectangle of the 3x3 path and
+//   warp 0        : TMA -- the tile's input patch with a halo of R pixels (one 4-D box, zero fill = the operator's zero padding) and the tile's
+//                   offset / mask channels (one box) per tile, double-buffered;
+//   warps 10-17   : sampling parameters of the 128 x 9 (pixel, tap) pairs (floor, bilinear weights x sigmoid(mask), position inside the patch)
+//                   once per tile, then per tap the blended A tile: 4 conflict-free 128-bit SHARED-memory reads per 8 channels, packed bf16x2
+//                   blend (same arithmetic as before), swizzled store into a 2-slot A ring (a corner outside the staged halo falls back to
+//                   global loads);
+//   warp 1        : 4 tcgen05.mma per tap against the resident weights, accumulator double-buffered in TMEM;
+//   warps 2-9     : the conv_v2 epilogue (GroupNorm statistics, bf16, bulk tensor store).
+// Shared-memory traffic (gather reads 590 KB + A writes / MMA reads 300 KB per tile) is the bound: ~90 us at 80x80.
+// =====================================================================================================================
+constexpr int DCN_GW = 8;            // gather warps
+constexpr int DCN_TAPS = 9;
+struct DcnParams {
+  V2Params v;
+  int R, pwr, phr;                   // halo radius, raw patch width / height in pixels
+  int aslots;
+  uint32_t off_raw, raw_stage_bytes, raw_tx_bytes, om_off, off_aslot, off_par;
+  const bf16* x;
+  int x_ld;
+};
+struct DcnSample {                   // 16 bytes per (tap, pixel)
+  int pos;                           // row index of the top-left corner inside the raw patch, or -1: outside the staged halo
+  int yx;                            // (y0 << 16) | (x0 & 0xffff) in image coordinates (fallback path)
+  uint32_t w01, w23;                 // bilinear weights x mask as bf16 pairs: (w00, w01), (w10, w11)
+};
+
+template <int ACT, bool GN>
+__global__ void __launch_bounds__(V2_MAX_THREADS, 1) dcn2_kernel(const __grid_constant__ DcnParams dp, const __grid_constant__ CUtensorMap tmX,
+                                                                 const __grid_constant__ CUtensorMap tmOM, const __grid_constant__ CUtensorMap tmB,
+                                                                 const __grid_constant__ CUtensorMap tmY) {
+  extern __shared__ uint8_t smem_raw[];
+  const V2Params& p = dp.v;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + p.off_bars;
+  // barrier slots: rawfull[2] rawempty[2] afull[4] aempty[4] tfull[2] tempty[2] b[9]
+  auto rawfull = [&](int i) { return bars + 8u * (uint32_t)i; };
+  auto rawempty = [&](int i) { return bars + 8u * (uint32_t)(2 + i); };
+  auto afull = [&](int i) { return bars + 8u * (uint32_t)(4 + i); };
+  auto aempty = [&](int i) { return bars + 8u * (uint32_t)(8 + i); };
+  auto tfull_bar = [&](int i) { return bars + 8u * (uint32_t)(12 + i); };
+  auto tempty_bar = [&](int i) { return bars + 8u * (uint32_t)(14 + i); };
+  auto b_bar = [&](int i) { return bars + 8u * (uint32_t)(16 + i); };
+  const uint32_t tmem_ptr_addr = bars + 8u * 25u;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int per_img = p.tiles_x * p.tiles_y;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; i++) { mbar_init(rawfull(i), 1); mbar_init(rawempty(i), DCN_GW); mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), (uint32_t)p.ew); }
+    for (int i = 0; i < 4; i++) { mbar_init(afull(i), DCN_GW); mbar_init(aempty(i), 1); }
+    for (int i = 0; i < DCN_TAPS; i++) mbar_init(b_bar(i), 1);
+    fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOM) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  pdl_sync();
+  {
+    float* bs = reinterpret_cast<float*>(smem_raw + (base + p.off_bias - raw));
+    for (int i = tid; i < p.n_tile; i += (int)blockDim.x) bs[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    const bool leader = elect_one();
+    for (int t = 0; t < DCN_TAPS; t++) {
+      if (leader) {
+        mbar_expect_tx(b_bar(t), p.b_chunk_bytes);
+        tma_load_2d(base + p.off_b + (uint32_t)t * p.b_chunk_bytes, &tmB, b_bar(t), t * 64, 0);
+      }
+    }
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+      const int img = tile / per_img, r = tile - img * per_img;
+      const int ty0 = (r / p.tiles_x) * V2_BH, tx0 = (r % p.tiles_x) * V2_BW;
+      const int rs = it & 1;
+      const uint32_t dst = base + dp.off_raw + (uint32_t)rs * dp.raw_stage_bytes;
+      mbar_wait(rawempty(rs), ((it >> 1) & 1u) ^ 1u);
+      if (leader) {
+        mbar_expect_tx(rawfull(rs), dp.raw_tx_bytes);
+        tma_load_4d(dst, &tmX, rawfull(rs), 0, tx0 - dp.R, ty0 - dp.R, img);
+        tma_load_4d(dst + dp.om_off, &tmOM, rawfull(rs), 0, tx0, ty0, img);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const bool leader = elect_one();
+    const uint32_t idesc = v2_idesc(p.n_tile);
+    const uint32_t hi = v2_desc_hi(1024u);
+    const uint32_t b_lo0 = v2_desc_lo(base + p.off_b), b_step = p.b_chunk_bytes >> 4;
+    uint32_t git = 0;
     int i = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, i++) {
-      const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n, n0 = nt * p.n_tile;
-      int img = 0, ty0 = 0, tx0 = 0, m_base = 0;
-      bool valid, uniform = true;
-      int dp = 0;
-      if (PATCH) {
-        img = mt / per_img;
-        const int r = mt - img * per_img;
-        ty0 = (r / p.tiles_x) * V2_BH;
-        tx0 = (r % p.tiles_x) * V2_BW;
-        const int oy = ty0 + 4 * q + (lane >> 3), ox = tx0 + (lane & 7);
-        valid = oy < p.hm && ox < p.wm;
-        dp = (img * p.hm + oy) * p.wm + ox;
-      } else {
-        m_base = mt * V2_BM + 32 * q;
-        dp = m_base + lane;
-        valid = dp < p.m_total;
-        if (GN || SCALE) {
-          const int img0 = m_base / p.hw, rem = m_base - img0 * p.hw;
-          uniform = rem + 32 <= p.hw;
-          img = img0 + ((rem + lane >= p.hw) ? 1 : 0);
-        }
-      }
-      float rsc = 1.0f;
-      if constexpr (SCALE) {
-        if (valid) {
-          if (p.img_scale) rsc = p.img_scale[img];
-          if (p.pix_scale) rsc *= __bfloat162float(p.pix_scale[(int64_t)dp * p.pix_scale_ld]);
-        }
-      }
-      const int acc = i % p.acc_stages;
-      mbar_wait(tfull_bar(acc), ((uint32_t)(i / p.acc_stages)) & 1u);
+      const int acc = i & 1;
+      mbar_wait(tempty_bar(acc), (((uint32_t)(i >> 1)) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t)(acc * p.ksplit * p.n_tile) + lane_base;
-      const bool store_ok = !PATCH || (ty0 + 4 * q < p.hm);  // warp-uniform: a patch-mode box entirely below the image is not issued
-      if (cb >= ce) {  // this warp owns no columns of so narrow a tile: hand the accumulator back at once
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
+      for (int t = 0; t < DCN_TAPS; t++, git++) {
+        const int s = (int)(git % (uint32_t)dp.aslots);
+        if (i == 0) { mbar_wait(b_bar(t), 0u); }
+        mbar_wait(afull(s), (git / (uint32_t)dp.aslots) & 1u);
+        tc_fence_after();
+        const uint32_t a_lo = v2_desc_lo(base + dp.off_aslot + (uint32_t)s * 16384u), b_lo = b_lo0 + (uint32_t)t * b_step;
+        if (leader) {
+          umma_f16(d_tmem, pack64(a_lo, hi), pack64(b_lo, hi), idesc, t > 0 ? 1u : 0u);
+          umma_bf16<true>(d_tmem, pack64(a_lo + 2u, hi), pack64(b_lo + 2u, hi), idesc);
+          umma_bf16<true>(d_tmem, pack64(a_lo + 4u, hi), pack64(b_lo + 4u, hi), idesc);
+          umma_bf16<true>(d_tmem, pack64(a_lo + 6u, hi), pack64(b_lo + 6u, hi), idesc);
+          umma_commit(aempty(s));
+        }
       }
-      for (int c0 = cb; c0 < ce; c0 += p.sc) {
-        if (p.sc >= 32) {
-          for (int u0 = 0; u0 < p.sc; u0 += 32)
-            epi_unit<32, ACT, GN, SCALE>(p, tacc + (uint32_t)(c0 + u0), bias_s + 4u * (uint32_t)(n0 + c0 + u0), rsc, row_addr, ph, u0 >> 3, u0 == 0, lane,
-                                         valid, img, uniform, n0 + c0 + u0);
-        } else {
-          epi_unit<16, ACT, GN, SCALE>(p, tacc + (uint32_t)c0, bias_s + 4u * (uint32_t)(n0 + c0), rsc, row_addr, ph, 0, true, lane, valid, img, uniform,
-                                       n0 + c0);
-        }
-        if (c0 + p.sc >= ce) {  // last TMEM read of this tile by this warp: hand the accumulator back before the stores
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
-        }
-        if constexpr (MULADD) {
-          if (p.mul || p.add) {
-            __syncwarp();
-            const int co = n0 + c0 + cj * 8;
-            if (co < p.cout) {
-#pragma unroll 2
-              for (int row = rr0; row < 32; row += rpp) {
-                int64_t d;
-                bool ok;
-                if (PATCH) {
-                  const int oy = ty0 + 4 * q + (row >> 3), ox = tx0 + (row & 7);
-                  ok = oy < p.hm && ox < p.wm;
-                  d = (int64_t)(img * p.hm + oy) * p.wm + ox;
-                } else {
-                  d = (int64_t)m_base + row;
-                  ok = d < p.m_total;
-                }
-                if (!ok) continue;
-                const uint32_t ra = stg + (uint32_t)row * RB;
-                const uint32_t ca = ra + ((((uint32_t)cj) ^ ((ra >> 7) & swz)) << 4);
-                uint4 u = lds16(ca);
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-                if (p.mul && p.add) {
-                  const uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.mul + d * p.mul_ld + co));
-                  const uint4 av = __ldg(reinterpret_cast<const uint4*>(p.add + d * p.add_ld + co));
-                  const __nv_bfloat162* hm = reinterpret_cast<const __nv_bfloat162*>(&mv);
-                  const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&av);
-#pragma unroll
-                  for (int e = 0; e < 4; e++) h[e] = __hfma2(h[e], hm[e], ha[e]);
-                } else if (p.mul) {
-                  const uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.mul + d * p.mul_ld + co));
-                  const __nv_bfloat162* hm = reinterpret_cast<const __nv_bfloat162*>(&mv);
-#pragma unroll
-                  for (int e = 0; e < 4; e++) h[e] = __hmul2(h[e], hm[e]);
-                } else {
-                  const uint4 av = __ldg(reinterpret_cast<const uint4*>(p.add + d * p.add_ld + co));
-                  const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&av);
-#pragma unroll
-                  for (int e = 0; e < 4; e++) h[e] = __hadd2(h[e], ha[e]);
-                }
-                sts16v(ca, u);
-              }
-            }
+      if (leader) umma_commit(tfull_bar(acc));
+    }
+    __syncwarp();
+    tc_fence_before();
+  } else if (warp < 2 + p.ew) {
+    v2_epilogue<true, ACT, false, GN, false>(p, &tmY, base, tmem_base, warp, lane, tfull_bar(0), tempty_bar(0));
+  } else {
+    // ================= gather warps =================
+    const int gtid = tid - 32 * (2 + p.ew);                // 0 .. 255
+    const int gc = gtid & 7, grow = gtid >> 3;             // 16-byte channel chunk; pixel row inside a pass of 32 pixels
+    DcnSample* par = reinterpret_cast<DcnSample*>(smem_raw + (base + dp.off_par - raw));
+    const int hi_ = p.hm, wi_ = p.wm;
+    uint32_t it = 0, git = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+      const int img = tile / per_img, r = tile - img * per_img;
+      const int ty0 = (r / p.tiles_x) * V2_BH, tx0 = (r % p.tiles_x) * V2_BW;
+      const int rs = it & 1;
+      const uint32_t xs = base + dp.off_raw + (uint32_t)rs * dp.raw_stage_bytes;
+      const bf16* oms = reinterpret_cast<const bf16*>(smem_raw + (xs + dp.om_off - raw));
+      mbar_wait(rawfull(rs), (it >> 1) & 1u);
+      asm volatile("bar.sync 2, 256;" ::: "memory");       // every gather warp is done with the previous tile's parameters
+      // ---- sampling parameters: [tap][pixel]
+      for (int idx = gtid; idx < DCN_TAPS * V2_BM; idx += 32 * DCN_GW) {
+        const int t = idx >> 7, pix = idx & 127;
+        const int py = ty0 + (pix >> 3), px = tx0 + (pix & 7);
+        DcnSample sm;
+        sm.pos = 0; sm.yx = 0; sm.w01 = 0u; sm.w23 = 0u;
+        if (py < hi_ && px < wi_) {
+          const bf16* o = oms + pix * 32;
+          const float ody = __bfloat162float(o[2 * t]), odx = __bfloat162float(o[2 * t + 1]);
+          const float mk = sigmoidf_(__bfloat162float(o[18 + t]));
+          const float fy_ = (float)(py + t / 3 - 1) + ody, fx_ = (float)(px + t % 3 - 1) + odx;
+          if (fy_ > -1.f && fx_ > -1.f && fy_ < (float)hi_ && fx_ < (float)wi_) {
+            const float fy = floorf(fy_), fx = floorf(fx_);
+            const int y0 = (int)fy, x0 = (int)fx;
+            const float ly = fy_ - fy, lx = fx_ - fx;
+            const bool vy0 = y0 >= 0, vy1 = y0 + 1 < hi_, vx0 = x0 >= 0, vx1 = x0 + 1 < wi_;
+            const float w00 = (vy0 && vx0) ? (1.f - ly) * (1.f - lx) * mk : 0.f, w01 = (vy0 && vx1) ? (1.f - ly) * lx * mk : 0.f;
+            const float w10 = (vy1 && vx0) ? ly * (1.f - lx) * mk : 0.f, w11 = (vy1 && vx1) ? ly * lx * mk : 0.f;
+            __nv_bfloat162 a = __floats2bfloat162_rn(w00, w01), b = __floats2bfloat162_rn(w10, w11);
+            sm.w01 = *reinterpret_cast<uint32_t*>(&a);
+            sm.w23 = *reinterpret_cast<uint32_t*>(&b);
+            sm.yx = (y0 << 16) | (x0 & 0xFFFF);
+            const int ry = y0 - (ty0 - dp.R), rx = x0 - (tx0 - dp.R);
+            sm.pos = (ry >= 0 && ry + 1 < dp.phr && rx >= 0 && rx + 1 < dp.pwr) ? ry * dp.pwr + rx : -1;
           }
+        }
+        par[idx] = sm;
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      // ---- per tap: blended A tile
+      for (int t = 0; t < DCN_TAPS; t++, git++) {
+        const int s = (int)(git % (uint32_t)dp.aslots);
+        const uint32_t a_s = base + dp.off_aslot + (uint32_t)s * 16384u;
+        mbar_wait(aempty(s), ((git / (uint32_t)dp.aslots) & 1u) ^ 1u);
+#pragma unroll
+        for (int pass = 0; pass < 4; pass++) {
+          const int pix = pass * 32 + grow;
+          const DcnSample sm = par[t * V2_BM + pix];
+          uint4 u00, u01, u10, u11;
+          if (sm.pos >= 0) {
+            const uint32_t r00 = (uint32_t)sm.pos, r10 = r00 + (uint32_t)dp.pwr;
+            u00 = lds16(xs + r00 * 128u + ((((uint32_t)gc) ^ (r00 & 7u)) << 4));
+            u01 = lds16(xs + (r00 + 1u) * 128u + ((((uint32_t)gc) ^ ((r00 + 1u) & 7u)) << 4));
+            u10 = lds16(xs + r10 * 128u + ((((uint32_t)gc) ^ (r10 & 7u)) << 4));
+            u11 = lds16(xs + (r10 + 1u) * 128u + ((((uint32_t)gc) ^ ((r10 + 1u) & 7u)) << 4));
+          } else {  // a corner outside the staged halo (large learned offsets): global loads, corners clamped into the map (invalid ones have weight 0)
+            const int y0 = sm.yx >> 16, x0 = (int)(short)(sm.yx & 0xFFFF);
+            const int ya = max(y0, 0), yb = min(y0 + 1, hi_ - 1), xa = max(x0, 0), xb = min(x0 + 1, wi_ - 1);
+            const bf16* xb_ = dp.x + (int64_t)img * hi_ * wi_ * dp.x_ld + gc * 8;
+            u00 = __ldg(reinterpret_cast<const uint4*>(xb_ + (int64_t)(ya * wi_ + xa) * dp.x_ld));
+            u01 = __ldg(reinterpret_cast<const uint4*>(xb_ + (int64_t)(ya * wi_ + xb) * dp.x_ld));
+            u10 = __ldg(reinterpret_cast<const uint4*>(xb_ + (int64_t)(yb * wi_ + xa) * dp.x_ld));
+            u11 = __ldg(reinterpret_cast<const uint4*>(xb_ + (int64_t)(yb * wi_ + xb) * dp.x_ld));
+          }
+          const __nv_bfloat162 wa = *reinterpret_cast<const __nv_bfloat162*>(&sm.w01), wb = *reinterpret_cast<const __nv_bfloat162*>(&sm.w23);
+          const __nv_bfloat162 w00 = __low2bfloat162(wa), w01 = __high2bfloat162(wa), w10 = __low2bfloat162(wb), w11 = __high2bfloat162(wb);
+          const __nv_bfloat162* h00 = reinterpret_cast<const __nv_bfloat162*>(&u00);
+          const __nv_bfloat162* h01 = reinterpret_cast<const __nv_bfloat162*>(&u01);
+          const __nv_bfloat162* h10 = reinterpret_cast<const __nv_bfloat162*>(&u10);
+          const __nv_bfloat162* h11 = reinterpret_cast<const __nv_bfloat162*>(&u11);
+          uint4 res;
+          __nv_bfloat162* hr = reinterpret_cast<__nv_bfloat162*>(&res);
+#pragma unroll
+          for (int e = 0; e < 4; e++) hr[e] = __hfma2(w11, h11[e], __hfma2(w10, h10[e], __hfma2(w01, h01[e], __hmul2(w00, h00[e]))));
+          sts16v(a_s + (uint32_t)pix * 128u + ((((uint32_t)gc) ^ ((uint32_t)pix & 7u)) << 4), res);
         }
         fence_proxy_async();
         __syncwarp();
-        if (store_ok) {  // warp-uniform
-          if (elect_one()) {
-            if (PATCH) tma_store_4d(&tmY, stg, n0 + c0, tx0, ty0 + 4 * q, img);
-            else tma_store_2d(&tmY, stg, n0 + c0, m_base);
-            tma_store_commit();
-          }
-        }
+        if (lane == 0) mbar_arrive(afull(s));
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rawempty(rs));
     }
-    if (elect_one()) tma_store_wait_read();  // shared memory must outlive the last bulk store's read
   }
   __syncthreads();
   if (warp == 1) {
@@ -615,6 +861,11 @@ static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilog
     p.ksplit = 1;
     if (patch && (ks_env == 2 || ks_env == 4) && 2 * ks_env * p.n_tile <= 512) p.ksplit = ks_env;
   }
+  {
+    static int dbg_env = -1;
+    if (dbg_env < 0) dbg_env = v2_env("YAD_CONV2_DBG", 0);
+    p.dbg = dbg_env;
+  }
   p.acc_stages = (2 * p.ksplit * p.n_tile <= 512) ? 2 : 1;
   p.tmem_cols = 32;
   while (p.tmem_cols < p.acc_stages * p.ksplit * p.n_tile) p.tmem_cols <<= 1;
@@ -655,13 +906,19 @@ static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilog
   const uint32_t max_stages = patch ? 4u : 8u, min_stages = patch ? 2u : 3u;
   uint32_t stages = 0, stg_total = 0;
   auto total = [&](uint32_t s) { return b_total + s * p.a_stage_bytes + stg_total + bias_bytes + 8u * (2u * s + 4u + V2_MAX_BCHUNKS) + 16u; };
-  for (int attempt = 0; attempt < 2; attempt++) {  // 16 epilogue warps need twice the staging: fall back to 8 when the pipeline would starve
-    p.stg_warp_bytes = 32u * (uint32_t)p.sc * 2u;  // 1024 / 2048 / 4096: every warp's staging tile starts on its swizzle period
-    stg_total = (uint32_t)p.ew * p.stg_warp_bytes;
+  // preference order: (epilogue warps as chosen, 2 staging tiles) > (same, 1 tile) > (8 warps, 2 tiles) > (8 warps, 1 tile), each only if the
+  // activation ring keeps min_stages
+  for (int attempt = 0; attempt < 4; attempt++) {
+    p.stg_bufs = (attempt & 1) ? 1 : 2;
+    if (attempt == 2) {
+      if (p.ew == 8) break;
+      set_ew(8);
+    }
+    p.stg_warp_bytes = 32u * (uint32_t)p.sc * 2u;  // 1024 / 2048 / 4096: every staging tile starts on its swizzle period
+    stg_total = (uint32_t)(p.ew * p.stg_bufs) * p.stg_warp_bytes;
     stages = max_stages;
     while (stages >= 2 && total(stages) > budget) stages--;
-    if (stages >= min_stages || p.ew == 8) break;
-    set_ew(8);
+    if (stages >= min_stages) break;
   }
   if (stages < 2) return 0;
   p.stages = (int)stages;
@@ -737,4 +994,108 @@ int yad_conv2d_v2(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
   int grid = num_sms < p.total_tiles ? num_sms : p.total_tiles;
   if (patch) return v2_dispatch<true>(p, tmA, tmB, tmY, grid, smem, st);
   return v2_dispatch<false>(p, tmA, tmB, tmY, grid, smem, st);
+}
+
+// Fused deformable 3x3 convolution (dcn2_kernel).  Returns -1 when the call is not eligible (the caller falls back to conv_tc_kernel<DEFORM>).
+int yad_conv2d_dcn_v2(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream) {
+  static int on = -1;
+  if (on < 0) on = v2_env("YAD_DCN_V2", 1);
+  if (!on || !get_encode()) return -1;
+  if (d->mode != YAD_CONV_DEFORM || x->c != 64 || (x->ld % 8) || (y->c % 8) || (y->ld % 8) || y->c > 256 || !d->offmask || (d->offmask_ld % 8)) return -1;
+  if (((uintptr_t)x->ptr & 15) || ((uintptr_t)y->ptr & 15) || ((uintptr_t)d->offmask & 15)) return -1;
+  if (e->mul || e->add || e->img_scale || e->pix_scale || (e->gn_stats && e->gn_groups == 0)) return -1;
+  const int64_t M = (int64_t)x->n * x->h * x->w;
+  if (M + V2_BM >= (int64_t)1 << 31) return -1;
+  DcnParams dp;
+  memset(&dp, 0, sizeof(dp));
+  V2Params& p = dp.v;
+  p.n = x->n; p.hm = y->h; p.wm = y->w; p.hw = y->h * y->w; p.cin = 64; p.cout = y->c; p.m_total = (int)M;
+  p.n_tile = pick_n_tile_v2(p.cout);
+  p.tiles_n = 1; p.ntaps = 9; p.kpt = 1; p.ksplit = 1; p.acc_stages = 2;
+  if (e->gn_stats) {
+    if (e->gn_groups <= 0 || y->c % e->gn_groups) return -1;
+    p.cpg = y->c / e->gn_groups;
+    if (p.cpg != 4 && p.cpg != 8 && p.cpg != 16) return -1;
+  }
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 2 * p.n_tile) p.tmem_cols <<= 1;
+  p.ew = 8; p.stg_bufs = 1;
+  {
+    const int u16 = p.n_tile / 16;
+    p.bnd[0] = 0; p.bnd[1] = 16 * ((u16 + 1) / 2);
+    for (int i = 2; i <= 4; i++) p.bnd[i] = p.n_tile;
+    int sc = 64;
+    for (int wv = 0; wv < 2; wv++)
+      while (sc > 16 && ((p.bnd[wv + 1] - p.bnd[wv]) % sc)) sc >>= 1;
+    p.sc = sc;
+  }
+  p.tiles_x = (p.wm + V2_BW - 1) / V2_BW;
+  p.tiles_y = (p.hm + V2_BH - 1) / V2_BH;
+  p.total_tiles = p.n * p.tiles_x * p.tiles_y;
+  p.b_chunk_bytes = (uint32_t)p.n_tile * 128u;
+  p.stg_warp_bytes = 32u * (uint32_t)p.sc * 2u;
+  const uint32_t b_total = 9u * p.b_chunk_bytes, stg_total = 8u * p.stg_warp_bytes, bias_bytes = ((uint32_t)p.n_tile * 4u + 127u) & ~127u;
+  const uint32_t par_bytes = 9u * V2_BM * 16u, budget = 227u * 1024u - 1024u;
+  bool fits = false;
+  for (int R = 2; R >= 1 && !fits; R--)
+    for (int as = 2; as >= 2 && !fits; as--) {
+      dp.R = R; dp.pwr = V2_BW + 2 * R; dp.phr = V2_BH + 2 * R; dp.aslots = as;
+      dp.om_off = ((uint32_t)(dp.pwr * dp.phr) * 128u + 1023u) & ~1023u;
+      dp.raw_stage_bytes = dp.om_off + 8192u;
+      fits = b_total + 2u * dp.raw_stage_bytes + (uint32_t)as * 16384u + par_bytes + stg_total + bias_bytes + 8u * 26u + 16u <= budget;
+    }
+  if (!fits) return -1;
+  dp.raw_tx_bytes = (uint32_t)(dp.pwr * dp.phr) * 128u + 8192u;
+  p.off_b = 0;
+  dp.off_raw = b_total;
+  dp.off_aslot = dp.off_raw + 2u * dp.raw_stage_bytes;
+  dp.off_par = dp.off_aslot + (uint32_t)dp.aslots * 16384u;
+  p.off_stg = dp.off_par + par_bytes;
+  p.off_bias = p.off_stg + stg_total;
+  p.off_bars = p.off_bias + bias_bytes;
+  const size_t smem = 1024 + (size_t)p.off_bars + 8 * 26 + 16;
+  p.bias = e->bias; p.act = e->act; p.alpha = e->alpha;
+  p.gn_stats = e->gn_stats; p.gn_groups = e->gn_groups;
+  dp.x = (const bf16*)x->ptr; dp.x_ld = x->ld;
+  CUtensorMap tmX, tmOM, tmB, tmY;
+  {
+    uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
+    uint64_t strides[3] = {(uint64_t)x->ld * 2, (uint64_t)x->w * x->ld * 2, (uint64_t)x->h * x->w * x->ld * 2};
+    uint32_t box[4] = {64, (uint32_t)dp.pwr, (uint32_t)dp.phr, 1};
+    if (v2_make_map(&tmX, x->ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {  // offsets / mask logits: 32 channels of the (n, h, w, >= 27) view (channels beyond the view are zero-filled), dense rows of 64 bytes
+    uint64_t dims[4] = {(uint64_t)32, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
+    uint64_t strides[3] = {(uint64_t)d->offmask_ld * 2, (uint64_t)x->w * d->offmask_ld * 2, (uint64_t)x->h * x->w * d->offmask_ld * 2};
+    uint32_t box[4] = {32, V2_BW, V2_BH, 1};
+    if (v2_make_map(&tmOM, d->offmask, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  }
+  {
+    const int cout_rows = (y->c + 7) / 8 * 8;
+    uint64_t dims[2] = {(uint64_t)(9 * 64), (uint64_t)cout_rows}, strides[1] = {(uint64_t)(9 * 64) * 2};
+    uint32_t box[2] = {64, (uint32_t)p.n_tile};
+    if (v2_make_map(&tmB, w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  {
+    const CUtensorMapSwizzle sw = p.sc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.sc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    uint64_t dims[4] = {(uint64_t)y->c, (uint64_t)y->w, (uint64_t)y->h, (uint64_t)y->n};
+    uint64_t strides[3] = {(uint64_t)y->ld * 2, (uint64_t)y->w * y->ld * 2, (uint64_t)y->h * y->w * y->ld * 2};
+    uint32_t box[4] = {(uint32_t)p.sc, V2_BW, 4, 1};
+    if (v2_make_map(&tmY, y->ptr, 4, dims, strides, box, sw)) return 1;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaFuncSetAttribute(dcn2_kernel<ACT_GENERIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      yad_set_error("conv2d (deformable, fused): cannot raise the dynamic shared memory limit");
+      num_sms = 0;
+      return 2;
+    }
+  }
+  const int grid = num_sms < p.total_tiles ? num_sms : p.total_tiles;
+  YAD_LAUNCH((dcn2_kernel<ACT_GENERIC, true>), grid, 32 * (2 + 8 + DCN_GW), smem, (cudaStream_t)stream, dp, tmX, tmOM, tmB, tmY);
+  YAD_LAUNCH_CHECK("conv2d (deformable, fused)");
+  return 0;
 }
