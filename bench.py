@@ -138,24 +138,25 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def measure_training(args, world, rank, sd, dtype, W, barrier):
+def measure_training(args, world, rank, sd, dtype, W, barrier, B=None, scaling="weak"):
     """BASELINE.json configs[3]: one training step (train()-mode forward + TaskAlignedAssigner + v8DetectionLoss + full backward + gradient
-    all-reduce over NCCL when N > 1 + clip / SGD / EMA), `train_batch` images per GPU (weak scaling).  Device-timed, max over ranks.  The e2e
-    figure adds, per step, the H2D copy of the pinned uint8 image batch + targets and the D2H read of the loss items."""
+    all-reduce over NCCL when N > 1 + clip / SGD / EMA), B images per GPU.  The step is a captured CUDA graph (TrainEngine.capture): one graph at
+    N = 1; forward + backward | NCCL all-reduce | optimizer at N > 1.  Device-timed, max over ranks.  The e2e figure adds, per step, the H2D copy
+    of the pinned uint8 image batch + targets (prefetched on a copy stream under the previous step) and the D2H read of the loss items."""
     from yolo_ad_refine_b200 import ops, parallel, synth
     from yolo_ad_refine_b200.trainer import TrainEngine
-    B = args.train_batch
+    B = B or args.train_batch
     eng = TrainEngine(sd, dtype=dtype, world_size=world)
     # uint8 images, as the reference's dataloader delivers them (the /255 happens on the device: models/yolo/detect/train.py:57-59)
     rs = np.random.RandomState(200 + rank)
     img_host = torch.from_numpy(rs.randint(0, 256, (B, 3, args.imgsz, args.imgsz), dtype=np.uint8)).pin_memory()
-    tg_host = [torch.from_numpy(a).pin_memory() for a in synth.make_targets(B, seed=300 + rank, max_per_img=8, empty_images=())]
-    img = img_host.cuda()
-    tg = [t.cuda() for t in tg_host]
+    tg_host = [torch.from_numpy(a).float().pin_memory() for a in synth.make_targets(B, seed=300 + rank, max_per_img=8, empty_images=())]
     loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
     l0 = ops.LAUNCHES
-    eng.step(img, *tg)
-    launches = ops.LAUNCHES - l0
+    eng.capture(B, args.imgsz, m_cap=8 * B, n_max=8)
+    launches = (ops.LAUNCHES - l0) // 3  # two warm-up passes + the captured one
+    eng.load_static(img_host, *tg_host)
+    torch.cuda.synchronize()
 
     def timed(fn, k):
         for _ in range(max(W, 3)):
@@ -169,21 +170,67 @@ def measure_training(args, world, rank, sd, dtype, W, barrier):
         barrier()
         return parallel.max_over_ranks(s.elapsed_time(e), device="cuda") / k
 
-    ms = timed(lambda: eng.step(img, *tg), args.train_steps)
+    ms = timed(lambda: eng.step_graphed(), args.train_steps)
+
+    # end to end: pinned host batch -> (copy stream) staging -> static inputs -> step -> loss items on the host, every step
+    copy_stream = torch.cuda.Stream()
+    stage = [(torch.empty_like(eng._s_img), [torch.empty(t.shape, dtype=torch.float32, device="cuda") for t in tg_host]) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    free = [torch.cuda.Event(), torch.cuda.Event()]
+    main = torch.cuda.current_stream()
+    for ev in free:
+        ev.record(main)
+    state = {"i": 0, "primed": False}
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[i % 2])
+            stage[i % 2][0].copy_(img_host, non_blocking=True)
+            for d, h in zip(stage[i % 2][1], tg_host):
+                d.copy_(h, non_blocking=True)
+            ready[i % 2].record(copy_stream)
 
     def e2e_step():
-        d_img = img_host.to("cuda", non_blocking=True)
-        d_tg = [t.to("cuda", non_blocking=True) for t in tg_host]
-        out4 = eng.step(d_img, *d_tg)
+        i = state["i"]
+        if not state["primed"]:
+            prefetch(i)
+            state["primed"] = True
+        prefetch(i + 1)                        # the next batch's H2D runs under this step
+        main.wait_event(ready[i % 2])
+        out4 = eng.step_graphed(stage[i % 2][0], *stage[i % 2][1])
+        free[i % 2].record(main)
         loss_host.copy_(out4, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        main.synchronize()                     # the trainer formats the loss items every iteration
+        state["i"] = i + 1
 
     e2e_ms = timed(e2e_step, args.train_steps)
-    # roofline of the training step's dominant kernels, measured live: one instrumented step, CUDA events around every libyad entry point
+    # where the step goes at N > 1 (CUDA events on this rank, a few steps): compute graph | all-reduce (wire + waiting for the slowest rank) | optimizer
+    decomp = None
+    if world > 1:
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(4)]
+        barrier()
+        for k in range(4):
+            eng.tp.set_hyper(lr=eng.lr, momentum=eng.momentum, weight_decay=eng.weight_decay, optimizer=eng.optimizer)
+            evs[k][0].record()
+            eng._gA.replay()
+            evs[k][1].record()
+            eng.exchange()
+            evs[k][2].record()
+            eng._gB.replay()
+            evs[k][3].record()
+        torch.cuda.synchronize()
+        decomp = {"compute_ms": float(np.mean([e[0].elapsed_time(e[1]) for e in evs[1:]])),
+                  "allreduce_ms": float(np.mean([e[1].elapsed_time(e[2]) for e in evs[1:]])),
+                  "optimizer_ms": float(np.mean([e[2].elapsed_time(e[3]) for e in evs[1:]])),
+                  "note": "rank 0; all-reduce = NCCL wire time + waiting for the slowest rank's backward; BatchNorm buffers are not exchanged per step "
+                          "(train-mode BatchNorm does not read them; rank 0's are the ones checkpointed)"}
+    # roofline of the training step's dominant kernels, measured live: one instrumented EAGER step, CUDA events around every libyad entry point
     torch.cuda.synchronize()
+    img, tg = eng._s_img, (eng._s_bi, eng._s_cls, eng._s_box)
     ops.PROFILE = {}
-    torch.cuda._sleep(int(200e6))  # keep the host ahead of the device (see the inference profile above): ~100 ms of queued spin
-    eng.step(img, *tg)
+    torch.cuda._sleep(int(200e6))  # keep the host ahead of the device (see the inference profile): ~100 ms of queued spin
+    eng.forward_backward(img, *tg, static_n_max=8)
+    eng.tp.optimizer_step_dev(eng.optimizer)
     torch.cuda.synchronize()
     prof = {k: (sum(a.elapsed_time(b) for a, b, _ in v), sum(m["flops"] for _, _, m in v if m), len(v)) for k, v in ops.PROFILE.items()}
     ops.PROFILE = None
@@ -191,19 +238,23 @@ def measure_training(args, world, rank, sd, dtype, W, barrier):
     pk = peaks()
     roof = {}
     for key, label in (("yad_conv_wgrad", "weight gradients: wgrad_tc_kernel (tcgen05 / TMEM, TMA-fed MN-major operands) + small-channel / split-K mma.sync kernels"),
-                       ("yad_conv2d", "forward convolutions + input gradients: conv_tma_kernel / conv_tc_kernel / conv_small_kernel")):
+                       ("yad_conv2d", "forward convolutions + input gradients: conv2_kernel / conv_tma_kernel / conv_tc_kernel / conv_small_kernel")):
         ms_k, fl, n = prof[key]
         roof[key] = {"kernel": label, "bound": "tensor", "achieved": fl / (ms_k / 1000.0) / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                      "frac": fl / (ms_k / 1000.0) / 1e12 / pk["tf_sustained"], "launches": n, "ms": ms_k, "share_of_step": ms_k / tot_ms,
                      "traffic": None, "note": "most launches are HBM-bound (1x1 wgrad reads 5.6 TB/s = 86 % of the measured HBM peak, profiles/r1_ncu_wgrad_tc.json)"}
     out = {"metric": "train img/s (forward + loss + backward + optimizer)", "value": world * B / (ms / 1000.0), "unit": "img/s",
            "ms_per_step": ms, "batch_per_gpu": B, "global_batch": world * B, "steps": args.train_steps, "launches_per_step": launches,
-           "scaling": "weak", "exchange": "none (1 GPU)" if world == 1 else f"NCCL all-reduce of the {eng.tp.total * 4 / 1e6:.1f} MB fp32 gradient arena",
+           "scaling": scaling, "graph": "one CUDA graph per step" if world == 1 else "graph(forward+backward) | NCCL all-reduce | graph(optimizer)",
+           "exchange": "none (1 GPU)" if world == 1 else f"NCCL all-reduce (SUM) of the {eng.tp.total * 4 / 1e6:.1f} MB fp32 gradient arena",
            "e2e": {"value": world * B / (e2e_ms / 1000.0), "unit": "img/s", "ms_per_step": e2e_ms,
-                   "h2d_bytes_per_step": img_host.numel() + sum(t.numel() * 4 for t in tg_host), "d2h_bytes_per_step": 16},
+                   "h2d_bytes_per_step": img_host.numel() + sum(t.numel() * 4 for t in tg_host), "d2h_bytes_per_step": 16,
+                   "h2d": "prefetched on a copy stream under the previous step (double-buffered staging)"},
            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "loss": [float(v) for v in loss_host], "roofline": roof,
            "profile_ms": {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:12]}}
-    del eng
+    if decomp:
+        out["decomposition"] = decomp
+    del eng, stage
     torch.cuda.empty_cache()
     return out
 
@@ -327,15 +378,25 @@ def main():
     if args.profile_json and rank == 0:
         json.dump({"eager_ms": eager_ms, "graph_ms_per_step": ms_per_step, "entries": prof}, open(args.profile_json, "w"), indent=1)
 
-    train = measure_training(args, world, rank, sd, dtype, W, barrier) if args.train_batch > 0 else None
+    launches_per_step = eng.launches_per_step
+    train = train_strong = None
+    if args.train_batch > 0:
+        del eng  # the inference engine's graphs and buffers are not needed any more
+        torch.cuda.empty_cache()
+        train = measure_training(args, world, rank, sd, dtype, W, barrier)
+        if world > 1 and args.train_batch % world == 0:
+            # BASELINE.json configs[3] as the reference runs it: GLOBAL batch 128 split over the ranks (engine/trainer.py:290) -- strong scaling
+            train_strong = measure_training(args, world, rank, sd, dtype, W, barrier, B=args.train_batch // world, scaling="strong")
 
     line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": make_config(args, world),
-            "e2e": e2e, "gpu_launches": eng.launches_per_step * args.steps, "launches_per_step": eng.launches_per_step,
+            "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "clocks": clk.summary(), "roofline": roofline}
     if train is not None:
         line["train"] = train
+    if train_strong is not None:
+        line["train_strong"] = train_strong
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             sec, cores, kind = cpu_steps(args.ref_batch, args.imgsz, 4, 1)

@@ -384,6 +384,15 @@ int yad_sgd_step(float* params, const float* grads, float* momentum_buf, const u
 int yad_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const uint8_t* group, int64_t n, const float* lr3_host,
                    const float* wd3_host, float beta1, float beta2, float eps, int step, float max_norm, const double* norm_sq, void* stream);
 int yad_ema_update(float* ema, const float* params, int64_t n, float decay, void* stream);
+/* The same optimizer / EMA steps with every per-step scalar read from DEVICE memory, so that ONE captured CUDA graph serves a whole run (the
+ * reference changes lr every iteration during warm-up, engine/trainer.py:363-378; Adam's bias correction and ModelEMA's decay ramp,
+ * utils/torch_utils.py:531-533, change every step).  hyper_dev: float[13] = lr[3] | weight_decay[3] | momentum or beta1 | beta2 | eps |
+ * 1 - beta1^t | sqrt(1 - beta2^t) | max_norm | ema decay.  The momentum arena must start at zero (then the first SGD step equals torch's). */
+int yad_sgd_step_dev(float* params, const float* grads, float* momentum_buf, const uint8_t* group, int64_t n, const float* hyper_dev,
+                     const double* norm_sq, void* stream);
+int yad_adamw_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const uint8_t* group, int64_t n,
+                       const float* hyper_dev, const double* norm_sq, void* stream);
+int yad_ema_update_dev(float* ema, const float* params, int64_t n, const float* decay_dev, void* stream);
 
 
 /* -- tcgen05 self-test: C[M][N] (fp32) = A[M][K] (bf16, row-major) x B[N][K]^T (bf16) through the UMMA/TMEM path.  Used by the GPU

@@ -122,6 +122,9 @@ SIGNATURES = {
     "yad_sgd_step": (i32, [vp, vp, vp, vp, i64, C.POINTER(f32), C.POINTER(f32), f32, f32, vp, i32, vp]),
     "yad_adamw_step": (i32, [vp, vp, vp, vp, vp, i64, C.POINTER(f32), C.POINTER(f32), f32, f32, f32, i32, f32, vp, vp]),
     "yad_ema_update": (i32, [vp, vp, i64, f32, vp]),
+    "yad_sgd_step_dev": (i32, [vp, vp, vp, vp, i64, vp, vp, vp]),
+    "yad_adamw_step_dev": (i32, [vp, vp, vp, vp, vp, i64, vp, vp, vp]),
+    "yad_ema_update_dev": (i32, [vp, vp, i64, vp, vp]),
 }
 
 _lib = None

@@ -101,6 +101,58 @@ __global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ p,
     ema[i] = d * ema[i] + (1.0f - d) * p[i];
 }
 
+// ---- the same three kernels with every per-step scalar read from DEVICE memory, so that one captured CUDA graph serves all steps of a run
+// (learning-rate warm-up, Adam bias correction and the EMA decay ramp change from step to step).  hyper[13] = lr0 lr1 lr2 | wd0 wd1 wd2 |
+// momentum or beta1 | beta2 | eps | 1 - beta1^t | sqrt(1 - beta2^t) | max_norm | ema decay
+__global__ void sgd_step_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, const uint8_t* __restrict__ group,
+                                    int64_t n, const float* __restrict__ hyper, const double* __restrict__ norm_sq) {
+  pdl_sync();
+  const float lr0 = hyper[0], lr1 = hyper[1], lr2 = hyper[2], wd0 = hyper[3], wd1 = hyper[4], wd2 = hyper[5], momentum = hyper[6], max_norm = hyper[11];
+  float coef = 1.0f;
+  if (max_norm > 0.f && norm_sq) {
+    const float nrm = (float)sqrt(*norm_sq);
+    coef = fminf(max_norm / (nrm + 1e-6f), 1.0f);
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int gr = group[i];
+    if (gr > 2) continue;  // frozen
+    const float lr = gr == 0 ? lr0 : (gr == 1 ? lr1 : lr2), wd = gr == 0 ? wd0 : (gr == 1 ? wd1 : wd2);
+    const float w = p[i];
+    float d = g[i] * coef + wd * w;
+    const float b = momentum * mom[i] + d;  // the momentum arena starts at zero: the first step's buffer is d, as torch.optim.SGD initialises it
+    mom[i] = b;
+    d = d + momentum * b;
+    p[i] = w - lr * d;
+  }
+}
+__global__ void adamw_step_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                      const uint8_t* __restrict__ group, int64_t n, const float* __restrict__ hyper, const double* __restrict__ norm_sq) {
+  pdl_sync();
+  const float lr0 = hyper[0], lr1 = hyper[1], lr2 = hyper[2], wd0 = hyper[3], wd1 = hyper[4], wd2 = hyper[5], beta1 = hyper[6], beta2 = hyper[7],
+              eps = hyper[8], bc1 = hyper[9], bc2_sqrt = hyper[10], max_norm = hyper[11];
+  float coef = 1.0f;
+  if (max_norm > 0.f && norm_sq) {
+    const float nrm = (float)sqrt(*norm_sq);
+    coef = fminf(max_norm / (nrm + 1e-6f), 1.0f);
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int gr = group[i];
+    if (gr > 2) continue;
+    const float lr = gr == 0 ? lr0 : (gr == 1 ? lr1 : lr2), wd = gr == 0 ? wd0 : (gr == 1 ? wd1 : wd2);
+    const float gi = g[i] * coef;
+    float w = p[i] * (1.0f - lr * wd);
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi, vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] = w - (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+__global__ void ema_dev_kernel(float* __restrict__ ema, const float* __restrict__ p, int64_t n, const float* __restrict__ d_dev) {
+  pdl_sync();
+  const float d = *d_dev;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    ema[i] = d * ema[i] + (1.0f - d) * p[i];
+}
+
 int blocks_for(int64_t n) {
   int64_t g = (n + 255) / 256;
   return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
@@ -153,6 +205,26 @@ int yad_adamw_step(float* params, const float* grads, float* exp_avg, float* exp
                                                                       wd3_host[0], wd3_host[1], wd3_host[2], beta1, beta2, eps, bc1, bc2_sqrt, max_norm,
                                                                       norm_sq);
   YAD_LAUNCH_CHECK("adamw_step");
+  return 0;
+}
+
+int yad_sgd_step_dev(float* params, const float* grads, float* momentum_buf, const uint8_t* group, int64_t n, const float* hyper_dev, const double* norm_sq,
+                     void* stream) {
+  YAD_LAUNCH(sgd_step_dev_kernel, blocks_for(n), 256, 0, (cudaStream_t)stream, params, grads, momentum_buf, group, n, hyper_dev, norm_sq);
+  YAD_LAUNCH_CHECK("sgd_step_dev");
+  return 0;
+}
+
+int yad_adamw_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const uint8_t* group, int64_t n, const float* hyper_dev,
+                       const double* norm_sq, void* stream) {
+  YAD_LAUNCH(adamw_step_dev_kernel, blocks_for(n), 256, 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, group, n, hyper_dev, norm_sq);
+  YAD_LAUNCH_CHECK("adamw_step_dev");
+  return 0;
+}
+
+int yad_ema_update_dev(float* ema, const float* params, int64_t n, const float* decay_dev, void* stream) {
+  YAD_LAUNCH(ema_dev_kernel, blocks_for(n), 256, 0, (cudaStream_t)stream, ema, params, n, decay_dev);
+  YAD_LAUNCH_CHECK("ema_update_dev");
   return 0;
 }
 

@@ -16,6 +16,9 @@ def _p(t):
 
 def preprocess_targets(batch_idx, cls, bboxes, batch_size, imgsz_hw, device):
     """utils/loss.py:392-408 + :443-446 -- host-side ragged -> padded packing of the ground truth (input plumbing, as in the reference)."""
+    n_max_host = None
+    if batch_idx.numel() and not batch_idx.is_cuda:  # the dataloader delivers labels on the host: the padded width costs no device sync
+        n_max_host = int(torch.bincount(batch_idx.reshape(-1).long(), minlength=batch_size).max())
     batch_idx = batch_idx.reshape(-1).to(device)
     cls, bboxes = cls.reshape(-1).to(device).float(), bboxes.reshape(-1, 4).to(device).float()
     if batch_idx.numel() == 0:
@@ -23,7 +26,7 @@ def preprocess_targets(batch_idx, cls, bboxes, batch_size, imgsz_hw, device):
     else:
         bi = batch_idx.long()
         counts = torch.bincount(bi, minlength=batch_size)
-        n_max = int(counts.max())
+        n_max = n_max_host if n_max_host is not None else int(counts.max())
         order = torch.argsort(bi, stable=True)
         start = torch.cumsum(counts, 0) - counts
         rank = torch.arange(bi.numel(), device=device) - start[bi[order]]
@@ -33,6 +36,33 @@ def preprocess_targets(batch_idx, cls, bboxes, batch_size, imgsz_hw, device):
         out[bi[order], rank, 0] = cls[order]
         out[bi[order], rank, 1:3] = xywh[:, :2] - xywh[:, 2:] / 2
         out[bi[order], rank, 3:5] = xywh[:, :2] + xywh[:, 2:] / 2
+    gt_labels, gt_bboxes = out[..., :1].contiguous(), out[..., 1:5].contiguous()
+    mask_gt = (gt_bboxes.sum(2, keepdim=True) > 0).float()
+    return gt_labels, gt_bboxes, mask_gt
+
+
+def pack_targets_static(batch_idx, cls, bboxes, batch_size, imgsz_hw, n_max):
+    """preprocess_targets for a CUDA-graph step: device tensors of FIXED length (padding rows carry batch_idx < 0), fixed n_max, no host
+    synchronisation and no data-dependent shapes.  batch_idx must be non-decreasing over the valid rows, which is how the reference's collate_fn
+    builds it (data/dataset.py:230-246).  Targets beyond n_max per image are dropped (choose n_max from the dataset's label statistics)."""
+    dev = batch_idx.device
+    bi = batch_idx.reshape(-1).long()
+    M = bi.numel()
+    valid = (bi >= 0) & (bi < batch_size)
+    bic = torch.where(valid, bi, torch.full_like(bi, batch_size))
+    counts = torch.zeros(batch_size + 1, dtype=torch.long, device=dev).scatter_add_(0, bic, torch.ones_like(bic))
+    start = torch.cumsum(counts, 0) - counts
+    rank = torch.arange(M, device=dev) - start[bic]
+    ok = valid & (rank < n_max)
+    row = torch.where(ok, bic, torch.full_like(bic, batch_size))       # trash row for padding / overflow
+    col = torch.where(ok, rank, torch.zeros_like(rank))
+    out = torch.zeros(batch_size + 1, n_max, 5, device=dev)
+    h, w = imgsz_hw
+    b = bboxes.reshape(-1, 4).float()
+    cx, cy, bw, bh = b[:, 0] * float(w), b[:, 1] * float(h), b[:, 2] * float(w), b[:, 3] * float(h)  # python scalars: no host tensor during capture
+    vals = torch.stack([cls.reshape(-1).float(), cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)
+    out[row, col] = vals
+    out = out[:batch_size]
     gt_labels, gt_bboxes = out[..., :1].contiguous(), out[..., 1:5].contiguous()
     mask_gt = (gt_bboxes.sum(2, keepdim=True) > 0).float()
     return gt_labels, gt_bboxes, mask_gt

@@ -100,6 +100,11 @@ class TrainParams:
         self._entries, self._packed = [], {}
         self._tables = None
         self.norm_sq = torch.zeros(1, dtype=torch.float64, device=dev)
+        # per-step scalars of the graph-captured optimizer (set_hyper / optimizer_step_dev).  Allocated HERE, never inside a capture: a tensor
+        # created while capturing lives in the graph's pool and its zero-fill would be replayed with every step
+        self._hyper = torch.zeros(16, dtype=torch.float32, device=dev)
+        # a small ring of pinned staging rows: the asynchronous upload of step k may still be pending when the host prepares step k + 1
+        self._hyper_host = torch.zeros(8, 16, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(8, 16)
         self.steps = 0
         self.ema_updates = 0
 
@@ -136,13 +141,27 @@ class TrainParams:
     def checkpoint(self):
         """everything a resumed run needs (the reference's `last.pt` keeps model, EMA, optimizer state and the EMA update count,
         engine/trainer.py:507-540): flat fp32 arenas as CPU tensors + counters; the key / offset table is implied by the state-dict order"""
-        return dict(flat=self.flat.cpu(), mom=self.mom.cpu(), ema=self.ema.cpu(), bufs=self.bufs.cpu(), ema_bufs=self.ema_bufs.cpu(),
-                    steps=self.steps, ema_updates=self.ema_updates, keys=list(self.keys), total=self.total)
+        ck = dict(flat=self.flat.cpu(), mom=self.mom.cpu(), ema=self.ema.cpu(), bufs=self.bufs.cpu(), ema_bufs=self.ema_bufs.cpu(),
+                  steps=self.steps, ema_updates=self.ema_updates, keys=list(self.keys), total=self.total,
+                  other={k: v.cpu() for k, v in self.other.items()}, optimizer=getattr(self, "optimizer_name", None))
+        if hasattr(self, "mom2"):  # AdamW's second moment: without it a resumed run divides by sqrt(~0) on its first steps
+            ck["mom2"] = self.mom2.cpu()
+        return ck
 
     def load_checkpoint(self, ck):
         assert ck["keys"] == self.keys and ck["total"] == self.total, "checkpoint was written for a different parameter layout"
         for name in ("flat", "mom", "ema", "bufs", "ema_bufs"):
             getattr(self, name).copy_(ck[name])
+        if ck.get("mom2") is not None:
+            self.mom2 = ck["mom2"].to(self.device)
+        elif hasattr(self, "mom2"):
+            del self.mom2
+        if ck.get("optimizer") is not None:
+            cur = getattr(self, "optimizer_name", None)
+            assert cur is None or cur == ck["optimizer"], f"checkpoint was written by {ck['optimizer']}, this run uses {cur}"
+            self.optimizer_name = ck["optimizer"]
+        for k, v in (ck.get("other") or {}).items():
+            self.other[k] = v.clone()
         self.steps, self.ema_updates = int(ck["steps"]), int(ck["ema_updates"])
 
     # ---- kernel layouts ---------------------------------------------------------------------------------------------
@@ -284,12 +303,60 @@ class TrainParams:
             if n:
                 ops._call("yad_permute_unpack", C.c_void_p(t.data_ptr()), n, mx, ops._fp(arena), ops._fp(self.grad), ops.stream_ptr())
 
+    def bump_batches_tracked(self):
+        """nn.BatchNorm2d increments num_batches_tracked once per training forward (torch/nn/modules/batchnorm.py); kept so that state_dict()
+        equals the reference's after the same number of steps"""
+        for k in self.other:
+            if k.endswith("num_batches_tracked"):
+                self.other[k] += 1
+
+    # ---- optimizer with device-resident hyper-parameters (CUDA-graph capturable) -----------------------------------------------------
+    def set_hyper(self, lr=0.01, bias_lr=None, momentum=0.937, weight_decay=5e-4, max_norm=10.0, ema_decay=0.9999, ema_tau=2000.0, optimizer="SGD",
+                  beta2=0.999, eps=1e-8):
+        """Advance the step counters and upload this step's scalars (13 floats, pinned -> device, asynchronous): call right before replaying a
+        graph that contains optimizer_step_dev()."""
+        self.steps += 1
+        self.ema_updates += 1
+        t = float(self.steps)
+        d = ema_decay * (1 - math.exp(-self.ema_updates / ema_tau)) if ema_decay > 0 else 1.0
+        vals = [lr, lr, lr if bias_lr is None else bias_lr, weight_decay, 0.0, 0.0, momentum, beta2, eps, 1.0 - momentum ** t,
+                math.sqrt(1.0 - beta2 ** t), max_norm, d]
+        row = self._hyper_host[self.steps % self._hyper_host.shape[0]]
+        row[:13] = torch.tensor(vals, dtype=torch.float32)
+        self._hyper.copy_(row, non_blocking=True)
+        self.optimizer_name = optimizer
+
+    def ensure_adamw_state(self):
+        if not hasattr(self, "mom2"):
+            self.mom2 = torch.zeros_like(self.mom)  # second-moment arena (the first moment reuses the momentum arena)
+
+    def optimizer_step_dev(self, optimizer="SGD"):
+        """clip + optimizer + EMA with all scalars read from the device buffer set_hyper() fills: capturable, replayable"""
+        self.norm_sq.zero_()
+        st = ops.stream_ptr()
+        hp = ops._fp(self._hyper)
+        ops._call("yad_sqnorm", ops._fp(self.grad), self.total, ops._fp(self.norm_sq), st)
+        if optimizer == "SGD":
+            ops._call("yad_sgd_step_dev", ops._fp(self.flat), ops._fp(self.grad), ops._fp(self.mom), C.c_void_p(self.group.data_ptr()), self.total, hp,
+                      ops._fp(self.norm_sq), st)
+        elif optimizer == "AdamW":
+            assert hasattr(self, "mom2"), "AdamW: call ensure_adamw_state() before capturing (state must not be allocated inside a capture)"
+            ops._call("yad_adamw_step_dev", ops._fp(self.flat), ops._fp(self.grad), ops._fp(self.mom), ops._fp(self.mom2),
+                      C.c_void_p(self.group.data_ptr()), self.total, hp, ops._fp(self.norm_sq), st)
+        else:
+            raise NotImplementedError(f"optimizer {optimizer!r}: SGD and AdamW are built")
+        dptr = C.c_void_p(self._hyper.data_ptr() + 12 * 4)
+        ops._call("yad_ema_update_dev", ops._fp(self.ema), ops._fp(self.flat), self.total, dptr, st)
+        if self.btotal:
+            ops._call("yad_ema_update_dev", ops._fp(self.ema_bufs), ops._fp(self.bufs), self.btotal, dptr, st)
+
     # ---- optimizer (engine/trainer.py:580-588) --------------------------------------------------------------------------
     def optimizer_step(self, lr=0.01, bias_lr=None, momentum=0.937, weight_decay=5e-4, max_norm=10.0, ema_decay=0.9999, ema_tau=2000.0,
                        optimizer="SGD", beta2=0.999, eps=1e-8):
         """clip_grad_norm_(max_norm) + the optimizer step over the flat arenas, then ModelEMA.update (parameters and BatchNorm buffers).
         optimizer: "SGD" (nesterov, momentum) or "AdamW" (betas = (momentum, beta2)): the two BaseTrainer.build_optimizer creates for this model
         (engine/trainer.py:773-808)."""
+        self.optimizer_name = optimizer
         self.norm_sq.zero_()
         st = ops.stream_ptr()
         ops._call("yad_sqnorm", ops._fp(self.grad), self.total, ops._fp(self.norm_sq), st)
