@@ -395,6 +395,22 @@ int yad_adamw_step_dev(float* params, const float* grads, float* exp_avg, float*
 int yad_ema_update_dev(float* ema, const float* params, int64_t n, const float* decay_dev, void* stream);
 
 
+/* -- row f4: training-time augmentations on HWC uint8 BGR device images (the reference runs them on the host: data/augment.py).
+ *    yad_hsv_lut : RandomHSV.__call__ (:1345-1378) in place: BGR2HSV -> per-image LUTs (uint8 [n][3][256]: hue, saturation, value; built on the
+ *                  host exactly as the reference builds them) -> HSV2BGR, OpenCV 4.x's 8-bit arithmetic bit for bit (vectorised path).
+ *    yad_flip    : RandomFlip.__call__ (:1429-1472), out of place; flags uint8 [n]: bit 0 = np.flipud, bit 1 = np.fliplr.
+ *    yad_mosaic4 : Mosaic._mosaic4 (:657-713): n_out canvases (2s x 2s, filled with 114), four paste rectangles each. */
+typedef struct {
+  const void* src;          /* HWC uint8 image, row pitch src_w pixels */
+  int32_t src_w;
+  int32_t x1a, y1a, x2a, y2a; /* destination rectangle in the canvas (exclusive max) */
+  int32_t x1b, y1b;           /* top-left corner of the source rectangle */
+  int32_t pad_;
+} yad_mosaic_desc;
+int yad_hsv_lut(void* img_u8_hwc_bgr, int n, int h, int w, const void* luts_dev, void* stream);
+int yad_flip(const void* src, void* dst, int n, int h, int w, const void* flags_dev, void* stream);
+int yad_mosaic4(void* canvas, int s2, int n_out, const yad_mosaic_desc* desc_dev, void* stream);
+
 /* -- tcgen05 self-test: C[M][N] (fp32) = A[M][K] (bf16, row-major) x B[N][K]^T (bf16) through the UMMA/TMEM path.  Used by the GPU
  *    tests to validate descriptor encodings independently of the convolution loader. */
 int yad_tc_gemm_selftest(const void* a, const void* b, float* c, int m, int n, int k, void* stream);

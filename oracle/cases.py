@@ -202,3 +202,14 @@ def val_inputs(n_img, nc, max_det, max_lab, jitter, seed, imgsz=640):
         bidx.append(np.full(m, i))
     return dict(dets=dets, ori_shape=ori, ratio_pad=ratio_pad, bboxes=np.concatenate(bboxes).astype(np.float32),
                 cls=np.concatenate(cls).astype(np.float32), batch_idx=np.concatenate(bidx).astype(np.int64), imgsz=imgsz)
+
+
+# ---- row f4: augmentation cases (oracle/augment.py) --------------------------------------------------------------------------------------
+# name -> (h, w, seed).  Widths are multiples of 64 so that every pixel of a row takes cv2's vectorised HSV2BGR path (see oracle/augment.py).
+AUG_HSV_CASES = {"a": (96, 128, 1), "b": (64, 192, 2), "c": (50, 64, 3), "d": (160, 640, 4)}
+# name -> (s, four (h, w) source shapes, seed): letterboxed-to-s images as the reference's dataset delivers them (long side = s)
+AUG_MOSAIC_CASES = {"s96": (96, [(96, 72), (64, 96), (96, 96), (80, 96)], 11), "s160": (160, [(160, 120), (160, 160), (90, 160), (160, 100)], 12)}
+
+
+def aug_image(h, w, seed):
+    return np.random.RandomState(1000 + seed).randint(0, 256, (h, w, 3)).astype(np.uint8)

@@ -455,7 +455,79 @@ def sfa_state(shapes, seed):
     return f(shapes, seed)
 
 
+def gen_augment():
+    """RandomHSV / RandomFlip / Mosaic._mosaic4 of the live reference (data/augment.py:1301-1378, 1380-1472, 657-713; cv2 of this image) on seeded
+    images and seeded random streams: pins oracle/augment.py and the yad_hsv_lut / yad_flip / yad_mosaic4 kernels.  Also the exhaustive cv2 checks
+    of the restated 8-bit BGR<->HSV arithmetic (all 2^24 colours / all 180 x 256 x 256 HSV triples), recorded as mismatch counts (must be 0)."""
+    import random
+    import zlib
+
+    import cv2
+    from ultralytics.data.augment import Mosaic, RandomFlip, RandomHSV
+    from ultralytics.utils.instance import Instances
+
+    from oracle import augment as oa
+    from oracle.cases import AUG_HSV_CASES, AUG_MOSAIC_CASES, aug_image
+    d = {"cv2_version": np.frombuffer(cv2.__version__.encode(), np.uint8)}
+    v = np.arange(256, dtype=np.uint8)
+    b, g, r = np.meshgrid(v, v, v, indexing="ij")
+    allc = np.stack([b.ravel(), g.ravel(), r.ravel()], 1).reshape(4096, 4096, 3)
+    d["bgr2hsv_exhaustive_mismatches"] = np.int64((oa.bgr2hsv(allc) != cv2.cvtColor(allc, cv2.COLOR_BGR2HSV)).any(-1).sum())
+    hh, ss, vv = np.meshgrid(v[:180], v, v, indexing="ij")
+    allh = np.stack([hh.ravel(), ss.ravel(), vv.ravel()], 1).reshape(-1, 4096, 3)
+    d["hsv2bgr_exhaustive_mismatches"] = np.int64((oa.hsv2bgr(allh, "simd") != cv2.cvtColor(allh, cv2.COLOR_HSV2BGR)).any(-1).sum())
+    print("exhaustive cv2 checks:", int(d["bgr2hsv_exhaustive_mismatches"]), int(d["hsv2bgr_exhaustive_mismatches"]))
+    for name, (h, w, seed) in AUG_HSV_CASES.items():
+        img = aug_image(h, w, seed)
+        np.random.seed(seed)
+        rr = np.random.uniform(-1, 1, 3) * [0.015, 0.7, 0.4] + 1     # the draw RandomHSV makes (cfg/default.yaml hsv_h / hsv_s / hsv_v)
+        np.random.seed(seed)
+        lab = {"img": img.copy()}
+        RandomHSV(0.015, 0.7, 0.4)(lab)
+        d[f"hsv_{name}_r"] = rr
+        d[f"hsv_{name}_crc"] = np.int64(zlib.crc32(lab["img"].tobytes()))
+        d[f"hsv_{name}_sample"] = lab["img"][::7, ::5].copy()
+        # flips of the same image with boxes
+        boxes = np.random.RandomState(seed).uniform(0.1, 0.9, (5, 4)).astype(np.float32)
+        for direction in ("vertical", "horizontal"):
+            random.seed(seed)
+            hit = random.random() < 0.5
+            random.seed(seed)
+            inst = Instances(boxes.copy(), np.zeros((0, 1000, 2), np.float32), None, bbox_format="xywh", normalized=True)
+            out = RandomFlip(p=0.5, direction=direction)({"img": img.copy(), "instances": inst})
+            d[f"flip_{name}_{direction}_hit"] = np.int64(hit)
+            d[f"flip_{name}_{direction}_crc"] = np.int64(zlib.crc32(out["img"].tobytes()))
+            d[f"flip_{name}_{direction}_boxes"] = out["instances"].bboxes.copy()
+    for name, (s, shapes, seed) in AUG_MOSAIC_CASES.items():
+        imgs = [aug_image(h, w, seed + i) for i, (h, w) in enumerate(shapes)]
+        mz = Mosaic.__new__(Mosaic)
+        mz.imgsz, mz.border, mz.n = s, (-s // 2, -s // 2), 4
+        random.seed(seed)
+        yc, xc = (int(random.uniform(-x, 2 * s + x)) for x in mz.border)
+        random.seed(seed)
+
+        def lab(i):
+            h, w = shapes[i]
+            bx = np.random.RandomState(seed + 10 + i).uniform(0.2, 0.8, (3, 4)).astype(np.float32)
+            bx[:, 2:] *= 0.3
+            return {"img": imgs[i], "resized_shape": (h, w), "im_file": f"img{i}.jpg", "ori_shape": (h, w), "cls": np.full((3, 1), float(i), np.float32),
+                    "instances": Instances(bx, np.zeros((0, 1000, 2), np.float32), None, bbox_format="xywh", normalized=True)}
+        labels = lab(0)
+        labels["mix_labels"] = [lab(1), lab(2), lab(3)]
+        out = mz._mosaic4(labels)
+        d[f"mosaic_{name}_center"] = np.asarray([yc, xc], np.int64)
+        d[f"mosaic_{name}_crc"] = np.int64(zlib.crc32(out["img"].tobytes()))
+        d[f"mosaic_{name}_sample"] = out["img"][::9, ::9].copy()
+        out["instances"].convert_bbox("xyxy")
+        d[f"mosaic_{name}_boxes_xyxy"] = out["instances"].bboxes.copy()
+        d[f"mosaic_{name}_cls"] = out["cls"].copy()
+        print("mosaic", name, out["img"].shape, yc, xc)
+    np.savez_compressed(os.path.join(GOLD, "augment.npz"), **d)
+
+
 def main():
+    if sys.argv[1:] == ["augment"]:
+        return gen_augment()
     if sys.argv[1:] == ["sfa_block"]:
         return gen_sfa_block()
     if sys.argv[1:] == ["psa_block"]:

@@ -127,6 +127,9 @@ def install():
                 return torchvision.ops.deform_conv2d(x, offset, self.weight, self.bias, self.stride,
                                                      self.padding, self.dilation, mask)
 
+        # picklable under the name a real mmcv install would give it (reference checkpoints pickle the module tree)
+        ModulatedDeformConv2d.__module__, ModulatedDeformConv2d.__qualname__ = "mmcv.ops", "ModulatedDeformConv2d"
+
         def build_norm_layer(cfg, num_features, postfix=""):
             assert cfg.get("type") == "GN"
             return "gn", nn.GroupNorm(cfg.get("num_groups", 16), num_features)

@@ -339,8 +339,11 @@ def test_graphed_step_equals_eager_step(state_dict, optimizer):
         if i == 0:
             np.testing.assert_allclose(la, lb, rtol=1e-5)
             upd = float((ea.tp.flat - f0).norm())
-            assert upd > 0 and float((ea.tp.flat - eb.tp.flat).norm()) < 1e-3 * upd
-            assert float((ea.tp.ema - eb.tp.ema).norm()) < 1e-3 * float((ea.tp.ema - f0).norm() + 1e-12)
+            # AdamW's first step is lr * sign(g) element-wise (m / sqrt(v) with one sample): gradient elements at the noise floor of the fp
+            # atomics flip their whole update, hence the looser bound
+            tol = 1e-3 if optimizer == "SGD" else 2e-2
+            assert upd > 0 and float((ea.tp.flat - eb.tp.flat).norm()) < tol * upd
+            assert float((ea.tp.ema - eb.tp.ema).norm()) < tol * float((ea.tp.ema - f0).norm() + 1e-12)
             np.testing.assert_allclose(ea.tp.bufs.cpu().numpy(), eb.tp.bufs.cpu().numpy(), rtol=1e-4, atol=1e-6)
         else:
             assert abs(la[3] - lb[3]) <= 3 * abs(la[3] - lc[3]) + 1e-3 * abs(la[3])

@@ -31,6 +31,11 @@ class YadPermuteEntry(C.Structure):
                 ("p2", C.c_int64), ("s0", C.c_int64), ("s1", C.c_int64), ("s2", C.c_int64), ("flip", C.c_int32), ("dst_f32", C.c_int32)]
 
 
+class YadMosaicDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("src_w", C.c_int32), ("x1a", C.c_int32), ("y1a", C.c_int32), ("x2a", C.c_int32), ("y2a", C.c_int32),
+                ("x1b", C.c_int32), ("y1b", C.c_int32), ("pad_", C.c_int32)]
+
+
 class YadImageDesc(C.Structure):
     _fields_ = [("src", C.c_void_p), ("src_h", C.c_int32), ("src_w", C.c_int32), ("src_pitch", C.c_int32), ("new_w", C.c_int32),
                 ("new_h", C.c_int32), ("top", C.c_int32), ("left", C.c_int32), ("gain", C.c_float), ("pad_x", C.c_float), ("pad_y", C.c_float)]
@@ -85,6 +90,9 @@ SIGNATURES = {
     "yad_loss_bbox": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, f32, f32, vp, vp]),
     "yad_loss_cls": (i32, [vp, vp, i32, i32, i32, vp, f32, vp, vp]),
     "yad_loss_finalize": (i32, [vp, f32, f32, f32, i32, vp, vp]),
+    "yad_hsv_lut": (i32, [vp, i32, i32, i32, vp, vp]),
+    "yad_flip": (i32, [vp, vp, i32, i32, i32, vp, vp]),
+    "yad_mosaic4": (i32, [vp, i32, i32, vp, vp]),
     "yad_tc_gemm_selftest": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     # ---- training path
     "yad_eltwise_dev": (i32, [i32, TP, vp, i32, vp, i32, vp, i32, f32, f32, f32, vp, vp, vp, TP, i32, vp]),

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libyad.so")
-SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_v2.cu", "conv_small.cu", "pointwise.cu", "attention.cu", "postprocess.cu", "preprocess.cu", "validate.cu", "train.cu", "backward.cu", "backward_attn.cu", "wgrad.cu", "wgrad_tc.cu", "optim.cu"]
+SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_v2.cu", "conv_small.cu", "pointwise.cu", "attention.cu", "postprocess.cu", "preprocess.cu", "augment.cu", "validate.cu", "train.cu", "backward.cu", "backward_attn.cu", "wgrad.cu", "wgrad_tc.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "--extended-lambda", "-Xcompiler", "-fPIC", "-diag-suppress", "177", "-diag-suppress", "550"]
 

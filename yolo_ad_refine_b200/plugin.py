@@ -33,6 +33,26 @@ BLOCKS = ["Conv", "C3k2", "C3k2_MLCA", "SPPF", "C2PTSSA", "C2ProgressiveTSSA_Fus
 HEADS = ["AYHead", "AYHead1"]
 
 
+_ORIGINALS = {}  # (module object, attribute) -> the reference's own object, recorded by install()
+
+
+class originals:
+    """Context manager: the reference's own classes / functions are bound back for the duration of the block (and the libyad ones again
+    afterwards).  checkpoint.save_reference_checkpoint uses it to build and pickle a genuine reference DetectionModel, whose classes are recorded by
+    qualified name -- so the file loads in an unmodified reference checkout."""
+
+    def __enter__(self):
+        self._swapped = [(m, a, getattr(m, a)) for (m, a) in _ORIGINALS]
+        for (m, a), obj in _ORIGINALS.items():
+            setattr(m, a, obj)
+        return self
+
+    def __exit__(self, *exc):
+        for m, a, obj in self._swapped:
+            setattr(m, a, obj)
+        return False
+
+
 def install(ultralytics_pkg="ultralytics"):
     """Rebind the reference's names to the libyad-backed implementations.  Returns the list of rebound qualified names."""
     done = []
@@ -43,6 +63,7 @@ def install(ultralytics_pkg="ultralytics"):
         except Exception:
             return
         if hasattr(mod, attr):
+            _ORIGINALS.setdefault((mod, attr), getattr(mod, attr))
             setattr(mod, attr, obj)
             done.append(f"{modname}.{attr}")
 
@@ -66,6 +87,7 @@ def install(ultralytics_pkg="ultralytics"):
     try:  # training-mode model(batch) -> libyad forward + loss + backward (bridge.py)
         tasks = importlib.import_module(f"{ultralytics_pkg}.nn.tasks")
         if not getattr(tasks.DetectionModel.loss, "_yad_wrapped", False):
+            _ORIGINALS.setdefault((tasks.DetectionModel, "loss"), tasks.DetectionModel.loss)
             tasks.DetectionModel.loss = ybridge.model_loss(tasks.DetectionModel.loss)
             done.append("nn.tasks.DetectionModel.loss")
     except Exception:
