@@ -259,6 +259,86 @@ def measure_training(args, world, rank, sd, dtype, W, barrier, B=None, scaling="
     return out
 
 
+def run_nms_micro(args):
+    """BASELINE.json configs[2]: fused DFL decode (yad_decode) + batched NMS (yad_nms) on synthetic head logits (batch 256,
+    8400 anchors, 80 classes, bf16 level maps, class logits -6 + 1.5 randn => ~350 candidates per image at conf 0.25).  HBM-bound: algorithmic bytes =
+    the level maps read once + the kept rows written."""
+    from yolo_ad_refine_b200 import ops, parallel, synth
+    from yolo_ad_refine_b200.postprocess import nms_raw
+    world, rank, local = parallel.env_world()
+    assert torch.cuda.is_available(), "bench.py needs a GPU: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    parallel.init("nccl")
+    B, N = 256, 8400
+    raw = torch.from_numpy(synth.make_head_logits(B, N, seed=rank))
+    host = [raw[:, :, :6400].reshape(B, 144, 80, 80).permute(0, 2, 3, 1).contiguous().bfloat16().pin_memory(),
+            raw[:, :, 6400:8000].reshape(B, 144, 40, 40).permute(0, 2, 3, 1).contiguous().bfloat16().pin_memory(),
+            raw[:, :, 8000:].reshape(B, 144, 20, 20).permute(0, 2, 3, 1).contiguous().bfloat16().pin_memory()]
+    lv = [t.cuda() for t in host]
+    levels = [ops.Act(t) for t in lv]
+    y = torch.empty(B, 84, N, device="cuda")
+    proj = torch.arange(16, dtype=torch.float32, device="cuda")
+    l0 = ops.LAUNCHES
+
+    def step():
+        ops.decode(levels, (8, 16, 32), 80, 16, proj, y)
+        return nms_raw(y, **NMS_ARGS)
+
+    det, _, cnt = step()
+    launches = ops.LAUNCHES - l0
+    W = max(args.warmup, 3)
+
+    def timed(fn, k):
+        for _ in range(W):
+            fn()
+        parallel.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(k):
+            fn()
+        e.record()
+        parallel.barrier()
+        torch.cuda.synchronize()
+        return parallel.max_over_ranks(s.elapsed_time(e), device="cuda") / k
+
+    with ClockSampler(local) as clk:
+        ms = timed(step, args.steps)
+    ms_dec = timed(lambda: ops.decode(levels, (8, 16, 32), 80, 16, proj, y), args.steps)
+    det_host = torch.empty((B, NMS_ARGS["max_det"], 6), dtype=torch.float32).pin_memory()
+    cnt_host = torch.empty((B,), dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        for d, h in zip(lv, host):
+            d.copy_(h, non_blocking=True)
+        dd, _, cc = step()
+        det_host.copy_(dd, non_blocking=True)
+        cnt_host.copy_(cc, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_ms = timed(e2e_step, max(3, args.steps // 4))
+    in_bytes = sum(t.numel() * 2 for t in host)
+    alg = in_bytes + int(cnt.sum()) * 6 * 4
+    pk = peaks()
+    line = {"metric": "img/s decode+NMS microbench (8400 anchors x 80 classes, batch 256)", "value": world * B / (ms / 1000.0), "unit": "img/s", "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[2]: fused DFL decode + batched NMS(conf .25, iou .7, max_det 300), batch 256/GPU, 8400 anchors, 80 classes, "
+                                   "synthetic bf16 head logits", "global_batch": world * B, "l2": "620 MB of level maps per step exceed the 126 MB L2; no flush"},
+            "e2e": {"value": world * B / (e2e_ms / 1000.0), "unit": "img/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": det_host.numel() * 4 + cnt_host.numel() * 4},
+            "gpu_launches": launches * args.steps, "launches_per_step": launches, "clocks": clk.summary(),
+            "detections_per_image": float(cnt.float().mean()), "candidates_per_image": float((y[:, 4:].amax(1) > NMS_ARGS["conf_thres"]).sum(1).float().mean()),
+            "roofline": {"kernel": "decode_kernel + nms_* (yad_decode + yad_nms, whole step)", "bound": "hbm", "achieved": alg / (ms / 1000.0) / 1e9, "peak": pk["hbm"],
+                         "unit": "GB/s", "frac": alg / (ms / 1000.0) / 1e9 / pk["hbm"], "traffic": None, "algorithmic_bytes": alg,
+                         "decode_only_ms": ms_dec, "decode_only_GBps": (in_bytes + 84 * N * B * 4) / (ms_dec / 1000.0) / 1e9,
+                         "peak_source": f"hbm_gbs of MEASURED_PEAKS.json ({pk['src']})"}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -274,9 +354,14 @@ def main():
     ap.add_argument("--train-batch", type=int, default=128, help="images per GPU of the training-step measurement (0 = skip)")
     ap.add_argument("--train-steps", type=int, default=5)
     ap.add_argument("--profile-json", default=None, help="write the per-entry-point CUDA-event profile of one eager step here")
+    ap.add_argument("--workload", default="inference", choices=["inference", "nms_micro"],
+                    help="inference = BASELINE.json configs[1] (default; --imgsz 1280 --batch 4 = configs[4] per GPU); nms_micro = configs[2]: fused DFL "
+                         "decode + batched NMS on synthetic head logits, batch 256 x 8400 anchors x 80 classes")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "nms_micro":
+        return run_nms_micro(args)
 
     from yolo_ad_refine_b200 import parallel
     world, rank, local = parallel.env_world()
@@ -363,14 +448,20 @@ def main():
     conv = prof["yad_conv2d"]
     pk = peaks()
     ach = conv["flops"] / (conv["ms"] / 1000.0) / 1e12
-    traffic = None  # DRAM bytes per launch of the same kernels from the committed ncu capture (profiles/r1_conv_traffic.json)
-    tpath = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
+    # DRAM bytes per launch of the same kernels: from the committed ncu capture of THIS build (profiles/r2_conv_traffic.json, written by
+    # tools/conv_traffic.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`); used only when it describes the same launches
+    traffic, traffic_note = None, "no ncu capture for this configuration"
+    tpath = os.path.join(ROOT, "profiles", "r2_conv_traffic.json")
     if os.path.exists(tpath) and args.batch == 64 and args.imgsz == 640:
-        traffic = json.load(open(tpath))["dram_bytes_per_launch"]
+        tj = json.load(open(tpath))
+        if tj.get("launches") == conv["calls"]:
+            traffic, traffic_note = tj["dram_bytes_per_launch"], f"profiles/r2_conv_traffic.json ({tj['launches']} launches, ncu)"
+        else:
+            traffic_note = f"profiles/r2_conv_traffic.json covers {tj.get('launches')} launches, this build issues {conv['calls']}: stale, not reported"
     roofline = {"kernel": "yad_conv2d = conv2_kernel (resident weights, haloed 3x3 patch) / conv_tma_kernel / conv_tc_kernel / conv_small_kernel "
                           "(tcgen05 implicit-GEMM convolution, all launches of one step)",
                 "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "traffic": traffic, "algorithmic_bytes_per_launch": sum(m["bytes"] for _, _, m in conv_evs) / max(1, len(conv_evs)),
+                "traffic": traffic, "traffic_source": traffic_note, "algorithmic_bytes_per_launch": sum(m["bytes"] for _, _, m in conv_evs) / max(1, len(conv_evs)),
                 "achieved_GBps_algorithmic": sum(m["bytes"] for _, _, m in conv_evs) / (conv["ms"] / 1000.0) / 1e9, "hbm_peak_GBps": pk["hbm"],
                 "peak_source": f"bf16_tflops_sustained of MEASURED_PEAKS.json ({pk['src']})", "launches": conv["calls"],
                 "avg_launch_us": 1000.0 * conv["ms"] / conv["calls"], "share_of_step": conv["ms"] / eager_ms,
@@ -379,6 +470,11 @@ def main():
         json.dump({"eager_ms": eager_ms, "graph_ms_per_step": ms_per_step, "entries": prof}, open(args.profile_json, "w"), indent=1)
 
     launches_per_step = eng.launches_per_step
+    eng.step()
+    eng.join()
+    _y, _, _det, _, _cnt = eng._out
+    det_per_img = float(_cnt.float().mean())
+    cand_per_img = float((_y[:, 4:].amax(1) > NMS_ARGS["conf_thres"]).sum(1).float().mean())
     train = train_strong = None
     if args.train_batch > 0:
         del eng  # the inference engine's graphs and buffers are not needed any more
@@ -392,7 +488,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": make_config(args, world),
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-            "clocks": clk.summary(), "roofline": roofline}
+            "clocks": clk.summary(), "detections_per_image": det_per_img, "candidates_per_image": cand_per_img, "roofline": roofline}
     if train is not None:
         line["train"] = train
     if train_strong is not None:

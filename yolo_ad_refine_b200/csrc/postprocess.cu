@@ -107,6 +107,7 @@ struct NmsWs {
   int32_t* best_cls;    // [B][N]
   uint64_t* key;        // [B][cap_pad]
   float4* box;          // [B][cap]
+  float4* sbox;         // [B][cap]  class-offset boxes in sorted order (written by the sort kernel)
   float* sc;            // [B][cap]
   int32_t* cls;         // [B][cap]
   int32_t* anchor;      // [B][cap]
@@ -353,41 +354,174 @@ __global__ void __launch_bounds__(CH) nms_gather_kernel(const float* __restrict_
   (void)tot_e; (void)tot_i; (void)s_base;
 }
 
-// K5: per-image bitonic sort of the 64-bit keys (ascending = score descending, index ascending)
-constexpr int SORT_SMEM = 4096;
-__global__ void __launch_bounds__(1024) nms_sort_kernel(NmsWs ws) {
+// K5: per-image bitonic sort of the 64-bit keys (ascending = score descending, index ascending), then the gather of the class-offset boxes in
+// sorted order (ws.sbox) so that the greedy pass streams them with one coalesced, prefetchable load per 64-candidate chunk.
+//   np <= 1024          one key per thread, compare-exchange through shared memory
+//   2048 .. 16384       E = np / 1024 keys per thread IN REGISTERS: strides inside a thread are register swaps, strides inside a warp are
+//                       shuffles, and only the five top index bits need shared memory -- two transpositions per merge size (layout A: index =
+//                       thread * E + r; layout B: index = r << 10 | lane << 5 | warp) instead of one block-wide pass per stride (105 passes of
+//                       16 K keys measured 208 us per image batch; see profiles/r2_nms.md)
+//   larger              in global memory / L2 (multi_label lists of up to max_nms = 30000 keys)
+constexpr int SORT_SMEM = 16384;  // keys held in (dynamic) shared memory: 128 KB
+__device__ __forceinline__ int sort_swz(int i) { return i ^ ((i >> 5) & 15); }  // conflict-free for both layouts (8-byte banks)
+__device__ __forceinline__ uint64_t shfl_xor64(uint64_t v, int m) {
+  uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  lo = __shfl_xor_sync(0xffffffffu, lo, m);
+  hi = __shfl_xor_sync(0xffffffffu, hi, m);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// compare-exchange helpers: `up` / `keep_min` are uniform over a thread's registers wherever the merge size exceeds the thread's own span
+__device__ __forceinline__ void cmpx(uint64_t& lo, uint64_t& hi, bool up) {  // up: the lower index receives the minimum
+  const uint64_t x = lo, y = hi;
+  const bool sw = (y < x) == up;
+  lo = sw ? y : x;
+  hi = sw ? x : y;
+}
+__device__ __forceinline__ void cmps(uint64_t& v, int lane_mask, bool keep_min) {  // partner in another lane of the warp
+  const uint64_t y = shfl_xor64(v, lane_mask);
+  if ((y < v) == keep_min) v = y;
+}
+
+// layout A (index = thread * E + r): stages on index bits hi_bit .. 0 of merge size 2^sb, sb >= LOGE (direction uniform per thread)
+template <int E, int LOGE>
+__device__ __forceinline__ void sort_stages_a(uint64_t (&v)[E], int sb, int hi_bit, int t, int lane) {
+  const bool up = ((t >> (sb - LOGE)) & 1) == 0;
+  for (int jb = hi_bit; jb >= LOGE; jb--) {  // across lanes
+    const int lm = 1 << (jb - LOGE);
+    const bool keep_min = ((lane & lm) != 0) != up;
+#pragma unroll
+    for (int r = 0; r < E; r++) cmps(v[r], lm, keep_min);
+  }
+#pragma unroll
+  for (int jb = LOGE - 1; jb >= 0; jb--) {  // inside the thread (hi_bit >= LOGE - 1 for every sb >= LOGE)
+#pragma unroll
+    for (int r = 0; r < E; r++)
+      if (!(r & (1 << jb))) cmpx(v[r], v[r | (1 << jb)], up);
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void sort_regs(uint64_t* sk, const uint64_t* gk) {
+  constexpr int LOGE = E == 2 ? 1 : E == 4 ? 2 : E == 8 ? 3 : 4;
+  constexpr int LOGN = 10 + LOGE, NP = 1024 * E;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  uint64_t v[E];
+  for (int i = t; i < NP; i += 1024) sk[sort_swz(i)] = gk[i];
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < E; r++) v[r] = sk[sort_swz(t * E + r)];
+  // merge sizes below the thread's span: directions are compile-time constants
+#pragma unroll
+  for (int sb = 1; sb < LOGE; sb++) {
+#pragma unroll
+    for (int jb = sb - 1; jb >= 0; jb--) {
+#pragma unroll
+      for (int r = 0; r < E; r++)
+        if (!(r & (1 << jb))) cmpx(v[r], v[r | (1 << jb)], ((r >> sb) & 1) == 0);
+    }
+  }
+  for (int sb = LOGE; sb <= LOGN; sb++) {
+    if (sb - 1 > LOGE + 4) {
+      // index bits sb-1 .. LOGE+5 in layout B (index = r << 10 | lane << 5 | warp: bits 10.. are registers, bits 5..9 lanes)
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < E; r++) sk[sort_swz(t * E + r)] = v[r];
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < E; r++) v[r] = sk[sort_swz((r << 10) | (lane << 5) | warp)];
+      const bool lane_up = sb >= 10 ? true : ((lane >> (sb - 5)) & 1) == 0;
+      const int rbit = sb >= 10 && sb - 10 < LOGE ? (1 << (sb - 10)) : 0;  // register bit that flips the direction (0: none)
+#pragma unroll
+      for (int jb = LOGN - 1; jb >= 10; jb--) {
+        if (jb > sb - 1) continue;
+#pragma unroll
+        for (int r = 0; r < E; r++)
+          if (!(r & (1 << (jb - 10)))) cmpx(v[r], v[r | (1 << (jb - 10))], lane_up && !(r & rbit));
+      }
+      for (int jb = (sb - 1 < 9 ? sb - 1 : 9); jb >= LOGE + 5; jb--) {
+        const int lm = 1 << (jb - 5);
+        const bool upper = (lane & lm) != 0;
+#pragma unroll
+        for (int r = 0; r < E; r++) cmps(v[r], lm, upper != (lane_up && !(r & rbit)));
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < E; r++) sk[sort_swz((r << 10) | (lane << 5) | warp)] = v[r];
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < E; r++) v[r] = sk[sort_swz(t * E + r)];
+      sort_stages_a<E, LOGE>(v, sb, LOGE + 4, t, lane);
+    } else {
+      sort_stages_a<E, LOGE>(v, sb, sb - 1, t, lane);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < E; r++) sk[sort_swz(t * E + r)] = v[r];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) nms_sort_kernel(NmsWs ws, int agnostic, float max_wh) {
   pdl_sync();
-  __shared__ uint64_t sk[SORT_SMEM];
+  extern __shared__ uint64_t sk[];
   const int b = blockIdx.x;
   const int n = ws.meta[b * 4 + 3];
-  if (n <= 1) return;
+  if (n <= 0) return;
   int np = 2;
   while (np < n) np <<= 1;
   uint64_t* gk = ws.key + (int64_t)b * ws.cap_pad;
-  for (int i = n + threadIdx.x; i < np; i += blockDim.x) gk[i] = ~0ull;
-  uint64_t* k = gk;
   const bool in_smem = np <= SORT_SMEM;
-  __syncthreads();
-  if (in_smem) {
-    for (int i = threadIdx.x; i < np; i += blockDim.x) sk[i] = gk[i];
-    k = sk;
+  bool swizzled = false;
+  if (n > 1) {
+    for (int i = n + threadIdx.x; i < np; i += blockDim.x) gk[i] = ~0ull;
     __syncthreads();
-  }
-  for (int size = 2; size <= np; size <<= 1) {
-    for (int j = size >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < np; i += blockDim.x) {
-        int p = i ^ j;
-        if (p > i) {
-          uint64_t x = k[i], y = k[p];
-          bool up = (i & size) == 0;
-          if ((x > y) == up) { k[i] = y; k[p] = x; }
+    if (in_smem && np >= 2048) {
+      swizzled = true;
+      switch (np >> 10) {
+        case 2: sort_regs<2>(sk, gk); break;
+        case 4: sort_regs<4>(sk, gk); break;
+        case 8: sort_regs<8>(sk, gk); break;
+        default: sort_regs<16>(sk, gk); break;
+      }
+    } else {
+      uint64_t* k = gk;
+      if (in_smem) {
+        for (int i = threadIdx.x; i < np; i += blockDim.x) sk[i] = gk[i];
+        k = sk;
+        __syncthreads();
+      }
+      for (int size = 2; size <= np; size <<= 1) {
+        for (int j = size >> 1; j > 0; j >>= 1) {
+          for (int i = threadIdx.x; i < np; i += blockDim.x) {
+            int p = i ^ j;
+            if (p > i) {
+              uint64_t x = k[i], y = k[p];
+              bool up = (i & size) == 0;
+              if ((x > y) == up) { k[i] = y; k[p] = x; }
+            }
+          }
+          __syncthreads();
         }
       }
-      __syncthreads();
     }
   }
-  if (in_smem)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) gk[i] = sk[i];
+  // sorted keys back to global memory + the class-offset boxes in sorted order
+  const int64_t base = (int64_t)b * ws.cap;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    uint64_t key = gk[i];
+    if (n > 1 && in_smem) {
+      key = sk[swizzled ? sort_swz(i) : i];
+      gk[i] = key;
+    }
+    const int ci = (int)(key & 0xFFFFFFFFu);
+    float4 bx = ws.box[base + ci];
+    if (!agnostic) {
+      float off = __fmul_rn((float)ws.cls[base + ci], max_wh);  // utils/ops.py:285 (fp32 class offset)
+      bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off); bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
+    }
+    ws.sbox[base + i] = bx;
+  }
 }
 
 __device__ __forceinline__ bool iou_gt(const float4& a, float area_a, const float4& b, float area_b, float thr) {
@@ -398,40 +532,40 @@ __device__ __forceinline__ bool iou_gt(const float4& a, float area_a, const floa
   return ovr > thr;
 }
 
-// K6: greedy suppression, one block (256 threads) per image
-__global__ void __launch_bounds__(256) nms_greedy_kernel(NmsWs ws, float iou_thres, int agnostic, float max_wh, int max_det,
-                                                         float* __restrict__ out, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_count) {
+// K6: greedy suppression, one block of GREEDY_T threads per image, 64 sorted candidates per round.  Inside the loop there is no dependent global
+// access: the next chunk's boxes are prefetched into registers, the serial part works on two 64-bit masks in shared memory, and the rows of
+// the kept candidates are written by all threads after the loop.
+constexpr int GREEDY_T = 1024;
+__global__ void __launch_bounds__(GREEDY_T) nms_greedy_kernel(NmsWs ws, float iou_thres, int max_det, float* __restrict__ out,
+                                                              int32_t* __restrict__ out_idx, int32_t* __restrict__ out_count) {
   pdl_sync();
-  extern __shared__ float4 kept[];                 // [max_det] offset boxes, then float areas[max_det]
+  extern __shared__ float4 kept[];                 // [max_det] offset boxes, float areas[max_det], int sorted rank[max_det]
   float* kept_area = reinterpret_cast<float*>(kept + max_det);
+  int* kept_rank = reinterpret_cast<int*>(kept_area + max_det);
   __shared__ float4 cb[64];
   __shared__ float ca[64];
-  __shared__ int cidx[64];
   __shared__ unsigned int dead[2];                 // suppressed-by-kept bitmask
-  __shared__ unsigned int sup[64][2];              // sup[i] = mask of j > i suppressed by i
+  __shared__ unsigned long long sup[64];           // sup[i] = mask of j > i suppressed by i
   __shared__ int s_nk;
+  __shared__ unsigned int s_keep[2];
   const int b = blockIdx.x, n = ws.meta[b * 4 + 3];
   const uint64_t* key = ws.key + (int64_t)b * ws.cap_pad;
   const int64_t base = (int64_t)b * ws.cap;
   if (threadIdx.x == 0) s_nk = 0;
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int PARTS = GREEDY_T / 64, IPW = 64 / (GREEDY_T / 32);
+  float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.x < 64 && threadIdx.x < n) nxt = ws.sbox[base + threadIdx.x];
+  __syncthreads();
   for (int s = 0; s < n; s += 64) {
     const int m = min(64, n - s);
     const int nk = s_nk;
     if (nk >= max_det) break;
     if (threadIdx.x < 64) {
-      if (threadIdx.x < m) {
-        int ci = (int)(key[s + threadIdx.x] & 0xFFFFFFFFu);
-        float4 bx = ws.box[base + ci];
-        if (!agnostic) {
-          float off = __fmul_rn((float)ws.cls[base + ci], max_wh);  // utils/ops.py:285 (fp32 class offset)
-          bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off); bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
-        }
-        cb[threadIdx.x] = bx;
-        ca[threadIdx.x] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
-        cidx[threadIdx.x] = ci;
-      }
+      const float4 bx = nxt;
+      if (s + 64 + threadIdx.x < n) nxt = ws.sbox[base + s + 64 + threadIdx.x];
+      cb[threadIdx.x] = bx;
+      ca[threadIdx.x] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
       if (threadIdx.x < 2) dead[threadIdx.x] = 0u;
     }
     __syncthreads();
@@ -442,45 +576,63 @@ __global__ void __launch_bounds__(256) nms_greedy_kernel(NmsWs ws, float iou_thr
       if (j < m) {
         const float4 bj = cb[j];
         const float aj = ca[j];
-        for (int k = part; k < nk && !d; k += 4) d = iou_gt(kept[k], kept_area[k], bj, aj, iou_thres);
+        for (int k = part; k < nk && !d; k += PARTS) d = iou_gt(kept[k], kept_area[k], bj, aj, iou_thres);
       }
       if (d) atomicOr(&dead[j >> 5], 1u << (j & 31));
     }
-    // B: intra-chunk bitmask with warp ballots: warp w handles i in [8w, 8w+8)
-    for (int ii = 0; ii < 8; ii++) {
-      const int i = warp * 8 + ii;
+    // B: intra-chunk bitmask with warp ballots: warp w handles i in [IPW w, IPW w + IPW)
+    for (int ii = 0; ii < IPW; ii++) {
+      const int i = warp * IPW + ii;
       for (int half = 0; half < 2; half++) {
         const int j = half * 32 + lane;
         bool p = false;
         if (i < m && j < m && j > i) p = iou_gt(cb[i], ca[i], cb[j], ca[j], iou_thres);
         unsigned int bal = __ballot_sync(0xffffffffu, p);
-        if (lane == 0) sup[i][half] = bal;
+        if (lane == 0) reinterpret_cast<unsigned int*>(sup)[i * 2 + half] = bal;
       }
     }
     __syncthreads();
-    // C: serial resolve
+    // C: serial resolve on the bitmasks alone: one thread hops from kept candidate to kept candidate
     if (threadIdx.x == 0) {
-      uint64_t remv = ((uint64_t)dead[1] << 32) | dead[0];
+      const uint64_t valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
+      uint64_t remv = ((uint64_t)dead[1] << 32) | dead[0], keep = 0ull;
+      uint64_t avail = ~remv & valid;
       int k = nk;
-      for (int i = 0; i < m && k < max_det; i++) {
-        if (!((remv >> i) & 1ull)) {
-          kept[k] = cb[i];
-          kept_area[k] = ca[i];
-          const int ci = cidx[i];
-          const float4 ob = ws.box[base + ci];
-          float* o = out + ((int64_t)b * max_det + k) * 6;
-          o[0] = ob.x; o[1] = ob.y; o[2] = ob.z; o[3] = ob.w; o[4] = ws.sc[base + ci]; o[5] = (float)ws.cls[base + ci];
-          out_idx[((int64_t)b * max_det + k) * 2] = ws.anchor[base + ci];
-          out_idx[((int64_t)b * max_det + k) * 2 + 1] = ws.cls[base + ci];
-          k++;
-          remv |= ((uint64_t)sup[i][1] << 32) | sup[i][0];
-        }
+      while (avail && k < max_det) {
+        const int i = __ffsll((long long)avail) - 1;
+        keep |= 1ull << i;
+        k++;
+        remv |= sup[i];
+        avail = ~remv & valid & ~((2ull << i) - 1ull);
       }
+      s_keep[0] = (unsigned int)keep;
+      s_keep[1] = (unsigned int)(keep >> 32);
       s_nk = k;
     }
     __syncthreads();
+    if (threadIdx.x < 64) {
+      const int i = threadIdx.x;
+      const uint64_t keep = ((uint64_t)s_keep[1] << 32) | s_keep[0];
+      if ((keep >> i) & 1ull) {
+        const int k = nk + __popcll(keep & ((1ull << i) - 1ull));
+        kept[k] = cb[i];
+        kept_area[k] = ca[i];
+        kept_rank[k] = s + i;
+      }
+    }
+    __syncthreads();
   }
-  if (threadIdx.x == 0) out_count[b] = s_nk;
+  const int nk = s_nk;
+  for (int k = threadIdx.x; k < nk; k += blockDim.x) {
+    const int ci = (int)(key[kept_rank[k]] & 0xFFFFFFFFu);
+    const float4 ob = ws.box[base + ci];
+    const int cl = ws.cls[base + ci];
+    float* o = out + ((int64_t)b * max_det + k) * 6;
+    o[0] = ob.x; o[1] = ob.y; o[2] = ob.z; o[3] = ob.w; o[4] = ws.sc[base + ci]; o[5] = (float)cl;
+    out_idx[((int64_t)b * max_det + k) * 2] = ws.anchor[base + ci];
+    out_idx[((int64_t)b * max_det + k) * 2 + 1] = cl;
+  }
+  if (threadIdx.x == 0) out_count[b] = nk;
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -504,6 +656,7 @@ size_t carve(NmsWs& ws, char* p, int B, int N, int nc, int multi_label, int max_
   ws.best_cls = (int32_t*)take(sizeof(int32_t) * (size_t)B * N);
   ws.key = (uint64_t*)take(sizeof(uint64_t) * (size_t)B * ws.cap_pad);
   ws.box = (float4*)take(sizeof(float4) * (size_t)B * ws.cap);
+  ws.sbox = (float4*)take(sizeof(float4) * (size_t)B * ws.cap);
   ws.sc = (float*)take(sizeof(float) * (size_t)B * ws.cap);
   ws.cls = (int32_t*)take(sizeof(int32_t) * (size_t)B * ws.cap);
   ws.anchor = (int32_t*)take(sizeof(int32_t) * (size_t)B * ws.cap);
@@ -572,9 +725,21 @@ int yad_nms(const float* pred, int batch, int nc, int n_anchors, float conf_thre
     YAD_LAUNCH(nms_count2_kernel<false>, gc, CH, 0, st, pred, nc, n_anchors, conf_thres, classes_mask, ws);
     YAD_LAUNCH(nms_gather_kernel<false>, gc, CH, 0, st, pred, nc, n_anchors, conf_thres, classes_mask, ws);
   }
-  YAD_LAUNCH(nms_sort_kernel, batch, 1024, 0, st, ws);
-  size_t smem = (size_t)max_det * (sizeof(float4) + sizeof(float));
-  YAD_LAUNCH(nms_greedy_kernel, batch, 256, smem, st, ws, iou_thres, agnostic, max_wh, max_det, out, out_idx, out_count);
+  {
+    static bool attr = false;
+    if (!attr) {
+      if (cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM * 8) != cudaSuccess ||
+          cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 24) != cudaSuccess) {
+        yad_set_error("nms: cannot raise the dynamic shared memory limit of the sort / greedy kernels");
+        return 2;
+      }
+      attr = true;
+    }
+    const int np = ws.cap_pad < SORT_SMEM ? ws.cap_pad : SORT_SMEM;
+    YAD_LAUNCH(nms_sort_kernel, batch, 1024, (size_t)np * 8, st, ws, agnostic, max_wh);
+  }
+  size_t smem = (size_t)max_det * (sizeof(float4) + sizeof(float) + sizeof(int));
+  YAD_LAUNCH(nms_greedy_kernel, batch, GREEDY_T, smem, st, ws, iou_thres, max_det, out, out_idx, out_count);
   YAD_LAUNCH_CHECK("nms");
   return 0;
 }

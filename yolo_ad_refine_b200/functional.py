@@ -375,6 +375,25 @@ def progressive_feature_fusion(ctx, p, x):
     outs, cur = [], x
     for i in range(3):
         q = f"{p}.stages.{i}"
+        tmp = done = None
+        if i < 2:  # stage_fusion over cat([cur, o]) as two accumulating 1x1 convs (no concat buffer); the half on `cur` does not depend on this
+            # stage's own chain: under graph capture it runs on a side stream (a parallel branch), one launch less on the critical path per stage
+            wk, bk = f"{p}.stage_fusion.{i}.weight", f"{p}.stage_fusion.{i}.bias"
+            wfull = P.sd[wk].float()
+            c1 = P.conv_raw(wk + "#a", wfull[:, :c], P.sd[bk].float())
+            c2 = P.conv_raw(wk + "#b", wfull[:, c:], None)
+            if ctx.parallel_levels:
+                main = torch.cuda.current_stream()
+                fork = torch.cuda.Event()
+                fork.record(main)
+                br = ctx.side_streams(8)[7]
+                br.wait_event(fork)
+                with torch.cuda.stream(br):
+                    tmp = conv(ctx, cur, c1)
+                    done = torch.cuda.Event()
+                    done.record(br)
+            else:
+                tmp = conv(ctx, cur, c1)
         dw3, b3, _ = P.dw(q + ".conv.weight", q + ".conv.bias")
         sc, sh = P.bn_affine(q + ".norm")
         t = ops.dwconv(cur, dw3, ctx.act(n, h, w, c), bias=b3, scale=sc, shift=sh, k=3, act=ops.ACT_GELU)
@@ -382,12 +401,9 @@ def progressive_feature_fusion(ctx, p, x):
         sm = ops.dwconv(t, dw7, ctx.act(n, h, w, c), bias=b7, k=7, add=cur)  # spatial_mix(t) + cur
         o = conv(ctx, t, P.conv(q + ".channel_mix.weight", q + ".channel_mix.bias"), add=sm)  # + channel_mix(t)
         outs.append(o)
-        if i < 2:  # stage_fusion over cat([cur, o]) as two accumulating 1x1 convs (no concat buffer)
-            wk, bk = f"{p}.stage_fusion.{i}.weight", f"{p}.stage_fusion.{i}.bias"
-            wfull = P.sd[wk].float()
-            c1 = P.conv_raw(wk + "#a", wfull[:, :c], P.sd[bk].float())
-            c2 = P.conv_raw(wk + "#b", wfull[:, c:], None)
-            tmp = conv(ctx, cur, c1)
+        if i < 2:
+            if done is not None:
+                torch.cuda.current_stream().wait_event(done)
             cur = conv(ctx, o, c2, add=tmp)
     sa = P.vec(p + ".stage_attention")
     return ops.eltwise(3, outs[0], outs[1], ctx.act(n, h, w, c), c3=outs[2], d4=x, alpha=sa[0], beta=sa[1], gamma=sa[2])
