@@ -35,6 +35,7 @@ constexpr int V2_MAX_EPI_WARPS = 16;  // 8 (two per TMEM lane quarter) or 16 (fo
 constexpr int V2_MAX_THREADS = 64 + 32 * V2_MAX_EPI_WARPS;
 constexpr int V2_BH = 16, V2_BW = 8;   // 3x3 M tile: 16 rows of 8 pixels
 constexpr int V2_MAX_BCHUNKS = 32;     // resident weight chunks (one mbarrier each)
+constexpr int V2_MAX_ACC = 8;          // TMEM accumulator stages (tile-split epilogue of narrow tiles: 8 x 64 columns)
 constexpr int ACT_GENERIC = -1;        // activation chosen at run time (relu / gelu / hardswish)
 
 struct V2Params {
@@ -47,6 +48,8 @@ struct V2Params {
   int tap_row[9];           // patch row (= pixel index inside the patch) the A descriptor of tap t starts at
   int stages, acc_stages, tmem_cols;
   int dbg;                  // bring-up / profiling switch (YAD_CONV2_DBG): 1 = the MMA lane issues nothing, 2 = the epilogue skips its TMEM reads and math (results are garbage)
+  int tsplit;               // narrow tiles (n_tile <= 64): number of epilogue warp groups (4 warps = the 4 TMEM lane quarters) that take whole tiles in
+                            // turn instead of sharing the columns of one tile (0: column split); several tiles' epilogue latencies then overlap
   int ksplit;               // 3x3: taps are dealt round-robin to `ksplit` accumulators (independent tcgen05.mma dependency chains), summed in the epilogue
   uint32_t off_b, b_chunk_bytes, off_a, a_stage_bytes, a_tx_bytes, off_stg, stg_warp_bytes, off_bias, off_bars;
   int sc, ew, stg_bufs;     // columns per TMA store box (16 / 32 / 64); epilogue warps (8 / 16); staging tiles per warp (2: the bulk store of piece i
@@ -162,6 +165,34 @@ __device__ __forceinline__ void gn_unit(const V2Params& p, const float (&v)[U], 
   }
 }
 
+// Per-tile bookkeeping without divisions: every role (producer, MMA issuer, epilogue warps) walks tile, tile + gridDim.x, ... and used to
+// decompose each tile index with 4-6 integer divisions (~140 instructions and ~1000 cycles of dependent latency per tile in the MMA warp alone:
+// the tensor pipe idled through it, profiles/r2_ncu_conv_v2.md).  The decomposition is now carried as mixed-radix digits
+// (column tile, tile x, tile y, image) advanced by the digits of the grid stride; flat (1x1) launches have tiles_x = tiles_y = 1, so `img` is
+// the M tile index there.  V2Ring is a ring-buffer slot with its mbarrier phase.
+struct V2TileIter {
+  int nt, tx, ty, img, d_nt, d_tx, d_ty, d_img;
+  __device__ __forceinline__ void init(const V2Params& p, int tile0, int step) {
+    nt = tile0 % p.tiles_n; int mt = tile0 / p.tiles_n;
+    tx = mt % p.tiles_x; mt /= p.tiles_x;
+    ty = mt % p.tiles_y; img = mt / p.tiles_y;
+    d_nt = step % p.tiles_n; mt = step / p.tiles_n;
+    d_tx = mt % p.tiles_x; mt /= p.tiles_x;
+    d_ty = mt % p.tiles_y; d_img = mt / p.tiles_y;
+  }
+  __device__ __forceinline__ void next(const V2Params& p) {
+    nt += d_nt; int c = nt >= p.tiles_n ? 1 : 0; nt -= c ? p.tiles_n : 0;
+    tx += d_tx + c; c = tx >= p.tiles_x ? 1 : 0; tx -= c ? p.tiles_x : 0;
+    ty += d_ty + c; c = ty >= p.tiles_y ? 1 : 0; ty -= c ? p.tiles_y : 0;
+    img += d_img + c;
+  }
+};
+struct V2Ring {
+  int idx = 0;
+  uint32_t ph = 0;
+  __device__ __forceinline__ void next(int n) { if (++idx == n) { idx = 0; ph ^= 1u; } }
+};
+
 // One unit of U (16 / 32) accumulator columns of this thread's row: TMEM -> registers -> scale / bias / activation / alpha (-> GroupNorm partial
 // sums) -> bf16 -> swizzled staging row.  `first` : the staging tile is about to be overwritten for the first time since the last bulk store.
 template <int U, int ACT, bool GN, bool SCALE>
@@ -246,7 +277,8 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
   {
     // ================= epilogue: 8 or 16 warps, TMEM lane quarter = warp & 3, the 2 / 4 warps of a quarter split the columns =================
     const int q = warp & 3, ew = warp - 2, way = ew >> 2;
-    const int cb = p.bnd[way], ce = p.bnd[way + 1];
+    const int G = p.tsplit;
+    const int cb = G ? 0 : p.bnd[way], ce = G ? p.n_tile : p.bnd[way + 1];
     const uint32_t stg0 = base + p.off_stg + (uint32_t)(ew * p.stg_bufs) * p.stg_warp_bytes;
     const uint32_t RB = 2u * (uint32_t)p.sc, swz = (RB >> 4) - 1u;
     const uint32_t ph = (((uint32_t)lane * RB) >> 7) & swz;  // every staging tile starts on its swizzle period
@@ -255,22 +287,25 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
     const uint32_t lane_base = ((uint32_t)(q * 32)) << 16;
     // phase-2 geometry (mul / add on the staged piece): cpr lanes sweep one row
     const int cpr = p.sc >> 3, rpp = 32 / cpr, rr0 = lane / cpr, cj = lane - rr0 * cpr;
-    int i = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, i++) {
-      const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n, n0 = nt * p.n_tile;
+    V2TileIter ti;
+    ti.init(p, (int)blockIdx.x, (int)gridDim.x);
+    V2Ring ar;     // accumulator stage of the current tile
+    int turn = 0;  // tile-split: whose turn it is
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ti.next(p), ar.next(p.acc_stages), turn = (turn + 1 == G) ? 0 : turn + 1) {
+      if (G && turn != way) continue;  // tile-split: this warp group's turn comes every G-th tile
+      const int n0 = ti.nt * p.n_tile;
       int img = 0, ty0 = 0, tx0 = 0, m_base = 0;
       bool valid, uniform = true;
       int dp = 0;
       if (PATCH) {
-        img = mt / per_img;
-        const int r = mt - img * per_img;
-        ty0 = (r / p.tiles_x) * V2_BH;
-        tx0 = (r % p.tiles_x) * V2_BW;
+        img = ti.img;
+        ty0 = ti.ty * V2_BH;
+        tx0 = ti.tx * V2_BW;
         const int oy = ty0 + 4 * q + (lane >> 3), ox = tx0 + (lane & 7);
         valid = oy < p.hm && ox < p.wm;
         dp = (img * p.hm + oy) * p.wm + ox;
       } else {
-        m_base = mt * V2_BM + 32 * q;
+        m_base = ti.img * V2_BM + 32 * q;
         dp = m_base + lane;
         valid = dp < p.m_total;
         if (GN || SCALE) {
@@ -286,8 +321,8 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
           if (p.pix_scale) rsc *= __bfloat162float(p.pix_scale[(int64_t)dp * p.pix_scale_ld]);
         }
       }
-      const int acc = i % p.acc_stages;
-      mbar_wait((tfull0 + 8u * (uint32_t)acc), ((uint32_t)(i / p.acc_stages)) & 1u);
+      const int acc = ar.idx;
+      mbar_wait((tfull0 + 8u * (uint32_t)acc), ar.ph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(acc * p.ksplit * p.n_tile) + lane_base;
       const bool store_ok = !PATCH || (ty0 + 4 * q < p.hm);  // warp-uniform: a patch-mode box entirely below the image is not issued
@@ -383,9 +418,9 @@ __global__ void __launch_bounds__(V2_MAX_THREADS, 1) conv2_kernel(const __grid_c
   auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(p.stages + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * p.stages + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * p.stages + 2 + a); };
-  auto b_bar = [&](int i) { return bars + 8u * (uint32_t)(2 * p.stages + 4 + i); };
-  const uint32_t tmem_ptr_addr = bars + 8u * (uint32_t)(2 * p.stages + 4 + V2_MAX_BCHUNKS);
+  auto tempty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * p.stages + V2_MAX_ACC + a); };
+  auto b_bar = [&](int i) { return bars + 8u * (uint32_t)(2 * p.stages + 2 * V2_MAX_ACC + i); };
+  const uint32_t tmem_ptr_addr = bars + 8u * (uint32_t)(2 * p.stages + 2 * V2_MAX_ACC + V2_MAX_BCHUNKS);
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -394,7 +429,7 @@ __global__ void __launch_bounds__(V2_MAX_THREADS, 1) conv2_kernel(const __grid_c
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (uint32_t)p.ew); }
+    for (int a = 0; a < p.acc_stages; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), p.tsplit ? 4u : (uint32_t)p.ew); }
     for (int i = 0; i < nbch; i++) mbar_init(b_bar(i), 1);
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -425,25 +460,19 @@ __global__ void __launch_bounds__(V2_MAX_THREADS, 1) conv2_kernel(const __grid_c
           tma_load_2d(base + p.off_b + (uint32_t)i * p.b_chunk_bytes, &tmB, b_bar(i), t * p.cin + c * 64, nt * p.n_tile);
         }
       }
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.tiles_n;
-        int img = 0, ty0 = 0, tx0 = 0;
-        if (PATCH) {
-          img = mt / per_img;
-          const int r = mt - img * per_img;
-          ty0 = (r / p.tiles_x) * V2_BH;
-          tx0 = (r % p.tiles_x) * V2_BW;
-        }
-        for (int c = 0; c < p.kpt; c++, it++) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1u;
+      V2TileIter ti;
+      ti.init(p, (int)blockIdx.x, (int)gridDim.x);
+      V2Ring sr;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ti.next(p)) {
+        const int img = ti.img, ty0 = ti.ty * V2_BH, tx0 = ti.tx * V2_BW;
+        for (int c = 0; c < p.kpt; c++, sr.next(p.stages)) {
+          const int s = sr.idx;
           const uint32_t a_s = base + p.off_a + (uint32_t)s * p.a_stage_bytes;
-          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_wait(empty_bar(s), sr.ph ^ 1u);
           if (leader) {
             mbar_expect_tx(full_bar(s), p.a_tx_bytes);
             if (PATCH) tma_load_4d(a_s, &tmA, full_bar(s), c * 64, tx0 - 1, ty0 - 1, img);
-            else tma_load_2d(a_s, &tmA, full_bar(s), c * 64, mt * V2_BM);
+            else tma_load_2d(a_s, &tmA, full_bar(s), c * 64, img * V2_BM);
           }
         }
       }
@@ -465,20 +494,21 @@ __global__ void __launch_bounds__(V2_MAX_THREADS, 1) conv2_kernel(const __grid_c
       constexpr int NT = PATCH ? 9 : 1;
       // every weight chunk must have landed before its first use: the first tile waits chunk by chunk (so its MMAs start under the weight
       // load), later tiles never look at those barriers again
-      uint32_t it = 0;
+      V2Ring sr, ar;
       int i = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, i++) {
-        const int nt = tile % p.tiles_n;
-        const int acc = i % p.acc_stages;
-        mbar_wait(tempty_bar(acc), (((uint32_t)(i / p.acc_stages)) & 1u) ^ 1u);  // the epilogue has drained this accumulator
+      int nt = (int)(blockIdx.x % (unsigned)p.tiles_n);
+      const int nt_step = (int)(gridDim.x % (unsigned)p.tiles_n);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, i++, ar.next(p.acc_stages), nt = nt + nt_step >= p.tiles_n ? nt + nt_step - p.tiles_n : nt + nt_step) {
+        const int acc = ar.idx;
+        mbar_wait(tempty_bar(acc), ar.ph ^ 1u);  // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.ksplit * p.n_tile);
         const uint32_t nt_cols = (uint32_t)p.n_tile;
         const int ks = p.ksplit;  // tap t accumulates into split t % ks; its first visit (chunk 0, t < ks) overwrites
         const bool first_pass = i < p.tiles_n;  // the first visit of column tile nt (tiles of one CTA cycle through the column tiles)
-        for (int c = 0; c < p.kpt; c++, it++) {
-          const int s = it % p.stages;
-          mbar_wait(full_bar(s), (it / p.stages) & 1u);
+        for (int c = 0; c < p.kpt; c++, sr.next(p.stages)) {
+          const int s = sr.idx;
+          mbar_wait(full_bar(s), sr.ph);
           tc_fence_after();
           const uint32_t a_lo0 = v2_desc_lo(base + p.off_a + (uint32_t)s * p.a_stage_bytes);
           const int bi0 = nt * NT * p.kpt + c;                      // chunk of tap 0
@@ -866,13 +896,24 @@ static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilog
     if (dbg_env < 0) dbg_env = v2_env("YAD_CONV2_DBG", 0);
     p.dbg = dbg_env;
   }
+  static int ew_env = -1, ts_env = -1;
+  if (ew_env < 0) ew_env = v2_env("YAD_CONV2_EW", 0);
+  if (ts_env < 0) ts_env = v2_env("YAD_CONV2_TSPLIT", 1);
+  // measured (profiles/r2_conv_tsplit.txt): 1x1 convolutions with <= 64 output channels gain 10-17 %; the 3x3 patch kernels are not bound by the
+  // epilogue's latency and keep the column split (YAD_CONV2_TSPLIT=2 forces the tile split there too)
+  const bool tsplit = ts_env && p.n_tile <= 64 && p.ksplit == 1 && (flat || ts_env == 2);
   p.acc_stages = (2 * p.ksplit * p.n_tile <= 512) ? 2 : 1;
+  if (tsplit) p.acc_stages = 512 / p.n_tile < V2_MAX_ACC ? 512 / p.n_tile : V2_MAX_ACC;
   p.tmem_cols = 32;
   while (p.tmem_cols < p.acc_stages * p.ksplit * p.n_tile) p.tmem_cols <<= 1;
-  static int ew_env = -1;
-  if (ew_env < 0) ew_env = v2_env("YAD_CONV2_EW", 0);
   auto set_ew = [&](int ew) {
     p.ew = ew;
+    if (tsplit) {  // whole tiles per 4-warp group; store boxes of at most 32 columns keep the staging tiles small
+      p.tsplit = ew / 4;
+      for (int w = 0; w <= 4; w++) p.bnd[w] = w == 0 ? 0 : p.n_tile;
+      p.sc = (p.n_tile % 32) ? 16 : 32;
+      return;
+    }
     const int ways = p.ew / 4, u16 = p.n_tile / 16;  // columns are dealt in units of 16, the first ways take the remainder
     int at = 0;
     for (int w = 0; w < ways; w++) { p.bnd[w] = at; at += 16 * (u16 / ways + (w < u16 % ways ? 1 : 0)); }
@@ -882,7 +923,7 @@ static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilog
       while (sc > 16 && ((p.bnd[w + 1] - p.bnd[w]) % sc)) sc >>= 1;
     p.sc = sc;
   };
-  set_ew(ew_env == 8 || ew_env == 16 ? ew_env : (p.n_tile > 64 ? 16 : 8));
+  set_ew(ew_env == 8 || ew_env == 16 ? ew_env : (p.n_tile > 64 || tsplit ? 16 : 8));
   if (patch) {
     static int pw_env = -1;
     if (pw_env < 0) pw_env = v2_env("YAD_CONV2_PW", 10);
@@ -905,7 +946,7 @@ static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilog
   const uint32_t budget = 227u * 1024u - 1024u;
   const uint32_t max_stages = patch ? 4u : 8u, min_stages = patch ? 2u : 3u;
   uint32_t stages = 0, stg_total = 0;
-  auto total = [&](uint32_t s) { return b_total + s * p.a_stage_bytes + stg_total + bias_bytes + 8u * (2u * s + 4u + V2_MAX_BCHUNKS) + 16u; };
+  auto total = [&](uint32_t s) { return b_total + s * p.a_stage_bytes + stg_total + bias_bytes + 8u * (2u * s + 2u * V2_MAX_ACC + V2_MAX_BCHUNKS) + 16u; };
   // preference order: (epilogue warps as chosen, 2 staging tiles) > (same, 1 tile) > (8 warps, 2 tiles) > (8 warps, 1 tile), each only if the
   // activation ring keeps min_stages
   for (int attempt = 0; attempt < 4; attempt++) {
