@@ -394,9 +394,10 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // producer warps only
     }
-    for (int kc = 0; kc < nk; kc++) {
-      const int s = kc % p.stages;
-      const uint32_t ph = (uint32_t)(kc / p.stages) & 1u;
+    RingPos ring;
+    for (int kc = 0; kc < nk; kc++, ring.next(p.stages)) {
+      const int s = ring.idx;
+      const uint32_t ph = ring.ph;
       const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
       const int kk = kc * BK + c * 8;  // this thread's K offset inside the chunk: fixed tap / channel for all its rows
       const bool kvalid = kk < K;
@@ -490,9 +491,10 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const TcParams p) {
       const bool leader = elect_one();
       const uint32_t idesc = make_idesc(p.n_tile);
       const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-      for (int kc = 0; kc < nk; kc++) {
-        const int s = kc % p.stages;
-        mbar_wait(full_bar(s), (uint32_t)(kc / p.stages) & 1u);
+      RingPos sr;
+      for (int kc = 0; kc < nk; kc++, sr.next(p.stages)) {
+        const int s = sr.idx;
+        mbar_wait(full_bar(s), sr.ph);
         tc_fence_after();
         const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
         const uint32_t a_lo = ((a_s & 0x3FFFFu) >> 4) | (1u << 16), b_lo = ((b_s & 0x3FFFFu) >> 4) | (1u << 16);
@@ -657,7 +659,7 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
   const int kpt = (p.cin + tp.bk - 1) / tp.bk;  // K chunks per tap
   const int nk = p.ntaps * kpt;
   const int acc_stages = tp.acc_stages;
-  const int per_img = tp.tiles_x * tp.tiles_y;
+  const int rx_ = tp.patch ? tp.tiles_x : 1, ry_ = tp.patch ? tp.tiles_y : 1;  // tile-grid radices (flat launches: the M tile index is the image digit)
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -678,21 +680,17 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
     {  // warp-uniform producer loop, the elected lane issues
       const bool leader = elect_one();
       const uint32_t tx_bytes = (uint32_t)tp.a_bytes + b_bytes;
-      uint32_t it = 0;  // running K-chunk counter across tiles
-      for (int tile = blockIdx.x; tile < tp.total_tiles; tile += gridDim.x) {
-        const int mt = tile / tp.tiles_n, n0 = (tile - mt * tp.tiles_n) * p.n_tile;
-        int img = 0, ty0 = 0, tx0 = 0;
-        if (tp.patch) {
-          img = mt / per_img;
-          const int r = mt - img * per_img;
-          ty0 = (r / tp.tiles_x) * tp.bh;
-          tx0 = (r % tp.tiles_x) * tp.bw;
-        }
-        for (int kc = 0; kc < nk; kc++, it++) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1u;
+      TileDigits ti;
+      ti.init((int)blockIdx.x, (int)gridDim.x, tp.tiles_n, rx_, ry_);
+      RingPos sr;  // pipeline slot of the running K chunk (across tiles)
+      for (int tile = blockIdx.x; tile < tp.total_tiles; tile += gridDim.x, ti.next(tp.tiles_n, rx_, ry_)) {
+        const int mt = ti.img, n0 = ti.nt * p.n_tile;  // flat launches: rx_ = ry_ = 1, the image digit is the M tile
+        const int img = ti.img, ty0 = ti.ty * tp.bh, tx0 = ti.tx * tp.bw;
+        int t = 0, ci = 0;
+        for (int kc = 0; kc < nk; kc++, sr.next(p.stages)) {
+          const int s = sr.idx;
+          const uint32_t ph = sr.ph;
           const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
-          const int t = kc / kpt, ci = (kc - t * kpt) * tp.bk;
           mbar_wait(empty_bar(s), ph ^ 1u);
           if (leader) {
             mbar_expect_tx(full_bar(s), tx_bytes);
@@ -704,6 +702,8 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
               tma_load_2d(a_s, &tmA, full_bar(s), ci, mt * BM);
             tma_load_2d(b_s, &tmB, full_bar(s), p.wtap[t] * p.cin + ci, n0);
           }
+          ci += tp.bk;
+          if (ci >= kpt * tp.bk) { ci = 0; t++; }
         }
       }
     }
@@ -714,17 +714,16 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
       const uint32_t idesc = make_idesc(p.n_tile);
       const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
       const uint32_t hi = ((8u * row_bytes) >> 4) | (1u << 14) | (layout << 29);
-      uint32_t it = 0;
-      int i = 0;
-      for (int tile = blockIdx.x; tile < tp.total_tiles; tile += gridDim.x, i++) {
-        const int acc = i % acc_stages;
-        mbar_wait(tempty_bar(acc), (((uint32_t)(i / acc_stages)) & 1u) ^ 1u);  // epilogue has drained this accumulator
+      RingPos sr, ar;
+      for (int tile = blockIdx.x; tile < tp.total_tiles; tile += gridDim.x, ar.next(acc_stages)) {
+        const int acc = ar.idx;
+        mbar_wait(tempty_bar(acc), ar.ph ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
         const int ks = tp.bk / 16;
-        for (int kc = 0; kc < nk; kc++, it++) {
-          const int s = it % p.stages;
-          mbar_wait(full_bar(s), (it / p.stages) & 1u);
+        for (int kc = 0; kc < nk; kc++, sr.next(p.stages)) {
+          const int s = sr.idx;
+          mbar_wait(full_bar(s), sr.ph);
           tc_fence_after();
           const uint32_t a_s = base + s * stage_bytes, b_s = a_s + a_bytes;
           const uint32_t a_lo = ((a_s & 0x3FFFFu) >> 4) | (1u << 16), b_lo = ((b_s & 0x3FFFFu) >> 4) | (1u << 16);
@@ -748,24 +747,25 @@ __global__ void __launch_bounds__(TMA_THREADS) conv_tma_kernel(const __grid_cons
     // column split between the two warps of a quarter: multiples of 16, first half rounded up
     const int csplit = ((p.n_tile / 16 + 1) / 2) * 16;
     const int col_begin = half ? csplit : 0, col_end = half ? p.n_tile : csplit;
-    int i = 0;
     BnAcc bn;
     bn_acc_clear(bn);
-    for (int tile = blockIdx.x; tile < tp.total_tiles; tile += gridDim.x, i++) {
-      const int mt = tile / tp.tiles_n, n0 = (tile - mt * tp.tiles_n) * p.n_tile;
+    TileDigits ti;
+    ti.init((int)blockIdx.x, (int)gridDim.x, tp.tiles_n, rx_, ry_);
+    RingPos ar;
+    const int ry = tp.patch ? row / tp.bw : 0, rx = tp.patch ? row - ry * tp.bw : 0;  // this thread's pixel inside the patch tile
+    for (int tile = blockIdx.x; tile < tp.total_tiles; tile += gridDim.x, ti.next(tp.tiles_n, rx_, ry_), ar.next(acc_stages)) {
+      const int mt = ti.img, n0 = ti.nt * p.n_tile;
       int dp = -1, img = 0;
       if (tp.patch) {
-        img = mt / per_img;
-        const int r = mt - img * per_img;
-        const int ry = row / tp.bw, rx = row - ry * tp.bw;
-        const int oy = (r / tp.tiles_x) * tp.bh + ry, ox = (r % tp.tiles_x) * tp.bw + rx;  // position in the logical (hm x wm) grid
+        img = ti.img;
+        const int oy = ti.ty * tp.bh + ry, ox = ti.tx * tp.bw + rx;  // position in the logical (hm x wm) grid
         if (ry < tp.bh && oy < p.hm && ox < p.wm) dp = (img * p.ho + p.os * oy + p.py) * p.wo + (p.os * ox + p.px);
       } else {
         const uint32_t m = (uint32_t)mt * BM + row;
         if (m < (uint32_t)(p.n * p.ho * p.wo)) { dp = (int)m; img = (int)(m / (uint32_t)(p.ho * p.wo)); }
       }
-      const int acc = i % acc_stages;
-      mbar_wait(tfull_bar(acc), ((uint32_t)(i / acc_stages)) & 1u);
+      const int acc = ar.idx;
+      mbar_wait(tfull_bar(acc), ar.ph);
       tc_fence_after();
       if (!BN && tp.store_cols)
         epilogue_warp_tma(p, &tmY, tmem_base + (uint32_t)(acc * p.n_tile), quarter, lane, base + stg_off + (uint32_t)(ew * STG_WARP), stg,

@@ -108,6 +108,32 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
                : "memory");
 }
 
+// ---- division-free bookkeeping for persistent tile loops (tile, tile + gridDim.x, ...): a tile index is carried as mixed-radix digits
+// (column tile, tile x, tile y, image) advanced by the digits of the grid stride, ring slots carry their mbarrier phase.  Decomposing each tile /
+// K chunk with integer divisions cost the single MMA-issuing warp ~1000 dependent cycles per tile (profiles/r2_ncu_conv_v2.md).
+struct TileDigits {
+  int nt, tx, ty, img, d_nt, d_tx, d_ty, d_img;
+  __device__ __forceinline__ void init(int tile0, int step, int rn, int rx, int ry) {
+    nt = tile0 % rn; int mt = tile0 / rn;
+    tx = mt % rx; mt /= rx;
+    ty = mt % ry; img = mt / ry;
+    d_nt = step % rn; mt = step / rn;
+    d_tx = mt % rx; mt /= rx;
+    d_ty = mt % ry; d_img = mt / ry;
+  }
+  __device__ __forceinline__ void next(int rn, int rx, int ry) {
+    nt += d_nt; int c = nt >= rn ? 1 : 0; nt -= c ? rn : 0;
+    tx += d_tx + c; c = tx >= rx ? 1 : 0; tx -= c ? rx : 0;
+    ty += d_ty + c; c = ty >= ry ? 1 : 0; ty -= c ? ry : 0;
+    img += d_img + c;
+  }
+};
+struct RingPos {
+  int idx = 0;
+  uint32_t ph = 0;
+  __device__ __forceinline__ void next(int n) { if (++idx == n) { idx = 0; ph ^= 1u; } }
+};
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode() {

@@ -95,12 +95,14 @@ __global__ void __launch_bounds__(WT_THREADS) wgrad_tc_kernel(const __grid_const
     {  // warp-uniform producer loop, the elected lane issues (up to 18 TMA boxes per stage: a divergent single thread pays ~100 cycles for each)
       const bool leader = elect_one();
       const uint32_t tx_bytes = (uint32_t)(p.n_groups + nrg) * box_bytes;
-      uint32_t it = 0;
-      for (int tile = t_begin; tile < t_end; tile++, it++) {
-        const int img = tile / per_img, r = tile - img * per_img;
-        const int ty0 = (r / p.tiles_x) * p.bh, tx0 = (r % p.tiles_x) * p.bw;
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1u;
+      // division-free walk (tc_ptx.cuh): consecutive tiles advance the (tile x, tile y, image) digits by one
+      TileDigits ti;
+      ti.init(t_begin, 1, 1, p.tiles_x, p.tiles_y);
+      RingPos sr;
+      for (int tile = t_begin; tile < t_end; tile++, ti.next(1, p.tiles_x, p.tiles_y), sr.next(p.stages)) {
+        const int img = ti.img, ty0 = ti.ty * p.bh, tx0 = ti.tx * p.bw;
+        const int s = sr.idx;
+        const uint32_t ph = sr.ph;
         const uint32_t st = base + s * stage_bytes;
         mbar_wait(empty_bar(s), ph ^ 1u);
         if (leader) mbar_expect_tx(full_bar(s), tx_bytes);
@@ -120,10 +122,11 @@ __global__ void __launch_bounds__(WT_THREADS) wgrad_tc_kernel(const __grid_const
       const uint32_t idesc = make_idesc_mn(p.cout);
       const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);        // SBO 1024 B, version 1, SWIZZLE_128B
       const uint32_t lo_flags = ((box_bytes >> 4) & 0x3FFFu) << 16;               // LBO = one 64-channel box
-      uint32_t it = 0;
-      for (int tile = t_begin; tile < t_end; tile++, it++) {
-        const int s = it % p.stages;
-        mbar_wait(full_bar(s), (it / p.stages) & 1u);
+      RingPos sr;
+      bool it0 = true;  // the first tile overwrites the accumulators
+      for (int tile = t_begin; tile < t_end; tile++, sr.next(p.stages), it0 = false) {
+        const int s = sr.idx;
+        mbar_wait(full_bar(s), sr.ph);
         tc_fence_after();
         const uint32_t st = base + s * stage_bytes;
         const uint32_t b_lo = (((st) & 0x3FFFFu) >> 4) | lo_flags, a_lo0 = (((st + p.n_groups * box_bytes) & 0x3FFFFu) >> 4) | lo_flags;
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(WT_THREADS) wgrad_tc_kernel(const __grid_const
           const uint32_t d_tmem = tmem_base + (uint32_t)(mt * p.cout);
           const uint32_t a_lo = a_lo0 + (uint32_t)(2 * mt) * (box_bytes >> 4);
           if (leader) {
-            if (it == 0) umma_bf16<false>(d_tmem, pack64(a_lo, hi), pack64(b_lo, hi), idesc);
+            if (it0) umma_bf16<false>(d_tmem, pack64(a_lo, hi), pack64(b_lo, hi), idesc);
             else umma_bf16<true>(d_tmem, pack64(a_lo, hi), pack64(b_lo, hi), idesc);
             for (int k = 1; k < ks; k++) umma_bf16<true>(d_tmem, pack64(a_lo + 128u * k, hi), pack64(b_lo + 128u * k, hi), idesc);  // 2048 B per K step
           }
