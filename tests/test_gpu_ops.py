@@ -177,6 +177,20 @@ def test_gap_rowcol(dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("c,h,w", [(128, 80, 80), (64, 37, 150), (32, 5, 160), (256, 20, 20), (96, 3, 1), (64, 9, 300), (48, 21, 33), (16, 40, 64)])
+def test_rowcol_mean_single_pass(dtype, c, h, w):
+    """the one-read kernel (32-channel slices, column sums in registers, butterfly row sums): ragged widths up to 160 (1, 2, 3 and 5 column
+    positions per lane), a channel-sliced input view (ld > c), and a map wider than 160 that must take the two-pass fallback"""
+    x = q(torch.randn(3, c + 32, h, w, generator=torch.Generator().manual_seed(h + w)) + 0.2, dtype)
+    a = to_act(x, dtype).slice(32, c)
+    xs = x[:, 32:]
+    rows, cols = Act.empty(3, h, 1, c, dtype, DEV), Act.empty(3, w, 1, c, dtype, DEV)
+    ops.rowcol_mean(a, rows, cols)
+    assert rel_err(from_act(rows)[..., 0], xs.mean(3)) < tol(dtype)
+    assert rel_err(from_act(cols)[..., 0], xs.mean(2)) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("hw,s", [(20, 2), (20, 4), (40, 4), (10, 2), (5, 4), (12, 4)])
 def test_pool_upsample(dtype, hw, s):
     x = q(torch.randn(2, 16, hw, hw, generator=torch.Generator().manual_seed(hw + s)), dtype)

@@ -2,6 +2,8 @@
 // warp-shuffle reductions where a reduction is involved).  Each entry point cites the reference operator it replaces.
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -935,6 +937,118 @@ __global__ void rowcol_mean_kernel(yad_tensor x, yad_tensor rowmean, yad_tensor 
   for (int i = threadIdx.x; i < c; i += blockDim.x) st1(dst + i, sm[i] * inv);
 }
 
+// Single-pass variant (the map is read ONCE; rowcol_mean_kernel reads it once for the rows and once for the columns): one CTA per (image,
+// slice of 16 channels), 8 warps = 2 channel octets x 4 row groups (rows y = group, group + 4, ...).  The 32 lanes of a warp sweep a whole row
+// (x = lane + 32 k, NK positions), so a row costs NK 128-bit loads and ONE butterfly reduce-scatter (9 shuffles for 8 channels) whose result goes
+// straight to the row table in shared memory; the column sums stay in registers (NK x 8 per thread) and the four row groups are merged through
+// shared memory at the end.  History (profiles/r2_pointwise.md): lanes = 32 pixels of a quarter row needed one reduction per 32 pixels and was
+// instruction-bound (33.6 M warp instructions, 60 us for the 105 MB map = the two-pass kernel's time); 32-channel slices with four rows in flight
+// were latency-bound at the same 60 us.  Requires c % 16 == 0 and w <= 160 (the caller falls back otherwise).
+template <typename T, int NK>
+__global__ void __launch_bounds__(256, 2) rowcol_mean1_kernel(yad_tensor x, yad_tensor rowmean, yad_tensor colmean) {
+  pdl_sync();
+  extern __shared__ float sm[];  // rows[h][16], then cols[3][w][16] (row groups 1..3)
+  float* smc = sm + x.h * 16;
+  const int slices = x.c >> 4;
+  const int n = blockIdx.x / slices, c0 = (blockIdx.x - n * slices) * 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, oct = warp & 1, rg = warp >> 1;
+  const T* xb = reinterpret_cast<const T*>(x.ptr) + (int64_t)n * x.h * x.w * x.ld + c0 + oct * 8;
+  float col[NK][8];
+#pragma unroll
+  for (int k = 0; k < NK; k++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) col[k][i] = 0.f;
+  constexpr int RU = (sizeof(T) == 2 ? 8 : 4) / NK > 0 ? (sizeof(T) == 2 ? 8 : 4) / NK : 1;  // rows in flight per warp
+  for (int y0 = rg; y0 < x.h; y0 += 4 * RU) {
+    Raw8<T> r[RU][NK];
+#pragma unroll
+    for (int u = 0; u < RU; u++)
+#pragma unroll
+      for (int k = 0; k < NK; k++)
+        if (y0 + 4 * u < x.h && lane + 32 * k < x.w) raw_load(xb + ((int64_t)(y0 + 4 * u) * x.w + lane + 32 * k) * x.ld, r[u][k]);
+#pragma unroll
+    for (int u = 0; u < RU; u++) {
+      const int yy = y0 + 4 * u;
+      if (yy >= x.h) break;  // warp-uniform
+      float row[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) row[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < NK; k++)
+        if (lane + 32 * k < x.w) {
+          float v[8];
+          raw_unpack(r[u][k], v);
+#pragma unroll
+          for (int i = 0; i < 8; i++) { col[k][i] += v[i]; row[i] += v[i]; }
+        }
+      // reduce-scatter over the 32 lanes: lane bits 16 / 8 / 4 each keep one half of the channels, bits 2 / 1 finish the sum
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const bool up = (lane & 16) != 0;
+        const float got = __shfl_xor_sync(0xffffffffu, up ? row[i] : row[i + 4], 16);
+        row[i] = (up ? row[i + 4] : row[i]) + got;
+      }
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        const bool up = (lane & 8) != 0;
+        const float got = __shfl_xor_sync(0xffffffffu, up ? row[i] : row[i + 2], 8);
+        row[i] = (up ? row[i + 2] : row[i]) + got;
+      }
+      {
+        const bool up = (lane & 4) != 0;
+        const float got = __shfl_xor_sync(0xffffffffu, up ? row[0] : row[1], 4);
+        row[0] = (up ? row[1] : row[0]) + got;
+      }
+      row[0] += __shfl_xor_sync(0xffffffffu, row[0], 2);
+      row[0] += __shfl_xor_sync(0xffffffffu, row[0], 1);
+      if ((lane & 3) == 0) sm[yy * 16 + oct * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = row[0];
+    }
+  }
+  // columns: row groups 1..3 hand their partial sums to group 0
+  if (rg > 0) {
+#pragma unroll
+    for (int k = 0; k < NK; k++)
+      if (lane + 32 * k < x.w) {
+        float* d = smc + ((size_t)(rg - 1) * x.w + lane + 32 * k) * 16 + oct * 8;
+        *reinterpret_cast<float4*>(d) = make_float4(col[k][0], col[k][1], col[k][2], col[k][3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(col[k][4], col[k][5], col[k][6], col[k][7]);
+      }
+  }
+  __syncthreads();
+  if (rg == 0) {
+    T* cb = reinterpret_cast<T*>(colmean.ptr) + (int64_t)n * x.w * colmean.ld + c0 + oct * 8;
+    const float inv = 1.0f / (float)x.h;
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+      const int xx = lane + 32 * k;
+      if (xx < x.w) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = col[k][i];
+        for (int g = 0; g < 3; g++) {
+          const float* d = smc + ((size_t)g * x.w + xx) * 16 + oct * 8;
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] += d[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] *= inv;
+        store8(cb + (int64_t)xx * colmean.ld, v);
+      }
+    }
+  }
+  {
+    T* rb = reinterpret_cast<T*>(rowmean.ptr) + (int64_t)n * x.h * rowmean.ld + c0;
+    const float inv = 1.0f / (float)x.w;
+    for (int i = threadIdx.x; i < x.h * 2; i += blockDim.x) {
+      const int y = i >> 1, o = (i & 1) * 8;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = sm[y * 16 + o + j] * inv;
+      store8(rb + (int64_t)y * rowmean.ld + o, v);
+    }
+  }
+}
+
 template <typename T>
 __global__ void rowcol_gate_kernel(yad_tensor x, bool has_x, yad_tensor gh, yad_tensor gw, yad_tensor y) {
   pdl_sync();
@@ -1102,6 +1216,77 @@ __global__ void mlca_apply_kernel(yad_tensor x, const float* __restrict__ att, i
       for (int i = 0; i < 8; i++) v[i] += r[i];
     }
     store8(reinterpret_cast<T*>(y.ptr) + p * y.ld + o, v);
+  }
+}
+
+// Persistent variant in the style of rowcol_gate_kernel: a thread keeps its channel octet and walks pixels with a grid stride, four packed loads of
+// x (and of the residual) in flight per trip, 32-bit index arithmetic; the adaptive-pool bin bounds of every output row / column come from a
+// table built once per CTA in shared memory, the attention vectors (ls x ls x c floats per image) are read through L1.  History
+// (profiles/r2_pointwise.md): mlca_apply_kernel spends nine 64-bit integer divisions per 16 bytes (72 us for the 52 MB map of the P3 block); one
+// short CTA per output row with the y-reduced bins in shared memory was no faster (64 us: 5120 CTAs of ~7 us, each a chain of dependent loads).
+template <typename T>
+__global__ void __launch_bounds__(256) mlca_apply2_kernel(yad_tensor x, const float* __restrict__ att, int ls, const T* __restrict__ add, int add_ld,
+                                                          yad_tensor y) {
+  extern __shared__ int tb[];  // [h] y bins, [w] x bins: first | (last + 1) << 16
+  for (int i = threadIdx.x; i < x.h; i += blockDim.x) tb[i] = ((i * ls) / x.h) | ((((i + 1) * ls + x.h - 1) / x.h) << 16);
+  for (int i = threadIdx.x; i < x.w; i += blockDim.x) tb[x.h + i] = ((i * ls) / x.w) | ((((i + 1) * ls + x.w - 1) / x.w) << 16);
+  pdl_sync();
+  __syncthreads();
+  const int c = x.c, oct = c >> 3;
+  const int o = ((int)threadIdx.x % oct) * 8, pstep = (int)(gridDim.x * blockDim.x) / oct, hw = x.h * x.w, npix = x.n * hw;
+  const T* xp = reinterpret_cast<const T*>(x.ptr) + o;
+  T* yp = reinterpret_cast<T*>(y.ptr) + o;
+  const T* ap = add ? add + o : nullptr;
+  auto apply = [&](int p, float (&v)[8], const float (&r)[8]) {
+    const int n = p / hw, rem = p - n * hw, py = rem / x.w, px = rem - py * x.w;
+    const int by = tb[py], bx = tb[x.h + px], y0 = by & 0xFFFF, y1 = by >> 16, x0 = bx & 0xFFFF, x1 = bx >> 16;
+    const float* an = att + (int64_t)n * ls * ls * c + o;
+    float4 t0 = __ldg(reinterpret_cast<const float4*>(an + (y0 * ls + x0) * c)), t1 = __ldg(reinterpret_cast<const float4*>(an + (y0 * ls + x0) * c + 4));
+    const int cnt = (y1 - y0) * (x1 - x0);
+    if (cnt != 1) {  // several bins under this pixel (maps that ls does not divide, or smaller than ls)
+      t0 = make_float4(0.f, 0.f, 0.f, 0.f);
+      t1 = t0;
+      for (int yy = y0; yy < y1; yy++)
+        for (int xx = x0; xx < x1; xx++) {
+          const float4 u0 = __ldg(reinterpret_cast<const float4*>(an + (yy * ls + xx) * c)), u1 = __ldg(reinterpret_cast<const float4*>(an + (yy * ls + xx) * c + 4));
+          t0.x += u0.x; t0.y += u0.y; t0.z += u0.z; t0.w += u0.w; t1.x += u1.x; t1.y += u1.y; t1.z += u1.z; t1.w += u1.w;
+        }
+      const float inv = 1.0f / (float)cnt;
+      t0.x *= inv; t0.y *= inv; t0.z *= inv; t0.w *= inv; t1.x *= inv; t1.y *= inv; t1.z *= inv; t1.w *= inv;
+    }
+    v[0] = fmaf(v[0], t0.x, r[0]); v[1] = fmaf(v[1], t0.y, r[1]); v[2] = fmaf(v[2], t0.z, r[2]); v[3] = fmaf(v[3], t0.w, r[3]);
+    v[4] = fmaf(v[4], t1.x, r[4]); v[5] = fmaf(v[5], t1.y, r[5]); v[6] = fmaf(v[6], t1.z, r[6]); v[7] = fmaf(v[7], t1.w, r[7]);
+    store8(yp + (int64_t)p * y.ld, v);
+  };
+  int p = (int)(blockIdx.x * blockDim.x + threadIdx.x) / oct;
+  for (; p + 3 * pstep < npix; p += 4 * pstep) {
+    Raw8<T> rx[4], ra[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      raw_load(xp + (int64_t)(p + u * pstep) * x.ld, rx[u]);
+      if (ap) raw_load(ap + (int64_t)(p + u * pstep) * add_ld, ra[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      float v[8], r[8];
+      raw_unpack(rx[u], v);
+      if (ap) raw_unpack(ra[u], r);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) r[i] = 0.f;
+      }
+      apply(p + u * pstep, v, r);
+    }
+  }
+  for (; p < npix; p += pstep) {
+    float v[8], r[8];
+    load8(xp + (int64_t)p * x.ld, v);
+    if (ap) load8(ap + (int64_t)p * add_ld, r);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) r[i] = 0.f;
+    }
+    apply(p, v, r);
   }
 }
 
@@ -1674,6 +1859,21 @@ int yad_rowcol_mean(const yad_tensor* x, const yad_tensor* rowmean, const yad_te
   CHECK_VIEW(colmean, "rowcol_mean cols");
   YAD_CHECK(rowmean->c == x->c && colmean->c == x->c, "rowcol_mean: channel mismatch");
   cudaStream_t st = (cudaStream_t)stream;
+  static int rc1 = -1;
+  if (rc1 < 0) { const char* ev = getenv("YAD_ROWCOL_1PASS"); rc1 = (ev && ev[0] == '0') ? 0 : 1; }
+  const size_t rc_smem = ((size_t)x->h * 16 + (size_t)3 * x->w * 16) * sizeof(float);
+  if (rc1 && x->c % 16 == 0 && x->w <= 160 && rc_smem <= 48 * 1024 && (rowmean->ld % 8) == 0 && (colmean->ld % 8) == 0) {
+    const unsigned g1 = (unsigned)(x->n * (x->c / 16));
+    const int nk = (x->w + 31) / 32;
+    YAD_DISPATCH_DTYPE(dtype, {
+      if (nk <= 1) YAD_LAUNCH((rowcol_mean1_kernel<T, 1>), g1, 256, rc_smem, st, *x, *rowmean, *colmean);
+      else if (nk == 2) YAD_LAUNCH((rowcol_mean1_kernel<T, 2>), g1, 256, rc_smem, st, *x, *rowmean, *colmean);
+      else if (nk == 3) YAD_LAUNCH((rowcol_mean1_kernel<T, 3>), g1, 256, rc_smem, st, *x, *rowmean, *colmean);
+      else YAD_LAUNCH((rowcol_mean1_kernel<T, 5>), g1, 256, rc_smem, st, *x, *rowmean, *colmean);
+    })
+    YAD_LAUNCH_CHECK("rowcol_mean");
+    return 0;
+  }
   dim3 grid(x->h > x->w ? x->h : x->w, x->n, 2);
   int tpb = (x->c / 8) * 8;  // 8 pixel lanes per octet
   tpb = tpb < 64 ? 64 : (tpb > 256 ? 256 : tpb);
@@ -1748,6 +1948,14 @@ int yad_mlca_apply(const yad_tensor* x, const float* att, int local_size, const 
   SAME_SHAPE(x, y, "mlca_apply");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)x->n * x->h * x->w * (x->c / 8);
+  const int oct_ = x->c / 8;
+  const size_t tb_smem = (size_t)(x->h + x->w) * sizeof(int);
+  if (oct_ > 0 && 256 % oct_ == 0 && total < ((int64_t)1 << 31) && x->h < 32768 && x->w < 32768 && local_size <= 1024 && tb_smem <= 48 * 1024 && total > 0 &&
+      (!add || ((uintptr_t)add & 15) == 0)) {
+    YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(mlca_apply2_kernel<T>, grid_for(total), 256, tb_smem, st, *x, att, local_size, (const T*)add, add_ld, *y);)
+    YAD_LAUNCH_CHECK("mlca_apply");
+    return 0;
+  }
   YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(mlca_apply_kernel<T>, grid_for(total), TPB, 0, st, *x, att, local_size, (const T*)add, add_ld, *y);)
   YAD_LAUNCH_CHECK("mlca_apply");
   return 0;
