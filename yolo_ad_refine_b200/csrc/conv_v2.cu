@@ -934,6 +934,9 @@ static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilog
     p.a_tx_bytes = (uint32_t)(p.pw * (V2_BH + 2) * 128);
     p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
     p.total_tiles = p.n * p.tiles_x * p.tiles_y * p.tiles_n;
+    // few tiles per CTA (20 x 20 maps at batch 64: 2.6): loading the whole weight matrix up front does not pay and the fixed 16 x 8 tile wastes half
+    // of its rows; conv_tma_kernel with its fitted patch measured 8.1 us against 12.1 us here (profiles/r2_launch_floor_20.jsonl)
+    if (p.total_tiles < 5 * 148 && d->impl != 4) return 0;
   } else {
     p.tiles_x = p.tiles_y = 1;
     p.a_tx_bytes = V2_BM * 128;
