@@ -222,8 +222,8 @@ def measure_training(args, world, rank, sd, dtype, W, barrier, B=None, scaling="
         decomp = {"compute_ms": float(np.mean([e[0].elapsed_time(e[1]) for e in evs[1:]])),
                   "allreduce_ms": float(np.mean([e[1].elapsed_time(e[2]) for e in evs[1:]])),
                   "optimizer_ms": float(np.mean([e[2].elapsed_time(e[3]) for e in evs[1:]])),
-                  "note": "rank 0; all-reduce = NCCL wire time + waiting for the slowest rank's backward; BatchNorm buffers are not exchanged per step "
-                          "(train-mode BatchNorm does not read them; rank 0's are the ones checkpointed)"}
+                  "note": "rank 0; allreduce_ms = NCCL SUM all-reduce of the 16.4 MB fp32 gradient arena + rank-0 broadcast of the BatchNorm buffers "
+                          "(DDP semantics) + waiting for the slowest rank's backward"}
     # roofline of the training step's dominant kernels, measured live: one instrumented EAGER step, CUDA events around every libyad entry point
     torch.cuda.synchronize()
     img, tg = eng._s_img, (eng._s_bi, eng._s_cls, eng._s_box)
