@@ -27,6 +27,7 @@ int yad_conv2d_simt(const yad_tensor* x, const void* w, const yad_conv_desc* d, 
 int yad_conv2d_tc(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream);
 int yad_conv2d_tc_supported(const yad_tensor* x, const yad_conv_desc* d, const yad_tensor* y);
 int yad_conv2d_small(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream);
+int yad_conv2d_c3(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream);
 
 extern "C" {
 
@@ -49,6 +50,11 @@ int yad_conv2d(const yad_tensor* x, const void* w, const yad_conv_desc* d, const
                void* stream) {
   YAD_CHECK(x && w && d && e && y && x->ptr && y->ptr, "conv2d: null argument");
   int impl = d->impl;
+  if ((impl == 0 || impl == 6) && dtype == YAD_BF16) {  // 3x3 stride-1 convolutions with <= 32 channels: tcgen05 straight on a no-swizzle patch (conv_v2.cu)
+    const int r = yad_conv2d_c3(x, w, d, e, y, stream);
+    if (r >= 0) return r;
+    YAD_CHECK(impl != 6, "conv2d: impl 6 (small-channel tcgen05 kernel) does not cover this call");
+  }
   if (impl == 0 && dtype == YAD_BF16) {  // HBM-bound 3x3 convolutions with <= 32 channels: single-pass mma.sync kernel (conv_small.cu)
     const int r = yad_conv2d_small(x, w, d, e, y, stream);
     if (r >= 0) return r;

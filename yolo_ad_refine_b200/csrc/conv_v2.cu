@@ -97,6 +97,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src
                "r"(c3)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(tm),
+               "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ float v2_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -562,6 +567,131 @@ __global__ void __launch_bounds__(V2_MAX_THREADS, 1) conv2_kernel(const __grid_c
   } else {
     // ================= epilogue warps =================
     v2_epilogue<PATCH, ACT, MULADD, GN, SCALE>(p, &tmY, base, tmem_base, warp, lane, tfull_bar(0), tempty_bar(0));
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// =====================================================================================================================
+// Small-channel 3x3 stride-1 convolution (cin, cout in {8, 16, 32}): the C3k2 bottlenecks of the first stages.
+// conv2_kernel spends a 128-byte swizzled row per pixel on 16 - 64 bytes of data; conv_small_kernel (mma.sync) is instruction-bound: 33 M warp
+// instructions for 1.0 M MMAs at 8 -> 16 @160^2 (profiles/r2_ncu_conv_v2.md).  Here the haloed patch (18 rows x 10 pixels) is staged by ONE TMA
+// box per tile and the tensor core reads it in place:
+//   cin = 8   no swizzle: in the K-major no-swizzle canonical layout a core matrix is 8 rows x 16 bytes stored contiguously, and the 8 pixels of an
+//             output row ARE 8 contiguous 16-byte chunks of the patch.  An A descriptor starts anywhere in the patch (tap shift = pixel offset), its
+//             stride-byte-offset (between 8-row groups) is one patch row = 160 bytes, and its leading-byte-offset (between the two 16-byte K chunks
+//             of a K = 16 step) is whatever separates the two TAPS the step covers: +16 bytes for horizontally adjacent taps, +128 for the row
+//             wrap -- five MMAs per 128 pixels, no im2col copy.  Dense inputs (ld == 8) merge the pixel and channel axes: a patch row is one
+//             160-byte TMA line.
+//   cin = 16 / 32   SWIZZLE_32B / SWIZZLE_64B rows of one pixel each (one / two K steps per tap), stride-byte-offset = one patch row.
+// The weights are laid out once per CTA in the no-swizzle canonical form ([step][K chunk][8-row group][8 rows][16 bytes]; every descriptor carries
+// its own layout type).  Epilogue: v2_epilogue in tile-split mode.  Two CTAs per SM.
+constexpr int C3_MAX_MMA = 18;   // 9 taps x 32 channels / 16
+constexpr int C3_PLANE_BYTES = 18 * 10 * 16, C3_PLANE_STRIDE = 2944;  // 2880 rounded up to 128 (TMA destination alignment)
+struct C3Params {
+  V2Params v;
+  int nmma;
+  int dense;                            // cin = 8 and x.ld == 8: one patch row (10 pixels) is ONE 160-byte TMA line of the merged (w * 8) axis
+  uint32_t a_hi;                        // high descriptor word of the A operand (stride-byte-offset = one patch row, layout type)
+  uint32_t tx_bytes;
+  uint32_t stage_bytes, off_w;          // A stage; weights
+  uint32_t a_off[C3_MAX_MMA], a_lbo[C3_MAX_MMA];
+  uint32_t b_mma_bytes, b_lbo;
+  const bf16* w;
+  int w_row;                            // 9 * cin
+};
+
+template <int ACT, bool MULADD>
+__global__ void __launch_bounds__(320, 2) conv3_kernel(const __grid_constant__ C3Params cp, const __grid_constant__ CUtensorMap tmA,
+                                                       const __grid_constant__ CUtensorMap tmY) {
+  extern __shared__ uint8_t smem_raw[];
+  const V2Params& p = cp.v;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + p.off_bars;
+  auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(p.stages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (uint32_t)(2 * p.stages + V2_MAX_ACC + a); };
+  const uint32_t tmem_ptr_addr = bars + 8u * (uint32_t)(2 * p.stages + 2 * V2_MAX_ACC);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < p.acc_stages; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4u); }
+    fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  pdl_sync();
+  {  // bias table and the weights in canonical no-swizzle K-major form: chunk jc = K columns [8 jc, 8 jc + 8) of the [cout][9 cin] matrix
+    float* bs = reinterpret_cast<float*>(smem_raw + (base + p.off_bias - raw));
+    for (int i = tid; i < p.n_tile; i += (int)blockDim.x) bs[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
+    uint8_t* wsm = smem_raw + (base + cp.off_w - raw);
+    const int nchunk = cp.w_row >> 3;
+    for (int i = tid; i < cp.nmma * 2 * p.n_tile; i += (int)blockDim.x) {
+      const int n = i % p.n_tile, jc = i / p.n_tile;  // jc = 2 * step + chunk-in-step
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (n < p.cout && jc < nchunk) v = *reinterpret_cast<const uint4*>(cp.w + (int64_t)n * cp.w_row + jc * 8);
+      *reinterpret_cast<uint4*>(wsm + (size_t)(jc >> 1) * cp.b_mma_bytes + (size_t)(jc & 1) * cp.b_lbo + (size_t)(n >> 3) * 128 + (size_t)(n & 7) * 16) = v;
+    }
+  }
+  fence_proxy_async();  // generic-proxy writes of the weights -> visible to the tensor core's async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    const bool leader = elect_one();
+    V2TileIter ti;
+    ti.init(p, (int)blockIdx.x, (int)gridDim.x);
+    V2Ring sr;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ti.next(p), sr.next(p.stages)) {
+      const int s = sr.idx;
+      const uint32_t a_s = base + p.off_a + (uint32_t)s * cp.stage_bytes;
+      mbar_wait(empty_bar(s), sr.ph ^ 1u);
+      if (leader) {
+        mbar_expect_tx(full_bar(s), cp.tx_bytes);
+        if (cp.dense) tma_load_3d(a_s, &tmA, full_bar(s), (ti.tx * V2_BW - 1) * 8, ti.ty * V2_BH - 1, ti.img);
+        else tma_load_4d(a_s, &tmA, full_bar(s), 0, ti.tx * V2_BW - 1, ti.ty * V2_BH - 1, ti.img);
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader_lane = elect_one();
+    const bool leader = leader_lane && !(p.dbg & 1);
+    const uint32_t idesc = v2_idesc(p.n_tile);
+    const uint32_t a_hi = cp.a_hi, b_hi = (128u >> 4) | (1u << 14);  // weights: no swizzle, SBO = one 8-row group
+    const uint32_t b_lo0 = ((base + cp.off_w) & 0x3FFFFu) >> 4, b_lbo = (cp.b_lbo >> 4) << 16, b_step = cp.b_mma_bytes >> 4;
+    V2Ring sr, ar;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, sr.next(p.stages), ar.next(p.acc_stages)) {
+      const int acc = ar.idx, s = sr.idx;
+      mbar_wait(tempty_bar(acc), ar.ph ^ 1u);
+      mbar_wait(full_bar(s), sr.ph);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
+      const uint32_t a_s = base + p.off_a + (uint32_t)s * cp.stage_bytes;
+      if (leader) {
+        for (int i = 0; i < cp.nmma; i++) {
+          const uint32_t a_lo = (((a_s + cp.a_off[i]) & 0x3FFFFu) >> 4) | ((cp.a_lbo[i] >> 4) << 16);
+          const uint32_t b_lo = (b_lo0 + (uint32_t)i * b_step) | b_lbo;
+          umma_f16(d_tmem, pack64(a_lo, a_hi), pack64(b_lo, b_hi), idesc, i > 0 ? 1u : 0u);
+        }
+      }
+      if (leader_lane) {
+        umma_commit(empty_bar(s));
+        umma_commit(tfull_bar(acc));
+      }
+    }
+    __syncwarp();
+    tc_fence_before();
+  } else {
+    v2_epilogue<true, ACT, MULADD, false, false>(p, &tmY, base, tmem_base, warp, lane, tfull_bar(0), tempty_bar(0));
   }
   __syncthreads();
   if (warp == 1) {
@@ -1038,6 +1168,132 @@ int yad_conv2d_v2(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
   int grid = num_sms < p.total_tiles ? num_sms : p.total_tiles;
   if (patch) return v2_dispatch<true>(p, tmA, tmB, tmY, grid, smem, st);
   return v2_dispatch<false>(p, tmA, tmB, tmY, grid, smem, st);
+}
+
+// Small-channel 3x3 stride-1 convolution on conv3_kernel.  Returns -1 when the call is not covered (the caller goes on to conv_small_kernel /
+// the generic kernels), 0 when the launch was issued, > 0 on error.
+template <int ACT, bool MULADD>
+static int c3_launch_t(const C3Params& cp, const CUtensorMap& tmA, const CUtensorMap& tmY, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv3_kernel<ACT, MULADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024) != cudaSuccess) {
+      yad_set_error("conv2d (small-channel tcgen05): cannot raise the dynamic shared memory limit");
+      return 2;
+    }
+    attr_set = true;
+  }
+  YAD_LAUNCH((conv3_kernel<ACT, MULADD>), grid, 320, smem, st, cp, tmA, tmY);
+  YAD_LAUNCH_CHECK("conv2d (small-channel tcgen05)");
+  return 0;
+}
+
+int yad_conv2d_c3(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream) {
+  static int on = -1;
+  if (on < 0) on = v2_env("YAD_CONV_C3", 1);
+  if (!on || !get_encode()) return -1;
+  if (d->mode != YAD_CONV_NORMAL || d->kh != 3 || d->kw != 3 || d->pad_h != 1 || d->pad_w != 1 || d->stride != 1) return -1;
+  if (!(x->c == 8 || x->c == 16 || x->c == 32) || !(y->c == 8 || y->c == 16 || y->c == 32)) return -1;
+  if ((x->ld % 8) || (y->ld % 8) || ((uintptr_t)x->ptr & 15) || ((uintptr_t)y->ptr & 15) || ((uintptr_t)w & 15)) return -1;
+  if (y->h != x->h || y->w != x->w || y->n != x->n) return -1;
+  if (e->img_scale || e->pix_scale || e->mul || e->gn_stats) return -1;
+  if (e->add && (((uintptr_t)e->add & 15) || (e->add_ld % 8))) return -1;
+  const int64_t M = (int64_t)x->n * x->h * x->w;
+  if (M + V2_BM >= (int64_t)1 << 31) return -1;
+  C3Params cp;
+  memset(&cp, 0, sizeof(cp));
+  V2Params& p = cp.v;
+  p.n = x->n; p.hm = y->h; p.wm = y->w; p.hw = y->h * y->w; p.cin = x->c; p.cout = y->c; p.m_total = (int)M;
+  p.n_tile = y->c < 16 ? 16 : y->c;
+  p.tiles_n = 1; p.ntaps = 9; p.kpt = 1; p.ksplit = 1;
+  p.tiles_x = (p.wm + V2_BW - 1) / V2_BW;
+  p.tiles_y = (p.hm + V2_BH - 1) / V2_BH;
+  p.total_tiles = p.n * p.tiles_x * p.tiles_y;
+  if (p.total_tiles < 4 * 148) return -1;  // small maps: the per-CTA weight layout pass does not amortise
+  p.ew = 8; p.tsplit = 2; p.stg_bufs = 2;
+  p.acc_stages = 256 / p.n_tile < V2_MAX_ACC ? 256 / p.n_tile : V2_MAX_ACC;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.acc_stages * p.n_tile) p.tmem_cols <<= 1;
+  for (int i = 0; i <= 4; i++) p.bnd[i] = i == 0 ? 0 : p.n_tile;
+  p.sc = p.n_tile;  // 16 or 32 columns per store box
+  p.stg_warp_bytes = 32u * (uint32_t)p.sc * 2u;
+  {
+    static int dbg_env = -1;
+    if (dbg_env < 0) dbg_env = v2_env("YAD_CONV2_DBG", 0);
+    p.dbg = dbg_env;
+  }
+  // A-operand layout by input width (see the kernel's header)
+  const int nchunk = 9 * (x->c / 8);  // 16-byte K chunks of the weight rows
+  cp.nmma = (nchunk + 1) / 2;
+  if (x->c == 8) {
+    cp.dense = x->ld == 8;
+    for (int i = 0; i < cp.nmma; i++) {
+      const int t0 = 2 * i, t1 = 2 * i + 1;
+      cp.a_off[i] = (uint32_t)(((t0 / 3) * 10 + (t0 % 3)) * 16);
+      cp.a_lbo[i] = t1 < 9 ? (uint32_t)(((t1 / 3) * 10 + (t1 % 3)) * 16) - cp.a_off[i] : 0u;  // the odd last step re-reads its own chunk against zero weights
+    }
+    cp.a_hi = (160u >> 4) | (1u << 14);
+    cp.tx_bytes = C3_PLANE_BYTES;
+    cp.stage_bytes = C3_PLANE_STRIDE;
+  } else {
+    const uint32_t rb = (uint32_t)x->c * 2u;  // 32 or 64 bytes per pixel row
+    for (int i = 0; i < cp.nmma; i++) {
+      const int t = x->c == 16 ? i : i / 2, half = x->c == 16 ? 0 : i % 2;
+      cp.a_off[i] = (uint32_t)((t / 3) * 10 + (t % 3)) * rb + (uint32_t)half * 32u;
+      cp.a_lbo[i] = 16u;  // unused by the swizzled K-major layouts
+    }
+    cp.a_hi = ((10u * rb) >> 4) | (1u << 14) | ((x->c == 16 ? 6u : 4u) << 29);
+    cp.tx_bytes = 180u * rb;
+    cp.stage_bytes = (cp.tx_bytes + 1023u) & ~1023u;
+  }
+  cp.b_lbo = (uint32_t)(p.n_tile / 8) * 128u;
+  cp.b_mma_bytes = 2u * cp.b_lbo;
+  cp.w = (const bf16*)w;
+  cp.w_row = 9 * x->c;
+  p.stages = 6;
+  while (p.stages > 3 && 1024u + (uint32_t)p.stages * cp.stage_bytes + (uint32_t)cp.nmma * cp.b_mma_bytes + 1024u + (uint32_t)(p.ew * p.stg_bufs) * p.stg_warp_bytes + 512u > 112u * 1024u)
+    p.stages--;
+  p.off_a = 0;
+  cp.off_w = p.off_a + (uint32_t)p.stages * cp.stage_bytes;
+  cp.off_w = (cp.off_w + 127u) & ~127u;
+  p.off_stg = (cp.off_w + (uint32_t)cp.nmma * cp.b_mma_bytes + 1023u) & ~1023u;
+  p.off_bias = p.off_stg + (uint32_t)(p.ew * p.stg_bufs) * p.stg_warp_bytes;
+  p.off_bars = p.off_bias + 128u;
+  const size_t smem = 1024 + p.off_bars + 8u * (2u * (uint32_t)p.stages + 2u * V2_MAX_ACC) + 16u;
+  if (smem > 112 * 1024) return -1;
+  p.bias = e->bias; p.act = e->act; p.alpha = e->alpha;
+  p.add = (const bf16*)e->add; p.add_ld = e->add_ld;
+  CUtensorMap tmA, tmY;
+  if (cp.dense) {
+    uint64_t dims[3] = {(uint64_t)x->w * 8, (uint64_t)x->h, (uint64_t)x->n};
+    uint64_t strides[2] = {(uint64_t)x->w * 16, (uint64_t)x->h * x->w * 16};
+    uint32_t box[3] = {80, (uint32_t)(V2_BH + 2), 1};
+    if (v2_make_map(&tmA, x->ptr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+  } else {
+    uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
+    uint64_t strides[3] = {(uint64_t)x->ld * 2, (uint64_t)x->w * x->ld * 2, (uint64_t)x->h * x->w * x->ld * 2};
+    uint32_t box[4] = {(uint32_t)x->c, 10, (uint32_t)(V2_BH + 2), 1};
+    const CUtensorMapSwizzle sw = x->c == 8 ? CU_TENSOR_MAP_SWIZZLE_NONE : (x->c == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (v2_make_map(&tmA, x->ptr, 4, dims, strides, box, sw)) return 1;
+  }
+  {
+    const CUtensorMapSwizzle sw = p.sc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    uint64_t dims[4] = {(uint64_t)y->c, (uint64_t)y->w, (uint64_t)y->h, (uint64_t)y->n};
+    uint64_t strides[3] = {(uint64_t)y->ld * 2, (uint64_t)y->w * y->ld * 2, (uint64_t)y->h * y->w * y->ld * 2};
+    uint32_t box[4] = {(uint32_t)p.sc, V2_BW, 4, 1};
+    if (v2_make_map(&tmY, y->ptr, 4, dims, strides, box, sw)) return 1;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int grid = 2 * num_sms < p.total_tiles ? 2 * num_sms : p.total_tiles;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool muladd = e->add != nullptr;
+  if (e->act == YAD_ACT_SILU) return muladd ? c3_launch_t<YAD_ACT_SILU, true>(cp, tmA, tmY, grid, smem, st) : c3_launch_t<YAD_ACT_SILU, false>(cp, tmA, tmY, grid, smem, st);
+  if (e->act == YAD_ACT_NONE) return muladd ? c3_launch_t<YAD_ACT_NONE, true>(cp, tmA, tmY, grid, smem, st) : c3_launch_t<YAD_ACT_NONE, false>(cp, tmA, tmY, grid, smem, st);
+  return c3_launch_t<ACT_GENERIC, true>(cp, tmA, tmY, grid, smem, st);
 }
 
 // Fused deformable 3x3 convolution (dcn2_kernel).  Returns -1 when the call is not eligible (the caller falls back to conv_tc_kernel<DEFORM>).
