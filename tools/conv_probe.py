@@ -19,6 +19,9 @@ x = Act(torch.randn(n, hw, hw, cin, device=dev).to(dt))
 cw = pack_conv(torch.randn(cout, cin, k, k) / (cin * k * k) ** 0.5, torch.randn(cout) * 0.1, dt, dev, s)
 ho = (hw + 2 * (k // 2) - k) // s + 1
 y = Act.empty(n, ho, ho, cw.cout, dt, dev)
+if os.environ.get("SLICE") == "1":  # output = a channel window of a wider (concat) buffer
+    y = Act.empty(n, ho, ho, cw.cout + 32, dt, dev).slice(16, cw.cout)
+add = Act(torch.randn(n, ho, ho, cw.cout, device=dev).to(dt)) if os.environ.get("ADD") == "1" else None
 flops = 2.0 * n * ho * ho * cw.cout * k * k * cin
 byts = 2.0 * (x.buf.numel() + y.buf.numel() + cw.w.numel())
 deform = os.environ.get("DEFORM") == "1"
@@ -26,12 +29,12 @@ om = Act((torch.randn(n, hw, hw, 32, device=dev) * float(os.environ.get("DEFORM_
 mode = ops.CONV_DEFORM if deform else ops.CONV_NORMAL
 for impl in impls:
     for _ in range(3):
-        ops.conv2d(x, cw.w, y, bias=cw.b, kh=k, kw=k, stride=s, pad_h=k // 2, pad_w=k // 2, act=ops.ACT_SILU, impl=impl, mode=mode, offmask=om)
+        ops.conv2d(x, cw.w, y, bias=cw.b, kh=k, kw=k, stride=s, pad_h=k // 2, pad_w=k // 2, act=ops.ACT_SILU, impl=impl, mode=mode, offmask=om, add=add)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(reps):
-        ops.conv2d(x, cw.w, y, bias=cw.b, kh=k, kw=k, stride=s, pad_h=k // 2, pad_w=k // 2, act=ops.ACT_SILU, impl=impl, mode=mode, offmask=om)
+        ops.conv2d(x, cw.w, y, bias=cw.b, kh=k, kw=k, stride=s, pad_h=k // 2, pad_w=k // 2, act=ops.ACT_SILU, impl=impl, mode=mode, offmask=om, add=add)
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps

@@ -275,7 +275,7 @@ __device__ __forceinline__ void epi_unit(const V2Params& p, uint32_t taddr, uint
 // The epilogue of one warp over all tiles of its CTA (shared by conv2_kernel and dcn2_kernel): TMEM -> scale / bias / activation (-> GroupNorm
 // partial sums) -> bf16 -> swizzled staging tile -> optional mul / add on the staged tile -> bulk tensor store.  tfull0 / tempty0: shared-memory
 // addresses of the accumulator-full / accumulator-empty mbarrier pairs.
-template <bool PATCH, int ACT, bool MULADD, bool GN, bool SCALE>
+template <bool PATCH, int ACT, bool MULADD, bool GN, bool SCALE, bool PRE = false>
 __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap* tmY, uint32_t base, uint32_t tmem_base, int warp, int lane, uint32_t tfull0,
                                             uint32_t tempty0) {
   const int per_img = p.tiles_x * p.tiles_y;
@@ -326,6 +326,25 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
           if (p.pix_scale) rsc *= __bfloat162float(p.pix_scale[(int64_t)dp * p.pix_scale_ld]);
         }
       }
+      // conv3_kernel (PRE): the residual rows of this warp are fetched BEFORE the wait for the accumulator, so their global latency runs under the
+      // MMAs instead of inside the per-tile epilogue chain (the bottleneck adds doubled the kernel's time: 37 -> 65 us at 8 -> 16 @160^2)
+      constexpr bool PREFETCH = PRE && MULADD && !GN && !SCALE;
+      uint4 pav[4];
+      bool pre = false;
+      if constexpr (PREFETCH) {
+        if (p.add && !p.mul && ce - cb == p.sc && cpr <= 4) {
+          pre = true;
+          const int co = n0 + cb + cj * 8;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            pav[k] = make_uint4(0u, 0u, 0u, 0u);
+            const int row = rr0 + k * rpp;
+            if (k >= cpr || co >= p.cout) continue;
+            const int oy = ty0 + 4 * q + (row >> 3), ox = tx0 + (row & 7);
+            if (oy < p.hm && ox < p.wm) pav[k] = __ldg(reinterpret_cast<const uint4*>(p.add + ((int64_t)(img * p.hm + oy) * p.wm + ox) * p.add_ld + co));
+          }
+        }
+      }
       const int acc = ar.idx;
       mbar_wait((tfull0 + 8u * (uint32_t)acc), ar.ph);
       tc_fence_after();
@@ -353,8 +372,25 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
           __syncwarp();
           if (lane == 0) mbar_arrive((tempty0 + 8u * (uint32_t)acc));
         }
+        if constexpr (PREFETCH) {
+          if (pre) {  // rows outside the map hold zeros in pav and are clipped by the bulk store
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              if (k >= cpr) continue;
+              const uint32_t ra = stg + (uint32_t)(rr0 + k * rpp) * RB;
+              const uint32_t ca = ra + ((((uint32_t)cj) ^ ((ra >> 7) & swz)) << 4);
+              uint4 u = lds16(ca);
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+              const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&pav[k]);
+#pragma unroll
+              for (int e = 0; e < 4; e++) h[e] = __hadd2(h[e], ha[e]);
+              sts16v(ca, u);
+            }
+          }
+        }
         if constexpr (MULADD) {
-          if (p.mul || p.add) {
+          if ((p.mul || p.add) && !pre) {
             __syncwarp();
             const int co = n0 + c0 + cj * 8;
             if (co < p.cout) {
@@ -691,7 +727,7 @@ __global__ void __launch_bounds__(320, 2) conv3_kernel(const __grid_constant__ C
     __syncwarp();
     tc_fence_before();
   } else {
-    v2_epilogue<true, ACT, MULADD, false, false>(p, &tmY, base, tmem_base, warp, lane, tfull_bar(0), tempty_bar(0));
+    v2_epilogue<true, ACT, MULADD, false, false, true>(p, &tmY, base, tmem_base, warp, lane, tfull_bar(0), tempty_bar(0));
   }
   __syncthreads();
   if (warp == 1) {
