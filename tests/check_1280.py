@@ -30,7 +30,7 @@ np.testing.assert_array_equal(det[0].cpu().numpy(), ref)
 print("NMS rows bit-exact:", det[0].shape[0])
 del eng
 eng = RefineEngine(sd, batch=4, imgsz=1280, dtype=torch.bfloat16, nms_args=dict(conf_thres=0.25, iou_thres=0.7, max_det=300), input_u8=True)
-eng.img.copy_(torch.randint(0, 256, (4, 3, 1280, 1280), dtype=torch.uint8))
+eng.fill_inputs(torch.randint(0, 256, (4, 3, 1280, 1280), dtype=torch.uint8).cuda())
 for _ in range(5):
     eng.step()
 torch.cuda.synchronize()

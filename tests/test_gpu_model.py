@@ -117,12 +117,20 @@ def test_module_mirrors_forward_matches_reference_golden(gold, state_dict):
         model.train()(img)
 
 
-def test_engine_streaming_detect_many_matches_detect(state_dict):
-    eng = RefineEngine(state_dict, batch=2, imgsz=160, dtype=torch.float32, conv_impl=1, input_u8=True)
+@pytest.mark.parametrize("overlap", [True, False])
+def test_engine_streaming_detect_many_matches_detect(state_dict, overlap):
+    """streaming API against one-batch-at-a-time detect(): seven DIFFERENT batches, with two batches in flight (own input / forward stream per
+    buffer set, results through a pinned ring two batches late) and with one; every batch must come back in order with its own detections"""
+    eng = RefineEngine(state_dict, batch=2, imgsz=160, dtype=torch.float32, conv_impl=1, input_u8=True, overlap_batches=overlap)
     rs = np.random.RandomState(0)
-    batches = [torch.from_numpy(rs.randint(0, 256, (2, 3, 160, 160), dtype=np.uint8)).pin_memory() for _ in range(3)]
+    batches = [torch.from_numpy(rs.randint(0, 256, (2, 3, 160, 160), dtype=np.uint8)).pin_memory() for _ in range(7)]
+    for k, b in enumerate(batches):  # make the batches clearly different from one another
+        b[:, :, : 20 * (k + 1)] //= (k + 2)
     ref = [[d.cpu().numpy() for d in eng.detect(b)] for b in batches]
+    assert len({r[0].shape[0] for r in ref}) > 1 or len({float(r[0][0, 4]) for r in ref if r[0].shape[0]}) > 1  # the references differ
+    got = 0
     for (dh, ch), r in zip(eng.detect_many(batches), ref):
+        got += 1
         for i in range(2):
             # reductions use floating-point atomics, so two runs agree to rounding: a detection sitting exactly on the confidence / IoU
             # threshold may flip, hence counts within 2 and the leading rows compared by score
@@ -130,6 +138,7 @@ def test_engine_streaming_detect_many_matches_detect(state_dict):
             assert abs(k - r[i].shape[0]) <= 2
             m = min(k, r[i].shape[0], 10)
             np.testing.assert_allclose(dh[i, :m, 4].numpy(), r[i][:m, 4], rtol=1e-3, atol=1e-3)
+    assert got == len(batches)
 
 
 @pytest.mark.parametrize("size,batch", [(320, 3), (1280, 1), (160, 1)])

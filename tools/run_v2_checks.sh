@@ -1,10 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_conv_c3.py tests/test_gpu_conv_v2.py -q -x 2>&1 | tail -3
-for shape in "8 16 3 1 160" "16 32 3 1 80"; do
-  echo "== $shape plain"; python tools/conv_probe.py $shape 64 20 6 2>&1 | tail -1
-  echo "== $shape add"; ADD=1 python tools/conv_probe.py $shape 64 20 6 2>&1 | tail -1
-  echo "== $shape slice"; SLICE=1 python tools/conv_probe.py $shape 64 20 6 2>&1 | tail -1
-  echo "== $shape add+slice"; ADD=1 SLICE=1 python tools/conv_probe.py $shape 64 20 6 2>&1 | tail -1
-done
+timeout 1500 python -m pytest tests/test_gpu_model.py tests/test_gpu_preprocess.py tests/test_gpu_data.py -q -x 2>&1 | tail -3
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 1 --steps 20 --warmup 3 --train-batch 0 --no-cpu-baseline 2>/dev/null | head -c 300; echo

@@ -13,10 +13,14 @@ from .weights import prepare
 class RefineEngine:
     """use_graph: the hot path is captured in CUDA graphs.  pipeline_nms: forward + decode and NMS are two graphs on two streams with
     double-buffered predictions, so the NMS of batch i (one CTA per image: a low-occupancy tail) runs under the forward pass of batch i + 1.
-    step() then only ENQUEUES a batch; join() (called by forward / detect / detect_many) orders the current stream after its results."""
+    step() then only ENQUEUES a batch; join() (called by forward / detect / detect_many) orders the current stream after its results.
+    overlap_batches (with pipeline_nms): the two buffer sets also own their input buffer and their forward stream, so TWO batches are in flight:
+    the latency-bound stretches of one batch (the 20 x 20 maps of layer 10, 52 launches at the launch floor) run beside the throughput-bound
+    convolutions of the other.  Every batch is still computed exactly as before (same graphs, same arithmetic); only the order in which the GPU
+    interleaves the kernels of consecutive batches changes."""
 
     def __init__(self, state_dict, batch, imgsz=640, dtype=torch.bfloat16, device="cuda", nc=80, reg_max=16, strides=(8, 16, 32),
-                 use_graph=True, conv_impl=0, nms_args=None, input_u8=False, pipeline_nms=True):
+                 use_graph=True, conv_impl=0, nms_args=None, input_u8=False, pipeline_nms=True, overlap_batches=True):
         if not torch.cuda.is_available():
             raise RuntimeError("RefineEngine needs a CUDA device: the YOLO-AD-Refine hot path has no CPU fallback")
         ops.lib()  # fail loudly now if libyad.so is missing
@@ -26,13 +30,25 @@ class RefineEngine:
         self.ctx = Fn.Ctx(prepare(state_dict, dtype, self.device), conv_impl)
         self.nms_args = dict(conf_thres=0.25, iou_thres=0.7, max_det=300)
         self.nms_args.update(nms_args or {})
-        self.img = torch.zeros((batch, 3, self.h, self.w), dtype=torch.uint8 if input_u8 else torch.float32, device=self.device)
+        self.use_graph = use_graph
+        self.pipeline_nms = pipeline_nms and use_graph
+        self.overlap_batches = overlap_batches and self.pipeline_nms
+        self._imgs = [torch.zeros((batch, 3, self.h, self.w), dtype=torch.uint8 if input_u8 else torch.float32, device=self.device)
+                      for _ in range(2 if self.overlap_batches else 1)]
         self.graph = None
         self.launches_per_step = None
         self._out = None
-        self.use_graph = use_graph
-        self.pipeline_nms = pipeline_nms and use_graph
         self._i = 0
+
+    @property
+    def img(self):
+        """the static input buffer the NEXT step() reads (with overlap_batches the two buffer sets alternate)"""
+        return self._imgs[self._i & 1] if self.overlap_batches else self._imgs[0]
+
+    def fill_inputs(self, x):
+        """the same batch into every input buffer (device-resident benchmarking: step() then needs no copy at all)"""
+        for t in self._imgs:
+            t.copy_(x, non_blocking=True)
 
     # -- one eager pass of the hot path on the static input buffer
     def _run(self):
@@ -55,10 +71,12 @@ class RefineEngine:
             self._gf, self._gn, self._bufs = [], [], []
             self._ev_f = [torch.cuda.Event() for _ in range(2)]
             self._ev_n = [torch.cuda.Event() for _ in range(2)]
+            self._ev_in = [torch.cuda.Event() for _ in range(2)]
+            self._fstreams = [torch.cuda.Stream(device=self.device) for _ in range(2)] if self.overlap_batches else None
             for b in range(2):  # two buffer sets: predictions of batch i are read by its NMS while batch i + 1 is being computed
                 gf = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gf):
-                    y, feats = Fn.forward_model(self.ctx, self.img)
+                    y, feats = Fn.forward_model(self.ctx, self._imgs[b if self.overlap_batches else 0])
                 gn = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gn):
                     det, det_idx, count = nms_raw(y, **self.nms_args)
@@ -66,6 +84,7 @@ class RefineEngine:
                 self._gn.append(gn)
                 self._bufs.append((y, feats, det, det_idx, count))
                 self._ev_n[b].record(torch.cuda.current_stream())
+                self._ev_f[b].record(torch.cuda.current_stream())
             self.graph = self._gf[0]
             self._out = self._bufs[0]
         elif self.use_graph:
@@ -83,9 +102,21 @@ class RefineEngine:
             b = self._i & 1
             self._i += 1
             main = torch.cuda.current_stream()
-            main.wait_event(self._ev_n[b])       # the NMS that last read this buffer set (two batches ago) is done
-            self._gf[b].replay()
-            self._ev_f[b].record(main)
+            if self.overlap_batches:
+                # this set's input was written on the current stream; its forward runs on the set's own stream, beside the other set's batch
+                fs = self._fstreams[b]
+                self._ev_in[b].record(main)
+                fs.wait_event(self._ev_in[b])
+                fs.wait_event(self._ev_n[b])   # the NMS that last read this buffer set (two batches ago) is done
+                with torch.cuda.stream(fs):
+                    self._gf[b].replay()
+                    self._ev_f[b].record(fs)
+                # the caller may refill the OTHER set's input next; that set's previous forward (one batch ago) must have consumed it
+                main.wait_event(self._ev_f[b ^ 1])
+            else:
+                main.wait_event(self._ev_n[b])       # the NMS that last read this buffer set (two batches ago) is done
+                self._gf[b].replay()
+                self._ev_f[b].record(main)
             with torch.cuda.stream(self._nms_stream):
                 self._nms_stream.wait_event(self._ev_f[b])
                 self._gn[b].replay()
@@ -172,6 +203,7 @@ class RefineEngine:
         nxt = next(it, None)
         i = 0
         pending = None
+        lag = []
         if nxt is not None:
             enqueue(0, nxt)
         while nxt is not None:
@@ -182,7 +214,21 @@ class RefineEngine:
             self.img.copy_(self._staging[i % 2], non_blocking=True)  # device-to-device into the graph's static input
             self._free[i % 2].record(main)
             _, _, det, _, count = self.step()
-            if self.pipeline_nms:
+            if self.overlap_batches:
+                # two batches in flight: the device -> host copy of batch i is enqueued right behind its NMS (pinned ring of three, so the host
+                # may still be reading batch i - 2 while batch i - 1 lands), and the host only ever WAITS for batch i - 2 -- it keeps a whole
+                # batch of enqueued work ahead of the GPU.  Results arrive in order, two batches late; the tail is flushed after the loop.
+                if not hasattr(self, "_ring"):
+                    self._ring = [(torch.empty_like(det_host).pin_memory(), torch.empty_like(cnt_host).pin_memory(), torch.cuda.Event()) for _ in range(3)]
+                dh, ch, ev = self._ring[i % 3]
+                with torch.cuda.stream(self._nms_stream):
+                    dh.copy_(det, non_blocking=True)
+                    ch.copy_(count, non_blocking=True)
+                    ev.record(self._nms_stream)
+                lag.append(i % 3)
+                if len(lag) > 2:
+                    yield self._take(lag.pop(0), det_host, cnt_host)
+            elif self.pipeline_nms:
                 # software pipeline: batch i is only enqueued here; the detections handed to the caller are those of batch i - 1, read back on
                 # the NMS stream while batch i computes (results arrive in order, one batch late; the last one is flushed after the loop)
                 if pending is not None:
@@ -194,8 +240,18 @@ class RefineEngine:
                 main.synchronize()  # the caller reads this batch's detections on the host
                 yield det_host, cnt_host
             i += 1
+        while lag:
+            yield self._take(lag.pop(0), det_host, cnt_host)
         if pending is not None:
             yield self._read_back(pending, det_host, cnt_host)
+
+    def _take(self, slot, det_host, cnt_host):
+        """wait for ring slot `slot` (its NMS and device -> host copy) and hand its rows to the caller's pinned tensors"""
+        dh, ch, ev = self._ring[slot]
+        ev.synchronize()
+        det_host.copy_(dh)
+        cnt_host.copy_(ch)
+        return det_host, cnt_host
 
     def _read_back(self, b, det_host, cnt_host):
         """D2H copy of buffer set b's detections on the NMS stream (ordered after its NMS), then a host wait on that stream only"""
