@@ -82,8 +82,8 @@ def make_config(args, world):
                         "forward + DFL decode + NMS(conf .25, iou .7, max_det 300), random-init synthetic weights",
             "global_batch": world * args.batch, "parallelism": f"batch-sharded replicas x{world}, no collective",
             "pipeline": ("one batch in flight: " if getattr(args, "no_overlap", False) else
-                         "two batches in flight (each buffer set has its own input, forward stream and CUDA graph; every batch is computed exactly as "
-                         "alone, the GPU interleaves the kernels of consecutive batches): ") +
+                         f"{getattr(args, 'in_flight', 2)} batches in flight (each buffer set has its own input, forward stream and CUDA graph; every batch "
+                         "is computed exactly as alone, the GPU interleaves the kernels of consecutive batches): ") +
                         "forward + decode of batch i + 1 overlaps the NMS of batch i (two CUDA graphs, NMS stream, double-buffered predictions)",
             "l2": "inputs + activations of one step (>1 GB) exceed the 126 MB L2; no explicit flush"}
 
@@ -353,6 +353,7 @@ def main():
     ap.add_argument("--imgsz", type=int, default=640)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=2, help="batches in flight (buffer sets with their own input, forward stream and graph)")
     ap.add_argument("--no-overlap", action="store_true", help="one batch in flight (forward graphs of consecutive batches on one stream)")
     ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the CPU reference arm (a bounded sample of the workload)")
     ap.add_argument("--train-batch", type=int, default=128, help="images per GPU of the training-step measurement (0 = skip)")
@@ -378,7 +379,7 @@ def main():
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     W = max(args.warmup, 3)
     sd = synth.make_state_dict(seed=1)
-    eng = RefineEngine(sd, batch=args.batch, imgsz=args.imgsz, dtype=dtype, nms_args=NMS_ARGS, input_u8=True, overlap_batches=not args.no_overlap)
+    eng = RefineEngine(sd, batch=args.batch, imgsz=args.imgsz, dtype=dtype, nms_args=NMS_ARGS, input_u8=True, overlap_batches=False if args.no_overlap else args.in_flight)
     rs = np.random.RandomState(100 + rank)
     host_u8 = torch.from_numpy(rs.randint(0, 256, (args.batch, 3, args.imgsz, args.imgsz), dtype=np.uint8)).pin_memory()
     eng.fill_inputs(host_u8)

@@ -1,6 +1,11 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_model.py tests/test_gpu_preprocess.py tests/test_gpu_data.py -q -x 2>&1 | tail -3
-timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 1 --steps 20 --warmup 3 --train-batch 0 --no-cpu-baseline 2>/dev/null | head -c 300; echo
+for nf in 2 3 4; do
+timeout 600 python bench.py --steps 40 --warmup 4 --train-batch 0 --no-cpu-baseline --in-flight $nf > gpurun_out/r2_bench_ov.json 2> gpurun_out/r2_bench_ov.err; echo "in-flight $nf rc=$?"
+python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/r2_bench_ov.json') if l.startswith('{')][-1])
+print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'])
+PY
+done

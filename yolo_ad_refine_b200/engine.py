@@ -33,8 +33,10 @@ class RefineEngine:
         self.use_graph = use_graph
         self.pipeline_nms = pipeline_nms and use_graph
         self.overlap_batches = overlap_batches and self.pipeline_nms
+        # buffer sets: 2 with one batch in flight (forward i + 1 beside NMS i); overlap_batches = True -> 2 in flight, an integer n -> n in flight
+        self._nsets = (2 if overlap_batches is True else max(2, int(overlap_batches))) if self.overlap_batches else 2
         self._imgs = [torch.zeros((batch, 3, self.h, self.w), dtype=torch.uint8 if input_u8 else torch.float32, device=self.device)
-                      for _ in range(2 if self.overlap_batches else 1)]
+                      for _ in range(self._nsets if self.overlap_batches else 1)]
         self.graph = None
         self.launches_per_step = None
         self._out = None
@@ -43,7 +45,7 @@ class RefineEngine:
     @property
     def img(self):
         """the static input buffer the NEXT step() reads (with overlap_batches the two buffer sets alternate)"""
-        return self._imgs[self._i & 1] if self.overlap_batches else self._imgs[0]
+        return self._imgs[self._i % self._nsets] if self.overlap_batches else self._imgs[0]
 
     def fill_inputs(self, x):
         """the same batch into every input buffer (device-resident benchmarking: step() then needs no copy at all)"""
@@ -69,11 +71,12 @@ class RefineEngine:
         if self.pipeline_nms:
             self._nms_stream = torch.cuda.Stream(device=self.device)
             self._gf, self._gn, self._bufs = [], [], []
-            self._ev_f = [torch.cuda.Event() for _ in range(2)]
-            self._ev_n = [torch.cuda.Event() for _ in range(2)]
-            self._ev_in = [torch.cuda.Event() for _ in range(2)]
-            self._fstreams = [torch.cuda.Stream(device=self.device) for _ in range(2)] if self.overlap_batches else None
-            for b in range(2):  # two buffer sets: predictions of batch i are read by its NMS while batch i + 1 is being computed
+            ns = self._nsets
+            self._ev_f = [torch.cuda.Event() for _ in range(ns)]
+            self._ev_n = [torch.cuda.Event() for _ in range(ns)]
+            self._ev_in = [torch.cuda.Event() for _ in range(ns)]
+            self._fstreams = [torch.cuda.Stream(device=self.device) for _ in range(ns)] if self.overlap_batches else None
+            for b in range(ns):  # buffer sets: predictions of batch i are read by its NMS while batch i + 1 is being computed
                 gf = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gf):
                     y, feats = Fn.forward_model(self.ctx, self._imgs[b if self.overlap_batches else 0])
@@ -99,7 +102,7 @@ class RefineEngine:
         if self._out is None:
             self._capture()
         if self.pipeline_nms:
-            b = self._i & 1
+            b = self._i % self._nsets
             self._i += 1
             main = torch.cuda.current_stream()
             if self.overlap_batches:
@@ -112,7 +115,7 @@ class RefineEngine:
                     self._gf[b].replay()
                     self._ev_f[b].record(fs)
                 # the caller may refill the OTHER set's input next; that set's previous forward (one batch ago) must have consumed it
-                main.wait_event(self._ev_f[b ^ 1])
+                main.wait_event(self._ev_f[(b + 1) % self._nsets])
             else:
                 main.wait_event(self._ev_n[b])       # the NMS that last read this buffer set (two batches ago) is done
                 self._gf[b].replay()
@@ -137,8 +140,8 @@ class RefineEngine:
         """order the current stream after every batch enqueued so far (no-op without pipeline_nms)"""
         if self.pipeline_nms and self._i:
             main = torch.cuda.current_stream()
-            main.wait_event(self._ev_n[0])
-            main.wait_event(self._ev_n[1])
+            for ev in self._ev_n:
+                main.wait_event(ev)
 
     def forward(self, img):
         """img: (B, 3, H, W) float tensor in [0,1] (host or device).  Returns (y (B,4+nc,N) fp32, [raw (B,144,H,W) views])."""
@@ -218,15 +221,16 @@ class RefineEngine:
                 # two batches in flight: the device -> host copy of batch i is enqueued right behind its NMS (pinned ring of three, so the host
                 # may still be reading batch i - 2 while batch i - 1 lands), and the host only ever WAITS for batch i - 2 -- it keeps a whole
                 # batch of enqueued work ahead of the GPU.  Results arrive in order, two batches late; the tail is flushed after the loop.
+                nr = self._nsets + 1
                 if not hasattr(self, "_ring"):
-                    self._ring = [(torch.empty_like(det_host).pin_memory(), torch.empty_like(cnt_host).pin_memory(), torch.cuda.Event()) for _ in range(3)]
-                dh, ch, ev = self._ring[i % 3]
+                    self._ring = [(torch.empty_like(det_host).pin_memory(), torch.empty_like(cnt_host).pin_memory(), torch.cuda.Event()) for _ in range(nr)]
+                dh, ch, ev = self._ring[i % nr]
                 with torch.cuda.stream(self._nms_stream):
                     dh.copy_(det, non_blocking=True)
                     ch.copy_(count, non_blocking=True)
                     ev.record(self._nms_stream)
-                lag.append(i % 3)
-                if len(lag) > 2:
+                lag.append(i % nr)
+                if len(lag) > self._nsets:
                     yield self._take(lag.pop(0), det_host, cnt_host)
             elif self.pipeline_nms:
                 # software pipeline: batch i is only enqueued here; the detections handed to the caller are those of batch i - 1, read back on
