@@ -21,8 +21,14 @@ for r in rows[hdr + 1:]:
 ids = sorted(per)
 calls = int(sys.argv[2])  # yad_conv2d entry-point calls per step (bench.py roofline.launches); a transposed convolution is 4 kernel launches
 seq = [per[i]["kernel"] for i in ids]
-n_step = next(p for p in range(calls, len(seq) // 2 + 1) if seq[-p:] == seq[-2 * p:-p])  # period of the kernel sequence = kernel launches per pass
-last = ids[-n_step:]  # the launches of the last (post-warm-up) pass
+try:
+    n_step = next(p for p in range(calls, len(seq) // 2 + 1) if seq[-p:] == seq[-2 * p:-p])  # period of the kernel sequence = kernel launches per pass
+    last = ids[-n_step:]  # the launches of the last (post-warm-up) pass
+except StopIteration:
+    # two batches in flight: ncu serialises the kernels of both forward streams in an arbitrary interleaving, so the tail has no clean period; the
+    # two eager warm-up passes at the start of the run are sequential -- take the second one (ncu flushes the caches before every kernel anyway)
+    n_step = next(p for p in range(calls, len(seq) // 2 + 1) if seq[:p] == seq[p:2 * p])
+    last = ids[n_step:2 * n_step]
 rd = sum(per[i].get("dram__bytes_read.sum", 0) for i in last)
 wr = sum(per[i].get("dram__bytes_write.sum", 0) for i in last)
 names = {}
