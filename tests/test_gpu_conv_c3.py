@@ -54,3 +54,19 @@ def test_c3_add_alpha_channel_slices(cin, cout, act, fn):
     got = from_act(wide, cout + 32)
     assert rel_err(got[:, 16:16 + cout], ref) < TOL
     assert float(got[:, :16].abs().max()) == 0.0 and float(got[:, 16 + cout:].abs().max()) == 0.0  # neighbours of the slice untouched
+
+
+@pytest.mark.parametrize("cout", [8, 16, 32])
+@pytest.mark.parametrize("h,w,n", [(320, 320, 3), (166, 90, 20)])
+def test_c3_stride2_pixel_pair_planes(cout, h, w, n):
+    """stride 2, 16 input channels (backbone layer 1): two row-parity planes of pixel pairs (SWIZZLE_64B), a tap = (plane, pair offset, 32-byte half);
+    even maps whose output grid is ragged against the 16 x 8 tile"""
+    g = torch.Generator().manual_seed(cout + h)
+    x = q(torch.randn(n, 16, h, w, generator=g))
+    wt = q(torch.randn(cout, 16, 3, 3, generator=g) / 12.0)
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = F.silu(F.conv2d(x, wt, b, 2, 1))
+    cw = pack_conv(wt, b, BF, DEV, 2)
+    out = Act.empty(n, h // 2, w // 2, cw.cout, BF, DEV)
+    ops.conv2d(to_act(x, BF), cw.w, out, bias=cw.b, kh=3, kw=3, stride=2, pad_h=1, pad_w=1, act=ops.ACT_SILU, impl=6)
+    assert rel_err(from_act(out, cout), ref) < TOL

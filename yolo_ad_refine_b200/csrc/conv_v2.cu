@@ -623,14 +623,21 @@ __global__ void __launch_bounds__(V2_MAX_THREADS, 1) conv2_kernel(const __grid_c
 //             wrap -- five MMAs per 128 pixels, no im2col copy.  Dense inputs (ld == 8) merge the pixel and channel axes: a patch row is one
 //             160-byte TMA line.
 //   cin = 16 / 32   SWIZZLE_32B / SWIZZLE_64B rows of one pixel each (one / two K steps per tap), stride-byte-offset = one patch row.
+//   stride 2 (cin = 16, dense input)   the input is viewed as (2 x 16 channels of a horizontal pixel PAIR, w / 2, row parity, h / 2, n): two TMA boxes
+//             per tile, one per row parity, of 17 rows x 9 pairs x 64 bytes (SWIZZLE_64B).  Output pixels that are neighbours in x read neighbouring
+//             PAIRS, so the 8 rows of a core matrix are again consecutive 64-byte rows; a tap selects the row-parity plane, the pair offset and the
+//             32-byte half of the row (x parity) -- 9 MMAs per 128 output pixels from 306 TMA lines (conv_tma_kernel: one box per tap, 1152 lines of
+//             32 bytes, ~3 cycles per line: 150 us for the 16 -> 32 layer at 320^2).
 // The weights are laid out once per CTA in the no-swizzle canonical form ([step][K chunk][8-row group][8 rows][16 bytes]; every descriptor carries
 // its own layout type).  Epilogue: v2_epilogue in tile-split mode.  Two CTAs per SM.
 constexpr int C3_MAX_MMA = 18;   // 9 taps x 32 channels / 16
 constexpr int C3_PLANE_BYTES = 18 * 10 * 16, C3_PLANE_STRIDE = 2944;  // 2880 rounded up to 128 (TMA destination alignment)
+constexpr int C3_S2_PLANE = 10240;    // stride 2: one row-parity plane = 17 rows x 9 pixel pairs x 64 bytes = 9792, rounded up to 1024
 struct C3Params {
   V2Params v;
   int nmma;
   int dense;                            // cin = 8 and x.ld == 8: one patch row (10 pixels) is ONE 160-byte TMA line of the merged (w * 8) axis
+  int s2;                               // stride 2, cin = 16, dense input: two row-parity planes of [17 rows][9 pixel PAIRS][2 x 16 channels] (SWIZZLE_64B)
   uint32_t a_hi;                        // high descriptor word of the A operand (stride-byte-offset = one patch row, layout type)
   uint32_t tx_bytes;
   uint32_t stage_bytes, off_w;          // A stage; weights
@@ -694,8 +701,14 @@ __global__ void __launch_bounds__(320, 2) conv3_kernel(const __grid_constant__ C
       mbar_wait(empty_bar(s), sr.ph ^ 1u);
       if (leader) {
         mbar_expect_tx(full_bar(s), cp.tx_bytes);
-        if (cp.dense) tma_load_3d(a_s, &tmA, full_bar(s), (ti.tx * V2_BW - 1) * 8, ti.ty * V2_BH - 1, ti.img);
-        else tma_load_4d(a_s, &tmA, full_bar(s), 0, ti.tx * V2_BW - 1, ti.ty * V2_BH - 1, ti.img);
+        if (cp.s2) {
+          tma_load_5d(a_s, &tmA, full_bar(s), 0, ti.tx * V2_BW - 1, 0, ti.ty * V2_BH - 1, ti.img);
+          tma_load_5d(a_s + C3_S2_PLANE, &tmA, full_bar(s), 0, ti.tx * V2_BW - 1, 1, ti.ty * V2_BH - 1, ti.img);
+        } else if (cp.dense) {
+          tma_load_3d(a_s, &tmA, full_bar(s), (ti.tx * V2_BW - 1) * 8, ti.ty * V2_BH - 1, ti.img);
+        } else {
+          tma_load_4d(a_s, &tmA, full_bar(s), 0, ti.tx * V2_BW - 1, ti.ty * V2_BH - 1, ti.img);
+        }
       }
     }
   } else if (warp == 1) {
@@ -1227,13 +1240,15 @@ int yad_conv2d_c3(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
   static int on = -1;
   if (on < 0) on = v2_env("YAD_CONV_C3", 1);
   if (!on || !get_encode()) return -1;
-  if (d->mode != YAD_CONV_NORMAL || d->kh != 3 || d->kw != 3 || d->pad_h != 1 || d->pad_w != 1 || d->stride != 1) return -1;
+  if (d->mode != YAD_CONV_NORMAL || d->kh != 3 || d->kw != 3 || d->pad_h != 1 || d->pad_w != 1 || (d->stride != 1 && d->stride != 2)) return -1;
   if (!(x->c == 8 || x->c == 16 || x->c == 32) || !(y->c == 8 || y->c == 16 || y->c == 32)) return -1;
+  const bool s2 = d->stride == 2;
+  if (s2 && (x->c != 16 || x->ld != 16 || (x->h & 1) || (x->w & 1))) return -1;
   if ((x->ld % 8) || (y->ld % 8) || ((uintptr_t)x->ptr & 15) || ((uintptr_t)y->ptr & 15) || ((uintptr_t)w & 15)) return -1;
-  if (y->h != x->h || y->w != x->w || y->n != x->n) return -1;
+  if (y->h != x->h / d->stride || y->w != x->w / d->stride || y->n != x->n) return -1;
   if (e->img_scale || e->pix_scale || e->mul || e->gn_stats) return -1;
   if (e->add && (((uintptr_t)e->add & 15) || (e->add_ld % 8))) return -1;
-  const int64_t M = (int64_t)x->n * x->h * x->w;
+  const int64_t M = (int64_t)y->n * y->h * y->w;
   if (M + V2_BM >= (int64_t)1 << 31) return -1;
   C3Params cp;
   memset(&cp, 0, sizeof(cp));
@@ -1260,7 +1275,18 @@ int yad_conv2d_c3(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
   // A-operand layout by input width (see the kernel's header)
   const int nchunk = 9 * (x->c / 8);  // 16-byte K chunks of the weight rows
   cp.nmma = (nchunk + 1) / 2;
-  if (x->c == 8) {
+  if (s2) {
+    cp.s2 = 1;
+    for (int t = 0; t < 9; t++) {  // tap (dy, dx): input pixel (2 oy + dy - 1, 2 ox + dx - 1) -> row-parity plane, row / pair offset inside the box, x parity
+      const int dy = t / 3, dx = t % 3;
+      const int plane = dy == 1 ? 0 : 1, r0 = dy == 0 ? 0 : 1, c0 = dx == 0 ? 0 : 1, xpar = dx == 1 ? 0 : 1;
+      cp.a_off[t] = (uint32_t)(plane * C3_S2_PLANE + (r0 * 9 + c0) * 64 + xpar * 32);
+      cp.a_lbo[t] = 16u;
+    }
+    cp.a_hi = ((9u * 64u) >> 4) | (1u << 14) | (4u << 29);
+    cp.tx_bytes = 2u * 17u * 9u * 64u;
+    cp.stage_bytes = 2u * C3_S2_PLANE;
+  } else if (x->c == 8) {
     cp.dense = x->ld == 8;
     for (int i = 0; i < cp.nmma; i++) {
       const int t0 = 2 * i, t1 = 2 * i + 1;
@@ -1299,7 +1325,13 @@ int yad_conv2d_c3(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
   p.bias = e->bias; p.act = e->act; p.alpha = e->alpha;
   p.add = (const bf16*)e->add; p.add_ld = e->add_ld;
   CUtensorMap tmA, tmY;
-  if (cp.dense) {
+  if (cp.s2) {
+    const uint64_t rowb = (uint64_t)x->w * 32;  // bytes of one image row (16 channels)
+    uint64_t dims[5] = {32, (uint64_t)x->w / 2, 2, (uint64_t)x->h / 2, (uint64_t)x->n};
+    uint64_t strides[4] = {64, rowb, 2 * rowb, (uint64_t)x->h * rowb};
+    uint32_t box[5] = {32, 9, 1, 17, 1};
+    if (v2_make_map(&tmA, x->ptr, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  } else if (cp.dense) {
     uint64_t dims[3] = {(uint64_t)x->w * 8, (uint64_t)x->h, (uint64_t)x->n};
     uint64_t strides[2] = {(uint64_t)x->w * 16, (uint64_t)x->h * x->w * 16};
     uint32_t box[3] = {80, (uint32_t)(V2_BH + 2), 1};
