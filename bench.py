@@ -436,8 +436,9 @@ def main():
     torch.cuda.synchronize()
     ops.PROFILE = {}
     # the host must stay AHEAD of the device here: an event pair brackets the C call, so host work inside the call (tensor-map encoding, ctypes)
-    # would be billed to the kernel whenever the device has caught up.  A ~30 ms spin kernel is queued first and the whole step is enqueued behind it.
-    torch.cuda._sleep(int(60e6))
+    # would be billed to the kernel whenever the device has caught up.  A ~150 ms spin kernel is queued first and the whole step is enqueued behind it
+    # (30 ms was not always enough: the second half of the 253 calls then carried 10 - 15 us of host time each and the fraction read 0.108 instead of 0.13).
+    torch.cuda._sleep(int(300e6))
     eng._run()
     torch.cuda.synchronize()
     prof = {}
