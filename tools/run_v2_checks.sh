@@ -1,6 +1,11 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-DEFORM=1 DEFORM_STD=0.4 python tools/conv_probe.py 64 64 3 1 80 64 3 2 > gpurun_out/plain_dcn.log 2>&1 && \
-DEFORM=1 DEFORM_STD=0.4 ncu --set full --clock-control none --import-source on -k regex:dcn2_kernel -s 3 -c 1 -o gpurun_out/r2_dcn2 -f python tools/conv_probe.py 64 64 3 1 80 64 3 2 > gpurun_out/ncu_dcn.log 2>&1
-tail -2 gpurun_out/ncu_dcn.log
+for hs in 1 2 4; do
+YAD_HEAD_SPLIT=$hs timeout 600 python bench.py --steps 20 --warmup 3 --train-batch 0 --no-cpu-baseline > gpurun_out/r2_bench_hs.json 2> gpurun_out/r2_bench_hs.err; echo "head split $hs rc=$?"
+python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/r2_bench_hs.json') if l.startswith('{')][-1])
+print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['launches_per_step'])
+PY
+done
