@@ -110,7 +110,9 @@ for k, p in model.named_parameters():
     ref_norm = float(g[key])
     if k.endswith((".conv.bias", ".conv1.bias")) and ref_norm < 1e-3:
         continue
-    worst = max(worst, abs(float(p.grad.double().norm()) - ref_norm) / (ref_norm + 1e-6))
+    # same bar as tests/test_gpu_train_step.py: |norm - ref| <= 1e-2 ref + 1e-6 (the absolute term covers tensors whose whole gradient is ~1e-5:
+    # statistics accumulate with floating-point atomics, so their last bits move from run to run)
+    worst = max(worst, max(0.0, abs(float(p.grad.double().norm()) - ref_norm) - 1e-6) / (ref_norm + 1e-12))
     checked += 1
 w0 = model.model[0].conv.weight.detach().clone()
 opt.step()
