@@ -97,7 +97,7 @@ opt.zero_grad()
 loss, items = model(batch)                                          # engine/trainer.py:384
 loss.backward()                                                      # :389
 name = "b2_160"
-worst, checked, missing = 0.0, 0, 0
+worst, checked, missing, worst_key, worst_ref = 0.0, 0, 0, '', 0.0
 for k, p in model.named_parameters():
     if f"{name}|{k}|none" in g.files:
         continue
@@ -110,14 +110,17 @@ for k, p in model.named_parameters():
     ref_norm = float(g[key])
     if k.endswith((".conv.bias", ".conv1.bias")) and ref_norm < 1e-3:
         continue
-    # same bar as tests/test_gpu_train_step.py: |norm - ref| <= 1e-2 ref + 1e-6 (the absolute term covers tensors whose whole gradient is ~1e-5:
-    # statistics accumulate with floating-point atomics, so their last bits move from run to run)
-    worst = max(worst, max(0.0, abs(float(p.grad.double().norm()) - ref_norm) - 1e-6) / (ref_norm + 1e-12))
+    # same bar as tests/test_gpu_train_step.py: |norm - ref| <= 1e-2 ref + 1e-4.  The absolute term covers the few tensors whose whole gradient is
+    # ~3e-3 (TaskDecomposition's layer-attention convs, formed by cancellation): statistics accumulate with floating-point atomics, so those move by
+    # 0.1 - 1.2 % from run to run (measured over six runs: model.33.reg_decomp.la_conv1.weight / la_conv2.bias) against a total gradient norm of ~1e3
+    err = max(0.0, abs(float(p.grad.double().norm()) - ref_norm) - 1e-4) / (ref_norm + 1e-12)
+    if err > worst:
+        worst, worst_key, worst_ref = err, k, ref_norm
     checked += 1
 w0 = model.model[0].conv.weight.detach().clone()
 opt.step()
 print("RESULT " + json.dumps(dict(loss=float(loss), loss_ref=float(g[f"{name}_loss"]), items=[float(v) for v in items], items_ref=[float(v) for v in g[f"{name}_items"]],
-      worst=worst, checked=checked, missing=missing, moved=float((model.model[0].conv.weight - w0).abs().max()),
+      worst=worst, worst_key=worst_key, worst_ref=worst_ref, checked=checked, missing=missing, moved=float((model.model[0].conv.weight - w0).abs().max()),
       bn_moved=float((model.model[0].bn.running_mean - rm0).abs().max()), tracked=int(model.model[0].bn.num_batches_tracked))))
 """)
     assert abs(res["loss"] - res["loss_ref"]) < 1e-4 * abs(res["loss_ref"]), res

@@ -42,7 +42,7 @@ def test_train_step_fp32_matches_reference(gold, state_dict, name):
         if k.endswith((".conv.bias", ".conv1.bias")) and ref_norm < 1e-3:
             continue  # a bias in front of a batch-statistics BatchNorm: the exact gradient is 0, both sides hold rounding noise
         norm = float(np.sqrt((v.astype(np.float64) ** 2).sum()))
-        assert abs(norm - ref_norm) <= 1e-2 * ref_norm + 1e-6, (k, norm, ref_norm)
+        assert abs(norm - ref_norm) <= 1e-2 * ref_norm + 1e-4, (k, norm, ref_norm)  # absolute term: see tests/test_gpu_reference_api.py
         ref = g[f"{name}|{k}|samples"]
         np.testing.assert_allclose(v[cases.sample_positions(v.size, 16)], ref, rtol=2e-2, atol=1e-2 * ref_norm / np.sqrt(v.size) + 1e-7, err_msg=k)
         checked += 1

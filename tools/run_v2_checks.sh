@@ -1,11 +1,15 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-mkdir -p gpurun_out
-for hs in 1 2 4; do
-YAD_HEAD_SPLIT=$hs timeout 600 python bench.py --steps 20 --warmup 3 --train-batch 0 --no-cpu-baseline > gpurun_out/r2_bench_hs.json 2> gpurun_out/r2_bench_hs.err; echo "head split $hs rc=$?"
+for k in 1 2 3 4 5 6; do
 python - <<'PY'
-import json
-d=json.loads([l for l in open('gpurun_out/r2_bench_hs.json') if l.startswith('{')][-1])
-print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['launches_per_step'])
+import sys, json
+sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
+import test_gpu_reference_api as t
+import re
+body = open('tests/test_gpu_reference_api.py').read()
+# run the trainer scenario and print the worst tensor
+m = re.search(r'def test_reference_trainer_step.*?res = _run\(r"""(.*?)"""\)', body, re.S)
+res = t._run(m.group(1))
+print(round(res['worst'], 5), res['worst_key'], res['worst_ref'])
 PY
 done
