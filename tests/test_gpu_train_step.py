@@ -346,8 +346,13 @@ def test_graphed_step_equals_eager_step(state_dict, optimizer):
             assert float((ea.tp.ema - eb.tp.ema).norm()) < tol * float((ea.tp.ema - f0).norm() + 1e-12)
             np.testing.assert_allclose(ea.tp.bufs.cpu().numpy(), eb.tp.bufs.cpu().numpy(), rtol=1e-4, atol=1e-6)
         else:
-            assert abs(la[3] - lb[3]) <= 3 * abs(la[3] - lc[3]) + 1e-3 * abs(la[3])
-    assert float((ea.tp.flat - eb.tp.flat).norm()) <= 3 * float((ea.tp.flat - ec.tp.flat).norm()) + 1e-4 * float((ea.tp.flat - f0).norm())
+            # the eager-eager spread is ONE sample of a chaotic quantity (measured 0.05 % .. 1 % of the loss), so it is only one of two yardsticks:
+            # a wrong step (stale learning rate in the graph, missing update) moves the loss and the parameters by far more than the floors below
+            assert abs(la[3] - lb[3]) <= max(3 * abs(la[3] - lc[3]), 2e-2 * abs(la[3]))
+    assert float((ea.tp.flat - eb.tp.flat).norm()) <= max(3 * float((ea.tp.flat - ec.tp.flat).norm()), 0.05 * float((ea.tp.flat - f0).norm()))
+    # the three learning rates were applied: the total update of the graphed run has the eager run's size
+    ua, ub = float((ea.tp.flat - f0).norm()), float((eb.tp.flat - f0).norm())
+    assert abs(ua - ub) <= 0.05 * ua
     assert ea.tp.steps == eb.tp.steps == 3 and ea.tp.ema_updates == eb.tp.ema_updates
     hy = eb.tp._hyper.cpu().numpy()
     assert abs(hy[0] - lrs[-1]) < 1e-7 and abs(hy[11] - 10.0) < 1e-6      # the device-resident scalars of the last step
