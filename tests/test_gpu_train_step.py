@@ -340,10 +340,11 @@ def test_graphed_step_equals_eager_step(state_dict, optimizer):
             np.testing.assert_allclose(la, lb, rtol=1e-5)
             upd = float((ea.tp.flat - f0).norm())
             # AdamW's first step is lr * sign(g) element-wise (m / sqrt(v) with one sample): gradient elements at the noise floor of the fp
-            # atomics flip their whole update, hence the looser bound
-            tol = 1e-3 if optimizer == "SGD" else 2e-2
-            assert upd > 0 and float((ea.tp.flat - eb.tp.flat).norm()) < tol * upd
-            assert float((ea.tp.ema - eb.tp.ema).norm()) < tol * float((ea.tp.ema - f0).norm() + 1e-12)
+            # atomics flip their whole update, hence the looser bound (measured 1.5 - 2.6 % of the update norm between two runs, eager or graphed)
+            tol = 1e-3 if optimizer == "SGD" else 5e-2
+            spread = float((ea.tp.flat - ec.tp.flat).norm())  # the same quantity between the two EAGER runs
+            assert upd > 0 and float((ea.tp.flat - eb.tp.flat).norm()) < max(tol * upd, 2 * spread)
+            assert float((ea.tp.ema - eb.tp.ema).norm()) < max(tol, 2 * spread / upd) * float((ea.tp.ema - f0).norm() + 1e-12)
             np.testing.assert_allclose(ea.tp.bufs.cpu().numpy(), eb.tp.bufs.cpu().numpy(), rtol=1e-4, atol=1e-6)
         else:
             # the eager-eager spread is ONE sample of a chaotic quantity (measured 0.05 % .. 1 % of the loss), so it is only one of two yardsticks:
