@@ -811,7 +811,20 @@ __device__ __forceinline__ void block_pixel_sum(const yad_tensor& x, int64_t cou
     float s[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) s[i] = 0.f;
-    for (int64_t j = lane; j < count; j += step) {
+    int64_t j = lane;
+    for (; j + 3 * step < count; j += 4 * step) {  // four packed loads in flight (one per trip was latency-bound: 1.6 TB/s on a 52 MB map)
+      Raw8<T> r[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) raw_load(reinterpret_cast<const T*>(x.ptr) + pixel_offset(j + u * step) + o, r[u]);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        float v[8];
+        raw_unpack(r[u], v);
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] += v[i];
+      }
+    }
+    for (; j < count; j += step) {
       float v[8];
       load8(reinterpret_cast<const T*>(x.ptr) + pixel_offset(j) + o, v);
 #pragma unroll
@@ -850,7 +863,20 @@ __global__ void gap_kernel(yad_tensor x, float* __restrict__ out) {
     float s[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) s[i] = 0.f;
-    for (int64_t p = p0 + lane; p < p1; p += step) {
+    int64_t p = p0 + lane;
+    for (; p + 3 * step < p1; p += 4 * step) {  // four packed loads in flight
+      Raw8<T> r[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) raw_load(base + (p + u * step) * x.ld + o, r[u]);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        float v[8];
+        raw_unpack(r[u], v);
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] += v[i];
+      }
+    }
+    for (; p < p1; p += step) {
       float v[8];
       load8(base + p * x.ld + o, v);
 #pragma unroll
