@@ -33,7 +33,7 @@ typedef struct {
   int32_t ld; /* pixel stride in elements */
 } yad_tensor;
 
-/* y = act(acc * img_scale[n] * pix_scale[pixel] + bias[co]) * alpha ; y *= mul[pixel][co] ; y += add[pixel][co] */
+/* y = act(acc * img_scale[n] * pix_scale[pixel] + bias[co]) * alpha ; y *= mul[pixel][co] ; y *= gate_h[n][oy][co] * gate_w[n][ox][co] ; y += add[pixel][co] */
 typedef struct {
   const float* bias;      /* [cout] fp32 or NULL */
   const float* img_scale; /* [n] fp32 or NULL */
@@ -49,6 +49,14 @@ typedef struct {
    * [n][gn_groups][2] += (sum, sum of squares); yad_conv2d zeroes the buffer itself.  Used by Conv_GN (nn/modules/head.py:1265-1279). */
   double* gn_stats;
   int32_t gn_groups; /* 0 with gn_stats set: per-channel statistics over the WHOLE batch, double [cout][2] (train-mode BatchNorm, conv.py:50) */
+  /* optional separable gate: the output of ELA_HSFPN with flag=False (nn/modules/block.py:1408-1424: sigmoid(x_h) * sigmoid(x_w) broadcast over the
+   * map) followed by the yaml's Multiply, without materialising the (n, h, w, c) gate map.  gate_h: (n, out_h, c) and gate_w: (n, out_w, c) in the
+   * activation dtype, rows of gate_ld elements; both or neither; the product gate_h * gate_w is rounded to the activation dtype first (= the map
+   * yad_rowcol_gate would have written).  NORMAL-mode 1x1 stride-1 convolutions only, not combined with mul / gn_stats. */
+  const void* gate_h;
+  const void* gate_w;
+  int32_t gate_ld;
+  int32_t gate_hm, gate_wm; /* set by yad_conv2d itself (output height / width); callers leave them 0 */
 } yad_epilogue;
 
 typedef struct {
@@ -101,6 +109,11 @@ int yad_gap(const yad_tensor* x, float* out, int dtype, void* stream);
 int yad_rowcol_mean(const yad_tensor* x, const yad_tensor* rowmean, const yad_tensor* colmean, int dtype, void* stream);
 /* y = x * gh[n][y][ch] * gw[n][x][ch]  (x may be NULL: pure outer product, ELA flag=False); gh (n,h,1,c), gw (n,w,1,c) views */
 int yad_rowcol_gate(const yad_tensor* x, const yad_tensor* gh, const yad_tensor* gw, const yad_tensor* y, int dtype, void* stream);
+/* CoordAtt between its pooling and its gating (nn/modules/head.py:694-703): rows (n, h, 1, c) / cols (n, w, 1, c) from yad_rowcol_mean ->
+ * gh (n, h, 1, co) = sigmoid(conv_h(hardswish(bn1(conv1(rows))))), gw likewise with conv_w.  w1 fp32 [mip][c] / b1 [mip]: conv1 with the
+ * eval-mode bn1 folded in; wh, ww fp32 [co][mip], bh, bw [co]; mip = 8, 16 or 32.  One launch instead of four 1x1 yad_conv2d calls. */
+int yad_coordatt_mlp(const yad_tensor* rows, const yad_tensor* cols, const float* w1, const float* b1, int mip, const float* wh, const float* bh,
+                     const float* ww, const float* bw, const yad_tensor* gh, const yad_tensor* gw, int dtype, void* stream);
 /* adaptive_avg_pool to (h/s, w/s) followed by bilinear upsample back, align_corners=False (block.py:2451-2457) */
 int yad_pool_upsample(const yad_tensor* x, int s, const yad_tensor* y, int dtype, void* stream);
 

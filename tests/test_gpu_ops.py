@@ -336,3 +336,21 @@ def test_stem_conv_tensor_core_u8(n, h, w):
     # the f16 tensor-core path against the fp32-weight SIMT kernel on the same input: they differ by the weight rounding only
     y32 = ops.stem_conv(img.to(DEV), wq.to(DEV), b.to(DEV), Act.empty(n, ho, wo, 16, torch.float32, DEV))
     assert rel_err(from_act(y), from_act(y32)) < tol(torch.bfloat16)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,h,w,c,mip,oup", [(2, 80, 80, 64, 8, 64), (3, 7, 13, 64, 8, 64), (1, 20, 5, 512, 16, 256), (2, 3, 40, 1024, 32, 64), (65, 1, 1, 8, 8, 8)])
+def test_coordatt_mlp(dtype, n, h, w, c, mip, oup):
+    """yad_coordatt_mlp against nn/modules/head.py:694-703 (conv1 with the eval-mode bn1 folded in -> Hardswish -> conv_h / conv_w -> sigmoid)"""
+    g = torch.Generator().manual_seed(n + h + c)
+    rows, cols = q(torch.randn(n, c, h, 1, generator=g), dtype), q(torch.randn(n, c, w, 1, generator=g), dtype)
+    w1, b1 = torch.randn(mip, c, generator=g) / c ** 0.5, torch.randn(mip, generator=g)
+    wh, bh = torch.randn(oup, mip, generator=g) / mip ** 0.5, torch.randn(oup, generator=g) * 0.3
+    ww, bw = torch.randn(oup, mip, generator=g) / mip ** 0.5, torch.randn(oup, generator=g) * 0.3
+    ref_h = torch.sigmoid(F.conv2d(F.hardswish(F.conv2d(rows, w1.view(mip, c, 1, 1), b1)), wh.view(oup, mip, 1, 1), bh))
+    ref_w = torch.sigmoid(F.conv2d(F.hardswish(F.conv2d(cols, w1.view(mip, c, 1, 1), b1)), ww.view(oup, mip, 1, 1), bw))
+    d = lambda t: t.contiguous().to(DEV)  # noqa: E731
+    gh, gw = ops.coordatt_mlp(to_act(rows, dtype), to_act(cols, dtype), d(w1), d(b1), d(wh), d(bh), d(ww), d(bw),
+                              Act.empty(n, h, 1, oup, dtype, DEV), Act.empty(n, w, 1, oup, dtype, DEV))
+    t = 1e-5 if dtype == torch.float32 else 5e-3  # bf16: the only rounding is the store of the gate (values in (0, 1))
+    assert rel_err(from_act(gh), ref_h) < t and rel_err(from_act(gw), ref_w) < t

@@ -111,3 +111,60 @@ def test_conv_tc_7x1():
     out = Act.empty(4, 20, 1, 128, BF, DEV)
     ops.conv2d(to_act(v[:, :, :, None], BF), cw.w, out, bias=cw.b, kh=7, kw=1, pad_h=3, pad_w=0, impl=2)
     assert rel_err(from_act(out)[:, :, :, 0], ref) < TOL
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, BF])
+@pytest.mark.parametrize("n,h,w,cin,cout,with_add,act", [(2, 12, 9, 64, 128, True, ops.ACT_NONE), (3, 20, 20, 128, 128, True, ops.ACT_NONE),
+                                                         (2, 7, 13, 32, 64, False, ops.ACT_NONE), (1, 40, 40, 128, 256, True, ops.ACT_SILU),
+                                                         (5, 3, 50, 64, 80, True, ops.ACT_SIGMOID), (2, 16, 16, 64, 64, True, ops.ACT_GELU)])
+def test_conv_separable_gate_epilogue(dtype, n, h, w, cin, cout, with_add, act):
+    """yad_epilogue.gate_h / gate_w (ELA_HSFPN flag=False + Multiply folded into the lateral 1x1, z-yaml layers 15-18 / 22-25, block.py:1408-1424):
+    against torch, and in bf16 bit-identical to the path that materialises the gate map with yad_rowcol_gate and passes it as `mul`"""
+    g = torch.Generator().manual_seed(n * 100 + h + cout)
+    rnd = (lambda t: q(t)) if dtype == BF else (lambda t: t)
+    x = rnd(torch.randn(n, cin, h, w, generator=g))
+    wt = rnd(torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    gh = rnd(torch.rand(n, cout, h, 1, generator=g))
+    gw = rnd(torch.rand(n, cout, w, 1, generator=g))
+    add = rnd(torch.randn(n, cout, h, w, generator=g))
+    gate = rnd(gh * gw.permute(0, 1, 3, 2))
+    acts = {ops.ACT_NONE: lambda t: t, ops.ACT_SILU: F.silu, ops.ACT_SIGMOID: torch.sigmoid, ops.ACT_GELU: F.gelu}
+    ref = acts[act](F.conv2d(x, wt, b)) * gate + (add if with_add else 0)
+    cw = pack_conv(wt, b, dtype, DEV)
+    impl = 0 if dtype == BF else 1
+    gha, gwa = to_act(gh, dtype), to_act(gw, dtype)
+    out = Act.empty(n, h, w, cw.cout, dtype, DEV)
+    ops.conv2d(to_act(x, dtype), cw.w, out, bias=cw.b, act=act, gate=(gha, gwa), add=to_act(add, dtype) if with_add else None, impl=impl)
+    assert rel_err(from_act(out, cout), ref) < (TOL if dtype == BF else 1e-4)
+    gmap = ops.rowcol_gate(None, gha, gwa, Act.empty(n, h, w, cw.cout, dtype, DEV))
+    out2 = Act.empty(n, h, w, cw.cout, dtype, DEV)
+    ops.conv2d(to_act(x, dtype), cw.w, out2, bias=cw.b, act=act, mul=gmap, add=to_act(add, dtype) if with_add else None, impl=impl)
+    if dtype == BF:
+        assert torch.equal(out.buf, out2.buf)
+    else:
+        assert rel_err(from_act(out, cout), from_act(out2, cout)) < 1e-6
+
+
+def test_conv_separable_gate_rejected_outside_its_scope():
+    x = to_act(torch.randn(1, 64, 8, 8), BF)
+    cw = pack_conv(torch.randn(64, 64, 3, 3) / 24, None, BF, DEV)
+    gh, gw = to_act(torch.rand(1, 64, 8, 1), BF), to_act(torch.rand(1, 64, 8, 1), BF)
+    with pytest.raises(RuntimeError, match="separable gate"):
+        ops.conv2d(x, cw.w, Act.empty(1, 8, 8, 64, BF, DEV), kh=3, kw=3, pad_h=1, pad_w=1, gate=(gh, gw))
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 80, 80, 64, 80), (3, 12, 9, 64, 80), (2, 20, 20, 64, 32), (1, 33, 7, 128, 64)])
+def test_conv_v2_pix_scale_alpha_and_relu_variants(n, h, w, cin, cout):
+    """the dedicated conv2_kernel variants for the head's cv3 (per-pixel scale only, head.py:1171-1173) and cls_prob_conv.0 (ReLU, head.py:1168)"""
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = q(torch.randn(n, cin, h, w, generator=g))
+    wt = q(torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    pix = q(torch.rand(n, 8, h, w, generator=g))
+    cw = pack_conv(wt, b, BF, DEV)
+    out = Act.empty(n, h, w, cw.cout, BF, DEV)
+    ops.conv2d(to_act(x, BF), cw.w, out, bias=cw.b, pix_scale=to_act(pix, BF), alpha=0.5)
+    assert rel_err(from_act(out, cout), (F.conv2d(x, wt) * pix[:, :1] + b.view(1, -1, 1, 1)) * 0.5) < TOL
+    ops.conv2d(to_act(x, BF), cw.w, out, bias=cw.b, act=ops.ACT_RELU)
+    assert rel_err(from_act(out, cout), F.relu(F.conv2d(x, wt, b))) < TOL

@@ -18,7 +18,8 @@ class YadTensor(C.Structure):
 class YadEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("img_scale", C.c_void_p), ("pix_scale", C.c_void_p), ("pix_scale_ld", C.c_int32),
                 ("act", C.c_int32), ("alpha", C.c_float), ("mul", C.c_void_p), ("mul_ld", C.c_int32), ("add", C.c_void_p),
-                ("add_ld", C.c_int32), ("gn_stats", C.c_void_p), ("gn_groups", C.c_int32)]
+                ("add_ld", C.c_int32), ("gn_stats", C.c_void_p), ("gn_groups", C.c_int32), ("gate_h", C.c_void_p), ("gate_w", C.c_void_p),
+                ("gate_ld", C.c_int32), ("gate_hm", C.c_int32), ("gate_wm", C.c_int32)]
 
 
 class YadConvDesc(C.Structure):
@@ -58,6 +59,7 @@ SIGNATURES = {
     "yad_gap": (i32, [TP, vp, i32, vp]),
     "yad_rowcol_mean": (i32, [TP, TP, TP, i32, vp]),
     "yad_rowcol_gate": (i32, [TP, TP, TP, TP, i32, vp]),
+    "yad_coordatt_mlp": (i32, [TP, TP, vp, vp, i32, vp, vp, vp, vp, TP, TP, i32, vp]),
     "yad_pool_upsample": (i32, [TP, i32, TP, i32, vp]),
     "yad_mlca_pool": (i32, [TP, vp, i32, i32, vp]),
     "yad_mlca_att": (i32, [vp, vp, vp, i32, f32, i32, i32, i32, vp, vp, vp]),

@@ -49,6 +49,19 @@ int yad_device_is_sm100(void) {
 int yad_conv2d(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, int dtype,
                void* stream) {
   YAD_CHECK(x && w && d && e && y && x->ptr && y->ptr, "conv2d: null argument");
+  yad_epilogue eg;
+  if (e->gate_h || e->gate_w) {  // separable gate (ELA_HSFPN flag=False + Multiply): 1x1 stride-1 NORMAL convolutions, rows aligned like every other operand
+    YAD_CHECK(e->gate_h && e->gate_w, "conv2d: gate_h and gate_w come together");
+    YAD_CHECK(d->mode == YAD_CONV_NORMAL && d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad_h == 0 && d->pad_w == 0,
+              "conv2d: the separable gate epilogue covers 1x1 stride-1 convolutions only");
+    YAD_CHECK(!e->mul && !e->gn_stats, "conv2d: the separable gate epilogue cannot be combined with mul / fused statistics");
+    YAD_CHECK(e->gate_ld >= y->c && e->gate_ld % 8 == 0 && ((uintptr_t)e->gate_h & 15) == 0 && ((uintptr_t)e->gate_w & 15) == 0,
+              "conv2d: gate rows must be 16-byte aligned with gate_ld >= cout, a multiple of 8");
+    eg = *e;
+    eg.gate_hm = y->h;
+    eg.gate_wm = y->w;
+    e = &eg;
+  }
   int impl = d->impl;
   if ((impl == 0 || impl == 6) && dtype == YAD_BF16) {  // 3x3 stride-1 convolutions with <= 32 channels: tcgen05 straight on a no-swizzle patch (conv_v2.cu)
     const int r = yad_conv2d_c3(x, w, d, e, y, stream);

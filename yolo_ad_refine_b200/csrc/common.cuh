@@ -107,6 +107,12 @@ __device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
   h[1] = __floats2bfloat162_rn(v[2], v[3]);
   *reinterpret_cast<uint2*>(p) = u;
 }
+template <typename T>
+__device__ __forceinline__ float round_to(float v);  // v rounded to the storage type T
+template <>
+__device__ __forceinline__ float round_to<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float round_to<bf16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 __device__ __forceinline__ float ld1(const float* p) { return *p; }
 __device__ __forceinline__ float ld1(const bf16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
@@ -210,6 +216,15 @@ __device__ __forceinline__ void epilogue4(float (&acc)[4], const yad_epilogue& e
     load4(reinterpret_cast<const T*>(e.mul) + pix * e.mul_ld + co, m);
 #pragma unroll
     for (int i = 0; i < 4; i++) acc[i] *= m[i];
+  }
+  if (e.gate_h) {  // separable gate; the product is rounded to the activation dtype first, as the materialised gate map would have been
+    const int64_t rem = pix - (int64_t)img * e.gate_hm * e.gate_wm;
+    const int oy = (int)(rem / e.gate_wm), ox = (int)(rem - (int64_t)oy * e.gate_wm);
+    float gh[4], gw[4];
+    load4(reinterpret_cast<const T*>(e.gate_h) + ((int64_t)img * e.gate_hm + oy) * e.gate_ld + co, gh);
+    load4(reinterpret_cast<const T*>(e.gate_w) + ((int64_t)img * e.gate_wm + ox) * e.gate_ld + co, gw);
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc[i] *= round_to<T>(gh[i] * gw[i]);
   }
   if (e.add) {
     float a[4];

@@ -1058,6 +1058,7 @@ int yad_conv2d_tc(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
       if (r >= 0) return r;
     }
     YAD_CHECK(d->impl != 4, "conv2d: impl 4 (resident-weight tcgen05 kernel) does not support this shape / epilogue");
+    YAD_CHECK(!e->gate_h, "conv2d: the separable gate epilogue runs on conv2_kernel (bf16: channels and strides multiples of 8, cin >= 16) or the SIMT kernel only");
     if (d->impl != 3 && tma_supported(x, d, y)) return launch_tma(p, d, st);
     if (p.bn_stats) {  // batch statistics are fused on the TMA-fed kernel only: thread-gathered kernel first, stand-alone statistics after it
       p.bn_stats = 0;

@@ -65,6 +65,9 @@ struct V2Params {
   int mul_ld;
   const bf16* add;
   int add_ld;
+  const bf16* gate_h;  // separable gate rows (n, hm, cout) / (n, wm, cout): y *= round_bf16(gate_h * gate_w), flat (1x1) tiles only
+  const bf16* gate_w;
+  int gate_ld;
   double* gn_stats;
   int gn_groups, cpg;
 };
@@ -233,6 +236,9 @@ __device__ __forceinline__ void epi_unit(const V2Params& p, uint32_t taddr, uint
   } else if constexpr (ACT == YAD_ACT_SIGMOID) {
 #pragma unroll
     for (int i = 0; i < U; i++) v[i] = fmaf(0.5f, v2_tanh(0.5f * v[i]), 0.5f);
+  } else if constexpr (ACT == YAD_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < U; i++) v[i] = fmaxf(v[i], 0.0f);
   } else if constexpr (ACT == ACT_GENERIC) {
     if (p.act == YAD_ACT_SILU) {
 #pragma unroll
@@ -326,24 +332,71 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
           if (p.pix_scale) rsc *= __bfloat162float(p.pix_scale[(int64_t)dp * p.pix_scale_ld]);
         }
       }
-      // conv3_kernel (PRE): the residual rows of this warp are fetched BEFORE the wait for the accumulator, so their global latency runs under the
-      // MMAs instead of inside the per-tile epilogue chain (the bottleneck adds doubled the kernel's time: 37 -> 65 us at 8 -> 16 @160^2)
-      constexpr bool PREFETCH = PRE && MULADD && !GN && !SCALE;
-      uint4 pav[4];
-      bool pre = false;
-      if constexpr (PREFETCH) {
-        if (p.add && !p.mul && ce - cb == p.sc && cpr <= 4) {
-          pre = true;
-          const int co = n0 + cb + cj * 8;
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            pav[k] = make_uint4(0u, 0u, 0u, 0u);
-            const int row = rr0 + k * rpp;
-            if (k >= cpr || co >= p.cout) continue;
-            const int oy = ty0 + 4 * q + (row >> 3), ox = tx0 + (row & 7);
-            if (oy < p.hm && ox < p.wm) pav[k] = __ldg(reinterpret_cast<const uint4*>(p.add + ((int64_t)(img * p.hm + oy) * p.wm + ox) * p.add_ld + co));
-          }
+      // The mul / add rows of a piece are pulled into L2 by prefetch hints BEFORE its accumulator is read (for the first piece: before the wait for
+      // the accumulator), so their DRAM latency runs under the MMAs / the TMEM reads instead of inside the per-tile epilogue chain (the bottleneck
+      // adds doubled conv3_kernel's time: 37 -> 65 us at 8 -> 16 @160^2; the lateral 1x1 with Multiply + Add ran at 115 us against 41 us without
+      // them).  Phase 2 then reads all rows of the piece at once, in the registers the accumulator has just left.  Holding the operands in registers
+      // across the TMEM reads does not fit the 96-register budget of the 576-thread CTA: ptxas spilled them right behind the loads, which stalls
+      // exactly where the prefetch was meant to run ahead.  YAD_CONV2_PREFETCH=0 (p.dbg & 8) keeps the old two-rows-at-a-time loop.
+      constexpr bool PREFETCH = MULADD && !GN && !SCALE;
+      const bool pre = PREFETCH && (p.add || p.mul || p.gate_h) && cpr <= 4 && !(p.dbg & 8);
+      // pixel index of row `row` of this warp's 32 rows; false outside the map
+      auto row_pixel = [&](int row, int64_t& d) -> bool {
+        if (PATCH) {
+          const int oy = ty0 + 4 * q + (row >> 3), ox = tx0 + (row & 7);
+          d = (int64_t)(img * p.hm + oy) * p.wm + ox;
+          return oy < p.hm && ox < p.wm;
         }
+        d = (int64_t)m_base + row;
+        return d < p.m_total;
+      };
+      // separable gate of a flat (1x1) tile: (image, y, x) of this warp's first row once per tile (two integer divisions), rows step from there
+      int g_img = 0, g_y = 0, g_x = 0;
+      if constexpr (MULADD && !PATCH) {
+        if (p.gate_h) {
+          g_img = m_base / p.hw;
+          const int rem = m_base - g_img * p.hw;
+          g_y = rem / p.wm;
+          g_x = rem - g_y * p.wm;
+        }
+      }
+      // addresses of the gate rows of row `row` (which must be inside the map), 8 channels from co
+      auto gate_addr = [&](int row, int co, const uint4*& ah, const uint4*& aw) {
+        int gi = g_img, gy = g_y, gx = g_x + row;
+        while (gx >= p.wm) { gx -= p.wm; gy++; }
+        while (gy >= p.hm) { gy -= p.hm; gi++; }
+        ah = reinterpret_cast<const uint4*>(p.gate_h + (int64_t)(gi * p.hm + gy) * p.gate_ld + co);
+        aw = reinterpret_cast<const uint4*>(p.gate_w + (int64_t)(gi * p.wm + gx) * p.gate_ld + co);
+      };
+      // round_bf16(gate_h * gate_w): exactly the values yad_rowcol_gate would have written into a gate map, so the tile below is bit-identical to
+      // the mul-operand path
+      auto gate_mul = [&](const uint4& a, const uint4& b) -> uint4 {
+        uint4 r;
+        const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+        __nv_bfloat162* hr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+        for (int e = 0; e < 4; e++) hr[e] = __hmul2(ha[e], hb[e]);
+        return r;
+      };
+      auto gate_vec = [&](int row, int co) -> uint4 {
+        const uint4 *ah, *aw;
+        gate_addr(row, co, ah, aw);
+        return gate_mul(__ldg(ah), __ldg(aw));
+      };
+      const bool has_mul = p.mul || (!PATCH && p.gate_h);
+      auto prefetch = [&](int c0) {
+        const int co = n0 + c0 + cj * 8;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          int64_t d;
+          if (k >= cpr || co >= p.cout || !row_pixel(rr0 + k * rpp, d)) continue;
+          if (p.add) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.add + d * p.add_ld + co));
+          if (p.mul) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mul + d * p.mul_ld + co));
+        }
+      };
+      if constexpr (PREFETCH) {
+        if (pre && cb < ce) prefetch(cb);
       }
       const int acc = ar.idx;
       mbar_wait((tfull0 + 8u * (uint32_t)acc), ar.ph);
@@ -373,8 +426,45 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
           if (lane == 0) mbar_arrive((tempty0 + 8u * (uint32_t)acc));
         }
         if constexpr (PREFETCH) {
-          if (pre) {  // rows outside the map hold zeros in pav and are clipped by the bulk store
+          if (pre) {  // rows outside the map get zeros and are clipped by the bulk store
             __syncwarp();
+            const int co = n0 + c0 + cj * 8;
+            uint4 pav[4], pmv[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {  // every row of the piece in flight at once (L2 hits after the hints above)
+              pav[k] = make_uint4(0u, 0u, 0u, 0u);
+              pmv[k] = make_uint4(0u, 0u, 0u, 0u);
+              int64_t d;
+              if (k >= cpr || co >= p.cout || !row_pixel(rr0 + k * rpp, d)) continue;
+              if (p.add) pav[k] = __ldg(reinterpret_cast<const uint4*>(p.add + d * p.add_ld + co));
+              if (p.mul) pmv[k] = __ldg(reinterpret_cast<const uint4*>(p.mul + d * p.mul_ld + co));
+            }
+            if constexpr (!PATCH) {
+              if (p.gate_h) {  // the gate rows of all four rows in flight together with the add rows (L1 / L2 residents); rows outside the map
+                               // multiply by zero and are clipped by the bulk store.  The epilogue is issue-bound (ncu: 51 % issue-active with the
+                               // add operand alone), so the position of the lane's first row is found once and the others step from it by rpp pixels
+                uint4 pgw[4];
+                int gi = g_img, gy = g_y, gx = g_x + rr0;
+                while (gx >= p.wm) { gx -= p.wm; gy++; }
+                while (gy >= p.hm) { gy -= p.hm; gi++; }
+                const bf16* gh0 = p.gate_h + co;
+                const bf16* gw0 = p.gate_w + co;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  pgw[k] = make_uint4(0u, 0u, 0u, 0u);
+                  if (k < cpr && co < p.cout && m_base + rr0 + k * rpp < p.m_total) {
+                    pmv[k] = __ldg(reinterpret_cast<const uint4*>(gh0 + (gi * p.hm + gy) * p.gate_ld));
+                    pgw[k] = __ldg(reinterpret_cast<const uint4*>(gw0 + (gi * p.wm + gx) * p.gate_ld));
+                  }
+                  gx += rpp;
+                  while (gx >= p.wm) { gx -= p.wm; gy++; }
+                  while (gy >= p.hm) { gy -= p.hm; gi++; }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) pmv[k] = gate_mul(pmv[k], pgw[k]);
+              }
+            }
+            if (c0 + p.sc < ce) prefetch(c0 + p.sc);  // the next piece's operands travel under this piece's store and the next TMEM reads
 #pragma unroll
             for (int k = 0; k < 4; k++) {
               if (k >= cpr) continue;
@@ -383,18 +473,27 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
               uint4 u = lds16(ca);
               __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
               const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&pav[k]);
+              const __nv_bfloat162* hm = reinterpret_cast<const __nv_bfloat162*>(&pmv[k]);
+              if (has_mul && p.add) {
 #pragma unroll
-              for (int e = 0; e < 4; e++) h[e] = __hadd2(h[e], ha[e]);
+                for (int e = 0; e < 4; e++) h[e] = __hfma2(h[e], hm[e], ha[e]);
+              } else if (has_mul) {
+#pragma unroll
+                for (int e = 0; e < 4; e++) h[e] = __hmul2(h[e], hm[e]);
+              } else if (p.add) {
+#pragma unroll
+                for (int e = 0; e < 4; e++) h[e] = __hadd2(h[e], ha[e]);
+              }
               sts16v(ca, u);
             }
           }
         }
         if constexpr (MULADD) {
-          if ((p.mul || p.add) && !pre) {
+          if ((p.mul || p.add || p.gate_h) && !pre) {
             __syncwarp();
             const int co = n0 + c0 + cj * 8;
             if (co < p.cout) {
-#pragma unroll 2
+#pragma unroll 4
               for (int row = rr0; row < 32; row += rpp) {
                 int64_t d;
                 bool ok;
@@ -411,19 +510,21 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
                 const uint32_t ca = ra + ((((uint32_t)cj) ^ ((ra >> 7) & swz)) << 4);
                 uint4 u = lds16(ca);
                 __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-                if (p.mul && p.add) {
-                  const uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.mul + d * p.mul_ld + co));
+                uint4 mv = make_uint4(0u, 0u, 0u, 0u);
+                if (p.mul) mv = __ldg(reinterpret_cast<const uint4*>(p.mul + d * p.mul_ld + co));
+                if constexpr (!PATCH) {
+                  if (p.gate_h) mv = gate_vec(row, co);
+                }
+                const __nv_bfloat162* hm = reinterpret_cast<const __nv_bfloat162*>(&mv);
+                if (has_mul && p.add) {
                   const uint4 av = __ldg(reinterpret_cast<const uint4*>(p.add + d * p.add_ld + co));
-                  const __nv_bfloat162* hm = reinterpret_cast<const __nv_bfloat162*>(&mv);
                   const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&av);
 #pragma unroll
                   for (int e = 0; e < 4; e++) h[e] = __hfma2(h[e], hm[e], ha[e]);
-                } else if (p.mul) {
-                  const uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.mul + d * p.mul_ld + co));
-                  const __nv_bfloat162* hm = reinterpret_cast<const __nv_bfloat162*>(&mv);
+                } else if (has_mul) {
 #pragma unroll
                   for (int e = 0; e < 4; e++) h[e] = __hmul2(h[e], hm[e]);
-                } else {
+                } else if (p.add) {
                   const uint4 av = __ldg(reinterpret_cast<const uint4*>(p.add + d * p.add_ld + co));
                   const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&av);
 #pragma unroll
@@ -1008,14 +1109,20 @@ int v2_launch_t(const V2Params& p, const CUtensorMap& tmA, const CUtensorMap& tm
 
 template <bool PATCH>
 int v2_dispatch(const V2Params& p, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, int grid, size_t smem, cudaStream_t st) {
-  const bool muladd = p.mul || p.add, gn = p.gn_stats != nullptr, scale = p.img_scale || p.pix_scale;
+  const bool muladd = p.mul || p.add || p.gate_h, gn = p.gn_stats != nullptr, scale = p.img_scale || p.pix_scale;
 #define V2_CASE(ACT_, MA_, GN_, SC_) return v2_launch_t<PATCH, ACT_, MA_, GN_, SC_>(p, tmA, tmB, tmY, grid, smem, st)
   if (!gn && !scale) {
     if (p.act == YAD_ACT_SILU) { if (muladd) V2_CASE(YAD_ACT_SILU, true, false, false); else V2_CASE(YAD_ACT_SILU, false, false, false); }
     if (p.act == YAD_ACT_NONE) { if (muladd) V2_CASE(YAD_ACT_NONE, true, false, false); else V2_CASE(YAD_ACT_NONE, false, false, false); }
     if constexpr (!PATCH) {
       if (p.act == YAD_ACT_SIGMOID) { if (muladd) V2_CASE(YAD_ACT_SIGMOID, true, false, false); else V2_CASE(YAD_ACT_SIGMOID, false, false, false); }
+      if (p.act == YAD_ACT_RELU && !muladd) V2_CASE(YAD_ACT_RELU, false, false, false);  // cls_prob_conv.0 of the head
     }
+  }
+  if constexpr (!PATCH) {
+    // per-row scales without GroupNorm statistics / mul / add (the head's cv3 with cls_prob folded into the rows): before this variant existed
+    // the call fell through to the generic all-features kernel (57.6 us at 64 -> 80 @80^2 against 26.9 us for the plain 64 -> 64)
+    if (!gn && scale && !muladd && p.act == YAD_ACT_NONE) V2_CASE(YAD_ACT_NONE, false, false, true);
   }
   if (gn && !muladd && p.act == YAD_ACT_NONE) {
     if (!scale) V2_CASE(YAD_ACT_NONE, false, true, false);
@@ -1049,12 +1156,22 @@ static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilog
   if (e->gn_stats && e->gn_groups == 0) return 0;  // fused batch statistics (train-mode BatchNorm) stay on conv_tma_kernel<true>
   if (patch && (e->img_scale || e->pix_scale)) return 0;
   if ((e->mul && ((uintptr_t)e->mul & 15 || e->mul_ld % 8)) || (e->add && ((uintptr_t)e->add & 15 || e->add_ld % 8))) return 0;
+  if (e->gate_h && (!flat || e->mul || e->gn_stats || e->img_scale || e->pix_scale)) return 0;
+  if (e->gate_h && (int64_t)x->n * (y->h > y->w ? y->h : y->w) * e->gate_ld >= (int64_t)1 << 31) return 0;  // 32-bit gate row offsets
   const int64_t M = (int64_t)x->n * x->h * x->w;
   if (M + V2_BM >= (int64_t)1 << 31) return 0;
   V2Params p;
   memset(&p, 0, sizeof(p));
   p.n = x->n; p.hm = y->h; p.wm = y->w; p.hw = y->h * y->w; p.cin = x->c; p.cout = y->c; p.m_total = (int)M;
   p.n_tile = pick_n_tile_v2(p.cout);
+  {
+    // 80 / 112 / ... output channels: the columns are dealt to the epilogue warps in units of 16, and one 16-column share forces 16-column (32-byte)
+    // store boxes on every warp.  Padding the tile to the next multiple of 32 keeps 32-column boxes (the extra accumulator columns come from
+    // zero-filled weight rows and are clipped by the store): the head's cv3 64 -> 80 @80^2 47 -> ?? us.  YAD_CONV2_NPAD=0 keeps the exact tile.
+    static int npad_env = -1;
+    if (npad_env < 0) npad_env = v2_env("YAD_CONV2_NPAD", 1);
+    if (npad_env && !e->gn_stats && p.n_tile > 64 && (p.n_tile % 32) && p.n_tile + 16 <= 256 && p.cout <= p.n_tile) p.n_tile += 16;
+  }
   p.tiles_n = (p.cout + p.n_tile - 1) / p.n_tile;
   p.ntaps = patch ? 9 : 1;
   p.kpt = (p.cin + 63) / 64;
@@ -1072,7 +1189,7 @@ static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilog
   }
   {
     static int dbg_env = -1;
-    if (dbg_env < 0) dbg_env = v2_env("YAD_CONV2_DBG", 0);
+    if (dbg_env < 0) dbg_env = (v2_env("YAD_CONV2_DBG", 0) & 7) | (v2_env("YAD_CONV2_PREFETCH", 1) ? 0 : 8);
     p.dbg = dbg_env;
   }
   static int ew_env = -1, ts_env = -1;
@@ -1154,6 +1271,7 @@ static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilog
   p.bias = e->bias; p.img_scale = e->img_scale; p.pix_scale = (const bf16*)e->pix_scale; p.pix_scale_ld = e->pix_scale_ld;
   p.act = e->act; p.alpha = e->alpha;
   p.mul = (const bf16*)e->mul; p.mul_ld = e->mul_ld; p.add = (const bf16*)e->add; p.add_ld = e->add_ld;
+  p.gate_h = (const bf16*)e->gate_h; p.gate_w = (const bf16*)e->gate_w; p.gate_ld = e->gate_ld;
   p.gn_stats = e->gn_stats; p.gn_groups = e->gn_groups;
   *out = p;
   return patch ? 2 : 1;
@@ -1269,7 +1387,7 @@ int yad_conv2d_c3(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
   p.stg_warp_bytes = 32u * (uint32_t)p.sc * 2u;
   {
     static int dbg_env = -1;
-    if (dbg_env < 0) dbg_env = v2_env("YAD_CONV2_DBG", 0);
+    if (dbg_env < 0) dbg_env = (v2_env("YAD_CONV2_DBG", 0) & 7) | (v2_env("YAD_CONV2_PREFETCH", 1) ? 0 : 8);
     p.dbg = dbg_env;
   }
   // A-operand layout by input width (see the kernel's header)

@@ -1075,6 +1075,52 @@ __global__ void __launch_bounds__(256, 2) rowcol_mean1_kernel(yad_tensor x, yad_
   }
 }
 
+// CoordAtt (nn/modules/head.py:694-703) between its pooling and its gating: y = hardswish(bn1(conv1(cat[x_h, x_w]))) (conv1 + eval-mode bn1 folded
+// into w1 [MIP][c] / b1 [MIP]), then a_h = sigmoid(conv_h(y_h)), a_w = sigmoid(conv_w(y_w)) (wh, ww [co][MIP]).  One warp per position of the
+// concatenated axis: lanes stride over the input channels, the MIP hidden sums are reduced with shuffles, then lanes stride over the output channels.
+// Replaces four 1x1 yad_conv2d launches on (n, L, 1, c) views (each at the launch floor); fp32 weights and hidden activations.
+template <typename T, int MIP>
+__global__ void __launch_bounds__(TPB) coordatt_mlp_kernel(yad_tensor rows, yad_tensor cols, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                           const float* __restrict__ wh, const float* __restrict__ bh, const float* __restrict__ ww,
+                                                           const float* __restrict__ bw, yad_tensor gh, yad_tensor gw) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31;
+  const int64_t pos = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nrows = (int64_t)rows.n * rows.h, ncols = (int64_t)cols.n * cols.h;
+  if (pos >= nrows + ncols) return;
+  const bool is_row = pos < nrows;
+  const int64_t idx = is_row ? pos : pos - nrows;
+  const yad_tensor& src = is_row ? rows : cols;
+  const yad_tensor& dst = is_row ? gh : gw;
+  const T* xp = reinterpret_cast<const T*>(src.ptr) + idx * src.ld;
+  float hid[MIP];
+#pragma unroll
+  for (int j = 0; j < MIP; j++) hid[j] = 0.f;
+  const int c = src.c;
+  for (int ch = lane; ch < c; ch += 32) {
+    const float v = ld1(xp + ch);
+#pragma unroll
+    for (int j = 0; j < MIP; j++) hid[j] = fmaf(__ldg(w1 + j * c + ch), v, hid[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < MIP; j++) {
+    float t = hid[j];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+    t += __ldg(b1 + j);
+    hid[j] = t * fminf(fmaxf(t + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f);  // nn.Hardswish
+  }
+  const float* wo = is_row ? wh : ww;
+  const float* bo = is_row ? bh : bw;
+  T* yp = reinterpret_cast<T*>(dst.ptr) + idx * dst.ld;
+  for (int co = lane; co < dst.c; co += 32) {
+    float t = __ldg(bo + co);
+#pragma unroll
+    for (int j = 0; j < MIP; j++) t = fmaf(__ldg(wo + co * MIP + j), hid[j], t);
+    st1(yp + co, sigmoidf_(t));
+  }
+}
+
 template <typename T>
 __global__ void rowcol_gate_kernel(yad_tensor x, bool has_x, yad_tensor gh, yad_tensor gw, yad_tensor y) {
   pdl_sync();
@@ -1918,6 +1964,32 @@ int yad_rowcol_gate(const yad_tensor* x, const yad_tensor* gh, const yad_tensor*
   yad_tensor xx = x ? *x : *y;
   YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(rowcol_gate_kernel<T>, grid_for(total), TPB, 0, st, xx, x != nullptr, *gh, *gw, *y);)
   YAD_LAUNCH_CHECK("rowcol_gate");
+  return 0;
+}
+
+// CoordAtt's gate MLP on the pooled rows / columns (nn/modules/head.py:694-703): one warp per position of the concatenated (h + w) axis.
+int yad_coordatt_mlp(const yad_tensor* rows, const yad_tensor* cols, const float* w1, const float* b1, int mip, const float* wh, const float* bh,
+                     const float* ww, const float* bw, const yad_tensor* gh, const yad_tensor* gw, int dtype, void* stream) {
+  CHECK_VIEW(rows, "coordatt_mlp rows");
+  CHECK_VIEW(cols, "coordatt_mlp cols");
+  CHECK_VIEW(gh, "coordatt_mlp gh");
+  CHECK_VIEW(gw, "coordatt_mlp gw");
+  YAD_CHECK(w1 && b1 && wh && bh && ww && bw, "coordatt_mlp: null weights");
+  YAD_CHECK(rows->w == 1 && cols->w == 1 && gh->w == 1 && gw->w == 1, "coordatt_mlp: (n, L, 1, c) views expected");
+  YAD_CHECK(rows->n == cols->n && rows->c == cols->c && gh->n == rows->n && gh->h == rows->h && gw->n == cols->n && gw->h == cols->h &&
+                gh->c == gw->c,
+            "coordatt_mlp: shape mismatch");
+  YAD_CHECK(mip == 8 || mip == 16 || mip == 32, "coordatt_mlp: %d hidden channels (8, 16 or 32 supported)", mip);
+  YAD_CHECK(rows->c <= 1024 && gh->c <= 1024, "coordatt_mlp: at most 1024 channels");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t positions = (int64_t)rows->n * (rows->h + cols->h);
+  const int wpb = TPB / 32;
+  const int grid = (int)((positions + wpb - 1) / wpb);
+  if (grid == 0) return 0;
+#define CA_LAUNCH(M) YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH((coordatt_mlp_kernel<T, M>), grid, TPB, 0, st, *rows, *cols, w1, b1, wh, bh, ww, bw, *gh, *gw);)
+  if (mip == 8) { CA_LAUNCH(8) } else if (mip == 16) { CA_LAUNCH(16) } else { CA_LAUNCH(32) }
+#undef CA_LAUNCH
+  YAD_LAUNCH_CHECK("coordatt_mlp");
   return 0;
 }
 

@@ -144,13 +144,15 @@ def sppf(ctx, p, x):
     return conv_bn_act(ctx, p + ".cv2", cat)
 
 
-def ela_hsfpn(ctx, p, x, flag=True, out=None):
-    """nn/modules/block.py:1408-1424 ELA_HSFPN: both 1-D branches share Conv1d(k7) + GroupNorm(16) + sigmoid"""
+def ela_hsfpn(ctx, p, x, flag=True, out=None, factors=False):
+    """nn/modules/block.py:1408-1424 ELA_HSFPN: both 1-D branches share Conv1d(k7) + GroupNorm(16) + sigmoid.  factors=True (with flag=False):
+    return the two 1-D gates (gh (n, h, 1, c), gw (n, w, 1, c)) instead of their broadcast product -- the consumer is the yaml's Multiply, which
+    the lateral 1x1 convolution applies in its epilogue (yad_epilogue.gate_h / gate_w), so the (n, h, w, c) gate map is never written or read."""
     P = ctx.P
     n, h, w, c = x.n, x.h, x.w, x.c
     cw = P.conv(p + ".conv1x1.0.weight", p + ".conv1x1.0.bias")
     gamma, beta = P.f32(p + ".conv1x1.1.weight"), P.f32(p + ".conv1x1.1.bias")
-    if out is None:
+    if out is None and not factors:
         out = ctx.act(n, h, w, c)
 
     def branch(means):
@@ -168,6 +170,9 @@ def ela_hsfpn(ctx, p, x, flag=True, out=None):
         rows, cols = ctx.act(n, h, 1, c), ctx.act(n, w, 1, c)
         ops.rowcol_mean(x, rows, cols)
         gh, gw = branch(rows), branch(cols)
+    if factors:
+        assert not flag and out is None
+        return gh, gw
     return ops.rowcol_gate(x if flag else None, gh, gw, out)
 
 
@@ -521,11 +526,20 @@ def coord_att(ctx, p, x, out=None):
                        P.sd[p + ".bn1.running_mean"].float(), P.sd[p + ".bn1.running_var"].float(), P.sd[p + ".conv1.bias"].float())
 
     wf, bf = P.misc(p + ".fold", fold)
-    c1 = P.conv_raw(p + ".conv1f", wf, bf)
     rows, cols = ctx.act(n, h, 1, c), ctx.act(n, w, 1, c)
     ops.rowcol_mean(x, rows, cols)
-    gh = conv(ctx, conv(ctx, rows, c1, act=ACT_HARDSWISH), P.conv(p + ".conv_h.weight", p + ".conv_h.bias"), act=ACT_SIGMOID)
-    gw = conv(ctx, conv(ctx, cols, c1, act=ACT_HARDSWISH), P.conv(p + ".conv_w.weight", p + ".conv_w.bias"), act=ACT_SIGMOID)
+    mip, oup = wf.shape[0], P.sd[p + ".conv_h.weight"].shape[0]
+    if mip in (8, 16, 32) and oup % 8 == 0:
+        # one launch for conv1 (+ bn1) -> h-swish -> conv_h / conv_w -> sigmoid on both axes (fp32 weights and hidden activations)
+        dev = lambda t: t.float().contiguous().to(ctx.device)  # noqa: E731
+        w1, b1 = P.misc(p + ".mlp1", lambda: (dev(wf.reshape(mip, c)), dev(bf)))
+        wh, ww = P.misc(p + ".mlp2", lambda: (dev(P.sd[p + ".conv_h.weight"].reshape(oup, mip)), dev(P.sd[p + ".conv_w.weight"].reshape(oup, mip))))
+        gh, gw = ops.coordatt_mlp(rows, cols, w1, b1, wh, P.f32(p + ".conv_h.bias"), ww, P.f32(p + ".conv_w.bias"),
+                                  ctx.act(n, h, 1, oup), ctx.act(n, w, 1, oup))
+    else:
+        c1 = P.conv_raw(p + ".conv1f", wf, bf)
+        gh = conv(ctx, conv(ctx, rows, c1, act=ACT_HARDSWISH), P.conv(p + ".conv_h.weight", p + ".conv_h.bias"), act=ACT_SIGMOID)
+        gw = conv(ctx, conv(ctx, cols, c1, act=ACT_HARDSWISH), P.conv(p + ".conv_w.weight", p + ".conv_w.bias"), act=ACT_SIGMOID)
     return ops.rowcol_gate(x, gh, gw, out if out is not None else ctx.act(n, h, w, c))
 
 
@@ -701,14 +715,20 @@ def forward_model(ctx, img, decode=True, keep_layers=False):
     L[11] = ela_hsfpn(ctx, "model.11", L[10], True)
     L[12] = conv(ctx, L[11], P.conv("model.12.weight", "model.12.bias"))
     L[13] = conv(ctx, L[12], P.conv("model.13.weight", "model.13.bias", stride=2, transposed=True), mode=ops.CONV_TRANSPOSED)
-    L[16] = ela_hsfpn(ctx, "model.16", L[13], False)
+    # ELA_HSFPN(flag=False) (16 / 23) hands its two 1-D gates to the lateral 1x1 convolution, whose epilogue does Multiply (17 / 24) + Add (18 / 25);
+    # keep_layers (the per-layer parity tests) materialises the gate map the yaml's layer 16 / 23 would output
+    g16 = ela_hsfpn(ctx, "model.16", L[13], False, factors=True)
+    if keep_layers:
+        L[16] = ops.rowcol_gate(None, g16[0], g16[1], ctx.act(L[13].n, L[13].h, L[13].w, L[13].c))
     join(14)
-    L[18] = conv(ctx, L[14], P.conv("model.15.weight", "model.15.bias"), mul=L[16], add=L[13])  # Multiply (17) + Add (18)
+    L[18] = conv(ctx, L[14], P.conv("model.15.weight", "model.15.bias"), gate=g16, add=L[13])  # Multiply (17) + Add (18)
     L[19] = c3k2(ctx, "model.19", L[18], False, True)
     L[20] = conv(ctx, L[19], P.conv("model.20.weight", "model.20.bias", stride=2, transposed=True), mode=ops.CONV_TRANSPOSED)
-    L[23] = ela_hsfpn(ctx, "model.23", L[20], False)
+    g23 = ela_hsfpn(ctx, "model.23", L[20], False, factors=True)
+    if keep_layers:
+        L[23] = ops.rowcol_gate(None, g23[0], g23[1], ctx.act(L[20].n, L[20].h, L[20].w, L[20].c))
     join(21)
-    L[25] = conv(ctx, L[21], P.conv("model.22.weight", "model.22.bias"), mul=L[23], add=L[20])  # Multiply (24) + Add (25)
+    L[25] = conv(ctx, L[21], P.conv("model.22.weight", "model.22.bias"), gate=g23, add=L[20])  # Multiply (24) + Add (25)
     L[26] = c3k2(ctx, "model.26", L[25], False, True)
     L[27] = conv_bn_act(ctx, "model.27", L[26], 2)
     L[28] = fusion_bifpn(ctx, "model.28", [L[27], L[19]])

@@ -125,19 +125,25 @@ def _ap(a):
 
 
 def conv2d(x, w, y, bias=None, kh=1, kw=1, stride=1, pad_h=0, pad_w=0, act=ACT_NONE, alpha=1.0, img_scale=None, pix_scale=None,
-           mul=None, add=None, mode=CONV_NORMAL, offmask=None, impl=0, gn_stats=None, gn_groups=0):
-    """y = epilogue(conv(x, w)); w packed [cout][kh*kw][cin] in the activation dtype."""
+           mul=None, add=None, mode=CONV_NORMAL, offmask=None, impl=0, gn_stats=None, gn_groups=0, gate=None):
+    """y = epilogue(conv(x, w)); w packed [cout][kh*kw][cin] in the activation dtype.  gate = (gh, gw): Act views (n, out_h, 1, c) / (n, out_w, 1, c)
+    whose product multiplies the output (ELA_HSFPN flag=False + Multiply without the materialised gate map; 1x1 stride-1 convolutions)."""
     d = YadConvDesc(mode, kh, kw, stride, pad_h, pad_w, None if offmask is None else offmask.ptr, 0 if offmask is None else offmask.ld, impl)
     mp, mld = _ap(mul)
     adp, ald = _ap(add)
     psp, psld = _ap(pix_scale)
     e = YadEpilogue(None if bias is None else bias.data_ptr(), None if img_scale is None else img_scale.data_ptr(),
                     psp, psld, act, alpha, mp, mld, adp, ald, None if gn_stats is None else gn_stats.data_ptr(), gn_groups)
+    if gate is not None:
+        gh, gw = gate
+        assert (gh.n, gh.h, gh.w, gh.c) == (y.n, y.h, 1, y.c) and (gw.n, gw.h, gw.w, gw.c) == (y.n, y.w, 1, y.c) and gh.ld == gw.ld, "conv2d: gate shapes"
+        e.gate_h, e.gate_w, e.gate_ld = gh.ptr, gw.ptr, gh.ld
     flops = 2.0 * y.n * y.h * y.w * y.c * kh * kw * x.c if mode != CONV_TRANSPOSED else 2.0 * x.n * x.h * x.w * y.c * kh * kw * x.c
     meta = None
     if PROFILE is not None:
         esz = x.buf.element_size()
-        byts = esz * (x.n * x.h * x.w * x.c + y.n * y.h * y.w * y.c * (1 + (mul is not None) + (add is not None)) + w.numel())
+        byts = esz * (x.n * x.h * x.w * x.c + y.n * y.h * y.w * y.c * (1 + (mul is not None) + (add is not None)) + w.numel()
+                      + (0 if gate is None else y.n * (y.h + y.w) * y.c))
         meta = dict(flops=flops, bytes=byts, shape=f"{x.c}->{y.c} k{kh}x{kw} s{stride} m{mode} in{x.h}x{x.w} out{y.h}x{y.w} n{x.n}")
     _call("yad_conv2d", x.yt(), _p(w), C.byref(d), C.byref(e), y.yt(), dt(x.dtype), stream_ptr(), meta=meta)
     return y
@@ -191,6 +197,16 @@ def rowcol_mean(x, rows, cols):
 def rowcol_gate(x, gh, gw, y):
     _call("yad_rowcol_gate", None if x is None else x.yt(), gh.yt(), gw.yt(), y.yt(), dt(y.dtype), stream_ptr())
     return y
+
+
+def coordatt_mlp(rows, cols, w1, b1, wh, bh, ww, bw, gh, gw):
+    """CoordAtt's conv1 (+ folded bn1) -> hardswish -> conv_h / conv_w -> sigmoid on the pooled rows / columns (head.py:694-703); fp32 weights"""
+    for t in (w1, b1, wh, bh, ww, bw):
+        assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous()
+    mip = b1.numel()
+    assert w1.numel() == mip * rows.c and wh.numel() == gh.c * mip and ww.numel() == gw.c * mip and bh.numel() == gh.c and bw.numel() == gw.c
+    _call("yad_coordatt_mlp", rows.yt(), cols.yt(), _p(w1), _p(b1), mip, _p(wh), _p(bh), _p(ww), _p(bw), gh.yt(), gw.yt(), dt(rows.dtype), stream_ptr())
+    return gh, gw
 
 
 def pool_upsample(x, s, y):
