@@ -354,3 +354,17 @@ def test_coordatt_mlp(dtype, n, h, w, c, mip, oup):
                               Act.empty(n, h, 1, oup, dtype, DEV), Act.empty(n, w, 1, oup, dtype, DEV))
     t = 1e-5 if dtype == torch.float32 else 5e-3  # bf16: the only rounding is the store of the gate (values in (0, 1))
     assert rel_err(from_act(gh), ref_h) < t and rel_err(from_act(gw), ref_w) < t
+
+
+@pytest.mark.parametrize("n,T,heads", [(2, 65, 2), (1, 128, 1), (3, 129, 2), (2, 1200, 2), (1, 1237, 4), (2, 4800, 2)])
+def test_mha_bf16_long_sequences(n, T, heads):
+    """yad_mha on the 128-query tensor-core kernel (two 16-row tiles per warp, ldmatrix.x4 fragments) against softmax(q k^T / sqrt(d)) v
+    (nn.MultiheadAttention's core, block.py:2479-2488): tile tails, the T = 1200 of the benchmark and the T = 4800 of 1280^2 inputs"""
+    g = torch.Generator().manual_seed(T + heads)
+    c = heads * 64
+    qkv = q(torch.randn(n, T, 3 * c, generator=g), torch.bfloat16)
+    qq, kk, vv = (t.view(n, T, heads, 64).transpose(1, 2) for t in qkv.chunk(3, -1))
+    ref = F.scaled_dot_product_attention(qq, kk, vv).transpose(1, 2).reshape(n, T, c)
+    a = Act(qkv.view(n, T, 1, 3 * c).to(DEV).to(torch.bfloat16).contiguous())
+    out = ops.mha(a, heads, Act.empty(n, T, 1, c, torch.bfloat16, DEV))
+    assert rel_err(out.torch().float().cpu().view(n, T, c), ref) < tol(torch.bfloat16)

@@ -1,5 +1,7 @@
 // Layer-10 token kernels: CrossScaleAttentionTSSA statistics (nn/modules/block.py:2459-2474) and the core of
 // nn.MultiheadAttention (block.py:2432-2434, 2479-2486) as a flash-style streaming-softmax kernel (fp32 accumulate).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -301,6 +303,166 @@ __global__ void __launch_bounds__(128) mha_mma_kernel(const bf16* __restrict__ q
 }
 
 
+// ---- second version of the tensor-core attention core: 128 queries per CTA, 32 per warp -------------------------------------------
+// ncu of mha_mma_kernel at the benchmark shape (batch 64, T = 1200, 2 heads x 64; profiles/r2_ncu_mha.md): tensor pipe 44 % active, issue slots
+// 58 %, LSU 32 %, shared-memory wavefronts 48 % -- one ldmatrix.x2 per mma.sync, because a warp owns only one 16-row tile and every B fragment
+// is used once.  Here a warp owns TWO 16-row query tiles, so each K / V fragment feeds two MMAs, and the fragments arrive four 8x8 matrices at a
+// time (ldmatrix.x4: both k halves of a K fragment pair, two d tiles of a V fragment): 32 ldmatrix.x4 for 128 MMAs per 64-key tile instead of
+// 128 ldmatrix.x2, half the shared-memory bytes per MMA, and half the L2 -> shared traffic for K / V (10 CTAs per (image, head) instead of 19).
+// The key-tail mask is evaluated on the last tile only.
+__device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+
+constexpr int FA2_Q = 128;
+
+__global__ void __launch_bounds__(128, 2) mha_mma2_kernel(const bf16* __restrict__ qkv, int64_t ld, int Tn, int c, int heads, bf16* __restrict__ out,
+                                                          int64_t out_ld, float scale_log2e) {
+  pdl_sync();
+  __shared__ __align__(16) bf16 Ks[2][FA_K * FA_PITCH];  // double buffer: tile k + 1 streams in (cp.async) while tile k is consumed
+  __shared__ __align__(16) bf16 Vs[2][FA_K * FA_PITCH];
+  const int n = blockIdx.y / heads, h = blockIdx.y % heads;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
+  const bf16* base = qkv + (int64_t)n * Tn * ld + h * HD;
+  const int q0 = blockIdx.x * FA2_Q + warp * 32;  // this warp's first query row (two 16-row tiles)
+  uint32_t qa[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++) {
+#pragma unroll
+    for (int kt = 0; kt < 4; kt++) {
+      const int r0 = q0 + mt * 16 + g, r1 = r0 + 8, col = kt * 16 + 2 * q4;
+      qa[mt][kt][0] = r0 < Tn ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r0 * ld + col) : 0u;
+      qa[mt][kt][1] = r1 < Tn ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r1 * ld + col) : 0u;
+      qa[mt][kt][2] = r0 < Tn ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r0 * ld + col + 8) : 0u;
+      qa[mt][kt][3] = r1 < Tn ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r1 * ld + col + 8) : 0u;
+    }
+  }
+  float o[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+#pragma unroll
+      for (int i = 0; i < 4; i++) o[mt][j][i] = 0.f;
+  float mrun[2][2], lrun[2][2];  // [m tile][row g / row g + 8]
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++) { mrun[mt][0] = mrun[mt][1] = -INFINITY; lrun[mt][0] = lrun[mt][1] = 0.f; }
+  const uint32_t ks_base = (uint32_t)__cvta_generic_to_shared(&Ks[0][0]), vs_base = (uint32_t)__cvta_generic_to_shared(&Vs[0][0]);
+  constexpr uint32_t BUF = FA_K * FA_PITCH * 2;
+  auto stage = [&](int k0, int buf) {  // 64 rows x 8 chunks of 16 bytes, 8 lanes per row; rows beyond Tn are zero-filled (src-size 0)
+    for (int ch = tid; ch < FA_K * 8; ch += 128) {
+      const int row = ch >> 3, cc = (ch & 7) * 8;
+      const bool ok = k0 + row < Tn;
+      const bf16* gp = base + (int64_t)(ok ? k0 + row : Tn - 1) * ld + cc;
+      const uint32_t off = (uint32_t)((row * FA_PITCH + cc) * 2) + buf * BUF;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ks_base + off), "l"(gp + c), "r"(ok ? 16 : 0) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vs_base + off), "l"(gp + 2 * c), "r"(ok ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // per-lane ldmatrix.x4 offsets (bytes): K: row = key (lane & 7), the four matrices are the d columns (lane >> 3) * 8 of a 32-wide d block;
+  // V (transposed): row = key (lane & 15), the matrices pair (keys 0-7 / 8-15) x (d tile j, j + 1)
+  const uint32_t k_lane = (uint32_t)(((lane & 7) * FA_PITCH + (lane >> 3) * 8) * 2);
+  const uint32_t v_lane = (uint32_t)(((lane & 15) * FA_PITCH + (lane >> 4) * 8) * 2);
+  stage(0, 0);
+  for (int k0 = 0, it = 0; k0 < Tn; k0 += FA_K, it++) {
+    const int buf = it & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // tile `it` has landed; everybody is done with tile it - 1, whose buffer is refilled now
+    if (k0 + FA_K < Tn) stage(k0 + FA_K, buf ^ 1);
+    const uint32_t ks_addr = ks_base + buf * BUF + k_lane, vs_addr = vs_base + buf * BUF + v_lane;
+    // S = Q K^T for both query tiles: 8 key tiles of 8, every K fragment pair (one ldmatrix.x4) feeds 4 MMAs
+    float s[2][8][4];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) s[mt][j][i] = 0.f;
+#pragma unroll
+      for (int kp = 0; kp < 2; kp++) {  // d block of 32 = k steps 2 kp, 2 kp + 1
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(b0, b1, b2, b3, ks_addr + (uint32_t)((j * 8 * FA_PITCH + kp * 32) * 2));
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+          mma_bf16_16816(s[mt][j], qa[mt][2 * kp], b0, b1);
+          mma_bf16_16816(s[mt][j], qa[mt][2 * kp + 1], b2, b3);
+        }
+      }
+    }
+    if (k0 + FA_K > Tn) {  // key tail (last tile only, warp-uniform)
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int key = k0 + j * 8 + 2 * q4;
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+          if (key >= Tn) { s[mt][j][0] = -INFINITY; s[mt][j][2] = -INFINITY; }
+          if (key + 1 >= Tn) { s[mt][j][1] = -INFINITY; s[mt][j][3] = -INFINITY; }
+        }
+      }
+    }
+    uint32_t pa[2][4][4];  // P as A fragments: key tile pairs (2 kt, 2 kt + 1)
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        mx0 = fmaxf(mx0, fmaxf(s[mt][j][0], s[mt][j][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[mt][j][2], s[mt][j][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(mrun[mt][0], mx0), mn1 = fmaxf(mrun[mt][1], mx1);
+      const float c0 = exp2f((mrun[mt][0] - mn0) * scale_log2e), c1 = exp2f((mrun[mt][1] - mn1) * scale_log2e);  // m = -inf on the first tile -> 0
+      float l0 = lrun[mt][0] * c0, l1 = lrun[mt][1] * c1;
+#pragma unroll
+      for (int j = 0; j < 8; j++) { o[mt][j][0] *= c0; o[mt][j][1] *= c0; o[mt][j][2] *= c1; o[mt][j][3] *= c1; }
+      const float mb0 = mn0 * scale_log2e, mb1 = mn1 * scale_log2e;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float p0 = exp2f(fmaf(s[mt][j][0], scale_log2e, -mb0)), p1 = exp2f(fmaf(s[mt][j][1], scale_log2e, -mb0));
+        const float p2 = exp2f(fmaf(s[mt][j][2], scale_log2e, -mb1)), p3 = exp2f(fmaf(s[mt][j][3], scale_log2e, -mb1));
+        l0 += p0 + p1; l1 += p2 + p3;
+        pa[mt][j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
+        pa[mt][j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+      }
+      mrun[mt][0] = mn0; mrun[mt][1] = mn1; lrun[mt][0] = l0; lrun[mt][1] = l1;
+    }
+    // O += P V : k = keys (4 steps of 16), n = d (8 tiles of 8); one transposed ldmatrix.x4 = the V fragments of two d tiles, used by both query tiles
+#pragma unroll
+    for (int kt = 0; kt < 4; kt++) {
+#pragma unroll
+      for (int jp = 0; jp < 4; jp++) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_trans(b0, b1, b2, b3, vs_addr + (uint32_t)((kt * 16 * FA_PITCH + jp * 16) * 2));
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+          mma_bf16_16816(o[mt][2 * jp], pa[mt][kt], b0, b1);
+          mma_bf16_16816(o[mt][2 * jp + 1], pa[mt][kt], b2, b3);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++) {
+    float l0 = lrun[mt][0], l1 = lrun[mt][1];
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    const int r0 = q0 + mt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int col = h * HD + j * 8 + 2 * q4;
+      if (r0 < Tn) *reinterpret_cast<uint32_t*>(out + ((int64_t)n * Tn + r0) * out_ld + col) = pack_bf16(o[mt][j][0] * i0, o[mt][j][1] * i0);
+      if (r1 < Tn) *reinterpret_cast<uint32_t*>(out + ((int64_t)n * Tn + r1) * out_ld + col) = pack_bf16(o[mt][j][2] * i1, o[mt][j][3] * i1);
+    }
+  }
+}
+
+
 // ---------------------------------------------------------------------------------------------------------------------
 // AttentionTSSA (nn/modules/block.py:1646-1683, the ToST token-statistics attention of the C2TSSA_DYT_Mona_EDFFN sibling blocks; SURVEY.md
 // section 8f rank 3) on the projected tokens w = qkv(x), one CTA per image, fp32 statistics in shared memory:
@@ -431,6 +593,14 @@ int yad_mha(const yad_tensor* qkv, int heads, const yad_tensor* out, int dtype, 
   cudaStream_t st = (cudaStream_t)stream;
   const float scale = 1.0f / sqrtf((float)HD);
   if (dtype == YAD_BF16) {  // tensor-core path
+    static int v2 = -1;  // YAD_MHA_V2=0 keeps the 64-query CTA / 16 rows per warp kernel
+    if (v2 < 0) { const char* ev = getenv("YAD_MHA_V2"); v2 = (ev && ev[0] == '0') ? 0 : 1; }
+    if (v2 && Tn > FA_Q) {  // (a single 64-query CTA per (image, head) covers short sequences with less padding)
+      dim3 g3((Tn + FA2_Q - 1) / FA2_Q, qkv->n * heads);
+      YAD_LAUNCH(mha_mma2_kernel, g3, 128, 0, st, (const bf16*)qkv->ptr, qkv->ld, Tn, c, heads, (bf16*)out->ptr, out->ld, scale * 1.44269504088896340736f);
+      YAD_LAUNCH_CHECK("mha");
+      return 0;
+    }
     dim3 g2((Tn + FA_Q - 1) / FA_Q, qkv->n * heads);
     YAD_LAUNCH(mha_mma_kernel, g2, 128, 0, st, (const bf16*)qkv->ptr, qkv->ld, Tn, c, heads, (bf16*)out->ptr, out->ld, scale * 1.44269504088896340736f);
     YAD_LAUNCH_CHECK("mha");

@@ -298,6 +298,8 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
     const uint32_t lane_base = ((uint32_t)(q * 32)) << 16;
     // phase-2 geometry (mul / add on the staged piece): cpr lanes sweep one row
     const int cpr = p.sc >> 3, rpp = 32 / cpr, rr0 = lane / cpr, cj = lane - rr0 * cpr;
+    const int rsh = 31 - __clz(rpp);                                // rpp is a power of two (cpr = 2, 4, 8)
+    const int step_a = rpp * p.add_ld, step_m = rpp * p.mul_ld;     // element distance between a lane's consecutive rows (flat tiles)
     V2TileIter ti;
     ti.init(p, (int)blockIdx.x, (int)gridDim.x);
     V2Ring ar;     // accumulator stage of the current tile
@@ -385,14 +387,47 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
         return gate_mul(__ldg(ah), __ldg(aw));
       };
       const bool has_mul = p.mul || (!PATCH && p.gate_h);
+      // The epilogue is issue-bound (ncu on the lateral 1x1 + add: 51 % issue-active, 740 warp instructions per 32 x 32 piece, most of them
+      // predicates and 64-bit address arithmetic of these operand rows), so everything that does not change inside a tile is computed once:
+      // the lane's operand pointers at its first row (rows are rpp pixels = step_a / step_m elements apart), and how many of its rows are valid.
+      const bf16* add_l = nullptr;
+      const bf16* mul_l = nullptr;
+      int nrows = 0;
+      if constexpr (PREFETCH) {
+        if (pre) {
+          int64_t d0;
+          if (PATCH) {
+            // a lane's rows rr0 + k * rpp: for cpr = 4 they are the tile rows (oy) 4q + k at ox = rr0 & 7 ... only a first-row pointer is shared
+            row_pixel(rr0, d0);
+            nrows = -1;  // patch tiles keep the per-row validity test
+          } else {
+            d0 = (int64_t)m_base + rr0;
+            const int left = p.m_total - (m_base + rr0);
+            nrows = left <= 0 ? 0 : (left + rpp - 1) >> rsh;
+            nrows = nrows < cpr ? nrows : cpr;
+          }
+          add_l = p.add + d0 * p.add_ld + n0 + cj * 8;
+          mul_l = p.mul + d0 * p.mul_ld + n0 + cj * 8;
+        }
+      }
+      // is row k of this lane (k < 4) inside the map?  (d: its pixel index, patch tiles only)
+      auto row_ok = [&](int k, int64_t& d) -> bool {
+        if (PATCH) return k < cpr && row_pixel(rr0 + k * rpp, d);
+        return k < nrows;
+      };
       auto prefetch = [&](int c0) {
-        const int co = n0 + c0 + cj * 8;
+        if (n0 + c0 + cj * 8 >= p.cout) return;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          int64_t d;
-          if (k >= cpr || co >= p.cout || !row_pixel(rr0 + k * rpp, d)) continue;
-          if (p.add) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.add + d * p.add_ld + co));
-          if (p.mul) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mul + d * p.mul_ld + co));
+          int64_t d = 0;
+          if (!row_ok(k, d)) continue;
+          if (PATCH) {
+            if (p.add) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.add + d * p.add_ld + n0 + c0 + cj * 8));
+            if (p.mul) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mul + d * p.mul_ld + n0 + c0 + cj * 8));
+          } else {
+            if (p.add) asm volatile("prefetch.global.L2 [%0];" ::"l"(add_l + c0 + k * step_a));
+            if (p.mul) asm volatile("prefetch.global.L2 [%0];" ::"l"(mul_l + c0 + k * step_m));
+          }
         }
       };
       if constexpr (PREFETCH) {
@@ -434,10 +469,15 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
             for (int k = 0; k < 4; k++) {  // every row of the piece in flight at once (L2 hits after the hints above)
               pav[k] = make_uint4(0u, 0u, 0u, 0u);
               pmv[k] = make_uint4(0u, 0u, 0u, 0u);
-              int64_t d;
-              if (k >= cpr || co >= p.cout || !row_pixel(rr0 + k * rpp, d)) continue;
-              if (p.add) pav[k] = __ldg(reinterpret_cast<const uint4*>(p.add + d * p.add_ld + co));
-              if (p.mul) pmv[k] = __ldg(reinterpret_cast<const uint4*>(p.mul + d * p.mul_ld + co));
+              int64_t d = 0;
+              if (co >= p.cout || !row_ok(k, d)) continue;
+              if (PATCH) {
+                if (p.add) pav[k] = __ldg(reinterpret_cast<const uint4*>(p.add + d * p.add_ld + co));
+                if (p.mul) pmv[k] = __ldg(reinterpret_cast<const uint4*>(p.mul + d * p.mul_ld + co));
+              } else {
+                if (p.add) pav[k] = __ldg(reinterpret_cast<const uint4*>(add_l + c0 + k * step_a));
+                if (p.mul) pmv[k] = __ldg(reinterpret_cast<const uint4*>(mul_l + c0 + k * step_m));
+              }
             }
             if constexpr (!PATCH) {
               if (p.gate_h) {  // the gate rows of all four rows in flight together with the add rows (L1 / L2 residents); rows outside the map
@@ -452,7 +492,7 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                   pgw[k] = make_uint4(0u, 0u, 0u, 0u);
-                  if (k < cpr && co < p.cout && m_base + rr0 + k * rpp < p.m_total) {
+                  if (k < nrows && co < p.cout) {
                     pmv[k] = __ldg(reinterpret_cast<const uint4*>(gh0 + (gi * p.hm + gy) * p.gate_ld));
                     pgw[k] = __ldg(reinterpret_cast<const uint4*>(gw0 + (gi * p.wm + gx) * p.gate_ld));
                   }
