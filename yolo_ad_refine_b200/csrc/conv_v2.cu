@@ -199,6 +199,10 @@ struct V2Ring {
   int idx = 0;
   uint32_t ph = 0;
   __device__ __forceinline__ void next(int n) { if (++idx == n) { idx = 0; ph ^= 1u; } }
+  __device__ __forceinline__ void advance(int k, int n) {  // k steps at once (k >= 0)
+    idx += k;
+    while (idx >= n) { idx -= n; ph ^= 1u; }
+  }
 };
 
 // One unit of U (16 / 32) accumulator columns of this thread's row: TMEM -> registers -> scale / bias / activation / alpha (-> GroupNorm partial
@@ -298,14 +302,19 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
     const uint32_t lane_base = ((uint32_t)(q * 32)) << 16;
     // phase-2 geometry (mul / add on the staged piece): cpr lanes sweep one row
     const int cpr = p.sc >> 3, rpp = 32 / cpr, rr0 = lane / cpr, cj = lane - rr0 * cpr;
-    const int rsh = 31 - __clz(rpp);                                // rpp is a power of two (cpr = 2, 4, 8)
-    const int step_a = rpp * p.add_ld, step_m = rpp * p.mul_ld;     // element distance between a lane's consecutive rows (flat tiles)
+    // a lane's consecutive operand rows (phase 2, cpr <= 4): rpp pixels apart in a flat tile; rpp / 8 image rows apart (same column) in a patch tile
+    const int rstep = PATCH ? (rpp >> 3) * p.wm : rpp;              // in pixels
+    const int rsh = 31 - __clz(PATCH ? (rpp >> 3 ? rpp >> 3 : 1) : rpp);  // log2 of the row step in its own unit (image rows / pixels); powers of two
+    const int step_a = rstep * p.add_ld, step_m = rstep * p.mul_ld;  // in elements
+    // tile-split: warp group `way` takes the CTA's tiles way, way + G, way + 2 G, ...: its iterator and its accumulator ring step G tiles at a time
+    // (walking every tile and skipping G - 1 of G cost ~60 instructions per skipped tile -- tile iterator + ring with their spilled state --
+    // which for G = 4 was a third of the instructions of this issue-bound epilogue; ncu of conv3_kernel: 15 % of all warp instructions for G = 2)
+    const int g1 = G ? G : 1, first_tile = (int)blockIdx.x + (G ? way : 0) * (int)gridDim.x;
     V2TileIter ti;
-    ti.init(p, (int)blockIdx.x, (int)gridDim.x);
+    ti.init(p, first_tile, g1 * (int)gridDim.x);
     V2Ring ar;     // accumulator stage of the current tile
-    int turn = 0;  // tile-split: whose turn it is
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ti.next(p), ar.next(p.acc_stages), turn = (turn + 1 == G) ? 0 : turn + 1) {
-      if (G && turn != way) continue;  // tile-split: this warp group's turn comes every G-th tile
+    ar.advance(G ? way : 0, p.acc_stages);
+    for (int tile = first_tile; tile < p.total_tiles; tile += g1 * (int)gridDim.x, ti.next(p), ar.advance(g1, p.acc_stages)) {
       const int n0 = ti.nt * p.n_tile;
       int img = 0, ty0 = 0, tx0 = 0, m_base = 0;
       bool valid, uniform = true;
@@ -342,16 +351,6 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
       // exactly where the prefetch was meant to run ahead.  YAD_CONV2_PREFETCH=0 (p.dbg & 8) keeps the old two-rows-at-a-time loop.
       constexpr bool PREFETCH = MULADD && !GN && !SCALE;
       const bool pre = PREFETCH && (p.add || p.mul || p.gate_h) && cpr <= 4 && !(p.dbg & 8);
-      // pixel index of row `row` of this warp's 32 rows; false outside the map
-      auto row_pixel = [&](int row, int64_t& d) -> bool {
-        if (PATCH) {
-          const int oy = ty0 + 4 * q + (row >> 3), ox = tx0 + (row & 7);
-          d = (int64_t)(img * p.hm + oy) * p.wm + ox;
-          return oy < p.hm && ox < p.wm;
-        }
-        d = (int64_t)m_base + row;
-        return d < p.m_total;
-      };
       // separable gate of a flat (1x1) tile: (image, y, x) of this warp's first row once per tile (two integer divisions), rows step from there
       int g_img = 0, g_y = 0, g_x = 0;
       if constexpr (MULADD && !PATCH) {
@@ -396,38 +395,28 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
       if constexpr (PREFETCH) {
         if (pre) {
           int64_t d0;
-          if (PATCH) {
-            // a lane's rows rr0 + k * rpp: for cpr = 4 they are the tile rows (oy) 4q + k at ox = rr0 & 7 ... only a first-row pointer is shared
-            row_pixel(rr0, d0);
-            nrows = -1;  // patch tiles keep the per-row validity test
+          int left;  // valid rows from the lane's first row on, in units of one row step
+          if (PATCH) {  // rows rr0 + k * rpp of the 8-pixel-wide tile: the same column ox, image rows (rpp >> 3) apart
+            const int oy0 = ty0 + 4 * q + (rr0 >> 3), ox = tx0 + (rr0 & 7);
+            d0 = (int64_t)(img * p.hm + oy0) * p.wm + ox;
+            left = ox < p.wm ? p.hm - oy0 : 0;
           } else {
             d0 = (int64_t)m_base + rr0;
-            const int left = p.m_total - (m_base + rr0);
-            nrows = left <= 0 ? 0 : (left + rpp - 1) >> rsh;
-            nrows = nrows < cpr ? nrows : cpr;
+            left = p.m_total - (m_base + rr0);
           }
+          nrows = left <= 0 ? 0 : (left + (1 << rsh) - 1) >> rsh;
+          nrows = nrows < cpr ? nrows : cpr;
           add_l = p.add + d0 * p.add_ld + n0 + cj * 8;
           mul_l = p.mul + d0 * p.mul_ld + n0 + cj * 8;
         }
       }
-      // is row k of this lane (k < 4) inside the map?  (d: its pixel index, patch tiles only)
-      auto row_ok = [&](int k, int64_t& d) -> bool {
-        if (PATCH) return k < cpr && row_pixel(rr0 + k * rpp, d);
-        return k < nrows;
-      };
       auto prefetch = [&](int c0) {
         if (n0 + c0 + cj * 8 >= p.cout) return;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          int64_t d = 0;
-          if (!row_ok(k, d)) continue;
-          if (PATCH) {
-            if (p.add) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.add + d * p.add_ld + n0 + c0 + cj * 8));
-            if (p.mul) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mul + d * p.mul_ld + n0 + c0 + cj * 8));
-          } else {
-            if (p.add) asm volatile("prefetch.global.L2 [%0];" ::"l"(add_l + c0 + k * step_a));
-            if (p.mul) asm volatile("prefetch.global.L2 [%0];" ::"l"(mul_l + c0 + k * step_m));
-          }
+          if (k >= nrows) continue;
+          if (p.add) asm volatile("prefetch.global.L2 [%0];" ::"l"(add_l + c0 + k * step_a));
+          if (p.mul) asm volatile("prefetch.global.L2 [%0];" ::"l"(mul_l + c0 + k * step_m));
         }
       };
       if constexpr (PREFETCH) {
@@ -469,15 +458,9 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
             for (int k = 0; k < 4; k++) {  // every row of the piece in flight at once (L2 hits after the hints above)
               pav[k] = make_uint4(0u, 0u, 0u, 0u);
               pmv[k] = make_uint4(0u, 0u, 0u, 0u);
-              int64_t d = 0;
-              if (co >= p.cout || !row_ok(k, d)) continue;
-              if (PATCH) {
-                if (p.add) pav[k] = __ldg(reinterpret_cast<const uint4*>(p.add + d * p.add_ld + co));
-                if (p.mul) pmv[k] = __ldg(reinterpret_cast<const uint4*>(p.mul + d * p.mul_ld + co));
-              } else {
-                if (p.add) pav[k] = __ldg(reinterpret_cast<const uint4*>(add_l + c0 + k * step_a));
-                if (p.mul) pmv[k] = __ldg(reinterpret_cast<const uint4*>(mul_l + c0 + k * step_m));
-              }
+              if (co >= p.cout || k >= nrows) continue;
+              if (p.add) pav[k] = __ldg(reinterpret_cast<const uint4*>(add_l + c0 + k * step_a));
+              if (p.mul) pmv[k] = __ldg(reinterpret_cast<const uint4*>(mul_l + c0 + k * step_m));
             }
             if constexpr (!PATCH) {
               if (p.gate_h) {  // the gate rows of all four rows in flight together with the add rows (L1 / L2 residents); rows outside the map
