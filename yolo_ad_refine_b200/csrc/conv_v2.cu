@@ -188,10 +188,13 @@ struct V2TileIter {
     d_tx = mt % p.tiles_x; mt /= p.tiles_x;
     d_ty = mt % p.tiles_y; d_img = mt / p.tiles_y;
   }
+  template <bool PATCH = true>
   __device__ __forceinline__ void next(const V2Params& p) {
     nt += d_nt; int c = nt >= p.tiles_n ? 1 : 0; nt -= c ? p.tiles_n : 0;
-    tx += d_tx + c; c = tx >= p.tiles_x ? 1 : 0; tx -= c ? p.tiles_x : 0;
-    ty += d_ty + c; c = ty >= p.tiles_y ? 1 : 0; ty -= c ? p.tiles_y : 0;
+    if constexpr (PATCH) {
+      tx += d_tx + c; c = tx >= p.tiles_x ? 1 : 0; tx -= c ? p.tiles_x : 0;
+      ty += d_ty + c; c = ty >= p.tiles_y ? 1 : 0; ty -= c ? p.tiles_y : 0;
+    }  // flat tiles: tiles_x = tiles_y = 1, tx = ty = d_tx = d_ty = 0 and the carry goes straight to the M-tile index
     img += d_img + c;
   }
 };
@@ -314,7 +317,7 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
     ti.init(p, first_tile, g1 * (int)gridDim.x);
     V2Ring ar;     // accumulator stage of the current tile
     ar.advance(G ? way : 0, p.acc_stages);
-    for (int tile = first_tile; tile < p.total_tiles; tile += g1 * (int)gridDim.x, ti.next(p), ar.advance(g1, p.acc_stages)) {
+    for (int tile = first_tile; tile < p.total_tiles; tile += g1 * (int)gridDim.x, ti.template next<PATCH>(p), ar.advance(g1, p.acc_stages)) {
       const int n0 = ti.nt * p.n_tile;
       int img = 0, ty0 = 0, tx0 = 0, m_base = 0;
       bool valid, uniform = true;
@@ -628,7 +631,7 @@ __global__ void __launch_bounds__(V2_MAX_THREADS, 1) conv2_kernel(const __grid_c
       V2TileIter ti;
       ti.init(p, (int)blockIdx.x, (int)gridDim.x);
       V2Ring sr;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ti.next(p)) {
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ti.template next<PATCH>(p)) {
         const int img = ti.img, ty0 = ti.ty * V2_BH, tx0 = ti.tx * V2_BW;
         for (int c = 0; c < p.kpt; c++, sr.next(p.stages)) {
           const int s = sr.idx;
@@ -1220,7 +1223,12 @@ static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilog
   if (ts_env < 0) ts_env = v2_env("YAD_CONV2_TSPLIT", 1);
   // measured (profiles/r2_conv_tsplit.txt): 1x1 convolutions with <= 64 output channels gain 10-17 %; the 3x3 patch kernels are not bound by the
   // epilogue's latency and keep the column split (YAD_CONV2_TSPLIT=2 forces the tile split there too)
-  const bool tsplit = ts_env && p.n_tile <= 64 && p.ksplit == 1 && (flat || ts_env == 2);
+  // 1x1 tiles of 65 .. 128 columns (4 accumulator stages for the 4 warp groups): measured at batch 64 @80^2 after the warp groups stopped walking
+  // the tiles of the other groups: 128 -> 128 plain 43.9 (column split) vs 45.6 us (tile split), + add 77.4 vs 68.4, + gate + add 97.0 vs 86.5,
+  // 64 -> 80 (96-column tile) 37.3 vs 28.9 -- tile split when the epilogue carries operand rows or the column shares are uneven
+  // (YAD_CONV2_TSPLIT=3: always, 0: never)
+  const bool wide_ts = flat && p.n_tile > 64 && p.n_tile <= 128 && (ts_env == 3 || e->mul || e->add || e->gate_h || (p.n_tile % 64));
+  const bool tsplit = ts_env && p.ksplit == 1 && ((p.n_tile <= 64 && (flat || ts_env == 2)) || wide_ts);
   p.acc_stages = (2 * p.ksplit * p.n_tile <= 512) ? 2 : 1;
   if (tsplit) p.acc_stages = 512 / p.n_tile < V2_MAX_ACC ? 512 / p.n_tile : V2_MAX_ACC;
   p.tmem_cols = 32;
