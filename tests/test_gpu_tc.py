@@ -168,3 +168,22 @@ def test_conv_v2_pix_scale_alpha_and_relu_variants(n, h, w, cin, cout):
     assert rel_err(from_act(out, cout), (F.conv2d(x, wt) * pix[:, :1] + b.view(1, -1, 1, 1)) * 0.5) < TOL
     ops.conv2d(to_act(x, BF), cw.w, out, bias=cw.b, act=ops.ACT_RELU)
     assert rel_err(from_act(out, cout), F.relu(F.conv2d(x, wt, b))) < TOL
+
+
+@pytest.mark.parametrize("n,cin,cout,h,w", [(2, 32, 24, 7, 9), (3, 128, 128, 20, 20), (1, 64, 64, 17, 33), (2, 128, 64, 16, 8), (64, 128, 128, 10, 10)])
+def test_conv_transposed_on_conv2_kernel(n, cin, cout, h, w):
+    """nn.ConvTranspose2d(k3, s2, p1, op1) (z-yaml layers 13 / 20) as four output phases on conv2_kernel (impl 4 forces that path on small maps):
+    run-time tap lists, patch origin at the tile, strided TMA store"""
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = q(torch.randn(n, cin, h, w, generator=g))
+    wt = q(torch.randn(cin, cout, 3, 3, generator=g) / (cin * 2.25) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv_transpose2d(x, wt, b, stride=2, padding=1, output_padding=1)
+    cw = pack_conv(wt, b, BF, DEV, transposed=True)
+    out = Act.empty(n, 2 * h, 2 * w, cw.cout, BF, DEV)
+    out.buf.fill_(float("nan"))
+    ops.conv2d(to_act(x, BF), cw.w, out, bias=cw.b, kh=3, kw=3, stride=2, pad_h=1, pad_w=1, mode=ops.CONV_TRANSPOSED, impl=4)
+    assert rel_err(from_act(out, cout), ref) < TOL
+    out5 = Act.empty(n, 2 * h, 2 * w, cw.cout, BF, DEV)
+    ops.conv2d(to_act(x, BF), cw.w, out5, bias=cw.b, kh=3, kw=3, stride=2, pad_h=1, pad_w=1, mode=ops.CONV_TRANSPOSED, impl=5)  # conv_tma_kernel
+    assert rel_err(from_act(out, cout), from_act(out5, cout)) < 1e-2

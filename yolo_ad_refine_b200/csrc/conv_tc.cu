@@ -806,6 +806,7 @@ int pick_n_tile(int cout);
 int yad_conv2d_v2_supported(const yad_tensor* x, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y);
 int yad_conv2d_v2(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream);
 int yad_conv2d_dcn_v2(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream);
+int yad_conv2d_v2_transposed(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream);
 namespace {
 
 // best (bw, bh) with bw * bh <= 128 for an (h, w) map: maximise useful pixels per 128-row MMA tile
@@ -1075,6 +1076,11 @@ int yad_conv2d_tc(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
   if (d->mode == YAD_CONV_TRANSPOSED) {
     YAD_CHECK(d->kh == 3 && d->kw == 3 && d->stride == 2 && d->pad_h == 1 && d->pad_w == 1 && y->h == 2 * x->h && y->w == 2 * x->w,
               "conv2d: transposed mode is k3 s2 p1 op1 only");
+    if (d->impl != 3 && d->impl != 5 && !p.bn_stats) {  // the four phases on conv2_kernel (haloed patch, resident taps, strided TMA store)
+      const int r = yad_conv2d_v2_transposed(x, w, d, e, y, stream);
+      if (r >= 0) return r;
+      YAD_CHECK(d->impl != 4, "conv2d: impl 4 (resident-weight tcgen05 kernel) does not support this transposed shape / epilogue");
+    }
     // oy = 2*iy - 1 + ky: even rows take ky = 1 (iy = m); odd rows take ky = 0 (iy = m + 1) and ky = 2 (iy = m)
     p.hm = x->h; p.wm = x->w; p.stride = 1; p.os = 2;
     for (int py = 0; py < 2; py++)

@@ -46,6 +46,10 @@ struct V2Params {
   int tiles_x, tiles_y;     // patch mode: tiles per image
   int kpt, ntaps, pw;       // 64-wide K chunks per tap; taps; patch pitch in pixels
   int tap_row[9];           // patch row (= pixel index inside the patch) the A descriptor of tap t starts at
+  int custom;               // 1: tap list given at run time (a phase of the stride-2 transposed convolution: 1, 2 or 4 taps with offsets 0 / +1);
+                            // the patch then starts AT the tile's first pixel (org = 0) and weight tap t sits at K offset wtap[t] * cin
+  int org;                  // the haloed patch starts org pixels left of / above the tile (1 for the 3x3 pad-1 convolution)
+  int wtap[9];
   int stages, acc_stages, tmem_cols;
   int dbg;                  // bring-up / profiling switch (YAD_CONV2_DBG): 1 = the MMA lane issues nothing, 2 = the epilogue skips its TMEM reads and math (results are garbage)
   int tsplit;               // narrow tiles (n_tile <= 64): number of epilogue warp groups (4 warps = the 4 TMEM lane quarters) that take whole tiles in
@@ -625,7 +629,7 @@ __global__ void __launch_bounds__(V2_MAX_THREADS, 1) conv2_kernel(const __grid_c
         const int c = i % p.kpt, t = (i / p.kpt) % p.ntaps, nt = i / (p.kpt * p.ntaps);
         if (leader) {
           mbar_expect_tx(b_bar(i), p.b_chunk_bytes);
-          tma_load_2d(base + p.off_b + (uint32_t)i * p.b_chunk_bytes, &tmB, b_bar(i), t * p.cin + c * 64, nt * p.n_tile);
+          tma_load_2d(base + p.off_b + (uint32_t)i * p.b_chunk_bytes, &tmB, b_bar(i), (p.custom ? p.wtap[t] : t) * p.cin + c * 64, nt * p.n_tile);
         }
       }
       V2TileIter ti;
@@ -639,7 +643,7 @@ __global__ void __launch_bounds__(V2_MAX_THREADS, 1) conv2_kernel(const __grid_c
           mbar_wait(empty_bar(s), sr.ph ^ 1u);
           if (leader) {
             mbar_expect_tx(full_bar(s), p.a_tx_bytes);
-            if (PATCH) tma_load_4d(a_s, &tmA, full_bar(s), c * 64, tx0 - 1, ty0 - 1, img);
+            if (PATCH) tma_load_4d(a_s, &tmA, full_bar(s), c * 64, tx0 - p.org, ty0 - p.org, img);
             else tma_load_2d(a_s, &tmA, full_bar(s), c * 64, img * V2_BM);
           }
         }
@@ -679,12 +683,24 @@ __global__ void __launch_bounds__(V2_MAX_THREADS, 1) conv2_kernel(const __grid_c
           mbar_wait(full_bar(s), sr.ph);
           tc_fence_after();
           const uint32_t a_lo0 = v2_desc_lo(base + p.off_a + (uint32_t)s * p.a_stage_bytes);
-          const int bi0 = nt * NT * p.kpt + c;                      // chunk of tap 0
+          const int bi0 = nt * (PATCH && p.custom ? p.ntaps : NT) * p.kpt + c;  // chunk of tap 0
           const uint32_t b_lo_c = b_lo0 + (uint32_t)bi0 * b_step;
           const int krem = p.cin - c * 64;
           const int ksteps = krem >= 64 ? 4 : (krem + 15) >> 4;
           const uint32_t acc0 = c > 0 ? 1u : 0u;                    // the first MMA of the tile overwrites the accumulator
-          if (first_pass) {
+          if (PATCH && p.custom) {  // run-time tap list (transposed-convolution phase): 1, 2 or 4 taps, one accumulator
+            for (int t = 0; t < p.ntaps; t++) {
+              if (first_pass) {
+                mbar_wait(b_bar(bi0 + t * p.kpt), 0u);
+                tc_fence_after();
+              }
+              const uint32_t a_lo = a_lo0 + (uint32_t)p.tap_row[t] * 8u, b_lo = b_lo_c + (uint32_t)t * tstep;
+              if (leader) {
+                umma_f16(d_tmem, pack64(a_lo, a_hi), pack64(b_lo, b_hi), idesc, t > 0 ? 1u : acc0);
+                for (int k = 1; k < ksteps; k++) umma_bf16<true>(d_tmem, pack64(a_lo + 2u * k, a_hi), pack64(b_lo + 2u * k, b_hi), idesc);
+              }
+            }
+          } else if (first_pass) {
             for (int t = 0; t < NT; t++) {
               mbar_wait(b_bar(bi0 + t * p.kpt), 0u);
               tc_fence_after();
@@ -1170,15 +1186,28 @@ int pick_n_tile_v2(int cout) {
 
 }  // namespace
 
+// One output phase (oy % 2, ox % 2) = (py, px) of the k3 s2 p1 op1 transposed convolution (nn.ConvTranspose2d of the neck, z-yaml layers 13 / 20):
+// a stride-1 convolution over the INPUT grid with 1, 2 or 4 taps at offsets 0 / +1, written to every second pixel of every second output row.
+struct V2Phase {
+  int py, px, ntaps;
+  int dy[4], dx[4], wtap[4];  // input offset of tap t and its index in the [cout][9][cin] weights
+};
+
 // 0: not eligible (the caller falls back to conv_tma_kernel / conv_tc_kernel); fills the launch plan otherwise
-static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, V2Params* out, size_t* smem_out) {
-  if (d->mode != YAD_CONV_NORMAL || d->stride != 1) return 0;
-  const bool flat = d->kh == 1 && d->kw == 1 && d->pad_h == 0 && d->pad_w == 0;
-  const bool patch = d->kh == 3 && d->kw == 3 && d->pad_h == 1 && d->pad_w == 1;
+static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, V2Params* out, size_t* smem_out,
+                   const V2Phase* phase = nullptr) {
+  if (phase) {
+    if (d->mode != YAD_CONV_TRANSPOSED || y->h != 2 * x->h || y->w != 2 * x->w || y->n != x->n) return 0;
+    if (e->mul || e->add || e->gate_h || e->gn_stats || e->img_scale || e->pix_scale) return 0;
+  } else if (d->mode != YAD_CONV_NORMAL || d->stride != 1) {
+    return 0;
+  }
+  const bool flat = !phase && d->kh == 1 && d->kw == 1 && d->pad_h == 0 && d->pad_w == 0;
+  const bool patch = phase || (d->kh == 3 && d->kw == 3 && d->pad_h == 1 && d->pad_w == 1);
   if (!flat && !patch) return 0;
   if (x->c < 16 || (x->c % 8) || (y->c % 8) || (x->ld % 8) || (y->ld % 8)) return 0;
   if (((uintptr_t)x->ptr & 15) || ((uintptr_t)y->ptr & 15)) return 0;
-  if (y->h != x->h || y->w != x->w || y->n != x->n) return 0;
+  if (!phase && (y->h != x->h || y->w != x->w || y->n != x->n)) return 0;
   if (e->gn_stats && e->gn_groups == 0) return 0;  // fused batch statistics (train-mode BatchNorm) stay on conv_tma_kernel<true>
   if (patch && (e->img_scale || e->pix_scale)) return 0;
   if ((e->mul && ((uintptr_t)e->mul & 15 || e->mul_ld % 8)) || (e->add && ((uintptr_t)e->add & 15 || e->add_ld % 8))) return 0;
@@ -1188,7 +1217,7 @@ static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilog
   if (M + V2_BM >= (int64_t)1 << 31) return 0;
   V2Params p;
   memset(&p, 0, sizeof(p));
-  p.n = x->n; p.hm = y->h; p.wm = y->w; p.hw = y->h * y->w; p.cin = x->c; p.cout = y->c; p.m_total = (int)M;
+  p.n = x->n; p.hm = x->h; p.wm = x->w; p.hw = x->h * x->w; p.cin = x->c; p.cout = y->c; p.m_total = (int)M;  // output grid = input grid (per phase)
   p.n_tile = pick_n_tile_v2(p.cout);
   {
     // 80 / 112 / ... output channels: the columns are dealt to the epilogue warps in units of 16, and one 16-column share forces 16-column (32-byte)
@@ -1199,7 +1228,7 @@ static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilog
     if (npad_env && !e->gn_stats && p.n_tile > 64 && (p.n_tile % 32) && p.n_tile + 16 <= 256 && p.cout <= p.n_tile) p.n_tile += 16;
   }
   p.tiles_n = (p.cout + p.n_tile - 1) / p.n_tile;
-  p.ntaps = patch ? 9 : 1;
+  p.ntaps = phase ? phase->ntaps : (patch ? 9 : 1);
   p.kpt = (p.cin + 63) / 64;
   if (p.tiles_n * p.ntaps * p.kpt > V2_MAX_BCHUNKS) return 0;
   if (e->gn_stats) {
@@ -1258,12 +1287,18 @@ static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilog
     p.tiles_x = (p.wm + V2_BW - 1) / V2_BW;
     p.tiles_y = (p.hm + V2_BH - 1) / V2_BH;
     for (int t = 0; t < 9; t++) p.tap_row[t] = (t / 3) * p.pw + (t % 3);
+    p.org = 1;
+    if (phase) {
+      p.custom = 1;
+      p.org = 0;
+      for (int t = 0; t < phase->ntaps; t++) { p.tap_row[t] = phase->dy[t] * p.pw + phase->dx[t]; p.wtap[t] = phase->wtap[t]; }
+    }
     p.a_tx_bytes = (uint32_t)(p.pw * (V2_BH + 2) * 128);
     p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
     p.total_tiles = p.n * p.tiles_x * p.tiles_y * p.tiles_n;
     // few tiles per CTA (20 x 20 maps at batch 64: 2.6): loading the whole weight matrix up front does not pay and the fixed 16 x 8 tile wastes half
     // of its rows; conv_tma_kernel with its fitted patch measured 8.1 us against 12.1 us here (profiles/r2_launch_floor_20.jsonl)
-    if (p.total_tiles < 5 * 148 && d->impl != 4) return 0;
+    if (p.total_tiles < 5 * 148 && d->impl != 4) return 0;  // (transposed phases alike: 20 -> 40 at batch 64 measured 51 us here, 43.5 us on conv_tma_kernel)
   } else {
     p.tiles_x = p.tiles_y = 1;
     p.a_tx_bytes = V2_BM * 128;
@@ -1318,11 +1353,11 @@ int yad_conv2d_v2_supported(const yad_tensor* x, const yad_conv_desc* d, const y
   return v2_plan(x, d, e, y, &p, &smem);
 }
 
-// The caller (yad_conv2d_tc) has validated shapes and zeroed the GroupNorm statistics buffer.
-int yad_conv2d_v2(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream) {
+static int v2_run(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream,
+                  const V2Phase* phase) {
   V2Params p;
   size_t smem = 0;
-  const int kind = v2_plan(x, d, e, y, &p, &smem);
+  const int kind = v2_plan(x, d, e, y, &p, &smem, phase);
   YAD_CHECK(kind != 0, "conv2d_v2: shape / epilogue not supported by the resident-weight tcgen05 kernel");
   const bool patch = kind == 2;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1346,7 +1381,13 @@ int yad_conv2d_v2(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
   }
   {
     const CUtensorMapSwizzle sw = p.sc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.sc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    if (patch) {
+    if (phase) {  // every second pixel of every second row, starting at (py, px): the phase's pixels as a dense (c, w / 2, h / 2, n) tensor
+      uint64_t dims[4] = {(uint64_t)y->c, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)y->n};
+      uint64_t strides[3] = {(uint64_t)y->ld * 4, (uint64_t)y->w * y->ld * 4, (uint64_t)y->h * y->w * y->ld * 2};
+      uint32_t box[4] = {(uint32_t)p.sc, V2_BW, 4, 1};
+      const bf16* y0 = reinterpret_cast<const bf16*>(y->ptr) + ((int64_t)phase->py * y->w + phase->px) * y->ld;
+      if (v2_make_map(&tmY, y0, 4, dims, strides, box, sw)) return 1;
+    } else if (patch) {
       uint64_t dims[4] = {(uint64_t)y->c, (uint64_t)y->w, (uint64_t)y->h, (uint64_t)y->n};
       uint64_t strides[3] = {(uint64_t)y->ld * 2, (uint64_t)y->w * y->ld * 2, (uint64_t)y->h * y->w * y->ld * 2};
       uint32_t box[4] = {(uint32_t)p.sc, V2_BW, 4, 1};
@@ -1366,6 +1407,44 @@ int yad_conv2d_v2(const yad_tensor* x, const void* w, const yad_conv_desc* d, co
   int grid = num_sms < p.total_tiles ? num_sms : p.total_tiles;
   if (patch) return v2_dispatch<true>(p, tmA, tmB, tmY, grid, smem, st);
   return v2_dispatch<false>(p, tmA, tmB, tmY, grid, smem, st);
+}
+
+// The caller (yad_conv2d_tc) has validated shapes and zeroed the GroupNorm statistics buffer.
+int yad_conv2d_v2(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream) {
+  return v2_run(x, w, d, e, y, stream, nullptr);
+}
+
+// k3 s2 p1 op1 transposed convolution as four launches of conv2_kernel, one per output phase (oy = 2 iy - 1 + ky: even rows take ky = 1 at
+// iy = m, odd rows ky = 2 at iy = m and ky = 0 at iy = m + 1; columns alike).  Every phase reads the input through the haloed-patch pipeline
+// with its 1, 2 or 4 weight taps resident and stores its pixels with a strided TMA map.  Returns -1 when the call is not covered (the caller
+// keeps the per-phase conv_tma_kernel launches), 0 when the four launches were issued, > 0 on error.
+int yad_conv2d_v2_transposed(const yad_tensor* x, const void* w, const yad_conv_desc* d, const yad_epilogue* e, const yad_tensor* y, void* stream) {
+  static int on = -1;
+  if (on < 0) on = v2_env("YAD_CONV_V2", 1) && v2_env("YAD_CONV2_TRANSPOSED", 1);
+  if ((!on && d->impl != 4) || !get_encode()) return -1;
+  if (d->kh != 3 || d->kw != 3 || d->stride != 2 || d->pad_h != 1 || d->pad_w != 1) return -1;
+  V2Phase ph[4];
+  for (int py = 0; py < 2; py++)
+    for (int px = 0; px < 2; px++) {
+      V2Phase& f = ph[py * 2 + px];
+      f.py = py; f.px = px; f.ntaps = 0;
+      for (int ky = 0; ky < 3; ky++) {
+        if ((py + 1 - ky) & 1) continue;
+        for (int kx = 0; kx < 3; kx++) {
+          if ((px + 1 - kx) & 1) continue;
+          f.dy[f.ntaps] = (py + 1 - ky) / 2; f.dx[f.ntaps] = (px + 1 - kx) / 2; f.wtap[f.ntaps] = ky * 3 + kx;
+          f.ntaps++;
+        }
+      }
+      V2Params p;
+      size_t smem;
+      if (!v2_plan(x, d, e, y, &p, &smem, &f)) return -1;  // all four phases or none
+    }
+  for (int i = 0; i < 4; i++) {
+    const int r = v2_run(x, w, d, e, y, stream, &ph[i]);
+    if (r) return r;
+  }
+  return 0;
 }
 
 // Small-channel 3x3 stride-1 convolution on conv3_kernel.  Returns -1 when the call is not covered (the caller goes on to conv_small_kernel /
