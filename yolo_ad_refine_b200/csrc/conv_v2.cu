@@ -56,6 +56,7 @@ struct V2Params {
                             // turn instead of sharing the columns of one tile (0: column split); several tiles' epilogue latencies then overlap
   int ksplit;               // 3x3: taps are dealt round-robin to `ksplit` accumulators (independent tcgen05.mma dependency chains), summed in the epilogue
   uint32_t off_b, b_chunk_bytes, off_a, a_stage_bytes, a_tx_bytes, off_stg, stg_warp_bytes, off_bias, off_bars;
+  uint32_t off_pf, pf_warp_bytes;  // operand-row staging (cp.async): per epilogue warp 2 KB per operand (4 rows x 32 lanes x 16 bytes); 0 = not allocated
   int sc, ew, stg_bufs;     // columns per TMA store box (16 / 32 / 64); epilogue warps (8 / 16); staging tiles per warp (2: the bulk store of piece i
                             // is still reading its tile while piece i + 1 is staged)
   int bnd[5];               // column ranges [bnd[w], bnd[w + 1]) of the ew / 4 warps that share a TMEM lane quarter
@@ -313,6 +314,8 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
     const int rstep = PATCH ? (rpp >> 3) * p.wm : rpp;              // in pixels
     const int rsh = 31 - __clz(PATCH ? (rpp >> 3 ? rpp >> 3 : 1) : rpp);  // log2 of the row step in its own unit (image rows / pixels); powers of two
     const int step_a = rstep * p.add_ld, step_m = rstep * p.mul_ld;  // in elements
+    const bool pf_smem = MULADD && p.pf_warp_bytes != 0u && cpr <= 4 && !(p.dbg & 8);
+    const uint32_t pf_lane = base + p.off_pf + (uint32_t)ew * p.pf_warp_bytes + (uint32_t)lane * 16u, pf_mul = p.add ? 2048u : 0u;
     // tile-split: warp group `way` takes the CTA's tiles way, way + G, way + 2 G, ...: its iterator and its accumulator ring step G tiles at a time
     // (walking every tile and skipping G - 1 of G cost ~60 instructions per skipped tile -- tile iterator + ring with their spilled state --
     // which for G = 4 was a third of the instructions of this issue-bound epilogue; ncu of conv3_kernel: 15 % of all warp instructions for G = 2)
@@ -419,6 +422,16 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
       }
       auto prefetch = [&](int c0) {
         if (n0 + c0 + cj * 8 >= p.cout) return;
+        if (pf_smem) {  // cp.async into this lane's own slots (row k at + 512 bytes, the mul block behind the add block): no cross-lane hazards
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (k >= nrows) continue;
+            if (p.add) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pf_lane + 512u * k), "l"(add_l + c0 + k * step_a) : "memory");
+            if (p.mul) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pf_lane + pf_mul + 512u * k), "l"(mul_l + c0 + k * step_m) : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          return;
+        }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           if (k >= nrows) continue;
@@ -461,13 +474,19 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
             __syncwarp();
             const int co = n0 + c0 + cj * 8;
             uint4 pav[4], pmv[4];
+            if (pf_smem) asm volatile("cp.async.wait_group 0;" ::: "memory");  // this lane's own copies have landed
 #pragma unroll
             for (int k = 0; k < 4; k++) {  // every row of the piece in flight at once (L2 hits after the hints above)
               pav[k] = make_uint4(0u, 0u, 0u, 0u);
               pmv[k] = make_uint4(0u, 0u, 0u, 0u);
               if (co >= p.cout || k >= nrows) continue;
-              if (p.add) pav[k] = __ldg(reinterpret_cast<const uint4*>(add_l + c0 + k * step_a));
-              if (p.mul) pmv[k] = __ldg(reinterpret_cast<const uint4*>(mul_l + c0 + k * step_m));
+              if (pf_smem) {
+                if (p.add) pav[k] = lds16(pf_lane + 512u * k);
+                if (p.mul) pmv[k] = lds16(pf_lane + pf_mul + 512u * k);
+              } else {
+                if (p.add) pav[k] = __ldg(reinterpret_cast<const uint4*>(add_l + c0 + k * step_a));
+                if (p.mul) pmv[k] = __ldg(reinterpret_cast<const uint4*>(mul_l + c0 + k * step_m));
+              }
             }
             if constexpr (!PATCH) {
               if (p.gate_h) {  // the gate rows of all four rows in flight together with the add rows (L1 / L2 residents); rows outside the map
@@ -494,7 +513,7 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
                 for (int k = 0; k < 4; k++) pmv[k] = gate_mul(pmv[k], pgw[k]);
               }
             }
-            if (c0 + p.sc < ce) prefetch(c0 + p.sc);  // the next piece's operands travel under this piece's store and the next TMEM reads
+            if (!pf_smem && c0 + p.sc < ce) prefetch(c0 + p.sc);  // the next piece's operands travel under this piece's store and the next TMEM reads
 #pragma unroll
             for (int k = 0; k < 4; k++) {
               if (k >= cpr) continue;
@@ -516,6 +535,8 @@ __device__ __forceinline__ void v2_epilogue(const V2Params& p, const CUtensorMap
               }
               sts16v(ca, u);
             }
+            // staged operands: the slots are refilled only after their values have been consumed above
+            if (pf_smem && c0 + p.sc < ce) prefetch(c0 + p.sc);
           }
         }
         if constexpr (MULADD) {
@@ -1327,13 +1348,28 @@ static int v2_plan(const yad_tensor* x, const yad_conv_desc* d, const yad_epilog
     if (stages >= min_stages) break;
   }
   if (stages < 2) return 0;
+  // operand rows (add / mul) staged through shared memory by cp.async, issued ahead of the accumulator reads: taken out of the activation ring when
+  // that keeps at least 4 (1x1) / 2 (3x3) stages (YAD_CONV2_PFSMEM=0: L2 prefetch hints + direct loads only)
+  uint32_t pf_total = 0;
+  {
+    static int pf_env = -1;
+    if (pf_env < 0) pf_env = v2_env("YAD_CONV2_PFSMEM", 1);
+    const int nops = (e->add ? 1 : 0) + (e->mul ? 1 : 0);
+    if (pf_env && nops && !e->gn_stats && !e->img_scale && !e->pix_scale && p.sc <= 32) {
+      const uint32_t want = (uint32_t)(p.ew * nops) * 2048u, floor_stages = patch ? 2u : 4u;
+      uint32_t st2 = stages;
+      while (st2 >= floor_stages && total(st2) + want > budget) st2--;
+      if (st2 >= floor_stages) { stages = st2; pf_total = want; p.pf_warp_bytes = (uint32_t)nops * 2048u; }
+    }
+  }
   p.stages = (int)stages;
   p.off_b = 0;
   p.off_a = b_total;
   p.off_stg = p.off_a + stages * p.a_stage_bytes;
-  p.off_bias = p.off_stg + stg_total;
+  p.off_pf = p.off_stg + stg_total;
+  p.off_bias = p.off_pf + pf_total;
   p.off_bars = p.off_bias + bias_bytes;
-  *smem_out = 1024 + total(stages);
+  *smem_out = 1024 + total(stages) + pf_total;
   p.bias = e->bias; p.img_scale = e->img_scale; p.pix_scale = (const bf16*)e->pix_scale; p.pix_scale_ld = e->pix_scale_ld;
   p.act = e->act; p.alpha = e->alpha;
   p.mul = (const bf16*)e->mul; p.mul_ld = e->mul_ld; p.add = (const bf16*)e->add; p.add_ld = e->add_ld;
