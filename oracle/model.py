@@ -483,7 +483,8 @@ def train_step_grads(sd, img, batch_idx, cls, bboxes, gains=(7.5, 0.5, 1.5)):
     work["__bn_train__"] = True
     work["__bn_updates__"] = {}
     feats = forward(work, img, training=True, grad=True)
-    loss, items, aux = detection_loss(feats, batch_idx, cls, bboxes, gains=gains)
+    nc = int(sd["model.33.cv3.weight"].shape[0])  # the class count lives in the head's cv3 (head.py:1094-1097), 80 in the yaml
+    loss, items, aux = detection_loss(feats, batch_idx, cls, bboxes, nc=nc, gains=gains)
     loss.backward()
     grads = {k: (p.grad if p.grad is not None else None) for k, p in params.items()}
     return loss.detach(), items, grads, work["__bn_updates__"], [f.detach() for f in feats]

@@ -1088,8 +1088,16 @@ __global__ void head_pack_kernel(yad_tensor lv, int a0, int N, int nd, int nc, f
     const int64_t b = p / hw, a = a0 + p % hw;
     float v[8];
     load8(reinterpret_cast<const T*>(lv.ptr) + p * lv.ld + o, v);
-    float* dst = o < nd ? distri + (b * N + a) * nd + o : logits + (b * N + a) * nc + (o - nd);
-    store8(dst, v);
+    if (o < nd) {
+      store8(distri + (b * N + a) * nd + o, v);
+    } else if ((nc & 7) == 0) {
+      store8(logits + (b * N + a) * nc + (o - nd), v);
+    } else {  // class count not a multiple of 8 (custom datasets): the level carries pad8(nc) class channels, the loss sees the first nc
+      float* dst = logits + (b * N + a) * nc;
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        if (o - nd + i < nc) dst[o - nd + i] = v[i];
+    }
   }
 }
 
@@ -1104,7 +1112,15 @@ __global__ void head_unpack_kernel(const float* __restrict__ gd, const float* __
     const int64_t p = it / oct;
     const int64_t b = p / hw, a = a0 + p % hw;
     float v[8];
-    load8(o < nd ? gd + (b * N + a) * nd + o : gl + (b * N + a) * nc + (o - nd), v);
+    if (o < nd) {
+      load8(gd + (b * N + a) * nd + o, v);
+    } else if ((nc & 7) == 0) {
+      load8(gl + (b * N + a) * nc + (o - nd), v);
+    } else {  // padding class channels get a zero gradient
+      const float* src = gl + (b * N + a) * nc;
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = (o - nd + i < nc) ? src[o - nd + i] : 0.f;
+    }
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] *= scale;
     store8(reinterpret_cast<T*>(lv.ptr) + p * lv.ld + o, v);
@@ -1414,8 +1430,8 @@ int yad_patch_filter_bwd(const yad_tensor* x, const yad_tensor* dy, const float*
 
 int yad_head_pack(const yad_tensor* level, int anchor0, int n_anchors, int reg_ch, int nc, float* distri, float* logits, int dtype, void* stream) {
   CHECK_VIEW(level, "head_pack");
-  YAD_CHECK(level->c == reg_ch + nc && reg_ch % 8 == 0 && nc % 8 == 0, "head_pack: level has %d channels, expected %d + %d (multiples of 8)", level->c,
-            reg_ch, nc);
+  YAD_CHECK(nc >= 1 && level->c == reg_ch + (nc + 7) / 8 * 8 && reg_ch % 8 == 0, "head_pack: level has %d channels, expected %d + %d classes padded to a multiple of 8",
+            level->c, reg_ch, nc);
   const int64_t total = (int64_t)level->n * level->h * level->w * (level->c / 8);
   YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(head_pack_kernel<T>, grid_for(total), TPB, 0, (cudaStream_t)stream, *level, anchor0, n_anchors, reg_ch, nc, distri, logits);)
   YAD_LAUNCH_CHECK("head_pack");
@@ -1425,7 +1441,8 @@ int yad_head_pack(const yad_tensor* level, int anchor0, int n_anchors, int reg_c
 int yad_head_unpack(const float* grad_distri, const float* grad_logits, float scale, int anchor0, int n_anchors, int reg_ch, int nc,
                     const yad_tensor* level, int dtype, void* stream) {
   CHECK_VIEW(level, "head_unpack");
-  YAD_CHECK(level->c == reg_ch + nc && reg_ch % 8 == 0 && nc % 8 == 0, "head_unpack: level has %d channels, expected %d + %d", level->c, reg_ch, nc);
+  YAD_CHECK(nc >= 1 && level->c == reg_ch + (nc + 7) / 8 * 8 && reg_ch % 8 == 0, "head_unpack: level has %d channels, expected %d + %d classes padded to a multiple of 8",
+            level->c, reg_ch, nc);
   const int64_t total = (int64_t)level->n * level->h * level->w * (level->c / 8);
   YAD_DISPATCH_DTYPE(dtype, YAD_LAUNCH(head_unpack_kernel<T>, grid_for(total), TPB, 0, (cudaStream_t)stream, grad_distri, grad_logits, scale, anchor0, n_anchors,
                                                                                                       reg_ch, nc, *level);)

@@ -753,10 +753,11 @@ def ayhead_level(g, p, x, i):
 
     g.tape.append(bwd_gate)
     reg_ch, nc = g.tp.shape[p + ".cv2.weight"][0], g.tp.shape[p + ".cv3.weight"][0]
-    out = g.act(n, h, w, reg_ch + nc)
+    ncp = (nc + 7) // 8 * 8  # class counts that are not multiples of 8 (custom datasets): cv3's packed weight has pad8(nc) rows, the padding channels
+    out = g.act(n, h, w, reg_ch + ncp)  # stay zero, yad_head_pack / yad_head_unpack hand the loss the first nc (as functional.ayhead_level does)
     r = conv(g, reg_e, p + ".cv2.weight", p + ".cv2.bias")
     scale_add(g, r, f"{p}.scale.{i}.scale", out=out.slice(0, reg_ch))
-    conv(g, z, p + ".cv3.weight", p + ".cv3.bias", out=out.slice(reg_ch, nc))
+    conv(g, z, p + ".cv3.weight", p + ".cv3.bias", out=out.slice(reg_ch, ncp))
     return out
 
 
