@@ -75,6 +75,9 @@ int yad_version(void);
 /* Programmatic dependent launch (griddepcontrol) between consecutive kernels of a stream: OFF by default (environment YAD_PDL=1 or yad_set_pdl(1) turns it on);
  * returns the previous setting.  Takes effect for launches (and graph captures) made after the call. */
 int yad_set_pdl(int enabled);
+/* sizeof of the structs that cross this ABI: 0 yad_tensor, 1 yad_epilogue, 2 yad_conv_desc, 3 yad_image_desc, 4 yad_permute_entry (-1 otherwise).
+ * A binding checks its own struct declarations against the loaded library with it (tests/test_library.py does so for the ctypes mirror). */
+int yad_struct_size(int which);
 /* 1 when the running device is sm_100 (tcgen05 path usable) */
 int yad_device_is_sm100(void);
 

@@ -45,3 +45,17 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libyad.so")
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         _lib.load()
+
+
+def test_ctypes_structs_match_the_library():
+    """the ctypes mirrors of the structs that cross the C ABI have the sizes this build of libyad.so was compiled with (yad_struct_size): a field
+    added to include/yad.h but not to _lib.py (or the other way round) would otherwise shift every later field silently"""
+    import ctypes as C
+
+    from yolo_ad_refine_b200 import _lib
+    lib = _lib.load()
+    for which, cls in enumerate((_lib.YadTensor, _lib.YadEpilogue, _lib.YadConvDesc, _lib.YadImageDesc, _lib.YadPermuteEntry)):
+        assert lib.yad_struct_size(which) == C.sizeof(cls), (cls.__name__, lib.yad_struct_size(which), C.sizeof(cls))
+    assert lib.yad_struct_size(99) == -1
+    # field offsets of the epilogue (the struct extended most often): the gate fields sit behind gn_groups
+    assert _lib.YadEpilogue.gate_h.offset > _lib.YadEpilogue.gn_groups.offset and _lib.YadEpilogue.gate_wm.offset + 4 <= C.sizeof(_lib.YadEpilogue)

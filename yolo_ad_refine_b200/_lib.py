@@ -51,6 +51,7 @@ SIGNATURES = {
     "yad_version": (i32, []),
     "yad_set_pdl": (i32, [i32]),
     "yad_device_is_sm100": (i32, []),
+    "yad_struct_size": (i32, [i32]),
     "yad_conv2d": (i32, [TP, vp, C.POINTER(YadConvDesc), C.POINTER(YadEpilogue), TP, i32, vp]),
     "yad_dwconv": (i32, [TP, vp, vp, vp, vp, i32, i32, i32, vp, i32, TP, i32, vp]),
     "yad_gn_stats": (i32, [TP, i32, vp, i32, vp]),

@@ -39,6 +39,18 @@ int yad_set_pdl(int enabled) {
   return old;
 }
 
+// sizeof of the structs that cross the C ABI, so that a binding (ctypes, cgo, JNI ...) can check its own declarations against this build
+int yad_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(yad_tensor);
+    case 1: return (int)sizeof(yad_epilogue);
+    case 2: return (int)sizeof(yad_conv_desc);
+    case 3: return (int)sizeof(yad_image_desc);
+    case 4: return (int)sizeof(yad_permute_entry);
+    default: return -1;
+  }
+}
+
 int yad_device_is_sm100(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
