@@ -225,6 +225,38 @@ def gen_train_step():
     np.savez_compressed(os.path.join(GOLD, "train_step.npz"), **d)
 
 
+def gen_train_step_nc3():
+    """The training step of gen_train_step for a model built with nc = 3 (a custom dataset: DetectionModel(yaml, nc=3) resizes the head's cv3,
+    nn/tasks.py:319-326, nn/modules/head.py:1094-1097): pins oracle.model.train_step_grads for a class count that is not a multiple of 8, the case
+    the CUDA training head pads (tests/test_gpu_train_step.py::test_train_step_with_a_class_count_that_is_not_a_multiple_of_8).  The synthetic
+    state-dict spec is the committed one with cv3 resized; the committed spec file is not touched."""
+    from oracle.cases import TRAIN_STEP_CASES, train_step_inputs
+    nc = 3
+    m = DetectionModel(YAML, ch=3, nc=nc, verbose=False)
+    spec = [(k, list(v.shape), str(v.dtype)) for k, v in m.state_dict().items()]
+    want = [[k, ([nc] + list(sh[1:]) if k in ("model.33.cv3.weight", "model.33.cv3.bias") else list(sh)), dt] for k, sh, dt in synth.load_spec()]
+    assert [list(e) for e in spec] == want, "the nc = 3 model differs from the committed spec in more than cv3"
+    m.load_state_dict(synth.make_state_dict(seed=5, spec=spec), strict=True)
+    m.args = _Args()
+    m.train()
+    m.criterion = None
+    m.model[-1].shape = None
+    img, bi, cl, bb = train_step_inputs(**TRAIN_STEP_CASES["b2_160"])
+    cl = (cl % nc).astype(cl.dtype)
+    loss, items = m.loss(dict(img=torch.from_numpy(img), batch_idx=torch.from_numpy(bi), cls=torch.from_numpy(cl), bboxes=torch.from_numpy(bb)))
+    loss.backward()
+    d = {"loss": np.float64(loss.item()), "items": items.detach().numpy().astype(np.float64)}
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            d[f"{k}|none"] = np.int32(1)
+            continue
+        g = p.grad.detach().numpy().reshape(-1)
+        d[f"{k}|norm"] = np.float64(np.sqrt((g.astype(np.float64) ** 2).sum()))
+        d[f"{k}|samples"] = g[sample_positions(g.size, 16)]
+    print("train_step_nc3 loss", loss.item(), items.detach().numpy())
+    np.savez_compressed(os.path.join(GOLD, "train_step_nc3.npz"), **d)
+
+
 OPT_HYP = dict(lr=0.01, momentum=0.937, weight_decay=5e-4, steps=2)
 ADAMW_LR = 1e-3
 
@@ -544,6 +576,8 @@ def main():
         return gen_preprocess()
     if sys.argv[1:] == ["train_step"]:
         return gen_train_step()
+    if sys.argv[1:] == ["train_step_nc3"]:
+        return gen_train_step_nc3()
     if sys.argv[1:] == ["opt_step"]:
         return gen_opt_step()
     if sys.argv[1:] == ["opt_step_adamw"]:

@@ -71,6 +71,40 @@ def test_train_step_matches_reference(gold, state_dict, name):
     assert len(bn_upd) > 50
 
 
+def test_train_step_with_three_classes_matches_reference(gold):
+    """a custom-dataset class count (nc = 3, not a multiple of 8): oracle.model.train_step_grads against the live reference's
+    DetectionModel(yaml, nc=3).loss(batch).backward() (tests/golden/train_step_nc3.npz, oracle/gen_golden.py train_step_nc3): loss, loss items and
+    every parameter gradient.  The CUDA training head is compared with this oracle in tests/test_gpu_train_step.py."""
+    from oracle import model as om
+    from oracle import synth
+    g = gold("train_step_nc3.npz")
+    nc = 3
+    spec = [[k, ([nc] + list(sh[1:]) if k in ("model.33.cv3.weight", "model.33.cv3.bias") else sh), dt] for k, sh, dt in synth.load_spec()]
+    sd = synth.make_state_dict(seed=5, spec=spec)
+    img, bi, cl, bb = cases.train_step_inputs(**cases.TRAIN_STEP_CASES["b2_160"])
+    cl = (cl % nc).astype(cl.dtype)
+    loss, items, grads, _, feats = om.train_step_grads(sd, torch.from_numpy(img), torch.from_numpy(bi), torch.from_numpy(cl), torch.from_numpy(bb))
+    assert feats[0].shape[1] == 64 + nc
+    assert abs(loss.item() - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    np.testing.assert_allclose(items.numpy(), g["items"], rtol=1e-4)
+    checked = 0
+    for k, gr in grads.items():
+        if f"{k}|none" in g.files:
+            assert gr is None or float(gr.abs().max()) == 0.0, k
+            continue
+        ref_norm = float(g[f"{k}|norm"])
+        v = gr.numpy().reshape(-1)
+        if k.endswith((".conv.bias", ".conv1.bias")) and ref_norm < 1e-3:
+            continue  # a bias in front of a batch-statistics BatchNorm: the exact gradient is 0, both sides hold rounding noise
+        norm = float(np.sqrt((v.astype(np.float64) ** 2).sum()))
+        assert abs(norm - ref_norm) <= 1e-2 * ref_norm + 1e-6, (k, norm, ref_norm)
+        ref = g[f"{k}|samples"]
+        np.testing.assert_allclose(v[cases.sample_positions(v.size, 16)], ref, rtol=2e-2, atol=1e-2 * ref_norm / np.sqrt(v.size) + 1e-7, err_msg=k)
+        checked += 1
+    assert checked > 300
+    assert tuple(grads["model.33.cv3.weight"].shape) == (nc, 64, 1, 1)
+
+
 def test_optimizer_step_matches_reference(gold, state_dict):
     """oracle/optim.py (clip + SGD nesterov + EMA) driven by oracle.model.train_step_grads for two steps, against the live reference's two
     steps (tests/golden/opt_step.npz): sampled parameter / EMA deltas."""
